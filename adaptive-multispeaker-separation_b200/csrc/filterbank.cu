@@ -1,0 +1,385 @@
+// Adaptive front/back end: the learnable sparse 1-D conv filterbank of models/adapt.py.
+//
+//   analysis  (adapt.py:115-117): tf.nn.conv2d(SAME, stride 1) + max_pool_with_argmax(VALID),
+//             fused -- the [Bt, L, N] tensor (65.5 MB per 4 s signal) never reaches HBM.
+//   synthesis (utils/ops.py:94-120 unpool + adapt.py:241-243 conv2d_transpose), fused as a
+//             sparse overlap-add gather: 99.6 % of the unpooled tensor is zeros.
+//   backward  w.r.t. the filters, sparse through the arg-max.
+//
+// This file holds the fp32 SIMT path (AMSS_PREC_FP32, the parity path).  The tcgen05 Toeplitz
+// implicit-GEMM analysis kernel lives in filterbank_tc.cu.
+#include "common.cuh"
+#include <algorithm>
+
+namespace amss {
+int filterbank_analysis_tc(const float* x, const float* filt, int Bt, int L, int W, int N, int pool, int hop,
+                           int precision, float* y, int64_t* argmax, void* workspace, size_t workspace_bytes,
+                           cudaStream_t st);
+size_t filterbank_analysis_tc_workspace(int Bt, int L, int W, int N, int pool, int hop, int precision);
+bool filterbank_analysis_tc_supported(int L, int W, int N, int pool, int hop, int mode);
+
+namespace {
+
+constexpr int FA_TT = 256;   // time positions per sub-tile
+constexpr int FA_NT = 64;    // filters per CTA
+constexpr int FA_KC = 32;    // taps per shared-memory chunk
+constexpr int FA_THREADS = 256;
+
+__host__ __device__ inline void same_pad(int L, int W, int stride, int* out, int* pl) {
+    const int o = (L + stride - 1) / stride;
+    int pad = (o - 1) * stride + W - L;
+    if (pad < 0) pad = 0;
+    *out = o;
+    *pl = pad / 2;
+}
+
+// MODE 0: max + argmax over [tp*hop, tp*hop+pool) ; MODE 1: mean over [tp*pool, (tp+1)*pool)
+// grid (Tp, N/64, Bt).  Thread (tg = tid/8, fg = tid%8) owns times tg*8..+8 and filters fg*8..+8
+// of the current 256-sample sub-tile; x slides through registers, filters come as float4.
+template <int MODE>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+analysis_pool_kernel(const float* __restrict__ x, const float* __restrict__ filt, int L, int W, int N, int pool,
+                     int hop, int Tp, float* __restrict__ y, int64_t* __restrict__ argmax) {
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    const int Wp = (W + FA_KC - 1) / FA_KC * FA_KC;
+    float* xs = reinterpret_cast<float*>(fb_smem);            // [FA_TT + Wp + 16]
+    float* fs = xs + (FA_TT + Wp + 16);                        // [FA_KC][FA_NT]
+    float* redv = fs + FA_KC * FA_NT;                         // [32][FA_NT]
+    int* redt = reinterpret_cast<int*>(redv + 32 * FA_NT);    // [32][FA_NT]
+    const int tp = blockIdx.x, n0 = blockIdx.y * FA_NT, r = blockIdx.z;
+    const int tid = threadIdx.x, tg = tid >> 3, fg = tid & 7;
+    const int pl = (W - 1) / 2;   // SAME padding, stride 1
+    const int win0 = (MODE == 0) ? tp * hop : tp * pool;
+
+    float best[8];
+    int bestt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = (MODE == 0) ? -INFINITY : 0.f; bestt[j] = 0; }
+
+    for (int sub = 0; sub < pool; sub += FA_TT) {
+        const int t0 = win0 + sub;                       // first time position of this sub-tile
+        __syncthreads();
+        for (int i = tid; i < FA_TT + Wp + 16; i += FA_THREADS) {
+            const int s = t0 + i - pl;
+            xs[i] = (s >= 0 && s < L && i < FA_TT + W) ? x[(size_t)r * L + s] : 0.f;
+        }
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+        for (int k0 = 0; k0 < W; k0 += FA_KC) {
+            __syncthreads();
+            for (int i = tid; i < FA_KC * FA_NT; i += FA_THREADS) {
+                const int kk = i / FA_NT, nn = i - kk * FA_NT;
+                fs[i] = (k0 + kk < W && n0 + nn < N) ? filt[(size_t)(k0 + kk) * N + n0 + nn] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k8 = 0; k8 < FA_KC; k8 += 8) {
+                float xw[16];
+                const float4* xp = reinterpret_cast<const float4*>(xs + tg * 8 + k0 + k8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = xp[q];
+                    xw[q * 4 + 0] = v.x; xw[q * 4 + 1] = v.y; xw[q * 4 + 2] = v.z; xw[q * 4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const float4 f0 = *reinterpret_cast<const float4*>(fs + (k8 + kk) * FA_NT + fg * 8);
+                    const float4 f1 = *reinterpret_cast<const float4*>(fs + (k8 + kk) * FA_NT + fg * 8 + 4);
+                    const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xw[kk + i], fv[j], acc[i][j]);
+                }
+            }
+        }
+        // fold this sub-tile into the running window statistic (ascending time, first max wins)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int tl = sub + tg * 8 + i;   // offset inside the pooling window
+            if (tl < pool) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (MODE == 0) { if (acc[i][j] > best[j]) { best[j] = acc[i][j]; bestt[j] = win0 + tl; } }
+                    else best[j] += acc[i][j];
+                }
+            }
+        }
+    }
+    // cross-thread reduction over the 32 time groups, ascending
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { redv[tg * FA_NT + fg * 8 + j] = best[j]; redt[tg * FA_NT + fg * 8 + j] = bestt[j]; }
+    __syncthreads();
+    if (tid < FA_NT && n0 + tid < N) {
+        float b = redv[tid];
+        int bt = redt[tid];
+        for (int g = 1; g < 32; ++g) {
+            const float v = redv[g * FA_NT + tid];
+            if (MODE == 0) { if (v > b) { b = v; bt = redt[g * FA_NT + tid]; } }
+            else b += v;
+        }
+        const size_t o = ((size_t)r * Tp + tp) * N + n0 + tid;
+        if (MODE == 0) { y[o] = b; if (argmax) argmax[o] = (int64_t)bt * N + n0 + tid; }
+        else y[o] = b / (float)pool;
+    }
+}
+
+// strided conv, SAME padding (adapt.py:121-122): y[r,tp,n] = sum_k x[tp*hop + k - pl] filt[k,n]
+__global__ void analysis_stride_kernel(const float* __restrict__ x, const float* __restrict__ filt, int L, int W,
+                                       int N, int hop, int Tp, int pl, float* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    float* xs = reinterpret_cast<float*>(fb_smem);   // [W]
+    const int tp = blockIdx.x, r = blockIdx.y;
+    for (int k = threadIdx.x; k < W; k += blockDim.x) {
+        const int s = tp * hop + k - pl;
+        xs[k] = (s >= 0 && s < L) ? x[(size_t)r * L + s] : 0.f;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float a = 0.f;
+        for (int k = 0; k < W; ++k) a = fmaf(xs[k], filt[(size_t)k * N + n], a);
+        y[((size_t)r * Tp + tp) * N + n] = a;
+    }
+}
+
+__global__ void transpose_filter_kernel(const float* __restrict__ f, int W, int N, float* __restrict__ fT) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int k = k0 + i, n = n0 + threadIdx.x;
+        tile[i][threadIdx.x] = (k < W && n < N) ? f[(size_t)k * N + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int n = n0 + i, k = k0 + threadIdx.x;
+        if (n < N && k < W) fT[(size_t)n * W + k] = tile[threadIdx.x][i];
+    }
+}
+
+// Sparse overlap-add gather.  grid (ceil(L/256), R).  Thread u accumulates, in a fixed atom order
+// (frame ascending, filter ascending), every atom whose filter support covers sample u.
+__global__ void __launch_bounds__(256)
+synthesis_fwd_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax,
+                     const float* __restrict__ filtT, int S, int L, int W, int N, int Tp, int hop_lo, int pool_hi,
+                     float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    float* sv = reinterpret_cast<float*>(fb_smem);    // [N]
+    int* sp = reinterpret_cast<int*>(sv + N);         // [N]
+    const int r = blockIdx.y, b = r / S, u0 = blockIdx.x * 256, u = u0 + threadIdx.x;
+    const int pl = (W - 1) / 2;
+    // atoms of frame tp sit at pos in [tp*hop_lo, tp*hop_lo + pool_hi); k = u - pos + pl in [0, W)
+    const int pos_min = u0 - (W - 1 - pl), pos_max = u0 + 255 + pl;
+    int tp_lo = (pos_min - pool_hi + 1);
+    tp_lo = tp_lo <= 0 ? 0 : (tp_lo + hop_lo - 1) / hop_lo;
+    int tp_hi = pos_max / hop_lo;
+    if (tp_hi > Tp - 1) tp_hi = Tp - 1;
+    float acc = 0.f;
+    for (int tp = tp_lo; tp <= tp_hi; ++tp) {
+        __syncthreads();
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            sv[n] = vals[((size_t)r * Tp + tp) * N + n];
+            sp[n] = (int)(argmax[((size_t)b * Tp + tp) * N + n] / N);
+        }
+        __syncthreads();
+        for (int n = 0; n < N; ++n) {
+            const int k = u - sp[n] + pl;
+            if (k >= 0 && k < W) acc = fmaf(sv[n], __ldg(filtT + (size_t)n * W + k), acc);
+        }
+    }
+    if (u < L) out[(size_t)r * L + u] = acc;
+}
+
+// dvals[r,tp,n] = sum_k dout[r, pos + k - pl] * filt2[k,n] : one warp per atom, lanes over taps.
+__global__ void __launch_bounds__(256)
+synthesis_bwd_vals_kernel(const float* __restrict__ dout, const int64_t* __restrict__ argmax,
+                          const float* __restrict__ filtT, int S, int L, int W, int N, int Tp,
+                          float* __restrict__ dvals) {
+    const int tp = blockIdx.x, r = blockIdx.y, b = r / S;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int pl = (W - 1) / 2;
+    for (int n = w; n < N; n += nw) {
+        const int pos = (int)(argmax[((size_t)b * Tp + tp) * N + n] / N);
+        float a = 0.f;
+        for (int k = lane; k < W; k += 32) {
+            const int s = pos + k - pl;
+            if (s >= 0 && s < L) a = fmaf(dout[(size_t)r * L + s], filtT[(size_t)n * W + k], a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) dvals[((size_t)r * Tp + tp) * N + n] = a;
+    }
+}
+
+// dfilt[k,n] = sum_{r,tp} vals[r,tp,n] * sig[r, pos(r,tp,n) + k - pl].  grid (N, chunks): a CTA
+// walks its slice of the (r,tp) atom list in order; partials [chunks][N][W] are summed in order.
+// argdiv: rows of argmax = r / argdiv (S for the synthesis: the mixture's argmax; 1 for analysis).
+__global__ void __launch_bounds__(256)
+sparse_filter_grad_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax,
+                          const float* __restrict__ sig, int R, int argdiv, int L, int W, int N, int Tp,
+                          float* __restrict__ part) {
+    const int n = blockIdx.x, chunk = blockIdx.y, chunks = gridDim.y;
+    const int pl = (W - 1) / 2;
+    const int64_t natoms = (int64_t)R * Tp;
+    const int64_t a0 = natoms * chunk / chunks, a1 = natoms * (chunk + 1) / chunks;
+    for (int kb = 0; kb < W; kb += 256 * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int64_t a = a0; a < a1; ++a) {
+            const int r = (int)(a / Tp), tp = (int)(a - (int64_t)r * Tp);
+            const float v = vals[((size_t)r * Tp + tp) * N + n];
+            const int pos = (int)(argmax[((size_t)(r / argdiv) * Tp + tp) * N + n] / N);
+            if (v != 0.f) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = kb + q * 256 + threadIdx.x;
+                    const int s = pos + k - pl;
+                    if (k < W && s >= 0 && s < L) acc[q] = fmaf(v, sig[(size_t)r * L + s], acc[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = kb + q * 256 + threadIdx.x;
+            if (k < W) part[((size_t)chunk * N + n) * W + k] = acc[q];
+        }
+    }
+}
+// dfilt[k][n] (+)= sum_chunks part[chunk][n][k]
+__global__ void filter_grad_final_kernel(const float* __restrict__ part, int chunks, int W, int N, int accumulate,
+                                         float* __restrict__ dfilt) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int n = n0 + i, k = k0 + threadIdx.x;
+        float a = 0.f;
+        if (n < N && k < W)
+            for (int c = 0; c < chunks; ++c) a += part[((size_t)c * N + n) * W + k];
+        tile[i][threadIdx.x] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int k = k0 + i, n = n0 + threadIdx.x;
+        if (k < W && n < N) {
+            const float v = tile[threadIdx.x][i];
+            dfilt[(size_t)k * N + n] = accumulate ? dfilt[(size_t)k * N + n] + v : v;
+        }
+    }
+}
+
+constexpr int FG_CHUNKS = 8;
+
+}  // namespace
+}  // namespace amss
+
+using namespace amss;
+
+extern "C" int amss_filterbank_analysis_out_frames(int L, int W, int pool, int hop, int mode) {
+    if (mode == AMSS_POOL_MAX) return L >= pool ? (L - pool) / hop + 1 : 0;
+    if (mode == AMSS_POOL_AVG) return L / pool;
+    int out, pl;
+    same_pad(L, W, hop, &out, &pl);
+    return out;
+}
+
+extern "C" size_t amss_filterbank_analysis_workspace_bytes(int Bt, int L, int W, int N, int pool, int hop, int mode,
+                                                           int precision) {
+    if (filterbank_analysis_tc_supported(L, W, N, pool, hop, mode) && precision != AMSS_PREC_FP32)
+        return filterbank_analysis_tc_workspace(Bt, L, W, N, pool, hop, precision);
+    return 256;
+}
+
+extern "C" int amss_filterbank_analysis_fwd(const float* x, const float* filt, int Bt, int L, int W, int N, int pool,
+                                            int hop, int mode, int precision, float* y, int64_t* argmax,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+    AMSS_REQUIRE(x && filt && y, "filterbank_analysis_fwd: null pointer");
+    AMSS_REQUIRE(Bt > 0 && L > 0 && W > 0 && N > 0 && hop > 0, "filterbank_analysis_fwd: bad sizes");
+    AMSS_REQUIRE(mode >= 0 && mode <= 2, "filterbank_analysis_fwd: bad mode %d", mode);
+    const int Tp = amss_filterbank_analysis_out_frames(L, W, pool, hop, mode);
+    AMSS_REQUIRE(Tp > 0, "filterbank_analysis_fwd: no output frames (L=%d pool=%d)", L, pool);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == AMSS_POOL_STRIDE) {
+        int out, pl;
+        same_pad(L, W, hop, &out, &pl);
+        dim3 grid(Tp, Bt);
+        AMSS_LAUNCH(analysis_stride_kernel, grid, 256, (size_t)W * 4, st, x, filt, L, W, N, hop, Tp, pl, y);
+        return AMSS_OK;
+    }
+    AMSS_REQUIRE(pool > 0, "filterbank_analysis_fwd: pool must be positive");
+    if (mode == AMSS_POOL_MAX && precision != AMSS_PREC_FP32 &&
+        filterbank_analysis_tc_supported(L, W, N, pool, hop, mode))
+        return filterbank_analysis_tc(x, filt, Bt, L, W, N, pool, hop, precision, y, argmax, workspace,
+                                      workspace_bytes, st);
+    const int Wp = (W + FA_KC - 1) / FA_KC * FA_KC;
+    const size_t smem = ((size_t)(FA_TT + Wp + 16) + FA_KC * FA_NT + 32 * FA_NT * 2) * 4;
+    dim3 grid(Tp, (N + FA_NT - 1) / FA_NT, Bt);
+    if (mode == AMSS_POOL_MAX) {
+        AMSS_CUDA(cudaFuncSetAttribute(analysis_pool_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(analysis_pool_kernel<0>, grid, FA_THREADS, smem, st, x, filt, L, W, N, pool, hop, Tp, y, argmax);
+    } else {
+        AMSS_CUDA(cudaFuncSetAttribute(analysis_pool_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(analysis_pool_kernel<1>, grid, FA_THREADS, smem, st, x, filt, L, W, N, pool, hop, Tp, y, argmax);
+    }
+    return AMSS_OK;
+}
+
+extern "C" size_t amss_filterbank_grad_workspace_bytes(int W, int N) {
+    return align_up((size_t)W * N * 4, 256) + (size_t)FG_CHUNKS * N * W * 4;
+}
+
+extern "C" int amss_filterbank_analysis_bwd(const float* x, const float* dy, const int64_t* argmax, int Bt, int L,
+                                            int W, int N, int Tp, int accumulate, float* dfilt, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+    AMSS_REQUIRE(x && dy && argmax && dfilt && workspace, "filterbank_analysis_bwd: null pointer");
+    if (workspace_bytes < amss_filterbank_grad_workspace_bytes(W, N)) { set_error("filterbank_analysis_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
+    float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
+    dim3 grid(N, FG_CHUNKS);
+    AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
+    dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);
+    AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, FG_CHUNKS, W, N, accumulate, dfilt);
+    return AMSS_OK;
+}
+
+extern "C" size_t amss_filterbank_synthesis_workspace_bytes(int B, int S, int L, int W, int N, int Tp) {
+    (void)B; (void)S; (void)L; (void)Tp;
+    return amss_filterbank_grad_workspace_bytes(W, N);
+}
+
+extern "C" int amss_filterbank_synthesis_fwd(const float* vals, const int64_t* argmax, const float* filt2, int B,
+                                             int S, int L, int W, int N, int Tp, int pool, int hop, float* out,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+    AMSS_REQUIRE(vals && argmax && filt2 && out && workspace, "filterbank_synthesis_fwd: null pointer");
+    AMSS_REQUIRE(B > 0 && S > 0 && pool > 0 && hop > 0, "filterbank_synthesis_fwd: bad sizes");
+    if (workspace_bytes < (size_t)W * N * 4) { set_error("filterbank_synthesis_fwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
+    float* fT = (float*)workspace;
+    dim3 gt((W + 31) / 32, (N + 31) / 32), bt(32, 8);
+    AMSS_LAUNCH(transpose_filter_kernel, gt, bt, 0, stream, filt2, W, N, fT);
+    dim3 grid((L + 255) / 256, B * S);
+    AMSS_LAUNCH(synthesis_fwd_kernel, grid, 256, (size_t)N * 8, stream, vals, argmax, fT, S, L, W, N, Tp, hop, pool,
+                out);
+    return AMSS_OK;
+}
+
+extern "C" int amss_filterbank_synthesis_bwd(const float* dout, const float* vals, const int64_t* argmax,
+                                             const float* filt2, int B, int S, int L, int W, int N, int Tp,
+                                             float* dvals, float* dfilt2, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+    AMSS_REQUIRE(dout && vals && argmax && filt2 && workspace, "filterbank_synthesis_bwd: null pointer");
+    if (workspace_bytes < amss_filterbank_grad_workspace_bytes(W, N)) { set_error("filterbank_synthesis_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
+    float* fT = (float*)workspace;
+    float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
+    if (dvals) {
+        dim3 gt((W + 31) / 32, (N + 31) / 32), bt(32, 8);
+        AMSS_LAUNCH(transpose_filter_kernel, gt, bt, 0, stream, filt2, W, N, fT);
+        dim3 grid(Tp, B * S);
+        AMSS_LAUNCH(synthesis_bwd_vals_kernel, grid, 256, 0, stream, dout, argmax, fT, S, L, W, N, Tp, dvals);
+    }
+    if (dfilt2) {
+        dim3 grid(N, FG_CHUNKS);
+        AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
+        dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);
+        AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, FG_CHUNKS, W, N, 0, dfilt2);
+    }
+    return AMSS_OK;
+}

@@ -1,0 +1,466 @@
+// In-graph multi-try hard/soft k-means (reference: models/Kmeans_2.py:14-188) and the mask
+// application of Separator.separate (models/network.py:554-582).
+//
+// Design: the reference tiles X `tries` times and materialises [B*tries, L, K, E] broadcast
+// temporaries per iteration.  Here X[B,L,E] is read ONCE per iteration: a CTA stages a tile of
+// points in shared memory, every point is labelled against all tries' centroids (phase 1), and
+// the per-(try, cluster) sums are accumulated by one owner thread per (try, feature) in a fixed
+// order (phase 2), so the result is deterministic (no floating-point atomics anywhere).
+// Per-CTA partials are reduced in a fixed order by a small finalize kernel.
+#include "common.cuh"
+#include <algorithm>
+
+namespace amss {
+namespace {
+
+constexpr int KM_TILE = 256;     // points per tile
+constexpr int KM_THREADS = 256;
+constexpr int KM_MAXK = 8;
+constexpr int KM_MAXG = 8;
+
+enum { KM_UPDATE = 0, KM_INERTIA = 1 };
+
+struct KmSmemLayout {
+    size_t xs, cs, lab, w, wv, ssum, total;
+    int G, NF;
+};
+
+__host__ __device__ inline KmSmemLayout km_layout(int E, int K, int tries, int mode, int soft) {
+    KmSmemLayout s;
+    const int EE = (mode == KM_UPDATE) ? E : 1;
+    s.NF = EE + 1;  // + the count feature
+    int G = KM_THREADS / (tries * s.NF);
+    if (G < 1) G = 1;
+    if (G > KM_MAXG) G = KM_MAXG;
+    s.G = G;
+    size_t off = 0;
+    s.xs = off;  off += (size_t)KM_TILE * (E + 1) * 4;
+    s.cs = off;  off += (size_t)((tries * K * E + 3) / 4 * 4) * 4;
+    s.lab = off; off += (size_t)((tries * KM_TILE + 15) / 16 * 16);            // u8 labels (hard)
+    s.w = off;   off += soft ? (size_t)tries * KM_TILE * K * 4 : 0;             // soft weights
+    s.wv = off;  off += (mode == KM_INERTIA) ? (size_t)tries * KM_TILE * (soft ? K : 1) * 4 : 0;
+    s.ssum = off; off += (size_t)G * tries * K * s.NF * 4;
+    s.total = off;
+    return s;
+}
+
+// One pass over X for all tries.  grid = (chunks, B).  cent[R,K,E], R = B*tries (row r=b*tries+t).
+// part[b][chunk][t][k][f], f in [0,NF): f<EE feature sums, f==EE the count / weight sum.
+template <int MODE, int SOFT>
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_pass_kernel(const float* __restrict__ X, const float* __restrict__ cent,
+                   const uint8_t* __restrict__ notsilent, int B, int64_t L, int E, int K, int tries,
+                   float beta, float* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char km_smem[];
+    const KmSmemLayout lay = km_layout(E, K, tries, MODE, SOFT);
+    float* xs = reinterpret_cast<float*>(km_smem + lay.xs);
+    float* cs = reinterpret_cast<float*>(km_smem + lay.cs);
+    uint8_t* lab = km_smem + lay.lab;
+    float* wsm = reinterpret_cast<float*>(km_smem + lay.w);
+    float* wv = reinterpret_cast<float*>(km_smem + lay.wv);
+    float* ssum = reinterpret_cast<float*>(km_smem + lay.ssum);
+    const int G = lay.G, NF = lay.NF, EE = NF - 1;
+    const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int tid = threadIdx.x;
+    const int EP = E + 1;
+
+    for (int i = tid; i < tries * K * E; i += KM_THREADS) cs[i] = cent[(size_t)b * tries * K * E + i];
+    for (int i = tid; i < G * tries * K * NF; i += KM_THREADS) ssum[i] = 0.f;
+    __syncthreads();
+
+    const int64_t ntiles = (L + KM_TILE - 1) / KM_TILE;
+    for (int64_t tile = chunk; tile < ntiles; tile += chunks) {
+        const int64_t p0 = tile * KM_TILE;
+        const int np = (int)((L - p0) < KM_TILE ? (L - p0) : KM_TILE);
+        // stage the tile: coalesced read of np*E contiguous floats
+        const float* src = X + ((size_t)b * L + p0) * E;
+        for (int i = tid; i < np * E; i += KM_THREADS) {
+            const int p = i / E, e = i - p * E;
+            xs[p * EP + e] = src[i];
+        }
+        __syncthreads();
+        // ---- phase 1: one thread per point, all tries -------------------------------------
+        if (tid < np) {
+            const float* xp = xs + tid * EP;
+            for (int t = 0; t < tries; ++t) {
+                // the reference tiles notsilent try-major while X is batch-major
+                // (Kmeans_2.py:80 vs :48-52): row r of [B*tries] uses mask row r % B.
+                const int r = b * tries + t;
+                float ns = 1.f;
+                if (notsilent) ns = notsilent[(size_t)(r % B) * L + p0 + tid] ? 1.f : 0.f;
+                float d2u[KM_MAXK];
+#pragma unroll
+                for (int k = 0; k < KM_MAXK; ++k) {
+                    if (k < K) {
+                        const float* c = cs + (t * K + k) * E;
+                        float a = 0.f;
+                        for (int e = 0; e < E; ++e) { const float d = xp[e] - c[e]; a = fmaf(d, d, a); }
+                        d2u[k] = a;
+                    }
+                }
+                if (SOFT) {
+                    float ev[KM_MAXK], tot = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KM_MAXK; ++k)
+                        if (k < K) { ev[k] = expf(-1.f * beta * (d2u[k] * ns)); tot += ev[k]; }
+#pragma unroll
+                    for (int k = 0; k < KM_MAXK; ++k)
+                        if (k < K) {
+                            const float w = ev[k] / tot;
+                            wsm[(t * KM_TILE + tid) * K + k] = w;
+                            if (MODE == KM_INERTIA) wv[(t * KM_TILE + tid) * K + k] = d2u[k] * w;
+                        }
+                } else {
+                    int best = 0;
+                    float bd = sqrtf(d2u[0] * ns);
+#pragma unroll
+                    for (int k = 1; k < KM_MAXK; ++k)
+                        if (k < K) { const float d = sqrtf(d2u[k] * ns); if (d < bd) { bd = d; best = k; } }
+                    lab[t * KM_TILE + tid] = (uint8_t)best;
+                    if (MODE == KM_INERTIA) {
+                        float sel = d2u[0];
+#pragma unroll
+                        for (int k = 1; k < KM_MAXK; ++k) if (k < K && k == best) sel = d2u[k];
+                        wv[t * KM_TILE + tid] = sel;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: owner thread per (group, try, feature), fixed point order -------------
+        const int nitems = G * tries * NF;
+        for (int item = tid; item < nitems; item += KM_THREADS) {
+            const int f = item % NF;
+            const int t = (item / NF) % tries;
+            const int g = item / (NF * tries);
+            const int r = b * tries + t;
+            const uint8_t* nsrow = notsilent ? notsilent + (size_t)(r % B) * L + p0 : nullptr;
+            float acc[KM_MAXK];
+#pragma unroll
+            for (int k = 0; k < KM_MAXK; ++k) acc[k] = 0.f;
+            for (int p = g; p < np; p += G) {
+                float val;
+                if (f == EE) val = 1.f;                       // count / weight-sum feature
+                else if (MODE == KM_UPDATE) {
+                    val = xs[p * EP + f];
+                    if (nsrow && !nsrow[p]) val = 0.f;        // X * notsilent (Kmeans_2.py:148)
+                } else val = 0.f;                             // inertia: value depends on k (below)
+                if (SOFT) {
+                    const float* wp = wsm + (t * KM_TILE + p) * K;
+                    const float* wvp = wv + (t * KM_TILE + p) * K;
+#pragma unroll
+                    for (int k = 0; k < KM_MAXK; ++k)
+                        if (k < K) {
+                            if (MODE == KM_INERTIA && f == 0) acc[k] += wvp[k];
+                            else acc[k] = fmaf(wp[k], val, acc[k]);
+                        }
+                } else {
+                    const int l = lab[t * KM_TILE + p];
+                    if (MODE == KM_INERTIA && f == 0) val = wv[t * KM_TILE + p];
+#pragma unroll
+                    for (int k = 0; k < KM_MAXK; ++k)
+                        if (k < K) acc[k] += (l == k) ? val : 0.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KM_MAXK; ++k)
+                if (k < K) ssum[((g * tries + t) * K + k) * NF + f] += acc[k];
+        }
+        __syncthreads();
+    }
+    // combine groups in fixed order, write this CTA's partial
+    float* dst = part + ((size_t)b * chunks + chunk) * tries * K * NF;
+    for (int i = tid; i < tries * K * NF; i += KM_THREADS) {
+        float a = 0.f;
+        for (int g = 0; g < G; ++g) a += ssum[(size_t)g * tries * K * NF + i];
+        dst[i] = a;
+    }
+}
+
+// cent[r][k][e] = sum_chunks part_sum / sum_chunks part_cnt   (Kmeans_2.py:158-165 / :151-155)
+__global__ void kmeans_finalize_kernel(const float* __restrict__ part, int B, int chunks, int tries, int K,
+                                       int E, float* __restrict__ cent) {
+    const int NF = E + 1;
+    const int64_t n = (int64_t)B * tries * K * E;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % E);
+        const int64_t rk = i / E;               // (b*tries+t)*K+k
+        const int b = (int)(rk / ((int64_t)tries * K));
+        const int tk = (int)(rk % ((int64_t)tries * K));
+        float s = 0.f, c = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const float* p = part + (((size_t)b * chunks + ch) * tries * K + tk) * NF;
+            s += p[e];
+            c += p[E];
+        }
+        cent[i] = s / c;   // empty cluster -> 0/0 = NaN, as in the reference
+    }
+}
+
+// inertia[b][t] = sum_k tot_k / cnt_k ; best = argmin_t (first minimum; a NaN inertia -- empty
+// cluster -- is never selected, as with tf.argmin's `<` reducer) ; centroids_out[b] = cent[b*tries+best]   (Kmeans_2.py:99-104)
+__global__ void kmeans_select_kernel(const float* __restrict__ part, const float* __restrict__ cent, int B,
+                                     int chunks, int tries, int K, int E, float* __restrict__ inertia_out,
+                                     int* __restrict__ best_out, float* __restrict__ cent_out) {
+    const int b = blockIdx.x;
+    __shared__ int sbest;
+    if (threadIdx.x == 0) {
+        int best = 0;
+        float bv = 0.f;
+        for (int t = 0; t < tries; ++t) {
+            float in = 0.f;
+            for (int k = 0; k < K; ++k) {
+                float s = 0.f, c = 0.f;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    const float* p = part + (((size_t)b * chunks + ch) * tries * K + t * K + k) * 2;
+                    s += p[0];
+                    c += p[1];
+                }
+                in += s / c;
+            }
+            if (inertia_out) inertia_out[b * tries + t] = in;
+            if (t == 0) { bv = isnan(in) ? INFINITY : in; best = 0; }
+            else if (in < bv) { bv = in; best = t; }   // NaN never wins, first minimum wins ties
+        }
+        sbest = best;
+        best_out[b] = best;
+    }
+    __syncthreads();
+    const int best = sbest;
+    for (int i = threadIdx.x; i < K * E; i += blockDim.x)
+        cent_out[(size_t)b * K * E + i] = cent[((size_t)b * tries + best) * K * E + i];
+}
+
+// centroids0[r][k] = X[b][init_idx[r][k]]   (Kmeans_2.py:66-71)
+__global__ void kmeans_gather_init_kernel(const float* __restrict__ X, const int* __restrict__ idx, int B,
+                                          int64_t L, int E, int K, int tries, float* __restrict__ cent) {
+    const int64_t n = (int64_t)B * tries * K * E;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % E);
+        const int64_t rk = i / E;
+        const int b = (int)(rk / ((int64_t)tries * K));
+        const int64_t row = idx[rk];
+        cent[i] = X[((size_t)b * L + row) * E + e];
+    }
+}
+
+// x * rsqrt(max(sum x^2, 1e-12)) per row of E   (Kmeans_2.py:40-41)
+__global__ void rows_l2norm_kernel(const float* __restrict__ X, int64_t rows, int E, float* __restrict__ Y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float* x = X + r * E;
+        float ss = 0.f;
+        for (int e = lane; e < E; e += 32) ss = fmaf(x[e], x[e], ss);
+        ss = warp_sum(ss);
+        const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+        for (int e = lane; e < E; e += 32) Y[r * E + e] = x[e] * inv;
+    }
+}
+
+// Final assignment against one centroid set per batch row   (Kmeans_2.py:106-107, 169-188)
+template <int SOFT>
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_assign_kernel(const float* __restrict__ X, const float* __restrict__ cent, const uint8_t* __restrict__ notsilent,
+                     const int* __restrict__ best, int B, int64_t L, int E, int K, int tries, float beta,
+                     int* __restrict__ labels, float* __restrict__ soft) {
+    extern __shared__ __align__(16) unsigned char km_smem[];
+    float* xs = reinterpret_cast<float*>(km_smem);
+    float* cs = xs + KM_TILE * (E + 1);
+    const int b = blockIdx.y, tid = threadIdx.x, EP = E + 1;
+    for (int i = tid; i < K * E; i += KM_THREADS) cs[i] = cent[(size_t)b * K * E + i];
+    const uint8_t* nsrow = nullptr;
+    if (notsilent) nsrow = notsilent + (size_t)((b * tries + best[b]) % B) * L;
+    const int64_t ntiles = (L + KM_TILE - 1) / KM_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p0 = tile * KM_TILE;
+        const int np = (int)((L - p0) < KM_TILE ? (L - p0) : KM_TILE);
+        const float* src = X + ((size_t)b * L + p0) * E;
+        __syncthreads();
+        for (int i = tid; i < np * E; i += KM_THREADS) {
+            const int p = i / E, e = i - p * E;
+            xs[p * EP + e] = src[i];
+        }
+        __syncthreads();
+        if (tid < np) {
+            const float* xp = xs + tid * EP;
+            const float ns = nsrow ? (nsrow[p0 + tid] ? 1.f : 0.f) : 1.f;
+            float d2[KM_MAXK];
+#pragma unroll
+            for (int k = 0; k < KM_MAXK; ++k)
+                if (k < K) {
+                    const float* c = cs + k * E;
+                    float a = 0.f;
+                    for (int e = 0; e < E; ++e) { const float d = xp[e] - c[e]; a = fmaf(d, d, a); }
+                    d2[k] = a * ns;
+                }
+            if (SOFT) {
+                float ev[KM_MAXK], tot = 0.f;
+#pragma unroll
+                for (int k = 0; k < KM_MAXK; ++k) if (k < K) { ev[k] = expf(-1.f * beta * d2[k]); tot += ev[k]; }
+#pragma unroll
+                for (int k = 0; k < KM_MAXK; ++k) if (k < K) soft[((size_t)b * L + p0 + tid) * K + k] = ev[k] / tot;
+            } else {
+                int bi = 0;
+                float bd = sqrtf(d2[0]);
+#pragma unroll
+                for (int k = 1; k < KM_MAXK; ++k)
+                    if (k < K) { const float d = sqrtf(d2[k]); if (d < bd) { bd = d; bi = k; } }
+                labels[(size_t)b * L + p0 + tid] = bi;
+            }
+        }
+    }
+}
+
+// max over L of latent per batch row, then notsilent = log10(max/latent) < threshold (Kmeans_2.py:76-79)
+__global__ void row_max_kernel(const float* __restrict__ x, int64_t L, float* __restrict__ out) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    float m = -INFINITY;
+    for (int64_t i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, x[(size_t)b * L + i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        m = warp_max(m);
+        if (threadIdx.x == 0) out[b] = m;
+    }
+}
+__global__ void silence_mask_kernel(const float* __restrict__ x, const float* __restrict__ rowmax, int64_t L,
+                                    int64_t n, float threshold, uint8_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = logf(rowmax[i / L] / x[i]) / logf(10.f);   // utils/ops.py:56-59 log10
+        out[i] = v < threshold ? 1 : 0;
+    }
+}
+
+// separated[b*S+s][i] = X_input[b][i] * mask[b][i][s]   (network.py:567-580)
+__global__ void apply_masks_kernel(const float* __restrict__ X, const int* __restrict__ labels,
+                                   const float* __restrict__ soft, int B, int S, int64_t TF, float* __restrict__ out) {
+    const int64_t n = (int64_t)B * TF;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / TF, j = i - b * TF;
+        const float x = X[i];
+        for (int s = 0; s < S; ++s) {
+            const float m = labels ? (labels[i] == s ? 1.f : 0.f) : soft[i * S + s];
+            out[((size_t)b * S + s) * TF + j] = x * m;
+        }
+    }
+}
+
+int km_chunks(int B, int64_t L) {
+    int64_t ntiles = (L + KM_TILE - 1) / KM_TILE;
+    int64_t want = (2 * kNumSMs + B - 1) / B;
+    if (want < 1) want = 1;
+    return (int)(ntiles < want ? ntiles : want);
+}
+
+struct KmWs {
+    float *Xn, *cent, *part;
+    size_t total;
+};
+KmWs km_ws(void* base, int B, int64_t L, int E, int K, int tries) {
+    KmWs w;
+    size_t off = 0;
+    char* p = (char*)base;
+    w.Xn = (float*)(p + off);   off += align_up((size_t)B * L * E * 4, 256);
+    w.cent = (float*)(p + off); off += align_up((size_t)B * tries * K * E * 4, 256);
+    w.part = (float*)(p + off); off += align_up((size_t)B * km_chunks(B, L) * tries * K * (E + 1) * 4, 256);
+    w.total = off;
+    return w;
+}
+
+template <int MODE, int SOFT>
+int launch_pass(const float* X, const float* cent, const uint8_t* ns, int B, int64_t L, int E, int K, int tries,
+                float beta, float* part, cudaStream_t st) {
+    const KmSmemLayout lay = km_layout(E, K, tries, MODE, SOFT);
+    AMSS_REQUIRE(lay.total <= 227 * 1024, "kmeans: shared memory %zu B exceeds 227 KB (E=%d K=%d tries=%d)",
+                 lay.total, E, K, tries);
+    AMSS_CUDA(cudaFuncSetAttribute(kmeans_pass_kernel<MODE, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)lay.total));
+    dim3 grid(km_chunks(B, L), B);
+    AMSS_LAUNCH((kmeans_pass_kernel<MODE, SOFT>), grid, KM_THREADS, lay.total, st, X, cent, ns, B, L, E, K, tries,
+                beta, part);
+    return AMSS_OK;
+}
+
+}  // namespace
+}  // namespace amss
+
+using namespace amss;
+
+extern "C" size_t amss_kmeans_workspace_bytes(int B, int64_t L, int E, int K, int tries) {
+    return km_ws(nullptr, B, L, E, K, tries).total;
+}
+
+extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const uint8_t* notsilent, int B, int64_t L,
+                               int E, int K, int tries, int iters, float beta, int normalize_input,
+                               int assign_at_end, float* centroids, int32_t* labels, float* soft, float* inertia,
+                               int32_t* best_try, void* workspace, size_t workspace_bytes, void* stream) {
+    AMSS_REQUIRE(X && init_idx && centroids && workspace && best_try, "kmeans_fit: null pointer");
+    AMSS_REQUIRE(B > 0 && L > 0 && E > 0 && tries > 0 && iters >= 0, "kmeans_fit: bad sizes");
+    AMSS_REQUIRE(K >= 1 && K <= KM_MAXK, "kmeans_fit: K=%d outside [1,%d]", K, KM_MAXK);
+    AMSS_REQUIRE(K <= L, "kmeans_fit: K > L");
+    const bool is_soft = !isnan(beta);
+    AMSS_REQUIRE(is_soft ? soft != nullptr : labels != nullptr, "kmeans_fit: output for the chosen mode is null");
+    KmWs w = km_ws(workspace, B, L, E, K, tries);
+    if (workspace_bytes < w.total) {
+        set_error("kmeans_fit: workspace %zu < %zu", workspace_bytes, w.total);
+        return AMSS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* Xw = X;
+    if (normalize_input) {
+        AMSS_LAUNCH(rows_l2norm_kernel, 4 * kNumSMs, 256, 0, st, X, (int64_t)B * L, E, w.Xn);
+        Xw = w.Xn;
+    }
+    AMSS_LAUNCH(kmeans_gather_init_kernel, 64, 256, 0, st, Xw, init_idx, B, L, E, K, tries, w.cent);
+    const int chunks = km_chunks(B, L);
+    int rc;
+    for (int it = 0; it < iters; ++it) {
+        rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st)
+                     : launch_pass<KM_UPDATE, 0>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st);
+        if (rc != AMSS_OK) return rc;
+        AMSS_LAUNCH(kmeans_finalize_kernel, 64, 256, 0, st, w.part, B, chunks, tries, K, E, w.cent);
+    }
+    rc = is_soft ? launch_pass<KM_INERTIA, 1>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st)
+                 : launch_pass<KM_INERTIA, 0>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st);
+    if (rc != AMSS_OK) return rc;
+    AMSS_LAUNCH(kmeans_select_kernel, B, 128, 0, st, w.part, w.cent, B, chunks, tries, K, E, inertia, best_try,
+                centroids);
+    // final labels: un-gated X if assign_at_end (Kmeans_2.py:106-107), else the best try's gated labels
+    const uint8_t* ns_final = assign_at_end ? nullptr : notsilent;
+    const size_t smem = ((size_t)KM_TILE * (E + 1) + (size_t)K * E) * 4;
+    dim3 grid((unsigned)std::min<int64_t>((L + KM_TILE - 1) / KM_TILE, (int64_t)std::max(1, 4 * kNumSMs / B)), B);
+    if (is_soft) {
+        AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(kmeans_assign_kernel<1>, grid, KM_THREADS, smem, st, Xw, centroids, ns_final, best_try, B, L, E, K,
+                    tries, beta, labels, soft);
+    } else {
+        AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(kmeans_assign_kernel<0>, grid, KM_THREADS, smem, st, Xw, centroids, ns_final, best_try, B, L, E, K,
+                    tries, beta, labels, soft);
+    }
+    return AMSS_OK;
+}
+
+extern "C" int amss_kmeans_silence_mask(const float* latent, int B, int64_t L, float threshold, uint8_t* notsilent,
+                                        void* workspace, void* stream) {
+    AMSS_REQUIRE(latent && notsilent && workspace, "kmeans_silence_mask: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* rowmax = (float*)workspace;  // B floats
+    AMSS_LAUNCH(row_max_kernel, B, 256, 0, st, latent, L, rowmax);
+    AMSS_LAUNCH(silence_mask_kernel, 2 * kNumSMs, 256, 0, st, latent, rowmax, L, (int64_t)B * L, threshold, notsilent);
+    return AMSS_OK;
+}
+
+extern "C" int amss_apply_masks(const float* X_input, const int32_t* labels, const float* soft, int B, int S,
+                                int64_t TF, float* separated, void* stream) {
+    AMSS_REQUIRE(X_input && separated && ((labels != nullptr) != (soft != nullptr)),
+                 "apply_masks: need exactly one of labels / soft");
+    AMSS_LAUNCH(apply_masks_kernel, 4 * kNumSMs, 256, 0, (cudaStream_t)stream, X_input, labels, soft, B, S, TF,
+                separated);
+    return AMSS_OK;
+}

@@ -1,0 +1,202 @@
+// STFT twin of the adaptive front end and its inverse.
+//   forward : tf.contrib.signal.stft(x, frame, hop, fft_length=frame)        models/network.py:480-502
+//   inverse : (mask*|X|)*exp(j*angle(X)) -> tf.contrib.signal.inverse_stft   models/network.py:584-607
+// Both are HBM/launch-bound (about 1.35 MB of traffic per 4 s mixture): one CTA per frame does
+// frame + periodic-hann window + radix-2 FFT in shared memory and writes |X| / X (and the
+// arg-max-over-speakers label) straight out; the inverse fuses mask, Hermitian fill, inverse FFT,
+// the inverse_stft_window_fn normalisation and the overlap-add gather (no atomics, no scratch).
+#include "common.cuh"
+
+namespace amss {
+namespace {
+
+// In-place radix-2 DIT FFT of N complex points held bit-reversed in `buf`; N/2 threads.
+// tw[k] = exp(-+ 2*pi*i*k/N), k < N/2 (sign chosen by the caller when filling tw).
+__device__ __forceinline__ void fft_shared(float2* buf, const float2* tw, int N, int logN) {
+    const int tid = threadIdx.x;
+    for (int s = 1; s <= logN; ++s) {
+        const int half = 1 << (s - 1);
+        __syncthreads();
+        if (tid < N / 2) {
+            const int grp = tid >> (s - 1), j = tid & (half - 1);
+            const int i0 = (grp << s) + j, i1 = i0 + half;
+            const float2 w = tw[j << (logN - s)];
+            const float2 a = buf[i0], b = buf[i1];
+            const float2 bw = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+            buf[i0] = make_float2(a.x + bw.x, a.y + bw.y);
+            buf[i1] = make_float2(a.x - bw.x, a.y - bw.y);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float hann_periodic(int i, int N) {
+    // tf.contrib.signal.hann_window(N, periodic=True) = 0.5 - 0.5*cos(2*pi*i/N)
+    return 0.5f - 0.5f * cospif(2.0f * (float)i / (float)N);
+}
+
+__device__ __forceinline__ void fill_twiddles(float2* tw, int N, float sign) {
+    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) {
+        float s, c;
+        sincospif(2.0f * (float)k / (float)N, &s, &c);
+        tw[k] = make_float2(c, sign * s);
+    }
+}
+
+// grid (T, R); block N/2 (>=32).  spec/mag optional.
+__global__ void stft_fwd_kernel(const float* __restrict__ x, int64_t L, int N, int logN, int hop, int T,
+                                float2* __restrict__ spec, float* __restrict__ mag) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    float2* buf = reinterpret_cast<float2*>(st_smem);
+    float2* tw = buf + N;
+    const int t = blockIdx.x, r = blockIdx.y, F = N / 2 + 1;
+    fill_twiddles(tw, N, -1.f);
+    const float* src = x + (size_t)r * L + (size_t)t * hop;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float v = src[i] * hann_periodic(i, N);
+        buf[__brev((unsigned)i) >> (32 - logN)] = make_float2(v, 0.f);
+    }
+    fft_shared(buf, tw, N, logN);
+    const size_t o = ((size_t)r * T + t) * F;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const float2 v = buf[f];
+        if (spec) spec[o + f] = v;
+        if (mag) mag[o + f] = sqrtf(v.x * v.x + v.y * v.y);
+    }
+}
+
+// grid (T, B): labels[b,t,f] = argmax_s |stft(non_mix[b,s])|[t,f]   (first index wins ties)
+__global__ void stft_labels_kernel(const float* __restrict__ x, int S, int64_t L, int N, int logN, int hop, int T,
+                                   uint8_t* __restrict__ labels, float* __restrict__ mag_nm) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    float2* buf = reinterpret_cast<float2*>(st_smem);
+    float2* tw = buf + N;
+    const int t = blockIdx.x, b = blockIdx.y, F = N / 2 + 1;
+    fill_twiddles(tw, N, -1.f);
+    // each thread owns bins f = tid and (thread 0) f = N/2
+    float best0 = -1.f, best1 = -1.f;
+    int lab0 = 0, lab1 = 0;
+    const size_t o = ((size_t)b * T + t) * F;
+    for (int s = 0; s < S; ++s) {
+        const float* src = x + ((size_t)b * S + s) * L + (size_t)t * hop;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const float v = src[i] * hann_periodic(i, N);
+            buf[__brev((unsigned)i) >> (32 - logN)] = make_float2(v, 0.f);
+        }
+        fft_shared(buf, tw, N, logN);
+        {
+            const float2 v = buf[threadIdx.x];
+            const float m = sqrtf(v.x * v.x + v.y * v.y);
+            if (m > best0) { best0 = m; lab0 = s; }
+            if (mag_nm) mag_nm[(o + threadIdx.x) * S + s] = m;
+        }
+        if (threadIdx.x == 0) {
+            const float2 v = buf[N / 2];
+            const float m = sqrtf(v.x * v.x + v.y * v.y);
+            if (m > best1) { best1 = m; lab1 = s; }
+            if (mag_nm) mag_nm[(o + N / 2) * S + s] = m;
+        }
+    }
+    labels[o + threadIdx.x] = (uint8_t)lab0;
+    if (threadIdx.x == 0) labels[o + N / 2] = (uint8_t)lab1;
+}
+
+// grid (nblocks = T-1+frame/hop, B*S); block N/2.  out[bs, m*hop + j], j < hop.
+__global__ void istft_masked_kernel(const float2* __restrict__ spec, const int* __restrict__ labels,
+                                    const float* __restrict__ masks, int S, int T, int N, int logN, int hop,
+                                    float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    float2* buf = reinterpret_cast<float2*>(st_smem);
+    float2* tw = buf + N;
+    float* acc = reinterpret_cast<float*>(tw + N / 2);   // hop floats
+    const int m = blockIdx.x, bs = blockIdx.y, b = bs / S, s = bs % S;
+    const int F = N / 2 + 1, r = N / hop;
+    const int64_t Lout = (int64_t)(T - 1) * hop + N;
+    fill_twiddles(tw, N, +1.f);
+    for (int j = threadIdx.x; j < hop; j += blockDim.x) acc[j] = 0.f;
+    for (int t = m - r + 1; t <= m; ++t) {
+        if (t < 0 || t >= T) continue;   // block-uniform
+        const size_t o = ((size_t)b * T + t) * F;
+        __syncthreads();
+        for (int k = threadIdx.x; k < F; k += blockDim.x) {
+            const float w = labels ? (labels[o + k] == s ? 1.f : 0.f) : masks[(o + k) * S + s];
+            float2 v = spec[o + k];
+            v.x *= w; v.y *= w;
+            if (k == 0 || k == N / 2) {   // irfft ignores the imaginary part of DC and Nyquist
+                buf[__brev((unsigned)k) >> (32 - logN)] = make_float2(v.x, 0.f);
+            } else {
+                buf[__brev((unsigned)k) >> (32 - logN)] = v;
+                buf[__brev((unsigned)(N - k)) >> (32 - logN)] = make_float2(v.x, -v.y);
+            }
+        }
+        fft_shared(buf, tw, N, logN);
+        const int base = (m - t) * hop;
+        for (int j = threadIdx.x; j < hop; j += blockDim.x) {
+            const int i = base + j;
+            // inverse_stft_window_fn(hop)(N): w[i] / sum_o w^2[(i mod hop) + o*hop]
+            float den = 0.f;
+            for (int o2 = 0; o2 < r; ++o2) { const float w = hann_periodic(j + o2 * hop, N); den = fmaf(w, w, den); }
+            acc[j] += buf[i].x * (1.0f / (float)N) * (hann_periodic(i, N) / den);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < hop; j += blockDim.x) {
+        const int64_t u = (int64_t)m * hop + j;
+        if (u < Lout) out[(size_t)bs * Lout + u] = acc[j];
+    }
+}
+
+int ilog2_exact(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return (1 << l) == n ? l : -1;
+}
+
+}  // namespace
+}  // namespace amss
+
+using namespace amss;
+
+extern "C" int amss_stft_fwd(const float* x, int R, int L, int frame, int hop, float* spec, float* mag,
+                             void* stream) {
+    AMSS_REQUIRE(x && (spec || mag), "stft_fwd: null pointer");
+    const int logN = ilog2_exact(frame);
+    AMSS_REQUIRE(logN >= 6 && logN <= 11, "stft_fwd: frame %d must be a power of two in [64,2048]", frame);
+    AMSS_REQUIRE(hop > 0 && L >= frame && R > 0, "stft_fwd: bad sizes L=%d frame=%d hop=%d", L, frame, hop);
+    const int T = 1 + (L - frame) / hop;
+    const size_t smem = (size_t)frame * 8 + (size_t)frame / 2 * 8;
+    dim3 grid(T, R);
+    AMSS_LAUNCH(stft_fwd_kernel, grid, frame / 2, smem, stream, x, (int64_t)L, frame, logN, hop, T,
+                reinterpret_cast<float2*>(spec), mag);
+    return AMSS_OK;
+}
+
+extern "C" int amss_stft_labels(const float* non_mix, int B, int S, int L, int frame, int hop, uint8_t* labels,
+                                float* mag_non_mix, void* stream) {
+    AMSS_REQUIRE(non_mix && labels, "stft_labels: null pointer");
+    const int logN = ilog2_exact(frame);
+    AMSS_REQUIRE(logN >= 6 && logN <= 11, "stft_labels: frame %d must be a power of two in [64,2048]", frame);
+    AMSS_REQUIRE(hop > 0 && L >= frame && B > 0 && S > 0 && S < 256, "stft_labels: bad sizes");
+    const int T = 1 + (L - frame) / hop;
+    const size_t smem = (size_t)frame * 8 + (size_t)frame / 2 * 8;
+    dim3 grid(T, B);
+    AMSS_LAUNCH(stft_labels_kernel, grid, frame / 2, smem, stream, non_mix, S, (int64_t)L, frame, logN, hop, T,
+                labels, mag_non_mix);
+    return AMSS_OK;
+}
+
+extern "C" int amss_istft_masked_fwd(const float* spec, const int32_t* labels, const float* masks, int B, int S,
+                                     int T, int frame, int hop, float* out, void* stream) {
+    AMSS_REQUIRE(spec && out && ((labels != nullptr) != (masks != nullptr)),
+                 "istft_masked_fwd: need spec, out and exactly one of labels / masks");
+    const int logN = ilog2_exact(frame);
+    AMSS_REQUIRE(logN >= 6 && logN <= 11, "istft_masked_fwd: frame %d must be a power of two in [64,2048]", frame);
+    AMSS_REQUIRE(hop > 0 && frame % hop == 0, "istft_masked_fwd: frame must be a multiple of hop");
+    const int nblocks = T - 1 + frame / hop;
+    const size_t smem = (size_t)frame * 8 + (size_t)frame / 2 * 8 + (size_t)hop * 4;
+    dim3 grid(nblocks, B * S);
+    AMSS_LAUNCH(istft_masked_kernel, grid, frame / 2, smem, stream, reinterpret_cast<const float2*>(spec), labels,
+                masks, S, T, frame, logN, hop, out);
+    return AMSS_OK;
+}

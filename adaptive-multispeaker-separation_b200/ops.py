@@ -1,0 +1,367 @@
+"""Functional host wrappers over the C ABI (include/amss.h).
+
+torch is used for device memory and the current stream only; every computation below is a
+kernel of libamss_b200.so.  All functions take/return CUDA float32 tensors (contiguous) unless
+noted, and raise if handed CPU tensors -- there is no CPU path.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import AMSS_PREC_FP32, AMSS_PREC_BF16, AMSS_POOL_MAX, AMSS_POOL_AVG, AMSS_POOL_STRIDE  # noqa: F401
+
+_f32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.AmssError("amss ops need CUDA tensors: there is no CPU fallback")
+        if not t.is_contiguous():
+            raise _lib.AmssError("amss ops need contiguous tensors")
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# adaptive filterbank
+# ------------------------------------------------------------------------------------------
+def make_filter(window, bases):
+    _chk(window, bases)
+    W, N = bases.shape
+    filt = torch.empty(W, N, dtype=_f32, device=bases.device)
+    _lib.call("amss_filterbank_make_filter", _p(window), _p(bases), W, N, _p(filt), _stream())
+    return filt
+
+
+def make_filter_bwd(window, bases, dfilt):
+    _chk(window, bases, dfilt)
+    W, N = bases.shape
+    dwindow = torch.empty_like(window)
+    dbases = torch.empty_like(bases)
+    _lib.call("amss_filterbank_make_filter_bwd", _p(window), _p(bases), _p(dfilt), W, N, _p(dwindow), _p(dbases),
+              _stream())
+    return dwindow, dbases
+
+
+def analysis_out_frames(L, W, pool, hop, mode):
+    return _lib.query("amss_filterbank_analysis_out_frames", L, W, pool, hop, mode)
+
+
+def filterbank_analysis(x, filt, pool, hop, mode=AMSS_POOL_MAX, precision=AMSS_PREC_FP32):
+    """x[Bt,L], filt[W,N] -> (y[Bt,Tp,N], argmax int64 [Bt,Tp,N] or None)."""
+    _chk(x, filt)
+    Bt, L = x.shape
+    W, N = filt.shape
+    Tp = analysis_out_frames(L, W, pool, hop, mode)
+    y = torch.empty(Bt, Tp, N, dtype=_f32, device=x.device)
+    am = torch.empty(Bt, Tp, N, dtype=torch.int64, device=x.device) if mode == AMSS_POOL_MAX else None
+    nb = _lib.query("amss_filterbank_analysis_workspace_bytes", Bt, L, W, N, pool, hop, mode, precision)
+    ws = _ws(nb, x.device)
+    _lib.call("amss_filterbank_analysis_fwd", _p(x), _p(filt), Bt, L, W, N, pool, hop, mode, precision, _p(y), _p(am),
+              _p(ws), ws.numel(), _stream())
+    return y, am
+
+
+def filterbank_analysis_bwd(x, dy, argmax, W):
+    """d(filt)[W,N] through the max-pool arg-max."""
+    _chk(x, dy, argmax)
+    Bt, L = x.shape
+    _, Tp, N = dy.shape
+    dfilt = torch.empty(W, N, dtype=_f32, device=x.device)
+    ws = _ws(_lib.query("amss_filterbank_grad_workspace_bytes", W, N), x.device)
+    _lib.call("amss_filterbank_analysis_bwd", _p(x), _p(dy), _p(argmax), Bt, L, W, N, Tp, 0, _p(dfilt), _p(ws),
+              ws.numel(), _stream())
+    return dfilt
+
+
+def filterbank_synthesis(vals, argmax_mix, filt2, B, S, L, pool, hop):
+    """vals[B*S,Tp,N], argmax_mix[B,Tp,N] (mixture rows), filt2[W,N] -> out[B*S,L]."""
+    _chk(vals, argmax_mix, filt2)
+    R, Tp, N = vals.shape
+    W = filt2.shape[0]
+    out = torch.empty(R, L, dtype=_f32, device=vals.device)
+    ws = _ws(_lib.query("amss_filterbank_synthesis_workspace_bytes", B, S, L, W, N, Tp), vals.device)
+    _lib.call("amss_filterbank_synthesis_fwd", _p(vals), _p(argmax_mix), _p(filt2), B, S, L, W, N, Tp, pool, hop,
+              _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
+def filterbank_synthesis_bwd(dout, vals, argmax_mix, filt2, B, S, need_dvals=True, need_dfilt=True):
+    _chk(dout, vals, argmax_mix, filt2)
+    R, Tp, N = vals.shape
+    W = filt2.shape[0]
+    L = dout.shape[1]
+    dvals = torch.empty_like(vals) if need_dvals else None
+    dfilt2 = torch.empty_like(filt2) if need_dfilt else None
+    ws = _ws(_lib.query("amss_filterbank_grad_workspace_bytes", W, N), vals.device)
+    _lib.call("amss_filterbank_synthesis_bwd", _p(dout), _p(vals), _p(argmax_mix), _p(filt2), B, S, L, W, N, Tp,
+              _p(dvals), _p(dfilt2), _p(ws), ws.numel(), _stream())
+    return dvals, dfilt2
+
+
+# ------------------------------------------------------------------------------------------
+# STFT twin
+# ------------------------------------------------------------------------------------------
+def stft(x, frame, hop, want_spec=True, want_mag=True):
+    """x[R,L] -> (spec complex64 [R,T,F] or None, mag [R,T,F] or None)."""
+    _chk(x)
+    R, L = x.shape
+    T, F = 1 + (L - frame) // hop, frame // 2 + 1
+    spec = torch.empty(R, T, F, 2, dtype=_f32, device=x.device) if want_spec else None
+    mag = torch.empty(R, T, F, dtype=_f32, device=x.device) if want_mag else None
+    _lib.call("amss_stft_fwd", _p(x), R, L, frame, hop, _p(spec), _p(mag), _stream())
+    return (torch.view_as_complex(spec) if want_spec else None), mag
+
+
+def stft_labels(non_mix, frame, hop, want_mag=False):
+    """non_mix[B,S,L] -> (labels uint8 [B,T,F], |X_non_mix| [B,T,F,S] or None)."""
+    _chk(non_mix)
+    B, S, L = non_mix.shape
+    T, F = 1 + (L - frame) // hop, frame // 2 + 1
+    labels = torch.empty(B, T, F, dtype=torch.uint8, device=non_mix.device)
+    mag = torch.empty(B, T, F, S, dtype=_f32, device=non_mix.device) if want_mag else None
+    _lib.call("amss_stft_labels", _p(non_mix), B, S, L, frame, hop, _p(labels), _p(mag), _stream())
+    return labels, mag
+
+
+def istft_masked(spec, S, frame, hop, labels=None, masks=None):
+    """spec complex64 [B,T,F]; labels int32 [B,T*F] or masks [B,T*F,S] -> out[B,S,L']."""
+    specr = torch.view_as_real(spec).contiguous()
+    _chk(specr, labels, masks)
+    B, T, F = spec.shape
+    Lout = (T - 1) * hop + frame
+    out = torch.empty(B, S, Lout, dtype=_f32, device=spec.device)
+    _lib.call("amss_istft_masked_fwd", _p(specr), _p(labels), _p(masks), B, S, T, frame, hop, _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM / BLSTM
+# ------------------------------------------------------------------------------------------
+def transpose_01(x):
+    """x[D0,D1,C] -> [D1,D0,C]."""
+    _chk(x)
+    D0, D1, C = x.shape
+    out = torch.empty(D1, D0, C, dtype=_f32, device=x.device)
+    _lib.call("amss_transpose_01", _p(x), D0, D1, C, _p(out), _stream())
+    return out
+
+
+def gemm(A, B, bias=None, transa=False, transb=False, out=None, accumulate=False, precision=AMSS_PREC_FP32,
+         out_swap=None):
+    """op(A) @ op(B) (+bias).  A, B 2-D, possibly row-strided views (stride(1) == 1).
+    out_swap=(b_count, t_count) remaps time-major output rows to batch-major."""
+    for t in (A, B):
+        if not t.is_cuda or t.dim() != 2 or t.stride(1) != 1:
+            raise _lib.AmssError("gemm: operands must be 2-D CUDA tensors with unit inner stride")
+    M = A.shape[1] if transa else A.shape[0]
+    K = A.shape[0] if transa else A.shape[1]
+    Kb = B.shape[1] if transb else B.shape[0]
+    N = B.shape[0] if transb else B.shape[1]
+    if K != Kb:
+        raise _lib.AmssError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=_f32, device=A.device)
+        accumulate = False
+    sb, st = (out_swap if out_swap else (0, 0))
+    nb = _lib.query("amss_gemm_workspace_bytes", M, N, K, int(transa), int(transb), precision)
+    ws = _ws(nb, A.device)
+    _lib.call("amss_gemm", _p(A), A.stride(0), _p(B), B.stride(0), _p(bias), M, N, K, int(transa), int(transb),
+              int(accumulate), precision, _p(out), out.stride(0), sb, st, _p(ws), ws.numel(), _stream())
+    return out
+
+
+def blstm_fwd(x_tm, kernel_fw, bias_fw, kernel_bw, bias_bw, forget_bias=1.0, precision=AMSS_PREC_FP32,
+              save_for_backward=True):
+    """x_tm[T,B,I] time-major -> (y_tm[T,B,2H], saved or None)."""
+    _chk(x_tm, kernel_fw, bias_fw, kernel_bw, bias_bw)
+    T, B, I = x_tm.shape
+    H = kernel_fw.shape[1] // 4
+    assert kernel_fw.shape[0] == I + H and kernel_bw.shape == kernel_fw.shape
+    y = torch.empty(T, B, 2 * H, dtype=_f32, device=x_tm.device)
+    saved = _ws(_lib.query("amss_blstm_saved_bytes", B, T, I, H), x_tm.device) if save_for_backward else None
+    ws = _ws(_lib.query("amss_blstm_workspace_bytes", B, T, I, H, precision), x_tm.device)
+    _lib.call("amss_blstm_fwd", _p(x_tm), _p(kernel_fw), _p(bias_fw), _p(kernel_bw), _p(bias_bw), B, T, I, H,
+              float(forget_bias), precision, _p(y), _p(saved), _p(ws), ws.numel(), _stream())
+    return y, saved
+
+
+def blstm_bwd(x_tm, kernel_fw, kernel_bw, y_tm, dy_tm, saved, precision=AMSS_PREC_FP32, need_dx=True):
+    _chk(x_tm, kernel_fw, kernel_bw, y_tm, dy_tm, saved)
+    T, B, I = x_tm.shape
+    H = kernel_fw.shape[1] // 4
+    dx = torch.empty_like(x_tm) if need_dx else None
+    dk_fw, dk_bw = torch.empty_like(kernel_fw), torch.empty_like(kernel_bw)
+    db_fw = torch.empty(4 * H, dtype=_f32, device=x_tm.device)
+    db_bw = torch.empty(4 * H, dtype=_f32, device=x_tm.device)
+    ws = _ws(_lib.query("amss_blstm_workspace_bytes", B, T, I, H, precision), x_tm.device)
+    _lib.call("amss_blstm_bwd", _p(x_tm), _p(kernel_fw), _p(kernel_bw), _p(y_tm), _p(dy_tm), _p(saved), B, T, I, H,
+              precision, _p(dx), _p(dk_fw), _p(db_fw), _p(dk_bw), _p(db_bw), _p(ws), ws.numel(), _stream())
+    return dx, dk_fw, db_fw, dk_bw, db_bw
+
+
+# ------------------------------------------------------------------------------------------
+# normalisation / losses
+# ------------------------------------------------------------------------------------------
+def l2norm_fwd(z, E):
+    _chk(z)
+    rows = z.numel() // E
+    v = torch.empty_like(z)
+    inv = torch.empty(rows, dtype=_f32, device=z.device)
+    _lib.call("amss_l2norm_fwd", _p(z), rows, E, _p(v), _p(inv), _stream())
+    return v, inv
+
+
+def l2norm_bwd(v, inv, dv, E):
+    _chk(v, inv, dv)
+    dz = torch.empty_like(v)
+    _lib.call("amss_l2norm_bwd", _p(v), _p(inv), _p(dv), v.numel() // E, E, _p(dz), _stream())
+    return dz
+
+
+def colsum(dZ):
+    _chk(dZ)
+    M, N = dZ.shape
+    out = torch.empty(N, dtype=_f32, device=dZ.device)
+    ws = _ws(_lib.query("amss_colsum_workspace_bytes", M, N), dZ.device)
+    _lib.call("amss_colsum", _p(dZ), M, N, _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
+def dpcl_loss_fwd(V, labels, S):
+    """V[B,TF,E], labels uint8 [B,TF] -> (loss[1], workspace for the backward)."""
+    _chk(V, labels)
+    B, TF, E = V.shape
+    loss = torch.empty(1, dtype=_f32, device=V.device)
+    ws = _ws(_lib.query("amss_dpcl_workspace_bytes", B, TF, E, S), V.device)
+    _lib.call("amss_dpcl_loss_fwd", _p(V), _p(labels), B, TF, E, S, _p(loss), _p(ws), ws.numel(), _stream())
+    return loss, ws
+
+
+def dpcl_loss_bwd(V, labels, S, dloss, ws):
+    _chk(V, labels, dloss)
+    B, TF, E = V.shape
+    dV = torch.empty_like(V)
+    _lib.call("amss_dpcl_loss_bwd", _p(V), _p(labels), _p(dloss), B, TF, E, S, _p(dV), _p(ws), _stream())
+    return dV
+
+
+def l41_loss_fwd(emb, labels, spk):
+    """emb[B,TF,E], labels uint8 [B,TF], spk[B,S,E] -> loss[1]."""
+    _chk(emb, labels, spk)
+    B, TF, E = emb.shape
+    S = spk.shape[1]
+    loss = torch.empty(1, dtype=_f32, device=emb.device)
+    ws = _ws(_lib.query("amss_l41_workspace_bytes", B, TF, E, S), emb.device)
+    _lib.call("amss_l41_loss_fwd", _p(emb), _p(labels), _p(spk), B, TF, E, S, _p(loss), _p(ws), ws.numel(), _stream())
+    return loss
+
+
+def l41_loss_bwd(emb, labels, spk, dloss):
+    _chk(emb, labels, spk, dloss)
+    B, TF, E = emb.shape
+    S = spk.shape[1]
+    demb = torch.empty_like(emb)
+    dspk = torch.empty_like(spk)
+    ws = _ws(_lib.query("amss_l41_workspace_bytes", B, TF, E, S), emb.device)
+    _lib.call("amss_l41_loss_bwd", _p(emb), _p(labels), _p(spk), _p(dloss), B, TF, E, S, _p(demb), _p(dspk), _p(ws),
+              ws.numel(), _stream())
+    return demb, dspk
+
+
+def plugged_labels(front_y, B, S):
+    """front_y[B(S+1),Tp,N] -> labels uint8 [B,Tp,N] (argmax_s |X_non_mix|)."""
+    _chk(front_y)
+    _, Tp, N = front_y.shape
+    labels = torch.empty(B, Tp, N, dtype=torch.uint8, device=front_y.device)
+    _lib.call("amss_plugged_labels", _p(front_y), B, S, Tp * N, _p(labels), _stream())
+    return labels
+
+
+def wave_stats(target, approx):
+    """target, approx [R,L] -> [R,4] = (<t,t>, <a,a>, <t,a>, <t-a,t-a>)."""
+    _chk(target, approx)
+    R, L = target.shape
+    out = torch.empty(R, 4, dtype=_f32, device=target.device)
+    _lib.call("amss_wave_stats", _p(target), _p(approx), R, L, _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# k-means
+# ------------------------------------------------------------------------------------------
+def kmeans_fit(X, init_idx, K, tries, iters, beta=None, notsilent=None, normalize_input=True, assign_at_end=True):
+    """X[B,L,E]; init_idx int32 [B*tries,K]; notsilent uint8 [B,L] or None.
+    -> (centroids[B,K,E], labels int32 [B,L] or soft [B,L,K], inertia[B,tries], best_try int32 [B])."""
+    _chk(X, init_idx, notsilent)
+    B, L, E = X.shape
+    dev = X.device
+    cent = torch.empty(B, K, E, dtype=_f32, device=dev)
+    soft = beta is not None
+    labels = None if soft else torch.empty(B, L, dtype=torch.int32, device=dev)
+    softo = torch.empty(B, L, K, dtype=_f32, device=dev) if soft else None
+    inertia = torch.empty(B, tries, dtype=_f32, device=dev)
+    best = torch.empty(B, dtype=torch.int32, device=dev)
+    ws = _ws(_lib.query("amss_kmeans_workspace_bytes", B, L, E, K, tries), dev)
+    _lib.call("amss_kmeans_fit", _p(X), _p(init_idx), _p(notsilent), B, L, E, K, tries, iters,
+              float("nan") if beta is None else float(beta), int(normalize_input), int(assign_at_end), _p(cent),
+              _p(labels), _p(softo), _p(inertia), _p(best), _p(ws), ws.numel(), _stream())
+    return cent, (softo if soft else labels), inertia, best
+
+
+def kmeans_silence_mask(latent, threshold):
+    """latent[B,L] -> notsilent uint8 [B,L] = log10(max/latent) < threshold."""
+    _chk(latent)
+    B, L = latent.shape
+    out = torch.empty(B, L, dtype=torch.uint8, device=latent.device)
+    ws = _ws(4 * B, latent.device)
+    _lib.call("amss_kmeans_silence_mask", _p(latent), B, L, float(threshold), _p(out), _p(ws), _stream())
+    return out
+
+
+def apply_masks(X_input, S, labels=None, soft=None):
+    """X_input[B,TF] -> separated[B*S,TF]."""
+    _chk(X_input, labels, soft)
+    B, TF = X_input.shape
+    out = torch.empty(B * S, TF, dtype=_f32, device=X_input.device)
+    _lib.call("amss_apply_masks", _p(X_input), _p(labels), _p(soft), B, S, TF, _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------
+def amsgrad_step(p, g, m, v, vhat, lr_t, beta1, beta2, eps, grad_scale=1.0, grad_scale_dev=None):
+    _chk(p, g, m, v, vhat, grad_scale_dev)
+    _lib.call("amss_amsgrad_step", _p(p), _p(g), _p(m), _p(v), _p(vhat), p.numel(), float(lr_t), float(beta1),
+              float(beta2), float(eps), float(grad_scale), _p(grad_scale_dev), _stream())
+
+
+def global_norm_clip_factor(g, clip):
+    """-> device scalar clip / max(||g||, clip)  (tf.clip_by_global_norm)."""
+    _chk(g)
+    sumsq = torch.zeros(1, dtype=_f32, device=g.device)
+    ws = _ws(_lib.query("amss_sumsq_workspace_bytes"), g.device)
+    _lib.call("amss_sumsq", _p(g), g.numel(), _p(sumsq), _p(ws), _stream())
+    factor = torch.empty(1, dtype=_f32, device=g.device)
+    _lib.call("amss_clip_factor", _p(sumsq), float(clip), _p(factor), _stream())
+    return factor
+
+
+def amsgrad_lr_t(lr, beta1, beta2, step):
+    """utils/ops.py:681-683: lr * sqrt(1 - beta2^t) / (1 - beta1^t), t = step (1-based)."""
+    return lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)

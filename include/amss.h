@@ -1,0 +1,246 @@
+/*
+ * amss.h -- C ABI of libamss_b200.so: the sm_100a kernels behind the hot path of
+ * Totoketchup/Adaptive-MultiSpeaker-Separation (adaptive conv filterbank / STFT twin ->
+ * stacked BLSTM embeddings -> k-means masks -> waveform inversion, fwd + bwd + AMSGrad).
+ *
+ * The reference has no FFI: its operator boundary is Python/TensorFlow graph ops.  Each
+ * entry point below replaces the TF op(s) one reference call site lowers to; the call
+ * site is cited as file:line relative to the reference repository root.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer
+ *     unless the name ends in _host.  The caller owns every buffer (including the
+ *     scratch ones, whose sizes come from the *_workspace_bytes queries); the library
+ *     never allocates device memory and keeps no global mutable state.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
+ *   - All tensors are row-major contiguous with the layouts written in the comments.
+ *   - Return value: AMSS_OK (0) or a negative AMSS_ERR_* code; amss_last_error()
+ *     returns a thread-local message for the last failing call.  Nothing throws.
+ *   - `precision`: AMSS_PREC_FP32 = fp32-equivalent arithmetic (SIMT fp32 or 3xbf16
+ *     split tensor-core products, used for the 1e-3 parity gate), AMSS_PREC_BF16 =
+ *     bf16 operands / fp32 accumulate on tcgen05.
+ */
+#ifndef AMSS_H_
+#define AMSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define AMSS_OK 0
+#define AMSS_ERR_INVALID_ARG (-1)
+#define AMSS_ERR_CUDA (-2)
+#define AMSS_ERR_UNSUPPORTED (-3)
+#define AMSS_ERR_WORKSPACE (-4)
+
+#define AMSS_PREC_FP32 0
+#define AMSS_PREC_BF16 1
+
+#define AMSS_POOL_MAX 0     /* --with_max_pool      models/adapt.py:114-117 */
+#define AMSS_POOL_AVG 1     /* --with_average_pool  models/adapt.py:118-120 */
+#define AMSS_POOL_STRIDE 2  /* strided conv         models/adapt.py:121-122 */
+
+int amss_version(void);
+const char* amss_last_error(void);
+/* Number of kernels launched by this library in the calling process (all threads). */
+uint64_t amss_launch_count(void);
+
+/* ------------------------------------------------------------------------------------ *
+ * Adaptive front end  (models/adapt.py:95-134)
+ * ------------------------------------------------------------------------------------ */
+/* filt[W,N] = |window[k]| * bases[k,n]                      models/adapt.py:106, :234   */
+int amss_filterbank_make_filter(const float* window, const float* bases, int W, int N,
+                                float* filt, void* stream);
+/* d(window), d(bases) from d(filt)  (autograd of the line above)                        */
+int amss_filterbank_make_filter_bwd(const float* window, const float* bases,
+                                    const float* dfilt, int W, int N, float* dwindow,
+                                    float* dbases, void* stream);
+
+/* tf.nn.conv2d(SAME, stride 1) + tf.nn.max_pool_with_argmax(VALID)   adapt.py:115-117
+ * (or avg-pool :118-120 / strided conv :121-122), fused: the [Bt,L,N] tensor is never
+ * written.  x[Bt,L], filt[W,N] -> y[Bt,Tp,N], argmax_i64[Bt,Tp,N] (per-sample flat
+ * index t*N+n, TF convention; may be NULL unless mode==AMSS_POOL_MAX).
+ * Tp = (L-pool)/hop+1 (max), L/pool (avg), ceil(L/hop) (stride).                        */
+int amss_filterbank_analysis_fwd(const float* x, const float* filt, int Bt, int L, int W,
+                                 int N, int pool, int hop, int mode, int precision,
+                                 float* y, int64_t* argmax, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+size_t amss_filterbank_analysis_workspace_bytes(int Bt, int L, int W, int N, int pool,
+                                                int hop, int mode, int precision);
+int amss_filterbank_analysis_out_frames(int L, int W, int pool, int hop, int mode);
+/* Backward of the max-pool path w.r.t. the filter (sparse through the argmax):
+ * dfilt[k,n] += sum_{b,tp} dy[b,tp,n] * x[b, pos(b,tp,n)+k-pad_left]   (adapt.py:115-117) */
+int amss_filterbank_analysis_bwd(const float* x, const float* dy, const int64_t* argmax,
+                                 int Bt, int L, int W, int N, int Tp, int accumulate,
+                                 float* dfilt, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+size_t amss_filterbank_grad_workspace_bytes(int W, int N);
+
+/* unpool (utils/ops.py:94-120) + tf.nn.conv2d_transpose(SAME)  (adapt.py:205-252), fused
+ * as a sparse overlap-add: out[r,u] = sum_{tp,n} vals[r,tp,n]*filt2[u-pos+pad_left,n],
+ * pos = argmax[r / S][tp][n] / N  (the mixture's argmax, tiled S times: adapt.py:212-218).
+ * vals[R=B*S,Tp,N], argmax_i64[B,Tp,N], filt2[W,N] -> out[R,L]                           */
+int amss_filterbank_synthesis_fwd(const float* vals, const int64_t* argmax,
+                                  const float* filt2, int B, int S, int L, int W, int N,
+                                  int Tp, int pool, int hop, float* out, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+size_t amss_filterbank_synthesis_workspace_bytes(int B, int S, int L, int W, int N, int Tp);
+/* dvals[R,Tp,N] and dfilt2[W,N] (either may be NULL; overwritten) from dout[R,L].        */
+int amss_filterbank_synthesis_bwd(const float* dout, const float* vals,
+                                  const int64_t* argmax, const float* filt2, int B, int S,
+                                  int L, int W, int N, int Tp, float* dvals, float* dfilt2,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * STFT twin  (models/network.py:480-502, 584-607)
+ * ------------------------------------------------------------------------------------ */
+/* tf.contrib.signal.stft(x, frame, hop, fft_length=frame), periodic hann, no padding.
+ * x[R,L] -> spec[R,T,F] interleaved (re,im), mag[R,T,F] (either may be NULL),
+ * T = 1+(L-frame)/hop, F = frame/2+1.  frame must be a power of two in [64, 2048].      */
+int amss_stft_fwd(const float* x, int R, int L, int frame, int hop, float* spec,
+                  float* mag, void* stream);
+/* |stft| of the S clean sources + argmax over S (network.py:489-502):
+ * non_mix[B,S,L] -> labels_u8[B,T,F] (first index wins ties), mag_non_mix[B,T,F,S]
+ * (optional, NULL to skip).                                                            */
+int amss_stft_labels(const float* non_mix, int B, int S, int L, int frame, int hop,
+                     uint8_t* labels, float* mag_non_mix, void* stream);
+/* Separator.postprocessing (network.py:584-607): (mask * |X|) * exp(j*angle(X)) ->
+ * tf.contrib.signal.inverse_stft(frame, hop, window_fn=inverse_stft_window_fn(hop)).
+ * spec[B,T,F] complex; exactly one of labels_i32[B,T*F] (hard one-hot masks) or
+ * masks[B,T*F,S] (soft) is non-NULL -> out[B,S,(T-1)*hop+frame].                        */
+int amss_istft_masked_fwd(const float* spec, const int32_t* labels, const float* masks,
+                          int B, int S, int T, int frame, int hop, float* out,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * BLSTM  (utils/ops.py:358-383: BasicLSTMCell gate order i,j,f,o; forget_bias 1.0)
+ * ------------------------------------------------------------------------------------ */
+/* One bidirectional layer, TIME-MAJOR activations: x[T,B,I]; kernel_{fw,bw}[I+H,4H] (TF
+ * layout: rows 0..I-1 multiply x, rows I..I+H-1 multiply h); bias_{fw,bw}[4H] ->
+ * y[T,B,2H] (fw | bw).  The reference layout is [B,T,*]: amss_transpose_01 converts.
+ * `saved` (optional, NULL for inference) receives what the backward pass needs.        */
+size_t amss_blstm_workspace_bytes(int B, int T, int I, int H, int precision);
+size_t amss_blstm_saved_bytes(int B, int T, int I, int H);
+int amss_blstm_fwd(const float* x, const float* kernel_fw, const float* bias_fw,
+                   const float* kernel_bw, const float* bias_bw, int B, int T, int I,
+                   int H, float forget_bias, int precision, float* y, void* saved,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* dy[T,B,2H] -> dx[T,B,I] (may be NULL), dkernel_*[I+H,4H], dbias_*[4H] (overwritten). */
+int amss_blstm_bwd(const float* x, const float* kernel_fw, const float* kernel_bw,
+                   const float* y, const float* dy, const void* saved, int B, int T, int I,
+                   int H, int precision, float* dx, float* dkernel_fw, float* dbias_fw,
+                   float* dkernel_bw, float* dbias_bw, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * Dense / embedding head  (utils/ops.py:486-503 Conv1D k=1, :318-324 Normalize)
+ * ------------------------------------------------------------------------------------ */
+/* C[M,N] (ldc) = op(A) * op(B) (+ bias[N]) (+ C if accumulate); row-major with leading
+ * dimensions; transa/transb as in BLAS.  out_swap_b/out_swap_t > 0: row m = t*b_count + b
+ * (time-major) is written to row b*t_count + t (batch-major) -- the [T,B,*] -> [B,T,*]
+ * hand-over between the BLSTM stack and the embedding reshape (models/dpcl.py:30-36).    */
+int amss_gemm(const float* A, int lda, const float* B, int ldb, const float* bias, int M,
+              int N, int K, int transa, int transb, int accumulate, int precision, float* C,
+              int ldc, int out_swap_b, int out_swap_t, void* workspace,
+              size_t workspace_bytes, void* stream);
+/* in[D0,D1,C] -> out[D1,D0,C]                                                           */
+int amss_transpose_01(const float* in, int D0, int D1, int C, float* out, void* stream);
+size_t amss_gemm_workspace_bytes(int M, int N, int K, int transa, int transb, int precision);
+/* v = z * rsqrt(max(sum_E z^2, 1e-12)) over groups of E consecutive values
+ * (tf.nn.l2_normalize, axis=3 of [B,T,F,E]).  In place allowed.                         */
+int amss_l2norm_fwd(const float* z, int64_t rows, int E, float* v, float* inv_norm,
+                    void* stream);
+int amss_l2norm_bwd(const float* v, const float* inv_norm, const float* dv, int64_t rows,
+                    int E, float* dz, void* stream);
+/* dbias[N] = column sums of dZ[M,N]                                                    */
+int amss_colsum(const float* dZ, int64_t M, int N, float* dbias, void* workspace,
+                size_t workspace_bytes, void* stream);
+size_t amss_colsum_workspace_bytes(int64_t M, int N);
+
+/* ------------------------------------------------------------------------------------ *
+ * Losses
+ * ------------------------------------------------------------------------------------ */
+/* DPCL.cost (models/dpcl.py:41-86), Y = one_hot(labels) with on/off = 1/0:
+ * mean_b ( ||V^T D V||_F - 2 ||V^T D Y||_F + ||Y^T D Y||_F ),  D = diag(1/sqrt(Y Y^T 1)).
+ * V[B,TF,E], labels_u8[B,TF] -> loss[1]; stats (workspace) is reused by the backward.   */
+size_t amss_dpcl_workspace_bytes(int B, int64_t TF, int E, int S);
+int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, int64_t TF, int E,
+                       int S, float* loss, void* workspace, size_t workspace_bytes,
+                       void* stream);
+/* dV[B,TF,E] = dloss * d(loss)/dV, using the workspace filled by the forward call.      */
+int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const float* dloss, int B,
+                       int64_t TF, int E, int S, float* dV, const void* workspace,
+                       void* stream);
+/* L41Model.cost, sampling=None (models/L41.py:47-63, 150-178):
+ * mean_{b,tf,s} -log sigmoid(y * <spk[b,s,:], emb[b,tf,:]>), y=+1 if labels==s else -1.
+ * spk[B,S,E] = (normalised) gathered speaker vectors.                                   */
+int amss_l41_loss_fwd(const float* emb, const uint8_t* labels, const float* spk, int B,
+                      int64_t TF, int E, int S, float* loss, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int amss_l41_loss_bwd(const float* emb, const uint8_t* labels, const float* spk,
+                      const float* dloss, int B, int64_t TF, int E, int S, float* demb,
+                      float* dspk, void* workspace, size_t workspace_bytes, void* stream);
+size_t amss_l41_workspace_bytes(int B, int64_t TF, int E, int S);
+/* labels_u8[B,T,F] = argmax_s |X_non_mix| from the front output (network.py:369-378):
+ * front_y[B(S+1),Tp,N]: rows [0,B) mixtures, rows B+b*S+s the sources.                  */
+int amss_plugged_labels(const float* front_y, int B, int S, int64_t TN, uint8_t* labels,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * K-means  (models/Kmeans_2.py:14-188) + mask application (models/network.py:554-582)
+ * ------------------------------------------------------------------------------------ */
+/* X[B,L,E]; init_idx_i32[B*tries,K] = rows of X used as initial centroids (the reference
+ * draws them on the host, Kmeans_2.py:61-65; the caller supplies them); notsilent_u8[B,L]
+ * or NULL (Kmeans_2.py:76-82); beta: NaN => hard assignments, else softmax(-beta*d^2).
+ * -> centroids[B,K,E]; labels_i32[B,L] (hard) or soft[B,L,K] (beta given);
+ *    inertia[B,tries] (optional) and best_try_i32[B] (optional).                        */
+size_t amss_kmeans_workspace_bytes(int B, int64_t L, int E, int K, int tries);
+int amss_kmeans_fit(const float* X, const int32_t* init_idx, const uint8_t* notsilent,
+                    int B, int64_t L, int E, int K, int tries, int iters, float beta,
+                    int normalize_input, int assign_at_end, float* centroids,
+                    int32_t* labels, float* soft, float* inertia, int32_t* best_try,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* notsilent = log10(max_L(latent)/latent) < threshold   (Kmeans_2.py:76-79)             */
+int amss_kmeans_silence_mask(const float* latent, int B, int64_t L, float threshold,
+                             uint8_t* notsilent, void* workspace, void* stream);
+/* separated[B*S,TF] = X_input[B,TF] * mask  (network.py:567-580)                        */
+int amss_apply_masks(const float* X_input, const int32_t* labels, const float* soft,
+                     int B, int S, int64_t TF, float* separated, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * Optimizer  (utils/ops.py:639-704 AMSGrad; models/network.py:181-192)
+ * ------------------------------------------------------------------------------------ */
+/* One fused pass over a flat parameter buffer: m,v EMA; vhat=max(vhat,v);
+ * p -= lr_t * m / (sqrt(vhat)+eps); lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) computed by the
+ * caller.  grad_scale multiplies g first (1/world_size and/or the global-norm clip).
+ * If grad_scale_dev != NULL it is read from the device and multiplied in.               */
+int amss_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat,
+                      int64_t n, float lr_t, float beta1, float beta2, float eps,
+                      float grad_scale, const float* grad_scale_dev, void* stream);
+/* sumsq[0] += sum g^2 (caller zeroes); clip factor = clip/max(sqrt(sumsq),clip).        */
+int amss_sumsq(const float* g, int64_t n, float* sumsq, void* workspace, void* stream);
+size_t amss_sumsq_workspace_bytes(void);
+int amss_clip_factor(const float* sumsq, float clip, float* factor, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
+ * Adapt pre-training losses (models/adapt.py:307-402, models/network.py:196-221)
+ * ------------------------------------------------------------------------------------ */
+/* Per (b,s) sums over L: tt=<s,s>, aa=<a,a>, ta=<s,a>, ee=<s-a,s-a> -> stats[B*S,4]     */
+int amss_wave_stats(const float* target, const float* approx, int R, int64_t L,
+                    float* stats, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMSS_H_ */

@@ -88,7 +88,10 @@ class KMeans:
             centroids = self.body(X, labels, notsilent)
             labels = self.get_labels(X, centroids, notsilent)
         inertia = self.get_inertia(X, centroids, notsilent).reshape(b, self.tries)
-        bests = torch.argmin(inertia, 1)
+        # tf.argmin (Kmeans_2.py:99) lowers to Eigen's ArgMin reducer: `if (v < best) best = v`
+        # starting from +max, so a NaN inertia (empty cluster -> 0/0) is never selected and the
+        # first minimum wins ties; an all-NaN row yields index 0.
+        bests = torch.argmin(torch.where(torch.isnan(inertia), torch.full_like(inertia, float("inf")), inertia), 1)
         index = bests + torch.arange(b) * self.tries
         centroids = centroids[index]
         if self.assign_at_end:

@@ -1,0 +1,448 @@
+"""GPU parity tests: every kernel family, called through the C ABI (ctypes -> libamss_b200.so),
+against the CPU oracle (oracle/) on the same seeded inputs.
+
+Tolerances: floating point within 1e-3 relative (north_star) -- written per test as
+`rel(a, b) = max|a-b| / max|b|`; integer / index outputs bit-exact on margin-safe inputs
+(near-ties are excluded explicitly and the excluded fraction is bounded)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf_ops as T
+from oracle import models as M
+from oracle.kmeans import KMeans as OracleKMeans, random_init_idx
+from oracle.amsgrad import AMSGrad as OracleAMSGrad
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-3
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import amss_b200  # noqa: F401
+    from amss_b200 import ops as o
+    return o
+
+
+def dev(x):
+    return torch.as_tensor(x).cuda().contiguous()
+
+
+# ------------------------------------------------------------------------------------------ gemm
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("shape", [(37, 53, 29), (128, 128, 16), (300, 1200, 257), (1, 7, 3)])
+def test_gemm_fp32(ops, ta, tb, shape):
+    Mm, N, K = shape
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn((K, Mm) if ta else (Mm, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double() + bias.double()
+    out = ops.gemm(dev(A), dev(B), dev(bias), bool(ta), bool(tb))
+    assert rel(out, ref) < 1e-5
+
+
+def test_gemm_strided_accumulate_swap(ops):
+    g = torch.Generator().manual_seed(2)
+    Tt, Bb, C, N = 5, 3, 20, 33
+    big = torch.randn(Tt * Bb, 2 * C, generator=g)
+    A = dev(big)[:, C:]                       # row-strided view (lda = 2C)
+    W = torch.randn(C, N, generator=g)
+    base = torch.randn(Tt * Bb, N, generator=g)
+    out = dev(base.clone())
+    ops.gemm(A, dev(W), None, out=out, accumulate=True)
+    ref = base.double() + big[:, C:].double() @ W.double()
+    assert rel(out, ref) < 1e-5
+    # time-major rows -> batch-major rows
+    out2 = ops.gemm(A, dev(W), None, out_swap=(Bb, Tt))
+    ref2 = (big[:, C:].double() @ W.double()).reshape(Tt, Bb, N).transpose(0, 1).reshape(Bb * Tt, N)
+    assert rel(out2, ref2) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ STFT
+def test_stft_matches_oracle(ops):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 4096, generator=g) * 0.05
+    ref = T.stft(x, 512, 256)
+    spec, mag = ops.stft(dev(x), 512, 256)
+    assert spec.shape == ref.shape == (3, 15, 257)
+    assert rel(torch.view_as_real(spec), torch.view_as_real(ref)) < 1e-4
+    assert rel(mag, ref.abs()) < 1e-4
+
+
+@pytest.mark.parametrize("frame,hop", [(64, 16), (256, 128), (1024, 256)])
+def test_stft_other_frames(ops, frame, hop):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 5000, generator=g)
+    ref = T.stft(x, frame, hop)
+    spec, mag = ops.stft(dev(x), frame, hop)
+    assert rel(torch.view_as_real(spec), torch.view_as_real(ref)) < 1e-4
+
+
+def test_stft_labels_bit_exact_off_ties(ops):
+    mix, nm, _ = M.synthetic_mixtures(2, 3, 8192, seed=5)
+    pre = M.separator_preprocessing(torch.tensor(mix), torch.tensor(nm), 512, 256, 1.0, 0.0)
+    labels, mag = ops.stft_labels(dev(nm), 512, 256, want_mag=True)
+    assert rel(mag, pre["X_non_mix"]) < 1e-4
+    srt = pre["X_non_mix"].sort(-1).values
+    margin = (srt[..., -1] - srt[..., -2]) > 1e-4 * srt[..., -1].clamp_min(1e-6)
+    assert margin.float().mean() > 0.9
+    assert torch.equal(labels.cpu().long()[margin], pre["argmax"][margin])
+
+
+def test_istft_masked_matches_oracle(ops):
+    mix, nm, _ = M.synthetic_mixtures(2, 2, 8192, seed=6)
+    pre = M.separator_preprocessing(torch.tensor(mix), torch.tensor(nm), 512, 256, 1.0, 0.0)
+    B, Tt, Fb = pre["X"].shape
+    labels = pre["argmax"].reshape(B, Tt * Fb)
+    sep, masks = M.separate(torch.zeros(B, Tt, Fb, 1), pre["X"], lambda V: labels, 2)
+    ref = M.postprocessing(sep, pre["stfts"], 2, 512, 256)
+    spec, _ = ops.stft(dev(mix), 512, 256)
+    out = ops.istft_masked(spec, 2, 512, 256, labels=dev(labels.to(torch.int32)))
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 1e-4
+    # soft masks
+    g = torch.Generator().manual_seed(7)
+    soft = torch.softmax(torch.randn(B, Tt * Fb, 2, generator=g), -1)
+    sep2 = (pre["X"].reshape(B, -1, 1) * soft).reshape(B, Tt, Fb, 2).permute(0, 3, 1, 2).reshape(B * 2, Tt, Fb)
+    ref2 = M.postprocessing(sep2, pre["stfts"], 2, 512, 256)
+    out2 = ops.istft_masked(spec, 2, 512, 256, masks=dev(soft))
+    assert rel(out2, ref2) < 1e-4
+
+
+def test_stft_istft_round_trip_full_size(ops):
+    """Size-independent property at the BASELINE size (L=64000): all-ones masks give back the
+    mixture on [hop, L-hop) (the TF inverse window does not reconstruct the edges)."""
+    mix, nm, _ = M.synthetic_mixtures(2, 2, 64000, seed=8)
+    spec, _ = ops.stft(dev(mix), 512, 256)
+    ones = torch.ones(2, spec.shape[1] * spec.shape[2], 1, device="cuda")
+    out = ops.istft_masked(spec, 1, 512, 256, masks=ones)
+    ref = torch.tensor(mix)
+    assert rel(out[:, 0, 256:-256], ref[:, 256:-256]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ BLSTM
+def _blstm_case(ops, B, Tt, I, H, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Tt, I, generator=g, dtype=torch.float64) * 0.5
+    ks = [(torch.rand(I + H, 4 * H, generator=g, dtype=torch.float64) * 2 - 1) * math.sqrt(6.0 / (I + 5 * H))
+          for _ in range(2)]
+    bs = [torch.randn(4 * H, generator=g, dtype=torch.float64) * 0.1 for _ in range(2)]
+    dy = torch.randn(B, Tt, 2 * H, generator=g, dtype=torch.float64)
+    leaves = [x] + ks + bs
+    for t in leaves:
+        t.requires_grad_(True)
+    y = T.blstm(x, ks[0], bs[0], ks[1], bs[1])
+    grads = torch.autograd.grad((y * dy).sum(), leaves)
+    f = lambda t: dev(t.detach().float())
+    x_tm = ops.transpose_01(f(x))
+    y_tm, saved = ops.blstm_fwd(x_tm, f(ks[0]), f(bs[0]), f(ks[1]), f(bs[1]))
+    y_gpu = ops.transpose_01(y_tm)
+    assert rel(y_gpu, y) < REL
+    dy_tm = ops.transpose_01(f(dy))
+    dx, dkf, dbf, dkb, dbb = ops.blstm_bwd(x_tm, f(ks[0]), f(ks[1]), y_tm, dy_tm, saved)
+    assert rel(ops.transpose_01(dx), grads[0]) < REL
+    assert rel(dkf, grads[1]) < REL and rel(dkb, grads[2]) < REL
+    assert rel(dbf, grads[3]) < REL and rel(dbb, grads[4]) < REL
+
+
+@pytest.mark.parametrize("B,Tt,I,H", [(3, 7, 11, 6), (1, 1, 5, 4), (4, 20, 129, 150), (70, 5, 33, 20)])
+def test_blstm_fwd_bwd_matches_oracle(ops, B, Tt, I, H):
+    _blstm_case(ops, B, Tt, I, H, seed=10 + B)
+
+
+def test_blstm_matches_oracle_reference_width(ops):
+    # the BASELINE width (layer_size 600 -> H=300 per direction), short sequence
+    _blstm_case(ops, 2, 12, 64, 300, seed=20)
+
+
+# ------------------------------------------------------------------------------------------ head / losses
+def test_l2norm_fwd_bwd(ops):
+    g = torch.Generator().manual_seed(30)
+    z = torch.randn(500, 40, generator=g, dtype=torch.float64)
+    z[7] = 0.0                                    # the clamped branch (sum z^2 < 1e-12)
+    z.requires_grad_(True)
+    dv = torch.randn(500, 40, generator=g, dtype=torch.float64)
+    v = T.l2_normalize(z, -1)
+    (gz,) = torch.autograd.grad((v * dv).sum(), z)
+    vg, inv = ops.l2norm_fwd(dev(z.detach().float()), 40)
+    assert rel(vg, v) < 1e-5
+    dz = ops.l2norm_bwd(vg, inv, dev(dv.float()), 40)
+    assert rel(dz, gz) < 1e-4
+
+
+def test_colsum(ops):
+    g = torch.Generator().manual_seed(31)
+    Z = torch.randn(1000, 77, generator=g)
+    assert rel(ops.colsum(dev(Z)), Z.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("S", [2, 3])
+def test_dpcl_loss_fwd_bwd(ops, S):
+    g = torch.Generator().manual_seed(32)
+    B, Tt, Fb, E = 3, 9, 33, 40
+    V = T.l2_normalize(torch.randn(B, Tt, Fb, E, generator=g, dtype=torch.float64), 3).requires_grad_(True)
+    lab = torch.randint(0, S, (B, Tt, Fb), generator=g)
+    y = torch.nn.functional.one_hot(lab, S).double()
+    cost = M.dpcl_cost(V, y)
+    (gV,) = torch.autograd.grad(cost, V)
+    Vg = dev(V.detach().float().reshape(B, Tt * Fb, E))
+    labg = dev(lab.to(torch.uint8).reshape(B, Tt * Fb))
+    loss, ws = ops.dpcl_loss_fwd(Vg, labg, S)
+    assert abs(float(loss) - float(cost)) < REL * abs(float(cost))
+    dV = ops.dpcl_loss_bwd(Vg, labg, S, torch.ones(1, device="cuda"), ws)
+    assert rel(dV, gV.reshape(B, Tt * Fb, E)) < REL
+
+
+def test_l41_loss_fwd_bwd(ops):
+    g = torch.Generator().manual_seed(33)
+    B, Tt, Fb, E, S = 2, 7, 21, 40, 2
+    emb = T.l2_normalize(torch.randn(B, Tt, Fb, E, generator=g, dtype=torch.float64), 3).requires_grad_(True)
+    lab = torch.randint(0, S, (B, Tt, Fb), generator=g)
+    y = torch.nn.functional.one_hot(lab, S).double() * 2 - 1
+    spk = T.l2_normalize(torch.randn(B, S, E, generator=g, dtype=torch.float64), -1).requires_grad_(True)
+    dot = (spk[:, None, None, :, :] * emb[:, :, :, None, :]).sum(4)
+    cost = (-torch.log(torch.sigmoid(y * dot))).mean(3).mean(0).mean()
+    gE, gS = torch.autograd.grad(cost, [emb, spk])
+    embg = dev(emb.detach().float().reshape(B, Tt * Fb, E))
+    labg = dev(lab.to(torch.uint8).reshape(B, Tt * Fb))
+    spkg = dev(spk.detach().float())
+    loss = ops.l41_loss_fwd(embg, labg, spkg)
+    assert abs(float(loss) - float(cost)) < REL * abs(float(cost))
+    demb, dspk = ops.l41_loss_bwd(embg, labg, spkg, torch.ones(1, device="cuda"))
+    assert rel(demb, gE.reshape(B, Tt * Fb, E)) < REL
+    assert rel(dspk, gS) < REL
+
+
+# ------------------------------------------------------------------------------------------ filterbank
+@pytest.mark.parametrize("L,W,N,pool,hop", [(2048, 64, 32, 64, 64), (3000, 100, 70, 128, 64), (4096, 1024, 256, 256, 256),
+                                            (1500, 33, 8, 300, 100)])
+def test_filterbank_analysis_max(ops, L, W, N, pool, hop):
+    g = torch.Generator().manual_seed(40)
+    x = torch.randn(3, L, generator=g) * 0.1
+    filt = torch.randn(W, N, generator=g) / math.sqrt(W)
+    X = T.conv2d_same_1d(x.double(), filt.double(), 1)
+    y_ref, am_ref = T.max_pool_with_argmax_1d(X, pool, hop)
+    y, am = ops.filterbank_analysis(dev(x), dev(filt), pool, hop, ops.AMSS_POOL_MAX)
+    assert y.shape == y_ref.shape
+    assert rel(y, y_ref) < 1e-4
+    am = am.cpu()
+    t = (am // N)
+    n = (am % N)
+    assert torch.equal(n, torch.arange(N).view(1, 1, N).expand_as(n))
+    # every picked position lies in its window and is a near-maximiser of the oracle's X
+    tp = torch.arange(y.shape[1]).view(1, -1, 1)
+    assert bool(((t >= tp * hop) & (t < tp * hop + pool)).all())
+    picked = torch.gather(X, 1, t)
+    assert float((y_ref - picked).abs().max()) < 1e-5 * float(y_ref.abs().max())
+    assert float((am == am_ref).float().mean()) > 0.999
+
+
+def test_filterbank_analysis_avg_and_stride(ops):
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 2100, generator=g) * 0.1
+    filt = torch.randn(50, 24, generator=g) / 7.0
+    X = T.conv2d_same_1d(x.double(), filt.double(), 1)
+    y, _ = ops.filterbank_analysis(dev(x), dev(filt), 64, 64, ops.AMSS_POOL_AVG)
+    assert rel(y, T.avg_pool_1d(X, 64)) < 1e-4
+    ys, _ = ops.filterbank_analysis(dev(x), dev(filt), 64, 48, ops.AMSS_POOL_STRIDE)
+    assert rel(ys, T.conv2d_same_1d(x.double(), filt.double(), 48)) < 1e-4
+
+
+def test_make_filter_fwd_bwd(ops):
+    g = torch.Generator().manual_seed(42)
+    w = torch.randn(64, generator=g, dtype=torch.float64).requires_grad_(True)
+    b = torch.randn(64, 16, generator=g, dtype=torch.float64).requires_grad_(True)
+    df = torch.randn(64, 16, generator=g, dtype=torch.float64)
+    f = w.abs().unsqueeze(1) * b
+    gw, gb = torch.autograd.grad((f * df).sum(), [w, b])
+    fg = ops.make_filter(dev(w.detach().float()), dev(b.detach().float()))
+    assert rel(fg, f) < 1e-6
+    dw, db = ops.make_filter_bwd(dev(w.detach().float()), dev(b.detach().float()), dev(df.float()))
+    assert rel(dw, gw) < 1e-5 and rel(db, gb) < 1e-5
+
+
+@pytest.mark.parametrize("L,W,N,pool,hop,B,S", [(2048, 64, 32, 64, 64, 2, 2), (3000, 100, 24, 128, 64, 1, 3),
+                                                (4096, 1024, 256, 256, 256, 1, 2)])
+def test_filterbank_synthesis_fwd_bwd_and_analysis_bwd(ops, L, W, N, pool, hop, B, S):
+    g = torch.Generator().manual_seed(43)
+    x = torch.randn(B * (S + 1), L, generator=g, dtype=torch.float64) * 0.1
+    filt = (torch.randn(W, N, generator=g, dtype=torch.float64) / math.sqrt(W)).requires_grad_(True)
+    filt2 = (torch.randn(W, N, generator=g, dtype=torch.float64) / math.sqrt(W)).requires_grad_(True)
+    X = T.conv2d_same_1d(x, filt, 1)
+    y, am = T.max_pool_with_argmax_1d(X, pool, hop)
+    Tp = y.shape[1]
+    vals = y[B:].detach().clone().requires_grad_(True)          # 'mask' separation == non-mix rows
+    am_mix = am[:B].unsqueeze(1).repeat(1, S, 1, 1).reshape(B * S, Tp, N)
+    U = T.unpool(vals, am_mix, L, N)
+    out = T.conv2d_transpose_same_1d(U, filt2, L, 1)
+    dout = torch.randn(B * S, L, generator=g, dtype=torch.float64)
+    gvals, gf2 = torch.autograd.grad((out * dout).sum(), [vals, filt2])
+    f = lambda t: dev(t.detach().float())
+    # use the ORACLE's argmax so that the comparison is not perturbed by near-ties
+    am_g = dev(am[:B])
+    og = ops.filterbank_synthesis(f(vals), am_g, f(filt2), B, S, L, pool, hop)
+    assert rel(og, out) < 1e-4
+    dv, df2 = ops.filterbank_synthesis_bwd(f(dout), f(vals), am_g, f(filt2), B, S)
+    assert rel(dv, gvals) < 1e-4
+    assert rel(df2, gf2) < 1e-4
+    # analysis backward w.r.t. the filter, through the arg-max
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (gf,) = torch.autograd.grad((y * dy).sum(), filt)
+    dfilt = ops.filterbank_analysis_bwd(f(x), f(dy), dev(am), W)
+    assert rel(dfilt, gf) < 1e-4
+
+
+def test_synthesis_is_adjoint_of_analysis_full_size(ops):
+    """<A x, y> = <x, A^T y> at the BASELINE size (L=64000, W=1024, N=256, pool=hop=256), using the
+    sparse structure: scatter y at the arg-max positions == synthesis with the same filter."""
+    g = torch.Generator().manual_seed(44)
+    L, W, N = 64000, 1024, 256
+    x = dev(torch.randn(1, L, generator=g) * 0.1)
+    filt = dev(torch.randn(W, N, generator=g) / 32.0)
+    y, am = ops.filterbank_analysis(x, filt, 256, 256, ops.AMSS_POOL_MAX)
+    c = dev(torch.randn(1, y.shape[1], N, generator=g))
+    lhs = float((y.double() * c.double()).sum())          # <P A x, c> with P = arg-max selection
+    back = ops.filterbank_synthesis(c, am, filt, 1, 1, L, 256, 256)
+    rhs = float((x.double() * back.double()).sum())       # <x, A^T P^T c>
+    assert abs(lhs - rhs) < 1e-3 * max(abs(lhs), 1.0)
+
+
+def test_plugged_labels_and_wave_stats(ops):
+    g = torch.Generator().manual_seed(45)
+    B, S, Tp, N = 3, 2, 10, 16
+    y = torch.randn(B * (S + 1), Tp, N, generator=g)
+    ref = M.separator_plugged_inputs(y, B, S, 1.0, 0.0)["argmax"]
+    lab = ops.plugged_labels(dev(y), B, S)
+    assert torch.equal(lab.cpu().long(), ref)
+    a = torch.randn(5, 3001, generator=g)
+    b = torch.randn(5, 3001, generator=g)
+    st = ops.wave_stats(dev(a), dev(b)).cpu().double()
+    ref4 = torch.stack([(a.double() ** 2).sum(1), (b.double() ** 2).sum(1), (a.double() * b.double()).sum(1),
+                        ((a.double() - b.double()) ** 2).sum(1)], 1)
+    assert rel(st, ref4) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ k-means
+def _blobs(B, L, E, K, seed, spread=0.05):
+    rng = np.random.RandomState(seed)
+    X = np.zeros((B, L, E), np.float32)
+    truth = np.zeros((B, L), np.int64)
+    for b in range(B):
+        centers = rng.randn(K, E)
+        centers /= np.linalg.norm(centers, axis=1, keepdims=True)
+        truth[b] = rng.randint(0, K, L)
+        X[b] = centers[truth[b]] + spread * rng.randn(L, E)
+    return X, truth
+
+
+def _same_partition(a, b, K):
+    pairs = set(zip(a.tolist(), b.tolist()))
+    return len(pairs) == len({p[0] for p in pairs}) == len({p[1] for p in pairs})
+
+
+@pytest.mark.parametrize("K,tries,with_silence,assign_at_end", [(2, 1, False, True), (3, 4, False, True),
+                                                                (2, 3, True, True), (3, 2, True, False)])
+def test_kmeans_hard_bit_exact(ops, K, tries, with_silence, assign_at_end):
+    B, L, E, iters = 3, 3000, 40, 6
+    X, _ = _blobs(B, L, E, K, seed=50 + K)
+    rng = np.random.RandomState(60)
+    idx = random_init_idx(B * tries, L, K, rng)
+    latent = None
+    ns = None
+    if with_silence:
+        latent = np.abs(rng.randn(B, L)).astype(np.float32) + 1e-3
+        latent[:, ::7] *= 1e-4                                 # silent bins
+    okm = OracleKMeans(K, tries, iters, True, None, 2.0, assign_at_end)
+    c_ref, l_ref = okm.fit(torch.tensor(X), idx, None if latent is None else torch.tensor(latent))
+    if with_silence:
+        ns = ops.kmeans_silence_mask(dev(latent), 2.0)
+        ref_ns = (T.log10(torch.tensor(latent).max(-1, keepdim=True).values / torch.tensor(latent)) < 2.0)
+        assert torch.equal(ns.cpu().bool(), ref_ns)
+    cent, labels, inertia, best = ops.kmeans_fit(dev(X), dev(idx), K, tries, iters, None, ns, True, assign_at_end)
+    ok = ~torch.isnan(okm.last_inertia)
+    assert torch.equal(torch.isnan(inertia.cpu()), ~ok)
+    assert rel(inertia.cpu()[ok], okm.last_inertia[ok]) < 1e-4
+    best = best.cpu().long()
+    for b in range(B):
+        if int(best[b]) == int(okm.last_best[b]):
+            assert rel(cent[b], c_ref[b]) < 1e-4
+            assert torch.equal(labels[b].cpu(), l_ref[b])      # bit-exact hard assignments
+        else:
+            # two tries converged to the same optimum: inertias tie to rounding, the chosen try (and
+            # so the numbering of the clusters) may differ -- the partition must still be identical
+            i_ref = okm.last_inertia[b]
+            assert abs(float(i_ref[best[b]] - i_ref[okm.last_best[b]])) < 1e-5 * float(i_ref[okm.last_best[b]])
+            assert _same_partition(labels[b].cpu(), l_ref[b], K)
+
+
+def test_kmeans_soft_matches_oracle(ops):
+    B, L, E, K, tries, iters = 2, 2000, 40, 2, 3, 5
+    X, _ = _blobs(B, L, E, K, seed=70, spread=0.2)
+    idx = random_init_idx(B * tries, L, K, np.random.RandomState(71))
+    okm = OracleKMeans(K, tries, iters, True, 5.0, 2.0, True)
+    c_ref, l_ref = okm.fit(torch.tensor(X), idx)
+    cent, soft, inertia, best = ops.kmeans_fit(dev(X), dev(idx), K, tries, iters, 5.0, None, True, True)
+    assert torch.equal(best.cpu().long(), okm.last_best)
+    assert rel(cent, c_ref) < 1e-4
+    assert rel(soft, l_ref) < 1e-4
+
+
+def test_kmeans_recovers_blobs_reference_smoke(ops):
+    """Mirrors the reference's own smoke block (models/Kmeans_2.py:197-219): well-separated blobs,
+    4 clusters, 40 features, 10 tries x 10 iterations -> the generating partition (up to a
+    permutation of the labels)."""
+    B, L, E, K = 3, 1000, 40, 4
+    X, truth = _blobs(B, L, E, K, seed=80, spread=0.02)
+    idx = random_init_idx(B * 10, L, K, np.random.RandomState(81))
+    _, labels, _, _ = ops.kmeans_fit(dev(X), dev(idx), K, 10, 10, None, None, True, True)
+    labels = labels.cpu().numpy()
+    for b in range(B):
+        mapping = {}
+        for l, t in zip(labels[b], truth[b]):
+            assert mapping.setdefault(int(l), int(t)) == int(t)
+        assert len(set(mapping.values())) == K
+
+
+def test_kmeans_full_size_idempotent(ops):
+    """BASELINE size (TF = 63993 bins, E = 40, K = 3, 10 tries): a converged fit is a fixed point
+    -- re-running one more iteration from the returned centroids reproduces labels exactly."""
+    B, L, E, K = 2, 63993, 40, 3
+    X, truth = _blobs(B, L, E, K, seed=90, spread=0.05)
+    idx = random_init_idx(B * 10, L, K, np.random.RandomState(91))
+    cent, labels, inertia, best = ops.kmeans_fit(dev(X), dev(idx), K, 10, 10, None, None, True, True)
+    assert bool(torch.isfinite(inertia).all())
+    Xn = torch.tensor(X) / torch.tensor(X).norm(dim=-1, keepdim=True)
+    d = ((Xn.unsqueeze(2) - cent.cpu().unsqueeze(1)) ** 2).sum(-1)
+    srt = d.sort(-1).values
+    safe = (srt[..., 1] - srt[..., 0]) > 1e-4
+    assert torch.equal(d.argmin(-1)[safe].int(), labels.cpu()[safe])
+    masks = ops.apply_masks(dev(np.ones((B, L), np.float32)), K, labels=labels)
+    assert float(masks.reshape(B, K, L).sum(1).min()) == 1.0 and float(masks.sum()) == B * L
+
+
+# ------------------------------------------------------------------------------------------ optimizer
+def test_amsgrad_matches_oracle(ops):
+    g = torch.Generator().manual_seed(100)
+    n = 10007
+    p0 = torch.randn(n, generator=g)
+    params = {"p": p0.clone()}
+    opt = OracleAMSGrad(params, lr=1e-3, clip=0.5)
+    p = dev(p0.clone())
+    m, v, vh = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g)
+        opt.step({"p": grad})
+        gd = dev(grad)
+        fac = ops.global_norm_clip_factor(gd, 0.5)
+        ops.amsgrad_step(p, gd, m, v, vh, ops.amsgrad_lr_t(1e-3, 0.9, 0.99, step), 0.9, 0.99, 1e-3, 1.0, fac)
+    assert rel(p, params["p"]) < 1e-5
