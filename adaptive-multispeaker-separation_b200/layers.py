@@ -1,0 +1,333 @@
+"""The reference's layer protocol on top of the CUDA library: any object with ``f_prop(x)``,
+composed by ``f_props(layers, x)`` (reference utils/ops.py:82-85), plus the parameter store that
+keeps every trainable tensor inside ONE flat fp32 buffer (so AMSGrad is a single fused kernel and
+the data-parallel gradient exchange is a single NCCL all-reduce).
+
+Each layer's forward/backward is a kernel of libamss_b200.so wrapped in a torch.autograd.Function;
+torch only records the tape.  Variable names follow the reference's TF checkpoint names
+(SURVEY.md section 5): ``prediction/forward_BLSTM_0/rnn/basic_lstm_cell/kernel`` etc.
+"""
+import math
+
+import torch
+
+from . import ops
+from ._lib import AMSS_PREC_FP32
+
+
+# --------------------------------------------------------------------------------------------
+# parameters
+# --------------------------------------------------------------------------------------------
+class ParamStore:
+    """Flat parameter / gradient buffers with named views.
+
+    register() before finalize(); after finalize() ``self[name]`` is a torch.nn.Parameter that
+    views ``self.flat`` and whose ``.grad`` views ``self.grad_flat``."""
+
+    def __init__(self, device="cuda", seed=42):
+        self.device = torch.device(device)
+        self.gen = torch.Generator().manual_seed(seed)      # reference: seed 42 (config.py:7)
+        self._specs = []            # (name, shape, init tensor (cpu), trainable)
+        self.params = {}
+        self.flat = None
+        self.grad_flat = None
+        self._slices = {}
+
+    def register(self, name, init, trainable=True):
+        if self.flat is not None:
+            raise RuntimeError("ParamStore already finalized")
+        if any(n == name for n, *_ in self._specs):
+            raise KeyError(f"duplicate parameter {name}")
+        self._specs.append((name, tuple(init.shape), init.to(torch.float32), trainable))
+
+    def finalize(self):
+        # trainable parameters first so that the optimizer / all-reduce see one contiguous range
+        specs = [s for s in self._specs if s[3]] + [s for s in self._specs if not s[3]]
+        off = 0
+        self.n_trainable = 0
+        for name, shape, init, tr in specs:
+            n = int(math.prod(shape))
+            self._slices[name] = (off, n, shape, tr)
+            off += (n + 3) // 4 * 4                          # keep every view 16-byte aligned
+            if tr:
+                self.n_trainable = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.grad_flat = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
+        for name, shape, init, tr in specs:
+            o, n, _, _ = self._slices[name]
+            self.flat[o:o + n].copy_(init.reshape(-1))
+            p = torch.nn.Parameter(self.flat[o:o + n].view(shape), requires_grad=tr)
+            if tr:
+                p.grad = self.grad_flat[o:o + n].view(shape)
+            self.params[name] = p
+        return self
+
+    def __getitem__(self, name):
+        return self.params[name]
+
+    def names(self):
+        return list(self.params)
+
+    def set_trainable(self, predicate):
+        """Freeze / unfreeze by name (the reference's freeze_all_with / --train substrings).
+        Frozen parameters keep their slot in the flat buffer; their gradient slice stays zero."""
+        for name, p in self.params.items():
+            o, n, shape, tr = self._slices[name]
+            if not tr:
+                continue
+            p.requires_grad_(bool(predicate(name)))
+
+    def state_dict(self):
+        return {k: v.detach().cpu().clone() for k, v in self.params.items()}
+
+    def load_state_dict(self, sd, strict=True):
+        for k, v in sd.items():
+            if k not in self.params:
+                if strict:
+                    raise KeyError(k)
+                continue
+            self.params[k].data.copy_(torch.as_tensor(v).to(self.device))
+
+    # initialisers (distribution-faithful to the reference; TF's RNG stream cannot be matched)
+    def glorot(self, shape, fan_in, fan_out):
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return (torch.rand(shape, generator=self.gen, dtype=torch.float64) * 2 - 1).mul(lim).float()
+
+
+# --------------------------------------------------------------------------------------------
+# autograd wrappers (forward and backward are both library kernels)
+# --------------------------------------------------------------------------------------------
+class _BLSTMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kf, bf, kb, bb, precision):
+        need_bwd = any(ctx.needs_input_grad)
+        x_tm = ops.transpose_01(x.contiguous())
+        y_tm, saved = ops.blstm_fwd(x_tm, kf, bf, kb, bb, 1.0, precision, save_for_backward=need_bwd)
+        if need_bwd:
+            ctx.save_for_backward(x_tm, kf, kb, y_tm, saved)
+        ctx.precision = precision
+        return ops.transpose_01(y_tm)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_tm, kf, kb, y_tm, saved = ctx.saved_tensors
+        dy_tm = ops.transpose_01(dy.contiguous())
+        dx, dkf, dbf, dkb, dbb = ops.blstm_bwd(x_tm, kf, kb, y_tm, dy_tm, saved, ctx.precision,
+                                               need_dx=ctx.needs_input_grad[0])
+        return (ops.transpose_01(dx) if dx is not None else None), dkf, dbf, dkb, dbb, None
+
+
+class _DenseFn(torch.autograd.Function):
+    """y[M,N] = x[M,K] @ W[K,N] + b   (tf.nn.conv1d with a [1,K,N] filter)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, precision):
+        ctx.save_for_backward(x, W)
+        ctx.precision = precision
+        return ops.gemm(x, W, b, precision=precision)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.gemm(dy, W, None, transb=True, precision=ctx.precision) if ctx.needs_input_grad[0] else None
+        dW = ops.gemm(x, dy, None, transa=True, precision=ctx.precision) if ctx.needs_input_grad[1] else None
+        db = ops.colsum(dy) if ctx.needs_input_grad[2] else None
+        return dx, dW, db, None
+
+
+class _L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, E):
+        v, inv = ops.l2norm_fwd(z.contiguous(), E)
+        ctx.save_for_backward(v, inv)
+        ctx.E = E
+        return v
+
+    @staticmethod
+    def backward(ctx, dv):
+        v, inv = ctx.saved_tensors
+        return ops.l2norm_bwd(v, inv, dv.contiguous(), ctx.E), None
+
+
+class _DPCLLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V, labels, S):
+        loss, ws = ops.dpcl_loss_fwd(V, labels, S)
+        ctx.save_for_backward(V, labels, ws)
+        ctx.S = S
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        V, labels, ws = ctx.saved_tensors
+        return ops.dpcl_loss_bwd(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws), None, None
+
+
+class _L41LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, labels, spk):
+        ctx.save_for_backward(emb, labels, spk)
+        return ops.l41_loss_fwd(emb, labels, spk).view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        emb, labels, spk = ctx.saved_tensors
+        demb, dspk = ops.l41_loss_bwd(emb, labels, spk, dloss.reshape(1).contiguous())
+        return demb, None, dspk
+
+
+class _MakeFilterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, window, bases):
+        ctx.save_for_backward(window, bases)
+        return ops.make_filter(window, bases)
+
+    @staticmethod
+    def backward(ctx, dfilt):
+        window, bases = ctx.saved_tensors
+        return ops.make_filter_bwd(window, bases, dfilt.contiguous())
+
+
+class _AnalysisFn(torch.autograd.Function):
+    """conv2d SAME stride 1 + max_pool_with_argmax, fused (reference models/adapt.py:115-117).
+    Gradient flows to the filter only (the waveform is data)."""
+
+    @staticmethod
+    def forward(ctx, x, filt, pool, hop, precision):
+        y, am = ops.filterbank_analysis(x, filt, pool, hop, ops.AMSS_POOL_MAX, precision)
+        ctx.save_for_backward(x, am)
+        ctx.W = filt.shape[0]
+        ctx.mark_non_differentiable(am)
+        return y, am
+
+    @staticmethod
+    def backward(ctx, dy, _dam):
+        x, am = ctx.saved_tensors
+        return None, ops.filterbank_analysis_bwd(x, dy.contiguous(), am, ctx.W), None, None, None
+
+
+class _SynthesisFn(torch.autograd.Function):
+    """unpool + conv2d_transpose fused as a sparse overlap-add (reference models/adapt.py:205-252)."""
+
+    @staticmethod
+    def forward(ctx, vals, argmax_mix, filt2, B, S, L, pool, hop):
+        ctx.save_for_backward(vals, argmax_mix, filt2)
+        ctx.dims = (B, S)
+        return ops.filterbank_synthesis(vals, argmax_mix, filt2, B, S, L, pool, hop)
+
+    @staticmethod
+    def backward(ctx, dout):
+        vals, am, filt2 = ctx.saved_tensors
+        B, S = ctx.dims
+        dvals, dfilt2 = ops.filterbank_synthesis_bwd(dout.contiguous(), vals, am, filt2, B, S,
+                                                     ctx.needs_input_grad[0], ctx.needs_input_grad[2])
+        return dvals, None, dfilt2, None, None, None, None, None
+
+
+def blstm(x, kf, bf, kb, bb, precision=AMSS_PREC_FP32):
+    return _BLSTMFn.apply(x, kf, bf, kb, bb, precision)
+
+
+def dense(x, W, b, precision=AMSS_PREC_FP32):
+    return _DenseFn.apply(x, W, b, precision)
+
+
+def l2_normalize(z, E):
+    return _L2NormFn.apply(z, E)
+
+
+def dpcl_loss(V, labels, S):
+    return _DPCLLossFn.apply(V, labels, S)
+
+
+def l41_loss(emb, labels, spk):
+    return _L41LossFn.apply(emb, labels, spk)
+
+
+def make_filter(window, bases):
+    return _MakeFilterFn.apply(window, bases)
+
+
+def analysis(x, filt, pool, hop, precision=AMSS_PREC_FP32):
+    return _AnalysisFn.apply(x, filt, pool, hop, precision)
+
+
+def synthesis(vals, argmax_mix, filt2, B, S, L, pool, hop):
+    return _SynthesisFn.apply(vals, argmax_mix, filt2, B, S, L, pool, hop)
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's layer classes (utils/ops.py)
+# --------------------------------------------------------------------------------------------
+def f_props(layers, x):
+    """utils/ops.py:82-85."""
+    for layer in layers:
+        x = layer.f_prop(x)
+    return x
+
+
+class BLSTM:
+    """utils/ops.py:358-383.  hid_dim is the concatenated width: each direction has hid_dim//2 cells.
+    Variables: <scope>/{forward,backward}_<name>/rnn/basic_lstm_cell/{kernel,bias}."""
+
+    def __init__(self, hid_dim, name, drop_val=0.0, *, store, scope, in_dim, precision=AMSS_PREC_FP32):
+        if drop_val != 0.0:
+            raise NotImplementedError("recurrent dropout > 0 is outside the hot path (default 0.0, utils/trainer.py:77-78)")
+        self.hid_dim, self.name, self.precision = hid_dim, name, precision
+        H = hid_dim // 2
+        self.keys = []
+        for d in ("forward", "backward"):
+            base = f"{scope}/{d}_{name}/rnn/basic_lstm_cell"
+            store.register(base + "/kernel", store.glorot((in_dim + H, 4 * H), in_dim + H, 4 * H))
+            store.register(base + "/bias", torch.zeros(4 * H))
+            self.keys += [base + "/kernel", base + "/bias"]
+        self.store = store
+
+    def f_prop(self, x):
+        kf, bf, kb, bb = (self.store[k] for k in self.keys)
+        return blstm(x, kf, bf, kb, bb, self.precision)
+
+
+class Conv1D:
+    """utils/ops.py:486-503 with filter_shape [1, in, out]: a per-frame dense layer.
+    reference_scale=True reproduces the reference's (very wide) uniform init range."""
+
+    def __init__(self, filter_shape, *, store, scope, name="Conv1D", precision=AMSS_PREC_FP32, reference_scale=False):
+        assert filter_shape[0] == 1, "only kernel size 1 is on the hot path"
+        _, cin, cout = filter_shape
+        if reference_scale:
+            fan = math.sqrt(2.0 / float(cin + cout))
+            lim = math.sqrt(2.0 / fan)
+        else:
+            lim = math.sqrt(6.0 / (cin + cout))
+        W = (torch.rand((cin, cout), generator=store.gen, dtype=torch.float64) * 2 - 1).mul(lim).float()
+        store.register(f"{scope}/W", W)
+        store.register(f"{scope}/b", torch.zeros(cout))
+        self.store, self.scope, self.precision = store, scope, precision
+
+    def f_prop(self, x):
+        B, Tt, C = x.shape
+        y = dense(x.reshape(B * Tt, C), self.store[f"{self.scope}/W"], self.store[f"{self.scope}/b"], self.precision)
+        return y.view(B, Tt, -1)
+
+
+class Reshape:
+    """utils/ops.py:310-316."""
+
+    def __init__(self, shape, name="Reshape"):
+        self.shape, self.name = shape, name
+
+    def f_prop(self, x):
+        return x.reshape(self.shape)
+
+
+class Normalize:
+    """utils/ops.py:318-324: tf.nn.l2_normalize over the (last) axis."""
+
+    def __init__(self, axis, name="Normalize"):
+        self.axis, self.name = axis, name
+
+    def f_prop(self, x):
+        assert self.axis in (-1, x.dim() - 1), "l2_normalize is implemented over the innermost axis"
+        return l2_normalize(x, x.shape[-1])

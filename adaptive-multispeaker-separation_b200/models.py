@@ -1,0 +1,308 @@
+"""Host-side mirror of the reference's model classes for the hot path: Adapt (models/adapt.py),
+Separator / DPCL / L41Model (models/network.py, models/dpcl.py, models/L41.py) and KMeans
+(models/Kmeans_2.py).  Constructors take the reference's flat kwargs dict (CLI flag names,
+utils/trainer.py:17-166); methods keep the reference's property names (front, separator, back,
+cost, preprocessing, prediction, separate, postprocessing).
+
+The reference builds a TF graph once and runs it with sess.run; here the same nodes are plain
+methods that launch the library's kernels on torch CUDA tensors (eager, taped by torch.autograd).
+"""
+import itertools
+import math
+
+import numpy as np
+import torch
+
+from . import layers as L
+from . import ops
+from ._lib import AMSS_PREC_FP32, AMSS_PREC_BF16, AmssError
+
+DEFAULTS = dict(
+    # common (utils/trainer.py:17-48)
+    chunk_size=20480, nb_speakers=2, batch_size=64, epochs=10, learning_rate=0.1, optimizer="Adam",
+    decay_epoch=50, gradient_norm_clip=0.0, validation_step=1000, dataset_normalize=False,
+    # separator (utils/trainer.py:57-109)
+    normalize_separator="None", abs_input=False, pre_func="None", silence_mask_db=0, nb_layers=3, layer_size=600,
+    embedding_size=40, no_normalize=True, recurrent_dropout=0.0, nb_tries=10, nb_steps=10, beta_kmeans=None,
+    threshold=2.0, with_silence=False, end_assign=False, silence_loss=False, threshold_silence_loss=2.0,
+    function_mask="None", sampling=None, ns_rate=0.1, ns_method="random", add_dilated=False,
+    tot_speakers=251,
+    # enhance (utils/trainer.py:122-132)
+    normalize_enhance=False, nb_layers_enhance=3, layer_size_enhance=600, nonlinearity="softmax",
+    recurrent_dropout_enhance=0.0,
+    # adapt (utils/trainer.py:134-166)
+    filters=512, max_pool=512, with_max_pool=False, with_average_pool=False, regularization=1e-4, beta=1e-2,
+    sparsity=0.01, overlap_coef=0.001, overlap_value=0.1, non_negativity=0.0, loss="sdr", separation="perfect",
+    pretraining=True,
+    # this implementation
+    precision="fp32", seed=42, reference_init=False,
+)
+
+
+def _prec(v):
+    if v in (AMSS_PREC_FP32, AMSS_PREC_BF16):
+        return v
+    return {"fp32": AMSS_PREC_FP32, "bf16": AMSS_PREC_BF16}[str(v)]
+
+
+class Network:
+    """models/network.py:12-63 -- holds the flat kwargs and the shared parameter store."""
+
+    def __init__(self, store=None, **kwargs):
+        unknown = set(kwargs) - set(DEFAULTS) - {"window_size", "hop_size", "type", "pipeline", "mix", "non_mix",
+                                                  "ind", "model_folder", "sex", "train", "dataset", "men", "women",
+                                                  "no_random_picking", "mask_a", "mask_b"}
+        if unknown:
+            raise KeyError(f"unknown arguments: {sorted(unknown)}")
+        self.args = dict(DEFAULTS)
+        self.args.update(kwargs)
+        self.S = self.args["nb_speakers"]
+        self.precision = _prec(self.args["precision"])
+        self.store = store if store is not None else L.ParamStore(seed=self.args["seed"])
+        self._owns_store = store is None
+
+    def finalize(self):
+        if self.store.flat is None:
+            self.store.finalize()
+        return self
+
+    # the reference's freeze_all_with(prefix) (models/network.py:276-289)
+    def freeze_all_with(self, prefix):
+        self.store.set_trainable(lambda n, p=prefix: not n.startswith(p) and self.store[n].requires_grad)
+
+    def freeze_all_except(self, *prefixes):
+        self.store.set_trainable(lambda n: any(n.startswith(p) for p in prefixes))
+
+
+# =================================================================================================
+# Adaptive front / back end                                                    models/adapt.py
+# =================================================================================================
+class Adapt(Network):
+    def __init__(self, store=None, **kwargs):
+        kwargs.setdefault("window_size", 1024)
+        kwargs.setdefault("hop_size", 256)
+        super().__init__(store, **kwargs)
+        a = self.args
+        self.N, self.max_pool_value, self.window = a["filters"], a["max_pool"], a["window_size"]
+        self.hop_size, self.pretraining = a["hop_size"], a["pretraining"]
+        self.l, self.beta, self.p = a["regularization"], a["beta"], a["sparsity"]
+        self.overlap_coef, self.loss, self.separation = a["overlap_coef"], a["loss"], a["separation"]
+        self.with_max_pool, self.with_average_pool = a["with_max_pool"], a["with_average_pool"]
+        self.non_negativity = a["non_negativity"]
+        st, W, N = self.store, self.window, self.N
+        # xavier_initializer_conv2d variables (adapt.py:104-105, :232-233)
+        st.register("front/window/w", st.glorot((W,), W, 1))
+        st.register("front/bases/bases", st.glorot((W, N), W, N))
+        st.register("back/window/value", st.glorot((W,), W, 1))
+        st.register("back/bases/value", st.glorot((W, N), W, N))
+        self.sepNet = None
+        if self._owns_store and self.pretraining:
+            self.finalize()
+
+    @property
+    def pool_mode(self):
+        if self.with_max_pool:
+            return ops.AMSS_POOL_MAX
+        return ops.AMSS_POOL_AVG if self.with_average_pool else ops.AMSS_POOL_STRIDE
+
+    def conv_filter(self, scope="front"):
+        if scope == "front":
+            return L.make_filter(self.store["front/window/w"], self.store["front/bases/bases"])
+        return L.make_filter(self.store["back/window/value"], self.store["back/bases/value"])
+
+    # adapt.py:41-48 + 95-134
+    def front(self, x_mix, x_non_mix):
+        """-> (y [B(S+1),Tp,N], argmax int64 or None).  Mixture rows first, then the B*S sources."""
+        B, S, Lw = x_non_mix.shape
+        x = torch.cat([x_mix, x_non_mix.reshape(B * S, Lw)], 0).contiguous()
+        filt = self.conv_filter("front")
+        if self.with_max_pool:
+            y, am = L.analysis(x, filt, self.max_pool_value, self.hop_size, self.precision)
+        else:
+            if filt.requires_grad:
+                raise AmssError("avg-pool / strided front ends are inference-only here (no filter gradient kernel)")
+            y, am = ops.filterbank_analysis(x, filt.detach(), self.max_pool_value, self.hop_size, self.pool_mode,
+                                            AMSS_PREC_FP32)
+        return y, am
+
+    # adapt.py:162-196 (pretraining separator)
+    def separator(self, y, B):
+        S = self.S
+        Tp, N = y.shape[1], y.shape[2]
+        input_mix = y[:B].reshape(B, 1, Tp, N)
+        input_non_mix = y[B:].reshape(B, S, Tp, N)
+        if self.separation == "mask":
+            out = input_mix * (input_non_mix / input_mix)
+        else:
+            out = input_mix - (input_non_mix.sum(1, keepdim=True) - input_non_mix)
+        return out.reshape(B * S, Tp, N)
+
+    # adapt.py:205-252
+    def back(self, sep_out, argmax, B, Lw):
+        if not self.with_max_pool:
+            raise AmssError("back(): only the max-pool (unpool + transposed conv) synthesis is on the hot path")
+        filt2 = self.conv_filter("back")
+        out = L.synthesis(sep_out.contiguous(), argmax[:B].contiguous(), filt2, B, self.S, Lw, self.max_pool_value,
+                          self.hop_size)
+        return out.reshape(B, self.S, Lw)
+
+    def connect_front(self, separator_class, **extra):
+        """adapt.py:440-441 -- plug a Separator subclass on the front output (plugged=True)."""
+        args = dict(self.args)
+        args.update(extra)
+        self.sepNet = separator_class(plugged=True, store=self.store, F=self.N, **args)
+        return self.sepNet
+
+
+# =================================================================================================
+# Separator (STFT or plugged on the adaptive front)                          models/network.py:313-723
+# =================================================================================================
+class Separator(Network):
+    mask_a, mask_b = 1.0, 0.0
+
+    def __init__(self, plugged=False, store=None, F=None, **kwargs):
+        kwargs.pop("mask_a", None), kwargs.pop("mask_b", None)
+        if not plugged:
+            kwargs.setdefault("window_size", 512)
+            kwargs.setdefault("hop_size", 256)
+        super().__init__(store, **kwargs)
+        a = self.args
+        self.plugged = plugged
+        self.window_size, self.hop_size = a["window_size"], a["hop_size"]
+        self.F = F if plugged else self.window_size // 2 + 1
+        self.layer_size, self.embedding_size = a["layer_size"], a["embedding_size"]
+        self.normalize = a["no_normalize"]          # store_false flag: True = normalise (network.py:322)
+        self.nb_layers = a["nb_layers"]
+        self.num_speakers = a["tot_speakers"]
+        self.beta, self.threshold = a["beta_kmeans"], a["threshold"]
+        self.with_silence, self.nb_tries, self.nb_steps = a["with_silence"], a["nb_tries"], a["nb_steps"]
+        self.abs_input = a["abs_input"]
+        for flag, off in (("normalize_separator", "None"), ("pre_func", "None"), ("function_mask", "None")):
+            if a[flag] not in (off, None):
+                raise NotImplementedError(f"--{flag} {a[flag]} is outside the hot path (default off, SURVEY 8a11)")
+        if a["silence_loss"] or a["silence_mask_db"] or a["add_dilated"] or a["sampling"] is not None:
+            raise NotImplementedError("silence_loss / silence_mask_db / add_dilated / sampling are outside the hot path")
+        self._build_prediction()
+
+    # DPCL.prediction / L41Model.prediction trunk (dpcl.py:19-39, L41.py:21-45)
+    def _build_prediction(self):
+        st, prec = self.store, self.precision
+        in_dim = self.F
+        self.layers = []
+        for i in range(self.nb_layers):
+            self.layers.append(L.BLSTM(self.layer_size, name=f"BLSTM_{i}", drop_val=self.args["recurrent_dropout"],
+                                       store=st, scope="prediction", in_dim=in_dim, precision=prec))
+            in_dim = 2 * (self.layer_size // 2)
+        self.layers.append(L.Conv1D([1, in_dim, self.embedding_size * self.F], store=st, scope="prediction",
+                                    precision=prec, reference_scale=self.args["reference_init"]))
+
+    # network.py:480-502
+    def preprocessing(self, x_mix, x_non_mix, want_mag_non_mix=False):
+        spec, X = ops.stft(x_mix.contiguous(), self.window_size, self.hop_size)
+        labels, mag_nm = ops.stft_labels(x_non_mix.contiguous(), self.window_size, self.hop_size, want_mag_non_mix)
+        return {"stfts": spec, "X": X, "labels": labels, "X_non_mix": mag_nm}
+
+    # network.py:357-400 (plugged branch, default flags)
+    def plugged_inputs(self, front_y, B):
+        X = front_y[:B]
+        labels = ops.plugged_labels(front_y.contiguous(), B, self.S)
+        return {"X": X.abs() if self.abs_input else X, "labels": labels, "X_raw": X}
+
+    def prediction(self, X):
+        """X [B,T,F] -> embeddings [B,T,F,E] (L2-normalised over E unless --no_normalize)."""
+        B, Tt, Fb = X.shape
+        z = L.f_props(self.layers, X)
+        z = L.Reshape([B, Tt, Fb, self.embedding_size]).f_prop(z)
+        return L.Normalize(3).f_prop(z) if self.normalize else z
+
+    # network.py:554-582
+    def separate(self, V, X_input, init_idx=None, rng=None):
+        """V [B,T,F,E], X_input [B,T,F] -> (separated [B*S,T,F], labels int32 [B,TF] | soft [B,TF,S])."""
+        B, Tt, Fb, E = V.shape
+        emb = V.detach().reshape(B, Tt * Fb, E).contiguous()
+        km = KMeans(nb_clusters=self.S, nb_tries=self.nb_tries, nb_iterations=self.nb_steps, beta=self.beta,
+                    latent_space_tensor=X_input.abs().reshape(B, Tt * Fb) if self.with_silence else None,
+                    threshold=self.threshold, assign_at_end=self.args["end_assign"], rng=rng)
+        _, lab = km.fit(emb, init_idx)
+        self.kmeans = km
+        Xf = X_input.reshape(B, Tt * Fb).contiguous()
+        sep = ops.apply_masks(Xf, self.S, labels=lab) if self.beta is None else ops.apply_masks(Xf, self.S, soft=lab)
+        return sep.view(B * self.S, Tt, Fb), lab
+
+    # network.py:584-607
+    def postprocessing(self, stfts, labels_or_masks):
+        if self.beta is None:
+            return ops.istft_masked(stfts, self.S, self.window_size, self.hop_size, labels=labels_or_masks)
+        return ops.istft_masked(stfts, self.S, self.window_size, self.hop_size, masks=labels_or_masks)
+
+
+class DPCL(Separator):
+    """models/dpcl.py -- affinity loss with un-squared Frobenius norms, one-hot labels 1/0."""
+    mask_a, mask_b = 1.0, 0.0
+
+    def cost(self, V, labels, I=None):
+        B, Tt, Fb, E = V.shape
+        return L.dpcl_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), self.S)
+
+
+class L41Model(Separator):
+    """models/L41.py -- speaker-vector table [tot_speakers, E], sigmoid-dot loss, labels +1/-1."""
+    mask_a, mask_b = 1.0, -1.0
+
+    def __init__(self, plugged=False, store=None, F=None, **kwargs):
+        super().__init__(plugged, store, F, **kwargs)
+        E = self.embedding_size
+        g = self.store.gen
+        v = torch.randn(self.num_speakers, E, generator=g, dtype=torch.float64).clamp_(-2.0, 2.0) * math.sqrt(2.0 / E)
+        self.store.register("speaker_centroids", v.float())          # L41.py:16-18
+
+    def cost(self, V, labels, I):
+        B, Tt, Fb, E = V.shape
+        sv = self.store["speaker_centroids"]
+        if self.normalize:
+            sv = L.l2_normalize(sv, E)                               # L41.py:60-61
+        spk = sv[I.long()].contiguous()                              # [B,S,E] gather (L41.py:62)
+        return L.l41_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), spk)
+
+
+# =================================================================================================
+# KMeans                                                                       models/Kmeans_2.py
+# =================================================================================================
+class KMeans:
+    """KMeans(nb_clusters, centroids_init, nb_tries, nb_iterations, input_tensor, normalize_input,
+    latent_space_tensor, beta, threshold, assign_at_end) -- same argument names as the reference
+    (Kmeans_2.py:14-17).  The random initial rows are drawn on the host exactly as the reference's
+    py_func does (np.random.choice without replacement per row, :61-65) unless init_idx is given."""
+
+    def __init__(self, nb_clusters, centroids_init=None, nb_tries=10, nb_iterations=10, input_tensor=None,
+                 normalize_input=True, latent_space_tensor=None, beta=None, threshold=2.5, assign_at_end=True,
+                 rng=None):
+        if centroids_init is not None:
+            raise NotImplementedError("centroids_init is dead code in the reference (Kmeans_2.py:72-74)")
+        self.nb_clusters, self.nb_tries, self.nb_iterations = nb_clusters, nb_tries, nb_iterations
+        self.normalize_input, self.latent, self.beta = normalize_input, latent_space_tensor, beta
+        self.threshold, self.assign_at_end = threshold, assign_at_end
+        self.rng = rng if rng is not None else np.random.RandomState(42)
+        self.input_tensor = input_tensor
+
+    def random_init(self, rows, Lp):
+        return np.stack([self.rng.choice(Lp, size=self.nb_clusters, replace=False) for _ in range(rows)]).astype(np.int32)
+
+    def fit(self, X, init_idx=None):
+        """X [B,L,E] (CUDA) -> (centroids [B,K,E], labels int32 [B,L] or soft [B,L,K])."""
+        B, Lp, E = X.shape
+        if init_idx is None:
+            init_idx = self.random_init(B * self.nb_tries, Lp)
+        idx = torch.as_tensor(np.asarray(init_idx), dtype=torch.int32).to(X.device).contiguous()
+        ns = None
+        if self.latent is not None:
+            ns = ops.kmeans_silence_mask(self.latent.reshape(B, Lp).contiguous(), self.threshold)
+        cent, lab, inertia, best = ops.kmeans_fit(X.contiguous(), idx, self.nb_clusters, self.nb_tries,
+                                                  self.nb_iterations, self.beta, ns, self.normalize_input,
+                                                  self.assign_at_end)
+        self.inertia, self.best_try = inertia, best
+        return cent, lab
+
+    @property
+    def network(self):
+        return self.fit(self.input_tensor)
