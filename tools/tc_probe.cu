@@ -1,0 +1,255 @@
+// tc_probe -- hardware probe for the tcgen05 building blocks in csrc/tc.cuh (test tooling, not
+// part of the library).  The HOST builds the exact shared-memory byte image of both operands and
+// the descriptor strides; the kernel only copies the image, issues tcgen05.mma and dumps TMEM.
+// Each case is checked against a CPU product of the bf16-rounded operands, under both possible
+// readings of the descriptor's LBO/SBO fields, so one run pins the semantics the kernels rely on.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I../adaptive-multispeaker-separation_b200/csrc
+//        -o tc_probe.bin tc_probe.cu   &&   ./tc_probe.bin
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "tc.cuh"
+
+using namespace amss::tc;
+
+struct ProbeArgs {
+    const uint8_t* a_img; uint32_t a_bytes;
+    const uint8_t* b_img; uint32_t b_bytes;
+    uint32_t a_lbo, a_sbo, a_kstep;     // kstep: byte advance of the start address per K=16
+    uint32_t b_lbo, b_sbo, b_kstep;
+    int N, ksteps, a_mn, b_mn, use_bulk;
+    float* D;                          // [128][N]
+};
+
+__global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* a_s = smem;
+    uint8_t* b_s = smem + ((p.a_bytes + 1023) / 1024) * 1024;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (p.use_bulk) {
+        if (tid == 0) {
+            mbar_expect_tx(bar_load, p.a_bytes + p.b_bytes);
+            bulk_g2s(smem_u32(a_s), p.a_img, p.a_bytes, bar_load);
+            bulk_g2s(smem_u32(b_s), p.b_img, p.b_bytes, bar_load);
+        }
+        mbar_wait(bar_load, 0);
+    } else {
+        for (uint32_t i = tid * 16; i < p.a_bytes; i += 128 * 16)
+            *reinterpret_cast<uint4*>(a_s + i) = *reinterpret_cast<const uint4*>(p.a_img + i);
+        for (uint32_t i = tid * 16; i < p.b_bytes; i += 128 * 16)
+            *reinterpret_cast<uint4*>(b_s + i) = *reinterpret_cast<const uint4*>(p.b_img + i);
+        fence_async_smem();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        const uint32_t idesc = idesc_bf16(128, p.N, p.a_mn, p.b_mn);
+        for (int kk = 0; kk < p.ksteps; ++kk) {
+            const uint64_t ad = smem_desc(smem_u32(a_s) + kk * p.a_kstep, p.a_lbo, p.a_sbo);
+            const uint64_t bd = smem_desc(smem_u32(b_s) + kk * p.b_kstep, p.b_lbo, p.b_sbo);
+            mma_bf16(tmem, ad, bd, idesc, kk > 0);
+        }
+        mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) p.D[(size_t)tid * p.N + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf2f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// image builders: core matrices of 128 B; (mn_grp, k_grp) -> byte offset mn_grp*mn_stride + k_grp*k_stride
+static void put(std::vector<uint8_t>& img, size_t off, uint16_t v) {
+    if (off + 2 > img.size()) img.resize(off + 2, 0);
+    memcpy(&img[off], &v, 2);
+}
+// K-major: element (mn, k) at core(mn/8, k/8) + (mn%8)*16 + (k%8)*2
+static std::vector<uint8_t> image_kmajor(const std::vector<float>& X, int MN, int K, size_t mn_stride, size_t k_stride) {
+    std::vector<uint8_t> img;
+    for (int mn = 0; mn < MN; ++mn)
+        for (int k = 0; k < K; ++k)
+            put(img, (mn / 8) * mn_stride + (k / 8) * k_stride + (mn % 8) * 16 + (k % 8) * 2, f2bf(X[(size_t)mn * K + k]));
+    img.resize((img.size() + 15) / 16 * 16, 0);
+    return img;
+}
+// MN-major: element (mn, k) at core(mn/8, k/8) + (k%8)*16 + (mn%8)*2
+static std::vector<uint8_t> image_mnmajor(const std::vector<float>& X, int MN, int K, size_t mn_stride, size_t k_stride) {
+    std::vector<uint8_t> img;
+    for (int mn = 0; mn < MN; ++mn)
+        for (int k = 0; k < K; ++k)
+            put(img, (mn / 8) * mn_stride + (k / 8) * k_stride + (k % 8) * 16 + (mn % 8) * 2, f2bf(X[(size_t)mn * K + k]));
+    img.resize((img.size() + 15) / 16 * 16, 0);
+    return img;
+}
+
+struct Case {
+    const char* name;
+    std::vector<uint8_t> a, b;
+    uint32_t a_mnstride, a_kstride, b_mnstride, b_kstride;   // true strides of the images
+    int N, K, a_mn, b_mn, use_bulk;
+    std::vector<float> ref;   // [128][N]
+};
+
+static int run_case(const Case& c, bool swap_fields) {
+    uint8_t *da, *db;
+    float* dD;
+    cudaMalloc(&da, c.a.size());
+    cudaMalloc(&db, c.b.size());
+    cudaMalloc(&dD, (size_t)128 * c.N * 4);
+    cudaMemcpy(da, c.a.data(), c.a.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(db, c.b.data(), c.b.size(), cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0xFF, (size_t)128 * c.N * 4);
+    ProbeArgs p;
+    p.a_img = da; p.a_bytes = (uint32_t)c.a.size();
+    p.b_img = db; p.b_bytes = (uint32_t)c.b.size();
+    // hypothesis H1: LBO = K-direction stride, SBO = MN-direction stride; swap_fields tests H2
+    p.a_lbo = swap_fields ? c.a_mnstride : c.a_kstride; p.a_sbo = swap_fields ? c.a_kstride : c.a_mnstride;
+    p.b_lbo = swap_fields ? c.b_mnstride : c.b_kstride; p.b_sbo = swap_fields ? c.b_kstride : c.b_mnstride;
+    p.a_kstep = 2 * c.a_kstride; p.b_kstep = 2 * c.b_kstride;
+    p.N = c.N; p.ksteps = c.K / 16; p.a_mn = c.a_mn; p.b_mn = c.b_mn; p.use_bulk = c.use_bulk; p.D = dD;
+    const size_t smem = ((c.a.size() + 1023) / 1024) * 1024 + c.b.size() + 1024;
+    cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe_kernel<<<1, 128, smem>>>(p);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("CASE %-28s %s: CUDA ERROR %s\n", c.name, swap_fields ? "H2(swapped)" : "H1", cudaGetErrorString(e));
+        return -1;
+    }
+    std::vector<float> D((size_t)128 * c.N);
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0, maxref = 0;
+    for (size_t i = 0; i < D.size(); ++i) {
+        double d = fabs((double)D[i] - c.ref[i]);
+        if (!(d == d)) d = 1e30;
+        maxerr = d > maxerr ? d : maxerr;
+        maxref = fabs(c.ref[i]) > maxref ? fabs(c.ref[i]) : maxref;
+    }
+    const bool ok = maxerr <= 1e-3 * maxref;
+    printf("CASE %-28s %-11s: %s  (max err %.3g, max |ref| %.3g)\n", c.name, swap_fields ? "H2(swapped)" : "H1",
+           ok ? "MATCH" : "mismatch", maxerr, maxref);
+    cudaFree(da); cudaFree(db); cudaFree(dD);
+    return ok ? 1 : 0;
+}
+
+int main() {
+    srand(1234);
+    auto rnd = [](size_t n) {
+        std::vector<float> v(n);
+        for (auto& x : v) x = bf2f(f2bf((float)rand() / RAND_MAX - 0.5f));
+        return v;
+    };
+    auto matmul = [](const std::vector<float>& A, const std::vector<float>& B, int N, int K) {   // A[128][K], B[N][K]
+        std::vector<float> R((size_t)128 * N);
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < N; ++n) {
+                double s = 0;
+                for (int k = 0; k < K; ++k) s += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k];
+                R[(size_t)m * N + n] = (float)s;
+            }
+        return R;
+    };
+    std::vector<Case> cases;
+    {   // 1. K-major A and B, distinct strides: A mn-stride 128 / k-stride 2048 ; B mn-stride 128 / k-stride 4096
+        Case c; c.name = "kmajor_kmajor_N256_K64"; c.N = 256; c.K = 64; c.a_mn = 0; c.b_mn = 0; c.use_bulk = 0;
+        auto A = rnd(128 * 64), B = rnd(256 * 64);
+        c.a_mnstride = 128; c.a_kstride = 16 * 128; c.b_mnstride = 128; c.b_kstride = 32 * 128;
+        c.a = image_kmajor(A, 128, 64, c.a_mnstride, c.a_kstride);
+        c.b = image_kmajor(B, 256, 64, c.b_mnstride, c.b_kstride);
+        c.ref = matmul(A, B, 256, 64);
+        cases.push_back(c);
+        Case c2 = c; c2.name = "same_via_bulk_copy"; c2.use_bulk = 1; cases.push_back(c2);
+    }
+    {   // 2. K-major, other stride assignment (k-stride 128, mn-stride 1024): rows of core matrices along K
+        Case c; c.name = "kmajor_kinner_N128_K64"; c.N = 128; c.K = 64; c.a_mn = 0; c.b_mn = 0; c.use_bulk = 0;
+        auto A = rnd(128 * 64), B = rnd(128 * 64);
+        c.a_mnstride = 8 * 128; c.a_kstride = 128; c.b_mnstride = 8 * 128; c.b_kstride = 128;
+        c.a = image_kmajor(A, 128, 64, c.a_mnstride, c.a_kstride);
+        c.b = image_kmajor(B, 128, 64, c.b_mnstride, c.b_kstride);
+        c.ref = matmul(A, B, 128, 64);
+        cases.push_back(c);
+    }
+    {   // 3. MN-major A and B
+        Case c; c.name = "mnmajor_mnmajor_N256_K32"; c.N = 256; c.K = 32; c.a_mn = 1; c.b_mn = 1; c.use_bulk = 0;
+        auto A = rnd(128 * 32), B = rnd(256 * 32);
+        c.a_mnstride = 128; c.a_kstride = 16 * 128; c.b_mnstride = 128; c.b_kstride = 32 * 128;
+        c.a = image_mnmajor(A, 128, 32, c.a_mnstride, c.a_kstride);
+        c.b = image_mnmajor(B, 256, 32, c.b_mnstride, c.b_kstride);
+        c.ref = matmul(A, B, 256, 32);
+        cases.push_back(c);
+    }
+    {   // 4. mixed: A MN-major, B K-major, N = 160 (not a power of two)
+        Case c; c.name = "mnmajorA_kmajorB_N160_K48"; c.N = 160; c.K = 48; c.a_mn = 1; c.b_mn = 0; c.use_bulk = 0;
+        auto A = rnd(128 * 48), B = rnd(160 * 48);
+        c.a_mnstride = 128; c.a_kstride = 16 * 128; c.b_mnstride = 6 * 128; c.b_kstride = 128;
+        c.a = image_mnmajor(A, 128, 48, c.a_mnstride, c.a_kstride);
+        c.b = image_kmajor(B, 160, 48, c.b_mnstride, c.b_kstride);
+        c.ref = matmul(A, B, 160, 48);
+        cases.push_back(c);
+    }
+    {   // 5. Hankel B operand: B[n][k] = x[n + k] served from ONE array of overlapping core matrices,
+        //    G[q] = {x[8q + r + e]}_{r,e<8}; core matrix (n/8, k/8) = G[n/8 + k/8] -> LBO = SBO = 128 B.
+        Case c; c.name = "hankel_B_N256_K64"; c.N = 256; c.K = 64; c.a_mn = 0; c.b_mn = 0; c.use_bulk = 0;
+        auto A = rnd(128 * 64);
+        auto x = rnd(256 + 64 + 16);
+        std::vector<float> B((size_t)256 * 64);
+        for (int n = 0; n < 256; ++n) for (int k = 0; k < 64; ++k) B[(size_t)n * 64 + k] = x[n + k];
+        c.a_mnstride = 128; c.a_kstride = 16 * 128; c.b_mnstride = 128; c.b_kstride = 128;
+        c.a = image_kmajor(A, 128, 64, c.a_mnstride, c.a_kstride);
+        const int Q = (256 + 64) / 8;
+        c.b.assign((size_t)Q * 128, 0);
+        for (int q = 0; q < Q; ++q) for (int r = 0; r < 8; ++r) for (int e = 0; e < 8; ++e) {
+            uint16_t v = f2bf(x[8 * q + r + e]);
+            memcpy(&c.b[(size_t)q * 128 + r * 16 + e * 2], &v, 2);
+        }
+        c.ref = matmul(A, B, 256, 64);
+        cases.push_back(c);
+    }
+    int h1 = 0, h2 = 0, n = 0;
+    for (auto& c : cases) {
+        int r1 = run_case(c, false);
+        if (r1 < 0) return 2;
+        int r2 = run_case(c, true);
+        if (r2 < 0) return 2;
+        h1 += r1; h2 += r2; ++n;
+    }
+    printf("SUMMARY: H1 (LBO=K stride, SBO=MN stride) matches %d/%d ; H2 (swapped) matches %d/%d\n", h1, n, h2, n);
+    return 0;
+}
