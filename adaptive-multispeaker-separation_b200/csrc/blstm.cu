@@ -18,6 +18,11 @@ namespace amss {
 int gemm_dispatch(const float* A, int lda, const float* B, int ldb, const float* bias, int M, int N, int K, int transa,
                   int transb, int accumulate, int precision, float* C, int ldc, int swapB, int swapT, void* workspace,
                   size_t workspace_bytes, cudaStream_t st);
+bool blstm_rec_tc_supported(int B, int T, int H);
+int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gates, float* cst, float* y, int B, int T,
+                     int H, float forget_bias, cudaStream_t st);
+int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,
+                     const float* dy, float* dZ, int B, int T, int H, cudaStream_t st);
 namespace {
 
 constexpr int RC_THREADS = 256;
@@ -274,6 +279,9 @@ extern "C" int amss_blstm_fwd(const float* x, const float* kernel_fw, const floa
                                gates + (size_t)d * T * B * 4 * H, 4 * H, 0, 0, gws, gws_bytes, st);
         if (rc != AMSS_OK) return rc;
     }
+    if (precision == AMSS_PREC_BF16 && blstm_rec_tc_supported(B, T, H))
+        return blstm_rec_fwd_tc(kernel_fw + (size_t)I * 4 * H, kernel_bw + (size_t)I * 4 * H, 4 * H, gates, cst, y, B, T, H,
+                                forget_bias, st);
     AMSS_CUDA(cudaMemsetAsync(bar, 0, 256, st));
     RecFwdParams p;
     p.Wh[0] = kernel_fw + (size_t)I * 4 * H;
@@ -307,6 +315,12 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
     const size_t gws_bytes = workspace_bytes - (size_t)((char*)gws - ws);
     const float* gates = (const float*)saved;
     const float* cst = (const float*)((const char*)saved + gates_bytes(B, T, H));
+    const bool use_tc = precision == AMSS_PREC_BF16 && blstm_rec_tc_supported(B, T, H);
+    if (use_tc) {
+        int rc = blstm_rec_bwd_tc(kernel_fw + (size_t)I * 4 * H, kernel_bw + (size_t)I * 4 * H, 4 * H, gates, cst, dy, dZ, B,
+                                  T, H, st);
+        if (rc != AMSS_OK) return rc;
+    } else {
     AMSS_CUDA(cudaMemsetAsync(bar, 0, 256, st));
     RecBwdParams p;
     p.Wh[0] = kernel_fw + (size_t)I * 4 * H;
@@ -318,6 +332,7 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
     AMSS_CUDA(cudaLaunchCooperativeKernel((void*)blstm_rec_bwd_kernel, dim3(2 * geo.NC), dim3(RC_THREADS), args,
                                           geo.smem_bwd, st));
     count_launch();
+    }
     const float* kern[2] = {kernel_fw, kernel_bw};
     float* dkern[2] = {dkernel_fw, dkernel_bw};
     float* dbias[2] = {dbias_fw, dbias_bw};

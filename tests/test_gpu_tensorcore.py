@@ -80,3 +80,93 @@ def test_analysis_tc_close_to_fp32_kernel(ops):
     print(f"bf16 vs fp32 analysis: max rel err {err:.2e}, arg-max agreement {agree:.4f}")
     assert err < 1e-2
     assert agree > 0.9
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (37, 53, 29), (300, 1200, 257), (1, 7, 3), (260, 520, 1000),
+                                   (600, 1200, 4000)])
+def test_gemm_tc_matches_bf16_operand_product(ops, ta, tb, shape):
+    Mm, N, K = shape
+    g = torch.Generator().manual_seed(21)
+    A = torch.randn((K, Mm) if ta else (Mm, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    Ar, Br = bf16_round(A), bf16_round(B)
+    ref = (Ar.t() if ta else Ar).double() @ (Br.t() if tb else Br).double() + bias.double()
+    out = ops.gemm(dev(A), dev(B), dev(bias), bool(ta), bool(tb), precision=ops.AMSS_PREC_BF16)
+    assert rel(out, ref) < 1e-4          # fp32 accumulation of exact bf16 products
+
+
+def test_gemm_tc_strided_accumulate_swap(ops):
+    g = torch.Generator().manual_seed(22)
+    Tt, Bb, C, N = 50, 6, 40, 72
+    big = torch.randn(Tt * Bb, 2 * C, generator=g)
+    A = dev(big)[:, C:]                       # row-strided view (lda = 2C)
+    W = torch.randn(C, N, generator=g)
+    base = torch.randn(Tt * Bb, N, generator=g)
+    out = dev(base.clone())
+    ops.gemm(A, dev(W), None, out=out, accumulate=True, precision=ops.AMSS_PREC_BF16)
+    prod = bf16_round(big[:, C:]).double() @ bf16_round(W).double()
+    assert rel(out, base.double() + prod) < 1e-4
+    out2 = ops.gemm(A, dev(W), None, out_swap=(Bb, Tt), precision=ops.AMSS_PREC_BF16)
+    ref2 = prod.reshape(Tt, Bb, N).transpose(0, 1).reshape(Bb * Tt, N)
+    assert rel(out2, ref2) < 1e-4
+    # split-K with accumulate (weight-gradient shape): C += A^T B
+    X = torch.randn(4000, 96, generator=g)
+    dZ = torch.randn(4000, 200, generator=g)
+    acc0 = torch.randn(96, 200, generator=g)
+    out3 = dev(acc0.clone())
+    ops.gemm(dev(X), dev(dZ), None, transa=True, out=out3, accumulate=True, precision=ops.AMSS_PREC_BF16)
+    ref3 = acc0.double() + bf16_round(X).double().t() @ bf16_round(dZ).double()
+    assert rel(out3, ref3) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ BLSTM
+def _saved_views(saved, B, Tt, H):
+    """amss_blstm_saved_bytes layout: gates [2][T][B][4H] (256-byte aligned), then cst [2][T][B][H]."""
+    f = saved.view(torch.float32)
+    ng = 2 * Tt * B * 4 * H
+    off = (ng * 4 + 255) // 256 * 256 // 4
+    return f[:ng], f[off:off + 2 * Tt * B * H]
+
+
+BLSTM_CASES = [(3, 7, 11, 6), (5, 20, 40, 150), (40, 12, 64, 300), (70, 9, 33, 20), (16, 30, 256, 300)]
+
+
+@pytest.mark.parametrize("B,Tt,I,H", BLSTM_CASES)
+def test_blstm_tc_fwd_bwd_close_to_oracle(ops, B, Tt, I, H):
+    """bf16 weights / hidden state / dz on the tensor cores, MUFU tanh, bf16 partial-sum exchange:
+    forward within 1e-2 of the output range, gradients within 3e-2 of each gradient's range."""
+    import math
+    g = torch.Generator().manual_seed(40 + B)
+    x = (torch.randn(B, Tt, I, generator=g, dtype=torch.float64) * 0.5).requires_grad_(True)
+    ks = [((torch.rand(I + H, 4 * H, generator=g, dtype=torch.float64) * 2 - 1) * math.sqrt(6.0 / (I + 5 * H))).requires_grad_(True)
+          for _ in range(2)]
+    bs = [(torch.randn(4 * H, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True) for _ in range(2)]
+    dy = torch.randn(B, Tt, 2 * H, generator=g, dtype=torch.float64)
+    y = T.blstm(x, ks[0], bs[0], ks[1], bs[1])
+    grads = torch.autograd.grad((y * dy).sum(), [x] + ks + bs)
+    f = lambda t: dev(t.detach().float())
+    x_tm = ops.transpose_01(f(x))
+    args = (x_tm, f(ks[0]), f(bs[0]), f(ks[1]), f(bs[1]))
+    y_tm, saved = ops.blstm_fwd(*args, precision=ops.AMSS_PREC_BF16)
+    y32, saved32 = ops.blstm_fwd(*args, precision=ops.AMSS_PREC_FP32)
+    err = rel(ops.transpose_01(y_tm), y)
+    g16, c16 = _saved_views(saved, B, Tt, H)
+    g32, c32 = _saved_views(saved32, B, Tt, H)
+    eg, ec = rel(g16, g32), rel(c16, c32)
+    dy_tm = ops.transpose_01(f(dy))
+    dx, dkf, dbf, dkb, dbb = ops.blstm_bwd(x_tm, f(ks[0]), f(ks[1]), y_tm, dy_tm, saved, precision=ops.AMSS_PREC_BF16)
+    errs = [rel(ops.transpose_01(dx), grads[0]), rel(dkf, grads[1]), rel(dkb, grads[2]), rel(dbf, grads[3]),
+            rel(dbb, grads[4])]
+    print(f"blstm tc B={B} T={Tt} I={I} H={H}: y {err:.2e} gates {eg:.2e} c {ec:.2e} "
+          f"dx {errs[0]:.2e} dK {errs[1]:.2e}/{errs[2]:.2e} db {errs[3]:.2e}/{errs[4]:.2e}")
+    assert err < 1e-2 and eg < 2e-2 and ec < 2e-2
+    assert max(errs) < 3e-2
