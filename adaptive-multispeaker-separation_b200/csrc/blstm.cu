@@ -208,18 +208,27 @@ __global__ void __launch_bounds__(RC_THREADS, 1) blstm_rec_bwd_kernel(RecBwdPara
     }
 }
 
-__global__ void colsum_rows_kernel(const float* __restrict__ Z, int64_t M, int N, float* __restrict__ out) {
-    // out[n] = sum_m Z[m][n], fixed order: one thread per column walks 8 interleaved partials
+// dbias[n] = sum_m Z[m][n], deterministic two-level sum: grid (ceil(N/32), CS_CHUNKS) -> part[chunk][N] -> out[N]
+constexpr int CS_CHUNKS = 64;
+__global__ void colsum_chunk_kernel(const float* __restrict__ Z, int64_t M, int N, float* __restrict__ part) {
     __shared__ float tile[8][33];
     const int n = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
     float a = 0.f;
-    if (n < N) for (int64_t m = ty; m < M; m += 8) a += Z[m * N + n];
+    if (n < N) for (int64_t m = blockIdx.y * 8 + ty; m < M; m += (int64_t)gridDim.y * 8) a += Z[m * N + n];
     tile[ty][threadIdx.x & 31] = a;
     __syncthreads();
     if (ty == 0 && n < N) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += tile[i][threadIdx.x & 31];
+        part[(size_t)blockIdx.y * N + n] = s;
+    }
+}
+__global__ void colsum_sum_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) {
+        float s = 0.f;
+        for (int c = 0; c < chunks; ++c) s += part[(size_t)c * N + n];
         out[n] = s;
     }
 }
@@ -253,6 +262,7 @@ extern "C" size_t amss_blstm_workspace_bytes(int B, int T, int I, int H, int pre
     g = std::max(g, amss_gemm_workspace_bytes(I, 4 * H, T * B, 1, 0, precision));
     g = std::max(g, amss_gemm_workspace_bytes(H, 4 * H, T * B, 1, 0, precision));
     g = std::max(g, amss_gemm_workspace_bytes(T * B, I, 4 * H, 0, 1, precision));
+    g = std::max(g, (size_t)CS_CHUNKS * 4 * H * 4);   // column-sum partials share the GEMM scratch
     return 256 + gates_bytes(B, T, H) + cst_bytes(B, T, H) + align_up((size_t)2 * B * H * 4, 256) + align_up(g, 256);
 }
 
@@ -354,7 +364,11 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
         } else {
             AMSS_CUDA(cudaMemsetAsync(dWh, 0, (size_t)H * H4 * 4, st));
         }
-        AMSS_LAUNCH(colsum_rows_kernel, (H4 + 31) / 32, 256, 0, st, dZd, (int64_t)T * B, H4, dbias[d]);
+        {
+            dim3 cg((H4 + 31) / 32, CS_CHUNKS);
+            AMSS_LAUNCH(colsum_chunk_kernel, cg, 256, 0, st, dZd, (int64_t)T * B, H4, (float*)gws);
+            AMSS_LAUNCH(colsum_sum_kernel, (H4 + 255) / 256, 256, 0, st, (const float*)gws, CS_CHUNKS, H4, dbias[d]);
+        }
         if (dx) {
             rc = gemm_dispatch(dZd, H4, kern[d], H4, nullptr, T * B, I, H4, 0, 1, d, precision, dx, I, 0, 0, gws,
                                gws_bytes, st);

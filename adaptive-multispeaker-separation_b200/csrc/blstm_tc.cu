@@ -132,10 +132,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
 #pragma unroll
             for (int b = 0; b < NB; ++b) zx[b] = (b < nvalid && ug < H) ? __ldcg(gp + (size_t)b * H4) : 0.f;
         };
-        load_zx(d == 0 ? 0 : T - 1);
         const float fb = q == 2 ? p.forget_bias : 0.f;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
+            load_zx(t);                           // in flight while the MMA of this step runs
             uint32_t acc[NB];
             if (s > 0) {
                 mbar_wait(bar, (s - 1) & 1);
@@ -155,7 +155,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
                 const float z = __uint_as_float(acc[b]) + zx[b] + fb;
                 gx[(q * 32 + lane) * GXP + b] = q == 1 ? tanh_fast(z) : sigmoid_fast(z);
             }
-            if (s + 1 < T) load_zx(d == 0 ? t + 1 : t - 1);
             bar_sync_named(1, 256);               // gx complete (compute + writer warps)
             const uint32_t hdst = smem_u32(h_s + ((s + 1) & 1) * h_bytes);
             float* cys = cy + (s & 1) * (2 * NB * 33);
@@ -348,9 +347,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 sv[i][6] = ok ? __ldcg(p.dy + ((size_t)t * B + b0 + b) * 2 * H + d * H + ug) : 0.f;
             }
         };
-        prefetch(T - 1);
         for (int s = T - 1; s >= 0; --s) {
             const int n = T - 1 - s;                  // step counter
+            prefetch(s);                              // in flight while the MMA of this step runs
             const uint32_t rbuf = smem_u32(r_s + (n & 1) * r_bytes);
             if (n > 0) {
                 // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]  ->  owner CTA of unit u
@@ -416,7 +415,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                         __float2bfloat16_rn(dz[g4]);
                 }
             }
-            if (s > 0) prefetch(s - 1);
             fence_async_smem();
             bar_sync_named(1, 288);                   // dz staged: MMA warp may issue, writers may store
         }

@@ -15,140 +15,163 @@ constexpr int LS_MAXS = 4;
 constexpr int LS_RB = 4;        // register block (RB x RB entries of the E x E Gram matrix per thread)
 
 // ---- DPCL forward --------------------------------------------------------------------------
-// Y is one-hot, so with N_s = #bins of speaker s and D_i = N_{l_i}^{-1/2}:
-//   V^T D V = sum_s N_s^{-1/2} G_s,  G_s = sum_{i in s} v_i v_i^T   (E x E)
+// Y is one-hot, so with N_s = #bins of speaker s and w_i = N_{l_i}^{-1/2}:
+//   V^T D V = sum_i w_i v_i v_i^T                                   (E x E, symmetric)
 //   V^T D Y[:, s] = N_s^{-1/2} sum_{i in s} v_i                      (E)
 //   Y^T D Y = diag(sqrt(N_s))
-// part[b][chunk][s][E*E + E + 1] = (G_s, m_s, N_s) partials.
-__global__ void __launch_bounds__(LS_THREADS)
-dpcl_gram_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels, int64_t TF, int E, int S,
-                 float* __restrict__ part) {
-    extern __shared__ __align__(16) unsigned char ls_smem[];
-    float* xs = reinterpret_cast<float*>(ls_smem);              // [LS_TILE][E+1]
-    uint8_t* ls = reinterpret_cast<uint8_t*>(xs + LS_TILE * (E + 1));
-    const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x, tid = threadIdx.x, EP = E + 1;
-    const int nb = (E + LS_RB - 1) / LS_RB;                     // blocks per side
-    // thread -> (bi, bj) block of the Gram matrix (threads beyond nb*nb idle in the Gram part)
-    const int bi = tid / nb, bj = tid % nb;
-    const bool active = bi < nb;
-    float acc[LS_MAXS][LS_RB][LS_RB];
-    float macc[LS_MAXS];
-    float cnt[LS_MAXS];
+// Pass 1 counts N_s; pass 2 accumulates the weighted Gram matrix (upper-triangular 4x4 register
+// blocks, LS_PT points staged per tile, point groups spread over the CTA) and the per-speaker
+// column sums: part[b][chunk][E*E + S*E]; pass 3 reduces the chunks in a fixed order.
+constexpr int LS_PT = 256;      // points per tile
+
+__global__ void dpcl_count_kernel(const uint8_t* __restrict__ labels, int64_t TF, int S, float* __restrict__ counts) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    int c[LS_MAXS] = {0, 0, 0, 0};
+    for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) {
+        const int l = labels[(size_t)b * TF + i];
 #pragma unroll
-    for (int s = 0; s < LS_MAXS; ++s) {
-        macc[s] = 0.f; cnt[s] = 0.f;
-#pragma unroll
-        for (int i = 0; i < LS_RB; ++i)
-#pragma unroll
-            for (int j = 0; j < LS_RB; ++j) acc[s][i][j] = 0.f;
+        for (int s = 0; s < LS_MAXS; ++s) c[s] += (l == s);
     }
-    const int64_t ntiles = (TF + LS_TILE - 1) / LS_TILE;
+    for (int s = 0; s < LS_MAXS; ++s) {
+        const float v = block_sum((float)c[s], red);      // exact: counts < 2^24
+        if (threadIdx.x == 0) counts[b * LS_MAXS + s] = s < S ? v : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(LS_THREADS)
+dpcl_gram_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels, const float* __restrict__ counts,
+                 int64_t TF, int E, int S, float* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char ls_smem[];
+    const int EP = (E + 3) & ~3;
+    float* xs = reinterpret_cast<float*>(ls_smem);              // [LS_PT][EP]   (reused for the final reduction)
+    float* wsm = xs + LS_PT * EP;                               // [LS_PT] weights
+    uint8_t* ls = reinterpret_cast<uint8_t*>(wsm + LS_PT);      // [LS_PT] labels
+    const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x, tid = threadIdx.x;
+    const int nb = EP / 4, nt = nb * (nb + 1) / 2;
+    int G = LS_THREADS / nt; if (G > 8) G = 8; if (G < 1) G = 1;
+    const bool active = tid < nt * G;
+    const int blk = tid % nt, gq = tid / nt;
+    int bi = 0, bj = 0;
+    { int r = blk; while (r >= nb - bi) { r -= nb - bi; ++bi; } bj = bi + r; }   // upper triangle, row-major
+    float wS[LS_MAXS];
+#pragma unroll
+    for (int s = 0; s < LS_MAXS; ++s) { const float n = counts[b * LS_MAXS + s]; wS[s] = n > 0.f ? rsqrtf(n) : 0.f; }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float macc[LS_MAXS] = {0.f, 0.f, 0.f, 0.f};
+    const int me = tid % EP, mg = tid / EP;                     // column-sum role: column me, point group mg (< 4)
+    const int64_t ntiles = (TF + LS_PT - 1) / LS_PT;
     for (int64_t tile = chunk; tile < ntiles; tile += chunks) {
-        const int64_t p0 = tile * LS_TILE;
-        const int np = (int)((TF - p0) < LS_TILE ? (TF - p0) : LS_TILE);
+        const int64_t p0 = tile * LS_PT;
+        const int np = (int)((TF - p0) < LS_PT ? (TF - p0) : LS_PT);
         const float* src = V + ((size_t)b * TF + p0) * E;
         __syncthreads();
-        for (int i = tid; i < np * E; i += LS_THREADS) { const int p = i / E, e = i - p * E; xs[p * EP + e] = src[i]; }
-        for (int i = tid; i < np; i += LS_THREADS) ls[i] = labels[(size_t)b * TF + p0 + i];
+        if (EP == E) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(xs);
+            for (int i = tid; i < np * (E / 4); i += LS_THREADS) d4[i] = __ldg(s4 + i);
+        } else {
+            for (int i = tid; i < np * EP; i += LS_THREADS) { const int p = i / EP, e = i - p * EP; xs[i] = e < E ? src[p * E + e] : 0.f; }
+        }
+        for (int i = tid; i < np; i += LS_THREADS) {
+            const int l = labels[(size_t)b * TF + p0 + i];
+            ls[i] = (uint8_t)l;
+            wsm[i] = l == 0 ? wS[0] : (l == 1 ? wS[1] : (l == 2 ? wS[2] : wS[3]));
+        }
         __syncthreads();
         if (active) {
-            for (int p = 0; p < np; ++p) {
-                const int l = ls[p];
-                float vi[LS_RB], vj[LS_RB];
+            for (int p = gq; p < np; p += G) {
+                const float w = wsm[p];
+                const float4 a = *reinterpret_cast<const float4*>(xs + p * EP + bi * 4);
+                const float4 c = *reinterpret_cast<const float4*>(xs + p * EP + bj * 4);
+                const float av[4] = {w * a.x, w * a.y, w * a.z, w * a.w};
+                const float cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
-                for (int i = 0; i < LS_RB; ++i) {
-                    const int ei = bi * LS_RB + i, ej = bj * LS_RB + i;
-                    vi[i] = ei < E ? xs[p * EP + ei] : 0.f;
-                    vj[i] = ej < E ? xs[p * EP + ej] : 0.f;
-                }
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int s = 0; s < LS_MAXS; ++s)
-                    if (s < S) {
-                        const float w = (l == s) ? 1.f : 0.f;
-#pragma unroll
-                        for (int i = 0; i < LS_RB; ++i) {
-                            const float wi = w * vi[i];
-#pragma unroll
-                            for (int j = 0; j < LS_RB; ++j) acc[s][i][j] = fmaf(wi, vj[j], acc[s][i][j]);
-                        }
-                    }
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], cv[j], acc[i][j]);
             }
         }
-        // column sums and counts: thread e < E owns m_s[e]; thread E owns the counts
-        if (tid < E) {
-            for (int p = 0; p < np; ++p) {
+        if (mg < 4) {
+            for (int p = mg; p < np; p += 4) {
                 const int l = ls[p];
-                const float v = xs[p * EP + tid];
+                const float v = xs[p * EP + me];
 #pragma unroll
-                for (int s = 0; s < LS_MAXS; ++s) if (s < S) macc[s] += (l == s) ? v : 0.f;
-            }
-        } else if (tid == E) {
-            for (int p = 0; p < np; ++p) {
-                const int l = ls[p];
-#pragma unroll
-                for (int s = 0; s < LS_MAXS; ++s) if (s < S) cnt[s] += (l == s) ? 1.f : 0.f;
+                for (int s = 0; s < LS_MAXS; ++s) macc[s] += (l == s) ? v : 0.f;
             }
         }
     }
-    const int stride = E * E + E + 1;
-    float* dst = part + ((size_t)b * chunks + chunk) * S * stride;
+    // fixed-order reduction over the point groups, then one partial per (b, chunk)
+    __syncthreads();
+    float* red = xs;                                            // [G][nt][16] then [4][LS_MAXS][EP]
+    float* mred = xs + 8 * nt * 16;
+    if (active) {
 #pragma unroll
-    for (int s = 0; s < LS_MAXS; ++s)
-        if (s < S) {
-            if (active) {
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int i = 0; i < LS_RB; ++i)
+            for (int j = 0; j < 4; ++j) red[(gq * nt + blk) * 16 + i * 4 + j] = acc[i][j];
+    }
+    if (mg < 4) {
 #pragma unroll
-                    for (int j = 0; j < LS_RB; ++j) {
-                        const int ei = bi * LS_RB + i, ej = bj * LS_RB + j;
-                        if (ei < E && ej < E) dst[s * stride + ei * E + ej] = acc[s][i][j];
-                    }
+        for (int s = 0; s < LS_MAXS; ++s) mred[(mg * LS_MAXS + s) * EP + me] = macc[s];
+    }
+    __syncthreads();
+    float* dst = part + ((size_t)b * chunks + chunk) * ((size_t)E * E + (size_t)S * E);
+    if (tid < nt) {
+        int ri = 0, rj = 0;
+        { int r = tid; while (r >= nb - ri) { r -= nb - ri; ++ri; } rj = ri + r; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a = 0.f;
+                for (int g = 0; g < G; ++g) a += red[(g * nt + tid) * 16 + i * 4 + j];
+                const int ei = ri * 4 + i, ej = rj * 4 + j;
+                if (ei < E && ej < E) { dst[ei * E + ej] = a; dst[ej * E + ei] = a; }
             }
-            if (tid < E) dst[s * stride + E * E + tid] = macc[s];
-            else if (tid == E) dst[s * stride + E * E + E] = cnt[s];
-        }
+    }
+    for (int i = tid; i < S * E; i += LS_THREADS) {
+        const int s = i / E, e = i - s * E;
+        dst[E * E + i] = mred[(0 * LS_MAXS + s) * EP + e] + mred[(1 * LS_MAXS + s) * EP + e] +
+                         mred[(2 * LS_MAXS + s) * EP + e] + mred[(3 * LS_MAXS + s) * EP + e];
+    }
 }
 
 // One CTA per batch row: reduce the partials, form the three Frobenius norms, keep what the
 // backward needs:  stats[b] = { An[E*E] = 2*A/||A||, Bn[S*E] = 2*Bm[:,s]/||Bm||, dinv[S], loss_b }.
-__global__ void dpcl_finalize_kernel(const float* __restrict__ part, int chunks, int E, int S,
-                                     float* __restrict__ stats) {
-    extern __shared__ __align__(16) unsigned char ls_smem[];
+__global__ void dpcl_finalize_kernel(const float* __restrict__ part, const float* __restrict__ counts, int chunks, int E,
+                                     int S, float* __restrict__ stats) {
     __shared__ float red[32];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int stride = E * E + E + 1;
-    float* g = reinterpret_cast<float*>(ls_smem);               // [S][stride]
-    for (int i = tid; i < S * stride; i += blockDim.x) {
-        float a = 0.f;
-        for (int ch = 0; ch < chunks; ++ch) a += part[((size_t)b * chunks + ch) * S * stride + i];
-        g[i] = a;
-    }
-    __syncthreads();
+    const int stride = E * E + S * E;
     const int sstride = E * E + S * E + S + 1;
     float* out = stats + (size_t)b * sstride;
     float sa = 0.f, sb = 0.f;
-    for (int i = tid; i < E * E; i += blockDim.x) {
+    for (int i = tid; i < stride; i += blockDim.x) {
         float a = 0.f;
-        for (int s = 0; s < S; ++s) { const float n = g[s * stride + E * E + E]; if (n > 0.f) a += g[s * stride + i] / sqrtf(n); }
+        for (int ch = 0; ch < chunks; ++ch) a += part[((size_t)b * chunks + ch) * stride + i];
+        if (i >= E * E) {
+            const float n = counts[b * LS_MAXS + (i - E * E) / E];
+            a = n > 0.f ? a / sqrtf(n) : 0.f;
+            sb = fmaf(a, a, sb);
+        } else {
+            sa = fmaf(a, a, sa);
+        }
         out[i] = a;
-        sa = fmaf(a, a, sa);
-    }
-    for (int i = tid; i < S * E; i += blockDim.x) {
-        const int s = i / E, e = i - s * E;
-        const float n = g[s * stride + E * E + E];
-        const float v = n > 0.f ? g[s * stride + E * E + e] / sqrtf(n) : 0.f;
-        out[E * E + i] = v;
-        sb = fmaf(v, v, sb);
     }
     sa = block_sum(sa, red);
     sb = block_sum(sb, red);
     float sc = 0.f;
-    for (int s = 0; s < S; ++s) sc += g[s * stride + E * E + E];   // ||diag(sqrt(N_s))||_F^2 = sum N_s
+    for (int s = 0; s < S; ++s) sc += counts[b * LS_MAXS + s];     // ||diag(sqrt(N_s))||_F^2 = sum N_s
     const float na = sqrtf(sa), nbm = sqrtf(sb), nc = sqrtf(sc);
     __syncthreads();
     for (int i = tid; i < E * E; i += blockDim.x) out[i] = 2.f * out[i] / na;
     for (int i = tid; i < S * E; i += blockDim.x) out[E * E + i] = 2.f * out[E * E + i] / nbm;
-    if (tid < S) { const float n = g[tid * stride + E * E + E]; out[E * E + S * E + tid] = n > 0.f ? 1.f / sqrtf(n) : 0.f; }
+    if (tid < S) { const float n = counts[b * LS_MAXS + tid]; out[E * E + S * E + tid] = n > 0.f ? 1.f / sqrtf(n) : 0.f; }
     if (tid == 0) out[E * E + S * E + S] = na - 2.f * nbm + nc;
 }
 
@@ -162,13 +185,18 @@ __global__ void mean_of_stat_kernel(const float* __restrict__ stats, int B, int 
 }
 
 // dV_i = (dloss/B) * D_i * ( An v_i - Bn[:, l_i] ),  An = 2A/||A||, Bn = 2Bm/||Bm||   (A symmetric)
+// Register-blocked [256 points x E] x [E x E] product: thread = 4 points x OB outputs; the points are
+// staged transposed (point-contiguous) so the 4 point values are one LDS.128, the An row is a
+// warp-uniform broadcast; results go back through shared memory for coalesced stores.
+constexpr int LS_BP = 256, LS_BPT = 260;
+template <int OB>
 __global__ void __launch_bounds__(LS_THREADS)
 dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels, const float* __restrict__ dloss,
                 const float* __restrict__ stats, int B, int64_t TF, int E, int S, float* __restrict__ dV) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
-    const int EP = E + 1;
-    float* xs = reinterpret_cast<float*>(ls_smem);              // [LS_THREADS][E+1]
-    float* An = xs + LS_THREADS * EP;                           // [E][E]
+    float* xt = reinterpret_cast<float*>(ls_smem);              // [E][LS_BPT]  transposed points
+    float* os = xt + E * LS_BPT;                                // [LS_BP][E]   results, row-major
+    float* An = os + LS_BP * E;                                 // [E][E]
     float* Bn = An + E * E;                                     // [S][E]
     float* dinv = Bn + S * E;                                   // [S]
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -176,33 +204,49 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
     const float* st = stats + (size_t)b * sstride;
     for (int i = tid; i < E * E + S * E + S; i += LS_THREADS) An[i] = st[i];
     const float gscale = dloss[0] / (float)B;
-    const int64_t ntiles = (TF + LS_THREADS - 1) / LS_THREADS;
+    const int OBr = (E + 3) / 4;                                // outputs per thread (<= OB)
+    const int ob = tid >> 6, pg = tid & 63;
+    const int o0 = ob * OBr;
+    const int64_t ntiles = (TF + LS_BP - 1) / LS_BP;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t p0 = tile * LS_THREADS;
-        const int np = (int)((TF - p0) < LS_THREADS ? (TF - p0) : LS_THREADS);
+        const int64_t p0 = tile * LS_BP;
+        const int np = (int)((TF - p0) < LS_BP ? (TF - p0) : LS_BP);
         const float* src = V + ((size_t)b * TF + p0) * E;
         __syncthreads();
-        for (int i = tid; i < np * E; i += LS_THREADS) { const int p = i / E, e = i - p * E; xs[p * EP + e] = src[i]; }
+        for (int i = tid; i < LS_BP * E; i += LS_THREADS) {
+            const int p = i / E, e = i - p * E;
+            xt[e * LS_BPT + p] = p < np ? __ldg(src + i) : 0.f;
+        }
         __syncthreads();
-        if (tid < np) {
-            const int l = labels[(size_t)b * TF + p0 + tid];
-            const float d = gscale * dinv[l];
-            float* xp = xs + tid * EP;
-            // out[e] = sum_e2 An[e][e2] v[e2]; computed into registers in chunks of 8 rows
-            for (int e0 = 0; e0 < E; e0 += 8) {
-                float o[8];
+        float acc[4][OB];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = 0.f;
-                for (int e2 = 0; e2 < E; ++e2) {
-                    const float v = xp[e2];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) if (e0 + i < E) o[i] = fmaf(An[(e0 + i) * E + e2], v, o[i]);
-                }
+            for (int j = 0; j < OB; ++j) acc[i][j] = 0.f;
+        for (int e2 = 0; e2 < E; ++e2) {
+            const float4 v = *reinterpret_cast<const float4*>(xt + e2 * LS_BPT + pg * 4);
+            const float* ar = An + e2 * E + o0;                  // An symmetric: column block of row e2
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (e0 + i < E) dV[((size_t)b * TF + p0 + tid) * E + e0 + i] = d * (o[i] - Bn[l * E + e0 + i]);
+            for (int j = 0; j < OB; ++j) {
+                const float a = (j < OBr && o0 + j < E) ? ar[j] : 0.f;
+                acc[0][j] = fmaf(a, v.x, acc[0][j]); acc[1][j] = fmaf(a, v.y, acc[1][j]);
+                acc[2][j] = fmaf(a, v.z, acc[2][j]); acc[3][j] = fmaf(a, v.w, acc[3][j]);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = pg * 4 + i;
+            if (p < np) {
+                const int l = labels[(size_t)b * TF + p0 + p];
+                const float d = gscale * dinv[l];
+#pragma unroll
+                for (int j = 0; j < OB; ++j)
+                    if (j < OBr && o0 + j < E) os[p * E + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
+            }
+        }
+        __syncthreads();
+        float* dst = dV + ((size_t)b * TF + p0) * E;
+        for (int i = tid; i < np * E; i += LS_THREADS) dst[i] = os[i];
     }
 }
 
@@ -235,6 +279,58 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ v, const float* __re
         float inv = inv_norm[r];
         if (inv < 0.f) { inv = -inv; dot = 0.f; }
         for (int e = lane; e < E; e += 32) dz[r * E + e] = inv * (dv[r * E + e] - v[r * E + e] * dot);
+    }
+}
+
+// Vectorised variants for E % 4 == 0, E <= 128: E/4 lanes per row (one float4 each), 32/(E/4) rows per
+// warp per iteration -> fully coalesced 16-byte accesses; segmented shuffle reduction inside the row group.
+__device__ __forceinline__ float group_sum(float s, int gl, int lpr, int leader) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float t = __shfl_down_sync(0xffffffffu, s, off);
+        if (off < lpr && gl + off < lpr) s += t;
+    }
+    return __shfl_sync(0xffffffffu, s, leader);
+}
+__global__ void l2norm_fwd_vec_kernel(const float4* __restrict__ z, int64_t rows, int lpr, float4* __restrict__ v,
+                                      float* __restrict__ inv_norm) {
+    const int lane = threadIdx.x & 31, rpw = 32 / lpr;
+    const int g = lane / lpr, gl = lane - g * lpr;
+    const bool on = g < rpw;
+    const int leader = on ? g * lpr : 0;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+        const int64_t r = r0 + g;
+        const bool ok = on && r < rows;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) x = __ldcs(z + r * lpr + gl);
+        const float ss = group_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w, gl, lpr, leader);
+        const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+        if (ok) {
+            v[r * lpr + gl] = make_float4(x.x * inv, x.y * inv, x.z * inv, x.w * inv);
+            if (inv_norm && gl == 0) inv_norm[r] = (ss >= 1e-12f) ? inv : -inv;
+        }
+    }
+}
+__global__ void l2norm_bwd_vec_kernel(const float4* __restrict__ v, const float* __restrict__ inv_norm,
+                                      const float4* __restrict__ dv, int64_t rows, int lpr, float4* __restrict__ dz) {
+    const int lane = threadIdx.x & 31, rpw = 32 / lpr;
+    const int g = lane / lpr, gl = lane - g * lpr;
+    const bool on = g < rpw;
+    const int leader = on ? g * lpr : 0;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+        const int64_t r = r0 + g;
+        const bool ok = on && r < rows;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d = a;
+        float inv = 0.f;
+        if (ok) { a = __ldcs(v + r * lpr + gl); d = __ldcs(dv + r * lpr + gl); inv = inv_norm[r]; }
+        float dot = group_sum(a.x * d.x + a.y * d.y + a.z * d.z + a.w * d.w, gl, lpr, leader);
+        if (inv < 0.f) { inv = -inv; dot = 0.f; }
+        if (ok) dz[r * lpr + gl] = make_float4(inv * (d.x - a.x * dot), inv * (d.y - a.y * dot), inv * (d.z - a.z * dot),
+                                               inv * (d.w - a.w * dot));
     }
 }
 
@@ -416,27 +512,31 @@ int ls_chunks(int B, int64_t TF, int tile) {
 using namespace amss;
 
 extern "C" size_t amss_dpcl_workspace_bytes(int B, int64_t TF, int E, int S) {
-    const size_t stride = (size_t)E * E + E + 1;
+    const size_t stride = (size_t)E * E + (size_t)S * E;
     const size_t sstride = (size_t)E * E + (size_t)S * E + S + 1;
-    return align_up((size_t)B * sstride * 4, 256) + align_up((size_t)B * ls_chunks(B, TF, LS_TILE) * S * stride * 4, 256);
+    return align_up((size_t)B * sstride * 4, 256) + align_up((size_t)B * LS_MAXS * 4, 256) +
+           align_up((size_t)B * ls_chunks(B, TF, LS_PT) * stride * 4, 256);
 }
 
 extern "C" int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S, float* loss,
                                   void* workspace, size_t workspace_bytes, void* stream) {
     AMSS_REQUIRE(V && labels && loss && workspace, "dpcl_loss_fwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_fwd: S=%d outside [1,%d]", S, LS_MAXS);
-    const int nb = (E + LS_RB - 1) / LS_RB;
-    AMSS_REQUIRE(E >= 1 && nb * nb <= LS_THREADS, "dpcl_loss_fwd: E=%d too large (max %d)", E, 16 * LS_RB);
+    AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_fwd: E=%d outside [1,64]", E);
     if (workspace_bytes < amss_dpcl_workspace_bytes(B, TF, E, S)) { set_error("dpcl_loss_fwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
     const int sstride = E * E + S * E + S + 1;
     float* stats = (float*)workspace;
-    float* part = (float*)((char*)workspace + align_up((size_t)B * sstride * 4, 256));
-    const int chunks = ls_chunks(B, TF, LS_TILE);
-    const size_t smem1 = (size_t)LS_TILE * (E + 1) * 4 + LS_TILE;
+    float* counts = (float*)((char*)workspace + align_up((size_t)B * sstride * 4, 256));
+    float* part = (float*)((char*)counts + align_up((size_t)B * LS_MAXS * 4, 256));
+    const int chunks = ls_chunks(B, TF, LS_PT);
+    const int EP = (E + 3) & ~3, nb = EP / 4, nt = nb * (nb + 1) / 2;
+    size_t smem1 = (size_t)LS_PT * EP * 4 + LS_PT * 4 + LS_PT;
+    smem1 = std::max(smem1, ((size_t)8 * nt * 16 + (size_t)4 * LS_MAXS * EP) * 4);
+    AMSS_LAUNCH(dpcl_count_kernel, B, 256, 0, stream, labels, TF, S, counts);
+    AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     dim3 grid(chunks, B);
-    AMSS_LAUNCH(dpcl_gram_kernel, grid, LS_THREADS, smem1, stream, V, labels, TF, E, S, part);
-    const size_t smem2 = (size_t)S * (E * E + E + 1) * 4;
-    AMSS_LAUNCH(dpcl_finalize_kernel, B, 256, smem2, stream, part, chunks, E, S, stats);
+    AMSS_LAUNCH(dpcl_gram_kernel, grid, LS_THREADS, smem1, stream, V, labels, counts, TF, E, S, part);
+    AMSS_LAUNCH(dpcl_finalize_kernel, B, 256, 0, stream, part, counts, chunks, E, S, stats);
     AMSS_LAUNCH(mean_of_stat_kernel, 1, 32, 0, stream, stats, B, sstride, sstride - 1, loss);
     return AMSS_OK;
 }
@@ -445,23 +545,37 @@ extern "C" int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const f
                                   int S, float* dV, const void* workspace, void* stream) {
     AMSS_REQUIRE(V && labels && dloss && dV && workspace, "dpcl_loss_bwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_bwd: S out of range");
-    const size_t smem = ((size_t)LS_THREADS * (E + 1) + (size_t)E * E + (size_t)S * E + S) * 4;
-    AMSS_REQUIRE(smem <= 200 * 1024, "dpcl_loss_bwd: E too large");
-    AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ls_chunks(B, TF, LS_THREADS), B);
-    AMSS_LAUNCH(dpcl_bwd_kernel, grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E,
-                S, dV);
+    AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd: E=%d outside [1,64]", E);
+    const size_t smem = ((size_t)E * LS_BPT + (size_t)LS_BP * E + (size_t)E * E + (size_t)S * E + S) * 4;
+    dim3 grid(ls_chunks(B, TF, LS_BP), B);
+    if ((E + 3) / 4 <= 10) {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(dpcl_bwd_kernel<10>, grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
+    } else {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(dpcl_bwd_kernel<16>, grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
+    }
     return AMSS_OK;
 }
 
 extern "C" int amss_l2norm_fwd(const float* z, int64_t rows, int E, float* v, float* inv_norm, void* stream) {
     AMSS_REQUIRE(z && v && rows > 0 && E > 0, "l2norm_fwd: bad arguments");
+    if (E % 4 == 0 && E <= 128 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+        AMSS_LAUNCH(l2norm_fwd_vec_kernel, 16 * kNumSMs, 256, 0, stream, (const float4*)z, rows, E / 4, (float4*)v, inv_norm);
+        return AMSS_OK;
+    }
     AMSS_LAUNCH(l2norm_fwd_kernel, 8 * kNumSMs, 256, 0, stream, z, rows, E, v, inv_norm);
     return AMSS_OK;
 }
 extern "C" int amss_l2norm_bwd(const float* v, const float* inv_norm, const float* dv, int64_t rows, int E, float* dz,
                                void* stream) {
     AMSS_REQUIRE(v && inv_norm && dv && dz, "l2norm_bwd: null pointer");
+    if (E % 4 == 0 && E <= 128 &&
+        ((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0) {
+        AMSS_LAUNCH(l2norm_bwd_vec_kernel, 16 * kNumSMs, 256, 0, stream, (const float4*)v, inv_norm, (const float4*)dv, rows,
+                    E / 4, (float4*)dz);
+        return AMSS_OK;
+    }
     AMSS_LAUNCH(l2norm_bwd_kernel, 8 * kNumSMs, 256, 0, stream, v, inv_norm, dv, rows, E, dz);
     return AMSS_OK;
 }
