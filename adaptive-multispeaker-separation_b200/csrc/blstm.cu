@@ -19,6 +19,7 @@ int gemm_dispatch(const float* A, int lda, const float* B, int ldb, const float*
                   int transb, int accumulate, int precision, float* C, int ldc, int swapB, int swapT, void* workspace,
                   size_t workspace_bytes, cudaStream_t st);
 bool blstm_rec_tc_supported(int B, int T, int H);
+void blstm_tc_set_profile(long long* dev_buf);
 int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gates, float* cst, float* y, int B, int T,
                      int H, float forget_bias, cudaStream_t st);
 int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,
@@ -375,5 +376,12 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
             if (rc != AMSS_OK) return rc;
         }
     }
+    return AMSS_OK;
+}
+
+// Diagnostics: clock64() stamps of the tcgen05 recurrence (CTA 0, steps 100..103, 12 slots per step) are
+// written to dev_buf (>= 48 int64) by subsequent amss_blstm_fwd calls; NULL switches it off.
+extern "C" int amss_debug_blstm_profile(long long* dev_buf) {
+    blstm_tc_set_profile(dev_buf);
     return AMSS_OK;
 }

@@ -30,7 +30,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int BT_THREADS = 288;   // warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA/control, 5-8 writers
+constexpr int BT_THREADS = 288;
+constexpr int FW_NACC = 1;        // forward: independent TMEM accumulators (K split round-robin), summed in the epilogue   // warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA/control, 5-8 writers
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -59,7 +60,13 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 // =================================================================================================
 // forward
 // =================================================================================================
+// Optional step profile (diagnostics): clock64() stamps of CTA 0, steps [PROF_S0, PROF_S0+4).
+constexpr int PROF_S0 = 100, PROF_N = 4, PROF_K = 12;
+long long* g_prof = nullptr;
+#define PROF(k) do { if (prof && s >= PROF_S0 && s < PROF_S0 + PROF_N) prof[(s - PROF_S0) * PROF_K + (k)] = clock64(); } while (0)
+
 struct RecTcFwd {
+    long long* prof;
     const float* Wh[2];   // [H][ldw]
     int ldw;
     float* gates;         // [2][T][B][4H] in: hoisted input projection (+bias); out: activated gates
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
     const uint32_t bar = smem_u32(&bar_mma);
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), NB < 32 ? 32 : NB);
+    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), FW_NACC * NB < 32 ? 32 : FW_NACC * NB);
     if (warp < 4) {   // pack this CTA's slice of W_h:  A[g][k] = Wh[k][gate(g)*H + u0 + g%32]
         const float* Wh = p.Wh[d];
         const int u = u0 + lane, g = warp * 32 + lane;
@@ -133,29 +140,43 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
             for (int b = 0; b < NB; ++b) zx[b] = (b < nvalid && ug < H) ? __ldcg(gp + (size_t)b * H4) : 0.f;
         };
         const float fb = q == 2 ? p.forget_bias : 0.f;
+        long long* prof = (blockIdx.x == 0 && tid == 0) ? p.prof : nullptr;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
+            PROF(0);
             load_zx(t);                           // in flight while the MMA of this step runs
             uint32_t acc[NB];
             if (s > 0) {
                 mbar_wait(bar, (s - 1) & 1);
+                PROF(1);
                 tc_fence_after();
-                if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16), acc);
-                else {
 #pragma unroll
-                    for (int c0 = 0; c0 < NB; c0 += 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, acc + c0);
+                for (int a = 0; a < FW_NACC; ++a) {
+                    if (a >= KCH / 2) break;          // fewer k-steps than accumulators (tiny H)
+                    uint32_t part[NB];
+                    if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + a * NB, part);
+                    else {
+#pragma unroll
+                        for (int c0 = 0; c0 < NB; c0 += 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + a * NB + c0, part + c0);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int b = 0; b < NB; ++b)
+                        acc[b] = a == 0 ? part[b] : __float_as_uint(__uint_as_float(acc[b]) + __uint_as_float(part[b]));
                 }
-                tmem_ld_wait();
             } else {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) acc[b] = 0u;
             }
+            PROF(2);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const float z = __uint_as_float(acc[b]) + zx[b] + fb;
                 gx[(q * 32 + lane) * GXP + b] = q == 1 ? tanh_fast(z) : sigmoid_fast(z);
             }
+            PROF(3);
             bar_sync_named(1, 256);               // gx complete (compute + writer warps)
+            PROF(4);
             const uint32_t hdst = smem_u32(h_s + ((s + 1) & 1) * h_bytes);
             float* cys = cy + (s & 1) * (2 * NB * 33);
 #pragma unroll
@@ -183,25 +204,33 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
                     }
                 }
             }
+            PROF(5);
             fence_proxy_async_cluster();
             tc_fence_before();
+            PROF(6);
             cluster_arrive_release();
+            PROF(7);
             cluster_wait();
+            PROF(8);
         }
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
+        long long* prof = (blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
         for (int s = 0; s < T; ++s) {
-            if (lane == 0 && s > 0) {
+            PROF(9);
+            if (s > 0) {                              // converged: every lane computes the (uniform) descriptors
                 tc_fence_after();
                 fence_async_smem();
                 const uint32_t aaddr = smem_u32(a_s), haddr = smem_u32(h_s + (s & 1) * h_bytes);
+                const bool leader = elect_one();
                 for (int kk = 0; kk < KCH / 2; ++kk) {
                     const uint64_t ad = smem_desc(aaddr + kk * 4096, 2048, 128);
                     const uint64_t bd = smem_desc(haddr + kk * 2 * BG * 128, BG * 128, 128);
-                    mma_bf16(tmem, ad, bd, idesc, kk > 0);
+                    if (leader) mma_bf16(tmem + (kk % FW_NACC) * NB, ad, bd, idesc, kk >= FW_NACC);
                 }
-                mma_commit(bar);
+                if (leader) mma_commit(bar);
             }
+            PROF(10);
             __syncwarp();
             cluster_arrive_relaxed();
             cluster_wait();
@@ -235,7 +264,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, NB < 32 ? 32 : NB);
+    if (warp == 4) tmem_dealloc(tmem, FW_NACC * NB < 32 ? 32 : FW_NACC * NB);
 }
 
 template <int NB>
@@ -422,16 +451,17 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
         // =========================== MMA issuer ===========================
         for (int s = T - 1; s >= 0; --s) {
             const int n = T - 1 - s;
-            if (lane == 0 && n > 0) {
+            if (n > 0) {                              // converged issue loop, elected lane executes the MMAs
                 tc_fence_after();
                 const uint32_t aaddr = smem_u32(a_s), zaddr = smem_u32(z_s);
-                for (int m = 0; m < MT; ++m)
-                    for (int kk = 0; kk < 8; ++kk) {
+                const bool leader = elect_one();
+                for (int kk = 0; kk < 8; ++kk)
+                    for (int m = 0; m < MT; ++m) {
                         const uint64_t ad = smem_desc(aaddr + m * 2048 + kk * 2 * (MT * 16) * 128, (MT * 16) * 128, 128);
                         const uint64_t bd = smem_desc(zaddr + kk * 2 * BG * 128, BG * 128, 128);
-                        mma_bf16(tmem + m * NB, ad, bd, idesc, kk > 0);
+                        if (leader) mma_bf16(tmem + m * NB, ad, bd, idesc, kk > 0);
                     }
-                mma_commit(bar);
+                if (leader) mma_commit(bar);
             }
             __syncwarp();
             cluster_arrive_relaxed();
@@ -491,6 +521,8 @@ int pick_nb(int B, int NC, int nb_max) {
 
 }  // namespace
 
+void blstm_tc_set_profile(long long* dev_buf) { g_prof = dev_buf; }
+
 bool blstm_rec_tc_supported(int B, int T, int H) {
     (void)B; (void)T;
     const int NC = (H + 31) / 32;
@@ -501,6 +533,7 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
                      int H, float forget_bias, cudaStream_t st) {
     const int NC = (H + 31) / 32;
     RecTcFwd p;
+    p.prof = g_prof;
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.y = y;
     p.B = B; p.T = T; p.H = H; p.forget_bias = forget_bias;
     const int nb = pick_nb(B, NC, 64);

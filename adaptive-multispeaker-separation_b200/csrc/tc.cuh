@@ -113,6 +113,19 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Warp-uniform leader election.  The MMA-issuing warp runs its loop CONVERGED (all lanes compute the
+// same descriptors, so the compiler keeps them in uniform registers) and only the elected lane
+// executes tcgen05.mma / tcgen05.commit; issuing from inside an `if (lane == 0)` region instead costs
+// an ELECT / R2UR.BROADCAST serialisation loop per operand (~90 clk per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {

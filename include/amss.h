@@ -139,6 +139,10 @@ int amss_blstm_bwd(const float* x, const float* kernel_fw, const float* kernel_b
                    float* dkernel_bw, float* dbias_bw, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Diagnostics only: clock64() stamps of the tensor-core recurrence (CTA 0, steps 100..103, 12
+ * slots per step) are written to dev_buf (>= 48 int64) by later amss_blstm_fwd calls; NULL = off. */
+int amss_debug_blstm_profile(long long* dev_buf);
+
 /* ------------------------------------------------------------------------------------ *
  * Dense / embedding head  (utils/ops.py:486-503 Conv1D k=1, :318-324 Normalize)
  * ------------------------------------------------------------------------------------ */

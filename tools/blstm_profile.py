@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Step profile of the tcgen05 BLSTM forward recurrence (diagnostics): prints clock deltas between the
+stamps of amss_debug_blstm_profile for steps 100..103 of CTA 0."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import amss_b200  # noqa: E402,F401
+from amss_b200 import ops, _lib  # noqa: E402
+
+NAMES = ["0 step start", "1 mma done", "2 tmem ld done", "3 activation done", "4 named bar", "5 cell done",
+         "6 fences", "7 arrive.release", "8 cluster wait", "9 mma warp start", "10 mma issued"]
+
+for B in (16, 64, 128):
+    T, I, H = 250, 600, 300
+    x = torch.randn(T, B, I, device="cuda") * 0.1
+    kf = torch.randn(I + H, 4 * H, device="cuda") * 0.05
+    kb = torch.randn(I + H, 4 * H, device="cuda") * 0.05
+    bf = torch.zeros(4 * H, device="cuda")
+    buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+    _lib.call("amss_debug_blstm_profile", buf.data_ptr())
+    for _ in range(3):
+        ops.blstm_fwd(x, kf, bf, kb, bf, precision=ops.AMSS_PREC_BF16)
+    torch.cuda.synchronize()
+    _lib.call("amss_debug_blstm_profile", 0)
+    p = buf.cpu().view(-1)[:48].view(4, 12)
+    print(f"--- B={B}")
+    for s in range(1, 3):
+        row = p[s]
+        base = int(row[0])
+        print(f" step {100 + s}: total {int(p[s + 1][0]) - base} clk ; " +
+              " ".join(f"[{k}]+{int(row[k]) - base}" for k in range(1, 11)))

@@ -242,6 +242,24 @@ int main() {
         c.ref = matmul(A, B, 256, 64);
         cases.push_back(c);
     }
+    {   // 6. padded strides (bank-conflict-free loader layouts): K-major A with LBO = 16*128+16, MN-major B with SBO = 144
+        Case c; c.name = "padded_kmajorA_mnmajorB"; c.N = 256; c.K = 64; c.a_mn = 0; c.b_mn = 1; c.use_bulk = 0;
+        auto A = rnd(128 * 64), B = rnd(256 * 64);
+        c.a_mnstride = 128; c.a_kstride = 16 * 128 + 16; c.b_mnstride = 144; c.b_kstride = 32 * 144;
+        c.a = image_kmajor(A, 128, 64, c.a_mnstride, c.a_kstride);
+        c.b = image_mnmajor(B, 256, 64, c.b_mnstride, c.b_kstride);
+        c.ref = matmul(A, B, 256, 64);
+        cases.push_back(c);
+    }
+    {   // 7. padded strides, the other pairing: MN-major A (SBO = 144), K-major B (LBO = 32*128+16)
+        Case c; c.name = "padded_mnmajorA_kmajorB"; c.N = 256; c.K = 64; c.a_mn = 1; c.b_mn = 0; c.use_bulk = 0;
+        auto A = rnd(128 * 64), B = rnd(256 * 64);
+        c.a_mnstride = 144; c.a_kstride = 16 * 144; c.b_mnstride = 128; c.b_kstride = 32 * 128 + 16;
+        c.a = image_mnmajor(A, 128, 64, c.a_mnstride, c.a_kstride);
+        c.b = image_kmajor(B, 256, 64, c.b_mnstride, c.b_kstride);
+        c.ref = matmul(A, B, 256, 64);
+        cases.push_back(c);
+    }
     int h1 = 0, h2 = 0, n = 0;
     for (auto& c : cases) {
         int r1 = run_case(c, false);
