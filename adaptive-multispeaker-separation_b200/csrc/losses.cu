@@ -195,8 +195,9 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
                 const float* __restrict__ stats, int B, int64_t TF, int E, int S, float* __restrict__ dV) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
     float* xt = reinterpret_cast<float*>(ls_smem);              // [E][LS_BPT]  transposed points
-    float* os = xt + E * LS_BPT;                                // [LS_BP][E]   results, row-major
-    float* An = os + LS_BP * E;                                 // [E][E]
+    const int EO = E | 1;                                       // odd row pitch of the result staging
+    float* os = xt + E * LS_BPT;                                // [LS_BP][EO]  results
+    float* An = os + LS_BP * EO;                                // [E][E]
     float* Bn = An + E * E;                                     // [S][E]
     float* dinv = Bn + S * E;                                   // [S]
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -205,7 +206,7 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
     for (int i = tid; i < E * E + S * E + S; i += LS_THREADS) An[i] = st[i];
     const float gscale = dloss[0] / (float)B;
     const int OBr = (E + 3) / 4;                                // outputs per thread (<= OB)
-    const int ob = tid >> 6, pg = tid & 63;
+    const int ob = tid & 3, pg = tid >> 2;                      // a warp = 8 point groups x 4 output blocks
     const int o0 = ob * OBr;
     const int64_t ntiles = (TF + LS_BP - 1) / LS_BP;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -241,12 +242,12 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
                 const float d = gscale * dinv[l];
 #pragma unroll
                 for (int j = 0; j < OB; ++j)
-                    if (j < OBr && o0 + j < E) os[p * E + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
+                    if (j < OBr && o0 + j < E) os[p * EO + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
             }
         }
         __syncthreads();
         float* dst = dV + ((size_t)b * TF + p0) * E;
-        for (int i = tid; i < np * E; i += LS_THREADS) dst[i] = os[i];
+        for (int i = tid; i < np * E; i += LS_THREADS) { const int pp = i / E; dst[i] = os[pp * EO + (i - pp * E)]; }
     }
 }
 
@@ -546,7 +547,7 @@ extern "C" int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const f
     AMSS_REQUIRE(V && labels && dloss && dV && workspace, "dpcl_loss_bwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_bwd: S out of range");
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd: E=%d outside [1,64]", E);
-    const size_t smem = ((size_t)E * LS_BPT + (size_t)LS_BP * E + (size_t)E * E + (size_t)S * E + S) * 4;
+    const size_t smem = ((size_t)E * LS_BPT + (size_t)LS_BP * (E | 1) + (size_t)E * E + (size_t)S * E + S) * 4;
     dim3 grid(ls_chunks(B, TF, LS_BP), B);
     if ((E + 3) / 4 <= 10) {
         AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

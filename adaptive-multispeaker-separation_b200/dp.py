@@ -1,0 +1,46 @@
+"""Data-parallel plumbing of the hot path: mixtures are independent units,
+so rank r takes rows [r*B/G, (r+1)*B/G) of every global batch (or its own synthetic stream), the
+parameters are replicated, and the ONLY collective is one all-reduce(sum) of the flat fp32 gradient
+buffer per step, scaled by 1/G inside the fused AMSGrad kernel.  Backend: NCCL over NVLink on the
+GPUs; the same code runs over gloo on CPU tensors (tests/test_dp_gloo.py).  No torch.cuda use here."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size, local_rank) from the launcher's environment (torchrun)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def active():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def shard_batch(batch, rank, world_size):
+    """Rows [r*B/G, (r+1)*B/G) of every array of a global (mix, non_mix, ind) batch."""
+    B = batch[0].shape[0]
+    if B % world_size:
+        raise ValueError(f"global batch {B} is not divisible by the world size {world_size}")
+    per = B // world_size
+    return tuple(a[rank * per:(rank + 1) * per] for a in batch)
+
+
+def allreduce_sum_(flat):
+    """The single collective of the path: in-place sum of the flat gradient buffer over all ranks.
+    Returns the scale (1/G) the optimizer must apply."""
+    if not active():
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return 1.0 / dist.get_world_size()
+
+
+def max_over_ranks(value, device="cpu"):
+    """Timing helper: max of a python float over ranks (multi-GPU numbers are max-over-ranks)."""
+    if not active():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)

@@ -97,43 +97,67 @@ class ParamStore:
 # --------------------------------------------------------------------------------------------
 # autograd wrappers (forward and backward are both library kernels)
 # --------------------------------------------------------------------------------------------
+def _as_time_major(x):
+    """[B,T,C] -> contiguous [T,B,C].  The BLSTM stack hands its activations on as transposed VIEWS of
+    time-major buffers, so between layers (and into the head) this is free; only a genuinely
+    batch-major tensor (the stack's input) costs one transpose kernel."""
+    xt = x.transpose(0, 1)
+    if xt.is_contiguous():
+        return xt
+    return ops.transpose_01(x.contiguous())
+
+
 class _BLSTMFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kf, bf, kb, bb, precision):
         need_bwd = any(ctx.needs_input_grad)
-        x_tm = ops.transpose_01(x.contiguous())
+        x_tm = _as_time_major(x)
         y_tm, saved = ops.blstm_fwd(x_tm, kf, bf, kb, bb, 1.0, precision, save_for_backward=need_bwd)
         if need_bwd:
             ctx.save_for_backward(x_tm, kf, kb, y_tm, saved)
         ctx.precision = precision
-        return ops.transpose_01(y_tm)
+        return y_tm.transpose(0, 1)              # [B,T,2H] view of the time-major result
 
     @staticmethod
     def backward(ctx, dy):
         x_tm, kf, kb, y_tm, saved = ctx.saved_tensors
-        dy_tm = ops.transpose_01(dy.contiguous())
+        dy_tm = _as_time_major(dy)
         dx, dkf, dbf, dkb, dbb = ops.blstm_bwd(x_tm, kf, kb, y_tm, dy_tm, saved, ctx.precision,
                                                need_dx=ctx.needs_input_grad[0])
-        return (ops.transpose_01(dx) if dx is not None else None), dkf, dbf, dkb, dbb, None
+        return (dx.transpose(0, 1) if dx is not None else None), dkf, dbf, dkb, dbb, None
 
 
 class _DenseFn(torch.autograd.Function):
-    """y[M,N] = x[M,K] @ W[K,N] + b   (tf.nn.conv1d with a [1,K,N] filter)."""
+    """y[M,N] = x[M,K] @ W[K,N] + b   (tf.nn.conv1d with a [1,K,N] filter).
+    swap=(B,T): the rows of x are time-major (t*B+b) and the rows of y batch-major (b*T+t) -- the
+    [T,B,*] -> [B,T,*] hand-over between the BLSTM stack and the embedding reshape, done by the
+    GEMM epilogue instead of a transpose pass."""
 
     @staticmethod
-    def forward(ctx, x, W, b, precision):
+    def forward(ctx, x, W, b, precision, swap):
         ctx.save_for_backward(x, W)
-        ctx.precision = precision
-        return ops.gemm(x, W, b, precision=precision)
+        ctx.precision, ctx.swap = precision, swap
+        return ops.gemm(x, W, b, precision=precision, out_swap=swap)
 
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = ops.gemm(dy, W, None, transb=True, precision=ctx.precision) if ctx.needs_input_grad[0] else None
-        dW = ops.gemm(x, dy, None, transa=True, precision=ctx.precision) if ctx.needs_input_grad[1] else None
-        db = ops.colsum(dy) if ctx.needs_input_grad[2] else None
-        return dx, dW, db, None
+        swap = ctx.swap
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            # rows of dy are batch-major; write dx back in x's (time-major) row order
+            dx = ops.gemm(dy, W, None, transb=True, precision=ctx.precision,
+                          out_swap=(swap[1], swap[0]) if swap else None)
+        if ctx.needs_input_grad[1]:
+            xr = x
+            if swap:                                # small [T*B,K] activation: bring it to dy's row order
+                Bq, Tq = swap
+                xr = ops.transpose_01(x.view(Tq, Bq, -1)).view(Bq * Tq, -1)
+            dW = ops.gemm(xr, dy, None, transa=True, precision=ctx.precision)
+        if ctx.needs_input_grad[2]:
+            db = ops.colsum(dy)
+        return dx, dW, db, None, None
 
 
 class _L2NormFn(torch.autograd.Function):
@@ -229,8 +253,8 @@ def blstm(x, kf, bf, kb, bb, precision=AMSS_PREC_FP32):
     return _BLSTMFn.apply(x, kf, bf, kb, bb, precision)
 
 
-def dense(x, W, b, precision=AMSS_PREC_FP32):
-    return _DenseFn.apply(x, W, b, precision)
+def dense(x, W, b, precision=AMSS_PREC_FP32, swap=None):
+    return _DenseFn.apply(x, W, b, precision, swap)
 
 
 def l2_normalize(z, E):
@@ -308,7 +332,13 @@ class Conv1D:
 
     def f_prop(self, x):
         B, Tt, C = x.shape
-        y = dense(x.reshape(B * Tt, C), self.store[f"{self.scope}/W"], self.store[f"{self.scope}/b"], self.precision)
+        W, b = self.store[f"{self.scope}/W"], self.store[f"{self.scope}/b"]
+        xt = x.transpose(0, 1)
+        if xt.is_contiguous() and not x.is_contiguous():
+            # time-major activations straight from the BLSTM stack: the GEMM epilogue remaps the rows
+            y = dense(xt.reshape(Tt * B, C), W, b, self.precision, swap=(B, Tt))
+        else:
+            y = dense(x.reshape(B * Tt, C), W, b, self.precision)
         return y.view(B, Tt, -1)
 
 

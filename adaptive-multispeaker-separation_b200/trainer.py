@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-from . import ops
+from . import dp, ops
 from .models import Adapt, DPCL, L41Model, DEFAULTS  # noqa: F401
 
 
@@ -146,10 +146,7 @@ class Trainer:
         self.store.grad_flat.zero_()
         cost = self.loss(x_mix, x_non_mix, ind)
         cost.backward()
-        scale = 1.0
-        if self.distributed:
-            torch.distributed.all_reduce(self.store.grad_flat)     # the single collective of the path
-            scale = 1.0 / self.world
+        scale = dp.allreduce_sum_(self.store.grad_flat)            # the single collective of the path
         self.optimizer.step(scale)
         return cost.detach()
 
