@@ -1,26 +1,30 @@
 // BLSTM recurrence on the 5th-gen tensor cores (utils/ops.py:358-383, BasicLSTMCell i,j,f,o).
 //
 // One thread-block CLUSTER per (direction, sub-batch of NB mixtures); CTA c of the cluster owns
-// hidden units [32c, 32c+32) for all T steps (persistent, weights resident in shared memory).
+// hidden units [32c, 32c+32) for all T steps (persistent).  The recurrent weights never move after
+// the prologue: each CTA's slice is converted to bf16 once and parked in TENSOR MEMORY as the A
+// operand (tcgen05.st), so a time step's MMAs read only the tiny activation operand from shared
+// memory (A-in-shared-memory MMAs at N = 16..64 cost ~100 clk each in operand fetch, measured).
 //
 // Forward step:  D[gate col, mixture] = W_h^T[own 128 gate cols, :] * h_{t-1}^T
-//   * A operand  = the CTA's 128 gate columns of W_h (lane = gate*32 + unit), bf16, K-major
-//     core-matrix layout, packed once;
-//   * B operand  = h_{t-1} of the whole direction, [NB x H] bf16 K-major, double buffered in every
-//     CTA; each CTA scatters its 32 fresh h columns into ALL CTAs of the cluster with
-//     st.shared::cluster (DSMEM) and ONE barrier.cluster per step publishes them;
-//   * D in TMEM: 128 lanes (gate columns) x NB columns (mixtures), fp32.
-//   Fused epilogue: tcgen05.ld -> + hoisted input projection (prefetched one step ahead) ->
+//   * A (TMEM)  = the CTA's 128 gate columns of W_h (lane = gate*32 + unit), K = H;
+//   * B (smem)  = h_{t-1} of the whole direction, [NB x H] bf16 K-major core matrices, double buffered
+//     in every CTA.  After its cell update a CTA stages its 32 fresh h columns (a contiguous block of
+//     the operand layout) and ONE thread pushes the block to every CTA of the cluster with
+//     cp.async.bulk shared::cta -> shared::cluster; the copies complete_tx on the DESTINATION's
+//     mbarrier, so the data path has no barrier.cluster at all -- the MMA warp of each CTA just waits
+//     for NC blocks on its local mbarrier;
+//   * D (TMEM)  = 128 lanes (gate columns) x NB columns (mixtures), fp32.
+//   Fused epilogue: tcgen05.ld -> + hoisted input projection (loaded while the MMAs run) ->
 //   sigmoid/tanh (MUFU.TANH) -> cell/hidden update with the cell state in registers for all T steps.
 //
 // Backward step (reverse time):  dh_t = dy_t + dz_{t+1} W_h^T.  CTA c multiplies ITS OWN 128 dz
 //   columns (B operand, produced locally, never gathered) with the matching W_h columns
-//   (A = W_h[all units, own cols], M = H in 128-row tiles, K = 128) and reduce-scatters the partial
-//   sums (bf16) through DSMEM to the CTAs owning the units; again one barrier.cluster per step.
+//   (A = W_h[all units, own cols] in TMEM, M = H in 128-row tiles, K = 128) and reduce-scatters the
+//   bf16 partial sums to the unit owners with the same bulk-copy / remote-mbarrier scheme.
 //
-// Global stores (saved gates, c, y, dZ) are issued by dedicated WRITER warps that join the cluster
-// barrier with .relaxed semantics, so the release fence of the compute warps never waits for
-// outstanding global-memory traffic.
+// Global stores (saved gates, c, y, dZ) are issued by dedicated WRITER warps from shared-memory
+// staging, one step behind, so the recurrence never waits for global-memory traffic.
 #include "common.cuh"
 #include "tc.cuh"
 #include <algorithm>
@@ -30,41 +34,34 @@ namespace {
 
 using namespace tc;
 
-constexpr int BT_THREADS = 288;
-constexpr int FW_NACC = 1;        // forward: independent TMEM accumulators (K split round-robin), summed in the epilogue   // warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA/control, 5-8 writers
+constexpr int BT_THREADS = 288;   // warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA/control, 5-8 writers
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint2 v) {
-    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive_named(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__host__ __device__ inline uint32_t pow2_cols(uint32_t c) { uint32_t r = 32; while (r < c) r <<= 1; return r; }
 
-// =================================================================================================
-// forward
-// =================================================================================================
 // Optional step profile (diagnostics): clock64() stamps of CTA 0, steps [PROF_S0, PROF_S0+4).
 constexpr int PROF_S0 = 100, PROF_N = 4, PROF_K = 12;
 long long* g_prof = nullptr;
 #define PROF(k) do { if (prof && s >= PROF_S0 && s < PROF_S0 + PROF_N) prof[(s - PROF_S0) * PROF_K + (k)] = clock64(); } while (0)
 
+// =================================================================================================
+// forward
+// =================================================================================================
 struct RecTcFwd {
     long long* prof;
     const float* Wh[2];   // [H][ldw]
@@ -76,10 +73,15 @@ struct RecTcFwd {
     float forget_bias;
 };
 
+// Dependent tcgen05.mma into ONE accumulator serialise at the MMA pipeline latency (~75 clk each at N = 16..64,
+// measured), so the K steps are dealt round-robin to FW_NACC independent accumulators, summed in the epilogue.
+constexpr int FW_NACC = 4;
+constexpr uint32_t FW_ACOL = 256;     // TMEM: D_a at columns [a*NB, (a+1)*NB), A at [FW_ACOL, FW_ACOL + 8*ksteps)
+
 template <int NB>
 __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ __align__(8) uint64_t bars[3];          // [0] MMA done, [1..2] h_full[buf]
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), NC = cluster_nctarank();
@@ -87,52 +89,65 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
     const int H = p.H, T = p.T, B = p.B, H4 = 4 * H;
     const int b0 = sub * NB, nvalid = min(NB, B - b0);
     const int u0 = crank * 32;
-    const int KCH = (H + 15) / 16 * 2;            // k-chunks (of 8) consumed by the MMAs
-    const int KCHB = NC * 4;                      // k-chunks present in the h buffers
+    const int KST = (H + 15) / 16;                // K steps of 16
+    const int KCHB = NC * 4;                      // k-chunks (of 8) present in the h buffers
     constexpr int BG = NB / 8;                    // batch groups of 8
     constexpr int GXP = NB + 1;                   // gx row pitch
-    const uint32_t a_bytes = (uint32_t)KCH * 2048, h_bytes = (uint32_t)KCHB * BG * 128;
-    uint8_t* a_s = smem;
-    uint8_t* h_s = smem + a_bytes;                                    // [2][h_bytes]
-    float* gx = reinterpret_cast<float*>(h_s + 2 * h_bytes);          // [128][NB+1] activated gates
-    float* cy = gx + 128 * GXP;                                       // [2][2][NB][33]  (c | h) staging
-    const uint32_t bar = smem_u32(&bar_mma);
+    constexpr uint32_t SLICE = 4 * BG * 128;      // bytes of one CTA's h block (32 units x NB mixtures, bf16)
+    const uint32_t h_bytes = (uint32_t)KCHB * BG * 128;
+    uint8_t* h_s = smem;                                              // [2][h_bytes]   B operand
+    uint8_t* hst = h_s + 2 * h_bytes;                                 // [2][SLICE]     own block, source of the bulk copies
+    float* gx = reinterpret_cast<float*>(hst + 2 * SLICE);            // [2][128][NB+1] activated gates
+    float* cy = gx + 2 * 128 * GXP;                                   // [2][2][NB][33] (c | h) staging for the writers
+    const uint32_t bar_mma = smem_u32(&bars[0]), h_full = smem_u32(&bars[1]);
+    const uint32_t tcols = pow2_cols(FW_ACOL + 8 * KST);
 
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), FW_NACC * NB < 32 ? 32 : FW_NACC * NB);
-    if (warp < 4) {   // pack this CTA's slice of W_h:  A[g][k] = Wh[k][gate(g)*H + u0 + g%32]
-        const float* Wh = p.Wh[d];
-        const int u = u0 + lane, g = warp * 32 + lane;
-        for (int kc = 0; kc < KCH; ++kc) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k = kc * 8 + e;
-                v[e] = (u < H && k < H) ? __ldg(Wh + (size_t)k * p.ldw + warp * H + u) : 0.f;
-            }
-            *reinterpret_cast<uint4*>(a_s + (size_t)(kc * 16 + (g >> 3)) * 128 + (g & 7) * 16) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        }
+    if (tid == 0) {
+        mbar_init(bar_mma, 1); mbar_init(h_full, 1); mbar_init(h_full + 8, 1);
+        mbar_fence_init();
     }
+    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), tcols);
     for (uint32_t i = tid * 16; i < 2 * h_bytes; i += BT_THREADS * 16) *reinterpret_cast<uint4*>(h_s + i) = make_uint4(0, 0, 0, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (warp < 4) {   // park this CTA's W_h slice in TMEM:  A[g][k] = Wh[k][gate(g)*H + u0 + g%32]
+        const float* Wh = p.Wh[d];
+        const int u = u0 + lane;
+        for (int kk = 0; kk < KST; ++kk) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kk * 16 + 2 * j;
+                const float e0 = (u < H && k < H) ? __ldg(Wh + (size_t)k * p.ldw + warp * H + u) : 0.f;
+                const float e1 = (u < H && k + 1 < H) ? __ldg(Wh + (size_t)(k + 1) * p.ldw + warp * H + u) : 0.f;
+                w[j] = pack_bf16(e0, e1);
+            }
+            tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + FW_ACOL + kk * 8, w);
+        }
+        tmem_st_wait();
+    }
+    if (tid == 0) {   // arm the first phase of both h buffers (h_0 -> buf 1, h_1 -> buf 0)
+        if (T > 1) mbar_expect_tx(h_full + 8, NC * SLICE);
+        if (T > 2) mbar_expect_tx(h_full, NC * SLICE);
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    cluster_arrive_release();
-    cluster_wait();
+    cluster_sync_all();                               // every CTA's barriers / buffers are ready for remote traffic
     tc_fence_after();
-    const uint32_t tmem = tmem_base_s;
     const uint32_t idesc = idesc_bf16(128, NB, 0, 0);
 
     if (warp < 4) {
         // =========================== compute warps ===========================
         const int q = warp, ug = u0 + lane;
-        constexpr int ITEMS = (4 * NB + 127) / 128;   // (k-chunk, mixture) items per thread in the cell phase
-        float creg[ITEMS][8];
+        constexpr int ITEMS = (8 * NB + 127) / 128;   // (k-chunk, half, mixture) items of 4 units per thread in the cell phase
+        float creg[ITEMS][4];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) creg[i][e] = 0.f;
+            for (int e = 0; e < 4; ++e) creg[i][e] = 0.f;
         float zx[NB];
         auto load_zx = [&](int t) {
             const float* gp = p.gates + (((size_t)d * T + t) * B + b0) * H4 + q * H + ug;
@@ -144,15 +159,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
             PROF(0);
-            load_zx(t);                           // in flight while the MMA of this step runs
+            load_zx(t);                           // in flight while the MMAs of this step run
             uint32_t acc[NB];
             if (s > 0) {
-                mbar_wait(bar, (s - 1) & 1);
+                mbar_wait(bar_mma, (s - 1) & 1);
                 PROF(1);
                 tc_fence_after();
 #pragma unroll
                 for (int a = 0; a < FW_NACC; ++a) {
-                    if (a >= KCH / 2) break;          // fewer k-steps than accumulators (tiny H)
+                    if (a >= KST) break;              // fewer K steps than accumulators (tiny H)
                     uint32_t part[NB];
                     if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + a * NB, part);
                     else {
@@ -164,76 +179,72 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
                     for (int b = 0; b < NB; ++b)
                         acc[b] = a == 0 ? part[b] : __float_as_uint(__uint_as_float(acc[b]) + __uint_as_float(part[b]));
                 }
+                tc_fence_before();
             } else {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) acc[b] = 0u;
             }
             PROF(2);
+            float* gxs = gx + (s & 1) * (128 * GXP);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const float z = __uint_as_float(acc[b]) + zx[b] + fb;
-                gx[(q * 32 + lane) * GXP + b] = q == 1 ? tanh_fast(z) : sigmoid_fast(z);
+                gxs[(q * 32 + lane) * GXP + b] = q == 1 ? tanh_fast(z) : sigmoid_fast(z);
             }
             PROF(3);
-            bar_sync_named(1, 256);               // gx complete (compute + writer warps)
+            bar_sync_named(1, 256);               // gx[s&1] complete (compute + writer warps)
             PROF(4);
-            const uint32_t hdst = smem_u32(h_s + ((s + 1) & 1) * h_bytes);
+            uint8_t* hsl = hst + (s & 1) * SLICE;
             float* cys = cy + (s & 1) * (2 * NB * 33);
 #pragma unroll
             for (int it = 0; it < ITEMS; ++it) {
                 const int item = tid + it * 128;
-                if (item < 4 * NB) {
-                    const int kc = item / NB, b = item % NB;
-                    float hv[8];
+                if (item < 8 * NB) {
+                    const int kc = item / (2 * NB), rem = item % (2 * NB), half = rem / NB, b = rem % NB;
+                    float hv[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int ul = kc * 8 + e;
-                        const float gi = gx[(0 * 32 + ul) * GXP + b], gj = gx[(1 * 32 + ul) * GXP + b];
-                        const float gf = gx[(2 * 32 + ul) * GXP + b], go = gx[(3 * 32 + ul) * GXP + b];
+                    for (int e = 0; e < 4; ++e) {
+                        const int ul = kc * 8 + half * 4 + e;
+                        const float gi = gxs[(0 * 32 + ul) * GXP + b], gj = gxs[(1 * 32 + ul) * GXP + b];
+                        const float gf = gxs[(2 * 32 + ul) * GXP + b], go = gxs[(3 * 32 + ul) * GXP + b];
                         const float c = fmaf(creg[it][e], gf, gi * gj);
                         creg[it][e] = c;
                         hv[e] = b < nvalid ? tanh_fast(c) * go : 0.f;
                         cys[b * 33 + ul] = c;
                         cys[NB * 33 + b * 33 + ul] = hv[e];
                     }
-                    if (s + 1 < T) {
-                        const uint4 pk = make_uint4(pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]), pack_bf16(hv[4], hv[5]),
-                                                    pack_bf16(hv[6], hv[7]));
-                        const uint32_t off = (uint32_t)(((crank * 4 + kc) * BG + (b >> 3)) * 128 + (b & 7) * 16);
-                        for (uint32_t r = 0; r < NC; ++r) st_cluster_v4(mapa(hdst + off, r), pk);
-                    }
+                    *reinterpret_cast<uint2*>(hsl + (size_t)(kc * BG + (b >> 3)) * 128 + (b & 7) * 16 + half * 8) =
+                        make_uint2(pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]));
                 }
             }
             PROF(5);
-            fence_proxy_async_cluster();
-            tc_fence_before();
+            fence_async_smem();                   // staged block -> visible to the bulk-copy engine
+            bar_sync_named(2, 128);
             PROF(6);
-            cluster_arrive_release();
+            if ((uint32_t)tid < NC && s + 1 < T) {     // one bulk copy per thread: all NC pushes issue in parallel
+                const uint32_t dst = smem_u32(h_s + ((s + 1) & 1) * h_bytes) + crank * SLICE;
+                const uint32_t bar = h_full + 8 * ((s + 1) & 1);
+                bulk_s2c(mapa(dst, tid), smem_u32(hsl), SLICE, mapa(bar, tid));
+            }
             PROF(7);
-            cluster_wait();
-            PROF(8);
         }
     } else if (warp == 4) {
-        // =========================== MMA issuer ===========================
+        // =========================== MMA issuer (converged loop, elected lane) ===========================
         long long* prof = (blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
-        for (int s = 0; s < T; ++s) {
+        const bool leader = elect_one();
+        for (int s = 1; s < T; ++s) {
+            const uint32_t buf = s & 1;
+            mbar_wait(h_full + 8 * buf, ((s - 1) >> 1) & 1);        // all NC blocks of h_{s-1} have landed
             PROF(9);
-            if (s > 0) {                              // converged: every lane computes the (uniform) descriptors
-                tc_fence_after();
-                fence_async_smem();
-                const uint32_t aaddr = smem_u32(a_s), haddr = smem_u32(h_s + (s & 1) * h_bytes);
-                const bool leader = elect_one();
-                for (int kk = 0; kk < KCH / 2; ++kk) {
-                    const uint64_t ad = smem_desc(aaddr + kk * 4096, 2048, 128);
-                    const uint64_t bd = smem_desc(haddr + kk * 2 * BG * 128, BG * 128, 128);
-                    if (leader) mma_bf16(tmem + (kk % FW_NACC) * NB, ad, bd, idesc, kk >= FW_NACC);
-                }
-                if (leader) mma_commit(bar);
+            if (leader && s + 2 < T) mbar_expect_tx(h_full + 8 * buf, NC * SLICE);   // re-arm for h_{s+1}
+            tc_fence_after();
+            const uint32_t haddr = smem_u32(h_s + buf * h_bytes);
+            for (int kk = 0; kk < KST; ++kk) {
+                const uint64_t bd = smem_desc(haddr + kk * 2 * BG * 128, BG * 128, 128);
+                if (leader) mma_bf16_ts(tmem + (kk % FW_NACC) * NB, tmem + FW_ACOL + kk * 8, bd, idesc, kk >= FW_NACC);
             }
+            if (leader) mma_commit(bar_mma);
             PROF(10);
-            __syncwarp();
-            cluster_arrive_relaxed();
-            cluster_wait();
         }
     } else {
         // =========================== writer warps: saved gates, c, y -> global ===========================
@@ -252,25 +263,26 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
             bar_sync_named(1, 256);
+            const float* gxs = gx + (s & 1) * (128 * GXP);
             if (wu < H) {
                 float* gout = p.gates + (((size_t)d * T + t) * B + b0) * H4 + wq * H + wu;
-                for (int b = 0; b < nvalid; ++b) __stcg(gout + (size_t)b * H4, gx[wt * GXP + b]);
+                for (int b = 0; b < nvalid; ++b) __stcg(gout + (size_t)b * H4, gxs[wt * GXP + b]);
             }
             if (s > 0) flush_cy(s - 1);
-            cluster_arrive_relaxed();
-            cluster_wait();
         }
+        bar_sync_named(3, 256);                       // the last cell phase has written cy
         flush_cy(T - 1);
     }
+    if (warp < 4) bar_sync_named(3, 256);
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, FW_NACC * NB < 32 ? 32 : FW_NACC * NB);
+    cluster_sync_all();                               // no CTA exits while peers may still push into it
+    if (warp == 4) tmem_dealloc(tmem, tcols);
 }
 
 template <int NB>
 int launch_fwd(const RecTcFwd& p, int NC, cudaStream_t st) {
-    const int KCH = (p.H + 15) / 16 * 2, KCHB = NC * 4;
-    const size_t smem = (size_t)KCH * 2048 + 2 * (size_t)KCHB * (NB / 8) * 128 + (size_t)128 * (NB + 1) * 4 +
+    const size_t smem = 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)2 * 128 * (NB + 1) * 4 +
                         (size_t)2 * 2 * NB * 33 * 4;
     if (smem > 226 * 1024) { set_error("blstm_rec_fwd_tc: H=%d NB=%d needs %zu B of shared memory", p.H, NB, smem); return AMSS_ERR_UNSUPPORTED; }
     AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_fwd_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -302,10 +314,12 @@ struct RecTcBwd {
     int B, T, H, nsub, MT;
 };
 
+constexpr uint32_t BW_ACOL = 256;     // TMEM: D tile (m, parity of the K step) at [(2m+par)*NB, +NB), A tile m at [BW_ACOL + 64m, +64)
+
 template <int NB>
 __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ __align__(8) uint64_t bars[3];          // [0] MMA done, [1..2] r_full[buf]
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), NC = cluster_nctarank();
@@ -315,38 +329,51 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
     const int u0 = crank * 32;
     constexpr int BG = NB / 8;
     constexpr int ZP = NB + 1;
-    const uint32_t a_bytes = (uint32_t)MT * 128 * 128 * 2;               // [MT*128 units][128 own cols] bf16
-    const uint32_t r_bytes = (uint32_t)NC * 32 * NB * 2;                 // partial sums from every CTA, bf16
-    uint8_t* a_s = smem;
-    uint8_t* z_s = a_s + a_bytes;                                        // dz operand [NB][128] bf16, K-major
-    uint8_t* r_s = z_s + NB * 128 * 2;                                   // [2][NC][32][NB] bf16
-    float* dzs = reinterpret_cast<float*>(r_s + 2 * r_bytes);            // [128][NB+1] fp32 dz staging for the writers
-    const uint32_t bar = smem_u32(&bar_mma);
-    const uint32_t tcols = MT * NB <= 32 ? 32 : (MT * NB <= 64 ? 64 : (MT * NB <= 128 ? 128 : 256));
+    constexpr uint32_t BLK = 32 * NB * 2;                                // one (src CTA -> dest CTA) block of bf16 partial sums
+    const uint32_t r_bytes = (uint32_t)NC * BLK;
+    uint8_t* z_s = smem;                                                 // dz operand [NB][128] bf16, K-major
+    uint8_t* r_s = z_s + NB * 128 * 2;                                   // [2][NC][32][NB] bf16   received partials
+    uint8_t* p_s = r_s + 2 * r_bytes;                                    // [2][NC][32][NB] bf16   partials to send (by dest)
+    float* dzs = reinterpret_cast<float*>(p_s + 2 * r_bytes);            // [2][128][NB+1] fp32 dz staging for the writers
+    const uint32_t bar_mma = smem_u32(&bars[0]), r_full = smem_u32(&bars[1]);
+    const uint32_t tcols = pow2_cols(BW_ACOL + 64 * MT);
 
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), tcols);
-    {   // pack A[u][g] = Wh[u][gate(g)*H + u0 + g%32]; unit id = (u, k-chunk of 8 own cols)
-        const float* Wh = p.Wh[d];
-        const int nunits = MT * 128 * 16;
-        for (int id = tid; id < nunits; id += BT_THREADS) {
-            const int u = id % (MT * 128), kc = id / (MT * 128);
-            const int gate = kc >> 2, ul = (kc & 3) * 8;
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                v[e] = (u < H && u0 + ul + e < H) ? __ldg(Wh + (size_t)u * p.ldw + gate * H + u0 + ul + e) : 0.f;
-            *reinterpret_cast<uint4*>(a_s + (size_t)(kc * (MT * 16) + (u >> 3)) * 128 + (u & 7) * 16) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        }
+    if (tid == 0) {
+        mbar_init(bar_mma, 1); mbar_init(r_full, 1); mbar_init(r_full + 8, 1);
+        mbar_fence_init();
     }
-    fence_async_smem();
+    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), tcols);
     tc_fence_before();
     __syncthreads();
-    cluster_arrive_release();
-    cluster_wait();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    if (warp < 4) {   // park A[u][g] = Wh[u][gate(g)*H + u0 + g%32] in TMEM (lane = unit of the M tile)
+        const float* Wh = p.Wh[d];
+        for (int m = 0; m < MT; ++m) {
+            const int u = m * 128 + warp * 32 + lane;
+            for (int kk = 0; kk < 8; ++kk) {
+                const int gate = kk >> 1, ul = (kk & 1) * 16;
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c0 = u0 + ul + 2 * j;
+                    const float e0 = (u < H && c0 < H) ? __ldg(Wh + (size_t)u * p.ldw + gate * H + c0) : 0.f;
+                    const float e1 = (u < H && c0 + 1 < H) ? __ldg(Wh + (size_t)u * p.ldw + gate * H + c0 + 1) : 0.f;
+                    w[j] = pack_bf16(e0, e1);
+                }
+                tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + BW_ACOL + m * 64 + kk * 8, w);
+            }
+        }
+        tmem_st_wait();
+    }
+    if (tid == 0) {   // arm the first phase of both receive buffers (step 1 -> buf 1, step 2 -> buf 0)
+        if (T > 1) mbar_expect_tx(r_full + 8, NC * BLK);
+        if (T > 2) mbar_expect_tx(r_full, NC * BLK);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
     const uint32_t idesc = idesc_bf16(128, NB, 0, 0);
 
     if (warp < 4) {
@@ -357,7 +384,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
         float dcc[IT];
 #pragma unroll
         for (int i = 0; i < IT; ++i) dcc[i] = 0.f;
-        float sv[IT][7];                              // gi gj gf go c cprev dy  (prefetched one step ahead)
+        float sv[IT][7];                              // gi gj gf go c cprev dy  (loaded while the MMAs run)
         auto prefetch = [&](int s) {
             const int t = d == 0 ? s : T - 1 - s;
             const int tprev = d == 0 ? t - 1 : t + 1;
@@ -378,41 +405,47 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
         };
         for (int s = T - 1; s >= 0; --s) {
             const int n = T - 1 - s;                  // step counter
-            prefetch(s);                              // in flight while the MMA of this step runs
-            const uint32_t rbuf = smem_u32(r_s + (n & 1) * r_bytes);
+            prefetch(s);
+            float dh[IT];
             if (n > 0) {
-                // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]  ->  owner CTA of unit u
-                mbar_wait(bar, (n - 1) & 1);
+                // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]  ->  staged per owner CTA
+                uint8_t* ps = p_s + (n & 1) * r_bytes;
+                mbar_wait(bar_mma, (n - 1) & 1);
                 tc_fence_after();
                 for (int m = 0; m < MT; ++m) {
                     const uint32_t dest = m * 4 + q;  // units m*128 + q*32 + lane  ->  CTA dest, local unit = lane
-                    uint32_t acc[NB];
-                    if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
-                    else tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
+                    uint32_t acc[NB], acc1[NB];
+                    if (NB == 16) { tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 2 * m * NB, acc); tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (2 * m + 1) * NB, acc1); }
+                    else { tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 2 * m * NB, acc); tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (2 * m + 1) * NB, acc1); }
                     tmem_ld_wait();
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) acc[b] = __float_as_uint(__uint_as_float(acc[b]) + __uint_as_float(acc1[b]));
                     if (dest < NC) {
-                        const uint32_t base = mapa(rbuf + (crank * 32 + lane) * (NB * 2), dest);
+                        uint8_t* pd = ps + (size_t)dest * BLK + lane * (NB * 2);
 #pragma unroll
                         for (int b = 0; b < NB; b += 8)
-                            st_cluster_v4(base + b * 2,
-                                          make_uint4(pack_bf16(__uint_as_float(acc[b]), __uint_as_float(acc[b + 1])),
-                                                     pack_bf16(__uint_as_float(acc[b + 2]), __uint_as_float(acc[b + 3])),
-                                                     pack_bf16(__uint_as_float(acc[b + 4]), __uint_as_float(acc[b + 5])),
-                                                     pack_bf16(__uint_as_float(acc[b + 6]), __uint_as_float(acc[b + 7]))));
+                            *reinterpret_cast<uint4*>(pd + b * 2) =
+                                make_uint4(pack_bf16(__uint_as_float(acc[b]), __uint_as_float(acc[b + 1])),
+                                           pack_bf16(__uint_as_float(acc[b + 2]), __uint_as_float(acc[b + 3])),
+                                           pack_bf16(__uint_as_float(acc[b + 4]), __uint_as_float(acc[b + 5])),
+                                           pack_bf16(__uint_as_float(acc[b + 6]), __uint_as_float(acc[b + 7])));
                     }
                 }
                 tc_fence_before();
-            }
-            cluster_arrive_release();
-            cluster_wait();
-            // reduce the partials of every CTA for (unit = lane, mixtures q*IT .. +IT)
-            float dh[IT];
-#pragma unroll
-            for (int i = 0; i < IT; ++i) dh[i] = sv[i][6];
-            if (n > 0) {
+                fence_async_smem();
+                bar_sync_named(2, 128);
+                if ((uint32_t)tid < NC) {                 // one bulk copy per thread
+                    const uint32_t dst = smem_u32(r_s + (n & 1) * r_bytes) + crank * BLK;
+                    const uint32_t bar = r_full + 8 * (n & 1);
+                    bulk_s2c(mapa(dst, tid), smem_u32(ps) + tid * BLK, BLK, mapa(bar, tid));
+                }
+                mbar_wait(r_full + 8 * (n & 1), ((n - 1) >> 1) & 1);       // every CTA's partials for my units have landed
+                if (tid == 0 && n + 2 < T) mbar_expect_tx(r_full + 8 * (n & 1), NC * BLK);   // re-arm for step n+2
                 const uint8_t* rb = r_s + (n & 1) * r_bytes + (size_t)lane * (NB * 2) + q * IT * 2;
+#pragma unroll
+                for (int i = 0; i < IT; ++i) dh[i] = sv[i][6];
                 for (uint32_t c = 0; c < NC; ++c) {
-                    const uint8_t* rp = rb + (size_t)c * 32 * NB * 2;
+                    const uint8_t* rp = rb + (size_t)c * BLK;
                     if (IT == 4) {
                         const uint2 w = *reinterpret_cast<const uint2*>(rp);
                         dh[0] += bf16_lo(w.x); dh[1] += bf16_hi(w.x); dh[2] += bf16_lo(w.y); dh[3] += bf16_hi(w.y);
@@ -422,8 +455,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                         dh[4 % IT] += bf16_lo(w.z); dh[5 % IT] += bf16_hi(w.z); dh[6 % IT] += bf16_lo(w.w); dh[7 % IT] += bf16_hi(w.w);
                     }
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < IT; ++i) dh[i] = sv[i][6];
             }
             // gate derivatives; dz -> fp32 staging (writers) and bf16 operand of the next step's MMA
+            float* dzb = dzs + (n & 1) * (128 * ZP);
 #pragma unroll
             for (int i = 0; i < IT; ++i) {
                 const int b = q * IT + i;
@@ -438,7 +475,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 dcc[i] = dc * gf;
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
-                    dzs[(g4 * 32 + lane) * ZP + b] = dz[g4];
+                    dzb[(g4 * 32 + lane) * ZP + b] = dz[g4];
                     const int k = g4 * 32 + lane;
                     *reinterpret_cast<__nv_bfloat16*>(z_s + (size_t)((k >> 3) * BG + (b >> 3)) * 128 + (b & 7) * 16 + (k & 7) * 2) =
                         __float2bfloat16_rn(dz[g4]);
@@ -448,49 +485,44 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
             bar_sync_named(1, 288);                   // dz staged: MMA warp may issue, writers may store
         }
     } else if (warp == 4) {
-        // =========================== MMA issuer ===========================
-        for (int s = T - 1; s >= 0; --s) {
-            const int n = T - 1 - s;
-            if (n > 0) {                              // converged issue loop, elected lane executes the MMAs
+        // =========================== MMA issuer (converged loop, elected lane) ===========================
+        const bool leader = elect_one();
+        for (int n = 0; n < T; ++n) {
+            if (n > 0) {
                 tc_fence_after();
-                const uint32_t aaddr = smem_u32(a_s), zaddr = smem_u32(z_s);
-                const bool leader = elect_one();
+                const uint32_t zaddr = smem_u32(z_s);
                 for (int kk = 0; kk < 8; ++kk)
                     for (int m = 0; m < MT; ++m) {
-                        const uint64_t ad = smem_desc(aaddr + m * 2048 + kk * 2 * (MT * 16) * 128, (MT * 16) * 128, 128);
                         const uint64_t bd = smem_desc(zaddr + kk * 2 * BG * 128, BG * 128, 128);
-                        if (leader) mma_bf16(tmem + m * NB, ad, bd, idesc, kk > 0);
+                        if (leader) mma_bf16_ts(tmem + (2 * m + (kk & 1)) * NB, tmem + BW_ACOL + m * 64 + kk * 8, bd, idesc, kk > 1);
                     }
-                if (leader) mma_commit(bar);
+                if (leader) mma_commit(bar_mma);
             }
             __syncwarp();
-            cluster_arrive_relaxed();
-            cluster_wait();
             bar_sync_named(1, 288);
         }
     } else {
         // =========================== writer warps: dZ -> global ===========================
         const int wt = tid - 160, wq = wt >> 5, wu = u0 + (wt & 31);
         for (int s = T - 1; s >= 0; --s) {
-            const int t = d == 0 ? s : T - 1 - s;
-            cluster_arrive_relaxed();
-            cluster_wait();
+            const int t = d == 0 ? s : T - 1 - s, n = T - 1 - s;
             bar_sync_named(1, 288);
+            const float* dzb = dzs + (n & 1) * (128 * ZP);
             if (wu < H) {
                 float* zo = p.dZ + (((size_t)d * T + t) * B + b0) * H4 + wq * H + wu;
-                for (int b = 0; b < nvalid; ++b) __stcg(zo + (size_t)b * H4, dzs[wt * ZP + b]);
+                for (int b = 0; b < nvalid; ++b) __stcg(zo + (size_t)b * H4, dzb[wt * ZP + b]);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     if (warp == 4) tmem_dealloc(tmem, tcols);
 }
 
 template <int NB>
 int launch_bwd(const RecTcBwd& p, int NC, cudaStream_t st) {
-    const size_t smem = (size_t)p.MT * 128 * 128 * 2 + (size_t)NB * 128 * 2 + 2 * (size_t)NC * 32 * NB * 2 +
-                        (size_t)128 * (NB + 1) * 4;
+    const size_t smem = (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4;
     if (smem > 226 * 1024) { set_error("blstm_rec_bwd_tc: H=%d NB=%d needs %zu B of shared memory", p.H, NB, smem); return AMSS_ERR_UNSUPPORTED; }
     AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (NC > 8) AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

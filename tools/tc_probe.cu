@@ -169,6 +169,114 @@ static int run_case(const Case& c, bool swap_fields) {
     return ok ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Probe B: A operand in TMEM (tcgen05.mma TS form).  Thread m writes row m of A[128][K] with
+// tcgen05.st (two consecutive k per 32-bit column, even k in the low half unless hi_first).
+// ---------------------------------------------------------------------------------------------------
+struct TsArgs { const float* A; const uint8_t* b_img; uint32_t b_bytes, b_lbo, b_sbo, b_kstep; int N, K, hi_first; float* D; };
+
+__global__ void __launch_bounds__(128, 1) ts_probe_kernel(TsArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar_mma = smem_u32(&bar);
+    if (tid == 0) { mbar_init(bar_mma, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t a_col = 256;                       // A at columns [256, 256 + K/2), D at [0, N)
+    for (uint32_t i = tid * 16; i < p.b_bytes; i += 128 * 16)
+        *reinterpret_cast<uint4*>(smem + i) = *reinterpret_cast<const uint4*>(p.b_img + i);
+    fence_async_smem();
+    for (int kk = 0; kk < p.K / 16; ++kk) {
+        uint32_t w[8];
+        for (int j = 0; j < 8; ++j) {
+            const float e0 = p.A[(size_t)tid * p.K + kk * 16 + 2 * j], e1 = p.A[(size_t)tid * p.K + kk * 16 + 2 * j + 1];
+            w[j] = p.hi_first ? pack_bf16(e1, e0) : pack_bf16(e0, e1);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
+                         tmem + ((uint32_t)(warp * 32) << 16) + a_col + kk * 8),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        const uint32_t idesc = idesc_bf16(128, p.N, 0, 0);
+        for (int kk = 0; kk < p.K / 16; ++kk) {
+            const uint64_t bd = smem_desc(smem_u32(smem) + kk * p.b_kstep, p.b_lbo, p.b_sbo);
+            const uint32_t acc = kk > 0;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem),
+                "r"(tmem + a_col + kk * 8), "l"(bd), "r"(idesc), "r"(acc)
+                : "memory");
+        }
+        mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) p.D[(size_t)tid * p.N + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Probe C: all-gather inside a cluster with cp.async.bulk shared::cta -> shared::cluster and the
+// destination CTA's mbarrier (complete_tx), no barrier.cluster in the data path.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(128, 1) dsmem_probe_kernel(uint32_t* out, int rounds) {
+    __shared__ __align__(128) uint8_t src[2][1024];
+    __shared__ __align__(128) uint8_t dst[2][4 * 1024];
+    __shared__ __align__(8) uint64_t bars[2];
+    uint32_t rank, nranks;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_fence_init(); }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    uint32_t bad = 0;
+    for (int s = 0; s < rounds; ++s) {
+        const int b = s & 1;
+        for (int i = tid; i < 256; i += 128) reinterpret_cast<uint32_t*>(src[b])[i] = (rank << 24) | (s << 8) | i;
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(smem_u32(&bars[b]), nranks * 1024);
+            for (uint32_t r = 0; r < nranks; ++r) {
+                uint32_t rdst, rbar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(&dst[b][rank * 1024])), "r"(r));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&bars[b])), "r"(r));
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst),
+                             "r"(smem_u32(src[b])), "r"(1024u), "r"(rbar)
+                             : "memory");
+            }
+        }
+        mbar_wait(smem_u32(&bars[b]), (s >> 1) & 1);
+        for (int i = tid; i < (int)nranks * 256; i += 128) {
+            const uint32_t v = reinterpret_cast<volatile uint32_t*>(dst[b])[i];
+            if (v != (((uint32_t)(i / 256) << 24) | (s << 8) | (i % 256))) ++bad;
+        }
+        __syncthreads();
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    atomicAdd(out + rank, bad);
+    if (tid == 0) out[8 + rank] = 1;
+}
+
 int main() {
     srand(1234);
     auto rnd = [](size_t n) {
@@ -268,5 +376,39 @@ int main() {
         h1 += r1; h2 += r2; ++n;
     }
     printf("SUMMARY: H1 (LBO=K stride, SBO=MN stride) matches %d/%d ; H2 (swapped) matches %d/%d\n", h1, n, h2, n);
+
+    {   // Probe B: A in TMEM
+        const int N = 64, K = 64;
+        auto A = rnd(128 * K), B = rnd((size_t)N * K);
+        auto bimg = image_kmajor(B, N, K, 128, (N / 8) * 128);
+        auto ref = matmul(A, B, N, K);
+        for (int hi = 0; hi < 2; ++hi) {
+            float *dA, *dD; uint8_t* db;
+            cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dD, (size_t)128 * N * 4); cudaMalloc(&db, bimg.size());
+            cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(db, bimg.data(), bimg.size(), cudaMemcpyHostToDevice);
+            TsArgs t; t.A = dA; t.b_img = db; t.b_bytes = (uint32_t)bimg.size(); t.b_lbo = (N / 8) * 128; t.b_sbo = 128;
+            t.b_kstep = 2 * (N / 8) * 128; t.N = N; t.K = K; t.hi_first = hi; t.D = dD;
+            cudaFuncSetAttribute(ts_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bimg.size() + 1024);
+            ts_probe_kernel<<<1, 128, bimg.size() + 1024>>>(t);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("TS probe: CUDA ERROR %s\n", cudaGetErrorString(e)); return 2; }
+            std::vector<float> D((size_t)128 * N);
+            cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+            double me = 0, mr = 0;
+            for (size_t i = 0; i < D.size(); ++i) { me = fmax(me, fabs((double)D[i] - ref[i])); mr = fmax(mr, fabs(ref[i])); }
+            printf("TS probe (A in TMEM, %s k in low half): %s (max err %.3g, max |ref| %.3g)\n", hi ? "odd" : "even",
+                   me <= 1e-3 * mr ? "MATCH" : "mismatch", me, mr);
+        }
+    }
+    {   // Probe C: DSMEM bulk all-gather
+        uint32_t* d; cudaMalloc(&d, 64); cudaMemset(d, 0, 64);
+        dsmem_probe_kernel<<<4, 128>>>(d, 50);
+        cudaError_t e = cudaDeviceSynchronize();
+        uint32_t h[16] = {0};
+        cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+        printf("DSMEM bulk all-gather probe: %s, mismatches per rank %u %u %u %u, done %u %u %u %u\n",
+               e == cudaSuccess ? "ran" : cudaGetErrorString(e), h[0], h[1], h[2], h[3], h[8], h[9], h[10], h[11]);
+    }
     return 0;
 }
