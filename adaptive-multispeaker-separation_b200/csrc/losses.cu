@@ -189,31 +189,39 @@ __global__ void mean_of_stat_kernel(const float* __restrict__ stats, int B, int 
 // staged transposed (point-contiguous) so the 4 point values are one LDS.128, the An row is a
 // warp-uniform broadcast; results go back through shared memory for coalesced stores.
 constexpr int LS_BP = 256, LS_BPT = 260;
-template <int OB>
+// EC > 0: embedding size known at compile time (E = 40, the reference default) -> constant divisions, full unrolling.
+// Persistent: CTAs walk the flat (mixture, tile) list, so the grid is exactly the resident slots (no wave tail).
+template <int OB, int EC>
 __global__ void __launch_bounds__(LS_THREADS)
 dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels, const float* __restrict__ dloss,
-                const float* __restrict__ stats, int B, int64_t TF, int E, int S, float* __restrict__ dV) {
+                const float* __restrict__ stats, int B, int64_t TF, int Ert, int S, float* __restrict__ dV) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
-    float* xt = reinterpret_cast<float*>(ls_smem);              // [E][LS_BPT]  transposed points
+    const int E = EC > 0 ? EC : Ert;
     const int EO = E | 1;                                       // odd row pitch of the result staging
+    float* xt = reinterpret_cast<float*>(ls_smem);              // [E][LS_BPT]  transposed points
     float* os = xt + E * LS_BPT;                                // [LS_BP][EO]  results
     float* An = os + LS_BP * EO;                                // [E][E]
     float* Bn = An + E * E;                                     // [S][E]
     float* dinv = Bn + S * E;                                   // [S]
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int sstride = E * E + S * E + S + 1;
-    const float* st = stats + (size_t)b * sstride;
-    for (int i = tid; i < E * E + S * E + S; i += LS_THREADS) An[i] = st[i];
     const float gscale = dloss[0] / (float)B;
     const int OBr = (E + 3) / 4;                                // outputs per thread (<= OB)
     const int ob = tid & 3, pg = tid >> 2;                      // a warp = 8 point groups x 4 output blocks
     const int o0 = ob * OBr;
     const int64_t ntiles = (TF + LS_BP - 1) / LS_BP;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t p0 = tile * LS_BP;
+    int bcur = -1;
+    for (int64_t w = blockIdx.x; w < (int64_t)B * ntiles; w += gridDim.x) {
+        const int b = (int)(w / ntiles);
+        const int64_t p0 = (w - (int64_t)b * ntiles) * LS_BP;
         const int np = (int)((TF - p0) < LS_BP ? (TF - p0) : LS_BP);
         const float* src = V + ((size_t)b * TF + p0) * E;
         __syncthreads();
+        if (b != bcur) {
+            const float* st = stats + (size_t)b * sstride;
+            for (int i = tid; i < E * E + S * E + S; i += LS_THREADS) An[i] = st[i];
+            bcur = b;
+        }
         for (int i = tid; i < LS_BP * E; i += LS_THREADS) {
             const int p = i / E, e = i - p * E;
             xt[e * LS_BPT + p] = p < np ? __ldg(src + i) : 0.f;
@@ -224,12 +232,13 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < OB; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
         for (int e2 = 0; e2 < E; ++e2) {
             const float4 v = *reinterpret_cast<const float4*>(xt + e2 * LS_BPT + pg * 4);
             const float* ar = An + e2 * E + o0;                  // An symmetric: column block of row e2
 #pragma unroll
             for (int j = 0; j < OB; ++j) {
-                const float a = (j < OBr && o0 + j < E) ? ar[j] : 0.f;
+                const float a = (EC > 0 || (j < OBr && o0 + j < E)) ? ar[j] : 0.f;
                 acc[0][j] = fmaf(a, v.x, acc[0][j]); acc[1][j] = fmaf(a, v.y, acc[1][j]);
                 acc[2][j] = fmaf(a, v.z, acc[2][j]); acc[3][j] = fmaf(a, v.w, acc[3][j]);
             }
@@ -242,7 +251,7 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
                 const float d = gscale * dinv[l];
 #pragma unroll
                 for (int j = 0; j < OB; ++j)
-                    if (j < OBr && o0 + j < E) os[p * EO + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
+                    if (EC > 0 || (j < OBr && o0 + j < E)) os[p * EO + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
             }
         }
         __syncthreads();
@@ -548,13 +557,14 @@ extern "C" int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const f
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_bwd: S out of range");
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd: E=%d outside [1,64]", E);
     const size_t smem = ((size_t)E * LS_BPT + (size_t)LS_BP * (E | 1) + (size_t)E * E + (size_t)S * E + S) * 4;
-    dim3 grid(ls_chunks(B, TF, LS_BP), B);
-    if ((E + 3) / 4 <= 10) {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(dpcl_bwd_kernel<10>, grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
+    const int64_t work = (int64_t)B * ((TF + LS_BP - 1) / LS_BP);
+    const int grid = (int)std::min<int64_t>(work, 2 * kNumSMs);      // 2 resident CTAs per SM (89 KB of shared memory each)
+    if (E == 40) {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<10, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_bwd_kernel<10, 40>), grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
     } else {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(dpcl_bwd_kernel<16>, grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_bwd_kernel<16, 0>), grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
     }
     return AMSS_OK;
 }

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""One launch of each hot kernel at bench geometry, for `ncu --set full` captures (diagnostics)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import amss_b200  # noqa: E402,F401
+from amss_b200 import ops  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+T, L = 250, 64000
+P = ops.AMSS_PREC_BF16
+torch.manual_seed(0)
+x = torch.randn(3 * B, L, device="cuda") * 0.05
+filt = torch.randn(1024, 256, device="cuda") / 32
+ops.filterbank_analysis(x, filt, 256, 256, ops.AMSS_POOL_MAX, P)
+M = T * B
+h = torch.randn(M, 600, device="cuda")
+W = torch.randn(600, 10240, device="cuda") * 0.05
+bias = torch.zeros(10240, device="cuda")
+z = ops.gemm(h, W, bias, precision=P)                       # head fwd
+dz = torch.randn_like(z)
+ops.gemm(h, dz, None, transa=True, precision=P)             # head dW
+ops.gemm(dz, W, None, transb=True, precision=P)             # head dH
+xt = torch.randn(T, B, 600, device="cuda") * 0.1
+kf = torch.randn(900, 1200, device="cuda") * 0.05
+bf = torch.zeros(1200, device="cuda")
+y, saved = ops.blstm_fwd(xt, kf, bf, kf, bf, precision=P)
+ops.blstm_bwd(xt, kf, kf, y, torch.randn_like(y), saved, precision=P)
+V = torch.nn.functional.normalize(torch.randn(B, 64000, 40, device="cuda"), dim=-1)
+lab = torch.randint(0, 2, (B, 64000), device="cuda", dtype=torch.uint8)
+loss, ws = ops.dpcl_loss_fwd(V, lab, 2)
+ops.dpcl_loss_bwd(V, lab, 2, torch.ones(1, device="cuda"), ws)
+torch.cuda.synchronize()
+print("done")
