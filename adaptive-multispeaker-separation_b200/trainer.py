@@ -104,6 +104,45 @@ class AMSGradOptimizer:
                          self.eps, grad_scale, fac)
 
 
+class DevicePrefetcher:
+    """Host -> device input staging one step ahead (the role of the reference's tf.data prefetch(1),
+    data/dataset.py:506-514): pinned host batches are copied on a side stream into double-buffered device
+    inputs while the previous step computes; stream events (no host sync) order copy and compute."""
+
+    def __init__(self, example_batch):
+        self.stream = torch.cuda.Stream()
+        self.bufs = [[torch.empty(tuple(a.shape), dtype=a.dtype, device="cuda") for a in example_batch] for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [None, None]
+        self.k = 0
+
+    @staticmethod
+    def pin(batch):
+        return tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in batch)
+
+    def submit(self, pinned_batch):
+        """Start the H2D copy of a pinned batch; returns the slot to pass to get()."""
+        k = self.k
+        self.k ^= 1
+        if self.done[k] is not None:
+            self.stream.wait_event(self.done[k])          # the step that last read this slot has finished
+        with torch.cuda.stream(self.stream):
+            for d, h in zip(self.bufs[k], pinned_batch):
+                d.copy_(h, non_blocking=True)
+            self.ready[k].record(self.stream)
+        return k
+
+    def get(self, k):
+        torch.cuda.current_stream().wait_event(self.ready[k])
+        return self.bufs[k]
+
+    def release(self, k):
+        """Call after launching the step that consumes slot k."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.done[k] = ev
+
+
 class Trainer:
     """Common loop (utils/trainer.py:264-390).  Subclasses implement build() and loss(batch)."""
 
@@ -151,14 +190,26 @@ class Trainer:
         return cost.detach()
 
     def train(self, data, steps, log_every=0):
-        """data: iterator of host batches.  Returns the list of per-step costs (floats)."""
+        """data: iterator of host batches (numpy or pinned tensors).  Inputs are staged one step ahead
+        (DevicePrefetcher) and each step's cost is read back while the next step runs.
+        Returns the list of per-step costs (floats)."""
         costs = []
         t0 = time.time()
+        as_pinned = lambda b: b if torch.is_tensor(b[0]) and b[0].is_pinned() else DevicePrefetcher.pin(b)  # noqa: E731
+        first = as_pinned(next(data))
+        pf = DevicePrefetcher(first)
+        slot, pending = pf.submit(first), None
         for step in range(steps):
-            c = self.train_step(*self.to_device(next(data)))
-            costs.append(float(c))
-            if log_every and (step + 1) % log_every == 0 and self.rank == 0:
+            c = self.train_step(*pf.get(slot))
+            pf.release(slot)
+            if step + 1 < steps:
+                slot = pf.submit(as_pinned(next(data)))
+            if pending is not None:
+                costs.append(float(pending))
+            pending = c
+            if log_every and (step + 1) % log_every == 0 and self.rank == 0 and costs:
                 print(f"step {step + 1}/{steps} loss={costs[-1]:.6f} {(time.time() - t0) / (step + 1):.3f} s/step")
+        costs.append(float(pending))
         return costs
 
 
