@@ -188,13 +188,18 @@ __global__ void mean_of_stat_kernel(const float* __restrict__ stats, int B, int 
 // Register-blocked [256 points x E] x [E x E] product: thread = 4 points x OB outputs; the points are
 // staged transposed (point-contiguous) so the 4 point values are one LDS.128, the An row is a
 // warp-uniform broadcast; results go back through shared memory for coalesced stores.
-constexpr int LS_BP = 256, LS_BPT = 260;
-// EC > 0: embedding size known at compile time (E = 40, the reference default) -> constant divisions, full unrolling.
+constexpr int LS_BP = 256, LS_BPT = 260, LS_BWD_THREADS = 320;
+// EC > 0: embedding size known at compile time (E = 40, the reference default): 5 output blocks of 8 -> the An row
+// block is two LDS.128 per inner step (FFMA-bound), constant divisions, full unrolling.  Generic E: 4 blocks of OB.
 // Persistent: CTAs walk the flat (mixture, tile) list, so the grid is exactly the resident slots (no wave tail).
+// inv_norm != NULL fuses the backward of tf.nn.l2_normalize (utils/ops.py:323-324) into the same pass:
+//   out_i = inv_i * (dV_i - v_i <v_i, dV_i>)   (dz, the gradient w.r.t. the un-normalised embeddings)
+// so dV is never written and v is read once.
 template <int OB, int EC>
-__global__ void __launch_bounds__(LS_THREADS)
+__global__ void __launch_bounds__(LS_BWD_THREADS)
 dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels, const float* __restrict__ dloss,
-                const float* __restrict__ stats, int B, int64_t TF, int Ert, int S, float* __restrict__ dV) {
+                const float* __restrict__ stats, const float* __restrict__ inv_norm, int B, int64_t TF, int Ert, int S,
+                float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
     const int E = EC > 0 ? EC : Ert;
     const int EO = E | 1;                                       // odd row pitch of the result staging
@@ -206,8 +211,10 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
     const int tid = threadIdx.x;
     const int sstride = E * E + S * E + S + 1;
     const float gscale = dloss[0] / (float)B;
-    const int OBr = (E + 3) / 4;                                // outputs per thread (<= OB)
-    const int ob = tid & 3, pg = tid >> 2;                      // a warp = 8 point groups x 4 output blocks
+    constexpr int NOB = EC > 0 ? EC / OB : 4;                   // output blocks per point group
+    const int OBr = EC > 0 ? OB : (E + 3) / 4;                  // outputs per thread (<= OB)
+    const int ob = tid % NOB, pg = tid / NOB;                   // 64 point groups of 4 points
+    const bool worker = pg < LS_BP / 4;
     const int o0 = ob * OBr;
     const int64_t ntiles = (TF + LS_BP - 1) / LS_BP;
     int bcur = -1;
@@ -219,44 +226,65 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
         __syncthreads();
         if (b != bcur) {
             const float* st = stats + (size_t)b * sstride;
-            for (int i = tid; i < E * E + S * E + S; i += LS_THREADS) An[i] = st[i];
+            for (int i = tid; i < E * E + S * E + S; i += LS_BWD_THREADS) An[i] = st[i];
             bcur = b;
         }
-        for (int i = tid; i < LS_BP * E; i += LS_THREADS) {
+        for (int i = tid; i < LS_BP * E; i += LS_BWD_THREADS) {
             const int p = i / E, e = i - p * E;
             xt[e * LS_BPT + p] = p < np ? __ldg(src + i) : 0.f;
         }
         __syncthreads();
-        float acc[4][OB];
+        if (worker) {
+            float acc[4][OB];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < OB; ++j) acc[i][j] = 0.f;
+                for (int j = 0; j < OB; ++j) acc[i][j] = 0.f;
 #pragma unroll 8
-        for (int e2 = 0; e2 < E; ++e2) {
-            const float4 v = *reinterpret_cast<const float4*>(xt + e2 * LS_BPT + pg * 4);
-            const float* ar = An + e2 * E + o0;                  // An symmetric: column block of row e2
+            for (int e2 = 0; e2 < E; ++e2) {
+                const float4 v = *reinterpret_cast<const float4*>(xt + e2 * LS_BPT + pg * 4);
+                const float* ar = An + e2 * E + o0;              // An symmetric: column block of row e2
+                float a[OB];
+                if (EC > 0 && OB == 8) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(ar), a1 = *reinterpret_cast<const float4*>(ar + 4);
+                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4 % OB] = a1.x; a[5 % OB] = a1.y; a[6 % OB] = a1.z; a[7 % OB] = a1.w;
+                } else {
 #pragma unroll
-            for (int j = 0; j < OB; ++j) {
-                const float a = (EC > 0 || (j < OBr && o0 + j < E)) ? ar[j] : 0.f;
-                acc[0][j] = fmaf(a, v.x, acc[0][j]); acc[1][j] = fmaf(a, v.y, acc[1][j]);
-                acc[2][j] = fmaf(a, v.z, acc[2][j]); acc[3][j] = fmaf(a, v.w, acc[3][j]);
+                    for (int j = 0; j < OB; ++j) a[j] = (j < OBr && o0 + j < E) ? ar[j] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < OB; ++j) {
+                    acc[0][j] = fmaf(a[j], v.x, acc[0][j]); acc[1][j] = fmaf(a[j], v.y, acc[1][j]);
+                    acc[2][j] = fmaf(a[j], v.z, acc[2][j]); acc[3][j] = fmaf(a[j], v.w, acc[3][j]);
+                }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int p = pg * 4 + i;
-            if (p < np) {
-                const int l = labels[(size_t)b * TF + p0 + p];
-                const float d = gscale * dinv[l];
+            for (int i = 0; i < 4; ++i) {
+                const int p = pg * 4 + i;
+                if (p < np) {
+                    const int l = labels[(size_t)b * TF + p0 + p];
+                    const float d = gscale * dinv[l];
 #pragma unroll
-                for (int j = 0; j < OB; ++j)
-                    if (EC > 0 || (j < OBr && o0 + j < E)) os[p * EO + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
+                    for (int j = 0; j < OB; ++j)
+                        if (EC > 0 || (j < OBr && o0 + j < E)) os[p * EO + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
+                }
             }
         }
         __syncthreads();
-        float* dst = dV + ((size_t)b * TF + p0) * E;
-        for (int i = tid; i < np * E; i += LS_THREADS) { const int pp = i / E; dst[i] = os[pp * EO + (i - pp * E)]; }
+        if (inv_norm != nullptr) {                              // fused l2_normalize backward, one thread per point
+            if (tid < np) {
+                float inv = inv_norm[(size_t)b * TF + p0 + tid];
+                float dot = 0.f;
+#pragma unroll 8
+                for (int e = 0; e < E; ++e) dot = fmaf(xt[e * LS_BPT + tid], os[tid * EO + e], dot);
+                if (inv < 0.f) { inv = -inv; dot = 0.f; }       // clamped branch of l2_normalize: linear map
+#pragma unroll 8
+                for (int e = 0; e < E; ++e) os[tid * EO + e] = inv * (os[tid * EO + e] - xt[e * LS_BPT + tid] * dot);
+            }
+            __syncthreads();
+        }
+        float* dst = out + ((size_t)b * TF + p0) * E;
+        for (int i = tid; i < np * E; i += LS_BWD_THREADS) { const int pp = i / E; dst[i] = os[pp * EO + (i - pp * E)]; }
     }
 }
 
@@ -551,22 +579,40 @@ extern "C" int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, 
     return AMSS_OK;
 }
 
+namespace {
+int dpcl_bwd_launch(const float* V, const uint8_t* labels, const float* dloss, const float* inv_norm, int B, int64_t TF,
+                    int E, int S, float* out, const void* workspace, void* stream) {
+    const size_t smem = ((size_t)E * LS_BPT + (size_t)LS_BP * (E | 1) + (size_t)E * E + (size_t)S * E + S) * 4;
+    const int64_t work = (int64_t)B * ((TF + LS_BP - 1) / LS_BP);
+    const int grid = (int)std::min<int64_t>(work, 2 * kNumSMs);      // 2 resident CTAs per SM (89 KB of shared memory each)
+    if (E == 40) {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<8, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_bwd_kernel<8, 40>), grid, LS_BWD_THREADS, smem, stream, V, labels, dloss, (const float*)workspace,
+                    inv_norm, B, TF, E, S, out);
+    } else {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_bwd_kernel<16, 0>), grid, LS_BWD_THREADS, smem, stream, V, labels, dloss, (const float*)workspace,
+                    inv_norm, B, TF, E, S, out);
+    }
+    return AMSS_OK;
+}
+}  // namespace
+
 extern "C" int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const float* dloss, int B, int64_t TF, int E,
                                   int S, float* dV, const void* workspace, void* stream) {
     AMSS_REQUIRE(V && labels && dloss && dV && workspace, "dpcl_loss_bwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_bwd: S out of range");
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd: E=%d outside [1,64]", E);
-    const size_t smem = ((size_t)E * LS_BPT + (size_t)LS_BP * (E | 1) + (size_t)E * E + (size_t)S * E + S) * 4;
-    const int64_t work = (int64_t)B * ((TF + LS_BP - 1) / LS_BP);
-    const int grid = (int)std::min<int64_t>(work, 2 * kNumSMs);      // 2 resident CTAs per SM (89 KB of shared memory each)
-    if (E == 40) {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<10, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH((dpcl_bwd_kernel<10, 40>), grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
-    } else {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH((dpcl_bwd_kernel<16, 0>), grid, LS_THREADS, smem, stream, V, labels, dloss, (const float*)workspace, B, TF, E, S, dV);
-    }
-    return AMSS_OK;
+    return dpcl_bwd_launch(V, labels, dloss, nullptr, B, TF, E, S, dV, workspace, stream);
+}
+
+extern "C" int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labels, const float* dloss,
+                                             const float* inv_norm, int B, int64_t TF, int E, int S, float* dz,
+                                             const void* workspace, void* stream) {
+    AMSS_REQUIRE(V && labels && dloss && inv_norm && dz && workspace, "dpcl_loss_bwd_normalized: null pointer");
+    AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_bwd_normalized: S out of range");
+    AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd_normalized: E=%d outside [1,64]", E);
+    return dpcl_bwd_launch(V, labels, dloss, inv_norm, B, TF, E, S, dz, workspace, stream);
 }
 
 extern "C" int amss_l2norm_fwd(const float* z, int64_t rows, int E, float* v, float* inv_norm, void* stream) {

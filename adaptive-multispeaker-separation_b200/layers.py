@@ -166,10 +166,11 @@ class _L2NormFn(torch.autograd.Function):
         v, inv = ops.l2norm_fwd(z.contiguous(), E)
         ctx.save_for_backward(v, inv)
         ctx.E = E
-        return v
+        ctx.mark_non_differentiable(inv)
+        return v, inv
 
     @staticmethod
-    def backward(ctx, dv):
+    def backward(ctx, dv, _dinv):
         v, inv = ctx.saved_tensors
         return ops.l2norm_bwd(v, inv, dv.contiguous(), ctx.E), None
 
@@ -186,6 +187,24 @@ class _DPCLLossFn(torch.autograd.Function):
     def backward(ctx, dloss):
         V, labels, ws = ctx.saved_tensors
         return ops.dpcl_loss_bwd(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws), None, None
+
+
+class _NormDPCLLossFn(torch.autograd.Function):
+    """DPCL cost of V = l2_normalize(z) as ONE autograd node on z: the backward is a single kernel
+    (affinity-loss gradient + normalisation Jacobian), dV never reaches HBM and v is read once."""
+
+    @staticmethod
+    def forward(ctx, z, V, inv, labels, S):
+        loss, ws = ops.dpcl_loss_fwd(V, labels, S)
+        ctx.save_for_backward(V, inv, labels, ws)
+        ctx.S, ctx.zshape = S, z.shape
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        V, inv, labels, ws = ctx.saved_tensors
+        dz = ops.dpcl_loss_bwd_normalized(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws, inv)
+        return dz.view(ctx.zshape), None, None, None, None
 
 
 class _L41LossFn(torch.autograd.Function):
@@ -249,6 +268,29 @@ class _SynthesisFn(torch.autograd.Function):
         return dvals, None, dfilt2, None, None, None, None, None
 
 
+class _WaveLossFn(torch.autograd.Function):
+    """Per-(b,s) waveform statistics of the Adapt pre-training cost (models/adapt.py:323-330,
+    models/network.py:207-211), one fused reduction kernel: stats[r] = (<t,t>, <a,a>, <t,a>, <t-a,t-a>).
+    Gradient flows to the approximation a only (the targets are data):
+        d<a,a> = 2a, d<t,a> = t, d<t-a,t-a> = 2(a - t)."""
+
+    @staticmethod
+    def forward(ctx, target, approx):
+        ctx.save_for_backward(target, approx)
+        return ops.wave_stats(target.contiguous(), approx.contiguous())
+
+    @staticmethod
+    def backward(ctx, dstats):
+        target, approx = ctx.saved_tensors
+        ca = (2.0 * dstats[:, 1] + 2.0 * dstats[:, 3]).unsqueeze(1)
+        ct = (dstats[:, 2] - 2.0 * dstats[:, 3]).unsqueeze(1)
+        return None, ca * approx + ct * target
+
+
+def wave_stats(target, approx):
+    return _WaveLossFn.apply(target, approx)
+
+
 def blstm(x, kf, bf, kb, bb, precision=AMSS_PREC_FP32):
     return _BLSTMFn.apply(x, kf, bf, kb, bb, precision)
 
@@ -258,10 +300,18 @@ def dense(x, W, b, precision=AMSS_PREC_FP32, swap=None):
 
 
 def l2_normalize(z, E):
-    return _L2NormFn.apply(z, E)
+    v, inv = _L2NormFn.apply(z, E)
+    if z.requires_grad:
+        v._amss_prenorm = (z, inv)          # lets dpcl_loss() fuse the two backward passes (see _NormDPCLLossFn)
+    return v
 
 
-def dpcl_loss(V, labels, S):
+def dpcl_loss(V, labels, S, prenorm=None):
+    """prenorm = (z, inv_norm) as stashed by l2_normalize() on its output: the loss becomes one autograd node
+    on z with a fused backward (DPCL gradient + normalisation Jacobian)."""
+    if prenorm is not None:
+        z, inv = prenorm
+        return _NormDPCLLossFn.apply(z, V.detach(), inv, labels, S)
     return _DPCLLossFn.apply(V, labels, S)
 
 

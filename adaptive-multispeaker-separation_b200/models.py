@@ -146,6 +146,65 @@ class Adapt(Network):
                           self.hop_size)
         return out.reshape(B, self.S, Lw)
 
+    # network.py:196-221 (with_perm=False): SDR improvement metric and the 'sdr' loss ratio per (b,s)
+    def sdr_improvement(self, x_mix, s_target, s_approx):
+        B, S, Lw = s_target.shape
+        st = L.wave_stats(s_target.reshape(B * S, Lw), s_approx.reshape(B * S, Lw))
+        tn, an, ta = st[:, 0], st[:, 1], st[:, 2]
+        with torch.no_grad():
+            mixr = x_mix.unsqueeze(1).expand(B, S, Lw).reshape(B * S, Lw).contiguous()
+            sm = ops.wave_stats(s_target.reshape(B * S, Lw).contiguous(), mixr)
+            separated = 10.0 * torch.log(1.0 / ((tn * an) / (ta * ta) - 1.0)) / math.log(10.0)
+            non_sep = 10.0 * torch.log(1.0 / ((sm[:, 0] * sm[:, 1]) / (sm[:, 2] * sm[:, 2]) - 1.0)) / math.log(10.0)
+            val = (separated - non_sep).reshape(B, S).mean(-1).mean(-1)
+        loss = (tn * an) / (ta * ta + 1e-12)
+        return val, loss.reshape(B, S), st
+
+    # adapt.py:141-160
+    def overlap(self, y, B):
+        S = self.S
+        nm = y[B:].reshape(B, S, -1).abs()
+        vals = []
+        for a, b in itertools.combinations(range(S), 2):
+            pa, pb = nm[:, a], nm[:, b]
+            vals.append((1.0 - (pa - pb).abs() / (torch.maximum(pa, pb) + 1e-8)).mean(-1))
+        return torch.stack(vals, 1).mean(-1).mean(-1)
+
+    # adapt.py:307-338, 374-385 (pretraining branch)
+    def cost(self, x_mix, x_non_mix):
+        """Pre-training cost of the autoencoder: l2 / sdr (/ both) + beta*KL sparsity + lambda^2*reg +
+        overlap_coef*overlap + non_negativity^2*neg.  The heavy nodes (analysis, synthesis, waveform
+        statistics and their gradients) are library kernels; the remaining terms are reductions over the
+        [B(S+1),Tp,N] front output (0.26 MB per signal) composed from device tensor ops.
+        Returns (cost, aux)."""
+        B, S, Lw = x_non_mix.shape
+        y, am = self.front(x_mix, x_non_mix)
+        filt, filt2 = self.conv_filter("front"), self.conv_filter("back")
+        p_hat = y.abs().reshape(y.shape[0], -1).sum(0)                                   # adapt.py:129-131 (sum over batch)
+        rho = torch.as_tensor(self.p, dtype=y.dtype, device=y.device)
+        clip = lambda t: torch.clamp(t, 1e-10, 1.0)                                      # noqa: E731  utils/ops.py:46-54
+        kl = rho * torch.log(clip(rho) / clip(p_hat)) + (1 - rho) * torch.log(clip(1 - rho) / clip(1 - p_hat))
+        sparse = kl.sum()
+        overlapping = self.overlap(y, B)
+        sep = self.separator(y, B)
+        back = self.back(sep, am, B, Lw)
+        val, sdr_bs, st = self.sdr_improvement(x_mix, x_non_mix, back)
+        l2 = st[:, 3].reshape(B, S).sum(-1).mean(-1)                                    # adapt.py:323-325
+        sdr = sdr_bs.mean(-1).mean(-1)                                                   # adapt.py:327-330
+        cost = l2 if self.loss == "l2" else (sdr if self.loss == "sdr" else l2 + sdr)    # adapt.py:332-337
+        if self.beta != 0.0:
+            cost = cost + self.beta * sparse
+        if self.l != 0.0:                                                                # lambda applied twice (:312, :380)
+            reg = self.l * (0.5 * (filt2 ** 2).sum() + 0.5 * (filt ** 2).sum())
+            cost = cost + self.l * reg
+        if self.overlap_coef != 0.0:
+            cost = cost + self.overlap_coef * overlapping
+        if self.non_negativity:                                                          # applied twice (:316, :384)
+            neg = torch.where(y < 0, y, torch.zeros_like(y)) ** 2
+            cost = cost + self.non_negativity * (self.non_negativity * neg.reshape(neg.shape[0], -1).sum(1).mean())
+        return cost, {"y": y, "argmax": am, "back": back, "l2": l2, "sdr": sdr, "sdr_improvement": val,
+                      "sparse_constraint": sparse, "overlapping": overlapping, "p_hat": p_hat}
+
     def connect_front(self, separator_class, **extra):
         """adapt.py:440-441 -- plug a Separator subclass on the front output (plugged=True)."""
         args = dict(self.args)
@@ -229,6 +288,48 @@ class Separator(Network):
         sep = ops.apply_masks(Xf, self.S, labels=lab) if self.beta is None else ops.apply_masks(Xf, self.S, soft=lab)
         return sep.view(B * self.S, Tt, Fb), lab
 
+    # network.py:456-462, 629-636: the enhance BLSTM stack on [separated || X] (config 3)
+    def add_enhance_layer(self):
+        a, st, prec = self.args, self.store, self.precision
+        in_dim = 2 * self.F
+        self.enhance_layers = []
+        for i in range(a["nb_layers_enhance"]):
+            self.enhance_layers.append(L.BLSTM(a["layer_size_enhance"], name=f"BLSTM_{i}",
+                                               drop_val=a["recurrent_dropout_enhance"], store=st, scope="enhance",
+                                               in_dim=in_dim, precision=prec))
+            in_dim = 2 * (a["layer_size_enhance"] // 2)
+        self.enhance_layers.append(L.Conv1D([1, in_dim, self.F], store=st, scope="enhance", precision=prec))
+        return self
+
+    # network.py:610-660
+    def enhance(self, separated, X_input):
+        """separated [B*S,T,F] (k-means masks applied), X_input [B,T,F] -> (enhanced [B,S,TF], cost_in [B,TF,S])."""
+        B, Tt, Fb = X_input.shape
+        S = self.S
+        sep4 = separated.reshape(B, S, Tt, Fb)
+        z = torch.cat([sep4, X_input.unsqueeze(1).expand(B, S, Tt, Fb)], 3).reshape(B * S, Tt, 2 * Fb)
+        if self.args["normalize_enhance"]:
+            mean = z.mean((1, 2), keepdim=True)
+            var = z.var((1, 2), unbiased=False, keepdim=True)
+            z = (z - mean) / torch.sqrt(var)
+        yv = L.f_props(self.enhance_layers, z.contiguous())                       # [B*S,T,F]
+        yv = yv.reshape(B, S, Tt * Fb).transpose(1, 2)                           # [B,TF,S]
+        nl = self.args["nonlinearity"]
+        if nl == "softmax":
+            yv = torch.softmax(yv, -1)
+        elif nl == "tanh":
+            yv = torch.tanh(yv)
+        cost_in = yv * X_input.reshape(B, -1, 1)
+        return cost_in.transpose(1, 2), cost_in
+
+    # network.py:662-693: PIT L2 over the S! permutations, min over perms, mean over the batch
+    def enhance_cost(self, cost_in, X_non_mix):
+        B, TF, S = cost_in.shape
+        est = cost_in.transpose(1, 2)
+        tgt = X_non_mix.reshape(B, TF, S).transpose(1, 2)
+        costs = [((tgt - est[:, list(perm)]) ** 2).sum(-1).sum(-1) for perm in itertools.permutations(range(S))]
+        return torch.stack(costs, 1).min(1).values.mean()
+
     # network.py:584-607
     def postprocessing(self, stfts, labels_or_masks):
         if self.beta is None:
@@ -242,7 +343,8 @@ class DPCL(Separator):
 
     def cost(self, V, labels, I=None):
         B, Tt, Fb, E = V.shape
-        return L.dpcl_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), self.S)
+        return L.dpcl_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), self.S,
+                           prenorm=getattr(V, "_amss_prenorm", None))
 
 
 class L41Model(Separator):

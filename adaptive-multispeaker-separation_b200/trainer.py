@@ -261,6 +261,56 @@ class Front_Separator_Trainer(Trainer):
         return self.sepNet.cost(V, inp["labels"], ind)
 
 
+class Adapt_Pretrainer(Trainer):
+    """utils/trainer.py:529-537 -- raw-waveform autoencoder pre-training of the adaptive front/back end
+    (BASELINE config 4: `--loss sdr+l2 --separation mask --beta 0.01`, README.md:23)."""
+
+    def __init__(self, name="AdaptiveNet", **kwargs):
+        self.name = name
+        super().__init__(**kwargs)
+
+    def build(self):
+        args = {k: v for k, v in self.args.items() if k in DEFAULTS or k in ("window_size", "hop_size")}
+        args["pretraining"] = True
+        self.model = Adapt(**args)
+        self.store = self.model.store
+
+    def loss(self, x_mix, x_non_mix, ind):
+        cost, self.aux = self.model.cost(x_mix, x_non_mix)
+        return cost
+
+
+class STFT_Separator_enhance_Trainer(Trainer):
+    """utils/trainer.py:488-500 -- a trained STFT separator (frozen) + the enhance BLSTM layer trained on the
+    k-means separated magnitudes with the PIT-L2 enhance cost (BASELINE config 3, second stage).
+    init_idx (optional): the k-means initial rows, otherwise drawn like the reference (np.random.choice)."""
+
+    def __init__(self, separator, name="STFT_Separator_enhance", separator_state=None, **kwargs):
+        self.separator_class, self.name, self.separator_state = separator, name, separator_state
+        self.init_idx = None
+        super().__init__(**kwargs)
+
+    def build(self):
+        args = {k: v for k, v in self.args.items() if k in DEFAULTS or k in ("window_size", "hop_size")}
+        self.model = self.separator_class(plugged=False, **args)
+        self.model.add_enhance_layer()
+        self.store = self.model.store
+
+    def post_build(self):
+        if self.separator_state:
+            self.store.load_state_dict(self.separator_state, strict=False)
+        self.model.freeze_all_except("enhance/")
+
+    def loss(self, x_mix, x_non_mix, ind):
+        m = self.model
+        pre = m.preprocessing(x_mix, x_non_mix, want_mag_non_mix=True)
+        with torch.no_grad():                       # hard k-means labels are not differentiable (network.py:554-582)
+            V = m.prediction(pre["X"])
+            sep, _ = m.separate(V, pre["X"], self.init_idx)
+        _, cost_in = m.enhance(sep, pre["X"])
+        return m.enhance_cost(cost_in, pre["X_non_mix"])
+
+
 class STFT_Separator_Inference:
     """utils/trainer.py:406-417 + Trainer.inference (:190-229): mixture -> separated waveforms."""
 

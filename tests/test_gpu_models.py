@@ -128,3 +128,76 @@ def test_front_inference_round_trip(amss):
         vals = torch.stack([y[:B], torch.zeros_like(y[:B])], 1).reshape(2 * B, *y.shape[1:]).contiguous()
         full = inf.model.back(vals, am, B, 2048)
     assert rel(out.sum(1), full.sum(1)) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ config 4: pre-training
+@pytest.mark.parametrize("loss,separation,beta", [("sdr+l2", "mask", 0.01), ("sdr", "perfect", 0.01), ("l2", "perfect", 0.0)])
+def test_adapt_pretraining_steps_match_oracle(amss, loss, separation, beta):
+    """BASELINE config 4 (README.md:23: --loss sdr+l2 --separation mask --beta 0.01), reduced geometry:
+    autoencoder cost (models/adapt.py:307-385) through analysis / unpool+transposed-conv kernels, 3 AMSGrad steps
+    on front/ and back/."""
+    tr = amss["trainer"]
+    B, S, Lw = 2, 2, 2048
+    kw = dict(window_size=64, filters=16, max_pool=32, hop_size=32, with_max_pool=True, loss=loss, separation=separation,
+              beta=beta, regularization=1e-4, overlap_coef=1e-3, sparsity=0.01)
+    t = tr.Adapt_Pretrainer(learning_rate=1e-3, **kw)
+    p = _copy_params(t.store, {})
+
+    def fn(pp, xm, xn, I):
+        return M.adapt_pretraining_cost(pp, xm, xn, max_pool=32, hop=32, loss=loss, separation=separation, beta=beta,
+                                        regularization=1e-4, sparsity=0.01, overlap_coef=1e-3, non_negativity=0.0)
+
+    st = OS.Stepper(p, fn, train_prefixes=("front/", "back/"), lr=1e-3)
+    g = torch.Generator().manual_seed(300)
+    for step in range(3):
+        # noise sources: the synthetic speech has exact silences, where the reference's `mask` separation
+        # (input_non_mix / input_mix, models/adapt.py:179-184) divides 0 by 0
+        nm = (torch.randn(B, S, Lw, generator=g) * 0.05).numpy()
+        mix, I = nm.sum(1), np.zeros((B, S), np.int32)
+        c_ref, aux = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+        assert rel(t.aux["back"], aux["back"]) < REL
+        assert abs(float(t.aux["sdr_improvement"]) - float(aux["sdr_improvement"])) < 1e-2
+    for k in st.tr:
+        assert rel(t.store[k], st.tr[k]) < REL, k
+
+
+# ------------------------------------------------------------------------------------------ config 3: enhance layer
+def test_enhance_layer_steps_match_oracle(amss):
+    """BASELINE config 3, second stage (utils/trainer.py:488-500): frozen L41 trunk -> k-means masks -> enhance
+    BLSTM stack on [separated || X] -> PIT-L2 enhance cost (models/network.py:610-693); only enhance/ trains."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 4096
+    cfg = dict(nb_layers=1, layer_size=24, embedding_size=6, window_size=128, hop_size=64, nb_layers_enhance=2,
+               layer_size_enhance=20, nonlinearity="softmax", nb_tries=2, nb_steps=3)
+    t = tr.STFT_Separator_enhance_Trainer(mo.L41Model, learning_rate=1e-3, **cfg)
+    p = _copy_params(t.store, {})
+    Fb, TF = 65, None
+    rng = np.random.RandomState(5)
+
+    def fn(pp, xm, xn, I):
+        pre = M.separator_preprocessing(xm, xn, 128, 64, 1.0, -1.0)
+        with torch.no_grad():
+            V = M.separator_prediction(pp, pre["X"], 1, 6)
+            km = OracleKMeans(nb_clusters=S, nb_tries=2, nb_iterations=3)
+            sep, _ = M.separate(V, pre["X"], lambda e: km.fit(e, init_idx=fn.init)[1], S)
+        _, cost_in, _ = M.enhance(pp, sep, pre["X"], S, 2)
+        return M.enhance_cost(cost_in, pre["X_non_mix"]), {}
+
+    st = OS.Stepper(p, fn, train_prefixes=("enhance/",), lr=1e-3)
+    trunk_before = t.store["prediction/W"].detach().clone()
+    for step in range(2):
+        mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=400 + step)
+        Tt = 1 + (Lw - 128) // 64
+        fn.init = random_init_idx(B * 2, Tt * Fb, S, rng)
+        t.init_idx = fn.init
+        c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+    for k in st.tr:
+        # enhance/b has an exactly-zero true gradient (a per-bin constant added to every speaker's logit cancels in
+        # the softmax over S), so after two steps it holds fp32 round-off (~1e-7): compare on an absolute floor
+        a, b = t.store[k].detach().double().cpu(), st.tr[k].detach().double()
+        assert float((a - b).abs().max()) < REL * max(float(b.abs().max()), 1e-3), k
+    assert torch.equal(trunk_before, t.store["prediction/W"].detach())      # the trunk stays frozen

@@ -81,6 +81,23 @@ def bench_blstm(B):
             print(f"blstm I={I} H={H} B={B} {pname}: fwd {med:8.3f} ms ({med / T * 1e3:.1f} us/step)  bwd {medb:8.3f} ms")
 
 
+def bench_dpcl(B):
+    TF, E = 64000, 40
+    z = torch.randn(B, TF, E, device="cuda")
+    lab = torch.randint(0, 2, (B, TF), device="cuda", dtype=torch.uint8)
+    V, inv = ops.l2norm_fwd(z, E)
+    one = torch.ones(1, device="cuda")
+    gb = B * TF * E * 4 / 1e9
+    loss, ws = ops.dpcl_loss_fwd(V, lab, 2)
+    dV = ops.dpcl_loss_bwd(V, lab, 2, one, ws)
+    for name, fn, passes in (("l2norm_fwd", lambda: ops.l2norm_fwd(z, E), 2), ("dpcl_loss_fwd", lambda: ops.dpcl_loss_fwd(V, lab, 2), 1),
+                             ("dpcl_loss_bwd", lambda: ops.dpcl_loss_bwd(V, lab, 2, one, ws), 2),
+                             ("l2norm_bwd", lambda: ops.l2norm_bwd(V, inv, dV, E), 3),
+                             ("dpcl_loss_bwd_normalized", lambda: ops.dpcl_loss_bwd_normalized(V, lab, 2, one, ws, inv), 2)):
+        med, _ = timeit(fn, reps=5)
+        print(f"{name:26s} B={B}: {med:8.3f} ms  ({passes * gb / med * 1e3:7.0f} GB/s algorithmic)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="*", default=["analysis", "gemm", "blstm"])
@@ -93,3 +110,5 @@ if __name__ == "__main__":
         bench_gemm(a.batch)
     if "blstm" in a.what:
         bench_blstm(a.batch)
+    if "dpcl" in a.what:
+        bench_dpcl(a.batch)
