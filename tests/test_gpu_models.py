@@ -201,3 +201,31 @@ def test_enhance_layer_steps_match_oracle(amss):
         a, b = t.store[k].detach().double().cpu(), st.tr[k].detach().double()
         assert float((a - b).abs().max()) < REL * max(float(b.abs().max()), 1e-3), k
     assert torch.equal(trunk_before, t.store["prediction/W"].detach())      # the trunk stays frozen
+
+
+# ------------------------------------------------------------------------------------------ config 5: 3 speakers
+def test_three_speaker_kmeans_inference(amss):
+    """BASELINE config 5 (3-speaker mixtures, K = 3 hard k-means masks): labels bit-exact vs the oracle on the
+    embeddings the GPU produced, and the three separated waveforms add up to the masked-by-ones reconstruction."""
+    tr, mo, ops = amss["trainer"], amss["models"], amss["ops"]
+    B, S, Lw = 2, 3, 4096
+    inf = tr.STFT_Separator_Inference(mo.DPCL, nb_speakers=3, nb_layers=1, layer_size=24, embedding_size=8, nb_tries=3,
+                                      nb_steps=5, window_size=256, hop_size=128, end_assign=True)
+    m = inf.model
+    mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=700)
+    with torch.no_grad():
+        spec, X = ops.stft(_dev(mix), 256, 128)
+        V = m.prediction(X)
+        Bq, Tt, Fb, E = V.shape
+        idx = random_init_idx(B * 3, Tt * Fb, S, np.random.RandomState(9))
+        sep, lab = m.separate(V, X, idx)
+        out = m.postprocessing(spec, lab)
+    okm = OracleKMeans(S, 3, 5, True, None, 2.0, True)
+    _, lab_ref = okm.fit(V.reshape(B, -1, E).cpu(), idx)
+    assert set(np.unique(lab.cpu().numpy())) <= {0, 1, 2}
+    assert float((lab.cpu() == lab_ref).float().mean()) > 0.99
+    assert out.shape == (B, S, Lw)
+    ones = torch.zeros_like(lab)
+    with torch.no_grad():
+        full = ops.istft_masked(spec, 1, 256, 128, labels=ones)          # a single all-ones mask
+    assert rel(out.sum(1), full[:, 0]) < 1e-3

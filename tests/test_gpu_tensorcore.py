@@ -170,3 +170,51 @@ def test_blstm_tc_fwd_bwd_close_to_oracle(ops, B, Tt, I, H):
           f"dx {errs[0]:.2e} dK {errs[1]:.2e}/{errs[2]:.2e} db {errs[3]:.2e}/{errs[4]:.2e}")
     assert err < 1e-2 and eg < 2e-2 and ec < 2e-2
     assert max(errs) < 3e-2
+
+
+# ------------------------------------------------------------------------------------------ whole steps in bf16
+def test_training_steps_bf16_track_the_oracle():
+    """Whole fwd+bwd+AMSGrad steps with every tensor-core kernel switched on (precision='bf16'): the cost of each
+    step stays within 2 % of the fp32 oracle's and the parameter update points the same way (cosine > 0.98)."""
+    import functools
+    from amss_b200 import models, trainer
+    from oracle import models as M
+    from oracle import steps as OS
+    B, S, Lw = 3, 2, 4096
+    t = trainer.Front_Separator_Trainer(models.DPCL, nb_layers=2, layer_size=300, embedding_size=8, learning_rate=1e-3,
+                                        window_size=64, filters=16, max_pool=32, hop_size=32, with_max_pool=True,
+                                        precision="bf16")
+    p = {k: v.detach().cpu().clone() for k, v in t.store.params.items()}
+    p0 = {k: v.clone() for k, v in p.items()}
+    st = OS.Stepper(p, functools.partial(OS.front_separator_loss, nb_layers=2, embedding_size=8, max_pool=32, hop=32), lr=1e-3)
+    for step in range(2):
+        mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=500 + step)
+        c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = float(t.train_step(dev(mix), dev(nm), dev(I)))
+        assert abs(c - c_ref) < 2e-2 * abs(c_ref), (step, c, c_ref)
+    num = den_a = den_b = 0.0
+    for k, v in st.tr.items():
+        da = (t.store[k].detach().cpu() - p0[k]).double().reshape(-1)
+        db = (v.detach() - p0[k]).double().reshape(-1)
+        num += float(da @ db); den_a += float(da @ da); den_b += float(db @ db)
+    cos = num / (den_a ** 0.5 * den_b ** 0.5 + 1e-30)
+    print(f"bf16 step: update cosine vs fp32 oracle {cos:.4f}")
+    assert cos > 0.98
+
+
+def test_stft_dpcl_config1_width_bf16_step():
+    """BASELINE config 1 widths (2 x BLSTM-300 -> H = 150 per direction, NC = 5 CTAs per cluster) in bf16."""
+    import functools
+    from amss_b200 import models, trainer
+    from oracle import models as M
+    from oracle import steps as OS
+    B, S, Lw = 4, 2, 4096
+    t = trainer.STFT_Separator_Trainer(models.DPCL, nb_layers=2, layer_size=300, embedding_size=10, learning_rate=1e-3,
+                                       window_size=128, hop_size=64, precision="bf16")
+    p = {k: v.detach().cpu().clone() for k, v in t.store.params.items()}
+    st = OS.Stepper(p, functools.partial(OS.stft_separator_loss, nb_layers=2, embedding_size=10, window_size=128, hop_size=64),
+                    lr=1e-3)
+    mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=600)
+    c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+    c = float(t.train_step(dev(mix), dev(nm), dev(I)))
+    assert abs(c - c_ref) < 2e-2 * abs(c_ref), (c, c_ref)
