@@ -540,13 +540,37 @@ int launch_bwd(const RecTcBwd& p, int NC, cudaStream_t st) {
     return AMSS_OK;
 }
 
-// as many clusters as the chip holds (one CTA per SM); sub-batches of 16 / 32 / 64 mixtures
-int pick_nb(int B, int NC, int nb_max) {
-    const int max_clusters = std::max(2, kNumSMs / NC);
+// Co-resident clusters are limited by the GPC size (a cluster of 10 CTAs fits once in a 16-20 SM GPC), not by
+// SMs / NC: ask the occupancy API, then take the smallest sub-batch (16 / 32 / 64 mixtures) that runs in one wave.
+template <typename K>
+int max_clusters(K kernel, int NC, size_t smem) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(NC * 16);
+    cfg.blockDim = dim3(BT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (NC > 8) cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 2) { cudaGetLastError(); n = std::max(2, kNumSMs / NC / 2); }
+    return n;
+}
+
+size_t fwd_smem(int NC, int NB) {
+    return 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)2 * 2 * NB * 33 * 4;
+}
+size_t bwd_smem(int NC, int NB) {
+    return (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4;
+}
+
+int pick_nb(int B, int maxc, int nb_max) {
     for (int nb : {16, 32, 64}) {
         if (nb > nb_max) break;
         const int nsub = (B + nb - 1) / nb;
-        if (2 * nsub <= max_clusters) return nb;
+        if (2 * nsub <= maxc) return nb;
     }
     return nb_max;
 }
@@ -568,7 +592,9 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
     p.prof = g_prof;
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.y = y;
     p.B = B; p.T = T; p.H = H; p.forget_bias = forget_bias;
-    const int nb = pick_nb(B, NC, 64);
+    static int maxc_cache[17] = {0};
+    if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32));
+    const int nb = pick_nb(B, maxc_cache[NC], 64);
     p.nsub = (B + nb - 1) / nb;
     if (nb == 16) return launch_fwd<16>(p, NC, st);
     if (nb == 32) return launch_fwd<32>(p, NC, st);
@@ -581,7 +607,9 @@ int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const floa
     RecTcBwd p;
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.dy = dy; p.dZ = dZ;
     p.B = B; p.T = T; p.H = H; p.MT = (NC * 32 + 127) / 128;
-    const int nb = pick_nb(B, NC, 32);
+    static int maxc_cache[17] = {0};
+    if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
+    const int nb = pick_nb(B, maxc_cache[NC], 32);
     p.nsub = (B + nb - 1) / nb;
     if (nb == 16) return launch_bwd<16>(p, NC, st);
     return launch_bwd<32>(p, NC, st);

@@ -1,0 +1,223 @@
+// Fused backward of the DPCL affinity loss (models/dpcl.py:41-86) and of the tf.nn.l2_normalize that
+// produced the embeddings (utils/ops.py:323-324), tensor-core version (AMSS_PREC_BF16):
+//     dV_i = g * D_i * (An v_i - Bn[:, l_i]),   dz_i = inv_i * (dV_i - v_i <v_i, dV_i>)
+// The [points x E] x [E x E] product runs on tcgen05 (M = 128 points per tile, N = K = E padded to 16):
+// loader warps stream 128-point tiles of V (coalesced float4), keep the fp32 rows in shared memory for
+// the normalisation Jacobian and write the bf16 K-major A operand; the E x E matrix An of the current
+// mixture is the resident B operand; accumulators are double buffered in TMEM; the epilogue thread of a
+// point owns its whole row (TMEM lane), so the row dot product <v, dV> needs no shuffles.  One pass over
+// V, one write of dz: the kernel is HBM-bound (2 x 4E bytes per point).
+#include "common.cuh"
+#include "tc.cuh"
+#include <algorithm>
+
+namespace amss {
+namespace {
+
+using namespace tc;
+
+constexpr int DT_THREADS = 288;   // warps 0-3 loaders, 4 MMA (+TMEM alloc), 5-8 epilogue
+constexpr int DT_MAXS = 4;
+
+struct DtParams {
+    const float* V;            // [B][TF][E] normalised embeddings
+    const uint8_t* labels;     // [B][TF]
+    const float* dloss;        // [1]
+    const float* stats;        // [B][E*E + S*E + S + 1]  (An, Bn, dinv, loss) from the forward pass
+    const float* inv_norm;     // [B*TF]
+    float* dz;                 // [B][TF][E]
+    int B, E, S, EK, pitch;
+    int64_t TF, ntiles, per;   // tiles of 128 points per mixture; flat tiles per CTA
+};
+
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[8];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int E = p.E, EK = p.EK, S = p.S, pitch = p.pitch;
+    const uint32_t a_bytes = (uint32_t)(EK / 8) * 16 * 128;           // A operand: 128 rows x EK
+    const uint32_t b_bytes = (uint32_t)(EK / 8) * (EK / 8) * 128;     // B operand: EK x EK
+    float* vs = reinterpret_cast<float*>(smem);                       // [2][128][pitch] fp32 rows (v, then dz)
+    uint8_t* a_s = smem + (size_t)2 * 128 * pitch * 4;                // [2][a_bytes]
+    uint8_t* b_s = a_s + 2 * a_bytes;                                 // [2][b_bytes]   (by mixture generation)
+    float* bn_s = reinterpret_cast<float*>(b_s + 2 * b_bytes);        // [2][S*E + S]   Bn, dinv
+    const uint32_t a_full = smem_u32(&bars[0]), a_empty = a_full + 16, t_full = a_full + 32, t_empty = a_full + 48;
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(a_full + 8 * b, 128); mbar_init(a_empty + 8 * b, 1);
+            mbar_init(t_full + 8 * b, 1);   mbar_init(t_empty + 8 * b, 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int64_t w0 = (int64_t)blockIdx.x * p.per, w1 = min(w0 + p.per, (int64_t)p.B * p.ntiles);
+    const int sstride = E * E + S * E + S + 1;
+    const int b_first = w0 < w1 ? (int)(w0 / p.ntiles) : 0;
+
+    if (warp < 4) {
+        // ---------------- loaders: V tile -> fp32 rows + bf16 A operand; An/Bn when the mixture changes ----------------
+        int bcur = -1;
+        uint32_t i = 0;
+        for (int64_t w = w0; w < w1; ++w, ++i) {
+            const int b = (int)(w / p.ntiles);
+            const int64_t p0 = (w - (int64_t)b * p.ntiles) * 128;
+            const int np = (int)min((int64_t)128, p.TF - p0);
+            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            mbar_wait(t_empty + 8 * buf, ph ^ 1);          // the epilogue of tile i-2 has finished with vs[buf] / TMEM[buf]
+            mbar_wait(a_empty + 8 * buf, ph ^ 1);          // the MMAs of tile i-2 have finished with a_s[buf]
+            if (b != bcur) {        // generation (b - b_first) & 1: An -> bf16 B operand [n][k] (An symmetric), Bn/dinv fp32
+                const int gen = (b - b_first) & 1;
+                const float* st = p.stats + (size_t)b * sstride;
+                uint8_t* bd = b_s + gen * b_bytes;
+                for (int u = tid; u < EK * (EK / 8); u += 128) {
+                    const int n = u % EK, kc = u / EK;
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { const int k = kc * 8 + e; v[e] = (n < E && k < E) ? st[n * E + k] : 0.f; }
+                    *reinterpret_cast<uint4*>(bd + (size_t)(kc * (EK / 8) + (n >> 3)) * 128 + (n & 7) * 16) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+                float* bn = bn_s + gen * (S * E + S);
+                for (int u = tid; u < S * E + S; u += 128) bn[u] = st[E * E + u];
+                bcur = b;
+            }
+            float* vb = vs + (size_t)buf * 128 * pitch;
+            const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + p0) * E);
+            const int e4 = E / 4;
+            for (int u = tid; u < 128 * e4; u += 128) {
+                const int r = u / e4, c = u - r * e4;
+                *reinterpret_cast<float4*>(vb + r * pitch + c * 4) = r < np ? __ldcs(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            named_sync(1, 128);
+            uint8_t* ab = a_s + buf * a_bytes;
+            const float* row = vb + tid * pitch;
+            for (int kc = 0; kc < EK / 8; ++kc) {
+                float v[8];
+                if (kc * 8 + 8 <= E) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(row + kc * 8), x1 = *reinterpret_cast<const float4*>(row + kc * 8 + 4);
+                    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = kc * 8 + e < E ? row[kc * 8 + e] : 0.f;
+                }
+                *reinterpret_cast<uint4*>(ab + (size_t)(kc * 16 + (tid >> 3)) * 128 + (tid & 7) * 16) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+            fence_async_smem();
+            mbar_arrive(a_full + 8 * buf);
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = idesc_bf16(128, EK, 0, 0);
+        const bool leader = elect_one();
+        uint32_t i = 0;
+        for (int64_t w = w0; w < w1; ++w, ++i) {
+            const int b = (int)(w / p.ntiles);
+            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            mbar_wait(a_full + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t aaddr = smem_u32(a_s + buf * a_bytes), baddr = smem_u32(b_s + ((b - b_first) & 1) * b_bytes);
+            for (int kk = 0; kk < EK / 16; ++kk) {
+                const uint64_t ad = smem_desc(aaddr + kk * 2 * 16 * 128, 16 * 128, 128);
+                const uint64_t bd = smem_desc(baddr + kk * 2 * (EK / 8) * 128, (EK / 8) * 128, 128);
+                if (leader) mma_bf16(tmem + buf * 64, ad, bd, idesc, kk > 0);
+            }
+            if (leader) { mma_commit(a_empty + 8 * buf); mma_commit(t_full + 8 * buf); }
+        }
+    } else {
+        // ---------------- epilogue: thread = point (TMEM lane); dV row, <v,dV>, dz row ----------------
+        const int q = warp & 3, r = q * 32 + lane, et = tid - 160;
+        const float gscale = p.dloss[0] / (float)p.B;
+        const int e4 = E / 4;
+        uint32_t i = 0;
+        for (int64_t w = w0; w < w1; ++w, ++i) {
+            const int b = (int)(w / p.ntiles);
+            const int64_t p0 = (w - (int64_t)b * p.ntiles) * 128;
+            const int np = (int)min((int64_t)128, p.TF - p0);
+            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            const float* bn = bn_s + ((b - b_first) & 1) * (S * E + S);
+            int l = 0;
+            float inv = 0.f;
+            if (r < np) { l = p.labels[(size_t)b * p.TF + p0 + r]; inv = p.inv_norm[(size_t)b * p.TF + p0 + r]; }
+            mbar_wait(a_full + 8 * buf, ph);               // acquire the loaders' fp32 rows / Bn
+            mbar_wait(t_full + 8 * buf, ph);
+            tc_fence_after();
+            float* vb = vs + (size_t)buf * 128 * pitch;
+            float4* row4 = reinterpret_cast<float4*>(vb + r * pitch);
+            const float d = gscale * bn[S * E + l];
+            const float* bl = bn + l * E;
+            float dv[64];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c * 16 < EK) {                         // warp-uniform
+                    uint32_t v[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + buf * 64 + c * 16, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int e = c * 16 + j;
+                        dv[e] = e < E ? d * (__uint_as_float(v[j]) - bl[e]) : 0.f;
+                    }
+                }
+            }
+            tc_fence_before();
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < e4) {
+                    const float4 x = row4[c];
+                    dot = fmaf(x.x, dv[4 * c], dot); dot = fmaf(x.y, dv[4 * c + 1], dot);
+                    dot = fmaf(x.z, dv[4 * c + 2], dot); dot = fmaf(x.w, dv[4 * c + 3], dot);
+                }
+            if (inv < 0.f) { inv = -inv; dot = 0.f; }      // clamped branch of l2_normalize: linear map
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (c < e4) {
+                    const float4 x = row4[c];
+                    row4[c] = make_float4(inv * (dv[4 * c] - x.x * dot), inv * (dv[4 * c + 1] - x.y * dot),
+                                          inv * (dv[4 * c + 2] - x.z * dot), inv * (dv[4 * c + 3] - x.w * dot));
+                }
+            named_sync(2, 128);                            // all dz rows of the tile are in vs[buf]
+            float4* dst = reinterpret_cast<float4*>(p.dz + ((size_t)b * p.TF + p0) * E);
+            for (int u = et; u < np * e4; u += 128) {
+                const int rr = u / e4, c = u - rr * e4;
+                __stcs(dst + u, *reinterpret_cast<const float4*>(vb + rr * pitch + c * 4));
+            }
+            mbar_arrive(t_empty + 8 * buf);                // vs[buf] and TMEM[buf] may be reused
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace
+
+bool dpcl_bwd_tc_supported(int E, int S) { return E % 4 == 0 && E >= 8 && E <= 64 && S >= 1 && S <= DT_MAXS; }
+
+int dpcl_bwd_tc(const float* V, const uint8_t* labels, const float* dloss, const float* stats, const float* inv_norm, int B,
+                int64_t TF, int E, int S, float* dz, cudaStream_t st) {
+    DtParams p;
+    p.V = V; p.labels = labels; p.dloss = dloss; p.stats = stats; p.inv_norm = inv_norm; p.dz = dz;
+    p.B = B; p.E = E; p.S = S; p.TF = TF;
+    p.EK = (E + 15) / 16 * 16;
+    p.pitch = 4 * (((E + 3) / 4) | 1);
+    p.ntiles = (TF + 127) / 128;
+    const int64_t total = (int64_t)B * p.ntiles;
+    const int grid = (int)std::min<int64_t>(total, 2 * kNumSMs);
+    p.per = (total + grid - 1) / grid;
+    const size_t smem = (size_t)2 * 128 * p.pitch * 4 + 2 * (size_t)(p.EK / 8) * 16 * 128 + 2 * (size_t)(p.EK / 8) * (p.EK / 8) * 128 +
+                        2 * (size_t)(S * E + S) * 4 + 64;
+    AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AMSS_LAUNCH(dpcl_bwd_tc_kernel, grid, DT_THREADS, smem, st, p);
+    return AMSS_OK;
+}
+
+}  // namespace amss

@@ -606,12 +606,21 @@ extern "C" int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const f
     return dpcl_bwd_launch(V, labels, dloss, nullptr, B, TF, E, S, dV, workspace, stream);
 }
 
+namespace amss {
+bool dpcl_bwd_tc_supported(int E, int S);
+int dpcl_bwd_tc(const float* V, const uint8_t* labels, const float* dloss, const float* stats, const float* inv_norm, int B,
+                int64_t TF, int E, int S, float* dz, cudaStream_t st);
+}  // namespace amss
+
 extern "C" int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labels, const float* dloss,
-                                             const float* inv_norm, int B, int64_t TF, int E, int S, float* dz,
-                                             const void* workspace, void* stream) {
+                                             const float* inv_norm, int B, int64_t TF, int E, int S, int precision,
+                                             float* dz, const void* workspace, void* stream) {
     AMSS_REQUIRE(V && labels && dloss && inv_norm && dz && workspace, "dpcl_loss_bwd_normalized: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_bwd_normalized: S out of range");
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd_normalized: E=%d outside [1,64]", E);
+    if (precision == AMSS_PREC_BF16 && dpcl_bwd_tc_supported(E, S) &&
+        ((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0)
+        return dpcl_bwd_tc(V, labels, dloss, (const float*)workspace, inv_norm, B, TF, E, S, dz, (cudaStream_t)stream);
     return dpcl_bwd_launch(V, labels, dloss, inv_norm, B, TF, E, S, dz, workspace, stream);
 }
 

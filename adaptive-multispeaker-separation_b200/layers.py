@@ -194,17 +194,17 @@ class _NormDPCLLossFn(torch.autograd.Function):
     (affinity-loss gradient + normalisation Jacobian), dV never reaches HBM and v is read once."""
 
     @staticmethod
-    def forward(ctx, z, V, inv, labels, S):
+    def forward(ctx, z, V, inv, labels, S, precision):
         loss, ws = ops.dpcl_loss_fwd(V, labels, S)
         ctx.save_for_backward(V, inv, labels, ws)
-        ctx.S, ctx.zshape = S, z.shape
+        ctx.S, ctx.zshape, ctx.precision = S, z.shape, precision
         return loss.view(())
 
     @staticmethod
     def backward(ctx, dloss):
         V, inv, labels, ws = ctx.saved_tensors
-        dz = ops.dpcl_loss_bwd_normalized(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws, inv)
-        return dz.view(ctx.zshape), None, None, None, None
+        dz = ops.dpcl_loss_bwd_normalized(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws, inv, ctx.precision)
+        return dz.view(ctx.zshape), None, None, None, None, None
 
 
 class _L41LossFn(torch.autograd.Function):
@@ -306,12 +306,12 @@ def l2_normalize(z, E):
     return v
 
 
-def dpcl_loss(V, labels, S, prenorm=None):
+def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32):
     """prenorm = (z, inv_norm) as stashed by l2_normalize() on its output: the loss becomes one autograd node
     on z with a fused backward (DPCL gradient + normalisation Jacobian)."""
     if prenorm is not None:
         z, inv = prenorm
-        return _NormDPCLLossFn.apply(z, V.detach(), inv, labels, S)
+        return _NormDPCLLossFn.apply(z, V.detach(), inv, labels, S, precision)
     return _DPCLLossFn.apply(V, labels, S)
 
 

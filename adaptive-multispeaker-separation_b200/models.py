@@ -344,7 +344,7 @@ class DPCL(Separator):
     def cost(self, V, labels, I=None):
         B, Tt, Fb, E = V.shape
         return L.dpcl_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), self.S,
-                           prenorm=getattr(V, "_amss_prenorm", None))
+                           prenorm=getattr(V, "_amss_prenorm", None), precision=self.precision)
 
 
 class L41Model(Separator):

@@ -260,13 +260,13 @@ def dpcl_loss_bwd(V, labels, S, dloss, ws):
     return dV
 
 
-def dpcl_loss_bwd_normalized(V, labels, S, dloss, ws, inv_norm):
+def dpcl_loss_bwd_normalized(V, labels, S, dloss, ws, inv_norm, precision=AMSS_PREC_FP32):
     """Fused DPCL backward + l2_normalize backward: returns dz (gradient w.r.t. the un-normalised embeddings)."""
     _chk(V, labels, dloss, inv_norm)
     B, TF, E = V.shape
     dz = torch.empty_like(V)
-    _lib.call("amss_dpcl_loss_bwd_normalized", _p(V), _p(labels), _p(dloss), _p(inv_norm), B, TF, E, S, _p(dz), _p(ws),
-              _stream())
+    _lib.call("amss_dpcl_loss_bwd_normalized", _p(V), _p(labels), _p(dloss), _p(inv_norm), B, TF, E, S, precision, _p(dz),
+              _p(ws), _stream())
     return dz
 
 

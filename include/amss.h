@@ -184,10 +184,11 @@ int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const float* dloss
                        void* stream);
 /* Same, fused with the backward of the tf.nn.l2_normalize that produced V (utils/ops.py:323-324,
  * models/dpcl.py:36-37): V = normalised embeddings, inv_norm[B*TF] as written by amss_l2norm_fwd ->
- * dz[B,TF,E] = gradient w.r.t. the un-normalised embeddings.  dV is never materialised.          */
+ * dz[B,TF,E] = gradient w.r.t. the un-normalised embeddings.  dV is never materialised.
+ * AMSS_PREC_BF16 runs the [points x E] x [E x E] product on tcgen05 (bf16 operands).           */
 int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labels, const float* dloss,
-                                  const float* inv_norm, int B, int64_t TF, int E, int S, float* dz,
-                                  const void* workspace, void* stream);
+                                  const float* inv_norm, int B, int64_t TF, int E, int S,
+                                  int precision, float* dz, const void* workspace, void* stream);
 /* L41Model.cost, sampling=None (models/L41.py:47-63, 150-178):
  * mean_{b,tf,s} -log sigmoid(y * <spk[b,s,:], emb[b,tf,:]>), y=+1 if labels==s else -1.
  * spk[B,S,E] = (normalised) gathered speaker vectors.                                   */

@@ -218,3 +218,39 @@ def test_stft_dpcl_config1_width_bf16_step():
     c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
     c = float(t.train_step(dev(mix), dev(nm), dev(I)))
     assert abs(c - c_ref) < 2e-2 * abs(c_ref), (c, c_ref)
+
+
+# ------------------------------------------------------------------------------------------ fused DPCL backward
+@pytest.mark.parametrize("B,TF,E,S", [(3, 1000, 40, 2), (2, 130, 40, 3), (5, 128, 16, 2), (2, 4099, 64, 2), (70, 257, 40, 2)])
+def test_dpcl_fused_backward_tc_matches_autograd(ops, B, TF, E, S):
+    """dz of  loss(l2_normalize(z))  from the fused tcgen05 kernel vs torch autograd of the oracle (fp64) and vs the fp32
+    fused kernel: 5e-3 of the gradient range (bf16 operands in the [points x E] x [E x E] product)."""
+    from oracle import models as M
+    g = torch.Generator().manual_seed(70 + B)
+    lab = torch.randint(0, S, (B, TF), generator=g)
+    # clustered (anisotropic) embeddings with imperfect labels, so that An v is far from parallel to v and the
+    # tensor-core product really matters in dz
+    centers = torch.randn(B, S, E, generator=g, dtype=torch.float64) * 2.0
+    noisy = torch.where(torch.rand(B, TF, generator=g) < 0.3, torch.randint(0, S, (B, TF), generator=g), lab)
+    z = centers[torch.arange(B)[:, None], noisy] + 0.5 * torch.randn(B, TF, E, generator=g, dtype=torch.float64)
+    z[0, 3] = 0.0                                          # a row in the clamped branch of l2_normalize
+    z.requires_grad_(True)
+    V = T.l2_normalize(z, -1)
+    cost = M.dpcl_cost(V.reshape(B, TF, 1, E), torch.nn.functional.one_hot(lab, S).double().reshape(B, TF, 1, S))
+    (gz,) = torch.autograd.grad(cost, z)
+    zf = dev(z.detach().float())
+    labd = dev(lab.to(torch.uint8))
+    Vg, inv = ops.l2norm_fwd(zf, E)
+    loss, ws = ops.dpcl_loss_fwd(Vg, labd, S)
+    one = torch.ones(1, device="cuda")
+    dz32 = ops.dpcl_loss_bwd_normalized(Vg, labd, S, one, ws, inv, ops.AMSS_PREC_FP32)
+    dz16 = ops.dpcl_loss_bwd_normalized(Vg, labd, S, one, ws, inv, ops.AMSS_PREC_BF16)
+    # the clamped row has inv_norm = 1e6 and would dominate a max-norm comparison: check it on its own
+    keep = torch.ones(B, TF, dtype=torch.bool)
+    keep[0, 3] = False
+    gk = gz[keep]
+    assert rel(dz32.cpu()[keep], gk) < 1e-3 and rel(dz32.cpu()[0, 3], gz[0, 3]) < 1e-3
+    err = rel(dz16.cpu()[keep], gk)
+    print(f"fused dpcl bwd tc B={B} TF={TF} E={E} S={S}: rel err {err:.2e} (fp32 kernel {rel(dz32.cpu()[keep], gk):.1e})")
+    assert 1e-6 < err < 5e-3                               # bf16 operands: visibly not the fp32 kernel, within tolerance
+    assert rel(dz16.cpu()[0, 3], gz[0, 3]) < 5e-3

@@ -93,7 +93,8 @@ def bench_dpcl(B):
     for name, fn, passes in (("l2norm_fwd", lambda: ops.l2norm_fwd(z, E), 2), ("dpcl_loss_fwd", lambda: ops.dpcl_loss_fwd(V, lab, 2), 1),
                              ("dpcl_loss_bwd", lambda: ops.dpcl_loss_bwd(V, lab, 2, one, ws), 2),
                              ("l2norm_bwd", lambda: ops.l2norm_bwd(V, inv, dV, E), 3),
-                             ("dpcl_loss_bwd_normalized", lambda: ops.dpcl_loss_bwd_normalized(V, lab, 2, one, ws, inv), 2)):
+                             ("dpcl_loss_bwd_normalized", lambda: ops.dpcl_loss_bwd_normalized(V, lab, 2, one, ws, inv), 2),
+                             ("dpcl_bwd_normalized tc", lambda: ops.dpcl_loss_bwd_normalized(V, lab, 2, one, ws, inv, ops.AMSS_PREC_BF16), 2)):
         med, _ = timeit(fn, reps=5)
         print(f"{name:26s} B={B}: {med:8.3f} ms  ({passes * gb / med * 1e3:7.0f} GB/s algorithmic)")
 
