@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace amss {
 namespace {
@@ -48,6 +49,7 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -75,13 +77,13 @@ struct RecTcFwd {
 
 // Dependent tcgen05.mma into ONE accumulator serialise at the MMA pipeline latency (~75 clk each at N = 16..64,
 // measured), so the K steps are dealt round-robin to FW_NACC independent accumulators, summed in the epilogue.
-constexpr int FW_NACC = 4;
+constexpr int FW_NACC = 1;
 constexpr uint32_t FW_ACOL = 256;     // TMEM: D_a at columns [a*NB, (a+1)*NB), A at [FW_ACOL, FW_ACOL + 8*ksteps)
 
 template <int NB>
 __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[3];          // [0] MMA done, [1..2] h_full[buf]
+    __shared__ __align__(8) uint64_t bars[5];          // [0] MMA done, [1..2] h_full[buf], [3..4] zx_full[buf]
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), NC = cluster_nctarank();
@@ -99,11 +101,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
     uint8_t* hst = h_s + 2 * h_bytes;                                 // [2][SLICE]     own block, source of the bulk copies
     float* gx = reinterpret_cast<float*>(hst + 2 * SLICE);            // [2][128][NB+1] activated gates
     float* cy = gx + 2 * 128 * GXP;                                   // [2][2][NB][33] (c | h) staging for the writers
-    const uint32_t bar_mma = smem_u32(&bars[0]), h_full = smem_u32(&bars[1]);
+    float* zxs = cy + 2 * 2 * NB * 33;                                // [2][128][NB+1] hoisted input projection, two steps ahead
+    const uint32_t bar_mma = smem_u32(&bars[0]), h_full = smem_u32(&bars[1]), zx_full = smem_u32(&bars[3]);
     const uint32_t tcols = pow2_cols(FW_ACOL + 8 * KST);
 
     if (tid == 0) {
         mbar_init(bar_mma, 1); mbar_init(h_full, 1); mbar_init(h_full + 8, 1);
+        mbar_init(zx_full, 128); mbar_init(zx_full + 8, 128);
         mbar_fence_init();
     }
     if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), tcols);
@@ -148,18 +152,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
         for (int i = 0; i < ITEMS; ++i)
 #pragma unroll
             for (int e = 0; e < 4; ++e) creg[i][e] = 0.f;
-        float zx[NB];
-        auto load_zx = [&](int t) {
-            const float* gp = p.gates + (((size_t)d * T + t) * B + b0) * H4 + q * H + ug;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) zx[b] = (b < nvalid && ug < H) ? __ldcg(gp + (size_t)b * H4) : 0.f;
-        };
         const float fb = q == 2 ? p.forget_bias : 0.f;
         long long* prof = (blockIdx.x == 0 && tid == 0) ? p.prof : nullptr;
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
             PROF(0);
-            load_zx(t);                           // in flight while the MMAs of this step run
             uint32_t acc[NB];
             if (s > 0) {
                 mbar_wait(bar_mma, (s - 1) & 1);
@@ -185,14 +182,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
                 for (int b = 0; b < NB; ++b) acc[b] = 0u;
             }
             PROF(2);
+            mbar_wait(zx_full + 8 * (s & 1), (s >> 1) & 1);   // the writer warps staged this step's input projection 2 steps ago
             float* gxs = gx + (s & 1) * (128 * GXP);
+            const float* zr = zxs + (s & 1) * (128 * GXP) + (q * 32 + lane) * GXP;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const float z = __uint_as_float(acc[b]) + zx[b] + fb;
+                const float z = __uint_as_float(acc[b]) + zr[b] + fb;
                 gxs[(q * 32 + lane) * GXP + b] = q == 1 ? tanh_fast(z) : sigmoid_fast(z);
             }
             PROF(3);
-            bar_sync_named(1, 256);               // gx[s&1] complete (compute + writer warps)
+            bar_sync_named(1, 256);               // gx[s&1] complete, zxs consumed (compute + writer warps)
             PROF(4);
             uint8_t* hsl = hst + (s & 1) * SLICE;
             float* cys = cy + (s & 1) * (2 * NB * 33);
@@ -219,19 +218,23 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
             }
             PROF(5);
             fence_async_smem();                   // staged block -> visible to the bulk-copy engine
-            bar_sync_named(2, 128);
+            bar_arrive_named(2, 160);             // hand the block to the MMA/control warp (no wait here)
             PROF(6);
-            if ((uint32_t)tid < NC && s + 1 < T) {     // one bulk copy per thread: all NC pushes issue in parallel
-                const uint32_t dst = smem_u32(h_s + ((s + 1) & 1) * h_bytes) + crank * SLICE;
-                const uint32_t bar = h_full + 8 * ((s + 1) & 1);
-                bulk_s2c(mapa(dst, tid), smem_u32(hsl), SLICE, mapa(bar, tid));
-            }
-            PROF(7);
         }
     } else if (warp == 4) {
         // =========================== MMA issuer (converged loop, elected lane) ===========================
         long long* prof = (blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
         const bool leader = elect_one();
+        auto push_h = [&](int s) {                  // after the cell phase of step s: push the staged block to every CTA
+            bar_sync_named(2, 160);
+            if ((uint32_t)lane < NC && s + 1 < T) { // one bulk copy per lane: all NC pushes issue in parallel
+                const uint32_t dst = smem_u32(h_s + ((s + 1) & 1) * h_bytes) + crank * SLICE;
+                const uint32_t bar = h_full + 8 * ((s + 1) & 1);
+                bulk_s2c(mapa(dst, lane), smem_u32(hst + (s & 1) * SLICE), SLICE, mapa(bar, lane));
+            }
+            __syncwarp();
+        };
+        push_h(0);
         for (int s = 1; s < T; ++s) {
             const uint32_t buf = s & 1;
             mbar_wait(h_full + 8 * buf, ((s - 1) >> 1) & 1);        // all NC blocks of h_{s-1} have landed
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
             }
             if (leader) mma_commit(bar_mma);
             PROF(10);
+            push_h(s);
         }
     } else {
         // =========================== writer warps: saved gates, c, y -> global ===========================
@@ -254,21 +258,99 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
             const int tp = d == 0 ? sprev : T - 1 - sprev;
             const float* cys = cy + (sprev & 1) * (2 * NB * 33);
             const int ul = wt & 31;
-            if (u0 + ul < H)
-                for (int b = wt >> 5; b < nvalid; b += 4) {
-                    __stcg(p.cst + (((size_t)d * T + tp) * B + b0 + b) * H + u0 + ul, cys[b * 33 + ul]);
-                    __stcg(p.y + ((size_t)tp * B + b0 + b) * 2 * H + d * H + u0 + ul, cys[NB * 33 + b * 33 + ul]);
+            if (u0 + ul < H) {
+                float cv[NB / 4], hv[NB / 4];
+#pragma unroll
+                for (int i = 0; i < NB / 4; ++i) {      // loads first, then the stores: no LDS -> STG dependency chain
+                    const int b = (wt >> 5) + 4 * i;
+                    cv[i] = cys[b * 33 + ul];
+                    hv[i] = cys[NB * 33 + b * 33 + ul];
+                }
+#pragma unroll
+                for (int i = 0; i < NB / 4; ++i) {
+                    const int b = (wt >> 5) + 4 * i;
+                    if (b < nvalid) {
+                        __stcg(p.cst + (((size_t)d * T + tp) * B + b0 + b) * H + u0 + ul, cv[i]);
+                        __stcg(p.y + ((size_t)tp * B + b0 + b) * 2 * H + d * H + u0 + ul, hv[i]);
+                    }
+                }
+            }
+        };
+        long long* prof = (blockIdx.x == 0 && wt == 0) ? p.prof : nullptr;
+        // hoisted input projection (+bias) of step sn -> registers (issue) -> zxs[sn&1][gate*32+unit][mixture] (commit);
+        // 16-byte loads, a warp = 4 rows x 128 B.  Issued two steps ahead: the rows were just written by the projection
+        // GEMM and mostly come from HBM (~2 us under load).
+        constexpr int ZV = 4 * (NB / 16);
+        float4 zreg[ZV];
+        const int u4 = (wt & 7) * 4, rb = wt >> 3;
+        const bool vec = (H & 3) == 0 && u0 + u4 + 4 <= H;
+        auto issue_zx = [&](int sn) {
+            const int t = d == 0 ? sn : T - 1 - sn;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+                for (int rr = 0; rr < NB / 16; ++rr) {
+                    const int b = rr * 16 + rb;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b < nvalid) {
+                        const float* gi = p.gates + (((size_t)d * T + t) * B + b0 + b) * H4 + g4 * H + u0 + u4;
+                        if (vec) v = __ldcg(reinterpret_cast<const float4*>(gi));
+                        else {
+                            if (u0 + u4 < H) v.x = __ldcg(gi);
+                            if (u0 + u4 + 1 < H) v.y = __ldcg(gi + 1);
+                            if (u0 + u4 + 2 < H) v.z = __ldcg(gi + 2);
+                            if (u0 + u4 + 3 < H) v.w = __ldcg(gi + 3);
+                        }
+                    }
+                    zreg[g4 * (NB / 16) + rr] = v;
                 }
         };
+        auto commit_zx = [&](int sn) {
+            float* zb = zxs + (sn & 1) * (128 * GXP);
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+                for (int rr = 0; rr < NB / 16; ++rr) {
+                    const float4 v = zreg[g4 * (NB / 16) + rr];
+                    float* zp = zb + (g4 * 32 + u4) * GXP + rr * 16 + rb;
+                    zp[0] = v.x; zp[GXP] = v.y; zp[2 * GXP] = v.z; zp[3 * GXP] = v.w;
+                }
+            mbar_arrive(zx_full + 8 * (sn & 1));
+        };
+        issue_zx(0); commit_zx(0);
+        if (T > 1) { issue_zx(1); commit_zx(1); }
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
-            bar_sync_named(1, 256);
+            if (s + 2 < T) issue_zx(s + 2);               // in flight under this step's stores
+            bar_sync_named(1, 256);                       // gx[s&1] complete; zxs[s&1] consumed by the compute warps
+            PROF(7);
             const float* gxs = gx + (s & 1) * (128 * GXP);
-            if (wu < H) {
-                float* gout = p.gates + (((size_t)d * T + t) * B + b0) * H4 + wq * H + wu;
-                for (int b = 0; b < nvalid; ++b) __stcg(gout + (size_t)b * H4, gxs[wt * GXP + b]);
+            {   // saved gates: 16-byte stores, thread = (4 consecutive units, one mixture row); a warp covers 4 rows x 128 B
+                const int u4 = (wt & 7) * 4, rb = wt >> 3;            // unit quad, row within a group of 16 rows
+                const bool vec = (H & 3) == 0 && u0 + u4 + 4 <= H;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+                    for (int rr = 0; rr < NB; rr += 16) {
+                        const int b = rr + rb;
+                        const float* gp = gxs + (g4 * 32 + u4) * GXP + b;
+                        const float4 v = make_float4(gp[0], gp[GXP], gp[2 * GXP], gp[3 * GXP]);
+                        if (b < nvalid) {
+                            float* go = p.gates + (((size_t)d * T + t) * B + b0 + b) * H4 + g4 * H + u0 + u4;
+                            if (vec) __stcg(reinterpret_cast<float4*>(go), v);
+                            else {
+                                if (u0 + u4 < H) __stcg(go, v.x);
+                                if (u0 + u4 + 1 < H) __stcg(go + 1, v.y);
+                                if (u0 + u4 + 2 < H) __stcg(go + 2, v.z);
+                                if (u0 + u4 + 3 < H) __stcg(go + 3, v.w);
+                            }
+                        }
+                    }
             }
+            PROF(8);
             if (s > 0) flush_cy(s - 1);
+            if (s + 2 < T) commit_zx(s + 2);
+            PROF(11);
         }
         bar_sync_named(3, 256);                       // the last cell phase has written cy
         flush_cy(T - 1);
@@ -280,10 +362,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
     if (warp == 4) tmem_dealloc(tmem, tcols);
 }
 
+size_t fwd_smem(int NC, int NB);
+
 template <int NB>
 int launch_fwd(const RecTcFwd& p, int NC, cudaStream_t st) {
-    const size_t smem = 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)2 * 128 * (NB + 1) * 4 +
-                        (size_t)2 * 2 * NB * 33 * 4;
+    const size_t smem = fwd_smem(NC, NB);
     if (smem > 226 * 1024) { set_error("blstm_rec_fwd_tc: H=%d NB=%d needs %zu B of shared memory", p.H, NB, smem); return AMSS_ERR_UNSUPPORTED; }
     AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_fwd_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (NC > 8) AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_fwd_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -414,12 +497,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 tc_fence_after();
                 for (int m = 0; m < MT; ++m) {
                     const uint32_t dest = m * 4 + q;  // units m*128 + q*32 + lane  ->  CTA dest, local unit = lane
-                    uint32_t acc[NB], acc1[NB];
-                    if (NB == 16) { tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 2 * m * NB, acc); tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (2 * m + 1) * NB, acc1); }
-                    else { tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 2 * m * NB, acc); tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (2 * m + 1) * NB, acc1); }
+                    uint32_t acc[NB];
+                    if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
+                    else tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) acc[b] = __float_as_uint(__uint_as_float(acc[b]) + __uint_as_float(acc1[b]));
                     if (dest < NC) {
                         uint8_t* pd = ps + (size_t)dest * BLK + lane * (NB * 2);
 #pragma unroll
@@ -433,12 +514,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 }
                 tc_fence_before();
                 fence_async_smem();
-                bar_sync_named(2, 128);
-                if ((uint32_t)tid < NC) {                 // one bulk copy per thread
-                    const uint32_t dst = smem_u32(r_s + (n & 1) * r_bytes) + crank * BLK;
-                    const uint32_t bar = r_full + 8 * (n & 1);
-                    bulk_s2c(mapa(dst, tid), smem_u32(ps) + tid * BLK, BLK, mapa(bar, tid));
-                }
+                bar_arrive_named(2, 160);                 // the MMA/control warp pushes the staged partials
                 mbar_wait(r_full + 8 * (n & 1), ((n - 1) >> 1) & 1);       // every CTA's partials for my units have landed
                 if (tid == 0 && n + 2 < T) mbar_expect_tx(r_full + 8 * (n & 1), NC * BLK);   // re-arm for step n+2
                 const uint8_t* rb = r_s + (n & 1) * r_bytes + (size_t)lane * (NB * 2) + q * IT * 2;
@@ -494,9 +570,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 for (int kk = 0; kk < 8; ++kk)
                     for (int m = 0; m < MT; ++m) {
                         const uint64_t bd = smem_desc(zaddr + kk * 2 * BG * 128, BG * 128, 128);
-                        if (leader) mma_bf16_ts(tmem + (2 * m + (kk & 1)) * NB, tmem + BW_ACOL + m * 64 + kk * 8, bd, idesc, kk > 1);
+                        if (leader) mma_bf16_ts(tmem + m * NB, tmem + BW_ACOL + m * 64 + kk * 8, bd, idesc, kk > 0);
                     }
                 if (leader) mma_commit(bar_mma);
+                bar_sync_named(2, 160);                   // partial sums of this step are staged in p_s[n&1]
+                if ((uint32_t)lane < NC) {                // one bulk copy per lane
+                    const uint32_t dst = smem_u32(r_s + (n & 1) * r_bytes) + crank * BLK;
+                    const uint32_t bar = r_full + 8 * (n & 1);
+                    bulk_s2c(mapa(dst, lane), smem_u32(p_s + (n & 1) * r_bytes) + lane * BLK, BLK, mapa(bar, lane));
+                }
             }
             __syncwarp();
             bar_sync_named(1, 288);
@@ -510,7 +592,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
             const float* dzb = dzs + (n & 1) * (128 * ZP);
             if (wu < H) {
                 float* zo = p.dZ + (((size_t)d * T + t) * B + b0) * H4 + wq * H + wu;
-                for (int b = 0; b < nvalid; ++b) __stcg(zo + (size_t)b * H4, dzb[wt * ZP + b]);
+#pragma unroll
+                for (int c = 0; c < NB; c += 16) {
+                    float gv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) gv[j] = dzb[wt * ZP + c + j];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (c + j < nvalid) __stcg(zo + (size_t)(c + j) * H4, gv[j]);
+                }
             }
         }
     }
@@ -560,7 +649,7 @@ int max_clusters(K kernel, int NC, size_t smem) {
 }
 
 size_t fwd_smem(int NC, int NB) {
-    return 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)2 * 2 * NB * 33 * 4;
+    return 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)4 * 128 * (NB + 1) * 4 + (size_t)2 * 2 * NB * 33 * 4;
 }
 size_t bwd_smem(int NC, int NB) {
     return (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4;
@@ -594,11 +683,10 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
     p.B = B; p.T = T; p.H = H; p.forget_bias = forget_bias;
     static int maxc_cache[17] = {0};
     if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32));
-    const int nb = pick_nb(B, maxc_cache[NC], 64);
+    const int nb = pick_nb(B, maxc_cache[NC], 32);       // larger batches run as several waves of clusters
     p.nsub = (B + nb - 1) / nb;
     if (nb == 16) return launch_fwd<16>(p, NC, st);
-    if (nb == 32) return launch_fwd<32>(p, NC, st);
-    return launch_fwd<64>(p, NC, st);
+    return launch_fwd<32>(p, NC, st);
 }
 
 int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,

@@ -12,7 +12,8 @@ import amss_b200  # noqa: E402,F401
 from amss_b200 import ops, _lib  # noqa: E402
 
 NAMES = ["0 step start", "1 mma done", "2 tmem ld done", "3 activation done", "4 named bar", "5 cell done",
-         "6 fences", "7 arrive.release", "8 cluster wait", "9 mma warp start", "10 mma issued"]
+         "6 staged+arrive", "7 writer: barrier passed", "8 writer: gates stored", "9 mma warp: h landed", "10 mma issued",
+         "11 writer: c,y stored"]
 
 for B in (16, 64, 128):
     T, I, H = 250, 600, 300
@@ -32,4 +33,4 @@ for B in (16, 64, 128):
         row = p[s]
         base = int(row[0])
         print(f" step {100 + s}: total {int(p[s + 1][0]) - base} clk ; " +
-              " ".join(f"[{k}]+{int(row[k]) - base}" for k in range(1, 11)))
+              " ".join(f"[{k}]+{int(row[k]) - base}" for k in range(1, 12)))
