@@ -59,6 +59,8 @@ __host__ __device__ inline uint32_t pow2_cols(uint32_t c) { uint32_t r = 32; whi
 // Optional step profile (diagnostics): clock64() stamps of CTA 0, steps [PROF_S0, PROF_S0+4).
 constexpr int PROF_S0 = 100, PROF_N = 4, PROF_K = 12;
 long long* g_prof = nullptr;
+long long* g_prof_bwd = nullptr;
+#define PROFB(k) do { if (prof0 && n >= PROF_S0 && n < PROF_S0 + PROF_N) prof0[(n - PROF_S0) * PROF_K + (k)] = clock64(); } while (0)
 #define PROF(k) do { if (prof && s >= PROF_S0 && s < PROF_S0 + PROF_N) prof[(s - PROF_S0) * PROF_K + (k)] = clock64(); } while (0)
 
 // =================================================================================================
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
 }
 
 size_t fwd_smem(int NC, int NB);
+size_t bwd_smem(int NC, int NB);
 
 template <int NB>
 int launch_fwd(const RecTcFwd& p, int NC, cudaStream_t st) {
@@ -388,6 +391,7 @@ int launch_fwd(const RecTcFwd& p, int NC, cudaStream_t st) {
 // backward
 // =================================================================================================
 struct RecTcBwd {
+    long long* prof;
     const float* Wh[2];   // [H][ldw]
     int ldw;
     const float* gates;   // [2][T][B][4H] activated gates (saved by the forward pass)
@@ -402,7 +406,7 @@ constexpr uint32_t BW_ACOL = 256;     // TMEM: D tile (m, parity of the K step) 
 template <int NB>
 __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[3];          // [0] MMA done, [1..2] r_full[buf]
+    __shared__ __align__(8) uint64_t bars[6];          // [0] MMA done, [1..2] r_full[buf], [3..5] sv_full[slot]
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), NC = cluster_nctarank();
@@ -418,11 +422,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
     uint8_t* r_s = z_s + NB * 128 * 2;                                   // [2][NC][32][NB] bf16   received partials
     uint8_t* p_s = r_s + 2 * r_bytes;                                    // [2][NC][32][NB] bf16   partials to send (by dest)
     float* dzs = reinterpret_cast<float*>(p_s + 2 * r_bytes);            // [2][128][NB+1] fp32 dz staging for the writers
-    const uint32_t bar_mma = smem_u32(&bars[0]), r_full = smem_u32(&bars[1]);
+    float* svs = dzs + 2 * 128 * ZP;                                     // [3][7][NB][32] saved gates / c / c_prev / dy, 3 steps ahead (cp.async ring)
+    const uint32_t bar_mma = smem_u32(&bars[0]), r_full = smem_u32(&bars[1]), sv_full = smem_u32(&bars[3]);
     const uint32_t tcols = pow2_cols(BW_ACOL + 64 * MT);
 
     if (tid == 0) {
         mbar_init(bar_mma, 1); mbar_init(r_full, 1); mbar_init(r_full + 8, 1);
+        mbar_init(sv_full, 128); mbar_init(sv_full + 8, 128); mbar_init(sv_full + 16, 128);
         mbar_fence_init();
     }
     if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), tcols);
@@ -467,33 +473,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
         float dcc[IT];
 #pragma unroll
         for (int i = 0; i < IT; ++i) dcc[i] = 0.f;
-        float sv[IT][7];                              // gi gj gf go c cprev dy  (loaded while the MMAs run)
-        auto prefetch = [&](int s) {
-            const int t = d == 0 ? s : T - 1 - s;
-            const int tprev = d == 0 ? t - 1 : t + 1;
-#pragma unroll
-            for (int i = 0; i < IT; ++i) {
-                const int b = q * IT + i;
-                const bool ok = b < nvalid && ug < H;
-                const size_t row = ((size_t)d * T + t) * B + b0 + b;
-                const float* g = p.gates + row * H4 + ug;
-                sv[i][0] = ok ? __ldcg(g) : 0.f;
-                sv[i][1] = ok ? __ldcg(g + H) : 0.f;
-                sv[i][2] = ok ? __ldcg(g + 2 * H) : 0.f;
-                sv[i][3] = ok ? __ldcg(g + 3 * H) : 0.f;
-                sv[i][4] = ok ? __ldcg(p.cst + row * H + ug) : 0.f;
-                sv[i][5] = (ok && s > 0) ? __ldcg(p.cst + (((size_t)d * T + tprev) * B + b0 + b) * H + ug) : 0.f;
-                sv[i][6] = ok ? __ldcg(p.dy + ((size_t)t * B + b0 + b) * 2 * H + d * H + ug) : 0.f;
-            }
-        };
+        long long* prof0 = (blockIdx.x == 0 && tid == 0) ? p.prof : nullptr;
         for (int s = T - 1; s >= 0; --s) {
             const int n = T - 1 - s;                  // step counter
-            prefetch(s);
+            PROFB(0);
             float dh[IT];
             if (n > 0) {
                 // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]  ->  staged per owner CTA
                 uint8_t* ps = p_s + (n & 1) * r_bytes;
                 mbar_wait(bar_mma, (n - 1) & 1);
+                PROFB(2);
                 tc_fence_after();
                 for (int m = 0; m < MT; ++m) {
                     const uint32_t dest = m * 4 + q;  // units m*128 + q*32 + lane  ->  CTA dest, local unit = lane
@@ -515,11 +504,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 tc_fence_before();
                 fence_async_smem();
                 bar_arrive_named(2, 160);                 // the MMA/control warp pushes the staged partials
+                PROFB(3);
                 mbar_wait(r_full + 8 * (n & 1), ((n - 1) >> 1) & 1);       // every CTA's partials for my units have landed
+                PROFB(4);
                 if (tid == 0 && n + 2 < T) mbar_expect_tx(r_full + 8 * (n & 1), NC * BLK);   // re-arm for step n+2
                 const uint8_t* rb = r_s + (n & 1) * r_bytes + (size_t)lane * (NB * 2) + q * IT * 2;
 #pragma unroll
-                for (int i = 0; i < IT; ++i) dh[i] = sv[i][6];
+                for (int i = 0; i < IT; ++i) dh[i] = 0.f;
+#pragma unroll 4
                 for (uint32_t c = 0; c < NC; ++c) {
                     const uint8_t* rp = rb + (size_t)c * BLK;
                     if (IT == 4) {
@@ -533,14 +525,19 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < IT; ++i) dh[i] = sv[i][6];
+                for (int i = 0; i < IT; ++i) dh[i] = 0.f;
             }
+            PROFB(5);
+            mbar_wait(sv_full + 8 * (n % 3), (n / 3) & 1);    // staged three steps ago by the writer warps (cp.async)
+            const float* svb = svs + (n % 3) * (7 * NB * 32) + (q * IT) * 32 + lane;
             // gate derivatives; dz -> fp32 staging (writers) and bf16 operand of the next step's MMA
             float* dzb = dzs + (n & 1) * (128 * ZP);
 #pragma unroll
             for (int i = 0; i < IT; ++i) {
                 const int b = q * IT + i;
-                const float gi = sv[i][0], gj = sv[i][1], gf = sv[i][2], go = sv[i][3], c = sv[i][4], cprev = sv[i][5];
+                const float gi = svb[(0 * NB + i) * 32], gj = svb[(1 * NB + i) * 32], gf = svb[(2 * NB + i) * 32], go = svb[(3 * NB + i) * 32];
+                const float c = svb[(4 * NB + i) * 32], cprev = svb[(5 * NB + i) * 32];
+                dh[i] += svb[(6 * NB + i) * 32];
                 const float tc_ = tanh_fast(c);
                 const float dc = dcc[i] + dh[i] * go * (1.f - tc_ * tc_);
                 float dz[4];
@@ -557,14 +554,18 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                         __float2bfloat16_rn(dz[g4]);
                 }
             }
+            PROFB(6);
             fence_async_smem();
             bar_sync_named(1, 288);                   // dz staged: MMA warp may issue, writers may store
+            PROFB(7);
         }
     } else if (warp == 4) {
         // =========================== MMA issuer (converged loop, elected lane) ===========================
         const bool leader = elect_one();
+        long long* prof0 = (blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
         for (int n = 0; n < T; ++n) {
             if (n > 0) {
+                PROFB(9);
                 tc_fence_after();
                 const uint32_t zaddr = smem_u32(z_s);
                 for (int kk = 0; kk < 8; ++kk)
@@ -573,12 +574,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                         if (leader) mma_bf16_ts(tmem + m * NB, tmem + BW_ACOL + m * 64 + kk * 8, bd, idesc, kk > 0);
                     }
                 if (leader) mma_commit(bar_mma);
+                PROFB(10);
                 bar_sync_named(2, 160);                   // partial sums of this step are staged in p_s[n&1]
                 if ((uint32_t)lane < NC) {                // one bulk copy per lane
                     const uint32_t dst = smem_u32(r_s + (n & 1) * r_bytes) + crank * BLK;
                     const uint32_t bar = r_full + 8 * (n & 1);
                     bulk_s2c(mapa(dst, lane), smem_u32(p_s + (n & 1) * r_bytes) + lane * BLK, BLK, mapa(bar, lane));
                 }
+                PROFB(11);
             }
             __syncwarp();
             bar_sync_named(1, 288);
@@ -586,9 +589,49 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
     } else {
         // =========================== writer warps: dZ -> global ===========================
         const int wt = tid - 160, wq = wt >> 5, wu = u0 + (wt & 31);
+        // saved activations of step n (time s = T-1-n): rows k = gi gj gf go c c_prev dy, 32 units each (128 B per mixture):
+        // 16-byte loads, thread = (4 consecutive units, mixture rows rb, rb+16, ...), issued two steps ahead
+        const int u4 = (wt & 7) * 4, rb = wt >> 3;
+        const bool vec = (H & 3) == 0 && u0 + u4 + 4 <= H;
+        auto row_ptr = [&](int k, int s, int b) -> const float* {
+            const int t = d == 0 ? s : T - 1 - s;
+            const int tprev = d == 0 ? t - 1 : t + 1;
+            const size_t row = ((size_t)d * T + t) * B + b0 + b;
+            if (k < 4) return p.gates + row * H4 + k * H + u0 + u4;
+            if (k == 4) return p.cst + row * H + u0 + u4;
+            if (k == 5) return p.cst + (((size_t)d * T + tprev) * B + b0 + b) * H + u0 + u4;
+            return p.dy + ((size_t)t * B + b0 + b) * 2 * H + d * H + u0 + u4;
+        };
+        // asynchronous global -> shared copies (no registers, the writer never waits for them); completion arrives on
+        // sv_full[slot].  Invalid rows / units are zero-filled (src-size 0).
+        auto stage_sv = [&](int n) {
+            const int s = T - 1 - n;
+            const uint32_t sb = smem_u32(svs + (n % 3) * (7 * NB * 32));
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+#pragma unroll
+                for (int rr = 0; rr < NB / 16; ++rr) {
+                    const int b = rr * 16 + rb;
+                    const bool ok = b < nvalid && !(k == 5 && s == 0);
+                    const float* gi = ok ? row_ptr(k, s, b) : p.cst;
+                    const uint32_t dst = sb + ((k * NB + b) * 32 + u4) * 4;
+                    if (vec) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gi), "r"(ok ? 16u : 0u) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool okj = ok && u0 + u4 + j < H;
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * j), "l"(okj ? gi + j : p.cst), "r"(okj ? 4u : 0u) : "memory");
+                        }
+                    }
+                }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sv_full + 8 * (n % 3)) : "memory");
+        };
+        for (int n = 0; n < 3 && n < T; ++n) stage_sv(n);
         for (int s = T - 1; s >= 0; --s) {
             const int t = d == 0 ? s : T - 1 - s, n = T - 1 - s;
-            bar_sync_named(1, 288);
+            bar_sync_named(1, 288);                               // dz(n) staged; svs[n%3] consumed by the compute warps
+            if (n + 3 < T) stage_sv(n + 3);                       // refill the slot just freed, three steps ahead
             const float* dzb = dzs + (n & 1) * (128 * ZP);
             if (wu < H) {
                 float* zo = p.dZ + (((size_t)d * T + t) * B + b0) * H4 + wq * H + wu;
@@ -611,7 +654,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
 
 template <int NB>
 int launch_bwd(const RecTcBwd& p, int NC, cudaStream_t st) {
-    const size_t smem = (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4;
+    const size_t smem = bwd_smem(NC, NB);
     if (smem > 226 * 1024) { set_error("blstm_rec_bwd_tc: H=%d NB=%d needs %zu B of shared memory", p.H, NB, smem); return AMSS_ERR_UNSUPPORTED; }
     AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (NC > 8) AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -652,7 +695,7 @@ size_t fwd_smem(int NC, int NB) {
     return 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)4 * 128 * (NB + 1) * 4 + (size_t)2 * 2 * NB * 33 * 4;
 }
 size_t bwd_smem(int NC, int NB) {
-    return (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4;
+    return (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)3 * 7 * NB * 32 * 4;
 }
 
 int pick_nb(int B, int maxc, int nb_max) {
@@ -666,7 +709,7 @@ int pick_nb(int B, int maxc, int nb_max) {
 
 }  // namespace
 
-void blstm_tc_set_profile(long long* dev_buf) { g_prof = dev_buf; }
+void blstm_tc_set_profile(long long* dev_buf) { g_prof = dev_buf; g_prof_bwd = dev_buf ? dev_buf + 64 : nullptr; }
 
 bool blstm_rec_tc_supported(int B, int T, int H) {
     (void)B; (void)T;
@@ -693,6 +736,7 @@ int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const floa
                      const float* dy, float* dZ, int B, int T, int H, cudaStream_t st) {
     const int NC = (H + 31) / 32;
     RecTcBwd p;
+    p.prof = g_prof_bwd;
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.dy = dy; p.dZ = dZ;
     p.B = B; p.T = T; p.H = H; p.MT = (NC * 32 + 127) / 128;
     static int maxc_cache[17] = {0};

@@ -140,7 +140,7 @@ int amss_blstm_bwd(const float* x, const float* kernel_fw, const float* kernel_b
                    size_t workspace_bytes, void* stream);
 
 /* Diagnostics only: clock64() stamps of the tensor-core recurrence (CTA 0, steps 100..103, 12
- * slots per step) are written to dev_buf (>= 48 int64) by later amss_blstm_fwd calls; NULL = off. */
+ * slots per step; forward at [0,48), backward at [64,112)) are written to dev_buf (>= 128 int64) by later amss_blstm_fwd calls; NULL = off. */
 int amss_debug_blstm_profile(long long* dev_buf);
 
 /* ------------------------------------------------------------------------------------ *

@@ -21,10 +21,11 @@ for B in (16, 64, 128):
     kf = torch.randn(I + H, 4 * H, device="cuda") * 0.05
     kb = torch.randn(I + H, 4 * H, device="cuda") * 0.05
     bf = torch.zeros(4 * H, device="cuda")
-    buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(128, dtype=torch.int64, device="cuda")
     _lib.call("amss_debug_blstm_profile", buf.data_ptr())
     for _ in range(3):
-        ops.blstm_fwd(x, kf, bf, kb, bf, precision=ops.AMSS_PREC_BF16)
+        y, saved = ops.blstm_fwd(x, kf, bf, kb, bf, precision=ops.AMSS_PREC_BF16)
+        ops.blstm_bwd(x, kf, kb, y, torch.randn_like(y), saved, precision=ops.AMSS_PREC_BF16)
     torch.cuda.synchronize()
     _lib.call("amss_debug_blstm_profile", 0)
     p = buf.cpu().view(-1)[:48].view(4, 12)
@@ -33,4 +34,11 @@ for B in (16, 64, 128):
         row = p[s]
         base = int(row[0])
         print(f" step {100 + s}: total {int(p[s + 1][0]) - base} clk ; " +
+              " ".join(f"[{k}]+{int(row[k]) - base}" for k in range(1, 12)))
+
+    pb = buf.cpu().view(-1)[64:112].view(4, 12)
+    for s in range(1, 3):
+        row = pb[s]
+        base = int(row[0])
+        print(f" bwd step {100 + s}: total {int(pb[s + 1][0]) - base} clk ; " +
               " ".join(f"[{k}]+{int(row[k]) - base}" for k in range(1, 12)))
