@@ -221,3 +221,153 @@ int dpcl_bwd_tc(const float* V, const uint8_t* labels, const float* dloss, const
 }
 
 }  // namespace amss
+
+// =================================================================================================
+// DPCL forward statistics on the tensor cores (AMSS_PREC_BF16):
+//   A_w = sum_p w_p v_p v_p^T  (E x E),   m_s = sum_{p in s} v_p  (E),   w_p = N_{l_p}^{-1/2}
+// as ONE accumulating product  D = X^T [X | Y],  X[p][e] = sqrt(w_p) v[p][e],  Y[p][s] = 1[l_p = s]  (exact in bf16;
+// the per-speaker factor 1/sqrt(w_s) is applied in fp32 by the epilogue, so it carries no systematic rounding):
+// the operand tile (128 points, bf16, MN-major core matrices: a 16-byte unit = 8 consecutive e of one point)
+// serves as BOTH the A operand (M = e, padded to 128 rows that stay zero) and the B operand (N = E + S padded
+// to 16; the label columns live in the padding of the last unit).  A CTA owns one (mixture, chunk) and keeps
+// the accumulator in TMEM across all of its tiles; the partials go to the same buffer the SIMT kernel fills.
+// =================================================================================================
+namespace amss {
+namespace {
+
+struct GtcParams {
+    const float* V;            // [B][TF][E]
+    const uint8_t* labels;     // [B][TF]
+    const float* counts;       // [B][4]
+    float* part;               // [B][chunks][E*E + S*E]
+    int B, E, S, NN, chunks;
+    int64_t TF, ntiles;
+};
+
+constexpr int GG_THREADS = 160;           // warps 0-3 loaders / final epilogue, warp 4 MMA (+TMEM alloc)
+constexpr uint32_t GG_TILE = 16 * 2048;   // 16 point groups x (16 e-groups x 128 B)
+
+__global__ void __launch_bounds__(GG_THREADS, 2) dpcl_gram_tc_kernel(GtcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[5];          // full[2], empty[2], done
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int E = p.E, S = p.S, NN = p.NN;
+    const int b = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
+    const uint32_t full = smem_u32(&bars[0]), empty = full + 16, done = full + 32;
+    if (tid == 0) {
+        mbar_init(full, 128); mbar_init(full + 8, 128); mbar_init(empty, 1); mbar_init(empty + 8, 1); mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), 64);
+    for (uint32_t i = tid * 16; i < 2 * GG_TILE; i += GG_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int64_t t0 = p.ntiles * chunk / p.chunks, t1 = p.ntiles * (chunk + 1) / p.chunks;
+    const int egn = (E + S + 7) / 8;                   // 16-byte units per point that carry data
+
+    if (warp < 4) {
+        float wS[4], iwS[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float n = p.counts[b * 4 + s];
+            wS[s] = n > 0.f ? rsqrtf(sqrtf(n)) : 0.f;       // sqrt(w) = N^{-1/4}
+            iwS[s] = n > 0.f ? sqrtf(sqrtf(n)) : 0.f;       // 1 / sqrt(w)
+        }
+        uint32_t i = 0;
+        for (int64_t tile = t0; tile < t1; ++tile, ++i) {
+            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            const int64_t pt = tile * 128 + tid;
+            const bool ok = pt < p.TF;
+            const int l = ok ? p.labels[(size_t)b * p.TF + pt] : 0;
+            const float sw = ok ? (l == 0 ? wS[0] : (l == 1 ? wS[1] : (l == 2 ? wS[2] : wS[3]))) : 0.f;
+            const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + pt) * E);
+            mbar_wait(empty + 8 * buf, ph ^ 1);
+            uint8_t* tb = smem + buf * GG_TILE + (size_t)(tid >> 3) * 2048 + (tid & 7) * 16;
+            for (int eg = 0; eg < egn; ++eg) {
+                float v[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e0 = eg * 8 + h * 4;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && e0 + 4 <= E) x = __ldcs(src + (e0 >> 2));
+                    v[h * 4 + 0] = x.x * sw; v[h * 4 + 1] = x.y * sw; v[h * 4 + 2] = x.z * sw; v[h * 4 + 3] = x.w * sw;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = eg * 8 + j;
+                    if (e >= E && e < E + S) v[j] = (ok && l == e - E) ? 1.f : 0.f;    // the one-hot label columns
+                }
+                *reinterpret_cast<uint4*>(tb + eg * 128) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+            fence_async_smem();
+            mbar_arrive(full + 8 * buf);
+        }
+        // ---- final epilogue: D[e][e'] (lanes = e) -> partial Gram + per-speaker sums ----
+        if (t1 > t0) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+        }
+        float* dst = p.part + ((size_t)b * p.chunks + chunk) * ((size_t)E * E + (size_t)S * E);
+        const int e = warp * 32 + lane;
+        for (int c0 = 0; c0 < NN; c0 += 16) {
+            uint32_t v[16];
+            if (t1 > t0) { tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v); tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0u;
+            }
+            if (e < E) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + j;
+                    if (c < E) dst[e * E + c] = __uint_as_float(v[j]);
+                    else if (c < E + S) dst[E * E + (c - E) * E + e] = __uint_as_float(v[j]) * iwS[(c - E) & 3];
+                }
+            }
+        }
+    } else {
+        const uint32_t idesc = idesc_bf16(128, NN, 1, 1);      // both operands MN-major
+        const bool leader = elect_one();
+        uint32_t i = 0;
+        for (int64_t tile = t0; tile < t1; ++tile, ++i) {
+            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            mbar_wait(full + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t ta = smem_u32(smem + buf * GG_TILE);
+            for (int kk = 0; kk < 8; ++kk) {                   // 128 points = 8 K steps of 16
+                const uint64_t d = smem_desc(ta + kk * 2 * 2048, 2048, 128);
+                if (leader) mma_bf16(tmem, d, d, idesc, (i | kk) != 0);
+            }
+            if (leader) mma_commit(empty + 8 * buf);
+        }
+        if (leader && t1 > t0) mma_commit(done);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 64);
+}
+
+}  // namespace
+
+bool dpcl_gram_tc_supported(int E, int S) { return E % 4 == 0 && E >= 8 && E + S <= 64 && S >= 1 && S <= 4; }
+int dpcl_gram_tc_chunks(int B) { return std::max(1, (2 * kNumSMs) / std::max(1, B)); }
+
+int dpcl_gram_tc(const float* V, const uint8_t* labels, const float* counts, int B, int64_t TF, int E, int S, int chunks,
+                 float* part, cudaStream_t st) {
+    GtcParams p;
+    p.V = V; p.labels = labels; p.counts = counts; p.part = part; p.B = B; p.E = E; p.S = S; p.TF = TF;
+    p.NN = (E + S + 15) / 16 * 16;
+    p.chunks = chunks;
+    p.ntiles = (TF + 127) / 128;
+    const size_t smem = 2 * (size_t)GG_TILE;
+    AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AMSS_LAUNCH(dpcl_gram_tc_kernel, B * chunks, GG_THREADS, smem, st, p);
+    return AMSS_OK;
+}
+
+}  // namespace amss

@@ -556,8 +556,15 @@ extern "C" size_t amss_dpcl_workspace_bytes(int B, int64_t TF, int E, int S) {
            align_up((size_t)B * ls_chunks(B, TF, LS_PT) * stride * 4, 256);
 }
 
-extern "C" int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S, float* loss,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+namespace amss {
+bool dpcl_gram_tc_supported(int E, int S);
+int dpcl_gram_tc_chunks(int B);
+int dpcl_gram_tc(const float* V, const uint8_t* labels, const float* counts, int B, int64_t TF, int E, int S, int chunks,
+                 float* part, cudaStream_t st);
+}  // namespace amss
+
+static int dpcl_fwd_impl(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S, int precision, float* loss,
+                         void* workspace, size_t workspace_bytes, void* stream) {
     AMSS_REQUIRE(V && labels && loss && workspace, "dpcl_loss_fwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_fwd: S=%d outside [1,%d]", S, LS_MAXS);
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_fwd: E=%d outside [1,64]", E);
@@ -566,17 +573,35 @@ extern "C" int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, 
     float* stats = (float*)workspace;
     float* counts = (float*)((char*)workspace + align_up((size_t)B * sstride * 4, 256));
     float* part = (float*)((char*)counts + align_up((size_t)B * LS_MAXS * 4, 256));
-    const int chunks = ls_chunks(B, TF, LS_PT);
-    const int EP = (E + 3) & ~3, nb = EP / 4, nt = nb * (nb + 1) / 2;
-    size_t smem1 = (size_t)LS_PT * EP * 4 + LS_PT * 4 + LS_PT;
-    smem1 = std::max(smem1, ((size_t)8 * nt * 16 + (size_t)4 * LS_MAXS * EP) * 4);
     AMSS_LAUNCH(dpcl_count_kernel, B, 256, 0, stream, labels, TF, S, counts);
-    AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    dim3 grid(chunks, B);
-    AMSS_LAUNCH(dpcl_gram_kernel, grid, LS_THREADS, smem1, stream, V, labels, counts, TF, E, S, part);
+    int chunks = ls_chunks(B, TF, LS_PT);
+    const bool tc = precision == AMSS_PREC_BF16 && dpcl_gram_tc_supported(E, S) && (reinterpret_cast<uintptr_t>(V) & 15) == 0;
+    if (tc) {
+        chunks = std::min(chunks, dpcl_gram_tc_chunks(B));
+        int rc = dpcl_gram_tc(V, labels, counts, B, TF, E, S, chunks, part, (cudaStream_t)stream);
+        if (rc != AMSS_OK) return rc;
+    } else {
+        const int EP = (E + 3) & ~3, nb = EP / 4, nt = nb * (nb + 1) / 2;
+        size_t smem1 = (size_t)LS_PT * EP * 4 + LS_PT * 4 + LS_PT;
+        smem1 = std::max(smem1, ((size_t)8 * nt * 16 + (size_t)4 * LS_MAXS * EP) * 4);
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        dim3 grid(chunks, B);
+        AMSS_LAUNCH(dpcl_gram_kernel, grid, LS_THREADS, smem1, stream, V, labels, counts, TF, E, S, part);
+    }
     AMSS_LAUNCH(dpcl_finalize_kernel, B, 256, 0, stream, part, counts, chunks, E, S, stats);
     AMSS_LAUNCH(mean_of_stat_kernel, 1, 32, 0, stream, stats, B, sstride, sstride - 1, loss);
     return AMSS_OK;
+}
+
+extern "C" int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S, float* loss,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    return dpcl_fwd_impl(V, labels, B, TF, E, S, AMSS_PREC_FP32, loss, workspace, workspace_bytes, stream);
+}
+
+extern "C" int amss_dpcl_loss_fwd_prec(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S,
+                                       int precision, float* loss, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    return dpcl_fwd_impl(V, labels, B, TF, E, S, precision, loss, workspace, workspace_bytes, stream);
 }
 
 namespace {

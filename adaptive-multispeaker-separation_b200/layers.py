@@ -177,8 +177,8 @@ class _L2NormFn(torch.autograd.Function):
 
 class _DPCLLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, V, labels, S):
-        loss, ws = ops.dpcl_loss_fwd(V, labels, S)
+    def forward(ctx, V, labels, S, precision):
+        loss, ws = ops.dpcl_loss_fwd(V, labels, S, precision)
         ctx.save_for_backward(V, labels, ws)
         ctx.S = S
         return loss.view(())
@@ -186,7 +186,7 @@ class _DPCLLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         V, labels, ws = ctx.saved_tensors
-        return ops.dpcl_loss_bwd(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws), None, None
+        return ops.dpcl_loss_bwd(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws), None, None, None
 
 
 class _NormDPCLLossFn(torch.autograd.Function):
@@ -195,7 +195,7 @@ class _NormDPCLLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, V, inv, labels, S, precision):
-        loss, ws = ops.dpcl_loss_fwd(V, labels, S)
+        loss, ws = ops.dpcl_loss_fwd(V, labels, S, precision)
         ctx.save_for_backward(V, inv, labels, ws)
         ctx.S, ctx.zshape, ctx.precision = S, z.shape, precision
         return loss.view(())
@@ -312,7 +312,7 @@ def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32):
     if prenorm is not None:
         z, inv = prenorm
         return _NormDPCLLossFn.apply(z, V.detach(), inv, labels, S, precision)
-    return _DPCLLossFn.apply(V, labels, S)
+    return _DPCLLossFn.apply(V.contiguous(), labels, S, precision)
 
 
 def l41_loss(emb, labels, spk):

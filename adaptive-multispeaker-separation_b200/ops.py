@@ -242,13 +242,13 @@ def colsum(dZ):
     return out
 
 
-def dpcl_loss_fwd(V, labels, S):
+def dpcl_loss_fwd(V, labels, S, precision=AMSS_PREC_FP32):
     """V[B,TF,E], labels uint8 [B,TF] -> (loss[1], workspace for the backward)."""
     _chk(V, labels)
     B, TF, E = V.shape
     loss = torch.empty(1, dtype=_f32, device=V.device)
     ws = _ws(_lib.query("amss_dpcl_workspace_bytes", B, TF, E, S), V.device)
-    _lib.call("amss_dpcl_loss_fwd", _p(V), _p(labels), B, TF, E, S, _p(loss), _p(ws), ws.numel(), _stream())
+    _lib.call("amss_dpcl_loss_fwd_prec", _p(V), _p(labels), B, TF, E, S, precision, _p(loss), _p(ws), ws.numel(), _stream())
     return loss, ws
 
 

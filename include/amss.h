@@ -178,6 +178,10 @@ size_t amss_dpcl_workspace_bytes(int B, int64_t TF, int E, int S);
 int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, int64_t TF, int E,
                        int S, float* loss, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* Same with a precision selector: AMSS_PREC_BF16 accumulates the Gram statistics on tcgen05.   */
+int amss_dpcl_loss_fwd_prec(const float* V, const uint8_t* labels, int B, int64_t TF, int E,
+                            int S, int precision, float* loss, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* dV[B,TF,E] = dloss * d(loss)/dV, using the workspace filled by the forward call.      */
 int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const float* dloss, int B,
                        int64_t TF, int E, int S, float* dV, const void* workspace,

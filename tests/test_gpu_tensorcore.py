@@ -242,9 +242,12 @@ def test_dpcl_fused_backward_tc_matches_autograd(ops, B, TF, E, S):
     labd = dev(lab.to(torch.uint8))
     Vg, inv = ops.l2norm_fwd(zf, E)
     loss, ws = ops.dpcl_loss_fwd(Vg, labd, S)
+    loss16, ws16 = ops.dpcl_loss_fwd(Vg, labd, S, ops.AMSS_PREC_BF16)      # Gram statistics on tcgen05
+    assert abs(float(loss) - float(cost)) < 1e-3 * abs(float(cost))
+    assert abs(float(loss16) - float(cost)) < 3e-3 * abs(float(cost)), (float(loss16), float(cost))
     one = torch.ones(1, device="cuda")
     dz32 = ops.dpcl_loss_bwd_normalized(Vg, labd, S, one, ws, inv, ops.AMSS_PREC_FP32)
-    dz16 = ops.dpcl_loss_bwd_normalized(Vg, labd, S, one, ws, inv, ops.AMSS_PREC_BF16)
+    dz16 = ops.dpcl_loss_bwd_normalized(Vg, labd, S, one, ws16, inv, ops.AMSS_PREC_BF16)
     # the clamped row has inv_norm = 1e6 and would dominate a max-norm comparison: check it on its own
     keep = torch.ones(B, TF, dtype=torch.bool)
     keep[0, 3] = False

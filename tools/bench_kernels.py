@@ -91,6 +91,7 @@ def bench_dpcl(B):
     loss, ws = ops.dpcl_loss_fwd(V, lab, 2)
     dV = ops.dpcl_loss_bwd(V, lab, 2, one, ws)
     for name, fn, passes in (("l2norm_fwd", lambda: ops.l2norm_fwd(z, E), 2), ("dpcl_loss_fwd", lambda: ops.dpcl_loss_fwd(V, lab, 2), 1),
+                             ("dpcl_loss_fwd tc", lambda: ops.dpcl_loss_fwd(V, lab, 2, ops.AMSS_PREC_BF16), 1),
                              ("dpcl_loss_bwd", lambda: ops.dpcl_loss_bwd(V, lab, 2, one, ws), 2),
                              ("l2norm_bwd", lambda: ops.l2norm_bwd(V, inv, dV, E), 3),
                              ("dpcl_loss_bwd_normalized", lambda: ops.dpcl_loss_bwd_normalized(V, lab, 2, one, ws, inv), 2),
