@@ -32,6 +32,7 @@ struct DtParams {
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+template <int RV>   // float4 per loader thread and tile held in registers (E/4 <= RV)
 __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[8];
@@ -64,11 +65,25 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
     if (warp < 4) {
         // ---------------- loaders: V tile -> fp32 rows + bf16 A operand; An/Bn when the mixture changes ----------------
         int bcur = -1;
-        uint32_t i = 0;
-        for (int64_t w = w0; w < w1; ++w, ++i) {
+        const int e4 = E / 4;
+        // software pipeline: tile i+1 is fetched into registers (coalesced float4, unit u = tid + 128 j) before tile i is
+        // handed to the MMA, so the HBM latency overlaps the previous tile's conversion / MMAs / epilogue
+        float4 tilev[RV];
+        auto fetch = [&](int64_t w) {
             const int b = (int)(w / p.ntiles);
             const int64_t p0 = (w - (int64_t)b * p.ntiles) * 128;
             const int np = (int)min((int64_t)128, p.TF - p0);
+            const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + p0) * E);
+#pragma unroll
+            for (int j = 0; j < RV; ++j) {
+                const int u = tid + 128 * j;
+                tilev[j] = (j < e4 && u < np * e4) ? __ldcs(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (w0 < w1) fetch(w0);
+        uint32_t i = 0;
+        for (int64_t w = w0; w < w1; ++w, ++i) {
+            const int b = (int)(w / p.ntiles);
             const uint32_t buf = i & 1, ph = (i >> 1) & 1;
             mbar_wait(t_empty + 8 * buf, ph ^ 1);          // the epilogue of tile i-2 has finished with vs[buf] / TMEM[buf]
             mbar_wait(a_empty + 8 * buf, ph ^ 1);          // the MMAs of tile i-2 have finished with a_s[buf]
@@ -89,12 +104,14 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
                 bcur = b;
             }
             float* vb = vs + (size_t)buf * 128 * pitch;
-            const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + p0) * E);
-            const int e4 = E / 4;
-            for (int u = tid; u < 128 * e4; u += 128) {
-                const int r = u / e4, c = u - r * e4;
-                *reinterpret_cast<float4*>(vb + r * pitch + c * 4) = r < np ? __ldcs(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < RV; ++j) {
+                if (j < e4) {
+                    const int u = tid + 128 * j, r = u / e4, c = u - r * e4;
+                    *reinterpret_cast<float4*>(vb + r * pitch + c * 4) = tilev[j];
+                }
             }
+            if (w + 1 < w1) fetch(w + 1);
             named_sync(1, 128);
             uint8_t* ab = a_s + buf * a_bytes;
             const float* row = vb + tid * pitch;
@@ -215,8 +232,13 @@ int dpcl_bwd_tc(const float* V, const uint8_t* labels, const float* dloss, const
     p.per = (total + grid - 1) / grid;
     const size_t smem = (size_t)2 * 128 * p.pitch * 4 + 2 * (size_t)(p.EK / 8) * 16 * 128 + 2 * (size_t)(p.EK / 8) * (p.EK / 8) * 128 +
                         2 * (size_t)(S * E + S) * 4 + 64;
-    AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AMSS_LAUNCH(dpcl_bwd_tc_kernel, grid, DT_THREADS, smem, st, p);
+    if (E <= 40) {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(dpcl_bwd_tc_kernel<10>, grid, DT_THREADS, smem, st, p);
+    } else {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(dpcl_bwd_tc_kernel<16>, grid, DT_THREADS, smem, st, p);
+    }
     return AMSS_OK;
 }
 
@@ -247,7 +269,8 @@ struct GtcParams {
 constexpr int GG_THREADS = 160;           // warps 0-3 loaders / final epilogue, warp 4 MMA (+TMEM alloc)
 constexpr uint32_t GG_TILE = 16 * 2048;   // 16 point groups x (16 e-groups x 128 B)
 
-__global__ void __launch_bounds__(GG_THREADS, 2) dpcl_gram_tc_kernel(GtcParams p) {
+template <int RV>   // float4 per embedding row held in registers (E <= 4*RV)
+__global__ void __launch_bounds__(GG_THREADS, 3) dpcl_gram_tc_kernel(GtcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[5];          // full[2], empty[2], done
     __shared__ uint32_t tmem_base_s;
@@ -277,32 +300,46 @@ __global__ void __launch_bounds__(GG_THREADS, 2) dpcl_gram_tc_kernel(GtcParams p
             wS[s] = n > 0.f ? rsqrtf(sqrtf(n)) : 0.f;       // sqrt(w) = N^{-1/4}
             iwS[s] = n > 0.f ? sqrtf(sqrtf(n)) : 0.f;       // 1 / sqrt(w)
         }
+        // software pipeline: the row (and label) of tile i+1 is loaded into registers before tile i is converted,
+        // so the HBM latency overlaps the shared-memory stores / MMAs of the previous tile
+        float4 rowv[RV];
+        int lnext = 0;
+        bool oknext = false;
+        auto fetch = [&](int64_t tile) {
+            const int64_t pt = tile * 128 + tid;
+            oknext = pt < p.TF;
+            lnext = oknext ? p.labels[(size_t)b * p.TF + pt] : 0;
+            const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + pt) * E);
+#pragma unroll
+            for (int c = 0; c < RV; ++c) rowv[c] = (oknext && c * 4 + 4 <= E) ? __ldcs(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if (t0 < t1) fetch(t0);
         uint32_t i = 0;
         for (int64_t tile = t0; tile < t1; ++tile, ++i) {
             const uint32_t buf = i & 1, ph = (i >> 1) & 1;
-            const int64_t pt = tile * 128 + tid;
-            const bool ok = pt < p.TF;
-            const int l = ok ? p.labels[(size_t)b * p.TF + pt] : 0;
+            const bool ok = oknext;
+            const int l = lnext;
             const float sw = ok ? (l == 0 ? wS[0] : (l == 1 ? wS[1] : (l == 2 ? wS[2] : wS[3]))) : 0.f;
-            const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + pt) * E);
+            float4 cur[RV];
+#pragma unroll
+            for (int c = 0; c < RV; ++c) cur[c] = rowv[c];
+            if (tile + 1 < t1) fetch(tile + 1);
             mbar_wait(empty + 8 * buf, ph ^ 1);
             uint8_t* tb = smem + buf * GG_TILE + (size_t)(tid >> 3) * 2048 + (tid & 7) * 16;
-            for (int eg = 0; eg < egn; ++eg) {
-                float v[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int e0 = eg * 8 + h * 4;
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && e0 + 4 <= E) x = __ldcs(src + (e0 >> 2));
-                    v[h * 4 + 0] = x.x * sw; v[h * 4 + 1] = x.y * sw; v[h * 4 + 2] = x.z * sw; v[h * 4 + 3] = x.w * sw;
-                }
+            for (int eg = 0; eg < (RV + 2) / 2; ++eg) {
+                if (eg < egn) {
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 x0 = 2 * eg < RV ? cur[2 * eg < RV ? 2 * eg : 0] : z4, x1 = 2 * eg + 1 < RV ? cur[2 * eg + 1 < RV ? 2 * eg + 1 : 0] : z4;
+                    float v[8] = {x0.x * sw, x0.y * sw, x0.z * sw, x0.w * sw, x1.x * sw, x1.y * sw, x1.z * sw, x1.w * sw};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int e = eg * 8 + j;
-                    if (e >= E && e < E + S) v[j] = (ok && l == e - E) ? 1.f : 0.f;    // the one-hot label columns
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = eg * 8 + j;
+                        if (e >= E && e < E + S) v[j] = (ok && l == e - E) ? 1.f : 0.f;    // the one-hot label columns
+                    }
+                    *reinterpret_cast<uint4*>(tb + eg * 128) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 }
-                *reinterpret_cast<uint4*>(tb + eg * 128) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             }
             fence_async_smem();
             mbar_arrive(full + 8 * buf);
@@ -355,7 +392,7 @@ __global__ void __launch_bounds__(GG_THREADS, 2) dpcl_gram_tc_kernel(GtcParams p
 }  // namespace
 
 bool dpcl_gram_tc_supported(int E, int S) { return E % 4 == 0 && E >= 8 && E + S <= 64 && S >= 1 && S <= 4; }
-int dpcl_gram_tc_chunks(int B) { return std::max(1, (2 * kNumSMs) / std::max(1, B)); }
+int dpcl_gram_tc_chunks(int B) { return std::max(1, (3 * kNumSMs) / std::max(1, B)); }
 
 int dpcl_gram_tc(const float* V, const uint8_t* labels, const float* counts, int B, int64_t TF, int E, int S, int chunks,
                  float* part, cudaStream_t st) {
@@ -365,8 +402,13 @@ int dpcl_gram_tc(const float* V, const uint8_t* labels, const float* counts, int
     p.chunks = chunks;
     p.ntiles = (TF + 127) / 128;
     const size_t smem = 2 * (size_t)GG_TILE;
-    AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AMSS_LAUNCH(dpcl_gram_tc_kernel, B * chunks, GG_THREADS, smem, st, p);
+    if (E <= 40) {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(dpcl_gram_tc_kernel<10>, B * chunks, GG_THREADS, smem, st, p);
+    } else {
+        AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH(dpcl_gram_tc_kernel<16>, B * chunks, GG_THREADS, smem, st, p);
+    }
     return AMSS_OK;
 }
 
