@@ -303,7 +303,8 @@ extern "C" int amss_filterbank_analysis_fwd(const float* x, const float* filt, i
         int out, pl;
         same_pad(L, W, hop, &out, &pl);
         dim3 grid(Tp, Bt);
-        AMSS_LAUNCH(analysis_stride_kernel, grid, 256, (size_t)W * 4, st, x, filt, L, W, N, hop, Tp, pl, y);
+        AMSS_LAUNCH(analysis_stride_kernel, grid, 256, align_up((size_t)W * 4, 16), st,   // ptxas widens the tail reads to LDS.128
+                    x, filt, L, W, N, hop, Tp, pl, y);
         return AMSS_OK;
     }
     AMSS_REQUIRE(pool > 0, "filterbank_analysis_fwd: pool must be positive");
