@@ -1,20 +1,22 @@
-// Dense GEMM on the 5th-gen tensor cores: C[M,N] (+)= op(A) op(B) (+ bias), fp32 in / fp32 out,
-// bf16 operands, fp32 accumulation in TMEM.  Used (AMSS_PREC_BF16) for the hoisted BLSTM input
-// projections, the embedding head (utils/ops.py:501-503) and every backward GEMM of those.
+// Dense GEMM on the 5th-gen tensor cores: C[M,N] (+)= op(A) op(B) (+ bias), bf16 operands, fp32 accumulation in
+// TMEM, fp32 out.  Used (AMSS_PREC_BF16) for the hoisted BLSTM input projections, the embedding head
+// (utils/ops.py:501-503) and every backward GEMM of those.
 //
-//   1. pack: each operand is converted once to bf16 AND laid out as the exact shared-memory image the
-//      MMA wants -- K-major core matrices, tiles of RT rows x 64 k stored contiguously (A: RT = 128,
-//      16 KB; B: RT = 256, 32 KB), zero padded.  Transposed operands (dW = X^T dZ, dX = dZ W^T) are
-//      transposed by the pack kernel's addressing (coalesced reads either way), so the GEMM kernel
-//      only ever sees K-major x K-major;
-//   2. persistent CTAs (one per SM) walk (tile, k-split) work items; ONE thread feeds a 4-stage
-//      mbarrier ring with two cp.async.bulk (TMA engine) copies per stage (48 KB), i.e. ~190 KB of
-//      loads in flight per SM and no per-element load instructions at all;
-//   3. one warp issues tcgen05.mma 128x256x16 (converged loop, elected lane);
-//   4. TMEM accumulators are double buffered (2 x 256 columns): 4 epilogue warps drain tile i
-//      (bias, row remap, accumulate / split-K red.global.add) while tile i+1 is being multiplied.
+//   1. operands are plain ROW-MAJOR bf16 matrices (fp32 sources are converted once by convert_bf16_kernel; producers
+//      that already hold bf16 call gemm_bf16 directly).  Each operand is either K-major (X[r][k] = src[r*ld + k]) or
+//      MN-major (X[r][k] = src[k*ld + r]) -- the transposed GEMMs of the backward pass (dW = X^T dZ, dX = dZ W^T) need
+//      no transpose pass, the UMMA descriptors read both majors;
+//   2. TMA tensor maps (cuTensorMapEncodeTiled, SWIZZLE_128B) move 64-wide boxes global -> shared: K-major one box
+//      {64 k, 128|256 rows}, MN-major boxes {64 mn, 64 k}; out-of-range rows / k are zero filled by the TMA unit, so
+//      ragged M, N, K need no padding.  Descriptor fields pinned by tools/tma_probe.cu;
+//   3. persistent CTAs (one per SM) walk (tile, k-split) work items; ONE thread feeds a 4-stage mbarrier ring
+//      (48 KB per stage, ~190 KB of loads in flight per SM, no per-element load instructions);
+//   4. one warp issues tcgen05.mma 128x256x16 (converged loop, elected lane);
+//   5. TMEM accumulators are double buffered (2 x 256 columns): 4 epilogue warps drain tile i (bias, row remap,
+//      accumulate / split-K red.global.add) while tile i+1 is being multiplied.
 #include "common.cuh"
 #include "tc.cuh"
+#include <cuda.h>
 #include <algorithm>
 
 namespace amss {
@@ -26,57 +28,46 @@ constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 64, GT_STAGES = 4;
 constexpr int GT_THREADS = 192;                      // warp 0 loader, 1 MMA (+TMEM alloc), 2-5 epilogue
 constexpr int GT_A_BYTES = GT_BM * GT_BK * 2, GT_B_BYTES = GT_BN * GT_BK * 2;
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
+constexpr int GT_SMEM = GT_STAGES * GT_STAGE_BYTES + 1024;   // + slack to align the ring to the 1024-B swizzle atom
 
 struct GtParams {
-    const uint8_t *A, *B;             // packed bf16 tiles: A [tm][KS][16 KB], B [tn][KS][32 KB]
+    CUtensorMap mapA, mapB;
     const float* bias;
     float* C;
-    int ldc, M, N, K, KS, accumulate, swapB, swapT;
+    int ldc, M, N, K, KS, accumulate, swapB, swapT, a_mn, b_mn;
     int tm, tn, ksplit, sper;         // tiles, k-splits, stages per split
 };
 
-// src fp32 -> packed bf16 tiles.  Logical operand X[r][k], r < R, k < K: kcontig: X[r][k] = src[r*ld + k],
-// otherwise X[r][k] = src[k*ld + r].  16-byte unit (r, k8 = k/8) of tile (r/RT, k/64) goes to
-//   ((r/RT)*KS + k/64) * RT*128  +  ((k8 % 8) * (RT/8) + (r % RT)/8) * 128  +  (r % 8) * 16.
-// Consecutive threads take consecutive r of one k8: 16-byte writes are contiguous in groups of 8 rows,
-// reads are 32-byte runs (kcontig) or 4-byte elements coalesced across the warp (transposed source).
-template <int RT>
-__global__ void pack_bf16_kernel(const float* __restrict__ src, int R, int K, int ld, int kcontig, int KS, int rtiles,
-                                 uint4* __restrict__ dst) {
-    const int64_t rp = (int64_t)rtiles * RT;                      // padded rows
-    const int64_t units = rp * KS * 8;
+// fp32 [rows, cols] (ld) -> bf16 [rows, ldd] (ldd % 8 == 0, zero padded): one 16-byte store per thread
+__global__ void convert_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld, int ldd, uint4* __restrict__ dst) {
+    const int upr = ldd >> 3;
+    const int64_t units = (int64_t)rows * upr;
     const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = u % rp;
-        const int k8 = (int)(u / rp);                              // 0 .. KS*8-1
-        const int k0 = k8 * 8;
+        const int64_t r = u / upr;
+        const int c0 = (int)(u % upr) * 8;
+        const float* s = src + r * ld + c0;
         float v[8];
-        if (r < R && k0 < K) {
-            if (kcontig) {
-                const float* s = src + r * ld + k0;
-                if (k0 + 8 <= K && vec_ok) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
-                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = k0 + e < K ? __ldg(s + e) : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = k0 + e < K ? __ldg(src + (size_t)(k0 + e) * ld + r) : 0.f;
-            }
+        if (c0 + 8 <= cols && vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            for (int e = 0; e < 8; ++e) v[e] = c0 + e < cols ? __ldg(s + e) : 0.f;
         }
-        const int rt = (int)(r / RT), rl = (int)(r % RT), ks = k8 >> 3, kc = k8 & 7;
-        const size_t off = ((size_t)rt * KS + ks) * (RT * 8) + (size_t)(kc * (RT / 8) + (rl >> 3)) * 8 + (rl & 7);
-        dst[off] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        dst[u] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(GtParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GtParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bars[2 * GT_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -95,28 +86,40 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(GtParams p) {
     const int items = p.tm * p.tn * p.ksplit;
 
     if (warp == 0) {
-        // ---------------- loader: two bulk copies per stage (one lane) ----------------
+        // ---------------- loader: TMA box loads, one lane ----------------
         if (lane == 0) {
             uint32_t g = 0;
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int split = it % p.ksplit, tile = it / p.ksplit;
-                const int nt = tile % p.tn, mt = tile / p.tn;
+                const int n0 = (tile % p.tn) * GT_BN, m0 = (tile / p.tn) * GT_BM;
                 const int sbeg = split * p.sper, send = min(p.KS, sbeg + p.sper);
-                const uint8_t* pa = p.A + ((size_t)mt * p.KS + sbeg) * GT_A_BYTES;
-                const uint8_t* pb = p.B + ((size_t)nt * p.KS + sbeg) * GT_B_BYTES;
-                for (int j = sbeg; j < send; ++j, ++g, pa += GT_A_BYTES, pb += GT_B_BYTES) {
+                for (int j = sbeg; j < send; ++j, ++g) {
                     const uint32_t slot = g % GT_STAGES, ph = (g / GT_STAGES) & 1;
                     mbar_wait(empty + 8 * slot, ph ^ 1);
-                    const uint32_t sa = smem_u32(smem + slot * GT_STAGE_BYTES);
-                    mbar_expect_tx(full + 8 * slot, GT_STAGE_BYTES);
-                    bulk_g2s(sa, pa, GT_A_BYTES, full + 8 * slot);
-                    bulk_g2s(sa + GT_A_BYTES, pb, GT_B_BYTES, full + 8 * slot);
+                    const uint32_t sa = smem_u32(smem + slot * GT_STAGE_BYTES), sb = sa + GT_A_BYTES;
+                    const uint32_t bar = full + 8 * slot;
+                    mbar_expect_tx(bar, GT_STAGE_BYTES);
+                    const int k0 = j * GT_BK;
+                    if (!p.a_mn) tma_load_2d(sa, &p.mapA, k0, m0, bar);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < GT_BM / 64; ++i) tma_load_2d(sa + i * 8192, &p.mapA, m0 + i * 64, k0, bar);
+                    }
+                    if (!p.b_mn) tma_load_2d(sb, &p.mapB, k0, n0, bar);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < GT_BN / 64; ++i) tma_load_2d(sb + i * 8192, &p.mapB, n0 + i * 64, k0, bar);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (converged loop, elected lane) ----------------
-        const uint32_t idesc = idesc_bf16(GT_BM, GT_BN, 0, 0);
+        const uint32_t idesc = idesc_bf16(GT_BM, GT_BN, p.a_mn, p.b_mn);
+        // K-major: 8-row groups 1024 B apart, K step of 16 = +32 B inside the 128-B swizzle row.
+        // MN-major: 8-k groups 1024 B apart (SBO), 64-wide mn atoms 8192 B apart (LBO), K step of 16 = +2048 B.
+        const uint32_t a_step = p.a_mn ? 2048u : 32u, a_lbo = p.a_mn ? 8192u : 16u;
+        const uint32_t b_step = p.b_mn ? 2048u : 32u, b_lbo = p.b_mn ? 8192u : 16u;
         const bool leader = elect_one();
         uint32_t g = 0, ti = 0;
         for (int it = blockIdx.x; it < items; it += gridDim.x, ++ti) {
@@ -133,8 +136,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(GtParams p) {
                 const uint32_t sa = smem_u32(smem + slot * GT_STAGE_BYTES), sb = sa + GT_A_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < GT_BK / 16; ++kk) {
-                    const uint64_t ad = smem_desc(sa + kk * 2 * (GT_BM / 8) * 128, (GT_BM / 8) * 128, 128);
-                    const uint64_t bd = smem_desc(sb + kk * 2 * (GT_BN / 8) * 128, (GT_BN / 8) * 128, 128);
+                    const uint64_t ad = smem_desc_sw128(sa + kk * a_step, a_lbo, 1024);
+                    const uint64_t bd = smem_desc_sw128(sb + kk * b_step, b_lbo, 1024);
                     if (leader) mma_bf16(dcol, ad, bd, idesc, !(j == sbeg && kk == 0));
                 }
                 if (leader) mma_commit(empty + 8 * slot);
@@ -212,9 +215,39 @@ __global__ void zero_rows_kernel(float* C, int M, int N, int ldc) {
         C[(i / N) * ldc + (i % N)] = 0.f;
 }
 
-inline size_t packed_bytes(int R, int K, int RT) {
-    return (size_t)((R + RT - 1) / RT) * ((K + GT_BK - 1) / GT_BK) * RT * 128;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) { cudaGetLastError(); f = nullptr; }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
 }
+
+// Operand X[r][k], r < R, k < K.  K-major: src[r*ld + k], box {64 k, rows_box}; MN-major: src[k*ld + r], box {64 r, 64 k}.
+int make_operand_map(CUtensorMap* m, const uint16_t* src, int R, int K, int ld, int mn, int rows_box) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver"); return AMSS_ERR_CUDA; }
+    cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2], es[2] = {1, 1};
+    if (!mn) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)R; box[0] = GT_BK; box[1] = (cuuint32_t)rows_box; }
+    else { dims[0] = (cuuint64_t)R; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = GT_BK; }
+    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(src), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for R=%d K=%d ld=%d mn=%d", (int)rc, R, K, ld, mn);
+        return AMSS_ERR_CUDA;
+    }
+    return AMSS_OK;
+}
+
+inline int pad8(int x) { return (x + 7) & ~7; }
 
 }  // namespace
 
@@ -223,33 +256,38 @@ bool gemm_tc_supported(int M, int N, int K, int lda, int ldb, int ldc, int trans
     return M >= 1 && N >= 1 && K >= 1;
 }
 
+// bf16 copies of the two fp32 operands (leading dimensions padded to 8 elements = 16 bytes, a TMA requirement)
 size_t gemm_tc_workspace(int M, int N, int K, int transa, int transb, int precision) {
-    (void)precision; (void)transa; (void)transb;
-    return 1024 + align_up(packed_bytes(M, K, GT_BM), 256) + align_up(packed_bytes(N, K, GT_BN), 256);
+    (void)precision;
+    const size_t a = transa ? (size_t)K * pad8(M) : (size_t)M * pad8(K);
+    const size_t b = transb ? (size_t)N * pad8(K) : (size_t)K * pad8(N);
+    return 256 + align_up(a * 2, 256) + align_up(b * 2, 256);
 }
 
-int gemm_tc(const float* A, int lda, const float* B, int ldb, const float* bias, int M, int N, int K, int transa,
-            int transb, int accumulate, int precision, float* C, int ldc, int swapB, int swapT, void* workspace,
-            size_t workspace_bytes, cudaStream_t st) {
-    if (!workspace || workspace_bytes < gemm_tc_workspace(M, N, K, transa, transb, precision)) {
-        set_error("gemm_tc: workspace too small (%zu < %zu)", workspace_bytes, gemm_tc_workspace(M, N, K, transa, transb, precision));
-        return AMSS_ERR_WORKSPACE;
+int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, cudaStream_t st) {
+    const int64_t units = (int64_t)rows * (ldd / 8);
+    AMSS_LAUNCH(convert_bf16_kernel, (int)std::max<int64_t>(1, std::min<int64_t>((units + 255) / 256, 16 * kNumSMs)), 256, 0, st, src,
+                rows, cols, ld, ldd, (uint4*)dst);
+    return AMSS_OK;
+}
+
+// C[M,N] (+)= A B^T-style product of two bf16 row-major operands.  a_mn = 0: A[m][k] = A[m*lda + k]; 1: A[k*lda + m].
+// b_mn = 0: B[n][k] = B[n*ldb + k]; 1: B[k*ldb + n].  lda, ldb multiples of 8, pointers 16-byte aligned.
+int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
+              int K, int accumulate, float* C, int ldc, int swapB, int swapT, cudaStream_t st) {
+    if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) {
+        set_error("gemm_bf16: operands must be 16-byte aligned with leading dimensions that are multiples of 8 (lda=%d ldb=%d)", lda, ldb);
+        return AMSS_ERR_INVALID_ARG;
     }
     GtParams p;
     p.tm = (M + GT_BM - 1) / GT_BM; p.tn = (N + GT_BN - 1) / GT_BN;
     p.KS = (K + GT_BK - 1) / GT_BK;
-    uint8_t* Ap = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
-    uint8_t* Bp = Ap + align_up(packed_bytes(M, K, GT_BM), 256);
-    {
-        // A[m][k]: not transposed -> src[m*lda + k] (K-contiguous); transposed -> src[k*lda + m]
-        const int64_t ua = (int64_t)p.tm * GT_BM * p.KS * 8, ub = (int64_t)p.tn * GT_BN * p.KS * 8;
-        AMSS_LAUNCH((pack_bf16_kernel<GT_BM>), (int)std::min<int64_t>((ua + 255) / 256, 16 * kNumSMs), 256, 0, st, A, M, K, lda,
-                    transa ? 0 : 1, p.KS, p.tm, (uint4*)Ap);
-        // B^T[n][k]: not transposed -> src[k*ldb + n]; transposed -> src[n*ldb + k] (K-contiguous)
-        AMSS_LAUNCH((pack_bf16_kernel<GT_BN>), (int)std::min<int64_t>((ub + 255) / 256, 16 * kNumSMs), 256, 0, st, B, N, K, ldb,
-                    transb ? 1 : 0, p.KS, p.tn, (uint4*)Bp);
-    }
-    p.A = Ap; p.B = Bp; p.bias = bias; p.C = C; p.ldc = ldc;
+    int rc = make_operand_map(&p.mapA, A, M, K, lda, a_mn, GT_BM);
+    if (rc != AMSS_OK) return rc;
+    rc = make_operand_map(&p.mapB, B, N, K, ldb, b_mn, GT_BN);
+    if (rc != AMSS_OK) return rc;
+    p.a_mn = a_mn; p.b_mn = b_mn;
+    p.bias = bias; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.swapB = swapB; p.swapT = swapT;
     const int tiles = p.tm * p.tn;
     int ksplit = 1;
@@ -262,11 +300,29 @@ int gemm_tc(const float* A, int lda, const float* B, int ldb, const float* bias,
         const int64_t n = (int64_t)M * N;
         AMSS_LAUNCH(zero_rows_kernel, (int)std::min<int64_t>((n + 255) / 256, 8 * kNumSMs), 256, 0, st, C, M, N, ldc);
     }
-    const size_t smem = (size_t)GT_STAGES * GT_STAGE_BYTES;
-    AMSS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AMSS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
     const int grid = std::min(tiles * ksplit, kNumSMs);
-    AMSS_LAUNCH(gemm_tc_kernel, grid, GT_THREADS, smem, st, p);
+    AMSS_LAUNCH(gemm_tc_kernel, grid, GT_THREADS, GT_SMEM, st, p);
     return AMSS_OK;
+}
+
+int gemm_tc(const float* A, int lda, const float* B, int ldb, const float* bias, int M, int N, int K, int transa,
+            int transb, int accumulate, int precision, float* C, int ldc, int swapB, int swapT, void* workspace,
+            size_t workspace_bytes, cudaStream_t st) {
+    if (!workspace || workspace_bytes < gemm_tc_workspace(M, N, K, transa, transb, precision)) {
+        set_error("gemm_tc: workspace too small (%zu < %zu)", workspace_bytes, gemm_tc_workspace(M, N, K, transa, transb, precision));
+        return AMSS_ERR_WORKSPACE;
+    }
+    // A: not transposed -> [M,K] K-major; transposed -> source [K,M], MN-major.  B: not transposed -> source [K,N],
+    // MN-major; transposed -> source [N,K], K-major.
+    const int ar = transa ? K : M, ac = transa ? M : K, br = transb ? N : K, bc = transb ? K : N;
+    uint16_t* Ab = (uint16_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    uint16_t* Bb = Ab + align_up((size_t)ar * pad8(ac) * 2, 256) / 2;
+    int rc = convert_bf16(A, ar, ac, lda, Ab, pad8(ac), st);
+    if (rc != AMSS_OK) return rc;
+    rc = convert_bf16(B, br, bc, ldb, Bb, pad8(bc), st);
+    if (rc != AMSS_OK) return rc;
+    return gemm_bf16(Ab, pad8(ac), transa ? 1 : 0, Bb, pad8(bc), transb ? 0 : 1, bias, M, N, K, accumulate, C, ldc, swapB, swapT, st);
 }
 
 }  // namespace amss

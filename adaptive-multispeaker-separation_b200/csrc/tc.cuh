@@ -108,6 +108,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;
     return d;
 }
+// Shared-memory matrix descriptor for SWIZZLE_128B tiles written by TMA (layout type 2; the tile base must be
+// 1024-byte aligned).  K-major: rows are 128 B (64 bf16) long, 8-row groups `sbo` = 1024 B apart, `lbo` unused (16);
+// a K step of 16 advances the start address by 32 B.  MN-major: k rows of 64 mn elements, 8-k groups `sbo` = 1024 B
+// apart, 64-wide mn atoms `lbo` apart; a K step of 16 advances the start address by 2048 B.  (tools/tma_probe.cu)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
+}
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.  a_mn / b_mn: 1 = operand is MN-major.
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |

@@ -130,14 +130,18 @@ class _BLSTMFn(torch.autograd.Function):
 class _DenseFn(torch.autograd.Function):
     """y[M,N] = x[M,K] @ W[K,N] + b   (tf.nn.conv1d with a [1,K,N] filter).
     swap=(B,T): the rows of x are time-major (t*B+b) and the rows of y batch-major (b*T+t) -- the
-    [T,B,*] -> [B,T,*] hand-over between the BLSTM stack and the embedding reshape, done by the
-    GEMM epilogue instead of a transpose pass."""
+    [T,B,*] -> [B,T,*] hand-over between the BLSTM stack and the embedding reshape.  The small [M,K] activation is
+    re-ordered (and kept for dW); re-ordering the wide [M,N] output rows in the GEMM epilogue instead scatters every
+    128-row tile over 128 pages 10 MB apart and runs the head GEMM 3x slower (TLB misses)."""
 
     @staticmethod
     def forward(ctx, x, W, b, precision, swap):
+        if swap:
+            Bq, Tq = swap
+            x = ops.transpose_01(x.view(Tq, Bq, -1)).view(Bq * Tq, -1)
         ctx.save_for_backward(x, W)
         ctx.precision, ctx.swap = precision, swap
-        return ops.gemm(x, W, b, precision=precision, out_swap=swap)
+        return ops.gemm(x, W, b, precision=precision)
 
     @staticmethod
     def backward(ctx, dy):
@@ -146,15 +150,11 @@ class _DenseFn(torch.autograd.Function):
         swap = ctx.swap
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            # rows of dy are batch-major; write dx back in x's (time-major) row order
+            # rows of dy are batch-major; write dx back in the caller's (time-major) row order
             dx = ops.gemm(dy, W, None, transb=True, precision=ctx.precision,
                           out_swap=(swap[1], swap[0]) if swap else None)
         if ctx.needs_input_grad[1]:
-            xr = x
-            if swap:                                # small [T*B,K] activation: bring it to dy's row order
-                Bq, Tq = swap
-                xr = ops.transpose_01(x.view(Tq, Bq, -1)).view(Bq * Tq, -1)
-            dW = ops.gemm(xr, dy, None, transa=True, precision=ctx.precision)
+            dW = ops.gemm(x, dy, None, transa=True, precision=ctx.precision)
         if ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
         return dx, dW, db, None, None
