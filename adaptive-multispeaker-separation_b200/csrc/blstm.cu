@@ -20,6 +20,9 @@ int gemm_dispatch(const float* A, int lda, const float* B, int ldb, const float*
                   size_t workspace_bytes, cudaStream_t st);
 bool blstm_rec_tc_supported(int B, int T, int H);
 void blstm_tc_set_profile(long long* dev_buf);
+int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, cudaStream_t st);
+int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
+              int K, int accumulate, float* C, int ldc, int swapB, int swapT, cudaStream_t st);
 int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gates, float* cst, float* y, int B, int T,
                      int H, float forget_bias, cudaStream_t st);
 int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,
@@ -241,6 +244,27 @@ struct BlstmWs {
     size_t gemm_ws_bytes, total;
 };
 
+// bf16 operand copies for the tensor-core GEMMs (leading dimensions padded to 8 elements for TMA), carved out of the
+// GEMM scratch after the column-sum partials: x [TB,Ip], y per direction [2][TB,Hp], dZ [2*TB,H4p], W_x [2][I,H4p].
+inline int pad8i(int x) { return (x + 7) & ~7; }
+struct Bf16Scratch {
+    uint16_t *xb, *yb[2], *dzb, *wb[2];
+    int Ip, Hp, H4p;
+    size_t bytes;
+};
+Bf16Scratch bf16_scratch(void* base, int B, int T, int I, int H) {
+    Bf16Scratch s;
+    s.Ip = pad8i(I); s.Hp = pad8i(H); s.H4p = pad8i(4 * H);
+    const size_t TB = (size_t)T * B;
+    char* p = (char*)base + align_up((size_t)CS_CHUNKS * 4 * H * 4, 256);
+    s.xb = (uint16_t*)p;  p += align_up(TB * s.Ip * 2, 256);
+    for (int d = 0; d < 2; ++d) { s.yb[d] = (uint16_t*)p; p += align_up(TB * s.Hp * 2, 256); }
+    s.dzb = (uint16_t*)p; p += align_up(2 * TB * s.H4p * 2, 256);
+    for (int d = 0; d < 2; ++d) { s.wb[d] = (uint16_t*)p; p += align_up((size_t)I * s.H4p * 2, 256); }
+    s.bytes = (size_t)(p - (char*)base);
+    return s;
+}
+
 size_t gates_bytes(int B, int T, int H) { return align_up((size_t)2 * T * B * 4 * H * 4, 256); }
 size_t cst_bytes(int B, int T, int H) { return align_up((size_t)2 * T * B * H * 4, 256); }
 
@@ -264,6 +288,7 @@ extern "C" size_t amss_blstm_workspace_bytes(int B, int T, int I, int H, int pre
     g = std::max(g, amss_gemm_workspace_bytes(H, 4 * H, T * B, 1, 0, precision));
     g = std::max(g, amss_gemm_workspace_bytes(T * B, I, 4 * H, 0, 1, precision));
     g = std::max(g, (size_t)CS_CHUNKS * 4 * H * 4);   // column-sum partials share the GEMM scratch
+    if (precision == AMSS_PREC_BF16) g = std::max(g, bf16_scratch(nullptr, B, T, I, H).bytes);
     return 256 + gates_bytes(B, T, H) + cst_bytes(B, T, H) + align_up((size_t)2 * B * H * 4, 256) + align_up(g, 256);
 }
 
@@ -285,10 +310,24 @@ extern "C" int amss_blstm_fwd(const float* x, const float* kernel_fw, const floa
     const size_t gws_bytes = workspace_bytes - (size_t)((char*)gws - ws);
     const float* kern[2] = {kernel_fw, kernel_bw};
     const float* bias[2] = {bias_fw, bias_bw};
-    for (int d = 0; d < 2; ++d) {
-        int rc = gemm_dispatch(x, I, kern[d], 4 * H, bias[d], T * B, 4 * H, I, 0, 0, 0, precision,
-                               gates + (size_t)d * T * B * 4 * H, 4 * H, 0, 0, gws, gws_bytes, st);
+    if (precision == AMSS_PREC_BF16) {
+        // hoisted input projection on the tensor cores: x is converted once for both directions
+        const Bf16Scratch s = bf16_scratch(gws, B, T, I, H);
+        int rc = convert_bf16(x, T * B, I, I, s.xb, s.Ip, st);
         if (rc != AMSS_OK) return rc;
+        for (int d = 0; d < 2; ++d) {
+            rc = convert_bf16(kern[d], I, 4 * H, 4 * H, s.wb[d], s.H4p, st);
+            if (rc != AMSS_OK) return rc;
+            rc = gemm_bf16(s.xb, s.Ip, 0, s.wb[d], s.H4p, 1, bias[d], T * B, 4 * H, I, 0,
+                           gates + (size_t)d * T * B * 4 * H, 4 * H, 0, 0, st);
+            if (rc != AMSS_OK) return rc;
+        }
+    } else {
+        for (int d = 0; d < 2; ++d) {
+            int rc = gemm_dispatch(x, I, kern[d], 4 * H, bias[d], T * B, 4 * H, I, 0, 0, 0, precision,
+                                   gates + (size_t)d * T * B * 4 * H, 4 * H, 0, 0, gws, gws_bytes, st);
+            if (rc != AMSS_OK) return rc;
+        }
     }
     if (precision == AMSS_PREC_BF16 && blstm_rec_tc_supported(B, T, H))
         return blstm_rec_fwd_tc(kernel_fw + (size_t)I * 4 * H, kernel_bw + (size_t)I * 4 * H, 4 * H, gates, cst, y, B, T, H,
@@ -348,19 +387,38 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
     float* dkern[2] = {dkernel_fw, dkernel_bw};
     float* dbias[2] = {dbias_fw, dbias_bw};
     const int H4 = 4 * H;
+    const bool bf = precision == AMSS_PREC_BF16;
+    Bf16Scratch s{};
+    if (bf) {
+        // every operand is converted to bf16 ONCE (x, each direction's half of y, dZ of both directions, W_x); the
+        // t-1 / t+1 shifted views of dW_h are row offsets (multiples of the padded leading dimension: TMA-aligned)
+        s = bf16_scratch(gws, B, T, I, H);
+        int rc = convert_bf16(x, T * B, I, I, s.xb, s.Ip, st);
+        for (int d = 0; d < 2 && rc == AMSS_OK && T > 1; ++d) rc = convert_bf16(y + d * H, T * B, H, 2 * H, s.yb[d], s.Hp, st);
+        if (rc == AMSS_OK) rc = convert_bf16(dZ, 2 * T * B, H4, H4, s.dzb, s.H4p, st);
+        for (int d = 0; d < 2 && rc == AMSS_OK && dx; ++d) rc = convert_bf16(kern[d], I, H4, H4, s.wb[d], s.H4p, st);
+        if (rc != AMSS_OK) return rc;
+    }
     for (int d = 0; d < 2; ++d) {
         const float* dZd = dZ + (size_t)d * T * B * H4;
+        const uint16_t* dzb = bf ? s.dzb + (size_t)d * T * B * s.H4p : nullptr;
+        int rc;
         // dW_x = x^T dZ
-        int rc = gemm_dispatch(x, I, dZd, H4, nullptr, I, H4, T * B, 1, 0, 0, precision, dkern[d], H4, 0, 0, gws,
-                               gws_bytes, st);
+        if (bf) rc = gemm_bf16(s.xb, s.Ip, 1, dzb, s.H4p, 1, nullptr, I, H4, T * B, 0, dkern[d], H4, 0, 0, st);
+        else rc = gemm_dispatch(x, I, dZd, H4, nullptr, I, H4, T * B, 1, 0, 0, precision, dkern[d], H4, 0, 0, gws, gws_bytes, st);
         if (rc != AMSS_OK) return rc;
         // dW_h = h_prev^T dZ : forward dir pairs y[t-1] with dZ[t]; backward dir pairs y[t+1] with dZ[t]
         float* dWh = dkern[d] + (size_t)I * H4;
         if (T > 1) {
-            const float* hA = d == 0 ? y : y + (size_t)B * 2 * H + H;
-            const float* zB = d == 0 ? dZd + (size_t)B * H4 : dZd;
-            rc = gemm_dispatch(hA, 2 * H, zB, H4, nullptr, H, H4, (T - 1) * B, 1, 0, 0, precision, dWh, H4, 0, 0, gws,
-                               gws_bytes, st);
+            if (bf) {
+                rc = gemm_bf16(s.yb[d] + (d == 0 ? 0 : (size_t)B * s.Hp), s.Hp, 1, dzb + (d == 0 ? (size_t)B * s.H4p : 0), s.H4p, 1,
+                               nullptr, H, H4, (T - 1) * B, 0, dWh, H4, 0, 0, st);
+            } else {
+                const float* hA = d == 0 ? y : y + (size_t)B * 2 * H + H;
+                const float* zB = d == 0 ? dZd + (size_t)B * H4 : dZd;
+                rc = gemm_dispatch(hA, 2 * H, zB, H4, nullptr, H, H4, (T - 1) * B, 1, 0, 0, precision, dWh, H4, 0, 0, gws,
+                                   gws_bytes, st);
+            }
             if (rc != AMSS_OK) return rc;
         } else {
             AMSS_CUDA(cudaMemsetAsync(dWh, 0, (size_t)H * H4 * 4, st));
@@ -371,8 +429,9 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
             AMSS_LAUNCH(colsum_sum_kernel, (H4 + 255) / 256, 256, 0, st, (const float*)gws, CS_CHUNKS, H4, dbias[d]);
         }
         if (dx) {
-            rc = gemm_dispatch(dZd, H4, kern[d], H4, nullptr, T * B, I, H4, 0, 1, d, precision, dx, I, 0, 0, gws,
-                               gws_bytes, st);
+            // dx (+)= dZ W_x^T
+            if (bf) rc = gemm_bf16(dzb, s.H4p, 0, s.wb[d], s.H4p, 0, nullptr, T * B, I, H4, d, dx, I, 0, 0, st);
+            else rc = gemm_dispatch(dZd, H4, kern[d], H4, nullptr, T * B, I, H4, 0, 1, d, precision, dx, I, 0, 0, gws, gws_bytes, st);
             if (rc != AMSS_OK) return rc;
         }
     }

@@ -25,7 +25,8 @@ struct DtParams {
     const float* dloss;        // [1]
     const float* stats;        // [B][E*E + S*E + S + 1]  (An, Bn, dinv, loss) from the forward pass
     const float* inv_norm;     // [B*TF]
-    float* dz;                 // [B][TF][E]
+    float* dz;                 // [B][TF][E] fp32, or
+    uint16_t* dzb;             // [B][TF][E] bf16 (E % 8 == 0) when non-null: the head GEMMs consume it directly
     int B, E, S, EK, pitch;
     int64_t TF, ntiles, per;   // tiles of 128 points per mixture; flat tiles per CTA
 };
@@ -202,10 +203,21 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
                                           inv * (dv[4 * c + 2] - x.z * dot), inv * (dv[4 * c + 3] - x.w * dot));
                 }
             named_sync(2, 128);                            // all dz rows of the tile are in vs[buf]
-            float4* dst = reinterpret_cast<float4*>(p.dz + ((size_t)b * p.TF + p0) * E);
-            for (int u = et; u < np * e4; u += 128) {
-                const int rr = u / e4, c = u - rr * e4;
-                __stcs(dst + u, *reinterpret_cast<const float4*>(vb + rr * pitch + c * 4));
+            if (p.dzb) {
+                const int e8 = E / 8;
+                uint4* dst = reinterpret_cast<uint4*>(p.dzb + ((size_t)b * p.TF + p0) * E);
+                for (int u = et; u < np * e8; u += 128) {
+                    const int rr = u / e8, c = u - rr * e8;
+                    const float4 f0 = *reinterpret_cast<const float4*>(vb + rr * pitch + c * 8);
+                    const float4 f1 = *reinterpret_cast<const float4*>(vb + rr * pitch + c * 8 + 4);
+                    __stcs(dst + u, make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w)));
+                }
+            } else {
+                float4* dst = reinterpret_cast<float4*>(p.dz + ((size_t)b * p.TF + p0) * E);
+                for (int u = et; u < np * e4; u += 128) {
+                    const int rr = u / e4, c = u - rr * e4;
+                    __stcs(dst + u, *reinterpret_cast<const float4*>(vb + rr * pitch + c * 4));
+                }
             }
             mbar_arrive(t_empty + 8 * buf);                // vs[buf] and TMEM[buf] may be reused
         }
@@ -220,9 +232,9 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
 bool dpcl_bwd_tc_supported(int E, int S) { return E % 4 == 0 && E >= 8 && E <= 64 && S >= 1 && S <= DT_MAXS; }
 
 int dpcl_bwd_tc(const float* V, const uint8_t* labels, const float* dloss, const float* stats, const float* inv_norm, int B,
-                int64_t TF, int E, int S, float* dz, cudaStream_t st) {
+                int64_t TF, int E, int S, float* dz, uint16_t* dz_bf16, cudaStream_t st) {
     DtParams p;
-    p.V = V; p.labels = labels; p.dloss = dloss; p.stats = stats; p.inv_norm = inv_norm; p.dz = dz;
+    p.V = V; p.labels = labels; p.dloss = dloss; p.stats = stats; p.inv_norm = inv_norm; p.dz = dz; p.dzb = dz_bf16;
     p.B = B; p.E = E; p.S = S; p.TF = TF;
     p.EK = (E + 15) / 16 * 16;
     p.pitch = 4 * (((E + 3) / 4) | 1);

@@ -13,6 +13,10 @@ int gemm_tc(const float* A, int lda, const float* B, int ldb, const float* bias,
             int transb, int accumulate, int precision, float* C, int ldc, int swapB, int swapT, void* workspace,
             size_t workspace_bytes, cudaStream_t st);
 
+int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, cudaStream_t st);
+int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
+              int K, int accumulate, float* C, int ldc, int swapB, int swapT, cudaStream_t st);
+
 namespace {
 
 constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_THREADS = 256;
@@ -161,4 +165,23 @@ extern "C" int amss_gemm(const float* A, int lda, const float* B, int ldb, const
 extern "C" int amss_transpose_01(const float* in, int D0, int D1, int C, float* out, void* stream) {
     AMSS_REQUIRE(in && out && D0 > 0 && D1 > 0 && C > 0, "transpose_01: bad arguments");
     return transpose_01(in, D0, D1, C, out, (cudaStream_t)stream);
+}
+
+extern "C" int amss_convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, void* stream) {
+    AMSS_REQUIRE(src && dst && rows > 0 && cols > 0, "convert_bf16: bad arguments");
+    AMSS_REQUIRE(ld >= cols && ldd >= cols && ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 "convert_bf16: ldd must be a multiple of 8 (>= cols) and dst 16-byte aligned");
+    return convert_bf16(src, rows, cols, ld, dst, ldd, (cudaStream_t)stream);
+}
+
+extern "C" int amss_gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias,
+                              int M, int N, int K, int accumulate, float* C, int ldc, int out_swap_b, int out_swap_t,
+                              void* stream) {
+    AMSS_REQUIRE(A && B && C, "gemm_bf16: null pointer");
+    AMSS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
+    AMSS_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldc >= N, "gemm_bf16: leading dimension too small");
+    AMSS_REQUIRE((out_swap_b > 0) == (out_swap_t > 0), "gemm_bf16: out_swap_b/out_swap_t must both be set or both 0");
+    AMSS_REQUIRE(out_swap_b == 0 || (int64_t)out_swap_b * out_swap_t == M, "gemm_bf16: out_swap_b*out_swap_t != M");
+    return gemm_bf16(A, lda, a_mn ? 1 : 0, B, ldb, b_mn ? 1 : 0, bias, M, N, K, accumulate, C, ldc, out_swap_b,
+                     out_swap_t, (cudaStream_t)stream);
 }

@@ -99,16 +99,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
                     const uint32_t sa = smem_u32(smem + slot * GT_STAGE_BYTES), sb = sa + GT_A_BYTES;
                     const uint32_t bar = full + 8 * slot;
                     mbar_expect_tx(bar, GT_STAGE_BYTES);
-                    const int k0 = j * GT_BK;
-                    if (!p.a_mn) tma_load_2d(sa, &p.mapA, k0, m0, bar);
+                    const int ka = j * GT_BK, kb = ka;
+                    if (!p.a_mn) tma_load_2d(sa, &p.mapA, ka, m0, bar);
                     else {
 #pragma unroll
-                        for (int i = 0; i < GT_BM / 64; ++i) tma_load_2d(sa + i * 8192, &p.mapA, m0 + i * 64, k0, bar);
+                        for (int i = 0; i < GT_BM / 64; ++i) tma_load_2d(sa + i * 8192, &p.mapA, m0 + i * 64, ka, bar);
                     }
-                    if (!p.b_mn) tma_load_2d(sb, &p.mapB, k0, n0, bar);
+                    if (!p.b_mn) tma_load_2d(sb, &p.mapB, kb, n0, bar);
                     else {
 #pragma unroll
-                        for (int i = 0; i < GT_BN / 64; ++i) tma_load_2d(sb + i * 8192, &p.mapB, n0 + i * 64, k0, bar);
+                        for (int i = 0; i < GT_BN / 64; ++i) tma_load_2d(sb + i * 8192, &p.mapB, n0 + i * 64, kb, bar);
                     }
                 }
             }
@@ -272,7 +272,9 @@ int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, in
 }
 
 // C[M,N] (+)= A B^T-style product of two bf16 row-major operands.  a_mn = 0: A[m][k] = A[m*lda + k]; 1: A[k*lda + m].
-// b_mn = 0: B[n][k] = B[n*ldb + k]; 1: B[k*ldb + n].  lda, ldb multiples of 8, pointers 16-byte aligned.
+// b_mn = 0: B[n][k] = B[n*ldb + k]; 1: B[k*ldb + n].  lda, ldb multiples of 8 and base pointers 16-byte aligned (TMA;
+// a box may not start at an inner coordinate that is not a multiple of 16 bytes either -- the unit raises an
+// illegal-instruction fault -- so sub-matrix views are passed as offset POINTERS that keep this alignment).
 int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
               int K, int accumulate, float* C, int ldc, int swapB, int swapT, cudaStream_t st) {
     if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) {

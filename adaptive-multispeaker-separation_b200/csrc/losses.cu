@@ -389,6 +389,28 @@ __global__ void colsum_partial_kernel(const float* __restrict__ dZ, int64_t M, i
         part[(size_t)blockIdx.y * N + n] = s;
     }
 }
+// same for a bf16 matrix (N even): a thread owns two adjacent columns, a warp reads 128 contiguous bytes of a row
+__global__ void colsum_partial_bf16_kernel(const uint32_t* __restrict__ dZ2, int64_t M, int N2, float* __restrict__ part) {
+    __shared__ float2 tile[8][33];
+    const int n2 = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ty = threadIdx.x >> 5;
+    float2 a = make_float2(0.f, 0.f);
+    if (n2 < N2)
+        for (int64_t m = blockIdx.y * 8 + ty; m < M; m += (int64_t)gridDim.y * 8) {
+            const uint32_t w = __ldg(dZ2 + m * N2 + n2);
+            a.x += __uint_as_float(w << 16);
+            a.y += __uint_as_float(w & 0xFFFF0000u);
+        }
+    tile[ty][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (ty == 0 && n2 < N2) {
+        float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s.x += tile[i][threadIdx.x & 31].x; s.y += tile[i][threadIdx.x & 31].y; }
+        part[(size_t)blockIdx.y * (2 * N2) + 2 * n2] = s.x;
+        part[(size_t)blockIdx.y * (2 * N2) + 2 * n2 + 1] = s.y;
+    }
+}
 __global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < N) {
@@ -634,7 +656,7 @@ extern "C" int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const f
 namespace amss {
 bool dpcl_bwd_tc_supported(int E, int S);
 int dpcl_bwd_tc(const float* V, const uint8_t* labels, const float* dloss, const float* stats, const float* inv_norm, int B,
-                int64_t TF, int E, int S, float* dz, cudaStream_t st);
+                int64_t TF, int E, int S, float* dz, uint16_t* dz_bf16, cudaStream_t st);
 }  // namespace amss
 
 extern "C" int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labels, const float* dloss,
@@ -645,8 +667,20 @@ extern "C" int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labe
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd_normalized: E=%d outside [1,64]", E);
     if (precision == AMSS_PREC_BF16 && dpcl_bwd_tc_supported(E, S) &&
         ((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0)
-        return dpcl_bwd_tc(V, labels, dloss, (const float*)workspace, inv_norm, B, TF, E, S, dz, (cudaStream_t)stream);
+        return dpcl_bwd_tc(V, labels, dloss, (const float*)workspace, inv_norm, B, TF, E, S, dz, nullptr, (cudaStream_t)stream);
     return dpcl_bwd_launch(V, labels, dloss, inv_norm, B, TF, E, S, dz, workspace, stream);
+}
+
+extern "C" int amss_dpcl_loss_bwd_normalized_bf16(const float* V, const uint8_t* labels, const float* dloss,
+                                                  const float* inv_norm, int B, int64_t TF, int E, int S,
+                                                  uint16_t* dz_bf16, const void* workspace, void* stream) {
+    AMSS_REQUIRE(V && labels && dloss && inv_norm && dz_bf16 && workspace, "dpcl_loss_bwd_normalized_bf16: null pointer");
+    if (!(dpcl_bwd_tc_supported(E, S) && E % 8 == 0) ||
+        ((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(dz_bf16)) & 15) != 0) {
+        set_error("dpcl_loss_bwd_normalized_bf16: needs E %% 8 == 0, 8 <= E <= 64, 16-byte aligned buffers (E=%d S=%d)", E, S);
+        return AMSS_ERR_UNSUPPORTED;
+    }
+    return dpcl_bwd_tc(V, labels, dloss, (const float*)workspace, inv_norm, B, TF, E, S, nullptr, dz_bf16, (cudaStream_t)stream);
 }
 
 extern "C" int amss_l2norm_fwd(const float* z, int64_t rows, int E, float* v, float* inv_norm, void* stream) {
@@ -682,6 +716,18 @@ extern "C" int amss_colsum(const float* dZ, int64_t M, int N, float* dbias, void
     if (workspace_bytes < (size_t)chunks * N * 4) { set_error("colsum: workspace too small"); return AMSS_ERR_WORKSPACE; }
     dim3 grid((N + 31) / 32, chunks);
     AMSS_LAUNCH(colsum_partial_kernel, grid, 256, 0, stream, dZ, M, N, (float*)workspace);
+    AMSS_LAUNCH(colsum_final_kernel, (N + 255) / 256, 256, 0, stream, (const float*)workspace, chunks, N, dbias);
+    return AMSS_OK;
+}
+
+extern "C" int amss_colsum_bf16(const uint16_t* dZ, int64_t M, int N, float* dbias, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    AMSS_REQUIRE(dZ && dbias && workspace, "colsum_bf16: null pointer");
+    AMSS_REQUIRE(N % 2 == 0 && (reinterpret_cast<uintptr_t>(dZ) & 3) == 0, "colsum_bf16: N must be even and dZ 4-byte aligned");
+    int chunks = (int)std::min<int64_t>(64, (M + 7) / 8);
+    if (workspace_bytes < (size_t)chunks * N * 4) { set_error("colsum_bf16: workspace too small"); return AMSS_ERR_WORKSPACE; }
+    dim3 grid((N / 2 + 31) / 32, chunks);
+    AMSS_LAUNCH(colsum_partial_bf16_kernel, grid, 256, 0, stream, (const uint32_t*)dZ, M, N / 2, (float*)workspace);
     AMSS_LAUNCH(colsum_final_kernel, (N + 255) / 256, 256, 0, stream, (const float*)workspace, chunks, N, dbias);
     return AMSS_OK;
 }

@@ -132,29 +132,44 @@ class _DenseFn(torch.autograd.Function):
     swap=(B,T): the rows of x are time-major (t*B+b) and the rows of y batch-major (b*T+t) -- the
     [T,B,*] -> [B,T,*] hand-over between the BLSTM stack and the embedding reshape.  The small [M,K] activation is
     re-ordered (and kept for dW); re-ordering the wide [M,N] output rows in the GEMM epilogue instead scatters every
-    128-row tile over 128 pages 10 MB apart and runs the head GEMM 3x slower (TLB misses)."""
+    128-row tile over 128 pages 10 MB apart and runs the head GEMM 3x slower (TLB misses).
+    AMSS_PREC_BF16: x and W are converted to bf16 once; the copies feed the forward GEMM and are kept for the
+    backward (dW = x^T dy reads x MN-major, dx = dy W^T reads W K-major: no transposes)."""
 
     @staticmethod
     def forward(ctx, x, W, b, precision, swap):
         if swap:
             Bq, Tq = swap
             x = ops.transpose_01(x.view(Tq, Bq, -1)).view(Bq * Tq, -1)
-        ctx.save_for_backward(x, W)
         ctx.precision, ctx.swap = precision, swap
-        return ops.gemm(x, W, b, precision=precision)
+        if precision == AMSS_PREC_FP32:
+            ctx.save_for_backward(x, W)
+            return ops.gemm(x, W, b, precision=precision)
+        xb, Wb = ops.convert_bf16(x), ops.convert_bf16(W)
+        ctx.save_for_backward(xb, Wb)
+        ctx.bf16_operands = (xb, Wb)
+        return ops.gemm_bf16(xb, False, Wb, True, x.shape[0], W.shape[1], W.shape[0], bias=b)
 
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
         dy = dy.contiguous()
         swap = ctx.swap
+        back_swap = (swap[1], swap[0]) if swap else None      # dy rows are batch-major, dx rows time-major
         dx = dW = db = None
-        if ctx.needs_input_grad[0]:
-            # rows of dy are batch-major; write dx back in the caller's (time-major) row order
-            dx = ops.gemm(dy, W, None, transb=True, precision=ctx.precision,
-                          out_swap=(swap[1], swap[0]) if swap else None)
-        if ctx.needs_input_grad[1]:
-            dW = ops.gemm(x, dy, None, transa=True, precision=ctx.precision)
+        if ctx.precision == AMSS_PREC_FP32:
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm(dy, W, None, transb=True, precision=ctx.precision, out_swap=back_swap)
+            if ctx.needs_input_grad[1]:
+                dW = ops.gemm(x, dy, None, transa=True, precision=ctx.precision)
+        else:
+            M, N = dy.shape
+            K = W.shape[0]
+            dyb = ops.convert_bf16(dy)
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_bf16(dyb, False, W, False, M, K, N, out_swap=back_swap)
+            if ctx.needs_input_grad[1]:
+                dW = ops.gemm_bf16(x, True, dyb, True, K, N, M)
         if ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
         return dx, dW, db, None, None
@@ -205,6 +220,35 @@ class _NormDPCLLossFn(torch.autograd.Function):
         V, inv, labels, ws = ctx.saved_tensors
         dz = ops.dpcl_loss_bwd_normalized(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws, inv, ctx.precision)
         return dz.view(ctx.zshape), None, None, None, None, None
+
+
+class _HeadNormDPCLLossFn(torch.autograd.Function):
+    """DPCL cost of l2_normalize(x W + b) as ONE autograd node on (x, W, b) for the tensor-core path: the backward
+    writes dz once, in bf16, straight from the fused DPCL + normalisation kernel and feeds it to the two head GEMMs
+    (dx = dz W^T, dW = x^T dz) and the bias column sum -- the fp32 [B*T, F*E] gradient never exists."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, xb, Wb, V, inv, labels, S, swap):
+        loss, ws = ops.dpcl_loss_fwd(V, labels, S, ops.AMSS_PREC_BF16)
+        ctx.save_for_backward(xb, Wb, V, inv, labels, ws)
+        ctx.S, ctx.swap, ctx.K, ctx.N = S, swap, W.shape[0], W.shape[1]
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        xb, Wb, V, inv, labels, ws = ctx.saved_tensors
+        swap, K, N = ctx.swap, ctx.K, ctx.N
+        dzb = ops.dpcl_loss_bwd_normalized_bf16(V, labels, ctx.S, dloss.reshape(1).contiguous(), ws, inv)
+        M = dzb.numel() // N
+        dzb = dzb.view(M, N)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_bf16(dzb, False, Wb, False, M, K, N, out_swap=(swap[1], swap[0]) if swap else None)
+        if ctx.needs_input_grad[1]:
+            dW = ops.gemm_bf16(xb, True, dzb, True, K, N, M)
+        if ctx.needs_input_grad[2]:
+            db = ops.colsum_bf16(dzb)
+        return dx, dW, db, None, None, None, None, None, None, None
 
 
 class _L41LossFn(torch.autograd.Function):
@@ -295,8 +339,23 @@ def blstm(x, kf, bf, kb, bb, precision=AMSS_PREC_FP32):
     return _BLSTMFn.apply(x, kf, bf, kb, bb, precision)
 
 
+def _carry(src, dst):
+    """Views made by the layer protocol (Conv1D's [B,T,N] view, Reshape) keep the side-channel that lets dpcl_loss()
+    fuse the head's backward with the loss (see _HeadNormDPCLLossFn)."""
+    h = getattr(src, "_amss_dense", None)
+    if h is not None:
+        dst._amss_dense = h
+    return dst
+
+
 def dense(x, W, b, precision=AMSS_PREC_FP32, swap=None):
-    return _DenseFn.apply(x, W, b, precision, swap)
+    y = _DenseFn.apply(x, W, b, precision, swap)
+    if precision != AMSS_PREC_FP32 and y.requires_grad and b is not None:
+        fn = y.grad_fn
+        ops_b = getattr(fn, "bf16_operands", None)
+        if ops_b is not None:
+            y._amss_dense = (x, W, b, ops_b[0], ops_b[1], swap)
+    return y
 
 
 def l2_normalize(z, E):
@@ -308,9 +367,16 @@ def l2_normalize(z, E):
 
 def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32):
     """prenorm = (z, inv_norm) as stashed by l2_normalize() on its output: the loss becomes one autograd node
-    on z with a fused backward (DPCL gradient + normalisation Jacobian)."""
+    on z with a fused backward (DPCL gradient + normalisation Jacobian).  On the tensor-core path, when z is the
+    output of a dense layer, the node moves one step further up (onto the layer's x, W, b): _HeadNormDPCLLossFn."""
     if prenorm is not None:
         z, inv = prenorm
+        head = getattr(z, "_amss_dense", None)
+        E = V.shape[-1]
+        if head is not None and precision != AMSS_PREC_FP32 and E % 8 == 0 and 8 <= E <= 64 and S <= 4:
+            x, W, b, xb, Wb, swap = head
+            if W.shape[1] % 2 == 0 and z.numel() == V.numel():
+                return _HeadNormDPCLLossFn.apply(x, W, b, xb, Wb, V.detach(), inv, labels, S, swap)
         return _NormDPCLLossFn.apply(z, V.detach(), inv, labels, S, precision)
     return _DPCLLossFn.apply(V.contiguous(), labels, S, precision)
 
@@ -389,7 +455,7 @@ class Conv1D:
             y = dense(xt.reshape(Tt * B, C), W, b, self.precision, swap=(B, Tt))
         else:
             y = dense(x.reshape(B * Tt, C), W, b, self.precision)
-        return y.view(B, Tt, -1)
+        return _carry(y, y.view(B, Tt, -1))
 
 
 class Reshape:
@@ -399,7 +465,7 @@ class Reshape:
         self.shape, self.name = shape, name
 
     def f_prop(self, x):
-        return x.reshape(self.shape)
+        return _carry(x, x.reshape(self.shape))
 
 
 class Normalize:

@@ -185,6 +185,32 @@ def gemm(A, B, bias=None, transa=False, transb=False, out=None, accumulate=False
     return out
 
 
+def convert_bf16(x):
+    """fp32 [rows, cols] (unit inner stride) -> bf16 [rows, pad8(cols)] (zero padded): operand of gemm_bf16."""
+    if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+        raise _lib.AmssError("convert_bf16: need a 2-D CUDA tensor with unit inner stride")
+    rows, cols = x.shape
+    ldd = (cols + 7) // 8 * 8
+    out = torch.empty(rows, ldd, dtype=torch.bfloat16, device=x.device)
+    _lib.call("amss_convert_bf16", _p(x), rows, cols, x.stride(0), _p(out), ldd, _stream())
+    return out
+
+
+def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, accumulate=False, out_swap=None):
+    """C[M,N] (+)= A B from bf16 operands (see amss_gemm_bf16): a_mn False -> A [M,K]; True -> A stored [K,M];
+    b_mn True -> B [K,N]; False -> B stored [N,K]."""
+    for t in (A, B):
+        if not t.is_cuda or t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.bfloat16:
+            raise _lib.AmssError("gemm_bf16: operands must be 2-D bf16 CUDA tensors with unit inner stride")
+    if out is None:
+        out = torch.empty(M, N, dtype=_f32, device=A.device)
+        accumulate = False
+    sb, st = (out_swap if out_swap else (0, 0))
+    _lib.call("amss_gemm_bf16", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(bias), M, N, K,
+              int(accumulate), _p(out), out.stride(0), sb, st, _stream())
+    return out
+
+
 def blstm_fwd(x_tm, kernel_fw, bias_fw, kernel_bw, bias_bw, forget_bias=1.0, precision=AMSS_PREC_FP32,
               save_for_backward=True):
     """x_tm[T,B,I] time-major -> (y_tm[T,B,2H], saved or None)."""
@@ -242,6 +268,15 @@ def colsum(dZ):
     return out
 
 
+def colsum_bf16(dZ):
+    _chk(dZ)
+    M, N = dZ.shape
+    out = torch.empty(N, dtype=_f32, device=dZ.device)
+    ws = _ws(_lib.query("amss_colsum_workspace_bytes", M, N), dZ.device)
+    _lib.call("amss_colsum_bf16", _p(dZ), M, N, _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
 def dpcl_loss_fwd(V, labels, S, precision=AMSS_PREC_FP32):
     """V[B,TF,E], labels uint8 [B,TF] -> (loss[1], workspace for the backward)."""
     _chk(V, labels)
@@ -267,6 +302,16 @@ def dpcl_loss_bwd_normalized(V, labels, S, dloss, ws, inv_norm, precision=AMSS_P
     dz = torch.empty_like(V)
     _lib.call("amss_dpcl_loss_bwd_normalized", _p(V), _p(labels), _p(dloss), _p(inv_norm), B, TF, E, S, precision, _p(dz),
               _p(ws), _stream())
+    return dz
+
+
+def dpcl_loss_bwd_normalized_bf16(V, labels, S, dloss, ws, inv_norm):
+    """As dpcl_loss_bwd_normalized on the tensor cores, with dz returned as bf16 [B,TF,E] (operand of gemm_bf16)."""
+    _chk(V, labels, dloss, inv_norm)
+    B, TF, E = V.shape
+    dz = torch.empty(B, TF, E, dtype=torch.bfloat16, device=V.device)
+    _lib.call("amss_dpcl_loss_bwd_normalized_bf16", _p(V), _p(labels), _p(dloss), _p(inv_norm), B, TF, E, S, _p(dz), _p(ws),
+              _stream())
     return dz
 
 

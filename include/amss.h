@@ -154,9 +154,24 @@ int amss_gemm(const float* A, int lda, const float* B, int ldb, const float* bia
               int N, int K, int transa, int transb, int accumulate, int precision, float* C,
               int ldc, int out_swap_b, int out_swap_t, void* workspace,
               size_t workspace_bytes, void* stream);
+/* bf16 operands held by the caller (no conversion pass): C[M,N] (ldc) (+)= A B (+ bias), fp32
+ * accumulation and output.  Both operands are row-major bf16 matrices with leading dimensions
+ * that are multiples of 8 and 16-byte aligned bases (TMA tensor maps are built over them):
+ *   a_mn = 0: A is [M,K] (K contiguous);   a_mn = 1: A is stored [K,M] (dW = X^T dZ);
+ *   b_mn = 1: B is [K,N] (N contiguous);   b_mn = 0: B is stored [N,K] (dX = dZ W^T).
+ * Replaces the same reference ops as amss_gemm (utils/ops.py:501-503, :372-380).         */
+int amss_gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn,
+                   const float* bias, int M, int N, int K, int accumulate, float* C, int ldc,
+                   int out_swap_b, int out_swap_t, void* stream);
+/* fp32 [rows,cols] (ld) -> bf16 [rows,ldd], ldd % 8 == 0, columns >= cols zero filled.    */
+int amss_convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd,
+                      void* stream);
 /* in[D0,D1,C] -> out[D1,D0,C]                                                           */
 int amss_transpose_01(const float* in, int D0, int D1, int C, float* out, void* stream);
 size_t amss_gemm_workspace_bytes(int M, int N, int K, int transa, int transb, int precision);
+/* dbias[N] = column sums of a bf16 [M,N] matrix (N even); workspace as amss_colsum.       */
+int amss_colsum_bf16(const uint16_t* dZ, int64_t M, int N, float* dbias, void* workspace,
+                     size_t workspace_bytes, void* stream);
 /* v = z * rsqrt(max(sum_E z^2, 1e-12)) over groups of E consecutive values
  * (tf.nn.l2_normalize, axis=3 of [B,T,F,E]).  In place allowed.                         */
 int amss_l2norm_fwd(const float* z, int64_t rows, int E, float* v, float* inv_norm,
@@ -193,6 +208,11 @@ int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const float* dloss
 int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labels, const float* dloss,
                                   const float* inv_norm, int B, int64_t TF, int E, int S,
                                   int precision, float* dz, const void* workspace, void* stream);
+/* Same on tcgen05 with dz written as bf16 [B,TF,E] (E % 8 == 0): the embedding-head backward
+ * GEMMs (amss_gemm_bf16) read it directly and the fp32 gradient never reaches HBM.         */
+int amss_dpcl_loss_bwd_normalized_bf16(const float* V, const uint8_t* labels, const float* dloss,
+                                       const float* inv_norm, int B, int64_t TF, int E, int S,
+                                       uint16_t* dz_bf16, const void* workspace, void* stream);
 /* L41Model.cost, sampling=None (models/L41.py:47-63, 150-178):
  * mean_{b,tf,s} -log sigmoid(y * <spk[b,s,:], emb[b,tf,:]>), y=+1 if labels==s else -1.
  * spk[B,S,E] = (normalised) gathered speaker vectors.                                   */
