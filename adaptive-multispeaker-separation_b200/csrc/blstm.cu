@@ -22,7 +22,7 @@ bool blstm_rec_tc_supported(int B, int T, int H);
 void blstm_tc_set_profile(long long* dev_buf);
 int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, cudaStream_t st);
 int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
-              int K, int accumulate, float* C, int ldc, int swapB, int swapT, cudaStream_t st);
+              int K, int accumulate, float* C, int ldc, int swapB, int swapT, int norm_E, float* inv, cudaStream_t st);
 int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gates, float* cst, float* y, int B, int T,
                      int H, float forget_bias, cudaStream_t st);
 int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,
@@ -319,7 +319,7 @@ extern "C" int amss_blstm_fwd(const float* x, const float* kernel_fw, const floa
             rc = convert_bf16(kern[d], I, 4 * H, 4 * H, s.wb[d], s.H4p, st);
             if (rc != AMSS_OK) return rc;
             rc = gemm_bf16(s.xb, s.Ip, 0, s.wb[d], s.H4p, 1, bias[d], T * B, 4 * H, I, 0,
-                           gates + (size_t)d * T * B * 4 * H, 4 * H, 0, 0, st);
+                           gates + (size_t)d * T * B * 4 * H, 4 * H, 0, 0, 0, nullptr, st);
             if (rc != AMSS_OK) return rc;
         }
     } else {
@@ -404,7 +404,7 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
         const uint16_t* dzb = bf ? s.dzb + (size_t)d * T * B * s.H4p : nullptr;
         int rc;
         // dW_x = x^T dZ
-        if (bf) rc = gemm_bf16(s.xb, s.Ip, 1, dzb, s.H4p, 1, nullptr, I, H4, T * B, 0, dkern[d], H4, 0, 0, st);
+        if (bf) rc = gemm_bf16(s.xb, s.Ip, 1, dzb, s.H4p, 1, nullptr, I, H4, T * B, 0, dkern[d], H4, 0, 0, 0, nullptr, st);
         else rc = gemm_dispatch(x, I, dZd, H4, nullptr, I, H4, T * B, 1, 0, 0, precision, dkern[d], H4, 0, 0, gws, gws_bytes, st);
         if (rc != AMSS_OK) return rc;
         // dW_h = h_prev^T dZ : forward dir pairs y[t-1] with dZ[t]; backward dir pairs y[t+1] with dZ[t]
@@ -412,7 +412,7 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
         if (T > 1) {
             if (bf) {
                 rc = gemm_bf16(s.yb[d] + (d == 0 ? 0 : (size_t)B * s.Hp), s.Hp, 1, dzb + (d == 0 ? (size_t)B * s.H4p : 0), s.H4p, 1,
-                               nullptr, H, H4, (T - 1) * B, 0, dWh, H4, 0, 0, st);
+                               nullptr, H, H4, (T - 1) * B, 0, dWh, H4, 0, 0, 0, nullptr, st);
             } else {
                 const float* hA = d == 0 ? y : y + (size_t)B * 2 * H + H;
                 const float* zB = d == 0 ? dZd + (size_t)B * H4 : dZd;
@@ -430,7 +430,7 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
         }
         if (dx) {
             // dx (+)= dZ W_x^T
-            if (bf) rc = gemm_bf16(dzb, s.H4p, 0, s.wb[d], s.H4p, 0, nullptr, T * B, I, H4, d, dx, I, 0, 0, st);
+            if (bf) rc = gemm_bf16(dzb, s.H4p, 0, s.wb[d], s.H4p, 0, nullptr, T * B, I, H4, d, dx, I, 0, 0, 0, nullptr, st);
             else rc = gemm_dispatch(dZd, H4, kern[d], H4, nullptr, T * B, I, H4, 0, 1, d, precision, dx, I, 0, 0, gws, gws_bytes, st);
             if (rc != AMSS_OK) return rc;
         }

@@ -15,7 +15,7 @@ int gemm_tc(const float* A, int lda, const float* B, int ldb, const float* bias,
 
 int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, cudaStream_t st);
 int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
-              int K, int accumulate, float* C, int ldc, int swapB, int swapT, cudaStream_t st);
+              int K, int accumulate, float* C, int ldc, int swapB, int swapT, int norm_E, float* inv, cudaStream_t st);
 
 namespace {
 
@@ -176,12 +176,12 @@ extern "C" int amss_convert_bf16(const float* src, int rows, int cols, int ld, u
 
 extern "C" int amss_gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias,
                               int M, int N, int K, int accumulate, float* C, int ldc, int out_swap_b, int out_swap_t,
-                              void* stream) {
+                              int norm_E, float* inv_norm, void* stream) {
     AMSS_REQUIRE(A && B && C, "gemm_bf16: null pointer");
     AMSS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
     AMSS_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldc >= N, "gemm_bf16: leading dimension too small");
     AMSS_REQUIRE((out_swap_b > 0) == (out_swap_t > 0), "gemm_bf16: out_swap_b/out_swap_t must both be set or both 0");
     AMSS_REQUIRE(out_swap_b == 0 || (int64_t)out_swap_b * out_swap_t == M, "gemm_bf16: out_swap_b*out_swap_t != M");
     return gemm_bf16(A, lda, a_mn ? 1 : 0, B, ldb, b_mn ? 1 : 0, bias, M, N, K, accumulate, C, ldc, out_swap_b,
-                     out_swap_t, (cudaStream_t)stream);
+                     out_swap_t, norm_E, inv_norm, (cudaStream_t)stream);
 }

@@ -12,8 +12,8 @@
 //   3. persistent CTAs (one per SM) walk (tile, k-split) work items; ONE thread feeds a 4-stage mbarrier ring
 //      (48 KB per stage, ~190 KB of loads in flight per SM, no per-element load instructions);
 //   4. one warp issues tcgen05.mma 128x256x16 (converged loop, elected lane);
-//   5. TMEM accumulators are double buffered (2 x 256 columns): 4 epilogue warps drain tile i (bias, row remap,
-//      accumulate / split-K red.global.add) while tile i+1 is being multiplied.
+//   5. TMEM accumulators are double buffered (2 x 256 columns): 8 epilogue warps drain tile i (bias, optional fused
+//      l2-normalise over column groups, row remap, accumulate / split-K red.global.add) while tile i+1 is multiplied.
 #include "common.cuh"
 #include "tc.cuh"
 #include <cuda.h>
@@ -25,16 +25,19 @@ namespace {
 using namespace tc;
 
 constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 64, GT_STAGES = 4;
-constexpr int GT_THREADS = 192;                      // warp 0 loader, 1 MMA (+TMEM alloc), 2-5 epilogue
+constexpr int GT_THREADS = 320;                      // warp 0 loader, 1 MMA (+TMEM alloc), 2-9 epilogue
 constexpr int GT_A_BYTES = GT_BM * GT_BK * 2, GT_B_BYTES = GT_BN * GT_BK * 2;
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
+constexpr int GT_EMAX = 48;                         // widest l2-normalised group the fused epilogue handles
 constexpr int GT_SMEM = GT_STAGES * GT_STAGE_BYTES + 1024;   // + slack to align the ring to the 1024-B swizzle atom
 
 struct GtParams {
     CUtensorMap mapA, mapB;
     const float* bias;
     float* C;
+    float* inv;                       // norm_E > 0: [M][N / norm_E] reciprocal norms
     int ldc, M, N, K, KS, accumulate, swapB, swapT, a_mn, b_mn;
+    int bn, norm_E;                   // tile width along N (256, or the largest multiple of norm_E below it)
     int tm, tn, ksplit, sper;         // tiles, k-splits, stages per split
 };
 
@@ -65,6 +68,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  : "memory");
 }
 
+// E (multiple of 8, <= GT_EMAX) accumulator columns of this thread's row -> registers (no wait)
+__device__ __forceinline__ void load_group(uint32_t taddr, int E, uint32_t (&dst)[GT_EMAX]) {
+#pragma unroll
+    for (int c = 0; c < GT_EMAX / 8; ++c)
+        if (c * 8 < E) tmem_ld8(taddr + c * 8, &dst[c * 8]);
+}
+
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GtParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     const uint32_t tfull = smem_u32(&bars[2 * GT_STAGES]), tempty = tfull + 16;
     if (tid == 0) {
         for (int s = 0; s < GT_STAGES; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull + 8 * b, 1); mbar_init(tempty + 8 * b, 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull + 8 * b, 1); mbar_init(tempty + 8 * b, 256); }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
             uint32_t g = 0;
             for (int it = blockIdx.x; it < items; it += gridDim.x) {
                 const int split = it % p.ksplit, tile = it / p.ksplit;
-                const int n0 = (tile % p.tn) * GT_BN, m0 = (tile / p.tn) * GT_BM;
+                const int n0 = (tile % p.tn) * p.bn, m0 = (tile / p.tn) * GT_BM;
                 const int sbeg = split * p.sper, send = min(p.KS, sbeg + p.sper);
                 for (int j = sbeg; j < send; ++j, ++g) {
                     const uint32_t slot = g % GT_STAGES, ph = (g / GT_STAGES) & 1;
@@ -115,7 +125,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (converged loop, elected lane) ----------------
-        const uint32_t idesc = idesc_bf16(GT_BM, GT_BN, p.a_mn, p.b_mn);
+        const uint32_t idesc = idesc_bf16(GT_BM, p.bn, p.a_mn, p.b_mn);
         // K-major: 8-row groups 1024 B apart, K step of 16 = +32 B inside the 128-B swizzle row.
         // MN-major: 8-k groups 1024 B apart (SBO), 64-wide mn atoms 8192 B apart (LBO), K step of 16 = +2048 B.
         const uint32_t a_step = p.a_mn ? 2048u : 32u, a_lbo = p.a_mn ? 8192u : 16u;
@@ -145,15 +155,19 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
             if (leader) mma_commit(tfull + 8 * buf);
         }
     } else {
-        // ---------------- epilogue: warps 2..5, TMEM lane quadrant = warp % 4 ----------------
-        const int q = warp & 3;
+        // ---------------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, two warps per quadrant ----------------
+        // A thread owns one accumulator row (TMEM lane) and stores 128..192 contiguous bytes of it per chunk.  The
+        // epilogue is latency bound (tcgen05.ld -> bias -> stores), not bandwidth bound: two warps per quadrant take
+        // alternate column chunks and each prefetches its next chunk from TMEM while it stores the current one.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         const bool atomic = p.ksplit > 1;
+        const int E = p.norm_E;
         uint32_t ti = 0;
         for (int it = blockIdx.x; it < items; it += gridDim.x, ++ti) {
             const int split = it % p.ksplit, tile = it / p.ksplit;
-            const int n0 = (tile % p.tn) * GT_BN, m0 = (tile / p.tn) * GT_BM;
+            const int n0 = (tile % p.tn) * p.bn, m0 = (tile / p.tn) * GT_BM;
             const uint32_t buf = ti & 1, tph = (ti >> 1) & 1;
             mbar_wait(tfull + 8 * buf, tph);
             tc_fence_after();
@@ -162,46 +176,89 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
             if (p.swapB > 0 && m < p.M) row = (size_t)(m % p.swapB) * p.swapT + (size_t)(m / p.swapB);
             float* crow = p.C + row * p.ldc;
             const bool add_bias = p.bias != nullptr && split == 0;
+            const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + buf * GT_BN;
+            if (E > 0) {
+                // fused tf.nn.l2_normalize over groups of E output columns (utils/ops.py:323-324): C = normalised
+                // rows, inv[row][group] = 1/norm (negative on the clamped branch, as amss_l2norm_fwd writes it)
+                const int groups = min(p.bn, p.N - n0) / E, e4 = E >> 2, ngr = p.N / E;
 #pragma unroll 1
-            for (int c0 = 0; c0 < GT_BN; c0 += 32) {
-                uint32_t v[32];
-                const bool live = n0 + c0 < p.N;           // warp-uniform
-                if (live) {
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * GT_BN + c0, v);
+                for (int g = half; g < groups; g += 2) {
+                    uint32_t v[GT_EMAX];
+                    load_group(tacc + g * E, E, v);
                     tmem_ld_wait();
-                }
-                if (c0 + 32 == GT_BN) {                     // accumulator drained: release it before the stores
-                    tc_fence_before();
-                    mbar_arrive(tempty + 8 * buf);
-                }
-                if (!live || m >= p.M) continue;
-                const int nb = n0 + c0;
-                if (!atomic && vec_ok && nb + 32 <= p.N) {
+                    const int nb = n0 + g * E;
+                    float ss = 0.f;
 #pragma unroll
-                    for (int gq = 0; gq < 8; ++gq) {
-                        float4 o = make_float4(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1]),
-                                               __uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3]));
-                        if (add_bias) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + gq);
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                        }
-                        float4* dst = reinterpret_cast<float4*>(crow + nb) + gq;
-                        if (p.accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                        *dst = o;
-                    }
-                } else {
+                    for (int c = 0; c < GT_EMAX / 4; ++c)
+                        if (c < e4) {
+                            if (add_bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + c);
+                                v[4 * c] = __float_as_uint(__uint_as_float(v[4 * c]) + bb.x);
+                                v[4 * c + 1] = __float_as_uint(__uint_as_float(v[4 * c + 1]) + bb.y);
+                                v[4 * c + 2] = __float_as_uint(__uint_as_float(v[4 * c + 2]) + bb.z);
+                                v[4 * c + 3] = __float_as_uint(__uint_as_float(v[4 * c + 3]) + bb.w);
+                            }
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int n = nb + jj;
-                        if (n < p.N) {
-                            float o = __uint_as_float(v[jj]);
-                            if (add_bias) o += __ldg(p.bias + n);
-                            if (atomic) atomicAdd(crow + n, o);
-                            else crow[n] = p.accumulate ? crow[n] + o : o;
+                            for (int e = 0; e < 4; ++e) ss = fmaf(__uint_as_float(v[4 * c + e]), __uint_as_float(v[4 * c + e]), ss);
+                        }
+                    const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+                    if (m < p.M) {
+                        float4* dst = reinterpret_cast<float4*>(crow + nb);
+#pragma unroll
+                        for (int c = 0; c < GT_EMAX / 4; ++c)
+                            if (c < e4)
+                                dst[c] = make_float4(__uint_as_float(v[4 * c]) * inv, __uint_as_float(v[4 * c + 1]) * inv,
+                                                     __uint_as_float(v[4 * c + 2]) * inv, __uint_as_float(v[4 * c + 3]) * inv);
+                        p.inv[row * ngr + nb / E] = (ss >= 1e-12f) ? inv : -inv;
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty + 8 * buf);              // this warp's share of the accumulator is drained
+                continue;
+            }
+            const int chunks = (min(GT_BN, p.N - n0) + 31) >> 5;
+            uint32_t v[32], vn[32];
+            if (half < chunks) { tmem_ld32(tacc + half * 32, v); tmem_ld_wait(); }
+#pragma unroll 1
+            for (int ci = half; ci < chunks; ci += 2) {
+                const bool more = ci + 2 < chunks;
+                if (more) tmem_ld32(tacc + (ci + 2) * 32, vn);
+                const int nb = n0 + ci * 32;
+                if (m < p.M) {
+                    if (!atomic && vec_ok && nb + 32 <= p.N) {
+                        float4* dst = reinterpret_cast<float4*>(crow + nb);
+#pragma unroll
+                        for (int gq = 0; gq < 8; ++gq) {
+                            float4 o = make_float4(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1]),
+                                                   __uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3]));
+                            if (add_bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + gq);
+                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            }
+                            if (p.accumulate) { const float4 old = dst[gq]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                            dst[gq] = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const int n = nb + jj;
+                            if (n < p.N) {
+                                float o = __uint_as_float(v[jj]);
+                                if (add_bias) o += __ldg(p.bias + n);
+                                if (atomic) atomicAdd(crow + n, o);
+                                else crow[n] = p.accumulate ? crow[n] + o : o;
+                            }
                         }
                     }
+                }
+                if (more) {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = vn[jj];
                 }
             }
+            tc_fence_before();
+            mbar_arrive(tempty + 8 * buf);                  // this warp's share of the accumulator is drained
         }
     }
     tc_fence_before();
@@ -275,14 +332,26 @@ int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, in
 // b_mn = 0: B[n][k] = B[n*ldb + k]; 1: B[k*ldb + n].  lda, ldb multiples of 8 and base pointers 16-byte aligned (TMA;
 // a box may not start at an inner coordinate that is not a multiple of 16 bytes either -- the unit raises an
 // illegal-instruction fault -- so sub-matrix views are passed as offset POINTERS that keep this alignment).
+// norm_E > 0 (multiple of 8, <= 48, divides N; no accumulate): the epilogue l2-normalises every group of norm_E
+// consecutive output columns and writes the reciprocal norms to inv[M][N / norm_E] (amss_l2norm_fwd semantics).
 int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
-              int K, int accumulate, float* C, int ldc, int swapB, int swapT, cudaStream_t st) {
+              int K, int accumulate, float* C, int ldc, int swapB, int swapT, int norm_E, float* inv, cudaStream_t st) {
     if ((lda & 7) || (ldb & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) {
         set_error("gemm_bf16: operands must be 16-byte aligned with leading dimensions that are multiples of 8 (lda=%d ldb=%d)", lda, ldb);
         return AMSS_ERR_INVALID_ARG;
     }
     GtParams p;
-    p.tm = (M + GT_BM - 1) / GT_BM; p.tn = (N + GT_BN - 1) / GT_BN;
+    p.bn = GT_BN; p.norm_E = 0; p.inv = nullptr;
+    if (norm_E > 0) {
+        if ((norm_E & 7) || norm_E > GT_EMAX || N % norm_E || accumulate || !inv || (ldc & 3) ||
+            (reinterpret_cast<uintptr_t>(C) & 15)) {
+            set_error("gemm_bf16: fused l2-normalise needs norm_E %% 8 == 0, norm_E <= %d, N %% norm_E == 0, no accumulate (E=%d N=%d)",
+                      GT_EMAX, norm_E, N);
+            return AMSS_ERR_UNSUPPORTED;
+        }
+        p.bn = GT_BN / norm_E * norm_E; p.norm_E = norm_E; p.inv = inv;
+    }
+    p.tm = (M + GT_BM - 1) / GT_BM; p.tn = (N + p.bn - 1) / p.bn;
     p.KS = (K + GT_BK - 1) / GT_BK;
     int rc = make_operand_map(&p.mapA, A, M, K, lda, a_mn, GT_BM);
     if (rc != AMSS_OK) return rc;
@@ -293,7 +362,7 @@ int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, 
     p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.swapB = swapB; p.swapT = swapT;
     const int tiles = p.tm * p.tn;
     int ksplit = 1;
-    if (tiles < kNumSMs / 2 && p.KS >= 8) ksplit = std::max(1, std::min(kNumSMs / tiles, p.KS / 4));
+    if (tiles < kNumSMs / 2 && p.KS >= 8 && !norm_E) ksplit = std::max(1, std::min(kNumSMs / tiles, p.KS / 4));
     const int sper = (p.KS + ksplit - 1) / ksplit;
     ksplit = (p.KS + sper - 1) / sper;
     p.ksplit = ksplit;
@@ -324,7 +393,8 @@ int gemm_tc(const float* A, int lda, const float* B, int ldb, const float* bias,
     if (rc != AMSS_OK) return rc;
     rc = convert_bf16(B, br, bc, ldb, Bb, pad8(bc), st);
     if (rc != AMSS_OK) return rc;
-    return gemm_bf16(Ab, pad8(ac), transa ? 1 : 0, Bb, pad8(bc), transb ? 0 : 1, bias, M, N, K, accumulate, C, ldc, swapB, swapT, st);
+    return gemm_bf16(Ab, pad8(ac), transa ? 1 : 0, Bb, pad8(bc), transb ? 0 : 1, bias, M, N, K, accumulate, C, ldc, swapB, swapT, 0,
+                     nullptr, st);
 }
 
 }  // namespace amss

@@ -175,6 +175,42 @@ class _DenseFn(torch.autograd.Function):
         return dx, dW, db, None, None
 
 
+class _DenseNormFn(torch.autograd.Function):
+    """V = l2_normalize(x W + b) over groups of E output columns on the tensor-core path: the normalisation runs in the
+    GEMM epilogue (amss_gemm_bf16, norm_E), so the un-normalised [M,N] product is never written or re-read.
+    Returns (V, inv_norm).  The backward is the generic one (dV -> dz -> dx, dW, db); dpcl_loss() replaces it by
+    _HeadNormDPCLLossFn when the DPCL cost follows directly."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, E, swap):
+        if swap:
+            Bq, Tq = swap
+            x = ops.transpose_01(x.view(Tq, Bq, -1)).view(Bq * Tq, -1)
+        xb, Wb = ops.convert_bf16(x), ops.convert_bf16(W)
+        V, inv = ops.gemm_bf16(xb, False, Wb, True, x.shape[0], W.shape[1], W.shape[0], bias=b, norm_E=E)
+        ctx.save_for_backward(xb, Wb, V, inv)
+        ctx.E, ctx.swap, ctx.bf16_operands = E, swap, (xb, Wb)
+        ctx.mark_non_differentiable(inv)
+        return V, inv
+
+    @staticmethod
+    def backward(ctx, dV, _dinv):
+        xb, Wb, V, inv = ctx.saved_tensors
+        swap = ctx.swap
+        M, N = V.shape
+        K = Wb.shape[0]
+        dz = ops.l2norm_bwd(V, inv, dV.contiguous(), ctx.E)
+        dzb = ops.convert_bf16(dz)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_bf16(dzb, False, Wb, False, M, K, N, out_swap=(swap[1], swap[0]) if swap else None)
+        if ctx.needs_input_grad[1]:
+            dW = ops.gemm_bf16(xb, True, dzb, True, K, N, M)
+        if ctx.needs_input_grad[2]:
+            db = ops.colsum(dz)
+        return dx, dW, db, None, None
+
+
 class _L2NormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, E):
@@ -342,9 +378,10 @@ def blstm(x, kf, bf, kb, bb, precision=AMSS_PREC_FP32):
 def _carry(src, dst):
     """Views made by the layer protocol (Conv1D's [B,T,N] view, Reshape) keep the side-channel that lets dpcl_loss()
     fuse the head's backward with the loss (see _HeadNormDPCLLossFn)."""
-    h = getattr(src, "_amss_dense", None)
-    if h is not None:
-        dst._amss_dense = h
+    for attr in ("_amss_dense", "_amss_head"):
+        h = getattr(src, attr, None)
+        if h is not None:
+            setattr(dst, attr, h)
     return dst
 
 
@@ -358,6 +395,15 @@ def dense(x, W, b, precision=AMSS_PREC_FP32, swap=None):
     return y
 
 
+def dense_normalized(x, W, b, E, swap=None):
+    """l2_normalize(dense(x)) with the normalisation fused into the GEMM epilogue (tensor-core path only)."""
+    V, inv = _DenseNormFn.apply(x, W, b, E, swap)
+    if V.requires_grad:
+        xb, Wb = V.grad_fn.bf16_operands
+        V._amss_head = (x, W, b, xb, Wb, swap, inv)
+    return V
+
+
 def l2_normalize(z, E):
     v, inv = _L2NormFn.apply(z, E)
     if z.requires_grad:
@@ -365,10 +411,14 @@ def l2_normalize(z, E):
     return v
 
 
-def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32):
+def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32, head=None):
     """prenorm = (z, inv_norm) as stashed by l2_normalize() on its output: the loss becomes one autograd node
     on z with a fused backward (DPCL gradient + normalisation Jacobian).  On the tensor-core path, when z is the
     output of a dense layer, the node moves one step further up (onto the layer's x, W, b): _HeadNormDPCLLossFn."""
+    if head is not None and precision != AMSS_PREC_FP32 and S <= 4:
+        # V came out of dense_normalized(): (x, W, b, bf16 copies, swap, inv_norm)
+        x, W, b, xb, Wb, swap, inv = head
+        return _HeadNormDPCLLossFn.apply(x, W, b, xb, Wb, V.detach(), inv, labels, S, swap)
     if prenorm is not None:
         z, inv = prenorm
         head = getattr(z, "_amss_dense", None)
@@ -456,6 +506,18 @@ class Conv1D:
         else:
             y = dense(x.reshape(B * Tt, C), W, b, self.precision)
         return _carry(y, y.view(B, Tt, -1))
+
+    def f_prop_normalized(self, x, E):
+        """l2_normalize(f_prop(x)) over groups of E output channels (the Reshape + Normalize that follow the head in
+        models/dpcl.py:30-37), fused into the GEMM epilogue.  Tensor-core path only."""
+        B, Tt, C = x.shape
+        W, b = self.store[f"{self.scope}/W"], self.store[f"{self.scope}/b"]
+        xt = x.transpose(0, 1)
+        if xt.is_contiguous() and not x.is_contiguous():
+            V = dense_normalized(xt.reshape(Tt * B, C), W, b, E, swap=(B, Tt))
+        else:
+            V = dense_normalized(x.reshape(B * Tt, C), W, b, E)
+        return _carry(V, V.view(B, Tt, -1))
 
 
 class Reshape:

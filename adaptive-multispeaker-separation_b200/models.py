@@ -270,6 +270,12 @@ class Separator(Network):
     def prediction(self, X):
         """X [B,T,F] -> embeddings [B,T,F,E] (L2-normalised over E unless --no_normalize)."""
         B, Tt, Fb = X.shape
+        E, head = self.embedding_size, self.layers[-1]
+        if (self.normalize and self.precision != L.AMSS_PREC_FP32 and isinstance(head, L.Conv1D)
+                and E % 8 == 0 and E <= 48):
+            # tensor-core path: Reshape + Normalize run inside the head GEMM's epilogue
+            V = head.f_prop_normalized(L.f_props(self.layers[:-1], X), E)
+            return L._carry(V, V.view(B, Tt, Fb, E))
         z = L.f_props(self.layers, X)
         z = L.Reshape([B, Tt, Fb, self.embedding_size]).f_prop(z)
         return L.Normalize(3).f_prop(z) if self.normalize else z
@@ -344,7 +350,8 @@ class DPCL(Separator):
     def cost(self, V, labels, I=None):
         B, Tt, Fb, E = V.shape
         return L.dpcl_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), self.S,
-                           prenorm=getattr(V, "_amss_prenorm", None), precision=self.precision)
+                           prenorm=getattr(V, "_amss_prenorm", None), precision=self.precision,
+                           head=getattr(V, "_amss_head", None))
 
 
 class L41Model(Separator):

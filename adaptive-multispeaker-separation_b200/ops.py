@@ -196,9 +196,9 @@ def convert_bf16(x):
     return out
 
 
-def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, accumulate=False, out_swap=None):
+def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, accumulate=False, out_swap=None, norm_E=0):
     """C[M,N] (+)= A B from bf16 operands (see amss_gemm_bf16): a_mn False -> A [M,K]; True -> A stored [K,M];
-    b_mn True -> B [K,N]; False -> B stored [N,K]."""
+    b_mn True -> B [K,N]; False -> B stored [N,K].  norm_E > 0: returns (l2-normalised C, inv_norm[M*N/norm_E])."""
     for t in (A, B):
         if not t.is_cuda or t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.bfloat16:
             raise _lib.AmssError("gemm_bf16: operands must be 2-D bf16 CUDA tensors with unit inner stride")
@@ -206,9 +206,10 @@ def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, accumulate=False, 
         out = torch.empty(M, N, dtype=_f32, device=A.device)
         accumulate = False
     sb, st = (out_swap if out_swap else (0, 0))
+    inv = torch.empty(M * (N // norm_E), dtype=_f32, device=A.device) if norm_E else None
     _lib.call("amss_gemm_bf16", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(bias), M, N, K,
-              int(accumulate), _p(out), out.stride(0), sb, st, _stream())
-    return out
+              int(accumulate), _p(out), out.stride(0), sb, st, int(norm_E), _p(inv), _stream())
+    return (out, inv) if norm_E else out
 
 
 def blstm_fwd(x_tm, kernel_fw, bias_fw, kernel_bw, bias_bw, forget_bias=1.0, precision=AMSS_PREC_FP32,

@@ -159,10 +159,14 @@ int amss_gemm(const float* A, int lda, const float* B, int ldb, const float* bia
  * that are multiples of 8 and 16-byte aligned bases (TMA tensor maps are built over them):
  *   a_mn = 0: A is [M,K] (K contiguous);   a_mn = 1: A is stored [K,M] (dW = X^T dZ);
  *   b_mn = 1: B is [K,N] (N contiguous);   b_mn = 0: B is stored [N,K] (dX = dZ W^T).
+ * norm_E > 0 (multiple of 8, <= 48, divides N, accumulate = 0): the epilogue applies
+ * tf.nn.l2_normalize to every group of norm_E consecutive output columns (the embedding
+ * axis of [B,T,F,E], utils/ops.py:318-324) and writes inv_norm[M, N/norm_E] exactly as
+ * amss_l2norm_fwd does; the un-normalised product never reaches HBM.  norm_E = 0: plain.
  * Replaces the same reference ops as amss_gemm (utils/ops.py:501-503, :372-380).         */
 int amss_gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn,
                    const float* bias, int M, int N, int K, int accumulate, float* C, int ldc,
-                   int out_swap_b, int out_swap_t, void* stream);
+                   int out_swap_b, int out_swap_t, int norm_E, float* inv_norm, void* stream);
 /* fp32 [rows,cols] (ld) -> bf16 [rows,ldd], ldd % 8 == 0, columns >= cols zero filled.    */
 int amss_convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd,
                       void* stream);

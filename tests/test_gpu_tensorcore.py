@@ -104,6 +104,41 @@ def test_gemm_tc_matches_bf16_operand_product(ops, ta, tb, shape):
     assert rel(out, ref) < 1e-4          # fp32 accumulation of exact bf16 products
 
 
+@pytest.mark.parametrize("M,N,K,E", [(300, 1280, 600, 40), (77, 96, 50, 16), (129, 480, 64, 48), (260, 10240, 600, 40)])
+def test_gemm_bf16_fused_l2_normalize_epilogue(ops, M, N, K, E):
+    """amss_gemm_bf16 with norm_E: normalised rows and inv_norm equal l2_normalize(x W + b) over groups of E columns
+    (tf.nn.l2_normalize, utils/ops.py:323-324) computed from the same bf16 operands; one all-zero group exercises the
+    clamped branch (inv_norm stored negative, as amss_l2norm_fwd does)."""
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g) * 0.1
+    b = torch.randn(N, generator=g) * 0.1
+    W[:, E:2 * E] = 0.0
+    b[E:2 * E] = 0.0                                                   # group 1 is exactly zero
+    xb, Wb = ops.convert_bf16(dev(x)), ops.convert_bf16(dev(W))
+    assert xb.dtype == torch.bfloat16 and xb.shape[1] % 8 == 0
+    V, inv = ops.gemm_bf16(xb, False, Wb, True, M, N, K, bias=dev(b), norm_E=E)
+    z = bf16_round(x).double() @ bf16_round(W).double() + b.double()
+    zg = z.view(M, N // E, E)
+    ss = (zg * zg).sum(-1, keepdim=True)
+    ref = (zg / ss.clamp_min(1e-12).sqrt()).view(M, N)
+    assert rel(V, ref) < 1e-4
+    inv_ref = (1.0 / ss.clamp_min(1e-12).sqrt()).view(M, N // E)
+    inv_h = inv.view(M, N // E).double().cpu()
+    assert bool((inv_h[:, 1] < 0).all())                               # clamped group flagged
+    keep = torch.ones(N // E, dtype=torch.bool)
+    keep[1] = False
+    assert float(((inv_h - inv_ref)[:, keep].abs() / inv_ref[:, keep]).max()) < 1e-4
+    # plain bf16 GEMM through the same entry point, both operand majors
+    out = ops.gemm_bf16(xb, False, Wb, True, M, N, K, bias=dev(b))
+    assert rel(out, z) < 1e-4
+    dzb = ops.convert_bf16(dev(torch.randn(M, N, generator=g)))
+    dW = ops.gemm_bf16(xb, True, dzb, True, K, N, M)
+    assert rel(dW, bf16_round(x).double().t() @ dzb.double().cpu()[:, :N]) < 1e-4
+    dx = ops.gemm_bf16(dzb, False, Wb, False, M, K, N)
+    assert rel(dx, dzb.double().cpu()[:, :N] @ bf16_round(W).double().t()) < 1e-4
+
+
 def test_gemm_tc_strided_accumulate_swap(ops):
     g = torch.Generator().manual_seed(22)
     Tt, Bb, C, N = 50, 6, 40, 72
