@@ -25,8 +25,9 @@ int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, 
               int K, int accumulate, float* C, int ldc, int swapB, int swapT, int norm_E, float* inv, cudaStream_t st);
 int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gates, float* cst, float* y, int B, int T,
                      int H, float forget_bias, cudaStream_t st);
+int blstm_rec_bwd_tc_nsub(int B, int H);
 int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,
-                     const float* dy, float* dZ, int B, int T, int H, cudaStream_t st);
+                     const float* dy, float* dZ, uint16_t* dZb, int ldzb, float* dbpart, int B, int T, int H, cudaStream_t st);
 namespace {
 
 constexpr int RC_THREADS = 256;
@@ -366,9 +367,17 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
     const float* gates = (const float*)saved;
     const float* cst = (const float*)((const char*)saved + gates_bytes(B, T, H));
     const bool use_tc = precision == AMSS_PREC_BF16 && blstm_rec_tc_supported(B, T, H);
+    // Tensor-core recurrence: its writer warps emit dZ directly as the bf16 GEMM operand plus per-cluster column sums
+    // (the bias gradients), so the fp32 dZ, its conversion pass and the column-sum passes disappear.
+    int nsub = 0;
+    bool fused_dz = false;
     if (use_tc) {
-        int rc = blstm_rec_bwd_tc(kernel_fw + (size_t)I * 4 * H, kernel_bw + (size_t)I * 4 * H, 4 * H, gates, cst, dy, dZ, B,
-                                  T, H, st);
+        nsub = blstm_rec_bwd_tc_nsub(B, H);
+        fused_dz = 2 * nsub <= CS_CHUNKS;                 // the partials live in the column-sum scratch
+        const Bf16Scratch s0 = bf16_scratch(gws, B, T, I, H);
+        int rc = blstm_rec_bwd_tc(kernel_fw + (size_t)I * 4 * H, kernel_bw + (size_t)I * 4 * H, 4 * H, gates, cst, dy,
+                                  fused_dz ? nullptr : dZ, fused_dz ? s0.dzb : nullptr, s0.H4p, fused_dz ? (float*)gws : nullptr,
+                                  B, T, H, st);
         if (rc != AMSS_OK) return rc;
     } else {
     AMSS_CUDA(cudaMemsetAsync(bar, 0, 256, st));
@@ -395,7 +404,7 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
         s = bf16_scratch(gws, B, T, I, H);
         int rc = convert_bf16(x, T * B, I, I, s.xb, s.Ip, st);
         for (int d = 0; d < 2 && rc == AMSS_OK && T > 1; ++d) rc = convert_bf16(y + d * H, T * B, H, 2 * H, s.yb[d], s.Hp, st);
-        if (rc == AMSS_OK) rc = convert_bf16(dZ, 2 * T * B, H4, H4, s.dzb, s.H4p, st);
+        if (rc == AMSS_OK && !fused_dz) rc = convert_bf16(dZ, 2 * T * B, H4, H4, s.dzb, s.H4p, st);
         for (int d = 0; d < 2 && rc == AMSS_OK && dx; ++d) rc = convert_bf16(kern[d], I, H4, H4, s.wb[d], s.H4p, st);
         if (rc != AMSS_OK) return rc;
     }
@@ -423,7 +432,9 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
         } else {
             AMSS_CUDA(cudaMemsetAsync(dWh, 0, (size_t)H * H4 * 4, st));
         }
-        {
+        if (fused_dz) {
+            AMSS_LAUNCH(colsum_sum_kernel, (H4 + 255) / 256, 256, 0, st, (const float*)gws + (size_t)d * nsub * H4, nsub, H4, dbias[d]);
+        } else {
             dim3 cg((H4 + 31) / 32, CS_CHUNKS);
             AMSS_LAUNCH(colsum_chunk_kernel, cg, 256, 0, st, dZd, (int64_t)T * B, H4, (float*)gws);
             AMSS_LAUNCH(colsum_sum_kernel, (H4 + 255) / 256, 256, 0, st, (const float*)gws, CS_CHUNKS, H4, dbias[d]);

@@ -397,7 +397,10 @@ struct RecTcBwd {
     const float* gates;   // [2][T][B][4H] activated gates (saved by the forward pass)
     const float* cst;     // [2][T][B][H]
     const float* dy;      // [T][B][2H]
-    float* dZ;            // [2][T][B][4H]
+    float* dZ;            // [2][T][B][4H] fp32 (may be null when the bf16 copy + bias partials are requested instead)
+    uint16_t* dZb;        // [2][T][B][ldzb] bf16 copy for the weight / input-gradient GEMMs (optional)
+    int ldzb;
+    float* dbpart;        // [2][nsub][4H] per-cluster column sums of dZ = bias-gradient partials (optional)
     int B, T, H, nsub, MT;
 };
 
@@ -627,6 +630,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
                 }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sv_full + 8 * (n % 3)) : "memory");
         };
+        float bsum = 0.f;                                         // this thread's (gate, unit) column of dZ summed over t and b
         for (int n = 0; n < 3 && n < T; ++n) stage_sv(n);
         for (int s = T - 1; s >= 0; --s) {
             const int t = d == 0 ? s : T - 1 - s, n = T - 1 - s;
@@ -634,17 +638,25 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
             if (n + 3 < T) stage_sv(n + 3);                       // refill the slot just freed, three steps ahead
             const float* dzb = dzs + (n & 1) * (128 * ZP);
             if (wu < H) {
-                float* zo = p.dZ + (((size_t)d * T + t) * B + b0) * H4 + wq * H + wu;
+                const size_t r0 = ((size_t)d * T + t) * B + b0;
+                float* zo = p.dZ ? p.dZ + r0 * H4 + wq * H + wu : nullptr;
+                __nv_bfloat16* zb = p.dZb ? reinterpret_cast<__nv_bfloat16*>(p.dZb) + r0 * p.ldzb + wq * H + wu : nullptr;
 #pragma unroll
                 for (int c = 0; c < NB; c += 16) {
                     float gv[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) gv[j] = dzb[wt * ZP + c + j];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (c + j < nvalid) __stcg(zo + (size_t)(c + j) * H4, gv[j]);
+                    for (int j = 0; j < 16; ++j)
+                        if (c + j < nvalid) {
+                            if (zo) __stcg(zo + (size_t)(c + j) * H4, gv[j]);
+                            if (zb) zb[(size_t)(c + j) * p.ldzb] = __float2bfloat16_rn(gv[j]);
+                            bsum += gv[j];
+                        }
                 }
             }
         }
+        if (p.dbpart && wu < H) p.dbpart[((size_t)d * p.nsub + sub) * H4 + wq * H + wu] = bsum;
     }
     tc_fence_before();
     __syncthreads();
@@ -732,12 +744,16 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
     return launch_fwd<32>(p, NC, st);
 }
 
+// Sub-batches (clusters per direction) the backward recurrence will run with: sizes the bias-partial buffer.
+int blstm_rec_bwd_tc_nsub(int B, int H);
+
 int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,
-                     const float* dy, float* dZ, int B, int T, int H, cudaStream_t st) {
+                     const float* dy, float* dZ, uint16_t* dZb, int ldzb, float* dbpart, int B, int T, int H, cudaStream_t st) {
     const int NC = (H + 31) / 32;
     RecTcBwd p;
     p.prof = g_prof_bwd;
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.dy = dy; p.dZ = dZ;
+    p.dZb = dZb; p.ldzb = ldzb; p.dbpart = dbpart;
     p.B = B; p.T = T; p.H = H; p.MT = (NC * 32 + 127) / 128;
     static int maxc_cache[17] = {0};
     if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
@@ -745,6 +761,14 @@ int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const floa
     p.nsub = (B + nb - 1) / nb;
     if (nb == 16) return launch_bwd<16>(p, NC, st);
     return launch_bwd<32>(p, NC, st);
+}
+
+int blstm_rec_bwd_tc_nsub(int B, int H) {
+    const int NC = (H + 31) / 32;
+    static int maxc_cache[17] = {0};
+    if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
+    const int nb = pick_nb(B, maxc_cache[NC], 32);
+    return (B + nb - 1) / nb;
 }
 
 }  // namespace amss

@@ -18,21 +18,31 @@
 #include "tc.cuh"
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 
 namespace amss {
 namespace {
 
 using namespace tc;
 
-constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 64, GT_STAGES = 4;
+constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 64;
 constexpr int GT_THREADS = 320;                      // warp 0 loader, 1 MMA (+TMEM alloc), 2-9 epilogue
-constexpr int GT_A_BYTES = GT_BM * GT_BK * 2, GT_B_BYTES = GT_BN * GT_BK * 2;
-constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
+constexpr int GT_A_BYTES = GT_BM * GT_BK * 2;
+// CTAS = 1: a CTA owns a 128 x 256 tile (B stage 32 KB, 4 stages).  CTAS = 2: a CTA PAIR (cluster of 2, cta_group::2)
+// owns a 256 x 256 tile; each CTA stages its own 128 rows of A and HALF of B (16 KB) and the pair's MMA reads both
+// halves -> a third less L2 -> SM operand traffic per flop, which is what bounds these GEMMs; 6 stages.
+template <int CTAS> struct GtCfg {
+    static constexpr int B_ROWS = GT_BN / CTAS;
+    static constexpr int B_BYTES = B_ROWS * GT_BK * 2;
+    static constexpr int STAGE_BYTES = GT_A_BYTES + B_BYTES;
+    static constexpr int STAGES = CTAS == 1 ? 4 : 6;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;   // + slack to align the ring to the 1024-B swizzle atom
+};
+constexpr int GT_MAX_STAGES = 6;
 constexpr int GT_EMAX = 48;                         // widest l2-normalised group the fused epilogue handles
-constexpr int GT_SMEM = GT_STAGES * GT_STAGE_BYTES + 1024;   // + slack to align the ring to the 1024-B swizzle atom
 
 struct GtParams {
-    CUtensorMap mapA, mapB;
+    CUtensorMap mapA, mapB;           // mapB box: 256 rows (CTAS = 1) or 128 rows (CTAS = 2) for a K-major B
     const float* bias;
     float* C;
     float* inv;                       // norm_E > 0: [M][N / norm_E] reciprocal norms
@@ -68,6 +78,43 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: both CTAs of the pair issue the loads, completion lands on the LEADER's (even
+// rank) barrier -- a shared::cluster address with the pair-rank bit cleared; only the leader issues MMAs and commits.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar & kPeerMask)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t result_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(result_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ uint32_t pair_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pair_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // E (multiple of 8, <= GT_EMAX) accumulator columns of this thread's row -> registers (no wait)
 __device__ __forceinline__ void load_group(uint32_t taddr, int E, uint32_t (&dst)[GT_EMAX]) {
 #pragma unroll
@@ -75,64 +122,78 @@ __device__ __forceinline__ void load_group(uint32_t taddr, int E, uint32_t (&dst
         if (c * 8 < E) tmem_ld8(taddr + c * 8, &dst[c * 8]);
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GtParams p) {
+template <int CTAS>
+__device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
+    using Cfg = GtCfg<CTAS>;
+    constexpr int GT_STAGES = Cfg::STAGES, GT_STAGE_BYTES = Cfg::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bars[2 * GT_STAGES + 4];
+    __shared__ __align__(8) uint64_t bars[2 * GT_MAX_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = CTAS == 2 ? pair_rank() : 0u;            // 0 = leader of the pair
     const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[GT_STAGES]);
     const uint32_t tfull = smem_u32(&bars[2 * GT_STAGES]), tempty = tfull + 16;
     if (tid == 0) {
+        // full: the leader's arrive.expect_tx (covers the bytes of both CTAs of a pair); empty / tfull: one
+        // tcgen05.commit; tempty: one arrival per epilogue warp of every CTA of the pair
         for (int s = 0; s < GT_STAGES; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull + 8 * b, 1); mbar_init(tempty + 8 * b, 256); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull + 8 * b, 1); mbar_init(tempty + 8 * b, 8 * CTAS); }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    if (warp == 1) { if (CTAS == 2) tmem_alloc_pair(smem_u32(&tmem_base_s), 512); else tmem_alloc(smem_u32(&tmem_base_s), 512); }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) pair_sync(); else __syncthreads();              // barriers of BOTH CTAs initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const int items = p.tm * p.tn * p.ksplit;
+    const int first = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int stride = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int hb = p.bn / CTAS;                                    // B rows (output columns) staged by one CTA
 
     if (warp == 0) {
         // ---------------- loader: TMA box loads, one lane ----------------
         if (lane == 0) {
             uint32_t g = 0;
-            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+                if (CTAS == 2) tma_load_2d_pair(dst, map, c0, c1, bar); else tma_load_2d(dst, map, c0, c1, bar);
+            };
+            for (int it = first; it < items; it += stride) {
                 const int split = it % p.ksplit, tile = it / p.ksplit;
-                const int n0 = (tile % p.tn) * p.bn, m0 = (tile / p.tn) * GT_BM;
+                const int n0 = (tile % p.tn) * p.bn + (int)rank * hb;                    // this CTA's share of B
+                const int m0 = (tile / p.tn) * (GT_BM * CTAS) + (int)rank * GT_BM;       // this CTA's rows of A
                 const int sbeg = split * p.sper, send = min(p.KS, sbeg + p.sper);
                 for (int j = sbeg; j < send; ++j, ++g) {
                     const uint32_t slot = g % GT_STAGES, ph = (g / GT_STAGES) & 1;
                     mbar_wait(empty + 8 * slot, ph ^ 1);
                     const uint32_t sa = smem_u32(smem + slot * GT_STAGE_BYTES), sb = sa + GT_A_BYTES;
                     const uint32_t bar = full + 8 * slot;
-                    mbar_expect_tx(bar, GT_STAGE_BYTES);
+                    if (rank == 0) mbar_expect_tx(bar, GT_STAGE_BYTES * CTAS);
                     const int ka = j * GT_BK, kb = ka;
-                    if (!p.a_mn) tma_load_2d(sa, &p.mapA, ka, m0, bar);
+                    if (!p.a_mn) load(sa, &p.mapA, ka, m0, bar);
                     else {
 #pragma unroll
-                        for (int i = 0; i < GT_BM / 64; ++i) tma_load_2d(sa + i * 8192, &p.mapA, m0 + i * 64, ka, bar);
+                        for (int i = 0; i < GT_BM / 64; ++i) load(sa + i * 8192, &p.mapA, m0 + i * 64, ka, bar);
                     }
-                    if (!p.b_mn) tma_load_2d(sb, &p.mapB, kb, n0, bar);
+                    if (!p.b_mn) load(sb, &p.mapB, kb, n0, bar);
                     else {
 #pragma unroll
-                        for (int i = 0; i < GT_BN / 64; ++i) tma_load_2d(sb + i * 8192, &p.mapB, n0 + i * 64, kb, bar);
+                        for (int i = 0; i < Cfg::B_ROWS / 64; ++i) load(sb + i * 8192, &p.mapB, n0 + i * 64, kb, bar);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer (converged loop, elected lane) ----------------
-        const uint32_t idesc = idesc_bf16(GT_BM, p.bn, p.a_mn, p.b_mn);
+      if (rank == 0) {
+        // ---------------- MMA issuer (converged loop, elected lane; the leader CTA of a pair) ----------------
+        const uint32_t idesc = idesc_bf16(GT_BM * CTAS, p.bn, p.a_mn, p.b_mn);
         // K-major: 8-row groups 1024 B apart, K step of 16 = +32 B inside the 128-B swizzle row.
         // MN-major: 8-k groups 1024 B apart (SBO), 64-wide mn atoms 8192 B apart (LBO), K step of 16 = +2048 B.
         const uint32_t a_step = p.a_mn ? 2048u : 32u, a_lbo = p.a_mn ? 8192u : 16u;
         const uint32_t b_step = p.b_mn ? 2048u : 32u, b_lbo = p.b_mn ? 8192u : 16u;
         const bool leader = elect_one();
         uint32_t g = 0, ti = 0;
-        for (int it = blockIdx.x; it < items; it += gridDim.x, ++ti) {
+        for (int it = first; it < items; it += stride, ++ti) {
             const int split = it % p.ksplit;
             const int sbeg = split * p.sper, send = min(p.KS, sbeg + p.sper);
             const uint32_t buf = ti & 1, tph = (ti >> 1) & 1;
@@ -148,12 +209,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
                 for (int kk = 0; kk < GT_BK / 16; ++kk) {
                     const uint64_t ad = smem_desc_sw128(sa + kk * a_step, a_lbo, 1024);
                     const uint64_t bd = smem_desc_sw128(sb + kk * b_step, b_lbo, 1024);
-                    if (leader) mma_bf16(dcol, ad, bd, idesc, !(j == sbeg && kk == 0));
+                    if (leader) { if (CTAS == 2) mma_bf16_pair(dcol, ad, bd, idesc, !(j == sbeg && kk == 0)); else mma_bf16(dcol, ad, bd, idesc, !(j == sbeg && kk == 0)); }
                 }
-                if (leader) mma_commit(empty + 8 * slot);
+                if (leader) { if (CTAS == 2) mma_commit_pair(empty + 8 * slot); else mma_commit(empty + 8 * slot); }
             }
-            if (leader) mma_commit(tfull + 8 * buf);
+            if (leader) { if (CTAS == 2) mma_commit_pair(tfull + 8 * buf); else mma_commit(tfull + 8 * buf); }
         }
+      }
     } else {
         // ---------------- epilogue: warps 2..9; TMEM lane quadrant = warp % 4, two warps per quadrant ----------------
         // A thread owns one accumulator row (TMEM lane) and stores 128..192 contiguous bytes of it per chunk.  The
@@ -165,9 +227,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         const bool atomic = p.ksplit > 1;
         const int E = p.norm_E;
         uint32_t ti = 0;
-        for (int it = blockIdx.x; it < items; it += gridDim.x, ++ti) {
+        auto release = [&](uint32_t bar) {                  // one arrival per warp on the (leader's) tempty barrier
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(bar); else mbar_arrive(bar); }
+        };
+        for (int it = first; it < items; it += stride, ++ti) {
             const int split = it % p.ksplit, tile = it / p.ksplit;
-            const int n0 = (tile % p.tn) * p.bn, m0 = (tile / p.tn) * GT_BM;
+            const int n0 = (tile % p.tn) * p.bn, m0 = (tile / p.tn) * (GT_BM * CTAS) + (int)rank * GT_BM;
             const uint32_t buf = ti & 1, tph = (ti >> 1) & 1;
             mbar_wait(tfull + 8 * buf, tph);
             tc_fence_after();
@@ -212,8 +279,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
                         p.inv[row * ngr + nb / E] = (ss >= 1e-12f) ? inv : -inv;
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(tempty + 8 * buf);              // this warp's share of the accumulator is drained
+                release(tempty + 8 * buf);                  // this warp's share of the accumulator is drained
                 continue;
             }
             const int chunks = (min(GT_BN, p.N - n0) + 31) >> 5;
@@ -257,13 +323,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
                     for (int jj = 0; jj < 32; ++jj) v[jj] = vn[jj];
                 }
             }
-            tc_fence_before();
-            mbar_arrive(tempty + 8 * buf);                  // this warp's share of the accumulator is drained
+            release(tempty + 8 * buf);                      // this warp's share of the accumulator is drained
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (CTAS == 2) pair_sync(); else __syncthreads();              // both CTAs done with each other's barriers / TMEM
+    if (warp == 1) { if (CTAS == 2) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512); }
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GtParams p) { gemm_tc_body<1>(p); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ GtParams p) {
+    gemm_tc_body<2>(p);
 }
 
 __global__ void zero_rows_kernel(float* C, int M, int N, int ldc) {
@@ -351,18 +421,21 @@ int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, 
         }
         p.bn = GT_BN / norm_E * norm_E; p.norm_E = norm_E; p.inv = inv;
     }
-    p.tm = (M + GT_BM - 1) / GT_BM; p.tn = (N + p.bn - 1) / p.bn;
+    // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles; AMSS_GEMM_CTAS=1 forces single CTAs (debug)
+    static const int forced = [] { const char* e = getenv("AMSS_GEMM_CTAS"); return e ? atoi(e) : 0; }();
+    const int ctas = forced == 1 ? 1 : (forced == 2 ? 2 : (M > GT_BM ? 2 : 1));
+    p.tm = (M + GT_BM * ctas - 1) / (GT_BM * ctas); p.tn = (N + p.bn - 1) / p.bn;
     p.KS = (K + GT_BK - 1) / GT_BK;
     int rc = make_operand_map(&p.mapA, A, M, K, lda, a_mn, GT_BM);
     if (rc != AMSS_OK) return rc;
-    rc = make_operand_map(&p.mapB, B, N, K, ldb, b_mn, GT_BN);
+    rc = make_operand_map(&p.mapB, B, N, K, ldb, b_mn, GT_BN / ctas);
     if (rc != AMSS_OK) return rc;
     p.a_mn = a_mn; p.b_mn = b_mn;
     p.bias = bias; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.swapB = swapB; p.swapT = swapT;
-    const int tiles = p.tm * p.tn;
+    const int tiles = p.tm * p.tn, slots = kNumSMs / ctas;      // concurrently running tiles
     int ksplit = 1;
-    if (tiles < kNumSMs / 2 && p.KS >= 8 && !norm_E) ksplit = std::max(1, std::min(kNumSMs / tiles, p.KS / 4));
+    if (tiles < slots / 2 && p.KS >= 8 && !norm_E) ksplit = std::max(1, std::min(slots / tiles, p.KS / 4));
     const int sper = (p.KS + ksplit - 1) / ksplit;
     ksplit = (p.KS + sper - 1) / sper;
     p.ksplit = ksplit;
@@ -371,9 +444,14 @@ int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, 
         const int64_t n = (int64_t)M * N;
         AMSS_LAUNCH(zero_rows_kernel, (int)std::min<int64_t>((n + 255) / 256, 8 * kNumSMs), 256, 0, st, C, M, N, ldc);
     }
-    AMSS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
-    const int grid = std::min(tiles * ksplit, kNumSMs);
-    AMSS_LAUNCH(gemm_tc_kernel, grid, GT_THREADS, GT_SMEM, st, p);
+    const int grid = std::min(tiles * ksplit, slots) * ctas;
+    if (ctas == 2) {
+        AMSS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GtCfg<2>::SMEM));
+        AMSS_LAUNCH(gemm_tc_pair_kernel, grid, GT_THREADS, GtCfg<2>::SMEM, st, p);
+    } else {
+        AMSS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GtCfg<1>::SMEM));
+        AMSS_LAUNCH(gemm_tc_kernel, grid, GT_THREADS, GtCfg<1>::SMEM, st, p);
+    }
     return AMSS_OK;
 }
 
