@@ -28,6 +28,8 @@ using namespace tc;
 constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 64;
 constexpr int GT_THREADS = 320;                      // warp 0 loader, 1 MMA (+TMEM alloc), 2-9 epilogue
 constexpr int GT_A_BYTES = GT_BM * GT_BK * 2;
+constexpr int GT_EMAX = 48;                         // widest l2-normalised group the fused epilogue handles
+constexpr int GT_STG_BYTES = 32 * GT_EMAX * 4;      // one warp's staging block: 32 rows x (32 | E) fp32 columns
 // CTAS = 1: a CTA owns a 128 x 256 tile (B stage 32 KB, 4 stages).  CTAS = 2: a CTA PAIR (cluster of 2, cta_group::2)
 // owns a 256 x 256 tile; each CTA stages its own 128 rows of A and HALF of B (16 KB) and the pair's MMA reads both
 // halves -> a third less L2 -> SM operand traffic per flop, which is what bounds these GEMMs; 6 stages.
@@ -35,13 +37,15 @@ template <int CTAS> struct GtCfg {
     static constexpr int B_ROWS = GT_BN / CTAS;
     static constexpr int B_BYTES = B_ROWS * GT_BK * 2;
     static constexpr int STAGE_BYTES = GT_A_BYTES + B_BYTES;
-    static constexpr int STAGES = CTAS == 1 ? 4 : 6;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;   // + slack to align the ring to the 1024-B swizzle atom
+    static constexpr int STAGES = CTAS == 1 ? 3 : 5;
+    // ring + per-epilogue-warp output staging (TMA stores) + slack to align everything to the 1024-B swizzle atom
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 8 * GT_STG_BYTES + 1024;
 };
 constexpr int GT_MAX_STAGES = 6;
-constexpr int GT_EMAX = 48;                         // widest l2-normalised group the fused epilogue handles
 
 struct GtParams {
+    CUtensorMap mapC;                 // fp32 output, box {32 cols, 32 rows} SWIZZLE_128B (plain) or {norm_E, 32} (fused normalise)
+    int c_tma;                        // 1: the epilogue stores / reduces through mapC; 0: direct per-thread stores (row remap, odd ldc)
     CUtensorMap mapA, mapB;           // mapB box: 256 rows (CTAS = 1) or 128 rows (CTAS = 2) for a K-major B
     const float* bias;
     float* C;
@@ -114,6 +118,21 @@ __device__ __forceinline__ uint32_t pair_rank() { uint32_t r; asm volatile("mov.
 __device__ __forceinline__ void pair_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+
+// shared -> global tile store / fp32 add-reduce through a tensor map (rows and columns outside the tensor are clipped)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src, bool add) {
+    if (add)
+        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+                     "r"(c1), "r"(src)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+                     "r"(src)
+                     : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // E (multiple of 8, <= GT_EMAX) accumulator columns of this thread's row -> registers (no wait)
 __device__ __forceinline__ void load_group(uint32_t taddr, int E, uint32_t (&dst)[GT_EMAX]) {
@@ -226,6 +245,13 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                             ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         const bool atomic = p.ksplit > 1;
         const int E = p.norm_E;
+        // Output through TMA: the warp re-tiles its 32 rows x (32 | E) columns in a private shared-memory block and one
+        // lane issues a tile store (or fp32 add-reduce for accumulate / split-K).  Stores straight from the
+        // row-per-thread registers touch 32 half-used sectors per instruction and saturate the L1TEX / L2 store path.
+        const bool ctma = p.c_tma != 0;
+        uint8_t* stg = smem + GT_STAGES * GT_STAGE_BYTES + (warp - 2) * GT_STG_BYTES;
+        const uint32_t stg_u32 = smem_u32(stg);
+        const bool c_add = atomic || p.accumulate;
         uint32_t ti = 0;
         auto release = [&](uint32_t bar) {                  // one arrival per warp on the (leader's) tempty barrier
             tc_fence_before();
@@ -269,7 +295,20 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                             for (int e = 0; e < 4; ++e) ss = fmaf(__uint_as_float(v[4 * c + e]), __uint_as_float(v[4 * c + e]), ss);
                         }
                     const float inv = rsqrtf(fmaxf(ss, 1e-12f));
-                    if (m < p.M) {
+                    if (ctma) {
+                        if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the block
+                        __syncwarp();
+                        float4* dst = reinterpret_cast<float4*>(stg + lane * E * 4);
+#pragma unroll
+                        for (int c = 0; c < GT_EMAX / 4; ++c)
+                            if (c < e4)
+                                dst[c] = make_float4(__uint_as_float(v[4 * c]) * inv, __uint_as_float(v[4 * c + 1]) * inv,
+                                                     __uint_as_float(v[4 * c + 2]) * inv, __uint_as_float(v[4 * c + 3]) * inv);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&p.mapC, nb, m0 + q * 32, stg_u32, false);
+                        if (m < p.M) p.inv[row * ngr + nb / E] = (ss >= 1e-12f) ? inv : -inv;
+                    } else if (m < p.M) {
                         float4* dst = reinterpret_cast<float4*>(crow + nb);
 #pragma unroll
                         for (int c = 0; c < GT_EMAX / 4; ++c)
@@ -290,7 +329,24 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                 const bool more = ci + 2 < chunks;
                 if (more) tmem_ld32(tacc + (ci + 2) * 32, vn);
                 const int nb = n0 + ci * 32;
-                if (m < p.M) {
+                if (ctma) {
+                    if (lane == 0) tma_store_wait_read();           // the previous store has finished reading the block
+                    __syncwarp();
+#pragma unroll
+                    for (int gq = 0; gq < 8; ++gq) {
+                        float4 o = make_float4(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1]),
+                                               __uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3]));
+                        if (add_bias && nb + 4 * gq + 4 <= p.N) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + gq);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        }
+                        // 128-byte rows, SWIZZLE_128B: 16-byte chunk gq of row r sits at chunk gq ^ (r & 7)
+                        *reinterpret_cast<float4*>(stg + lane * 128 + ((gq ^ (lane & 7)) << 4)) = o;
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&p.mapC, nb, m0 + q * 32, stg_u32, c_add);
+                } else if (m < p.M) {
                     if (!atomic && vec_ok && nb + 32 <= p.N) {
                         float4* dst = reinterpret_cast<float4*>(crow + nb);
 #pragma unroll
@@ -325,6 +381,7 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
             }
             release(tempty + 8 * buf);                      // this warp's share of the accumulator is drained
         }
+        if (ctma && lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     if (CTAS == 2) pair_sync(); else __syncthreads();              // both CTAs done with each other's barriers / TMEM
@@ -371,6 +428,19 @@ int make_operand_map(CUtensorMap* m, const uint16_t* src, int R, int K, int ld, 
         set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for R=%d K=%d ld=%d mn=%d", (int)rc, R, K, ld, mn);
         return AMSS_ERR_CUDA;
     }
+    return AMSS_OK;
+}
+
+// fp32 output C[M][N] (ldc): box {bw columns, 32 rows}; 128-byte rows are swizzled (conflict-free staging writes)
+int make_c_map(CUtensorMap* m, float* C, int M, int N, int ldc, int bw) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver"); return AMSS_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}, strides[1] = {(cuuint64_t)ldc * 4};
+    cuuint32_t box[2] = {(cuuint32_t)bw, 32}, es[2] = {1, 1};
+    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            bw == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) for C M=%d N=%d ldc=%d", (int)rc, M, N, ldc); return AMSS_ERR_CUDA; }
     return AMSS_OK;
 }
 
@@ -430,6 +500,12 @@ int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, 
     if (rc != AMSS_OK) return rc;
     rc = make_operand_map(&p.mapB, B, N, K, ldb, b_mn, GT_BN / ctas);
     if (rc != AMSS_OK) return rc;
+    p.c_tma = swapB == 0 && (ldc & 3) == 0 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+    if (p.c_tma) {
+        rc = make_c_map(&p.mapC, C, M, N, ldc, norm_E > 0 ? norm_E : 32);
+        if (rc != AMSS_OK) return rc;
+    }
     p.a_mn = a_mn; p.b_mn = b_mn;
     p.bias = bias; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.swapB = swapB; p.swapT = swapT;
