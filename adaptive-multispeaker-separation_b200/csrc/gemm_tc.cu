@@ -321,7 +321,7 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                 release(tempty + 8 * buf);                  // this warp's share of the accumulator is drained
                 continue;
             }
-            const int chunks = (min(GT_BN, p.N - n0) + 31) >> 5;
+            const int chunks = (min(p.bn, p.N - n0) + 31) >> 5;
             uint32_t v[32], vn[32];
             if (half < chunks) { tmem_ld32(tacc + half * 32, v); tmem_ld_wait(); }
 #pragma unroll 1
@@ -329,7 +329,7 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                 const bool more = ci + 2 < chunks;
                 if (more) tmem_ld32(tacc + (ci + 2) * 32, vn);
                 const int nb = n0 + ci * 32;
-                if (ctma) {
+                if (ctma && ci * 32 + 32 <= p.bn) {                 // (a chunk cut by the tile edge takes the direct path)
                     if (lane == 0) tma_store_wait_read();           // the previous store has finished reading the block
                     __syncwarp();
 #pragma unroll
@@ -347,7 +347,8 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                     __syncwarp();
                     if (lane == 0) tma_store_2d(&p.mapC, nb, m0 + q * 32, stg_u32, c_add);
                 } else if (m < p.M) {
-                    if (!atomic && vec_ok && nb + 32 <= p.N) {
+                    const int nend = min(p.N, n0 + p.bn);
+                    if (!atomic && vec_ok && nb + 32 <= nend) {
                         float4* dst = reinterpret_cast<float4*>(crow + nb);
 #pragma unroll
                         for (int gq = 0; gq < 8; ++gq) {
@@ -364,7 +365,7 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) {
                             const int n = nb + jj;
-                            if (n < p.N) {
+                            if (n < nend) {
                                 float o = __uint_as_float(v[jj]);
                                 if (add_bias) o += __ldg(p.bias + n);
                                 if (atomic) atomicAdd(crow + n, o);
@@ -491,7 +492,14 @@ int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, 
         }
         p.bn = GT_BN / norm_E * norm_E; p.norm_E = norm_E; p.inv = inv;
     }
-    // CTA pairs (256-row tiles) whenever there are at least two 128-row tiles; AMSS_GEMM_CTAS=1 forces single CTAs (debug)
+    // Tile shape.  Columns: the fewest tiles of at most 256 columns, each a multiple of 32 wide (whole 32-column TMA store
+    // boxes; N = 600 -> 3 x 224 instead of 3 x 256: the MMA work follows the tile, not N).  Rows: CTA pairs (256-row
+    // tiles, a third less operand traffic per flop) whenever there is more than one 128-row tile; measured faster than
+    // single CTAs even at M = 600 (768 padded rows).  AMSS_GEMM_CTAS=1|2 forces the choice (debug).
+    if (!norm_E) {
+        const int nt = (N + GT_BN - 1) / GT_BN;
+        p.bn = std::min(GT_BN, ((N + nt - 1) / nt + 31) & ~31);
+    }
     static const int forced = [] { const char* e = getenv("AMSS_GEMM_CTAS"); return e ? atoi(e) : 0; }();
     const int ctas = forced == 1 ? 1 : (forced == 2 ? 2 : (M > GT_BM ? 2 : 1));
     p.tm = (M + GT_BM * ctas - 1) / (GT_BM * ctas); p.tn = (N + p.bn - 1) / p.bn;
@@ -510,8 +518,17 @@ int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, 
     p.bias = bias; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.swapB = swapB; p.swapT = swapT;
     const int tiles = p.tm * p.tn, slots = kNumSMs / ctas;      // concurrently running tiles
+    // split-K against wave quantisation: items = tiles * ksplit run `slots` at a time; take the split with the best
+    // occupancy of the last wave (each extra split costs one more add-reduce pass over C, hence the small penalty)
     int ksplit = 1;
-    if (tiles < slots / 2 && p.KS >= 8 && !norm_E) ksplit = std::max(1, std::min(slots / tiles, p.KS / 4));
+    if (p.KS >= 8 && !norm_E && tiles < 4 * slots) {
+        double best = 0.0;
+        for (int ks = 1; ks <= std::min(p.KS / 4, 32); ++ks) {
+            const int items = tiles * ks, waves = (items + slots - 1) / slots;
+            const double eff = (double)items / ((double)waves * slots) - 0.004 * (ks - 1);
+            if (eff > best + 1e-9) { best = eff; ksplit = ks; }
+        }
+    }
     const int sper = (p.KS + ksplit - 1) / ksplit;
     ksplit = (p.KS + sper - 1) / sper;
     p.ksplit = ksplit;

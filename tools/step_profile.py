@@ -44,7 +44,7 @@ def main():
     for name, us in sorted(tot.items(), key=lambda kv: -kv[1])[:40]:
         print(f"{us / a.steps / 1e3:8.3f} ms/step  {cnt[name] / a.steps:6.1f} launches/step  {name[:110]}")
     # the individual launches of the GEMM kernel, in order (which shape is slow?)
-    g = [ev.device_time for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "gemm_tc_kernel" in ev.name]
+    g = [ev.device_time for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "gemm_tc" in ev.name]
     per = len(g) // a.steps
     print("gemm_tc launches of the last step (us):", " ".join(f"{x:.0f}" for x in g[-per:]))
 
