@@ -21,18 +21,20 @@ M = T * B
 h = torch.randn(M, 600, device="cuda")
 W = torch.randn(600, 10240, device="cuda") * 0.05
 bias = torch.zeros(10240, device="cuda")
-z = ops.gemm(h, W, bias, precision=P)                       # head fwd
-dz = torch.randn_like(z)
-ops.gemm(h, dz, None, transa=True, precision=P)             # head dW
-ops.gemm(dz, W, None, transb=True, precision=P)             # head dH
+hb, Wb = ops.convert_bf16(h), ops.convert_bf16(W)
+V, inv = ops.gemm_bf16(hb, False, Wb, True, M, 10240, 600, bias=bias, norm_E=40)      # head fwd + fused l2-normalise
+dzb = ops.convert_bf16(torch.randn(M, 10240, device="cuda"))
+ops.gemm_bf16(hb, True, dzb, True, 600, 10240, M)                                     # head dW (split-K, add-reduce stores)
+ops.gemm_bf16(dzb, False, Wb, False, M, 600, 10240)                                   # head dH
+ops.gemm_bf16(hb, False, ops.convert_bf16(torch.randn(600, 1200, device="cuda")), True, M, 1200, 600)   # BLSTM in-proj
 xt = torch.randn(T, B, 600, device="cuda") * 0.1
 kf = torch.randn(900, 1200, device="cuda") * 0.05
 bf = torch.zeros(1200, device="cuda")
 y, saved = ops.blstm_fwd(xt, kf, bf, kf, bf, precision=P)
 ops.blstm_bwd(xt, kf, kf, y, torch.randn_like(y), saved, precision=P)
-V = torch.nn.functional.normalize(torch.randn(B, 64000, 40, device="cuda"), dim=-1)
 lab = torch.randint(0, 2, (B, 64000), device="cuda", dtype=torch.uint8)
-loss, ws = ops.dpcl_loss_fwd(V, lab, 2)
-ops.dpcl_loss_bwd(V, lab, 2, torch.ones(1, device="cuda"), ws)
+Vn, invn = ops.l2norm_fwd(torch.randn(B, 64000, 40, device="cuda"), 40)
+loss, ws = ops.dpcl_loss_fwd(Vn, lab, 2, P)                                           # tcgen05 Gram
+ops.dpcl_loss_bwd_normalized_bf16(Vn, lab, 2, torch.ones(1, device="cuda"), ws, invn)  # fused DPCL + l2norm backward, bf16 dz
 torch.cuda.synchronize()
 print("done")
