@@ -371,6 +371,25 @@ def wave_stats(target, approx):
     return _WaveLossFn.apply(target, approx)
 
 
+def pit_wave_l2(x_non_mix, est):
+    """cost_finetuning (models/network.py:697-723, models/adapt.py:404-431): 0.5 * sum_L (x_s - xhat_perm(s))^2, mean
+    over the S sources, min over the S! permutations, mean over the batch.  The S*S pairwise squared distances come
+    from S launches of the fused waveform-statistics kernel (pair s with estimate (s+k) mod S); the permutation
+    min/mean runs on the [B,S,S] table.  Gradient flows to `est` through the kernel's autograd wrapper."""
+    import itertools
+    B, S, Lw = x_non_mix.shape
+    tgt = x_non_mix.reshape(B * S, Lw).contiguous()
+    d = []
+    for k in range(S):
+        idx = [(sidx + k) % S for sidx in range(S)]
+        e = (est if k == 0 else est[:, idx]).reshape(B * S, Lw).contiguous()
+        d.append(0.5 * wave_stats(tgt, e)[:, 3].reshape(B, S))
+    D = torch.stack(d, 2)                                    # D[b, s, k] = 0.5 * |x[b,s] - est[b,(s+k)%S]|^2
+    costs = [torch.stack([D[:, sidx, (perm[sidx] - sidx) % S] for sidx in range(S)], 1).mean(1)
+             for perm in itertools.permutations(range(S))]
+    return torch.stack(costs, 1).min(1).values.mean()
+
+
 def blstm(x, kf, bf, kb, bb, precision=AMSS_PREC_FP32):
     return _BLSTMFn.apply(x, kf, bf, kb, bb, precision)
 

@@ -205,6 +205,11 @@ class Adapt(Network):
         return cost, {"y": y, "argmax": am, "back": back, "l2": l2, "sdr": sdr, "sdr_improvement": val,
                       "sparse_constraint": sparse, "overlapping": overlapping, "p_hat": p_hat}
 
+    # adapt.py:404-431
+    def cost_finetuning(self, x_non_mix, back):
+        """PIT waveform loss of the end-to-end fine-tuning recipes: back [B,S,L] = self.back(sepNet output)."""
+        return L.pit_wave_l2(x_non_mix, back)
+
     def connect_front(self, separator_class, **extra):
         """adapt.py:440-441 -- plug a Separator subclass on the front output (plugged=True)."""
         args = dict(self.args)
@@ -335,6 +340,11 @@ class Separator(Network):
         tgt = X_non_mix.reshape(B, TF, S).transpose(1, 2)
         costs = [((tgt - est[:, list(perm)]) ** 2).sum(-1).sum(-1) for perm in itertools.permutations(range(S))]
         return torch.stack(costs, 1).min(1).values.mean()
+
+    # network.py:697-723
+    def cost_finetuning(self, x_non_mix, postprocessed):
+        """PIT waveform loss on the separated waveforms [B,S,L] (same definition as Adapt.cost_finetuning)."""
+        return L.pit_wave_l2(x_non_mix, postprocessed)
 
     # network.py:584-607
     def postprocessing(self, stfts, labels_or_masks):

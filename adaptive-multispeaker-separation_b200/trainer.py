@@ -311,6 +311,49 @@ class STFT_Separator_enhance_Trainer(Trainer):
         return m.enhance_cost(cost_in, pre["X_non_mix"])
 
 
+class Front_Separator_Enhance_Finetuning_Trainer(Trainer):
+    """utils/trainer.py:636-658 -- end-to-end fine-tuning of the adaptive pipeline: front -> separator (k-means masks)
+    -> enhance BLSTM layer -> back (unpool + transposed conv) -> PIT waveform loss (`cost_finetuning`,
+    models/adapt.py:404-431).  Only the variables whose name contains one of `train` (the reference's --train
+    substrings, utils/trainer.py:119-120, :648-653) are optimised; model_folder restore is replaced by an optional
+    state dict.  The hard k-means labels are not differentiable (network.py:554-582): the gradient reaches the
+    enhance layer, the back filterbank and -- through the masked front output X * mask -- the front filterbank.
+    init_idx (optional): the k-means initial rows, otherwise drawn like the reference (np.random.choice)."""
+
+    def __init__(self, separator, name="Front_Separator_Enhance_Finetuning", state=None, train=("enhance", "back"), **kwargs):
+        self.separator_class, self.name, self.state, self.train_names = separator, name, state, tuple(train)
+        self.init_idx = None
+        super().__init__(**kwargs)
+
+    def build(self):
+        args = {k: v for k, v in self.args.items() if k in DEFAULTS or k in ("window_size", "hop_size")}
+        args["pretraining"] = False
+        self.model = Adapt(**args)
+        self.sepNet = self.model.connect_front(self.separator_class)
+        self.sepNet.add_enhance_layer()
+        self.store = self.model.store
+
+    def post_build(self):
+        if self.state:
+            self.store.load_state_dict(self.state, strict=False)
+        self.store.set_trainable(lambda name: any(t in name for t in self.train_names))
+
+    def loss(self, x_mix, x_non_mix, ind):
+        m, sn = self.model, self.sepNet
+        B, Lw = x_mix.shape
+        y, am = m.front(x_mix, x_non_mix)
+        X = y[:B].contiguous()
+        with torch.no_grad():                       # hard k-means labels are not differentiable
+            V = sn.prediction(X.detach())
+            _, lab = sn.separate(V, X.detach(), self.init_idx)
+        Xf = X.reshape(B, -1)
+        sep = torch.stack([Xf * (lab == k).to(Xf.dtype) for k in range(sn.S)], 1).reshape(B * sn.S, X.shape[1], X.shape[2]) \
+            if sn.beta is None else (Xf.unsqueeze(1) * lab.transpose(1, 2)).reshape(B * sn.S, X.shape[1], X.shape[2])
+        enhanced, _ = sn.enhance(sep, X)                                       # [B,S,TF]
+        back = m.back(enhanced.reshape(B * sn.S, X.shape[1], X.shape[2]), am, B, Lw)
+        return m.cost_finetuning(x_non_mix, back)
+
+
 class STFT_Separator_Inference:
     """utils/trainer.py:406-417 + Trainer.inference (:190-229): mixture -> separated waveforms."""
 

@@ -203,6 +203,65 @@ def test_enhance_layer_steps_match_oracle(amss):
     assert torch.equal(trunk_before, t.store["prediction/W"].detach())      # the trunk stays frozen
 
 
+# ------------------------------------------------------------------------------ fine-tuning
+def test_front_enhance_finetuning_steps_match_oracle(amss):
+    """End-to-end fine-tuning recipe (utils/trainer.py:636-658): front -> k-means masks -> enhance layer -> back ->
+    PIT waveform loss `cost_finetuning` (models/adapt.py:404-431); front/, back/ and enhance/ train, the separator
+    trunk stays frozen.  Two optimisation steps against the oracle: cost and every trained tensor within 1e-3."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 2048
+    cfg = dict(nb_layers=1, layer_size=16, embedding_size=6, window_size=32, filters=16, max_pool=32, hop_size=32,
+               with_max_pool=True, nb_layers_enhance=1, layer_size_enhance=12, nonlinearity="softmax", nb_tries=2,
+               nb_steps=3)
+    names = ("enhance", "back/", "front/")
+    t = tr.Front_Separator_Enhance_Finetuning_Trainer(mo.DPCL, learning_rate=1e-3, train=names, **cfg)
+    p = _copy_params(t.store, {})
+    rng = np.random.RandomState(9)
+
+    def fn(pp, xm, xn, I):
+        fr = M.adapt_front(pp, xm, xn, 32, 32)
+        y, am = fr["y"], fr["argmax"]
+        X = y[:B]
+        with torch.no_grad():
+            V = M.separator_prediction(pp, X, 1, 6)
+            km = OracleKMeans(nb_clusters=S, nb_tries=2, nb_iterations=3)
+            labels = km.fit(V.reshape(B, -1, 6), init_idx=fn.init)[1]
+        sep, _ = M.separate(V, X, lambda e: labels, S)
+        enhanced, _, _ = M.enhance(pp, sep, X, S, 1)
+        back, _ = M.adapt_back(pp, enhanced.reshape(B * S, X.shape[1], X.shape[2]), am, B, S, Lw, 32)
+        return M.cost_finetuning(xn, back), {}
+
+    st = OS.Stepper(p, fn, train_prefixes=names, lr=1e-3)
+    trunk_before = t.store["prediction/W"].detach().clone()
+    for step in range(2):
+        mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=500 + step)
+        fn.init = random_init_idx(B * 2, (Lw // 32) * 16, S, rng)
+        t.init_idx = fn.init
+        c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+    assert any(k.startswith("front/") for k in st.tr) and any(k.startswith("back/") for k in st.tr)
+    for k in st.tr:
+        a, b = t.store[k].detach().double().cpu(), st.tr[k].detach().double()
+        assert float((a - b).abs().max()) < REL * max(float(b.abs().max()), 1e-3), k
+    assert torch.equal(trunk_before, t.store["prediction/W"].detach())      # the separator trunk stays frozen
+
+
+def test_pit_wave_l2_three_speakers(amss):
+    """cost_finetuning with S = 3 (6 permutations): value and gradient vs the oracle definition."""
+    import amss_b200.layers as Lm
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(3, 3, 1500, generator=g) * 0.1
+    est = (x[:, [2, 0, 1]] + 0.03 * torch.randn(3, 3, 1500, generator=g)).requires_grad_(True)
+    ref = M.cost_finetuning(x.double(), est.double())
+    gref, = torch.autograd.grad(ref, est)
+    e = _dev(est.detach().numpy()).requires_grad_(True)
+    c = Lm.pit_wave_l2(_dev(x.numpy()), e)
+    c.backward()
+    assert abs(float(c) - float(ref)) < REL * abs(float(ref))
+    assert float((e.grad.double().cpu() - gref).abs().max()) < REL * float(gref.abs().max())
+
+
 # ------------------------------------------------------------------------------------------ config 5: 3 speakers
 def test_three_speaker_kmeans_inference(amss):
     """BASELINE config 5 (3-speaker mixtures, K = 3 hard k-means masks): labels bit-exact vs the oracle on the
