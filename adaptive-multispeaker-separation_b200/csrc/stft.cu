@@ -147,6 +147,37 @@ __global__ void istft_masked_kernel(const float2* __restrict__ spec, const int* 
     }
 }
 
+// Backward of istft_masked w.r.t. the soft masks (fine-tuning through Separator.postprocessing, network.py:584-607,
+// 697-723).  out[n] = sum_t winv[n - t*hop] * irfft(mask * X)[n - t*hop], so with g[i] = dout[t*hop + i] * winv[i]:
+//   d Re(mask*X)_k = (c_k / N) Re(DFT g)_k,   d Im(mask*X)_k = (c_k / N) Im(DFT g)_k   (c_k = 1 for k = 0, N/2, else 2;
+//   irfft ignores the imaginary part of those two bins),   d mask_k = Re(X_k) dRe_k + Im(X_k) dIm_k.
+// grid (T, B*S); block N/2.  dmasks[B, T*F, S].
+__global__ void istft_masked_bwd_kernel(const float2* __restrict__ spec, const float* __restrict__ dout, int S, int T, int N,
+                                        int logN, int hop, float* __restrict__ dmasks) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    float2* buf = reinterpret_cast<float2*>(st_smem);
+    float2* tw = buf + N;
+    const int t = blockIdx.x, bs = blockIdx.y, b = bs / S, s = bs % S;
+    const int F = N / 2 + 1, r = N / hop;
+    const int64_t Lout = (int64_t)(T - 1) * hop + N;
+    fill_twiddles(tw, N, -1.f);
+    const float* src = dout + (size_t)bs * Lout + (size_t)t * hop;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int j = i % hop;
+        float den = 0.f;
+        for (int o2 = 0; o2 < r; ++o2) { const float w = hann_periodic(j + o2 * hop, N); den = fmaf(w, w, den); }
+        const float v = src[i] * (hann_periodic(i, N) / den) * (1.0f / (float)N);
+        buf[__brev((unsigned)i) >> (32 - logN)] = make_float2(v, 0.f);
+    }
+    fft_shared(buf, tw, N, logN);
+    const size_t o = ((size_t)b * T + t) * F;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        const float2 g = buf[k], x = spec[o + k];
+        const bool edge = k == 0 || k == N / 2;
+        dmasks[(o + k) * S + s] = edge ? x.x * g.x : 2.f * (x.x * g.x + x.y * g.y);
+    }
+}
+
 int ilog2_exact(int n) {
     int l = 0;
     while ((1 << l) < n) ++l;
@@ -198,5 +229,18 @@ extern "C" int amss_istft_masked_fwd(const float* spec, const int32_t* labels, c
     dim3 grid(nblocks, B * S);
     AMSS_LAUNCH(istft_masked_kernel, grid, frame / 2, smem, stream, reinterpret_cast<const float2*>(spec), labels,
                 masks, S, T, frame, logN, hop, out);
+    return AMSS_OK;
+}
+
+extern "C" int amss_istft_masked_bwd(const float* spec, const float* dout, int B, int S, int T, int frame, int hop,
+                                     float* dmasks, void* stream) {
+    AMSS_REQUIRE(spec && dout && dmasks, "istft_masked_bwd: null pointer");
+    const int logN = ilog2_exact(frame);
+    AMSS_REQUIRE(logN >= 6 && logN <= 11, "istft_masked_bwd: frame %d must be a power of two in [64,2048]", frame);
+    AMSS_REQUIRE(hop > 0 && frame % hop == 0 && B > 0 && S > 0 && T > 0, "istft_masked_bwd: bad sizes");
+    const size_t smem = (size_t)frame * 8 + (size_t)frame / 2 * 8;
+    dim3 grid(T, B * S);
+    AMSS_LAUNCH(istft_masked_bwd_kernel, grid, frame / 2, smem, stream, reinterpret_cast<const float2*>(spec), dout, S, T,
+                frame, logN, hop, dmasks);
     return AMSS_OK;
 }

@@ -371,6 +371,27 @@ def wave_stats(target, approx):
     return _WaveLossFn.apply(target, approx)
 
 
+class _ISTFTMaskedFn(torch.autograd.Function):
+    """Separator.postprocessing with soft masks (network.py:584-607) as a differentiable node: (masks * X) ->
+    inverse_stft.  The gradient reaches the masks (the enhance layer's softmax output); the mixture STFT is data."""
+
+    @staticmethod
+    def forward(ctx, spec, masks, S, frame, hop):
+        ctx.save_for_backward(spec)
+        ctx.cfg = (S, frame, hop)
+        return ops.istft_masked(spec, S, frame, hop, masks=masks.contiguous())
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, = ctx.saved_tensors
+        S, frame, hop = ctx.cfg
+        return None, ops.istft_masked_bwd(spec, dout.contiguous(), S, frame, hop), None, None, None
+
+
+def istft_masked(spec, masks, S, frame, hop):
+    return _ISTFTMaskedFn.apply(spec, masks, S, frame, hop)
+
+
 def pit_wave_l2(x_non_mix, est):
     """cost_finetuning (models/network.py:697-723, models/adapt.py:404-431): 0.5 * sum_L (x_s - xhat_perm(s))^2, mean
     over the S sources, min over the S! permutations, mean over the batch.  The S*S pairwise squared distances come

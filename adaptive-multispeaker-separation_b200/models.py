@@ -330,6 +330,7 @@ class Separator(Network):
             yv = torch.softmax(yv, -1)
         elif nl == "tanh":
             yv = torch.tanh(yv)
+        self.enhance_masks = yv                                                  # [B,TF,S]: postprocessing_masks() input
         cost_in = yv * X_input.reshape(B, -1, 1)
         return cost_in.transpose(1, 2), cost_in
 
@@ -345,6 +346,11 @@ class Separator(Network):
     def cost_finetuning(self, x_non_mix, postprocessed):
         """PIT waveform loss on the separated waveforms [B,S,L] (same definition as Adapt.cost_finetuning)."""
         return L.pit_wave_l2(x_non_mix, postprocessed)
+
+    def postprocessing_masks(self, stfts, masks):
+        """Differentiable postprocessing for the fine-tuning recipes: masks [B,TF,S] (e.g. the enhance layer's output
+        ratio enhanced/|X|) -> waveforms [B,S,L'] with autograd to the masks."""
+        return L.istft_masked(stfts, masks, self.S, self.window_size, self.hop_size)
 
     # network.py:584-607
     def postprocessing(self, stfts, labels_or_masks):

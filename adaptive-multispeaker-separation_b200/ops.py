@@ -149,6 +149,16 @@ def istft_masked(spec, S, frame, hop, labels=None, masks=None):
     return out
 
 
+def istft_masked_bwd(spec, dout, S, frame, hop):
+    """Gradient of istft_masked(spec, masks=...) w.r.t. the soft masks: dout[B,S,L'] -> dmasks[B,T*F,S]."""
+    specr = torch.view_as_real(spec).contiguous()
+    _chk(specr, dout)
+    B, T, F = spec.shape
+    dmasks = torch.empty(B, T * F, S, dtype=_f32, device=spec.device)
+    _lib.call("amss_istft_masked_bwd", _p(specr), _p(dout), B, S, T, frame, hop, _p(dmasks), _stream())
+    return dmasks
+
+
 # ------------------------------------------------------------------------------------------
 # GEMM / BLSTM
 # ------------------------------------------------------------------------------------------

@@ -311,6 +311,41 @@ class STFT_Separator_enhance_Trainer(Trainer):
         return m.enhance_cost(cost_in, pre["X_non_mix"])
 
 
+class STFT_Separator_FineTune_Trainer(Trainer):
+    """utils/trainer.py:502-526 -- end-to-end fine-tuning of the STFT pipeline: |STFT| -> separator (k-means masks) ->
+    enhance BLSTM layer -> postprocessing (mixture phase, inverse STFT) -> PIT waveform loss (`cost_finetuning`,
+    models/network.py:697-723).  Trains the variables whose name contains one of `train` (--train substrings); the
+    gradient reaches them through the enhance layer's mask output (differentiable inverse STFT); hard k-means labels and
+    the separator trunk they come from carry no gradient.  The inverse STFT returns (T-1)*hop + frame samples: the
+    targets are cropped to that length, as TF's inverse_stft does."""
+
+    def __init__(self, separator, name="STFT_Separator_FineTune", state=None, train=("enhance",), **kwargs):
+        self.separator_class, self.name, self.state, self.train_names = separator, name, state, tuple(train)
+        self.init_idx = None
+        super().__init__(**kwargs)
+
+    def build(self):
+        args = {k: v for k, v in self.args.items() if k in DEFAULTS or k in ("window_size", "hop_size")}
+        self.model = self.separator_class(plugged=False, **args)
+        self.model.add_enhance_layer()
+        self.store = self.model.store
+
+    def post_build(self):
+        if self.state:
+            self.store.load_state_dict(self.state, strict=False)
+        self.store.set_trainable(lambda name: any(t in name for t in self.train_names))
+
+    def loss(self, x_mix, x_non_mix, ind):
+        m = self.model
+        spec, X = ops.stft(x_mix.contiguous(), m.window_size, m.hop_size)
+        with torch.no_grad():
+            V = m.prediction(X)
+            sep, _ = m.separate(V, X, self.init_idx)
+        m.enhance(sep, X)
+        out = m.postprocessing_masks(spec, m.enhance_masks)                   # [B,S,L']
+        return m.cost_finetuning(x_non_mix[:, :, :out.shape[2]], out)
+
+
 class Front_Separator_Enhance_Finetuning_Trainer(Trainer):
     """utils/trainer.py:636-658 -- end-to-end fine-tuning of the adaptive pipeline: front -> separator (k-means masks)
     -> enhance BLSTM layer -> back (unpool + transposed conv) -> PIT waveform loss (`cost_finetuning`,

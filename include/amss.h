@@ -118,6 +118,10 @@ int amss_stft_labels(const float* non_mix, int B, int S, int L, int frame, int h
 int amss_istft_masked_fwd(const float* spec, const int32_t* labels, const float* masks,
                           int B, int S, int T, int frame, int hop, float* out,
                           void* stream);
+/* Gradient of the soft-mask variant w.r.t. masks[B,T*F,S] (end-to-end fine-tuning through
+ * postprocessing, network.py:697-723): dout[B,S,(T-1)*hop+frame] -> dmasks[B,T*F,S].      */
+int amss_istft_masked_bwd(const float* spec, const float* dout, int B, int S, int T,
+                          int frame, int hop, float* dmasks, void* stream);
 
 /* ------------------------------------------------------------------------------------ *
  * BLSTM  (utils/ops.py:358-383: BasicLSTMCell gate order i,j,f,o; forget_bias 1.0)

@@ -9,6 +9,7 @@ import torch
 
 from oracle import models as M
 from oracle import steps as OS
+from oracle import tf_ops as T_
 from oracle.kmeans import KMeans as OracleKMeans, random_init_idx
 
 pytestmark = pytest.mark.gpu
@@ -245,6 +246,65 @@ def test_front_enhance_finetuning_steps_match_oracle(amss):
         a, b = t.store[k].detach().double().cpu(), st.tr[k].detach().double()
         assert float((a - b).abs().max()) < REL * max(float(b.abs().max()), 1e-3), k
     assert torch.equal(trunk_before, t.store["prediction/W"].detach())      # the separator trunk stays frozen
+
+
+def test_istft_masked_backward_matches_autograd(amss):
+    """amss_istft_masked_bwd: gradient of postprocessing (network.py:584-607) w.r.t. soft masks vs torch autograd of
+    the oracle's inverse STFT in float64."""
+    ops = amss["ops"]
+    import amss_b200.layers as Lm
+    g = torch.Generator().manual_seed(78)
+    B, S, Lw, frame, hop = 2, 3, 2048, 128, 64
+    x = torch.randn(B, Lw, generator=g) * 0.1
+    spec = T_.stft(x.double(), frame, hop)                                   # [B,T,F] complex128
+    Tt, Fb = spec.shape[1], spec.shape[2]
+    masks = torch.rand(B, Tt * Fb, S, generator=g, dtype=torch.float64).requires_grad_(True)
+    sep = (spec.abs().reshape(B, -1, 1) * masks).reshape(B, Tt, Fb, S).permute(0, 3, 1, 2).reshape(B * S, Tt, Fb)
+    out_ref = M.postprocessing(sep, spec, S, frame, hop)
+    w = torch.randn(out_ref.shape, generator=g, dtype=torch.float64)
+    gref, = torch.autograd.grad((out_ref * w).sum(), masks)
+    spec_d, _ = ops.stft(_dev(x.numpy()), frame, hop)
+    md = _dev(masks.detach().float().numpy()).requires_grad_(True)
+    out = Lm.istft_masked(spec_d, md, S, frame, hop)
+    assert rel(out, out_ref) < REL
+    (out * _dev(w.float().numpy())).sum().backward()
+    assert rel(md.grad, gref) < REL
+
+
+def test_stft_finetuning_steps_match_oracle(amss):
+    """STFT fine-tuning recipe (utils/trainer.py:502-526): |STFT| -> k-means masks -> enhance layer -> inverse STFT with
+    the mixture phase -> PIT waveform loss; only enhance/ trains.  Two steps against the oracle."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 4096
+    cfg = dict(nb_layers=1, layer_size=24, embedding_size=6, window_size=128, hop_size=64, nb_layers_enhance=1,
+               layer_size_enhance=20, nonlinearity="softmax", nb_tries=2, nb_steps=3)
+    t = tr.STFT_Separator_FineTune_Trainer(mo.DPCL, learning_rate=1e-3, **cfg)
+    p = _copy_params(t.store, {})
+    rng = np.random.RandomState(11)
+
+    def fn(pp, xm, xn, I):
+        pre = M.separator_preprocessing(xm, xn, 128, 64, 1.0, 0.0)
+        with torch.no_grad():
+            V = M.separator_prediction(pp, pre["X"], 1, 6)
+            km = OracleKMeans(nb_clusters=S, nb_tries=2, nb_iterations=3)
+            sep, _ = M.separate(V, pre["X"], lambda e: km.fit(e, init_idx=fn.init)[1], S)
+        enhanced, _, _ = M.enhance(pp, sep, pre["X"], S, 1)
+        Tt, Fb = pre["X"].shape[1], pre["X"].shape[2]
+        out = M.postprocessing(enhanced.reshape(B * S, Tt, Fb), pre["stfts"], S, 128, 64)
+        return M.cost_finetuning(xn[:, :, :out.shape[2]], out), {}
+
+    st = OS.Stepper(p, fn, train_prefixes=("enhance",), lr=1e-3)
+    for step in range(2):
+        mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=600 + step)
+        Tt = 1 + (Lw - 128) // 64
+        fn.init = random_init_idx(B * 2, Tt * 65, S, rng)
+        t.init_idx = fn.init
+        c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+    for k in st.tr:
+        a, b = t.store[k].detach().double().cpu(), st.tr[k].detach().double()
+        assert float((a - b).abs().max()) < REL * max(float(b.abs().max()), 1e-3), k
 
 
 def test_pit_wave_l2_three_speakers(amss):
