@@ -17,6 +17,9 @@ int filterbank_analysis_tc(const float* x, const float* filt, int Bt, int L, int
                            cudaStream_t st);
 size_t filterbank_analysis_tc_workspace(int Bt, int L, int W, int N, int pool, int hop, int precision);
 bool filterbank_analysis_tc_supported(int L, int W, int N, int pool, int hop, int mode);
+int filterbank_analysis_mix_tc(const float* x, const float* filt, int B, int S, int L, int W, int N, int pool, int hop,
+                               int precision, float* y, int64_t* argmax, void* workspace, size_t workspace_bytes,
+                               cudaStream_t st);
 
 namespace {
 
@@ -323,6 +326,18 @@ extern "C" int amss_filterbank_analysis_fwd(const float* x, const float* filt, i
         AMSS_LAUNCH(analysis_pool_kernel<1>, grid, FA_THREADS, smem, st, x, filt, L, W, N, pool, hop, Tp, y, argmax);
     }
     return AMSS_OK;
+}
+
+extern "C" int amss_filterbank_analysis_mix_fwd(const float* x, const float* filt, int B, int S, int L, int W, int N,
+                                                int pool, int hop, int mode, int precision, float* y, int64_t* argmax,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
+    AMSS_REQUIRE(B > 0 && S > 0, "filterbank_analysis_mix_fwd: bad batch B=%d S=%d", B, S);
+    if (x && filt && y && mode == AMSS_POOL_MAX && precision != AMSS_PREC_FP32 && pool > 0 &&
+        filterbank_analysis_tc_supported(L, W, N, pool, hop, mode))
+        return filterbank_analysis_mix_tc(x, filt, B, S, L, W, N, pool, hop, precision, y, argmax, workspace,
+                                          workspace_bytes, (cudaStream_t)stream);
+    return amss_filterbank_analysis_fwd(x, filt, B * (S + 1), L, W, N, pool, hop, mode, precision, y, argmax, workspace,
+                                        workspace_bytes, stream);
 }
 
 extern "C" size_t amss_filterbank_grad_workspace_bytes(int W, int N) {

@@ -317,8 +317,11 @@ class _AnalysisFn(torch.autograd.Function):
     Gradient flows to the filter only (the waveform is data)."""
 
     @staticmethod
-    def forward(ctx, x, filt, pool, hop, precision):
-        y, am = ops.filterbank_analysis(x, filt, pool, hop, ops.AMSS_POOL_MAX, precision)
+    def forward(ctx, x, filt, pool, hop, precision, batch=None):
+        if batch is not None:       # x = [B mixtures ; B*S sources]: lets the library use the linear-mixture fast path
+            y, am = ops.filterbank_analysis_mix(x, filt, batch[0], batch[1], pool, hop, precision)
+        else:
+            y, am = ops.filterbank_analysis(x, filt, pool, hop, ops.AMSS_POOL_MAX, precision)
         ctx.save_for_backward(x, am)
         ctx.W = filt.shape[0]
         ctx.mark_non_differentiable(am)
@@ -327,7 +330,7 @@ class _AnalysisFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dam):
         x, am = ctx.saved_tensors
-        return None, ops.filterbank_analysis_bwd(x, dy.contiguous(), am, ctx.W), None, None, None
+        return None, ops.filterbank_analysis_bwd(x, dy.contiguous(), am, ctx.W), None, None, None, None
 
 
 class _SynthesisFn(torch.autograd.Function):
@@ -479,8 +482,8 @@ def make_filter(window, bases):
     return _MakeFilterFn.apply(window, bases)
 
 
-def analysis(x, filt, pool, hop, precision=AMSS_PREC_FP32):
-    return _AnalysisFn.apply(x, filt, pool, hop, precision)
+def analysis(x, filt, pool, hop, precision=AMSS_PREC_FP32, batch=None):
+    return _AnalysisFn.apply(x, filt, pool, hop, precision, batch)
 
 
 def synthesis(vals, argmax_mix, filt2, B, S, L, pool, hop):

@@ -117,7 +117,7 @@ class Adapt(Network):
         x = torch.cat([x_mix, x_non_mix.reshape(B * S, Lw)], 0).contiguous()
         filt = self.conv_filter("front")
         if self.with_max_pool:
-            y, am = L.analysis(x, filt, self.max_pool_value, self.hop_size, self.precision)
+            y, am = L.analysis(x, filt, self.max_pool_value, self.hop_size, self.precision, batch=(B, S))
         else:
             if filt.requires_grad:
                 raise AmssError("avg-pool / strided front ends are inference-only here (no filter gradient kernel)")

@@ -76,6 +76,25 @@ def filterbank_analysis(x, filt, pool, hop, mode=AMSS_POOL_MAX, precision=AMSS_P
     return y, am
 
 
+def filterbank_analysis_mix(x, filt, B, S, pool, hop, precision=AMSS_PREC_FP32):
+    """Front end of a training batch x = [B mixtures ; B*S sources] (max-pool mode): same outputs as
+    filterbank_analysis; the library derives the mixture rows by linearity when x_mix == sum of its sources bit for bit
+    (checked on the device per call, see amss_filterbank_analysis_mix_fwd)."""
+    _chk(x, filt)
+    Bt, L = x.shape
+    if Bt != B * (S + 1):
+        raise _lib.AmssError(f"filterbank_analysis_mix: {Bt} rows for B={B}, S={S}")
+    W, N = filt.shape
+    Tp = analysis_out_frames(L, W, pool, hop, AMSS_POOL_MAX)
+    y = torch.empty(Bt, Tp, N, dtype=_f32, device=x.device)
+    am = torch.empty(Bt, Tp, N, dtype=torch.int64, device=x.device)
+    nb = _lib.query("amss_filterbank_analysis_workspace_bytes", Bt, L, W, N, pool, hop, AMSS_POOL_MAX, precision)
+    ws = _ws(nb, x.device)
+    _lib.call("amss_filterbank_analysis_mix_fwd", _p(x), _p(filt), B, S, L, W, N, pool, hop, AMSS_POOL_MAX, precision, _p(y),
+              _p(am), _p(ws), ws.numel(), _stream())
+    return y, am
+
+
 def filterbank_analysis_bwd(x, dy, argmax, W):
     """d(filt)[W,N] through the max-pool arg-max."""
     _chk(x, dy, argmax)

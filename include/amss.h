@@ -72,6 +72,17 @@ int amss_filterbank_analysis_fwd(const float* x, const float* filt, int Bt, int 
                                  int N, int pool, int hop, int mode, int precision,
                                  float* y, int64_t* argmax, void* workspace,
                                  size_t workspace_bytes, void* stream);
+/* The front end of a training batch, x = [B mixtures ; B*S sources] (adapt.py:41-48: the
+ * concat the reference feeds to Adapt.front).  Same outputs as amss_filterbank_analysis_fwd
+ * with Bt = B*(S+1).  On the tensor-core path with S = 2 the mixture rows are obtained by
+ * linearity of the convolution (response(x_mix) = response(x_0) + response(x_1)) whenever
+ * x_mix == x_0 + x_1 holds bit for bit -- how the reference's data pipeline builds its
+ * mixtures (data/dataset.py:462-468); the equality is checked on the device for every call
+ * and any other batch takes the stock path, so the result never depends on the assumption. */
+int amss_filterbank_analysis_mix_fwd(const float* x, const float* filt, int B, int S, int L,
+                                     int W, int N, int pool, int hop, int mode, int precision,
+                                     float* y, int64_t* argmax, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 size_t amss_filterbank_analysis_workspace_bytes(int Bt, int L, int W, int N, int pool,
                                                 int hop, int mode, int precision);
 int amss_filterbank_analysis_out_frames(int L, int W, int pool, int hop, int mode);

@@ -67,6 +67,42 @@ def test_analysis_tc_matches_oracle_on_bf16_operands(ops, Bt, L, W, N, pool):
     assert agree > 0.98, agree
 
 
+@pytest.mark.parametrize("B,L,W,N,pool", [(2, 4096, 64, 16, 128), (3, 8192, 1024, 256, 256), (1, 5000, 200, 130, 256)])
+def test_analysis_mix_linear_mixture_path(ops, B, L, W, N, pool):
+    """amss_filterbank_analysis_mix_fwd, S = 2: when x_mix == x_0 + x_1 bit for bit the mixture rows come from the sum of
+    the two source responses.  Source rows must equal the stock kernel's bit for bit (same products, same order);
+    mixture rows must match conv(bf16(x_0)) + conv(bf16(x_1)) pooled, and the fp32 kernel within the bf16 tolerance.
+    When the equality does not hold (one sample perturbed) the call must return exactly what the stock kernel returns."""
+    g = torch.Generator().manual_seed(13)
+    src = torch.randn(B, 2, L, generator=g) * 0.05
+    mix = src[:, 0] + src[:, 1]
+    x = torch.cat([mix, src.reshape(B * 2, L)], 0).contiguous()
+    filt = torch.randn(W, N, generator=g) / np.sqrt(W)
+    P = ops.AMSS_PREC_BF16
+    y_stock, am_stock = ops.filterbank_analysis(dev(x), dev(filt), pool, pool, ops.AMSS_POOL_MAX, P)
+    y, am = ops.filterbank_analysis_mix(dev(x), dev(filt), B, 2, pool, pool, P)
+    assert torch.equal(y[B:], y_stock[B:]) and torch.equal(am[B:], am_stock[B:])          # source rows: identical
+    fr = bf16_round(filt)
+    Xs = T.conv2d_same_1d(bf16_round(src.reshape(B * 2, L)), fr).reshape(B, 2, L, N)
+    ref_y, ref_am = T.max_pool_with_argmax_1d(Xs[:, 0] + Xs[:, 1], pool, pool)
+    scale = float(ref_y.abs().max())
+    assert float((y[:B].cpu() - ref_y).abs().max()) <= TOL_BF16 * scale
+    assert float((am[:B].cpu() == ref_am).float().mean()) > 0.98
+    assert float((y[:B] - y_stock[:B]).abs().max()) <= 1e-2 * scale                      # vs conv(bf16(x_mix))
+    assert not torch.equal(y[:B], y_stock[:B])                                            # (the fast path really ran)
+    # broken contract: the device-side check must route the batch through the stock kernel
+    x2 = x.clone()
+    x2[0, L // 2] += 1e-3
+    y2, am2 = ops.filterbank_analysis_mix(dev(x2), dev(filt), B, 2, pool, pool, P)
+    y2s, am2s = ops.filterbank_analysis(dev(x2), dev(filt), pool, pool, ops.AMSS_POOL_MAX, P)
+    assert torch.equal(y2, y2s) and torch.equal(am2, am2s)
+    # three sources per mixture: stock path
+    x3 = torch.randn(4, L, generator=g) * 0.05
+    y3, _ = ops.filterbank_analysis_mix(dev(x3), dev(filt), 1, 3, pool, pool, P)
+    y3s, _ = ops.filterbank_analysis(dev(x3), dev(filt), pool, pool, ops.AMSS_POOL_MAX, P)
+    assert torch.equal(y3, y3s)
+
+
 def test_analysis_tc_close_to_fp32_kernel(ops):
     """bf16-operand result vs the fp32 SIMT kernel on the same inputs: reports the operand-rounding
     error (about 2^-9 per product, averaged over W=1024 taps) and bounds it at 1e-2 of the peak."""

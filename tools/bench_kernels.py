@@ -40,6 +40,11 @@ def bench_analysis(B):
             continue
         med, best = timeit(lambda: ops.filterbank_analysis(x, filt, 256, 256, ops.AMSS_POOL_MAX, prec))
         print(f"analysis {name:14s} Bt={Bt}: {med:8.3f} ms median ({best:.3f} best)  {flops / med / 1e9:8.1f} TFLOP/s")
+    src = torch.randn(B, 2, L, device="cuda") * 0.05
+    xm = torch.cat([src[:, 0] + src[:, 1], src.reshape(2 * B, L)], 0).contiguous()
+    med, best = timeit(lambda: ops.filterbank_analysis_mix(xm, filt, B, 2, 256, 256, ops.AMSS_PREC_BF16))
+    print(f"analysis mix (linear mixture rows) B={B}: {med:8.3f} ms median ({best:.3f} best)  "
+          f"{flops / med / 1e9:8.1f} TFLOP/s algorithmic, {flops * 2 / 3 / med / 1e9:8.1f} executed")
 
 
 def bench_gemm(B):

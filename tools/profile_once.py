@@ -17,6 +17,9 @@ torch.manual_seed(0)
 x = torch.randn(3 * B, L, device="cuda") * 0.05
 filt = torch.randn(1024, 256, device="cuda") / 32
 ops.filterbank_analysis(x, filt, 256, 256, ops.AMSS_POOL_MAX, P)
+src = x[B:].reshape(B, 2, L)
+xm = torch.cat([src[:, 0] + src[:, 1], x[B:]], 0).contiguous()
+ops.filterbank_analysis_mix(xm, filt, B, 2, 256, 256, P)                                # linear-mixture fast path
 M = T * B
 h = torch.randn(M, 600, device="cuda")
 W = torch.randn(600, 10240, device="cuda") * 0.05
