@@ -29,9 +29,9 @@ if ROOT not in sys.path:
 L_SAMPLES = 64000
 CFG = dict(nb_speakers=2, nb_layers=3, layer_size=600, embedding_size=40, window_size=1024, filters=256, max_pool=256,
            hop_size=256, with_max_pool=True, learning_rate=1e-3)
-# from profiles/r01c_ncu_full_kernels.csv (analysis_pair_tc_kernel, 32 mixtures): dram read+write per mixture, tensor pipe
-NCU_DRAM_BYTES_PER_MIXTURE = 1.10e6
-NCU_TENSOR_PIPE_PCT = 88.0
+# from profiles/r01c_ncu_full_analysis.csv (analysis_pair_tc_kernel, 32 mixtures): 16.94 MB read + 17.42 MB written, tensor pipe
+NCU_DRAM_BYTES_PER_MIXTURE = 1.0737e6
+NCU_TENSOR_PIPE_PCT = 86.5
 WORKLOAD = ("adapt front (W=1024, 256 filters, max_pool 256, hop 256, frozen) + DPCL 3xBLSTM-600 E=40, 2-spk, "
             "L=64000 (4 s @ 16 kHz), fwd+bwd+AMSGrad")
 
