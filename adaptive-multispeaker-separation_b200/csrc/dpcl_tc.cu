@@ -33,7 +33,10 @@ struct DtParams {
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int RV>   // float4 per loader thread and tile held in registers (E/4 <= RV)
+// RV: float4 per loader thread and tile held in registers (E/4 <= RV).  E4C: E/4 as a compile-time constant (0 = runtime):
+// the unit -> (row, column) splits divide by it once per 16 bytes, and with 64-bit tile indices divided per tile the
+// kernel was spending half of its issue slots on integer arithmetic (ncu: IMAD + ISETP + IADD3 = 40 % of instructions).
+template <int RV, int E4C>
 __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[8];
@@ -62,17 +65,18 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
     const int64_t w0 = (int64_t)blockIdx.x * p.per, w1 = min(w0 + p.per, (int64_t)p.B * p.ntiles);
     const int sstride = E * E + S * E + S + 1;
     const int b_first = w0 < w1 ? (int)(w0 / p.ntiles) : 0;
+    const int nt = (int)p.ntiles, t_first = w0 < w1 ? (int)(w0 - (int64_t)b_first * p.ntiles) : 0;   // (mixture, tile) walk
+    const int ntile = w0 < w1 ? (int)(w1 - w0) : 0;                                                   // without divisions
 
     if (warp < 4) {
         // ---------------- loaders: V tile -> fp32 rows + bf16 A operand; An/Bn when the mixture changes ----------------
         int bcur = -1;
-        const int e4 = E / 4;
+        const int e4 = E4C ? E4C : E / 4;
         // software pipeline: tile i+1 is fetched into registers (coalesced float4, unit u = tid + 128 j) before tile i is
         // handed to the MMA, so the HBM latency overlaps the previous tile's conversion / MMAs / epilogue
         float4 tilev[RV];
-        auto fetch = [&](int64_t w) {
-            const int b = (int)(w / p.ntiles);
-            const int64_t p0 = (w - (int64_t)b * p.ntiles) * 128;
+        auto fetch = [&](int b, int tix) {
+            const int64_t p0 = (int64_t)tix * 128;
             const int np = (int)min((int64_t)128, p.TF - p0);
             const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + p0) * E);
 #pragma unroll
@@ -81,11 +85,12 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
                 tilev[j] = (j < e4 && u < np * e4) ? __ldcs(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        if (w0 < w1) fetch(w0);
-        uint32_t i = 0;
-        for (int64_t w = w0; w < w1; ++w, ++i) {
-            const int b = (int)(w / p.ntiles);
+        if (ntile > 0) fetch(b_first, t_first);
+        int b = b_first, tix = t_first;
+        for (uint32_t i = 0; i < (uint32_t)ntile; ++i) {
             const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            int bnext = b, tnext = tix + 1;
+            if (tnext == nt) { tnext = 0; ++bnext; }
             mbar_wait(t_empty + 8 * buf, ph ^ 1);          // the epilogue of tile i-2 has finished with vs[buf] / TMEM[buf]
             mbar_wait(a_empty + 8 * buf, ph ^ 1);          // the MMAs of tile i-2 have finished with a_s[buf]
             if (b != bcur) {        // generation (b - b_first) & 1: An -> bf16 B operand [n][k] (An symmetric), Bn/dinv fp32
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
                     *reinterpret_cast<float4*>(vb + r * pitch + c * 4) = tilev[j];
                 }
             }
-            if (w + 1 < w1) fetch(w + 1);
+            if (i + 1 < (uint32_t)ntile) fetch(bnext, tnext);
             named_sync(1, 128);
             uint8_t* ab = a_s + buf * a_bytes;
             const float* row = vb + tid * pitch;
@@ -130,14 +135,14 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
             }
             fence_async_smem();
             mbar_arrive(a_full + 8 * buf);
+            b = bnext; tix = tnext;
         }
     } else if (warp == 4) {
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = idesc_bf16(128, EK, 0, 0);
         const bool leader = elect_one();
-        uint32_t i = 0;
-        for (int64_t w = w0; w < w1; ++w, ++i) {
-            const int b = (int)(w / p.ntiles);
+        int b = b_first, tix = t_first;
+        for (uint32_t i = 0; i < (uint32_t)ntile; ++i) {
             const uint32_t buf = i & 1, ph = (i >> 1) & 1;
             mbar_wait(a_full + 8 * buf, ph);
             tc_fence_after();
@@ -148,16 +153,16 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
                 if (leader) mma_bf16(tmem + buf * 64, ad, bd, idesc, kk > 0);
             }
             if (leader) { mma_commit(a_empty + 8 * buf); mma_commit(t_full + 8 * buf); }
+            if (++tix == nt) { tix = 0; ++b; }
         }
     } else {
         // ---------------- epilogue: thread = point (TMEM lane); dV row, <v,dV>, dz row ----------------
         const int q = warp & 3, r = q * 32 + lane, et = tid - 160;
         const float gscale = p.dloss[0] / (float)p.B;
-        const int e4 = E / 4;
-        uint32_t i = 0;
-        for (int64_t w = w0; w < w1; ++w, ++i) {
-            const int b = (int)(w / p.ntiles);
-            const int64_t p0 = (w - (int64_t)b * p.ntiles) * 128;
+        const int e4 = E4C ? E4C : E / 4;
+        int b = b_first, tix = t_first;
+        for (uint32_t i = 0; i < (uint32_t)ntile; ++i) {
+            const int64_t p0 = (int64_t)tix * 128;
             const int np = (int)min((int64_t)128, p.TF - p0);
             const uint32_t buf = i & 1, ph = (i >> 1) & 1;
             const float* bn = bn_s + ((b - b_first) & 1) * (S * E + S);
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
                 }
             }
             mbar_arrive(t_empty + 8 * buf);                // vs[buf] and TMEM[buf] may be reused
+            if (++tix == nt) { tix = 0; ++b; }
         }
     }
     tc_fence_before();
@@ -244,12 +250,15 @@ int dpcl_bwd_tc(const float* V, const uint8_t* labels, const float* dloss, const
     p.per = (total + grid - 1) / grid;
     const size_t smem = (size_t)2 * 128 * p.pitch * 4 + 2 * (size_t)(p.EK / 8) * 16 * 128 + 2 * (size_t)(p.EK / 8) * (p.EK / 8) * 128 +
                         2 * (size_t)(S * E + S) * 4 + 64;
-    if (E <= 40) {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(dpcl_bwd_tc_kernel<10>, grid, DT_THREADS, smem, st, p);
+    if (E == 40) {          // the reference's embedding size (utils/trainer.py:74): E/4 folded into the index arithmetic
+        AMSS_CUDA(cudaFuncSetAttribute((dpcl_bwd_tc_kernel<10, 10>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_bwd_tc_kernel<10, 10>), grid, DT_THREADS, smem, st, p);
+    } else if (E <= 40) {
+        AMSS_CUDA(cudaFuncSetAttribute((dpcl_bwd_tc_kernel<10, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_bwd_tc_kernel<10, 0>), grid, DT_THREADS, smem, st, p);
     } else {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(dpcl_bwd_tc_kernel<16>, grid, DT_THREADS, smem, st, p);
+        AMSS_CUDA(cudaFuncSetAttribute((dpcl_bwd_tc_kernel<16, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_bwd_tc_kernel<16, 0>), grid, DT_THREADS, smem, st, p);
     }
     return AMSS_OK;
 }
