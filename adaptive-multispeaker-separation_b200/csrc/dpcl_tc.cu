@@ -290,7 +290,10 @@ struct GtcParams {
 constexpr int GG_THREADS = 160;           // warps 0-3 loaders / final epilogue, warp 4 MMA (+TMEM alloc)
 constexpr uint32_t GG_TILE = 16 * 2048;   // 16 point groups x (16 e-groups x 128 B)
 
-template <int RV>   // float4 per embedding row held in registers (E <= 4*RV)
+// RV: float4 per embedding row held in registers (E <= 4*RV).  E4C > 0 (E == 4*E4C, E % 8 == 0): the tile is fetched as
+// 128*E4C CONSECUTIVE float4 (unit u = tid + 128 j -> point u / E4C), i.e. fully coalesced, instead of one 4E-byte row
+// per thread (32 half-used sectors per load instruction).
+template <int RV, int E4C>
 __global__ void __launch_bounds__(GG_THREADS, 3) dpcl_gram_tc_kernel(GtcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[5];          // full[2], empty[2], done
@@ -321,6 +324,53 @@ __global__ void __launch_bounds__(GG_THREADS, 3) dpcl_gram_tc_kernel(GtcParams p
             wS[s] = n > 0.f ? rsqrtf(sqrtf(n)) : 0.f;       // sqrt(w) = N^{-1/4}
             iwS[s] = n > 0.f ? sqrtf(sqrtf(n)) : 0.f;       // 1 / sqrt(w)
         }
+      if constexpr (E4C > 0) {
+        // coalesced variant: registers hold E4C float4 of the tile + the labels of the points they belong to
+        float4 rowv[E4C];
+        int labv[E4C], lown = 255;
+        auto fetch = [&](int64_t tile) {
+            const int64_t p0 = tile * 128;
+            const float4* src = reinterpret_cast<const float4*>(p.V + ((size_t)b * p.TF + p0) * E);
+            const uint8_t* lb = p.labels + (size_t)b * p.TF + p0;
+#pragma unroll
+            for (int j = 0; j < E4C; ++j) {
+                const int u = tid + 128 * j, pt = u / E4C;
+                const bool ok = p0 + pt < p.TF;
+                rowv[j] = ok ? __ldcs(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                labv[j] = ok ? (int)__ldg(lb + pt) : 255;
+            }
+            lown = p0 + tid < p.TF ? (int)__ldg(lb + tid) : 255;
+        };
+        if (t0 < t1) fetch(t0);
+        uint32_t i = 0;
+        for (int64_t tile = t0; tile < t1; ++tile, ++i) {
+            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            uint2 w[E4C];
+#pragma unroll
+            for (int j = 0; j < E4C; ++j) {
+                const int l = labv[j];
+                const float sw = l == 0 ? wS[0] : (l == 1 ? wS[1] : (l == 2 ? wS[2] : (l == 3 ? wS[3] : 0.f)));
+                w[j] = make_uint2(pack_bf16(rowv[j].x * sw, rowv[j].y * sw), pack_bf16(rowv[j].z * sw, rowv[j].w * sw));
+            }
+            const int l0 = lown;
+            if (tile + 1 < t1) fetch(tile + 1);
+            mbar_wait(empty + 8 * buf, ph ^ 1);
+            uint8_t* tbase = smem + buf * GG_TILE;
+#pragma unroll
+            for (int j = 0; j < E4C; ++j) {
+                const int u = tid + 128 * j, pt = u / E4C, c = u - pt * E4C;
+                *reinterpret_cast<uint2*>(tbase + (size_t)(pt >> 3) * 2048 + (c >> 1) * 128 + (pt & 7) * 16 + (c & 1) * 8) = w[j];
+            }
+            {   // the one-hot label columns e = E .. E+S-1 (exact in bf16): unit E/8 of this thread's point
+                const uint32_t one = 0x3F80u;
+                uint32_t q0 = (l0 == 0 && S > 0 ? one : 0u) | (l0 == 1 && S > 1 ? one << 16 : 0u);
+                uint32_t q1 = (l0 == 2 && S > 2 ? one : 0u) | (l0 == 3 && S > 3 ? one << 16 : 0u);
+                *reinterpret_cast<uint4*>(tbase + (size_t)(tid >> 3) * 2048 + (E4C / 2) * 128 + (tid & 7) * 16) = make_uint4(q0, q1, 0u, 0u);
+            }
+            fence_async_smem();
+            mbar_arrive(full + 8 * buf);
+        }
+      } else {
         // software pipeline: the row (and label) of tile i+1 is loaded into registers before tile i is converted,
         // so the HBM latency overlaps the shared-memory stores / MMAs of the previous tile
         float4 rowv[RV];
@@ -365,6 +415,7 @@ __global__ void __launch_bounds__(GG_THREADS, 3) dpcl_gram_tc_kernel(GtcParams p
             fence_async_smem();
             mbar_arrive(full + 8 * buf);
         }
+      }
         // ---- final epilogue: D[e][e'] (lanes = e) -> partial Gram + per-speaker sums ----
         if (t1 > t0) {
             mbar_wait(done, 0);
@@ -423,12 +474,15 @@ int dpcl_gram_tc(const float* V, const uint8_t* labels, const float* counts, int
     p.chunks = chunks;
     p.ntiles = (TF + 127) / 128;
     const size_t smem = 2 * (size_t)GG_TILE;
-    if (E <= 40) {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(dpcl_gram_tc_kernel<10>, B * chunks, GG_THREADS, smem, st, p);
+    if (E == 40 && (reinterpret_cast<uintptr_t>(V) & 15) == 0) {     // the reference's embedding size: coalesced tile fetch
+        AMSS_CUDA(cudaFuncSetAttribute((dpcl_gram_tc_kernel<10, 10>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_gram_tc_kernel<10, 10>), B * chunks, GG_THREADS, smem, st, p);
+    } else if (E <= 40) {
+        AMSS_CUDA(cudaFuncSetAttribute((dpcl_gram_tc_kernel<10, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_gram_tc_kernel<10, 0>), B * chunks, GG_THREADS, smem, st, p);
     } else {
-        AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(dpcl_gram_tc_kernel<16>, B * chunks, GG_THREADS, smem, st, p);
+        AMSS_CUDA(cudaFuncSetAttribute((dpcl_gram_tc_kernel<16, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AMSS_LAUNCH((dpcl_gram_tc_kernel<16, 0>), B * chunks, GG_THREADS, smem, st, p);
     }
     return AMSS_OK;
 }
