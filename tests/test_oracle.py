@@ -218,3 +218,21 @@ def test_separator_stft_pipeline_and_l41():
     assert out.shape == (2, 2, 4096)
     # masks partition the mixture: summed estimates reconstruct the mixture interior
     assert torch.allclose(out.sum(1)[:, 256:-256], xm[:, 256:-256], atol=1e-4)
+
+
+def test_cost_finetuning_is_permutation_invariant_pit():
+    """cost_finetuning (models/network.py:697-723): 0.5*sum_L (x - xhat)^2, mean over S, MIN over the S! permutations,
+    mean over B -- zero for any permutation of the targets, invariant to permuting the estimates, equal to the
+    identity-permutation l2 when the estimates are already aligned, and its gradient pulls every estimate towards the
+    target it is matched with."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 3, 400, generator=g, dtype=torch.float64)
+    for perm in ([0, 1, 2], [2, 0, 1], [1, 0, 2]):
+        assert float(M.cost_finetuning(x, x[:, perm])) == 0.0
+    est = (x + 0.05 * torch.randn(3, 3, 400, generator=g, dtype=torch.float64)).requires_grad_(True)
+    c = M.cost_finetuning(x, est)
+    direct = (0.5 * ((x - est) ** 2).sum(-1)).mean(-1).mean()
+    assert abs(float(c) - float(direct)) < 1e-12
+    assert abs(float(M.cost_finetuning(x, est[:, [1, 2, 0]])) - float(c)) < 1e-12
+    grad, = torch.autograd.grad(c, est)
+    assert torch.allclose(grad, (est - x).detach() / 9.0, atol=1e-12)          # 1/(B*S) * (xhat - x)
