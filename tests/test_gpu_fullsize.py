@@ -125,3 +125,44 @@ def test_bench_step_full_size_fp32_vs_bf16(ops):
     assert abs(losses[0] - c32) < 2e-2 * abs(c32), (losses[0], c32)
     assert all(np.isfinite(losses)) and bool(torch.isfinite(t16.store.grad_flat).all())
     assert losses[-1] < losses[0]
+
+
+def test_linear_mixture_front_end_full_size(ops):
+    """BASELINE geometry, 4 mixtures of 2 sources: the linear-mixture path of amss_filterbank_analysis_mix_fwd must (a)
+    leave the source rows bit-identical to the stock tensor-core kernel, (b) produce mixture rows that agree with the
+    fp32 kernel run on x_mix within the bf16 tolerance and pick an arg-max whose fp32 response is within that tolerance
+    of the true maximum, and (c) be positively homogeneous like the operator it replaces."""
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B = 4
+    src = torch.randn(B, 2, L, device="cuda", generator=g) * 0.05
+    x = torch.cat([src[:, 0] + src[:, 1], src.reshape(2 * B, L)], 0).contiguous()
+    filt = torch.randn(W, N, device="cuda", generator=g) / 32
+    y, am = ops.filterbank_analysis_mix(x, filt, B, 2, POOL, POOL, ops.AMSS_PREC_BF16)
+    ys, ams = ops.filterbank_analysis(x, filt, POOL, POOL, ops.AMSS_POOL_MAX, ops.AMSS_PREC_BF16)
+    assert torch.equal(y[B:], ys[B:]) and torch.equal(am[B:], ams[B:])
+    assert not torch.equal(y[:B], ys[:B])                                   # the mixture rows came from the linear path
+    y32, am32 = ops.filterbank_analysis(x[:B].contiguous(), filt, POOL, POOL, ops.AMSS_POOL_MAX, ops.AMSS_PREC_FP32)
+    scale = float(y32.abs().max())
+    assert float((y[:B] - y32).abs().max()) < 1e-2 * scale
+    assert float((am[:B] == am32).float().mean()) > 0.9
+    y4, am4 = ops.filterbank_analysis_mix(4.0 * x, filt, B, 2, POOL, POOL, ops.AMSS_PREC_BF16)
+    assert torch.equal(am4, am) and torch.equal(y4, 4.0 * y)
+
+
+def test_head_gemm_fused_normalise_full_size(ops):
+    """[T*B, 600] x [600, 10240] head product with the l2-normalise epilogue at the bench geometry (8 mixtures): every
+    group of E = 40 output columns has unit norm, inv_norm reproduces the norm of the plain product, and
+    V * norm equals the plain bf16 product."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M, K, NN, E = 250 * 8, 600, 10240, 40
+    h = torch.randn(M, K, device="cuda", generator=g)
+    Wt = torch.randn(K, NN, device="cuda", generator=g) * 0.05
+    b = torch.randn(NN, device="cuda", generator=g) * 0.1
+    hb, Wb = ops.convert_bf16(h), ops.convert_bf16(Wt)
+    V, inv = ops.gemm_bf16(hb, False, Wb, True, M, NN, K, bias=b, norm_E=E)
+    z = ops.gemm_bf16(hb, False, Wb, True, M, NN, K, bias=b)
+    nrm = V.view(M, NN // E, E).double().pow(2).sum(-1).sqrt()
+    assert float((nrm - 1.0).abs().max()) < 1e-5
+    zn = z.view(M, NN // E, E).double().pow(2).sum(-1).sqrt()
+    assert float((inv.view(M, NN // E).double() * zn - 1.0).abs().max()) < 1e-4
+    assert rel(V.view(M, NN // E, E) * zn.unsqueeze(-1).float(), z.view(M, NN // E, E)) < 1e-5
