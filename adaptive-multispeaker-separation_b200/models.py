@@ -66,6 +66,50 @@ class Network:
             self.store.finalize()
         return self
 
+    # ---- model folder: `params` JSON + variables under the reference's names -------------------
+    # models/network.py:124-129 writes the flat kwargs (minus the input tensors) to <folder>/params, :223-226 saves the
+    # variables, :291-306 (`load`) rebuilds a model from that file letting a fixed list of keys be overridden.  TF's
+    # checkpoint bundle cannot be written or read without TensorFlow; the variables go to <folder>/model.npz keyed by
+    # the same names a TF checkpoint of the reference graph uses, so a converter is a rename-free
+    # dump of `tf.train.load_checkpoint(...).get_tensor(name)` on a machine that has TF 1.x.
+    KEYS_TO_UPDATE = ("learning_rate", "epochs", "batch_size", "chunk_size", "nb_speakers", "regularization", "overlap_coef",
+                      "loss", "beta", "model_folder", "type", "pretraining", "with_silence", "end_assign", "beta_kmeans",
+                      "nb_tries", "nb_steps", "threshold", "optimizer", "men", "women", "recurrent_dropout",
+                      "recurrent_dropout_enhance")
+
+    def save(self, folder):
+        import json
+        import os
+        os.makedirs(folder, exist_ok=True)
+        args = {k: v for k, v in self.args.items() if k not in ("mix", "non_mix", "ind")}
+        with open(os.path.join(folder, "params"), "w") as f:
+            json.dump(args, f)
+        self.finalize()
+        np.savez(os.path.join(folder, "model.npz"), **{k: v.numpy() for k, v in self.store.state_dict().items()})
+        return folder
+
+    @classmethod
+    def load(cls, path, modified_args=None):
+        """models/network.py:291-306: the stored kwargs, with `modified_args` applied for the keys in KEYS_TO_UPDATE and
+        for keys the stored file does not have.  Variables are restored separately (restore_model), as in the reference."""
+        import json
+        import os
+        modified_args = dict(modified_args or {})
+        with open(os.path.join(path, "params")) as f:
+            args = json.load(f)
+        upd = {k: modified_args[k] for k in cls.KEYS_TO_UPDATE if k in modified_args}
+        upd.update({k: v for k, v in modified_args.items() if k not in args})
+        args.update(upd)
+        return cls(**args)
+
+    def restore_model(self, path, strict=False):
+        """models/network.py:254-262: load every stored variable this model also has (by name)."""
+        import os
+        self.finalize()
+        with np.load(os.path.join(path, "model.npz")) as z:
+            self.store.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=strict)
+        return self
+
     # the reference's freeze_all_with(prefix) (models/network.py:276-289)
     def freeze_all_with(self, prefix):
         self.store.set_trainable(lambda n, p=prefix: not n.startswith(p) and self.store[n].requires_grad)

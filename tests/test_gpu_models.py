@@ -348,3 +348,20 @@ def test_three_speaker_kmeans_inference(amss):
     with torch.no_grad():
         full = ops.istft_masked(spec, 1, 256, 128, labels=ones)          # a single all-ones mask
     assert rel(out.sum(1), full[:, 0]) < 1e-3
+
+
+def test_model_folder_roundtrip(amss, tmp_path):
+    """`params` JSON + variables under the reference's names (models/network.py:124-129, 223-226, 291-306): save, rebuild
+    with `load` (only the reference's updatable keys are overridden), restore, and get the same embeddings."""
+    mo = amss["models"]
+    cfg = dict(nb_layers=1, layer_size=16, embedding_size=8, window_size=128, hop_size=64, nb_tries=2, nb_steps=3)
+    m = mo.DPCL(plugged=False, **cfg).finalize()
+    folder = m.save(str(tmp_path / "run"))
+    m2 = mo.DPCL.load(folder, {"learning_rate": 0.5, "nb_layers": 7})
+    assert m2.args["learning_rate"] == 0.5 and m2.args["nb_layers"] == 1          # nb_layers is not an updatable key
+    m2.restore_model(folder)
+    assert set(m2.store.names()) == set(m.store.names())
+    assert "prediction/forward_BLSTM_0/rnn/basic_lstm_cell/kernel" in m.store.names()
+    X = torch.rand(2, 20, 65, device="cuda")
+    with torch.no_grad():
+        assert torch.equal(m.prediction(X), m2.prediction(X))
