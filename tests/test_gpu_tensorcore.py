@@ -291,6 +291,51 @@ def test_stft_dpcl_config1_width_bf16_step():
     assert abs(c - c_ref) < 2e-2 * abs(c_ref), (c, c_ref)
 
 
+def test_l41_bf16_step_uses_the_generic_head_backward():
+    """L41 (sigmoid-dot loss on the normalised embeddings) in bf16: the fused dense + l2-normalise forward with the
+    GENERIC backward of _DenseNormFn (dV -> dz -> dx, dW, db), i.e. the path taken when the DPCL cost does not follow."""
+    import functools
+    from amss_b200 import models, trainer
+    from oracle import models as M
+    from oracle import steps as OS
+    B, S, Lw = 3, 2, 4096
+    t = trainer.STFT_Separator_Trainer(models.L41Model, nb_layers=1, layer_size=64, embedding_size=8, learning_rate=1e-3,
+                                       window_size=128, hop_size=64, precision="bf16")
+    p = {k: v.detach().cpu().clone() for k, v in t.store.params.items()}
+    p0 = {k: v.clone() for k, v in p.items()}
+    st = OS.Stepper(p, functools.partial(OS.stft_separator_loss, nb_layers=1, embedding_size=8, window_size=128, hop_size=64,
+                                         loss="l41"), lr=1e-3)
+    mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=700)
+    c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+    c = float(t.train_step(dev(mix), dev(nm), dev(I)))
+    assert abs(c - c_ref) < 2e-2 * abs(c_ref), (c, c_ref)
+    num = den_a = den_b = 0.0
+    for k, v in st.tr.items():
+        da = (t.store[k].detach().cpu() - p0[k]).double().reshape(-1)
+        db = (v.detach() - p0[k]).double().reshape(-1)
+        num += float(da @ db); den_a += float(da @ da); den_b += float(db @ db)
+    assert num / (den_a ** 0.5 * den_b ** 0.5 + 1e-30) > 0.97
+
+
+def test_dpcl_backward_bf16_output_matches_fp32_output(ops):
+    """amss_dpcl_loss_bwd_normalized_bf16 writes the same dz as the fp32-output tensor-core variant, rounded to bf16, and
+    amss_colsum_bf16 sums it like amss_colsum sums the fp32 one."""
+    g = torch.Generator().manual_seed(91)
+    B, TF, E, S = 3, 2000, 40, 2
+    z = dev(torch.randn(B, TF, E, generator=g))
+    lab = dev(torch.randint(0, S, (B, TF), generator=g).to(torch.uint8))
+    V, inv = ops.l2norm_fwd(z, E)
+    loss, ws = ops.dpcl_loss_fwd(V, lab, S, ops.AMSS_PREC_BF16)
+    one = torch.ones(1, device="cuda")
+    dz32 = ops.dpcl_loss_bwd_normalized(V, lab, S, one, ws, inv, ops.AMSS_PREC_BF16)
+    dzb = ops.dpcl_loss_bwd_normalized_bf16(V, lab, S, one, ws, inv)
+    assert dzb.dtype == torch.bfloat16
+    assert torch.equal(dzb, dz32.to(torch.bfloat16))
+    cs = ops.colsum_bf16(dzb.view(B * TF // 50, 50 * E))
+    ref = dzb.view(B * TF // 50, 50 * E).double().sum(0)
+    assert rel(cs, ref) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------ fused DPCL backward
 @pytest.mark.parametrize("B,TF,E,S", [(3, 1000, 40, 2), (2, 130, 40, 3), (5, 128, 16, 2), (2, 4099, 64, 2), (70, 257, 40, 2)])
 def test_dpcl_fused_backward_tc_matches_autograd(ops, B, TF, E, S):
