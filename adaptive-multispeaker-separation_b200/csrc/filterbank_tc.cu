@@ -17,6 +17,7 @@
 // (TMEM lane quadrant = warp % 4), w8-11 Hankel builders.  Persistent: one CTA per SM.
 #include "common.cuh"
 #include "tc.cuh"
+#include <cstdlib>
 
 namespace amss {
 namespace {
@@ -522,7 +523,9 @@ int filterbank_analysis_mix_tc(const float* x, const float* filt, int B, int S, 
     FtParams p;
     int rc = prepare(p, x, filt, L, W, N, pool, hop, y, argmax, workspace, workspace_bytes, Bt, precision, st);
     if (rc != AMSS_OK) return rc;
-    if (!filterbank_analysis_mix_tc_supported(S, L, W, N, pool, hop)) return launch_stock(p, Bt, L, pool, hop, st);
+    // AMSS_NO_LINEAR_MIX=1: always the stock three-signal kernel (A/B measurements; results agree within bf16 rounding)
+    static const bool off = [] { const char* e = getenv("AMSS_NO_LINEAR_MIX"); return e && e[0] == '1'; }();
+    if (off || !filterbank_analysis_mix_tc_supported(S, L, W, N, pool, hop)) return launch_stock(p, Bt, L, pool, hop, st);
     int* flag = reinterpret_cast<int*>(const_cast<uint8_t*>(p.packed) - 256);
     AMSS_CUDA(cudaMemsetAsync(flag, 0, 4, st));
     AMSS_LAUNCH(mix_is_sum_kernel, 4 * kNumSMs, 256, 0, st, x, B, (int64_t)L, flag);
