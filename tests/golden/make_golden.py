@@ -58,6 +58,21 @@ def cases():
     km = KMeans(nb_clusters=3, nb_tries=4, nb_iterations=6)
     cent, labels = km.fit(Xk, init_idx=init)
     out["kmeans"] = dict(X=Xk, init_idx=torch.as_tensor(init), labels=labels.to(torch.int32), centroids=cent)
+    # --- SURVEY 8(f) rows (own generator: the fixtures above keep their values)
+    g2 = torch.Generator().manual_seed(4321)
+    xs3 = torch.randn(2, 3, 800, generator=g2) * 0.1
+    est3 = (xs3[:, [1, 2, 0]] + 0.02 * torch.randn(2, 3, 800, generator=g2)).requires_grad_(True)
+    cft = M.cost_finetuning(xs3, est3)
+    (dest,) = torch.autograd.grad(cft, est3)
+    out["finetune"] = dict(x_non_mix=xs3, est=est3.detach(), cost=cft.detach().reshape(1), dest=dest)
+    from oracle import bss_eval as BE
+    refb = torch.randn(2, 2, 1800, generator=g2, dtype=torch.float64)
+    estb = torch.stack([0.8 * refb[:, 1] + 0.3 * refb[:, 0], refb[:, 0] - 0.1 * refb[:, 1]], 1) \
+        + 0.05 * torch.randn(2, 2, 1800, generator=g2, dtype=torch.float64)
+    res = [BE.bss_eval_sources(refb[b].numpy(), estb[b].numpy()) for b in range(2)]
+    out["bss_eval"] = dict(ref=refb, est=estb, sdr=torch.tensor(np.stack([r[0] for r in res])),
+                           sir=torch.tensor(np.stack([r[1] for r in res])), sar=torch.tensor(np.stack([r[2] for r in res])),
+                           perm=torch.tensor(np.stack([r[3] for r in res])))
     return out
 
 
