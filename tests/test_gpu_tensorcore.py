@@ -273,17 +273,21 @@ def test_training_steps_bf16_track_the_oracle():
     assert cos > 0.98
 
 
-def test_stft_dpcl_config1_width_bf16_step():
-    """BASELINE config 1 widths (2 x BLSTM-300 -> H = 150 per direction, NC = 5 CTAs per cluster) in bf16."""
+@pytest.mark.parametrize("E", [10, 56])
+def test_stft_dpcl_config1_width_bf16_step(E):
+    """BASELINE config 1 widths (2 x BLSTM-300 -> H = 150 per direction, NC = 5 CTAs per cluster) in bf16.  E = 10: not a
+    multiple of 4, the loss runs on the fp32 DPCL kernels behind the bf16 trunk.  E = 56: wider than the fused-normalise
+    epilogue handles (48), so the head takes the unfused dense -> l2_normalize path and the loss node still moves onto
+    the head's (x, W, b) with the bf16 dz hand-over (_amss_dense side channel)."""
     import functools
     from amss_b200 import models, trainer
     from oracle import models as M
     from oracle import steps as OS
     B, S, Lw = 4, 2, 4096
-    t = trainer.STFT_Separator_Trainer(models.DPCL, nb_layers=2, layer_size=300, embedding_size=10, learning_rate=1e-3,
+    t = trainer.STFT_Separator_Trainer(models.DPCL, nb_layers=2, layer_size=300, embedding_size=E, learning_rate=1e-3,
                                        window_size=128, hop_size=64, precision="bf16")
     p = {k: v.detach().cpu().clone() for k, v in t.store.params.items()}
-    st = OS.Stepper(p, functools.partial(OS.stft_separator_loss, nb_layers=2, embedding_size=10, window_size=128, hop_size=64),
+    st = OS.Stepper(p, functools.partial(OS.stft_separator_loss, nb_layers=2, embedding_size=E, window_size=128, hop_size=64),
                     lr=1e-3)
     mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=600)
     c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
