@@ -276,9 +276,9 @@ using namespace amss;
 
 extern "C" size_t amss_gemm_workspace_bytes(int M, int N, int K, int transa, int transb, int precision);
 
+// saved = [activated gates][cell states][bf16 copy of x, [T*B, pad8(I)] -- written and read on the tensor-core path only]
 extern "C" size_t amss_blstm_saved_bytes(int B, int T, int I, int H) {
-    (void)I;
-    return gates_bytes(B, T, H) + cst_bytes(B, T, H);
+    return gates_bytes(B, T, H) + cst_bytes(B, T, H) + align_up((size_t)T * B * pad8i(I) * 2, 256);
 }
 
 extern "C" size_t amss_blstm_workspace_bytes(int B, int T, int I, int H, int precision) {
@@ -313,13 +313,15 @@ extern "C" int amss_blstm_fwd(const float* x, const float* kernel_fw, const floa
     const float* bias[2] = {bias_fw, bias_bw};
     if (precision == AMSS_PREC_BF16) {
         // hoisted input projection on the tensor cores: x is converted once for both directions
+        // (the copy goes into `saved` when there is one: the backward pass reads it instead of converting x again)
         const Bf16Scratch s = bf16_scratch(gws, B, T, I, H);
-        int rc = convert_bf16(x, T * B, I, I, s.xb, s.Ip, st);
+        uint16_t* xb = saved ? (uint16_t*)((char*)saved + gates_bytes(B, T, H) + cst_bytes(B, T, H)) : s.xb;
+        int rc = convert_bf16(x, T * B, I, I, xb, s.Ip, st);
         if (rc != AMSS_OK) return rc;
         for (int d = 0; d < 2; ++d) {
             rc = convert_bf16(kern[d], I, 4 * H, 4 * H, s.wb[d], s.H4p, st);
             if (rc != AMSS_OK) return rc;
-            rc = gemm_bf16(s.xb, s.Ip, 0, s.wb[d], s.H4p, 1, bias[d], T * B, 4 * H, I, 0,
+            rc = gemm_bf16(xb, s.Ip, 0, s.wb[d], s.H4p, 1, bias[d], T * B, 4 * H, I, 0,
                            gates + (size_t)d * T * B * 4 * H, 4 * H, 0, 0, 0, nullptr, st);
             if (rc != AMSS_OK) return rc;
         }
@@ -402,7 +404,8 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
         // every operand is converted to bf16 ONCE (x, each direction's half of y, dZ of both directions, W_x); the
         // t-1 / t+1 shifted views of dW_h are row offsets (multiples of the padded leading dimension: TMA-aligned)
         s = bf16_scratch(gws, B, T, I, H);
-        int rc = convert_bf16(x, T * B, I, I, s.xb, s.Ip, st);
+        s.xb = (uint16_t*)((char*)saved + gates_bytes(B, T, H) + cst_bytes(B, T, H));      // written by amss_blstm_fwd (bf16)
+        int rc = AMSS_OK;
         for (int d = 0; d < 2 && rc == AMSS_OK && T > 1; ++d) rc = convert_bf16(y + d * H, T * B, H, 2 * H, s.yb[d], s.Hp, st);
         if (rc == AMSS_OK && !fused_dz) rc = convert_bf16(dZ, 2 * T * B, H4, H4, s.dzb, s.H4p, st);
         for (int d = 0; d < 2 && rc == AMSS_OK && dx; ++d) rc = convert_bf16(kern[d], I, H4, H4, s.wb[d], s.H4p, st);

@@ -5,6 +5,7 @@
 //   AMSS_PREC_BF16 : tcgen05 bf16 tiles with TMEM accumulators (gemm_tc.cu) when the shape is
 //                    supported, else an error (never a silent fallback).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace amss {
 bool gemm_tc_supported(int M, int N, int K, int lda, int ldb, int ldc, int transa, int transb);
@@ -103,6 +104,32 @@ __global__ void transpose_01_kernel(const float* __restrict__ in, int D0, int D1
     }
 }
 
+// in[D0][D1][C] fp32 -> out[D1][D0][ldd] bf16 (ldd = C padded to 8, zero filled): the [T,B,C] -> [B,T,C] hand-over into
+// the embedding head fused with its operand conversion (one pass instead of transpose + convert)
+__global__ void transpose_01_bf16_kernel(const float* __restrict__ in, int D0, int D1, int C, int ldd, uint4* __restrict__ out) {
+    const int upr = ldd >> 3;
+    const int64_t units = (int64_t)D0 * D1 * upr;
+    const bool vec_ok = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(u % upr) * 8;
+        const int64_t r = u / upr;                       // output row d1*D0 + d0
+        const int d0 = (int)(r % D0), d1 = (int)(r / D0);
+        const float* s = in + ((size_t)d0 * D1 + d1) * C + c0;
+        float v[8];
+        if (c0 + 8 <= C && vec_ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = c0 + e < C ? __ldg(s + e) : 0.f;
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+        out[u] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                            *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+    }
+}
+
 }  // namespace
 
 int sgemm_launch(const float* A, int lda, const float* B, int ldb, const float* bias, int M, int N, int K, int transa,
@@ -184,4 +211,12 @@ extern "C" int amss_gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16
     AMSS_REQUIRE(out_swap_b == 0 || (int64_t)out_swap_b * out_swap_t == M, "gemm_bf16: out_swap_b*out_swap_t != M");
     return gemm_bf16(A, lda, a_mn ? 1 : 0, B, ldb, b_mn ? 1 : 0, bias, M, N, K, accumulate, C, ldc, out_swap_b,
                      out_swap_t, norm_E, inv_norm, (cudaStream_t)stream);
+}
+
+extern "C" int amss_transpose_01_bf16(const float* in, int D0, int D1, int C, uint16_t* out, int ldd, void* stream) {
+    AMSS_REQUIRE(in && out && D0 > 0 && D1 > 0 && C > 0, "transpose_01_bf16: bad arguments");
+    AMSS_REQUIRE(ldd >= C && ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "transpose_01_bf16: ldd must be a multiple of 8 (>= C) and out 16-byte aligned");
+    AMSS_LAUNCH(transpose_01_bf16_kernel, 8 * kNumSMs, 256, 0, stream, in, D0, D1, C, ldd, (uint4*)out);
+    return AMSS_OK;
 }

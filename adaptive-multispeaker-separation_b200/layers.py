@@ -183,10 +183,12 @@ class _DenseNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, b, E, swap):
-        if swap:
+        if swap:                         # [T,B,C] -> [B*T,C] re-order fused with the bf16 conversion
             Bq, Tq = swap
-            x = ops.transpose_01(x.view(Tq, Bq, -1)).view(Bq * Tq, -1)
-        xb, Wb = ops.convert_bf16(x), ops.convert_bf16(W)
+            xb = ops.transpose_01_bf16(x.view(Tq, Bq, -1).contiguous())
+        else:
+            xb = ops.convert_bf16(x)
+        Wb = ops.convert_bf16(W)
         V, inv = ops.gemm_bf16(xb, False, Wb, True, x.shape[0], W.shape[1], W.shape[0], bias=b, norm_E=E)
         ctx.save_for_backward(xb, Wb, V, inv)
         ctx.E, ctx.swap, ctx.bf16_operands = E, swap, (xb, Wb)

@@ -214,6 +214,16 @@ def gemm(A, B, bias=None, transa=False, transb=False, out=None, accumulate=False
     return out
 
 
+def transpose_01_bf16(x):
+    """x[D0,D1,C] fp32 -> bf16 [D1*D0, pad8(C)] (rows in [D1][D0] order, zero padded): transpose_01 + convert_bf16 fused."""
+    _chk(x)
+    D0, D1, C = x.shape
+    ldd = (C + 7) // 8 * 8
+    out = torch.empty(D1 * D0, ldd, dtype=torch.bfloat16, device=x.device)
+    _lib.call("amss_transpose_01_bf16", _p(x), D0, D1, C, _p(out), ldd, _stream())
+    return out
+
+
 def convert_bf16(x):
     """fp32 [rows, cols] (unit inner stride) -> bf16 [rows, pad8(cols)] (zero padded): operand of gemm_bf16."""
     if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:

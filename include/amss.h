@@ -140,7 +140,9 @@ int amss_istft_masked_bwd(const float* spec, const float* dout, int B, int S, in
 /* One bidirectional layer, TIME-MAJOR activations: x[T,B,I]; kernel_{fw,bw}[I+H,4H] (TF
  * layout: rows 0..I-1 multiply x, rows I..I+H-1 multiply h); bias_{fw,bw}[4H] ->
  * y[T,B,2H] (fw | bw).  The reference layout is [B,T,*]: amss_transpose_01 converts.
- * `saved` (optional, NULL for inference) receives what the backward pass needs.        */
+ * `saved` (optional, NULL for inference) receives what the backward pass needs; it must
+ * be handed to amss_blstm_bwd with the SAME precision (the tensor-core path keeps a bf16
+ * copy of x in it).                                                                      */
 size_t amss_blstm_workspace_bytes(int B, int T, int I, int H, int precision);
 size_t amss_blstm_saved_bytes(int B, int T, int I, int H);
 int amss_blstm_fwd(const float* x, const float* kernel_fw, const float* bias_fw,
@@ -187,6 +189,10 @@ int amss_convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* ds
                       void* stream);
 /* in[D0,D1,C] -> out[D1,D0,C]                                                           */
 int amss_transpose_01(const float* in, int D0, int D1, int C, float* out, void* stream);
+/* Same, writing bf16 rows of ldd (= C padded to 8, zero filled) elements: the time-major ->
+ * batch-major hand-over into the embedding head fused with its operand conversion.        */
+int amss_transpose_01_bf16(const float* in, int D0, int D1, int C, uint16_t* out, int ldd,
+                           void* stream);
 size_t amss_gemm_workspace_bytes(int M, int N, int K, int transa, int transb, int precision);
 /* dbias[N] = column sums of a bf16 [M,N] matrix (N even); workspace as amss_colsum.       */
 int amss_colsum_bf16(const uint16_t* dZ, int64_t M, int N, float* dbias, void* workspace,

@@ -175,6 +175,18 @@ def test_gemm_bf16_fused_l2_normalize_epilogue(ops, M, N, K, E):
     assert rel(dx, dzb.double().cpu()[:, :N] @ bf16_round(W).double().t()) < 1e-4
 
 
+@pytest.mark.parametrize("D0,D1,C", [(7, 5, 600), (13, 3, 37), (250, 4, 256)])
+def test_transpose_01_bf16_is_transpose_then_round(ops, D0, D1, C):
+    g = torch.Generator().manual_seed(24)
+    x = torch.randn(D0, D1, C, generator=g)
+    out = ops.transpose_01_bf16(dev(x))
+    Cp = (C + 7) // 8 * 8
+    assert out.shape == (D1 * D0, Cp) and out.dtype == torch.bfloat16
+    ref = x.transpose(0, 1).reshape(D1 * D0, C).to(torch.bfloat16)
+    assert torch.equal(out[:, :C].cpu(), ref)
+    assert bool((out[:, C:] == 0).all())
+
+
 def test_gemm_tc_strided_accumulate_swap(ops):
     g = torch.Generator().manual_seed(22)
     Tt, Bb, C, N = 50, 6, 40, 72
