@@ -10,6 +10,7 @@ import time
 import numpy as np
 import torch
 
+from . import _lib
 from . import dp, ops
 from .models import Adapt, DPCL, L41Model, DEFAULTS  # noqa: F401
 
@@ -180,8 +181,50 @@ class Trainer:
             out.append(buf.to("cuda", non_blocking=True))
         return out
 
+    # -- optional CUDA-graph replay of forward + backward ---------------------------------------
+    def enable_cuda_graph(self, eager_steps=2):
+        """Capture zero-grad + loss + backward of one step into a CUDA graph (after `eager_steps` ordinary steps, which
+        also warm every lazily initialised kernel attribute) and replay it from then on; the gradient all-reduce and the
+        optimizer stay outside the graph (their arguments change per step).  Each train_step() call is still exactly
+        one optimisation step on the batch it is given (inputs are copied into the graph's static buffers).  The loss
+        must not depend on host-side state that changes between steps (k-means initial rows, Python control flow on
+        data): use it for the Front / STFT separator trainers."""
+        self._cg = {"eager": int(eager_steps), "calls": 0, "graph": None, "inputs": None, "cost": None}
+
+    def graph_kernel_launches(self):
+        """Library kernels executed through graph replays so far (they do not pass through the host-side launch counter)."""
+        cg = getattr(self, "_cg", None)
+        return cg["kernels"] * cg["replays"] if cg and cg["graph"] is not None else 0
+
+    def _capture_step(self, x_mix, x_non_mix, ind):
+        cg = self._cg
+        cg["inputs"] = [t.clone() for t in (x_mix, x_non_mix, ind)]
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            self.store.grad_flat.zero_()
+            cost = self.loss(*cg["inputs"])
+            cost.backward()
+        cg["graph"], cg["cost"] = graph, cost.detach()
+        cg["kernels"] = _lib.launch_count() - n0          # library kernels recorded in the graph = run by every replay
+        cg["replays"] = 0
+
     # -- one optimisation step on device tensors ------------------------------------------------
     def train_step(self, x_mix, x_non_mix, ind):
+        cg = getattr(self, "_cg", None)
+        if cg is not None:
+            if cg["graph"] is None and cg["calls"] >= cg["eager"]:
+                self._capture_step(x_mix, x_non_mix, ind)
+            cg["calls"] += 1
+            if cg["graph"] is not None:
+                for dst, src in zip(cg["inputs"], (x_mix, x_non_mix, ind)):
+                    dst.copy_(src, non_blocking=True)
+                cg["graph"].replay()
+                cg["replays"] += 1
+                scale = dp.allreduce_sum_(self.store.grad_flat)
+                self.optimizer.step(scale)
+                return cg["cost"].clone()
         self.store.grad_flat.zero_()
         cost = self.loss(x_mix, x_non_mix, ind)
         cost.backward()

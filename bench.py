@@ -171,15 +171,20 @@ def run_gpu(args):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 x = torch.cat([x_mix, x_non_mix.reshape(Bq * S, -1)], 0).contiguous()
                 filt = self.model.conv_filter("front")
-                e0.record()
+                capturing = torch.cuda.is_current_stream_capturing()      # (--cuda-graph: events cannot be timed in a graph)
+                if not capturing:
+                    e0.record()
                 y, _ = ops.filterbank_analysis_mix(x, filt, Bq, S, CFG["max_pool"], CFG["hop_size"], self.model.precision)
-                e1.record()
-                front_events.append((e0, e1))
+                if not capturing:
+                    e1.record()
+                    front_events.append((e0, e1))
             inp = self.sepNet.plugged_inputs(y, Bq)
             V = self.sepNet.prediction(inp["X"].contiguous())
             return self.sepNet.cost(V, inp["labels"], ind)
 
     t = BenchTrainer(models.DPCL, precision=args.precision, **CFG)
+    if args.cuda_graph:
+        t.enable_cuda_graph()
     stream = synth.SyntheticStream(B, S, L_SAMPLES, seed=42, rank=rank, pool=2)
     host_batches = [next(stream) for _ in range(2)]
     dev_batches = [[torch.as_tensor(a).cuda() for a in hb] for hb in host_batches]
@@ -212,10 +217,10 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     front_events.clear()
-    n0 = _lib.launch_count()
+    n0, g0 = _lib.launch_count(), t.graph_kernel_launches()
     ms = timed(lambda i: t.train_step(*dev_batches[i % 2]), args.steps)
-    launches = _lib.launch_count() - n0
-    front_ms = [a.elapsed_time(b) for a, b in front_events]
+    launches = (_lib.launch_count() - n0) + (t.graph_kernel_launches() - g0)     # host launches + kernels run by graph replays
+    front_ms = [a.elapsed_time(b) for a, b in front_events]      # empty when the steps were graph replays (see below)
 
     # -- end-to-end timing through the public trainer API: every step copies ITS batch from pinned host memory
     #    (side stream, one step ahead, as Trainer.train does) and reads ITS loss back (one step delayed) ----------
@@ -249,6 +254,15 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(ms_e2e_t, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_e2e_t)
+    if args.cuda_graph:
+        # kernels replayed from a graph cannot be bracketed by CUDA events: time the dominant kernel in three ordinary
+        # (host-launched) steps run right here, same process, same clocks, same inputs
+        t._cg = None
+        front_events.clear()
+        for i in range(3):
+            t.train_step(*dev_batches[i % 2])
+        barrier()
+        front_ms = [a.elapsed_time(b) for a, b in front_events]
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -275,7 +289,7 @@ def run_gpu(args):
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "precision": args.precision,
+                   "precision": args.precision, "cuda_graph": bool(args.cuda_graph),
                    "front": ("mixture rows by linearity of the convolution (x_mix == x_0 + x_1 verified on the device per "
                              "batch; stock kernel otherwise)" if linear else "stock: all B*(S+1) signals convolved"),
                    "l2": "per-step working set (embeddings V + dV + saved gates) exceeds the 126 MB L2; "
@@ -336,6 +350,9 @@ def main():
                     help="bf16 = tcgen05 kernels (BASELINE configs[1]); fp32 = the SIMT parity kernels")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                    help="launch every kernel of the step from the host instead of replaying forward + backward from a CUDA "
+                         "graph (Trainer.enable_cuda_graph, the default here: the step has ~100 launches)")
     ap.add_argument("--stock-front", action="store_true",
                     help="A/B: run all B*(S+1) signals through the stock analysis kernel instead of deriving the mixture "
                          "rows from the source rows by linearity (sets AMSS_NO_LINEAR_MIX=1)")

@@ -365,3 +365,24 @@ def test_model_folder_roundtrip(amss, tmp_path):
     X = torch.rand(2, 20, 65, device="cuda")
     with torch.no_grad():
         assert torch.equal(m.prediction(X), m2.prediction(X))
+
+
+def test_cuda_graph_replay_equals_eager_steps(amss):
+    """Trainer.enable_cuda_graph: forward + backward replayed from a CUDA graph (captured after two eager steps) must
+    leave exactly the same parameters as five eager steps on the same batches (same kernels, same order)."""
+    tr, mo = amss["trainer"], amss["models"]
+    cfg = dict(nb_layers=2, layer_size=64, embedding_size=8, learning_rate=1e-3, window_size=64, filters=16, max_pool=32,
+               hop_size=32, with_max_pool=True, precision="bf16")
+    B, S, Lw = 3, 2, 4096
+    batches = [M.synthetic_mixtures(B, S, Lw, seed=800 + i) for i in range(5)]
+    ta = tr.Front_Separator_Trainer(mo.DPCL, **cfg)
+    tb = tr.Front_Separator_Trainer(mo.DPCL, **cfg)
+    tb.store.load_state_dict(ta.store.state_dict())
+    tb.enable_cuda_graph(eager_steps=2)
+    for mix, nm, I in batches:
+        ca = ta.train_step(_dev(mix), _dev(nm), _dev(I))
+        cb = tb.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert float(ca) == float(cb)
+    assert tb._cg["graph"] is not None and tb._cg["replays"] == 3 and tb.graph_kernel_launches() > 0
+    for k in ta.store.names():
+        assert torch.equal(ta.store[k], tb.store[k]), k
