@@ -255,14 +255,15 @@ def run_gpu(args):
         dist.all_reduce(ms_e2e_t, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_e2e_t)
     if args.cuda_graph:
-        # kernels replayed from a graph cannot be bracketed by CUDA events: time the dominant kernel in three ordinary
-        # (host-launched) steps run right here, same process, same clocks, same inputs
+        # kernels replayed from a graph cannot be bracketed by CUDA events: time the dominant kernel in ordinary
+        # (host-launched) steps run right here, same process, same clocks, same inputs -- the last three of six, once the
+        # host is again a step ahead of the device (otherwise its launch latency sits between the two events)
         t._cg = None
         front_events.clear()
-        for i in range(3):
+        for i in range(6):
             t.train_step(*dev_batches[i % 2])
         barrier()
-        front_ms = [a.elapsed_time(b) for a, b in front_events]
+        front_ms = [a.elapsed_time(b) for a, b in front_events][-3:]
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
