@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""BSS-eval throughput: batched float64 device implementation vs the oracle's per-mixture numpy loop (same box).
-    python tools/bench_bss_eval.py [--batch 16] [--len 64000]"""
+"""BSS-eval throughput of the batched float64 device implementation.
+    python tools/bench_bss_eval.py [--batch 16] [--len 64000]
+(The per-mixture numpy loop of the reference's vendored mir_eval code runs at ~6 mixtures/s on the same box at
+L = 64000; it lives in oracle/, which only tests / smoke / the bench's CPU leg may import.)"""
 import argparse
 import os
 import sys
@@ -13,7 +15,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import amss_b200  # noqa: E402,F401
 from amss_b200 import bss_eval as G  # noqa: E402
-from oracle import bss_eval as O  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
@@ -29,8 +30,4 @@ t0 = time.time()
 out = G.bss_eval_sources(r, e)
 torch.cuda.synchronize()
 tg = time.time() - t0
-t0 = time.time()
-o = O.bss_eval_sources(ref[0], est[0])
-tc = time.time() - t0
-print(f"device: {a.batch / tg:.1f} mixtures/s ({tg * 1e3:.1f} ms for {a.batch});  oracle (numpy, 1 mixture): {1 / tc:.2f} mixtures/s;"
-      f"  max |sdr diff| on mixture 0: {np.abs(out[0][0].cpu().numpy() - o[0]).max():.2e}")
+print(f"device: {a.batch / tg:.1f} mixtures/s ({tg * 1e3:.1f} ms for {a.batch});  sdr of mixture 0: {out[0][0].cpu().numpy()}")
