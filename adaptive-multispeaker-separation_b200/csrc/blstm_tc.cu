@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
 
     if (warp < 4) {
         // =========================== compute warps ===========================
-        const int q = warp, ug = u0 + lane;
+        const int q = warp;
         constexpr int ITEMS = (8 * NB + 127) / 128;   // (k-chunk, half, mixture) items of 4 units per thread in the cell phase
         float creg[ITEMS][4];
 #pragma unroll
@@ -157,7 +157,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
         const float fb = q == 2 ? p.forget_bias : 0.f;
         long long* prof = (blockIdx.x == 0 && tid == 0) ? p.prof : nullptr;
         for (int s = 0; s < T; ++s) {
-            const int t = d == 0 ? s : T - 1 - s;
             PROF(0);
             uint32_t acc[NB];
             if (s > 0) {
@@ -255,7 +254,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFw
     } else {
         // =========================== writer warps: saved gates, c, y -> global ===========================
         const int wt = tid - 160;                     // 0..127
-        const int wq = wt >> 5, wu = u0 + (wt & 31);  // gate / unit for the gate stores
         auto flush_cy = [&](int sprev) {
             const int tp = d == 0 ? sprev : T - 1 - sprev;
             const float* cys = cy + (sprev & 1) * (2 * NB * 33);
@@ -472,7 +470,6 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
         // =========================== compute warps ===========================
         const int q = warp;
         constexpr int IT = NB / 4;                    // mixtures per thread: b = q*IT + i, unit = lane
-        const int ug = u0 + lane;
         float dcc[IT];
 #pragma unroll
         for (int i = 0; i < IT; ++i) dcc[i] = 0.f;

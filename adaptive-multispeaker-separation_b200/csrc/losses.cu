@@ -9,10 +9,8 @@
 namespace amss {
 namespace {
 
-constexpr int LS_TILE = 128;    // points staged per tile
 constexpr int LS_THREADS = 256;
 constexpr int LS_MAXS = 4;
-constexpr int LS_RB = 4;        // register block (RB x RB entries of the E x E Gram matrix per thread)
 
 // ---- DPCL forward --------------------------------------------------------------------------
 // Y is one-hot, so with N_s = #bins of speaker s and w_i = N_{l_i}^{-1/2}:
