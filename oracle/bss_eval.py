@@ -3,8 +3,11 @@
 The reference vendors mir_eval's `bss_eval_sources` (utils/bss_eval.py:156-370; Vincent et al. 2006, section III.B,
 512-tap time-invariant distortion filters) and calls it per mixture from its evaluation script
 (experiments/evaluation/eval.py:48-73).  Restated here with numpy / scipy, loop for loop, as the checker for
-amss_b200.bss_eval.  Parity unpinned in the sense of DESIGN.md section 2: neither the
-reference nor mir_eval can be run here; the algorithm is the published one.
+amss_b200.bss_eval.  PARITY PINNED: the numpy part of the reference module runs in the build
+container once its two unusable imports are dropped (oracle/make_ref.py -> oracle/_ref/bss_eval_ref.py, git-ignored);
+tests/golden/bss_eval_reference.npz holds the reference's own outputs (its __main__ demo, utils/bss_eval.py:753-760, a
+seeded batch and a 3-source case; generator tests/golden/make_bss_eval_golden.py) and tests/test_bss_eval.py checks this
+restatement and the product against them to 1e-9 / 1e-7 dB.
 """
 import itertools
 

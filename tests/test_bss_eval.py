@@ -54,3 +54,68 @@ def test_bss_eval_properties():
 @pytest.mark.gpu
 def test_bss_eval_matches_oracle_gpu():
     _check("cuda")
+
+
+# ---- pinned against THE REFERENCE's own implementation (utils/bss_eval.py:1-371, run by tests/golden/make_bss_eval_golden.py
+# through oracle/make_ref.py): fixture tests/golden/bss_eval_reference.npz -----------------------------------------------------
+def _reference_fixture():
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_bss_eval_golden import demo_inputs
+    z = np.load(os.path.join(here, "golden", "bss_eval_reference.npz"))
+    demo_ref, demo_est = demo_inputs()
+    cases = [("demo", demo_ref[None], demo_est[None]), ("batch", z["batch_ref"], z["batch_est"]),
+             ("s3", z["s3_ref"][None], z["s3_est"][None])]
+    return z, cases
+
+
+def test_oracle_pinned_to_reference_bss_eval():
+    """The reference's printed demo (utils/bss_eval.py:753-760) and two more cases: oracle == reference to 1e-9 dB."""
+    z, cases = _reference_fixture()
+    for name, ref, est in cases:
+        for b in range(ref.shape[0]):
+            sdr, sir, sar, perm = O.bss_eval_sources(ref[b], est[b])
+            want = [np.atleast_2d(z[f"{name}_{k}"])[b] for k in ("sdr", "sir", "sar", "perm")]
+            assert np.array_equal(perm, want[3]), name
+            for got, w in zip((sdr, sir, sar), want[:3]):
+                assert np.abs(got - w).max() < 1e-9, (name, got, w)
+    demo_ref, demo_est = cases[0][1][0], cases[0][2][0]
+    s = O.bss_eval_sources(demo_ref, demo_est, compute_permutation=False)
+    for got, k in zip(s[:3], ("sdr", "sir", "sar")):
+        assert np.abs(got - z[f"demo_noperm_{k}"]).max() < 1e-9
+
+
+def test_oracle_equals_live_reference_when_present():
+    """When oracle/_ref has been generated (build() does it wherever /root/reference exists) the comparison also runs live."""
+    from oracle import make_ref
+    ref_mod = make_ref.load()
+    if ref_mod is None:
+        pytest.skip("oracle/_ref/bss_eval_ref.py not generated (no /root/reference on this box)")
+    ref, est = _case(5, B=1, S=2, L=3000)
+    want = ref_mod.bss_eval_sources(ref[0], est[0])
+    got = O.bss_eval_sources(ref[0], est[0])
+    assert np.array_equal(got[3], want[3])
+    for g, w in zip(got[:3], want[:3]):
+        assert np.abs(g - w).max() < 1e-9
+
+
+def _product_vs_reference(device):
+    from amss_b200 import bss_eval as G
+    z, cases = _reference_fixture()
+    for name, ref, est in cases:
+        sdr, sir, sar, perm = G.bss_eval_sources(torch.tensor(ref, device=device), torch.tensor(est, device=device))
+        for k, got in (("sdr", sdr), ("sir", sir), ("sar", sar)):
+            want = np.atleast_2d(z[f"{name}_{k}"])
+            assert np.abs(got.cpu().numpy() - want).max() < 1e-7, (name, k)
+        assert np.array_equal(perm.cpu().numpy(), np.atleast_2d(z[f"{name}_perm"])), name
+
+
+def test_product_pinned_to_reference_bss_eval_cpu():
+    _product_vs_reference("cpu")
+
+
+@pytest.mark.gpu
+def test_product_pinned_to_reference_bss_eval_gpu():
+    _product_vs_reference("cuda")
