@@ -61,9 +61,71 @@ __global__ void sumsq_final_kernel(const float* __restrict__ part, int nparts, f
     a = block_sum(a, red);
     if (threadIdx.x == 0) sumsq[0] += a;
 }
-__global__ void clip_factor_kernel(const float* __restrict__ sumsq, float clip, float* __restrict__ factor) {
-    // tf.clip_by_global_norm: g * clip / max(global_norm, clip)
-    if (threadIdx.x == 0) factor[0] = clip / fmaxf(sqrtf(sumsq[0]), clip);
+__global__ void clip_factor_kernel(const float* __restrict__ sumsq, float clip, float gscale, float* __restrict__ factor) {
+    // tf.clip_by_global_norm: g * clip / max(global_norm, clip), the norm being that of gscale * g (gscale = 1 / world size:
+    // the buffer holds the SUM of the per-rank gradients, the reference clips the gradient of the batch-mean loss)
+    if (threadIdx.x == 0) factor[0] = clip / fmaxf(fabsf(gscale) * sqrtf(sumsq[0]), clip);
+}
+
+// tf.train.MomentumOptimizer(lr, momentum) (models/network.py:183): accum = momentum * accum + g ; p -= lr * accum.
+// 5 array passes (read p,g,accum; write p,accum) = 20 B per parameter: HBM-bound.
+__global__ void momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ acc, int64_t n,
+                                float lr, float momentum, float gscale, const float* __restrict__ gscale_dev) {
+    if (gscale_dev) gscale *= gscale_dev[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 aa = reinterpret_cast<float4*>(acc)[i];
+#define MOM1(c) { aa.c = momentum * aa.c + gg.c * gscale; pp.c -= lr * aa.c; }
+        MOM1(x) MOM1(y) MOM1(z) MOM1(w)
+#undef MOM1
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(acc)[i] = aa;
+    }
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float a = momentum * acc[i] + g[i] * gscale;
+        acc[i] = a;
+        p[i] -= lr * a;
+    }
+}
+
+// tf.train.RMSPropOptimizer(lr) (models/network.py:185; TF 1.x defaults decay 0.9, momentum 0, epsilon 1e-10, not centered;
+// the `rms` slot starts at ONE, the `momentum` slot at zero -- the caller initialises them):
+//   ms = decay * ms + (1 - decay) * g^2 ; mom = momentum * mom + lr * g * rsqrt(ms + eps) ; p -= mom.
+// 7 array passes = 28 B per parameter.
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ ms,
+                               float* __restrict__ mom, int64_t n, float lr, float decay, float momentum, float eps,
+                               float gscale, const float* __restrict__ gscale_dev) {
+    if (gscale_dev) gscale *= gscale_dev[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 ss = reinterpret_cast<float4*>(ms)[i];
+        float4 mm = reinterpret_cast<float4*>(mom)[i];
+#define RMS1(c)                                                     \
+        {                                                           \
+            const float gi = gg.c * gscale;                         \
+            ss.c = decay * ss.c + (1.f - decay) * gi * gi;          \
+            mm.c = momentum * mm.c + lr * gi / sqrtf(ss.c + eps);   \
+            pp.c -= mm.c;                                           \
+        }
+        RMS1(x) RMS1(y) RMS1(z) RMS1(w)
+#undef RMS1
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(ms)[i] = ss;
+        reinterpret_cast<float4*>(mom)[i] = mm;
+    }
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i] * gscale;
+        const float si = decay * ms[i] + (1.f - decay) * gi * gi;
+        const float mi = momentum * mom[i] + lr * gi / sqrtf(si + eps);
+        ms[i] = si; mom[i] = mi;
+        p[i] -= mi;
+    }
 }
 
 __global__ void make_filter_kernel(const float* __restrict__ window, const float* __restrict__ bases, int W, int N,
@@ -114,9 +176,28 @@ extern "C" int amss_sumsq(const float* g, int64_t n, float* sumsq, void* workspa
     AMSS_LAUNCH(sumsq_final_kernel, 1, 256, 0, stream, (const float*)workspace, grid, sumsq);
     return AMSS_OK;
 }
-extern "C" int amss_clip_factor(const float* sumsq, float clip, float* factor, void* stream) {
+extern "C" int amss_clip_factor(const float* sumsq, float clip, float grad_scale, float* factor, void* stream) {
     AMSS_REQUIRE(sumsq && factor && clip > 0.f, "clip_factor: bad arguments");
-    AMSS_LAUNCH(clip_factor_kernel, 1, 32, 0, stream, sumsq, clip, factor);
+    AMSS_LAUNCH(clip_factor_kernel, 1, 32, 0, stream, sumsq, clip, grad_scale, factor);
+    return AMSS_OK;
+}
+
+extern "C" int amss_momentum_step(float* p, const float* g, float* accum, int64_t n, float lr, float momentum,
+                                  float grad_scale, const float* grad_scale_dev, void* stream) {
+    AMSS_REQUIRE(p && g && accum && n > 0, "momentum_step: bad arguments");
+    AMSS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)accum) & 15) == 0, "momentum_step: buffers must be 16-byte aligned");
+    const int grid = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 8 * kNumSMs);
+    AMSS_LAUNCH(momentum_kernel, grid, 256, 0, stream, p, g, accum, n, lr, momentum, grad_scale, grad_scale_dev);
+    return AMSS_OK;
+}
+
+extern "C" int amss_rmsprop_step(float* p, const float* g, float* ms, float* mom, int64_t n, float lr, float decay,
+                                 float momentum, float eps, float grad_scale, const float* grad_scale_dev, void* stream) {
+    AMSS_REQUIRE(p && g && ms && mom && n > 0, "rmsprop_step: bad arguments");
+    AMSS_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)ms | (uintptr_t)mom) & 15) == 0,
+                 "rmsprop_step: buffers must be 16-byte aligned");
+    const int grid = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 8 * kNumSMs);
+    AMSS_LAUNCH(rmsprop_kernel, grid, 256, 0, stream, p, g, ms, mom, n, lr, decay, momentum, eps, grad_scale, grad_scale_dev);
     return AMSS_OK;
 }
 

@@ -37,6 +37,14 @@ def allreduce_sum_(flat):
     return 1.0 / dist.get_world_size()
 
 
+def clip_factor(norm_of_sum, clip, grad_scale=1.0):
+    """Host statement of what amss_clip_factor computes on the device: tf.clip_by_global_norm (models/network.py:191-192)
+    acts on the gradient of the batch-MEAN loss, while after the all-reduce the buffer holds the SUM over the G ranks,
+    so the norm that is compared with `clip` is |grad_scale| * ||sum|| with grad_scale = 1/G.  The optimizer then
+    multiplies the buffer by grad_scale * clip_factor."""
+    return clip / max(abs(grad_scale) * norm_of_sum, clip)
+
+
 def max_over_ranks(value, device="cpu"):
     """Timing helper: max of a python float over ranks (multi-GPU numbers are max-over-ranks)."""
     if not active():

@@ -32,6 +32,7 @@ class ParamStore:
         self.flat = None
         self.grad_flat = None
         self._slices = {}
+        self._segments = None
 
     def register(self, name, init, trainable=True):
         if self.flat is not None:
@@ -70,12 +71,39 @@ class ParamStore:
 
     def set_trainable(self, predicate):
         """Freeze / unfreeze by name (the reference's freeze_all_with / --train substrings).
-        Frozen parameters keep their slot in the flat buffer; their gradient slice stays zero."""
+        Frozen parameters keep their slot in the flat buffer, but leave the trainable segments: the optimizer and the
+        gradient exchange skip them (the reference removes them from the optimizer's var_list), and their gradient
+        slice is zeroed so that nothing stale is ever applied if they are unfrozen again."""
         for name, p in self.params.items():
             o, n, shape, tr = self._slices[name]
             if not tr:
                 continue
-            p.requires_grad_(bool(predicate(name)))
+            keep = bool(predicate(name))
+            if p.requires_grad and not keep:
+                self.grad_flat[o:o + n].zero_()
+            p.requires_grad_(keep)
+        self._segments = None
+
+    def trainable_segments(self):
+        """[(offset, length)] of the maximal contiguous runs of the flat buffer occupied by parameters that currently
+        require a gradient (16-byte aligned by construction; the alignment padding between neighbours is included)."""
+        if self._segments is None:
+            segs = []
+            for name, (o, n, _, tr) in sorted(self._slices.items(), key=lambda kv: kv[1][0]):
+                if not tr or not self.params[name].requires_grad:
+                    continue
+                n4 = (n + 3) // 4 * 4
+                if segs and segs[-1][0] + segs[-1][1] == o:
+                    segs[-1] = (segs[-1][0], segs[-1][1] + n4)
+                else:
+                    segs.append((o, n4))
+            self._segments = segs
+        return self._segments
+
+    def trainable_span(self):
+        """(lo, hi) covering every trainable segment: the range the single gradient all-reduce runs over."""
+        segs = self.trainable_segments()
+        return (segs[0][0], segs[-1][0] + segs[-1][1]) if segs else (0, 0)
 
     def state_dict(self):
         return {k: v.detach().cpu().clone() for k, v in self.params.items()}
@@ -86,7 +114,16 @@ class ParamStore:
                 if strict:
                     raise KeyError(k)
                 continue
-            self.params[k].data.copy_(torch.as_tensor(v).to(self.device))
+            v = torch.as_tensor(v)
+            tgt = self.params[k]
+            if tuple(v.shape) != tuple(tgt.shape):
+                # a raw TF checkpoint stores Conv1D filters as [1, in, out] (utils/ops.py:486-494): singleton axes may differ,
+                # anything else (which copy_ would silently broadcast) is an error
+                squeeze = lambda sh: tuple(d for d in sh if d != 1)  # noqa: E731
+                if squeeze(v.shape) != squeeze(tgt.shape):
+                    raise ValueError(f"{k}: stored shape {tuple(v.shape)} does not match {tuple(tgt.shape)}")
+                v = v.reshape(tgt.shape)
+            tgt.data.copy_(v.to(self.device))
 
     # initialisers (distribution-faithful to the reference; TF's RNG stream cannot be matched)
     def glorot(self, shape, fan_in, fan_out):

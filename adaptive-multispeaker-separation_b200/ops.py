@@ -438,6 +438,20 @@ def apply_masks(X_input, S, labels=None, soft=None):
 
 
 # ------------------------------------------------------------------------------------------
+# input contract
+# ------------------------------------------------------------------------------------------
+def prepare_inputs(x_non_mix, normalize=False):
+    """x_non_mix [B,S,L] -> (x_mix [B,L], stats [B*S,2] or None): the mixture as the sequential fp32 sum of the sources;
+    normalize=True first normalises every source row IN PLACE to zero mean / unit (population) variance."""
+    _chk(x_non_mix)
+    B, S, Lw = x_non_mix.shape
+    x_mix = torch.empty(B, Lw, dtype=_f32, device=x_non_mix.device)
+    stats = torch.empty(B * S, 2, dtype=_f32, device=x_non_mix.device) if normalize else None
+    _lib.call("amss_prepare_inputs", _p(x_non_mix), B, S, Lw, int(bool(normalize)), _p(stats), _p(x_mix), _stream())
+    return x_mix, stats
+
+
+# ------------------------------------------------------------------------------------------
 # optimizer
 # ------------------------------------------------------------------------------------------
 def amsgrad_step(p, g, m, v, vhat, lr_t, beta1, beta2, eps, grad_scale=1.0, grad_scale_dev=None):
@@ -446,14 +460,30 @@ def amsgrad_step(p, g, m, v, vhat, lr_t, beta1, beta2, eps, grad_scale=1.0, grad
               float(beta2), float(eps), float(grad_scale), _p(grad_scale_dev), _stream())
 
 
-def global_norm_clip_factor(g, clip):
-    """-> device scalar clip / max(||g||, clip)  (tf.clip_by_global_norm)."""
-    _chk(g)
-    sumsq = torch.zeros(1, dtype=_f32, device=g.device)
-    ws = _ws(_lib.query("amss_sumsq_workspace_bytes"), g.device)
-    _lib.call("amss_sumsq", _p(g), g.numel(), _p(sumsq), _p(ws), _stream())
-    factor = torch.empty(1, dtype=_f32, device=g.device)
-    _lib.call("amss_clip_factor", _p(sumsq), float(clip), _p(factor), _stream())
+def momentum_step(p, g, accum, lr, momentum=0.9, grad_scale=1.0, grad_scale_dev=None):
+    _chk(p, g, accum, grad_scale_dev)
+    _lib.call("amss_momentum_step", _p(p), _p(g), _p(accum), p.numel(), float(lr), float(momentum), float(grad_scale),
+              _p(grad_scale_dev), _stream())
+
+
+def rmsprop_step(p, g, ms, mom, lr, decay=0.9, momentum=0.0, eps=1e-10, grad_scale=1.0, grad_scale_dev=None):
+    _chk(p, g, ms, mom, grad_scale_dev)
+    _lib.call("amss_rmsprop_step", _p(p), _p(g), _p(ms), _p(mom), p.numel(), float(lr), float(decay), float(momentum),
+              float(eps), float(grad_scale), _p(grad_scale_dev), _stream())
+
+
+def global_norm_clip_factor(gs, clip, grad_scale=1.0):
+    """-> device scalar clip / max(||grad_scale * g||, clip)  (tf.clip_by_global_norm); gs: a tensor or a list of
+    tensors (the trainable segments of the flat gradient buffer)."""
+    gs = [gs] if torch.is_tensor(gs) else list(gs)
+    _chk(*gs)
+    dev = gs[0].device
+    sumsq = torch.zeros(1, dtype=_f32, device=dev)
+    ws = _ws(_lib.query("amss_sumsq_workspace_bytes"), dev)
+    for g in gs:
+        _lib.call("amss_sumsq", _p(g), g.numel(), _p(sumsq), _p(ws), _stream())
+    factor = torch.empty(1, dtype=_f32, device=dev)
+    _lib.call("amss_clip_factor", _p(sumsq), float(clip), float(grad_scale), _p(factor), _stream())
     return factor
 
 

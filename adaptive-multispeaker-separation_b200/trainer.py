@@ -83,26 +83,75 @@ class MyArgs:
         return vars(self.parser.parse_args(argv))
 
 
-class AMSGradOptimizer:
-    """Network.optimize (models/network.py:167-194): 'Adam' means AMSGrad(lr, beta1=0.9, beta2=0.99,
-    epsilon=1e-3) with a constant learning rate (utils/ops.py:639-704) and an optional global-norm
-    clip.  One fused kernel over the flat parameter range."""
+class Optimizer:
+    """Network.optimize (models/network.py:167-194) over the flat parameter buffer, one fused kernel per contiguous
+    trainable segment (normally one):
+      * 'Adam'    -> AMSGrad(lr, beta1=0.9, beta2=0.99, epsilon=1e-3), CONSTANT learning rate (:181-182, utils/ops.py:639-704);
+      * 'SGD'     -> tf.train.MomentumOptimizer(decayed lr, momentum=0.9) (:183);
+      * 'RMSProp' -> tf.train.RMSPropOptimizer(decayed lr) with TF 1.x's defaults decay 0.9, momentum 0, epsilon 1e-10 and
+                     the rms slot initialised to ONE (:185);
+      * decayed lr = exponential_decay(lr, global_epoch, decay_epoch, 0.5, staircase=True) = lr * 0.5^(epoch // decay_epoch)
+                     (:175-177); global_epoch advances through increment_epoch() once per epoch (utils/trainer.py:353);
+      * optional tf.clip_by_global_norm on the gradient of the batch-MEAN loss (:191-192): the norm is taken of
+        grad_scale * g, because under data parallelism the buffer holds the sum over ranks and grad_scale = 1 / world size.
+    Variables frozen with set_trainable() (the reference removes them from var_list) are not in any segment: they are
+    neither updated nor do they keep stale momentum."""
 
-    def __init__(self, store, lr, beta1=0.9, beta2=0.99, eps=1e-3, clip=0.0):
-        self.store, self.lr, self.b1, self.b2, self.eps, self.clip = store, lr, beta1, beta2, eps, clip
+    KINDS = ("Adam", "SGD", "RMSProp")
+
+    def __init__(self, store, lr, kind="Adam", decay_epoch=50, clip=0.0, beta1=0.9, beta2=0.99, eps=1e-3):
+        if kind not in self.KINDS:
+            raise ValueError(f"--optimizer {kind}: the reference knows {self.KINDS} (models/network.py:181-186)")
+        self.store, self.kind, self.lr, self.decay_epoch, self.clip = store, kind, float(lr), int(decay_epoch), float(clip or 0.0)
+        self.b1, self.b2, self.eps = beta1, beta2, eps
         n = store.n_trainable
-        self.m = torch.zeros(n, dtype=torch.float32, device=store.device)
-        self.v = torch.zeros_like(self.m)
-        self.vhat = torch.zeros_like(self.m)
+        z = lambda: torch.zeros(n, dtype=torch.float32, device=store.device)  # noqa: E731
+        if kind == "Adam":
+            self.m, self.v, self.vhat = z(), z(), z()
+        elif kind == "SGD":
+            self.accum = z()
+        else:
+            self.ms, self.mom = torch.ones(n, dtype=torch.float32, device=store.device), z()
         self.t = 0
+        self.global_epoch = 0
+
+    def increment_epoch(self):
+        self.global_epoch += 1
+
+    def learning_rate(self):
+        """The rate the next step uses (tf.train.exponential_decay, staircase; 'Adam' ignores the decay)."""
+        if self.kind == "Adam":
+            return self.lr
+        return self.lr * 0.5 ** (self.global_epoch // self.decay_epoch)
+
+    def state_tensors(self):
+        return {"Adam": ("m", "v", "vhat"), "SGD": ("accum",), "RMSProp": ("ms", "mom")}[self.kind]
 
     def step(self, grad_scale=1.0):
         st = self.store
         self.t += 1
-        lr_t = ops.amsgrad_lr_t(self.lr, self.b1, self.b2, self.t)
-        fac = ops.global_norm_clip_factor(st.grad_flat, self.clip) if self.clip else None
-        ops.amsgrad_step(st.flat[:st.n_trainable], st.grad_flat, self.m, self.v, self.vhat, lr_t, self.b1, self.b2,
-                         self.eps, grad_scale, fac)
+        segs = st.trainable_segments()
+        fac = None
+        if self.clip:
+            fac = ops.global_norm_clip_factor([st.grad_flat[o:o + n] for o, n in segs], self.clip, grad_scale)
+        for o, n in segs:
+            p, g = st.flat[o:o + n], st.grad_flat[o:o + n]
+            if self.kind == "Adam":
+                lr_t = ops.amsgrad_lr_t(self.lr, self.b1, self.b2, self.t)
+                ops.amsgrad_step(p, g, self.m[o:o + n], self.v[o:o + n], self.vhat[o:o + n], lr_t, self.b1, self.b2,
+                                 self.eps, grad_scale, fac)
+            elif self.kind == "SGD":
+                ops.momentum_step(p, g, self.accum[o:o + n], self.learning_rate(), 0.9, grad_scale, fac)
+            else:
+                ops.rmsprop_step(p, g, self.ms[o:o + n], self.mom[o:o + n], self.learning_rate(), 0.9, 0.0, 1e-10,
+                                 grad_scale, fac)
+
+
+class AMSGradOptimizer(Optimizer):
+    """Kept for callers of the first round: Optimizer(kind='Adam')."""
+
+    def __init__(self, store, lr, beta1=0.9, beta2=0.99, eps=1e-3, clip=0.0):
+        super().__init__(store, lr, "Adam", clip=clip, beta1=beta1, beta2=beta2, eps=eps)
 
 
 class DevicePrefetcher:
@@ -112,14 +161,15 @@ class DevicePrefetcher:
 
     def __init__(self, example_batch):
         self.stream = torch.cuda.Stream()
-        self.bufs = [[torch.empty(tuple(a.shape), dtype=a.dtype, device="cuda") for a in example_batch] for _ in range(2)]
+        self.bufs = [[None if a is None else torch.empty(tuple(a.shape), dtype=a.dtype, device="cuda") for a in example_batch]
+                     for _ in range(2)]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [None, None]
         self.k = 0
 
     @staticmethod
     def pin(batch):
-        return tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in batch)
+        return tuple(None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in batch)
 
     def submit(self, pinned_batch):
         """Start the H2D copy of a pinned batch; returns the slot to pass to get()."""
@@ -129,7 +179,8 @@ class DevicePrefetcher:
             self.stream.wait_event(self.done[k])          # the step that last read this slot has finished
         with torch.cuda.stream(self.stream):
             for d, h in zip(self.bufs[k], pinned_batch):
-                d.copy_(h, non_blocking=True)
+                if d is not None:
+                    d.copy_(h, non_blocking=True)
             self.ready[k].record(self.stream)
         return k
 
@@ -155,9 +206,10 @@ class Trainer:
         self.build()
         self.store.finalize()
         self.post_build()
-        self.optimizer = AMSGradOptimizer(self.store, self.args.get("learning_rate", DEFAULTS["learning_rate"]),
-                                          clip=self.args.get("gradient_norm_clip", 0.0))
-        self._pinned = None
+        self.optimizer = Optimizer(self.store, self.args.get("learning_rate", DEFAULTS["learning_rate"]),
+                                   kind=self.args.get("optimizer", DEFAULTS["optimizer"]),
+                                   decay_epoch=self.args.get("decay_epoch", DEFAULTS["decay_epoch"]),
+                                   clip=self.args.get("gradient_norm_clip", 0.0))
 
     # -- to override ---------------------------------------------------------------------------
     def build(self):
@@ -168,18 +220,6 @@ class Trainer:
 
     def loss(self, x_mix, x_non_mix, ind):
         raise NotImplementedError
-
-    # -- host -> device staging from pinned memory ----------------------------------------------
-    def to_device(self, batch):
-        mix, non_mix, ind = batch
-        if self._pinned is None or self._pinned[0].shape != mix.shape:
-            self._pinned = tuple(torch.empty(a.shape, dtype=torch.from_numpy(np.asarray(a)).dtype).pin_memory()
-                                 for a in (mix, non_mix, ind))
-        out = []
-        for buf, a in zip(self._pinned, (mix, non_mix, ind)):
-            buf.copy_(torch.from_numpy(np.ascontiguousarray(a)))
-            out.append(buf.to("cuda", non_blocking=True))
-        return out
 
     # -- optional CUDA-graph replay of forward + backward ---------------------------------------
     def enable_cuda_graph(self, eager_steps=2):
@@ -198,20 +238,41 @@ class Trainer:
 
     def _capture_step(self, x_mix, x_non_mix, ind):
         cg = self._cg
-        cg["inputs"] = [t.clone() for t in (x_mix, x_non_mix, ind)]
+        cg["inputs"] = [None if t is None else t.clone() for t in (x_mix, x_non_mix, ind)]
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self.store.grad_flat.zero_()
-            cost = self.loss(*cg["inputs"])
+            cost = self.loss(*self.prepare(cg["inputs"][0], cg["inputs"][1]), cg["inputs"][2])
             cost.backward()
         cg["graph"], cg["cost"] = graph, cost.detach()
         cg["kernels"] = _lib.launch_count() - n0          # library kernels recorded in the graph = run by every replay
         cg["replays"] = 0
 
+    # -- the input contract on the device ---------------------------------------------------------
+    def prepare(self, x_mix, x_non_mix):
+        """(x_mix or None, x_non_mix) -> (x_mix, x_non_mix) as the graph expects them (models/network.py:44-88): with
+        --dataset_normalize every source is normalised to zero mean / unit variance and the mixture is rebuilt from the
+        normalised sources (data/dataset.py:456-468; the reference normalises whole utterances before chunking, here the
+        unit is the chunk the caller hands over -- the data layer itself is out of scope); x_mix=None builds the
+        mixture on the device as the sum of the sources, so the host ships a third less."""
+        if self.args.get("dataset_normalize", False):
+            x_non_mix = x_non_mix.clone()
+            x_mix, self.norm_stats = ops.prepare_inputs(x_non_mix, normalize=True)
+        elif x_mix is None:
+            x_mix, _ = ops.prepare_inputs(x_non_mix.contiguous())
+        return x_mix, x_non_mix
+
+    def _exchange_and_update(self):
+        lo, hi = self.store.trainable_span()
+        scale = dp.allreduce_sum_(self.store.grad_flat[lo:hi])       # the single collective of the path
+        self.optimizer.step(scale)
+
     # -- one optimisation step on device tensors ------------------------------------------------
     def train_step(self, x_mix, x_non_mix, ind):
+        """Network.train (models/network.py:228-232): forward + backward + optimizer on one batch; returns the cost
+        (device scalar).  x_mix may be None (built on the device from the sources)."""
         cg = getattr(self, "_cg", None)
         if cg is not None:
             if cg["graph"] is None and cg["calls"] >= cg["eager"]:
@@ -219,26 +280,30 @@ class Trainer:
             cg["calls"] += 1
             if cg["graph"] is not None:
                 for dst, src in zip(cg["inputs"], (x_mix, x_non_mix, ind)):
-                    dst.copy_(src, non_blocking=True)
+                    if dst is not None:
+                        dst.copy_(src, non_blocking=True)
                 cg["graph"].replay()
                 cg["replays"] += 1
-                scale = dp.allreduce_sum_(self.store.grad_flat)
-                self.optimizer.step(scale)
+                self._exchange_and_update()
                 return cg["cost"].clone()
         self.store.grad_flat.zero_()
-        cost = self.loss(x_mix, x_non_mix, ind)
+        cost = self.loss(*self.prepare(x_mix, x_non_mix), ind)
         cost.backward()
-        scale = dp.allreduce_sum_(self.store.grad_flat)            # the single collective of the path
-        self.optimizer.step(scale)
+        self._exchange_and_update()
         return cost.detach()
 
-    def train(self, data, steps, log_every=0):
-        """data: iterator of host batches (numpy or pinned tensors).  Inputs are staged one step ahead
-        (DevicePrefetcher) and each step's cost is read back while the next step runs.
+    @torch.no_grad()
+    def eval_step(self, x_mix, x_non_mix, ind):
+        """Network.valid_batch / test_batch (models/network.py:240-262): the cost of one batch, no update."""
+        return self.loss(*self.prepare(x_mix, x_non_mix), ind).detach()
+
+    def run_steps(self, data, steps, log_every=0):
+        """data: iterator of host batches (numpy or pinned tensors; the mixture entry may be None).  Inputs are staged one
+        step ahead (DevicePrefetcher) and each step's cost is read back while the next step runs.
         Returns the list of per-step costs (floats)."""
         costs = []
         t0 = time.time()
-        as_pinned = lambda b: b if torch.is_tensor(b[0]) and b[0].is_pinned() else DevicePrefetcher.pin(b)  # noqa: E731
+        as_pinned = lambda b: b if _is_pinned(b) else DevicePrefetcher.pin(b)  # noqa: E731
         first = as_pinned(next(data))
         pf = DevicePrefetcher(first)
         slot, pending = pf.submit(first), None
@@ -254,6 +319,114 @@ class Trainer:
                 print(f"step {step + 1}/{steps} loss={costs[-1]:.6f} {(time.time() - t0) / (step + 1):.3f} s/step")
         costs.append(float(pending))
         return costs
+
+    # -- the reference's training loop ------------------------------------------------------------
+    def _mean_cost(self, batches):
+        """Mean cost over an iterable of host batches (utils/trainer.py:329-335); under data parallelism every rank
+        evaluates its own batches and the per-rank means are averaged (a scalar exchange outside the training step)."""
+        costs = []
+        for hb in batches:
+            dev = [None if a is None else torch.as_tensor(np.ascontiguousarray(a)).cuda() for a in hb]
+            costs.append(self.eval_step(*dev))
+        if not costs:
+            return float("nan")
+        c = torch.stack(costs).mean().reshape(1)
+        if self.distributed:
+            torch.distributed.all_reduce(c)
+            c /= self.world
+        return float(c)
+
+    def save(self, step):
+        """Network.save (models/network.py:223-226): <log_dir>/<name>/<runID>/model-<step>/{params, model.npz}."""
+        path = os.path.join(self.log_dir, getattr(self, "name", "model"), self.runID, f"model-{step}")
+        if self.rank == 0:
+            net = getattr(self, "model", None)
+            net.save(path)
+        if self.distributed:
+            torch.distributed.barrier()
+        return path
+
+    def train(self, data, steps=None, log_every=0, log_dir=None, runID=None, verbose=True):
+        """Trainer.train (utils/trainer.py:264-390).  `data` is either
+          * a dataset object with `train()`, `valid()`, `test()` methods, each returning a fresh iterable of host batches
+            (mix or None, non_mix, ind) -- the role of TFDataset's three initialisable iterators (data/dataset.py:520-645).
+            Then the reference's loop runs: `epochs` passes over train(); every `validation_step` steps the mean cost over
+            valid() and a checkpoint if it improved (:323-346); increment_epoch per epoch (:353: drives the SGD / RMSProp
+            learning-rate decay); after the last epoch one more validation + save-if-best (:358-375), the best
+            checkpoint is restored and the mean cost over test() reported (:380-388).  Returns a dict with the history;
+          * or an iterator of host batches together with `steps`: a plain step loop (run_steps), returns the costs."""
+        if steps is not None or not hasattr(data, "train"):
+            return self.run_steps(iter(data), steps, log_every)
+        import tempfile
+        self.log_dir = log_dir or self.args.get("log_dir") or tempfile.mkdtemp(prefix="amss_log_")
+        self.runID = runID or self.args.get("runID") or time.strftime("run-%Y%m%d-%H%M%S")
+        nb_epochs = int(self.args.get("epochs", DEFAULTS["epochs"]))
+        vstep = int(self.args.get("validation_step", DEFAULTS["validation_step"]))
+        say = print if (verbose and self.rank == 0) else (lambda *a, **k: None)
+        best, best_path, step = 1e100, "", 0
+        hist = {"train_costs": [], "valid": [], "saved": [], "learning_rates": []}
+        time_spent, t1 = [0.0] * 10, time.time()
+
+        def validate():
+            nonlocal best, best_path
+            t = time.time()
+            vc = self._mean_cost(data.valid())
+            hist["valid"].append((step, vc))
+            if vc < best:                                    # save the model if it is better (:338-342)
+                best = vc
+                best_path = self.save(step)
+                hist["saved"].append((step, best_path))
+                say("Save best model with :", best)
+            say(f"Validation set tested in {time.time() - t:.3f} seconds\nValidation set:  {vc}")
+
+        pf = None
+        for epoch in range(nb_epochs):
+            hist["learning_rates"].append(self.optimizer.learning_rate())
+            src = data.train()                                        # training_initializer (:313)
+            nb = len(src) if hasattr(src, "__len__") else getattr(data, "nb_batches_train", None)
+            it = iter(src)
+            nxt = next(it, None)
+            slot = None
+            if nxt is not None:
+                nxt = nxt if _is_pinned(nxt) else DevicePrefetcher.pin(nxt)
+                pf = pf or DevicePrefetcher(nxt)
+                slot = pf.submit(nxt)
+            b = 0
+            while slot is not None:
+                cost_dev = self.train_step(*pf.get(slot))
+                pf.release(slot)
+                nxt = next(it, None)                                  # stage the next batch while this step runs
+                slot = None
+                if nxt is not None:
+                    nxt = nxt if _is_pinned(nxt) else DevicePrefetcher.pin(nxt)
+                    slot = pf.submit(nxt)
+                c = float(cost_dev)
+                if c != c:
+                    raise FloatingPointError(f"NaN cost at step {step} (epoch {epoch + 1}, batch {b + 1})")
+                hist["train_costs"].append(c)
+                if (step + 1) % vstep == 0:
+                    validate()
+                time_spent = time_spent[1:] + [time.time() - t1]      # running mean over the last 10 steps (:348-351)
+                avg = sum(time_spent) / len(time_spent)
+                eta = f"{avg * ((nb_epochs - epoch - 1) * nb + (nb - b - 1)):.0f} s" if nb else "?"
+                say(f"Epoch # {epoch + 1} / {nb_epochs}  Batch # {b + 1} / {nb or '?'} in {avg:.4f} sec loss= {c}  ETA = {eta}")
+                t1 = time.time()
+                step += 1
+                b += 1
+            self.optimizer.increment_epoch()                          # sess.run(increment_epoch) (:353)
+        validate()                                                    # validation at the last step (:358-375)
+        say("Best model with Validation:  ", best, "\nPath = ", best_path)
+        if best_path:                                                 # restore_last_checkpoint (:380)
+            self.model.restore_model(best_path)
+        test_cost = self._mean_cost(data.test())
+        say("Test cost = ", test_cost)
+        hist.update(best_validation_cost=best, best_path=best_path, test_cost=test_cost, steps=step)
+        return hist
+
+
+def _is_pinned(batch):
+    t = next((a for a in batch if a is not None), None)
+    return torch.is_tensor(t) and t.is_pinned()
 
 
 class STFT_Separator_Trainer(Trainer):

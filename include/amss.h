@@ -275,6 +275,16 @@ int amss_apply_masks(const float* X_input, const int32_t* labels, const float* s
                      int B, int S, int64_t TF, float* separated, void* stream);
 
 /* ------------------------------------------------------------------------------------ *
+ * Input contract (models/network.py:44-88 placeholders / :65-88 pipeline; data/dataset.py:456-468)
+ * ------------------------------------------------------------------------------------ */
+/* Builds on the device what the reference's tf.data graph builds on the host: optional
+ * per-source normalisation (x-mean)/sqrt(var) of every row of x_non_mix[B,S,L] IN PLACE
+ * (--dataset_normalize, data/dataset.py:456-460; stats[B*S,2] = (mean, var), may be NULL) and the
+ * mixture x_mix[B,L] = ((x_0 + x_1) + x_2 ...) (data/dataset.py:462-468).  S <= 8.         */
+int amss_prepare_inputs(float* x_non_mix, int B, int S, int64_t L, int normalize, float* stats,
+                        float* x_mix, void* stream);
+
+/* ------------------------------------------------------------------------------------ *
  * Optimizer  (utils/ops.py:639-704 AMSGrad; models/network.py:181-192)
  * ------------------------------------------------------------------------------------ */
 /* One fused pass over a flat parameter buffer: m,v EMA; vhat=max(vhat,v);
@@ -284,10 +294,25 @@ int amss_apply_masks(const float* X_input, const int32_t* labels, const float* s
 int amss_amsgrad_step(float* p, const float* g, float* m, float* v, float* vhat,
                       int64_t n, float lr_t, float beta1, float beta2, float eps,
                       float grad_scale, const float* grad_scale_dev, void* stream);
-/* sumsq[0] += sum g^2 (caller zeroes); clip factor = clip/max(sqrt(sumsq),clip).        */
+/* sumsq[0] += sum g^2 (caller zeroes); tf.clip_by_global_norm (models/network.py:191-192):
+ * factor = clip / max(|grad_scale| * sqrt(sumsq), clip) -- the norm of grad_scale * g, so that a
+ * buffer holding the SUM of G per-rank gradients is clipped like the batch-mean gradient
+ * (grad_scale = 1/G).                                                                   */
 int amss_sumsq(const float* g, int64_t n, float* sumsq, void* workspace, void* stream);
 size_t amss_sumsq_workspace_bytes(void);
-int amss_clip_factor(const float* sumsq, float clip, float* factor, void* stream);
+int amss_clip_factor(const float* sumsq, float clip, float grad_scale, float* factor, void* stream);
+/* --optimizer SGD (models/network.py:183): tf.train.MomentumOptimizer(lr, 0.9):
+ * accum = momentum*accum + g ; p -= lr*accum.  lr = the staircase-decayed rate (:175-177),
+ * computed by the caller.                                                               */
+int amss_momentum_step(float* p, const float* g, float* accum, int64_t n, float lr,
+                       float momentum, float grad_scale, const float* grad_scale_dev, void* stream);
+/* --optimizer RMSProp (models/network.py:185): tf.train.RMSPropOptimizer(lr) with the TF 1.x
+ * defaults decay 0.9, momentum 0.0, epsilon 1e-10: ms = decay*ms + (1-decay)*g^2 ;
+ * mom = momentum*mom + lr*g/sqrt(ms+eps) ; p -= mom.  The caller initialises ms to ONE
+ * (TF's slot initialiser) and mom to zero.                                              */
+int amss_rmsprop_step(float* p, const float* g, float* ms, float* mom, int64_t n, float lr,
+                      float decay, float momentum, float eps, float grad_scale,
+                      const float* grad_scale_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------ *
  * Adapt pre-training losses (models/adapt.py:307-402, models/network.py:196-221)

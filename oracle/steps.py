@@ -8,7 +8,7 @@ Used by the end-to-end parity tests and as the timed CPU baseline of bench.py
 import torch
 
 from . import models as M
-from .amsgrad import AMSGrad
+from .amsgrad import make_optimizer
 
 
 def trainable(params, prefixes):
@@ -37,15 +37,16 @@ def front_separator_loss(p, x_mix, x_non_mix, I, *, nb_layers, embedding_size, m
 
 
 class Stepper:
-    """fwd + bwd + AMSGrad on the parameters whose names start with `train_prefixes`."""
+    """fwd + bwd + optimizer (AMSGrad by default) on the parameters whose names start with `train_prefixes`."""
 
-    def __init__(self, params, loss_fn, train_prefixes=("prediction/", "speaker_centroids"), lr=1e-3, clip=0.0):
+    def __init__(self, params, loss_fn, train_prefixes=("prediction/", "speaker_centroids"), lr=1e-3, clip=0.0,
+                 optimizer="Adam", decay_epoch=50):
         self.p = params
         self.loss_fn = loss_fn
         self.tr = trainable(params, train_prefixes)
         for v in self.tr.values():
             v.requires_grad_(True)
-        self.opt = AMSGrad(self.tr, lr, clip=clip)
+        self.opt = make_optimizer(optimizer, self.tr, lr, decay_epoch=decay_epoch, clip=clip)
 
     def step(self, x_mix, x_non_mix, I):
         cost, aux = self.loss_fn(self.p, x_mix, x_non_mix, I)

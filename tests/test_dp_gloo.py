@@ -51,7 +51,9 @@ def _worker(rank, world_size, port, out):
     flat, cost = _flat_grads(_params(), shard)
     scale = dp.allreduce_sum_(flat)
     worst = dp.max_over_ranks(float(rank))
-    out[rank] = ((flat * scale).numpy(), cost, worst)
+    clip = 0.5 * float(flat.norm()) * scale                        # a clip that bites: half the mean-gradient norm
+    clipped = flat * scale * dp.clip_factor(float(flat.norm()), clip, scale)
+    out[rank] = ((flat * scale).numpy(), cost, worst, clipped.numpy(), clip)
     dist.destroy_process_group()
 
 
@@ -63,13 +65,19 @@ def test_two_rank_allreduce_equals_full_batch_gradient():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     full, cost_full = _flat_grads(_params(), OM.synthetic_mixtures(B, S, L, seed=11))
-    g0, c0, w0 = out[0]
-    g1, c1, w1 = out[1]
+    g0, c0, w0, k0, clip = out[0]
+    g1, c1, w1, k1, _ = out[1]
     assert np.array_equal(g0, g1)                                  # replicas hold identical gradients after the collective
     assert w0 == w1 == 1.0                                         # max-over-ranks helper
     assert abs(0.5 * (c0 + c1) - cost_full) < 1e-5 * abs(cost_full)
     err = np.abs(g0 - full.numpy()).max() / (np.abs(full.numpy()).max() + 1e-30)
     assert err < 1e-4, err
+    # gradient clipping under data parallelism: the clipped exchange result equals tf.clip_by_global_norm of the
+    # FULL-batch gradient -- norm `clip`, not clip / world_size
+    want = full * (clip / max(float(full.norm()), clip))
+    assert np.array_equal(k0, k1)
+    assert abs(np.linalg.norm(k0) - clip) < 1e-4 * clip
+    assert np.abs(k0 - want.numpy()).max() / np.abs(want.numpy()).max() < 1e-4
 
 
 def test_shard_batch_rejects_ragged_split():

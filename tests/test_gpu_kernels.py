@@ -446,3 +446,61 @@ def test_amsgrad_matches_oracle(ops):
         fac = ops.global_norm_clip_factor(gd, 0.5)
         ops.amsgrad_step(p, gd, m, v, vh, ops.amsgrad_lr_t(1e-3, 0.9, 0.99, step), 0.9, 0.99, 1e-3, 1.0, fac)
     assert rel(p, params["p"]) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["SGD", "RMSProp"])
+def test_momentum_rmsprop_match_oracle(ops, kind):
+    """--optimizer SGD / RMSProp (models/network.py:183-186) with the staircase decay and a global-norm clip."""
+    from oracle.amsgrad import make_optimizer
+    g = torch.Generator().manual_seed(101)
+    n = 10007
+    p0 = torch.randn(n, generator=g)
+    params = {"p": p0.clone()}
+    opt = make_optimizer(kind, params, 1e-2, decay_epoch=1, clip=0.5)
+    p = dev(p0.clone())
+    s1 = torch.ones_like(p) if kind == "RMSProp" else torch.zeros_like(p)
+    s2 = torch.zeros_like(p)
+    for step in range(4):
+        if step == 2:
+            opt.increment_epoch()                     # decay_epoch 1: the rate halves from here on
+        lr = 1e-2 * (0.5 if step >= 2 else 1.0)
+        grad = torch.randn(n, generator=g)
+        opt.step({"p": grad})
+        gd = dev(grad)
+        fac = ops.global_norm_clip_factor(gd, 0.5)
+        if kind == "SGD":
+            ops.momentum_step(p, gd, s1, lr, 0.9, 1.0, fac)
+        else:
+            ops.rmsprop_step(p, gd, s1, s2, lr, 0.9, 0.0, 1e-10, 1.0, fac)
+    assert rel(p, params["p"]) < 1e-5
+
+
+def test_clip_factor_uses_the_mean_gradient_norm(ops):
+    """under data parallelism the buffer holds the SUM over G ranks; tf.clip_by_global_norm
+    (models/network.py:191-192) acts on the batch-mean gradient, so the norm must be taken of grad_scale * g."""
+    g = torch.Generator().manual_seed(5)
+    mean_grad = torch.randn(5000, generator=g)
+    G, clip = 4, 3.0
+    summed = dev(mean_grad * G)
+    fac = float(ops.global_norm_clip_factor(summed, clip, 1.0 / G))
+    want = clip / max(float(mean_grad.double().norm()), clip)
+    assert abs(fac - want) < 1e-5 * want
+    assert abs(float(ops.global_norm_clip_factor(summed, clip)) - clip / float((mean_grad * G).double().norm())) < 1e-6
+
+
+def test_prepare_inputs_mix_and_normalize(ops):
+    """Input contract on the device (data/dataset.py:456-468): mixture = sequential fp32 sum of the sources (bit-exact vs
+    numpy's sum over the stacked axis), --dataset_normalize = per-source (x - mean) / sqrt(var)."""
+    rng = np.random.RandomState(3)
+    for S, Lw in ((2, 4096), (3, 1001)):
+        nm = (rng.randn(3, S, Lw) * 0.05 + 0.01).astype(np.float32)
+        x_mix, _ = ops.prepare_inputs(dev(nm))
+        assert np.array_equal(x_mix.cpu().numpy(), nm.sum(1))
+        d = dev(nm.copy())
+        x_mix, stats = ops.prepare_inputs(d, normalize=True)
+        t = torch.tensor(nm)
+        mean, var = t.mean(-1, keepdim=True), t.var(-1, unbiased=False, keepdim=True)
+        want = (t - mean) / torch.sqrt(var)
+        assert rel(d, want) < 1e-5
+        assert rel(stats[:, 0], mean.reshape(-1)) < 1e-4 and rel(stats[:, 1], var.reshape(-1)) < 1e-4
+        assert rel(x_mix, want.sum(1)) < 1e-5

@@ -386,3 +386,129 @@ def test_cuda_graph_replay_equals_eager_steps(amss):
     assert tb._cg["graph"] is not None and tb._cg["replays"] == 3 and tb.graph_kernel_launches() > 0
     for k in ta.store.names():
         assert torch.equal(ta.store[k], tb.store[k]), k
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: optimizer flags, the reference's training loop, the input contract on the device
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["SGD", "RMSProp"])
+def test_optimizer_flag_selects_momentum_or_rmsprop(amss, kind):
+    """--optimizer SGD|RMSProp and --decay_epoch (models/network.py:171-186): 4 steps over 2 'epochs' with decay_epoch 1,
+    against the oracle's TF-faithful optimizers."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 2048
+    lr = 1e-2 if kind == "SGD" else 1e-3
+    t = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=24, embedding_size=8, learning_rate=lr, optimizer=kind,
+                                  decay_epoch=1, window_size=128, hop_size=64, gradient_norm_clip=50.0)
+    assert t.optimizer.kind == kind
+    p = _copy_params(t.store, {})
+    fn = functools.partial(OS.stft_separator_loss, nb_layers=1, embedding_size=8, window_size=128, hop_size=64)
+    st = OS.Stepper(p, fn, lr=lr, clip=50.0, optimizer=kind, decay_epoch=1)
+    for step in range(4):
+        if step == 2:
+            st.opt.increment_epoch()
+            t.optimizer.increment_epoch()
+            assert abs(t.optimizer.learning_rate() - lr / 2) < 1e-12
+        mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=300 + step)
+        c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+    for k in st.tr:
+        assert rel(t.store[k], st.tr[k]) < REL, k
+
+
+def test_unknown_optimizer_is_refused(amss):
+    tr, mo = amss["trainer"], amss["models"]
+    with pytest.raises(ValueError):
+        tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=8, embedding_size=4, optimizer="Adagrad",
+                                  window_size=64, hop_size=32)
+
+
+def test_freezing_on_a_live_optimizer_stops_the_update(amss):
+    """a variable frozen after it accumulated momentum must stop moving (the reference drops it from var_list)."""
+    tr, mo = amss["trainer"], amss["models"]
+    t = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=2, layer_size=16, embedding_size=4, learning_rate=1e-2,
+                                  window_size=64, hop_size=32)
+    mix, nm, I = M.synthetic_mixtures(2, 2, 1024, seed=1)
+    batch = (_dev(mix), _dev(nm), _dev(I))
+    t.train_step(*batch)
+    t.train_step(*batch)
+    t.store.set_trainable(lambda n: "BLSTM_0" not in n)
+    frozen = {k: v.detach().clone() for k, v in t.store.params.items() if "BLSTM_0" in k}
+    others = {k: v.detach().clone() for k, v in t.store.params.items() if "BLSTM_0" not in k}
+    assert len(t.store.trainable_segments()) >= 1 and frozen
+    t.train_step(*batch)
+    for k, v in frozen.items():
+        assert torch.equal(t.store[k].detach(), v), k
+    assert any(not torch.equal(t.store[k].detach(), v) for k, v in others.items())
+
+
+class _ToyDataset:
+    """The role of TFDataset (data/dataset.py:520-645): three re-initialisable iterables of host batches."""
+
+    def __init__(self, n_train, n_valid, n_test, B=2, S=2, Lw=1024, with_mix=True):
+        mk = lambda seed: M.synthetic_mixtures(B, S, Lw, seed=seed)  # noqa: E731
+        self._tr = [mk(10 + i) for i in range(n_train)]
+        self._va = [mk(500 + i) for i in range(n_valid)]
+        self._te = [mk(900 + i) for i in range(n_test)]
+        if not with_mix:
+            self._tr = [(None, b[1], b[2]) for b in self._tr]
+        self.valid_calls = 0
+
+    def train(self):
+        return list(self._tr)
+
+    def valid(self):
+        self.valid_calls += 1
+        return list(self._va)
+
+    def test(self):
+        return list(self._te)
+
+
+def test_trainer_train_runs_the_reference_loop(amss, tmp_path):
+    """Trainer.train (utils/trainer.py:264-390): epochs x batches, validation every validation_step, a checkpoint exactly
+    when the validation cost improves, increment_epoch per epoch, final validation, best checkpoint restored, test pass."""
+    import os
+    tr, mo = amss["trainer"], amss["models"]
+    ds = _ToyDataset(3, 2, 2, with_mix=False)                    # mixtures built on the device from the sources
+    t = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=16, embedding_size=4, learning_rate=3e-3,
+                                  window_size=64, hop_size=32, epochs=2, validation_step=2)
+    hist = t.train(ds, log_dir=str(tmp_path), runID="toy", verbose=False)
+    assert hist["steps"] == 6 and len(hist["train_costs"]) == 6
+    assert [s for s, _ in hist["valid"]] == [1, 3, 5, 6] and ds.valid_calls == 4      # steps 2, 4, 6 (0-based +1) and the final one
+    assert t.optimizer.global_epoch == 2
+    best = 1e100
+    expect = []
+    for step, vc in hist["valid"]:
+        if vc < best:
+            best = vc
+            expect.append(step)
+    assert [s for s, _ in hist["saved"]] == expect and expect
+    base = os.path.join(str(tmp_path), t.name, "toy")
+    assert sorted(os.listdir(base)) == sorted(f"model-{s}" for s in expect)
+    for s in expect:
+        assert sorted(os.listdir(os.path.join(base, f"model-{s}"))) == ["model.npz", "params"]
+    assert hist["best_path"].endswith(f"model-{expect[-1]}") and abs(hist["best_validation_cost"] - best) < 1e-12
+    # the best checkpoint is what the model holds after train(): its validation cost is reproduced
+    assert abs(t._mean_cost(ds.valid()) - best) < 1e-5 * abs(best)
+    assert hist["test_cost"] == hist["test_cost"]
+
+
+def test_dataset_normalize_and_device_built_mixture(amss):
+    """--dataset_normalize (data/dataset.py:456-460) + x_mix=None: the step equals the oracle's step on host-normalised data."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 2048
+    t = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=24, embedding_size=8, learning_rate=1e-3,
+                                  window_size=128, hop_size=64, dataset_normalize=True)
+    p = _copy_params(t.store, {})
+    fn = functools.partial(OS.stft_separator_loss, nb_layers=1, embedding_size=8, window_size=128, hop_size=64)
+    st = OS.Stepper(p, fn, lr=1e-3)
+    _, nm, I = M.synthetic_mixtures(B, S, Lw, seed=77)
+    nmt = torch.tensor(nm)
+    nmn = (nmt - nmt.mean(-1, keepdim=True)) / torch.sqrt(nmt.var(-1, unbiased=False, keepdim=True))
+    c_ref, _ = st.step(nmn.sum(1), nmn, torch.tensor(I))
+    c = t.train_step(None, _dev(nm), _dev(I))
+    assert abs(float(c) - c_ref) < REL * abs(c_ref)
+    for k in st.tr:
+        assert rel(t.store[k], st.tr[k]) < REL, k

@@ -236,3 +236,37 @@ def test_cost_finetuning_is_permutation_invariant_pit():
     assert abs(float(M.cost_finetuning(x, est[:, [1, 2, 0]])) - float(c)) < 1e-12
     grad, = torch.autograd.grad(c, est)
     assert torch.allclose(grad, (est - x).detach() / 9.0, atol=1e-12)          # 1/(B*S) * (xhat - x)
+
+
+def test_momentum_and_rmsprop_and_decay():
+    """--optimizer SGD / RMSProp (models/network.py:175-186): Momentum against torch.optim.SGD (same recurrence),
+    RMSProp against the closed form of TF's kernel (rms slot starts at ONE, epsilon inside the square root) and the
+    staircase decay lr * 0.5^(epoch // decay_epoch)."""
+    from oracle.amsgrad import Momentum, RMSProp, exponential_decay
+    g = torch.Generator().manual_seed(0)
+    w0 = torch.randn(7, generator=g)
+    grads = [torch.randn(7, generator=g) for _ in range(4)]
+    p = {"w": w0.clone()}
+    opt = Momentum(p, lr=0.1, decay_epoch=2)
+    wt = w0.clone().requires_grad_(True)
+    sgd = torch.optim.SGD([wt], lr=0.1, momentum=0.9)
+    for gr in grads[:2]:
+        opt.step({"w": gr})
+        wt.grad = gr.clone()
+        sgd.step()
+    assert torch.allclose(p["w"], wt.detach(), atol=1e-6)
+    opt.increment_epoch(); opt.increment_epoch()               # epoch 2 -> lr halves (decay_epoch = 2)
+    before = p["w"].clone()
+    acc = opt.accum["w"].clone()
+    opt.step({"w": grads[2]})
+    assert torch.allclose(p["w"], before - 0.05 * (0.9 * acc + grads[2]), atol=1e-7)
+    assert exponential_decay(0.1, 49, 50) == 0.1 and exponential_decay(0.1, 50, 50) == 0.05 and exponential_decay(0.1, 149, 50) == 0.025
+    q = {"w": w0.clone()}
+    rms = RMSProp(q, lr=0.01)
+    ms = torch.ones(7)
+    w = w0.clone()
+    for gr in grads[:3]:
+        rms.step({"w": gr})
+        ms = 0.9 * ms + 0.1 * gr * gr
+        w = w - 0.01 * gr / torch.sqrt(ms + 1e-10)
+    assert torch.allclose(q["w"], w, atol=1e-7)
