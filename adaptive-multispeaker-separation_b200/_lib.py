@@ -77,9 +77,38 @@ def raw(name):
     return _fns[name]
 
 
+# Optional per-entry-point device timing (bench.py / tools): time_calls([...]) makes call() bracket the named entry
+# points with CUDA events on the launching stream; timed_calls() returns {name: [(args, ms), ...]} after a synchronize.
+_timed = None
+
+
+def time_calls(names):
+    """Start (names = iterable of entry points, or "all") or stop (names = None) bracketing ABI calls with CUDA events."""
+    global _timed
+    _timed = None if names is None else {"__all__": names == "all", "names": set(() if names == "all" else names), "ev": []}
+
+
+def timed_calls():
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, args, e0, e1 in (_timed["ev"] if _timed else ()):
+        out.setdefault(name, []).append((args, e0.elapsed_time(e1)))
+    return out
+
+
 def call(name, *args):
     """Call an int-status entry point; raise AmssError with the library's message on failure."""
+    ev = None
+    if _timed is not None and (_timed["__all__"] or name in _timed["names"]):
+        import torch
+        if not torch.cuda.is_current_stream_capturing():
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
     rc = _fns[name](*args)
+    if ev is not None:
+        ev[1].record()
+        _timed["ev"].append((name, args, ev[0], ev[1]))
     if rc != 0:
         raise AmssError(f"{name} failed ({rc}): {last_error()}")
 

@@ -605,32 +605,88 @@ class Front_Separator_Enhance_Finetuning_Trainer(Trainer):
         return m.cost_finetuning(x_non_mix, back)
 
 
-class STFT_Separator_Inference:
+class _StreamingInference:
+    """Trainer.inference (utils/trainer.py:190-229) as a streaming generator: host batches are staged one step ahead from
+    pinned memory (DevicePrefetcher), every batch's separated waveforms [B,S,L'] are copied back into double-buffered
+    pinned host memory on a side stream, and the generator yields them one step late (so that the copy overlaps the next
+    batch's kernels).  A yielded tensor is valid until two more batches have been yielded.  Replicas only under
+    multi-GPU: each rank streams its own batches, no collective."""
+
+    def _infer_batch(self, dev_batch):
+        raise NotImplementedError
+
+    def inference(self, data, steps=None):
+        it = iter(data)
+        as_pinned = lambda b: b if _is_pinned(b) else DevicePrefetcher.pin(b)  # noqa: E731
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        nxt = as_pinned(nxt)
+        pf = DevicePrefetcher(nxt)
+        slot = pf.submit(nxt)
+        d2h = torch.cuda.Stream()
+        host, done, pending, k, n = [None, None], [None, None], None, 0, 0
+        while slot is not None and (steps is None or n < steps):
+            out = self._infer_batch(pf.get(slot))
+            pf.release(slot)
+            n += 1
+            nxt = next(it, None) if (steps is None or n < steps) else None
+            slot = pf.submit(as_pinned(nxt)) if nxt is not None else None
+            if host[k] is None or host[k].shape != out.shape:
+                host[k] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(ready)
+                host[k].copy_(out, non_blocking=True)
+                out.record_stream(d2h)
+                done[k] = torch.cuda.Event()
+                done[k].record(d2h)
+            if pending is not None:
+                done[pending].synchronize()
+                yield host[pending]
+            pending = k
+            k ^= 1
+        if pending is not None:
+            done[pending].synchronize()
+            yield host[pending]
+
+
+class STFT_Separator_Inference(_StreamingInference):
     """utils/trainer.py:406-417 + Trainer.inference (:190-229): mixture -> separated waveforms."""
 
-    def __init__(self, separator, **kwargs):
+    def __init__(self, separator, state=None, **kwargs):
         args = {k: v for k, v in kwargs.items() if k in DEFAULTS or k in ("window_size", "hop_size")}
         self.model = separator(plugged=False, **args)
         self.model.finalize()
+        if state:
+            self.model.store.load_state_dict(state, strict=False)
+        self.init_idx = None
 
     @torch.no_grad()
     def infer(self, x_mix, init_idx=None):
         m = self.model
         spec, X = ops.stft(x_mix.contiguous(), m.window_size, m.hop_size)
         V = m.prediction(X)
-        _, lab = m.separate(V, X, init_idx)
+        _, lab = m.separate(V, X, init_idx if init_idx is not None else self.init_idx)
         return m.postprocessing(spec, lab)
 
+    def _infer_batch(self, dev_batch):
+        return self.infer(dev_batch[0])
 
-class Front_Separator_Inference:
+
+class Front_Separator_Inference(_StreamingInference):
     """utils/trainer.py:420-434: front -> separator k-means masks -> back (unpool + transposed conv)."""
 
-    def __init__(self, separator, **kwargs):
+    def __init__(self, separator, state=None, **kwargs):
         args = {k: v for k, v in kwargs.items() if k in DEFAULTS or k in ("window_size", "hop_size")}
         args["pretraining"] = False
         self.model = Adapt(**args)
         self.sepNet = self.model.connect_front(separator)
         self.model.finalize()
+        if state:
+            self.model.store.load_state_dict(state, strict=False)
+        self.init_idx = None
 
     @torch.no_grad()
     def infer(self, x_mix, x_non_mix, init_idx=None):
@@ -638,5 +694,11 @@ class Front_Separator_Inference:
         y, am = self.model.front(x_mix, x_non_mix)
         X = y[:B].contiguous()
         V = self.sepNet.prediction(X)
-        sep, _ = self.sepNet.separate(V, X, init_idx)
+        sep, _ = self.sepNet.separate(V, X, init_idx if init_idx is not None else self.init_idx)
         return self.model.back(sep, am, B, Lw)
+
+    def _infer_batch(self, dev_batch):
+        x_mix, x_non_mix = dev_batch[0], dev_batch[1]
+        if x_mix is None:
+            x_mix, _ = ops.prepare_inputs(x_non_mix.contiguous())
+        return self.infer(x_mix, x_non_mix)

@@ -55,3 +55,46 @@ class Stepper:
         self.opt.step(grads)
         self.last_grads = grads
         return float(cost.detach()), aux
+
+
+def stft_enhance_loss(p, x_mix, x_non_mix, I, *, nb_layers, embedding_size, window_size=512, hop_size=256,
+                      nb_layers_enhance=3, nb_tries=10, nb_steps=10, init_idx=None, seed=0):
+    """STFT_Separator_enhance_Trainer's step (utils/trainer.py:488-500, BASELINE config 3): a trained separator (no gradient)
+    -> k-means masks (models/network.py:554-582) -> enhance BLSTM layer (:610-660) -> PIT-L2 enhance cost (:662-693)."""
+    import numpy as np
+    from .kmeans import KMeans, random_init_idx
+    S = x_non_mix.shape[1]
+    pre = M.separator_preprocessing(x_mix, x_non_mix, window_size, hop_size, 1.0, -1.0)
+    with torch.no_grad():
+        V = M.separator_prediction(p, pre["X"], nb_layers, embedding_size, True)
+        B, Tt, Fb, E = V.shape
+        if init_idx is None:
+            init_idx = random_init_idx(B * nb_tries, Tt * Fb, S, np.random.RandomState(seed))
+        km = KMeans(nb_clusters=S, nb_tries=nb_tries, nb_iterations=nb_steps)
+        sep, masks = M.separate(V, pre["X"], lambda emb: km.fit(emb, init_idx=init_idx)[1], S)
+    _, cost_in, _ = M.enhance(p, sep, pre["X"], S, nb_layers_enhance)
+    cost = M.enhance_cost(cost_in, pre["X_non_mix"])
+    return cost, {"V": V, "pre": pre, "masks": masks}
+
+
+def stft_inference(p, x_mix, x_non_mix, I, *, nb_layers, embedding_size, window_size=512, hop_size=256, S=2, nb_tries=10,
+                   nb_steps=10, init_idx=None, seed=0):
+    """STFT_Separator_Inference (utils/trainer.py:406-417; BASELINE config 5): |STFT| -> embeddings -> k-means masks ->
+    postprocessing (mixture phase, inverse STFT) -> separated waveforms [B,S,L']."""
+    import numpy as np
+    from .kmeans import KMeans, random_init_idx
+    stfts = T_stft(x_mix, window_size, hop_size)
+    X = stfts.abs()
+    V = M.separator_prediction(p, X, nb_layers, embedding_size, True)
+    B, Tt, Fb, E = V.shape
+    if init_idx is None:
+        init_idx = random_init_idx(B * nb_tries, Tt * Fb, S, np.random.RandomState(seed))
+    km = KMeans(nb_clusters=S, nb_tries=nb_tries, nb_iterations=nb_steps)
+    sep, masks = M.separate(V, X, lambda emb: km.fit(emb, init_idx=init_idx)[1], S)
+    out = M.postprocessing(sep, stfts, S, window_size, hop_size)
+    return out, {"V": V, "masks": masks}
+
+
+def T_stft(x, window_size, hop_size):
+    from . import tf_ops
+    return tf_ops.stft(x, window_size, hop_size)
