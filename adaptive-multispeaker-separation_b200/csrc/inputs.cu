@@ -53,10 +53,95 @@ __global__ void normalize_rows_kernel(float* __restrict__ x, int64_t L, float* _
     if (threadIdx.x == 0 && stats) { stats[2 * blockIdx.x] = mean; stats[2 * blockIdx.x + 1] = var; }
 }
 
+// Separator input options, one CTA per mixture row (256 KB per row: three short passes, L2-resident).
+__device__ __forceinline__ float prep_point(float x, int abs_input, int pre_func) {
+    if (abs_input) x = fabsf(x);
+    if (pre_func == 1) x = sqrtf(x);
+    else if (pre_func == 2) x = logf(x + 1e-12f) / logf(10.f);           // utils/ops.py:56-59 log10
+    return x;
+}
+__device__ __forceinline__ float block_minmax(float v, float* red, bool is_max) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const float u = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, u) : fminf(v, u); }
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, red[i]) : fminf(r, red[i]);
+    __syncthreads();
+    return r;
+}
+__global__ void separator_input_prep_kernel(const float* __restrict__ X, int64_t TF, int abs_input, int pre_func,
+                                            int normalize, float silence_db, float* __restrict__ out) {
+    __shared__ float red[32];
+    const float* x = X + (size_t)blockIdx.x * TF;
+    float* o = out + (size_t)blockIdx.x * TF;
+    float a = 0.f, b = 1.f;                                  // normalised value = (v - a) * b
+    float mx = -INFINITY;
+    if (normalize == 1 || silence_db > 0.f) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) { const float v = prep_point(x[i], abs_input, pre_func); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        lo = block_minmax(lo, red, false);
+        hi = block_minmax(hi, red, true);
+        if (normalize == 1) { a = lo; b = 1.f / (hi - lo); mx = 1.f; }
+        else mx = hi;
+    }
+    if (normalize == 2) {
+        float sum = 0.f;
+        for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) sum += prep_point(x[i], abs_input, pre_func);
+        const float mean = block_sum(sum, red) / (float)TF;
+        float q = 0.f;
+        for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) { const float d = prep_point(x[i], abs_input, pre_func) - mean; q = fmaf(d, d, q); }
+        const float var = block_sum(q, red) / (float)TF;
+        a = mean; b = 1.f / sqrtf(var);
+        if (silence_db > 0.f) mx = (mx - a) * b;
+    }
+    const float thr = silence_db / 20.f;
+    for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) {
+        float v = (prep_point(x[i], abs_input, pre_func) - a) * b;
+        if (silence_db > 0.f && !((mx - v) < thr)) v = 0.f;
+        o[i] = v;
+    }
+}
+__global__ void label_weights_kernel(const float* __restrict__ X, int64_t TF, int function_mask, float silence_threshold,
+                                     float* __restrict__ w) {
+    __shared__ float red[32];
+    const float* x = X + (size_t)blockIdx.x * TF;
+    float hi = 0.f;
+    for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) hi = fmaxf(hi, fabsf(x[i]));
+    hi = block_minmax(hi, red, true);
+    for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) {
+        const float v = fabsf(x[i]);
+        float m = 1.f;
+        const float r = v / hi;
+        if (function_mask == 1) m = r;
+        else if (function_mask == 2) m = sqrtf(r);
+        else if (function_mask == 3) m = r * r;
+        if (silence_threshold > 0.f) m *= (logf(hi / v) / logf(10.f) < silence_threshold) ? 1.f : 0.f;
+        w[(size_t)blockIdx.x * TF + i] = m;
+    }
+}
+
 }  // namespace
 }  // namespace amss
 
 using namespace amss;
+
+extern "C" int amss_separator_input_prep(const float* X, int B, int64_t TF, int abs_input, int pre_func, int normalize,
+                                         float silence_db, float* out, void* stream) {
+    AMSS_REQUIRE(X && out && B > 0 && TF > 0, "separator_input_prep: bad arguments");
+    AMSS_REQUIRE(pre_func >= 0 && pre_func <= 2 && normalize >= 0 && normalize <= 2, "separator_input_prep: unknown mode");
+    AMSS_LAUNCH(separator_input_prep_kernel, B, 1024, 0, stream, X, TF, abs_input, pre_func, normalize, silence_db, out);
+    return AMSS_OK;
+}
+
+extern "C" int amss_label_weights(const float* X, int B, int64_t TF, int function_mask, float silence_threshold, float* w,
+                                  void* stream) {
+    AMSS_REQUIRE(X && w && B > 0 && TF > 0 && function_mask >= 0 && function_mask <= 3, "label_weights: bad arguments");
+    AMSS_LAUNCH(label_weights_kernel, B, 1024, 0, stream, X, TF, function_mask, silence_threshold, w);
+    return AMSS_OK;
+}
 
 extern "C" int amss_prepare_inputs(float* x_non_mix, int B, int S, int64_t L, int normalize, float* stats, float* x_mix,
                                    void* stream) {

@@ -422,7 +422,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, 
 // cost = mean_{b,i,s} softplus(-y * <spk[b,s], emb[b,i]>), y = +1 if labels[b,i]==s else -1
 __global__ void __launch_bounds__(LS_THREADS)
 l41_fwd_kernel(const float* __restrict__ emb, const uint8_t* __restrict__ labels, const float* __restrict__ spk,
-               int64_t TF, int E, int S, float* __restrict__ part) {
+               const float* __restrict__ weights, int64_t TF, int E, int S, float* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
     __shared__ float red[32];
     const int EP = E + 1;
@@ -441,10 +441,13 @@ l41_fwd_kernel(const float* __restrict__ emb, const uint8_t* __restrict__ labels
         __syncthreads();
         if (tid < np) {
             const int l = labels[(size_t)b * TF + p0 + tid];
+            // y = +-1 (one_hot(argmax, S, 1, -1)) times the optional label weight (function_mask / silence_loss,
+            // models/network.py:381-396)
+            const float w = weights ? weights[(size_t)b * TF + p0 + tid] : 1.f;
             for (int s = 0; s < S; ++s) {
                 float d = 0.f;
                 for (int e = 0; e < E; ++e) d = fmaf(sp[s * E + e], xs[tid * EP + e], d);
-                const float x = (l == s) ? d : -d;
+                const float x = ((l == s) ? d : -d) * w;
                 // -log(sigmoid(x)) = softplus(-x)
                 acc += (x > 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
             }
@@ -463,8 +466,8 @@ __global__ void l41_fwd_final_kernel(const float* __restrict__ part, int n, floa
 // demb_i = sum_s c_is spk_s ;  dspk_s = sum_i c_is emb_i ;  c_is = -y * sigmoid(-y*dot) * dloss / (B*TF*S)
 __global__ void __launch_bounds__(LS_THREADS)
 l41_bwd_kernel(const float* __restrict__ emb, const uint8_t* __restrict__ labels, const float* __restrict__ spk,
-               const float* __restrict__ dloss, int B, int64_t TF, int E, int S, float* __restrict__ demb,
-               float* __restrict__ dspk_part) {
+               const float* __restrict__ weights, const float* __restrict__ dloss, int B, int64_t TF, int E, int S,
+               float* __restrict__ demb, float* __restrict__ dspk_part) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
     const int EP = E + 1;
     float* xs = reinterpret_cast<float*>(ls_smem);              // [LS_THREADS][EP]
@@ -486,10 +489,11 @@ l41_bwd_kernel(const float* __restrict__ emb, const uint8_t* __restrict__ labels
         __syncthreads();
         if (tid < np) {
             const int l = labels[(size_t)b * TF + p0 + tid];
+            const float w = weights ? weights[(size_t)b * TF + p0 + tid] : 1.f;
             for (int s = 0; s < S; ++s) {
                 float d = 0.f;
                 for (int e = 0; e < E; ++e) d = fmaf(sp[s * E + e], xs[tid * EP + e], d);
-                const float y = (l == s) ? 1.f : -1.f;
+                const float y = ((l == s) ? 1.f : -1.f) * w;
                 cs[tid * S + s] = -y * g / (1.f + expf(y * d));
             }
         }
@@ -734,8 +738,9 @@ extern "C" size_t amss_l41_workspace_bytes(int B, int64_t TF, int E, int S) {
     const int chunks = ls_chunks(B, TF, LS_THREADS);
     return align_up((size_t)B * chunks * 4, 256) + align_up((size_t)B * chunks * S * E * 4, 256);
 }
-extern "C" int amss_l41_loss_fwd(const float* emb, const uint8_t* labels, const float* spk, int B, int64_t TF, int E,
-                                 int S, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int amss_l41_loss_fwd(const float* emb, const uint8_t* labels, const float* spk, const float* weights, int B,
+                                 int64_t TF, int E, int S, float* loss, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
     AMSS_REQUIRE(emb && labels && spk && loss && workspace, "l41_loss_fwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "l41_loss_fwd: S out of range");
     if (workspace_bytes < amss_l41_workspace_bytes(B, TF, E, S)) { set_error("l41_loss_fwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
@@ -743,14 +748,14 @@ extern "C" int amss_l41_loss_fwd(const float* emb, const uint8_t* labels, const 
     const size_t smem = ((size_t)LS_THREADS * (E + 1) + (size_t)S * E) * 4;
     AMSS_CUDA(cudaFuncSetAttribute(l41_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(chunks, B);
-    AMSS_LAUNCH(l41_fwd_kernel, grid, LS_THREADS, smem, stream, emb, labels, spk, TF, E, S, (float*)workspace);
+    AMSS_LAUNCH(l41_fwd_kernel, grid, LS_THREADS, smem, stream, emb, labels, spk, weights, TF, E, S, (float*)workspace);
     AMSS_LAUNCH(l41_fwd_final_kernel, 1, 32, 0, stream, (const float*)workspace, B * chunks,
                 (float)B * (float)TF * (float)S, loss);
     return AMSS_OK;
 }
-extern "C" int amss_l41_loss_bwd(const float* emb, const uint8_t* labels, const float* spk, const float* dloss, int B,
-                                 int64_t TF, int E, int S, float* demb, float* dspk, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+extern "C" int amss_l41_loss_bwd(const float* emb, const uint8_t* labels, const float* spk, const float* weights,
+                                 const float* dloss, int B, int64_t TF, int E, int S, float* demb, float* dspk,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
     AMSS_REQUIRE(emb && labels && spk && dloss && demb && dspk && workspace, "l41_loss_bwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "l41_loss_bwd: S out of range");
     if (workspace_bytes < amss_l41_workspace_bytes(B, TF, E, S)) { set_error("l41_loss_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
@@ -759,7 +764,7 @@ extern "C" int amss_l41_loss_bwd(const float* emb, const uint8_t* labels, const 
     const size_t smem = ((size_t)LS_THREADS * (E + 1) + (size_t)S * E + (size_t)LS_THREADS * S) * 4;
     AMSS_CUDA(cudaFuncSetAttribute(l41_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(chunks, B);
-    AMSS_LAUNCH(l41_bwd_kernel, grid, LS_THREADS, smem, stream, emb, labels, spk, dloss, B, TF, E, S, demb, part);
+    AMSS_LAUNCH(l41_bwd_kernel, grid, LS_THREADS, smem, stream, emb, labels, spk, weights, dloss, B, TF, E, S, demb, part);
     AMSS_LAUNCH(l41_dspk_final_kernel, (B * S * E + 255) / 256, 256, 0, stream, part, B, chunks, S * E, dspk);
     return AMSS_OK;
 }

@@ -328,15 +328,15 @@ class _HeadNormDPCLLossFn(torch.autograd.Function):
 
 class _L41LossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, emb, labels, spk):
-        ctx.save_for_backward(emb, labels, spk)
-        return ops.l41_loss_fwd(emb, labels, spk).view(())
+    def forward(ctx, emb, labels, spk, weights):
+        ctx.save_for_backward(emb, labels, spk, weights)
+        return ops.l41_loss_fwd(emb, labels, spk, weights).view(())
 
     @staticmethod
     def backward(ctx, dloss):
-        emb, labels, spk = ctx.saved_tensors
-        demb, dspk = ops.l41_loss_bwd(emb, labels, spk, dloss.reshape(1).contiguous())
-        return demb, None, dspk
+        emb, labels, spk, weights = ctx.saved_tensors
+        demb, dspk = ops.l41_loss_bwd(emb, labels, spk, dloss.reshape(1).contiguous(), weights)
+        return demb, None, dspk, None
 
 
 class _MakeFilterFn(torch.autograd.Function):
@@ -434,7 +434,25 @@ def istft_masked(spec, masks, S, frame, hop):
     return _ISTFTMaskedFn.apply(spec, masks, S, frame, hop)
 
 
-def pit_wave_l2(x_non_mix, est):
+class _PairDotsFn(torch.autograd.Function):
+    """G[b, b'] = <t[b], a[b']> over L (library GEMM t a^T); gradient to a only: da = dG^T t."""
+
+    @staticmethod
+    def forward(ctx, t, a):
+        ctx.save_for_backward(t)
+        return ops.gemm(t, a, None, transb=True)
+
+    @staticmethod
+    def backward(ctx, dG):
+        t, = ctx.saved_tensors
+        return None, ops.gemm(dG.contiguous(), t, None, transa=True)
+
+
+def pair_dots(t, a):
+    return _PairDotsFn.apply(t, a)
+
+
+def pit_wave_l2(x_non_mix, est, reduce="mean"):
     """cost_finetuning (models/network.py:697-723, models/adapt.py:404-431): 0.5 * sum_L (x_s - xhat_perm(s))^2, mean
     over the S sources, min over the S! permutations, mean over the batch.  The S*S pairwise squared distances come
     from S launches of the fused waveform-statistics kernel (pair s with estimate (s+k) mod S); the permutation
@@ -448,7 +466,8 @@ def pit_wave_l2(x_non_mix, est):
         e = (est if k == 0 else est[:, idx]).reshape(B * S, Lw).contiguous()
         d.append(0.5 * wave_stats(tgt, e)[:, 3].reshape(B, S))
     D = torch.stack(d, 2)                                    # D[b, s, k] = 0.5 * |x[b,s] - est[b,(s+k)%S]|^2
-    costs = [torch.stack([D[:, sidx, (perm[sidx] - sidx) % S] for sidx in range(S)], 1).mean(1)
+    red = (lambda t: t.mean(1)) if reduce == "mean" else (lambda t: t.sum(1))          # over the S sources
+    costs = [red(torch.stack([D[:, sidx, (perm[sidx] - sidx) % S] for sidx in range(S)], 1))
              for perm in itertools.permutations(range(S))]
     return torch.stack(costs, 1).min(1).values.mean()
 
@@ -513,8 +532,8 @@ def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32, head=None):
     return _DPCLLossFn.apply(V.contiguous(), labels, S, precision)
 
 
-def l41_loss(emb, labels, spk):
-    return _L41LossFn.apply(emb, labels, spk)
+def l41_loss(emb, labels, spk, weights=None):
+    return _L41LossFn.apply(emb.contiguous(), labels, spk, weights)
 
 
 def make_filter(window, bases):

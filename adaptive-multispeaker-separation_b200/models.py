@@ -249,6 +249,49 @@ class Adapt(Network):
         return cost, {"y": y, "argmax": am, "back": back, "l2": l2, "sdr": sdr, "sdr_improvement": val,
                       "sparse_constraint": sparse, "overlapping": overlapping, "p_hat": p_hat}
 
+    # adapt.py:339-372 + network.py:196-221 (with_perm=True): the non-pretraining branch of Adapt.cost
+    def cost_separation(self, x_mix, x_non_mix, back, front_y=None):
+        """Adapt.cost with pretraining=False: `back` [B,S,L] is the synthesis of the separator's output.
+          l2  = mean_B min_perm sum_S mean_L (x_s - back_perm(s))^2                              (adapt.py:353-356)
+          sdr = mean_B sum_S min_{b'} tn[b,s] an[b',s] / (<x[b,s], back[b',s]>^2 + 1e-12)          (:358-362)
+        The sdr term reproduces the reference as written: it hands the UN-permuted `back` [B,S,L] to sdr_improvement next to
+        targets shaped [B,1,S,L], so broadcasting pairs target b with estimate b' of every OTHER mixture and the
+        `reduce_min(sdr, 1)` that was meant to run over permutations runs over b' (for B = 1 it is the plain ratio).
+        loss = l2 | sdr | 1e-3 * l2 + sdr (:364-369), then the same regularisers as the pretraining branch (:374-385; the KL
+        and overlap terms need the front output: pass front_y).  The pairwise <x[b,s], back[b',s]> come from the library
+        GEMM, everything else is a [B,B,S] table.  Returns (cost, aux)."""
+        B, S, Lw = x_non_mix.shape
+        l2 = 2.0 / Lw * L.pit_wave_l2(x_non_mix, back, reduce="sum")                       # 0.5*sum -> mean over L, sum over S
+        tn = (x_non_mix ** 2).sum(-1)                                                      # [B,S]   (data, no gradient)
+        st = L.wave_stats(back.reshape(B * S, Lw), back.reshape(B * S, Lw))                # <a,a> with autograd
+        an = st[:, 1].reshape(B, S)
+        cross = torch.stack([L.pair_dots(x_non_mix[:, s].contiguous(), back[:, s].contiguous()) for s in range(S)], 2)  # [B,B',S]
+        ratio = tn.unsqueeze(1) * an.unsqueeze(0) / (cross ** 2 + 1e-12)                   # [B,B',S]
+        sdr = ratio.min(1).values.sum(-1).mean(-1)
+        with torch.no_grad():                                                              # SDR improvement metric (with_perm)
+            mixn = (x_mix ** 2).sum(-1)                                                    # [B'] (mix is tiled to [1,B',S,L])
+            cm = torch.stack([L.pair_dots(x_non_mix[:, s].contiguous(), x_mix.contiguous()) for s in range(S)], 2)
+            separated = 10.0 * torch.log(1.0 / ((tn.unsqueeze(1) * an.unsqueeze(0)) / cross ** 2 - 1.0)) / math.log(10.0)
+            non_sep = 10.0 * torch.log(1.0 / ((tn.unsqueeze(1) * mixn.view(1, B, 1)) / cm ** 2 - 1.0)) / math.log(10.0)
+            val = (separated - non_sep).mean(-1).mean(0).max(-1).values
+        cost = l2 if self.loss == "l2" else (sdr if self.loss == "sdr" else 1e-3 * l2 + sdr)
+        filt, filt2 = self.conv_filter("front"), self.conv_filter("back")
+        if front_y is not None:
+            if self.beta != 0.0:
+                p_hat = front_y.abs().reshape(front_y.shape[0], -1).sum(0)
+                rho = torch.as_tensor(self.p, dtype=front_y.dtype, device=front_y.device)
+                clip = lambda t: torch.clamp(t, 1e-10, 1.0)                                # noqa: E731
+                kl = rho * torch.log(clip(rho) / clip(p_hat)) + (1 - rho) * torch.log(clip(1 - rho) / clip(1 - p_hat))
+                cost = cost + self.beta * kl.sum()
+            if self.overlap_coef != 0.0:
+                cost = cost + self.overlap_coef * self.overlap(front_y, B)
+            if self.non_negativity:
+                neg = torch.where(front_y < 0, front_y, torch.zeros_like(front_y)) ** 2
+                cost = cost + self.non_negativity * (self.non_negativity * neg.reshape(neg.shape[0], -1).sum(1).mean())
+        if self.l != 0.0:
+            cost = cost + self.l * (self.l * (0.5 * (filt2 ** 2).sum() + 0.5 * (filt ** 2).sum()))
+        return cost, {"l2": l2, "sdr": sdr, "sdr_improvement": val}
+
     # adapt.py:404-431
     def cost_finetuning(self, x_non_mix, back):
         """PIT waveform loss of the end-to-end fine-tuning recipes: back [B,S,L] = self.back(sepNet output)."""
@@ -285,12 +328,40 @@ class Separator(Network):
         self.beta, self.threshold = a["beta_kmeans"], a["threshold"]
         self.with_silence, self.nb_tries, self.nb_steps = a["with_silence"], a["nb_tries"], a["nb_steps"]
         self.abs_input = a["abs_input"]
-        for flag, off in (("normalize_separator", "None"), ("pre_func", "None"), ("function_mask", "None")):
-            if a[flag] not in (off, None):
-                raise NotImplementedError(f"--{flag} {a[flag]} is outside the hot path (default off, SURVEY 8a11)")
-        if a["silence_loss"] or a["silence_mask_db"] or a["add_dilated"] or a["sampling"] is not None:
-            raise NotImplementedError("silence_loss / silence_mask_db / add_dilated / sampling are outside the hot path")
+        # input / label options (models/network.py:381-396, 409-443, 504-521): library kernels amss_separator_input_prep /
+        # amss_label_weights; argparse hands over the STRING 'None' for the unset choices
+        self.normalize_input, self.pre_func = a["normalize_separator"], a["pre_func"]
+        self.silent_threshold = a["silence_mask_db"]
+        self.function_mask, self.loss_with_silence = a["function_mask"], a["silence_loss"]
+        self.threshold_silence_loss = a["threshold_silence_loss"]
+        for flag, table in (("normalize_separator", ops.NORMALIZE), ("pre_func", ops.PRE_FUNC), ("function_mask", ops.FUNCTION_MASK)):
+            if a[flag] not in table:
+                raise ValueError(f"--{flag} {a[flag]!r}: the reference knows {sorted(k for k in table if k)}")
+        if a["add_dilated"] or a["sampling"] is not None:
+            raise NotImplementedError("add_dilated / negative sampling are outside the hot path (SURVEY section 2, rows 2 and 4)")
+        if not plugged and (self.function_mask not in ("None", None) or self.loss_with_silence):
+            raise ValueError("--function_mask / --silence_loss act on the plugged separator only (models/network.py:381-396)")
         self._build_prediction()
+
+    @property
+    def weighted_labels(self):
+        return self.plugged and (self.function_mask not in ("None", None) or bool(self.loss_with_silence))
+
+    def _prep(self, X, plugged):
+        """init_separator (models/network.py:409-443): plugged: abs_input -> normalisation; STFT: pre_func -> normalisation
+        -> silent-dB mask.  One library kernel; no-op (and no launch) with the default flags."""
+        if plugged:
+            on = self.abs_input or self.normalize_input not in ("None", None)
+            if not on:
+                return X
+            if X.requires_grad:
+                raise AmssError("separator input options are forward-only: the front end must be frozen")
+            return ops.separator_input_prep(X.contiguous(), abs_input=self.abs_input, normalize=self.normalize_input)
+        on = self.pre_func not in ("None", None) or self.normalize_input not in ("None", None) or self.silent_threshold > 0
+        if not on:
+            return X
+        return ops.separator_input_prep(X.contiguous(), pre_func=self.pre_func, normalize=self.normalize_input,
+                                        silence_db=float(self.silent_threshold))
 
     # DPCL.prediction / L41Model.prediction trunk (dpcl.py:19-39, L41.py:21-45)
     def _build_prediction(self):
@@ -308,13 +379,18 @@ class Separator(Network):
     def preprocessing(self, x_mix, x_non_mix, want_mag_non_mix=False):
         spec, X = ops.stft(x_mix.contiguous(), self.window_size, self.hop_size)
         labels, mag_nm = ops.stft_labels(x_non_mix.contiguous(), self.window_size, self.hop_size, want_mag_non_mix)
-        return {"stfts": spec, "X": X, "labels": labels, "X_non_mix": mag_nm}
+        # X_input (the magnitudes the masks multiply, network.py:498) stays raw; X (the network input) takes the options
+        return {"stfts": spec, "X": self._prep(X, False), "X_input": X, "labels": labels, "X_non_mix": mag_nm}
 
     # network.py:357-400 (plugged branch, default flags)
     def plugged_inputs(self, front_y, B):
         X = front_y[:B]
         labels = ops.plugged_labels(front_y.contiguous(), B, self.S)
-        return {"X": X.abs() if self.abs_input else X, "labels": labels, "X_raw": X}
+        weights = None
+        if self.weighted_labels:                             # y * f(|X| / max) and / or y * silence mask (network.py:381-396)
+            weights = ops.label_weights(X.detach().contiguous(), self.function_mask,
+                                        self.threshold_silence_loss if self.loss_with_silence else 0.0)
+        return {"X": self._prep(X, True), "labels": labels, "X_raw": X, "weights": weights}
 
     def prediction(self, X):
         """X [B,T,F] -> embeddings [B,T,F,E] (L2-normalised over E unless --no_normalize)."""
@@ -407,8 +483,12 @@ class DPCL(Separator):
     """models/dpcl.py -- affinity loss with un-squared Frobenius norms, one-hot labels 1/0."""
     mask_a, mask_b = 1.0, 0.0
 
-    def cost(self, V, labels, I=None):
+    def cost(self, V, labels, I=None, weights=None):
         B, Tt, Fb, E = V.shape
+        if weights is not None:
+            # Y = one_hot * w is no longer one-hot: D = 1/sqrt(Y Y^T 1) needs per-point weights in every DPCL kernel, and
+            # with --silence_loss the reference itself divides by zero there (D = 1/sqrt(0)); supported for L41 only
+            raise NotImplementedError("--function_mask / --silence_loss with the DPCL cost (weighted label matrix)")
         return L.dpcl_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), self.S,
                            prenorm=getattr(V, "_amss_prenorm", None), precision=self.precision,
                            head=getattr(V, "_amss_head", None))
@@ -425,13 +505,13 @@ class L41Model(Separator):
         v = torch.randn(self.num_speakers, E, generator=g, dtype=torch.float64).clamp_(-2.0, 2.0) * math.sqrt(2.0 / E)
         self.store.register("speaker_centroids", v.float())          # L41.py:16-18
 
-    def cost(self, V, labels, I):
+    def cost(self, V, labels, I, weights=None):
         B, Tt, Fb, E = V.shape
         sv = self.store["speaker_centroids"]
         if self.normalize:
             sv = L.l2_normalize(sv, E)                               # L41.py:60-61
         spk = sv[I.long()].contiguous()                              # [B,S,E] gather (L41.py:62)
-        return L.l41_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), spk)
+        return L.l41_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), spk, weights)
 
 
 # =================================================================================================

@@ -355,26 +355,27 @@ def dpcl_loss_bwd_normalized_bf16(V, labels, S, dloss, ws, inv_norm):
     return dz
 
 
-def l41_loss_fwd(emb, labels, spk):
-    """emb[B,TF,E], labels uint8 [B,TF], spk[B,S,E] -> loss[1]."""
-    _chk(emb, labels, spk)
+def l41_loss_fwd(emb, labels, spk, weights=None):
+    """emb[B,TF,E], labels uint8 [B,TF], spk[B,S,E], optional label weights [B,TF] -> loss[1]."""
+    _chk(emb, labels, spk, weights)
     B, TF, E = emb.shape
     S = spk.shape[1]
     loss = torch.empty(1, dtype=_f32, device=emb.device)
     ws = _ws(_lib.query("amss_l41_workspace_bytes", B, TF, E, S), emb.device)
-    _lib.call("amss_l41_loss_fwd", _p(emb), _p(labels), _p(spk), B, TF, E, S, _p(loss), _p(ws), ws.numel(), _stream())
+    _lib.call("amss_l41_loss_fwd", _p(emb), _p(labels), _p(spk), _p(weights), B, TF, E, S, _p(loss), _p(ws), ws.numel(),
+              _stream())
     return loss
 
 
-def l41_loss_bwd(emb, labels, spk, dloss):
-    _chk(emb, labels, spk, dloss)
+def l41_loss_bwd(emb, labels, spk, dloss, weights=None):
+    _chk(emb, labels, spk, dloss, weights)
     B, TF, E = emb.shape
     S = spk.shape[1]
     demb = torch.empty_like(emb)
     dspk = torch.empty_like(spk)
     ws = _ws(_lib.query("amss_l41_workspace_bytes", B, TF, E, S), emb.device)
-    _lib.call("amss_l41_loss_bwd", _p(emb), _p(labels), _p(spk), _p(dloss), B, TF, E, S, _p(demb), _p(dspk), _p(ws),
-              ws.numel(), _stream())
+    _lib.call("amss_l41_loss_bwd", _p(emb), _p(labels), _p(spk), _p(weights), _p(dloss), B, TF, E, S, _p(demb), _p(dspk),
+              _p(ws), ws.numel(), _stream())
     return demb, dspk
 
 
@@ -449,6 +450,31 @@ def prepare_inputs(x_non_mix, normalize=False):
     stats = torch.empty(B * S, 2, dtype=_f32, device=x_non_mix.device) if normalize else None
     _lib.call("amss_prepare_inputs", _p(x_non_mix), B, S, Lw, int(bool(normalize)), _p(stats), _p(x_mix), _stream())
     return x_mix, stats
+
+
+PRE_FUNC = {"None": 0, None: 0, "sqrt": 1, "log": 2}
+NORMALIZE = {"None": 0, None: 0, "01": 1, "meanstd": 2}
+FUNCTION_MASK = {"None": 0, None: 0, "linear": 1, "sqrt": 2, "square": 3}
+
+
+def separator_input_prep(X, abs_input=False, pre_func="None", normalize="None", silence_db=0.0):
+    """X [B,...] -> same shape: abs -> sqrt / log10 -> '01' / 'meanstd' normalisation over each mixture -> silent-dB mask."""
+    _chk(X)
+    B = X.shape[0]
+    out = torch.empty_like(X)
+    _lib.call("amss_separator_input_prep", _p(X), B, X.numel() // B, int(bool(abs_input)), PRE_FUNC[pre_func],
+              NORMALIZE[normalize], float(silence_db), _p(out), _stream())
+    return out
+
+
+def label_weights(X, function_mask="None", silence_threshold=0.0):
+    """Mixture rows X [B,...] -> label weights [B,TF] (function_mask linear/sqrt/square and/or the silence-loss mask)."""
+    _chk(X)
+    B = X.shape[0]
+    w = torch.empty(B, X.numel() // B, dtype=_f32, device=X.device)
+    _lib.call("amss_label_weights", _p(X), B, X.numel() // B, FUNCTION_MASK[function_mask], float(silence_threshold), _p(w),
+              _stream())
+    return w
 
 
 # ------------------------------------------------------------------------------------------

@@ -474,7 +474,48 @@ class Front_Separator_Trainer(Trainer):
             y, _ = self.model.front(x_mix, x_non_mix)
         inp = self.sepNet.plugged_inputs(y, B)
         V = self.sepNet.prediction(inp["X"].contiguous())
+        if inp["weights"] is not None:
+            return self.sepNet.cost(V, inp["labels"], ind, inp["weights"])
         return self.sepNet.cost(V, inp["labels"], ind)
+
+
+class Front_Separator_Enhance_Trainer(Trainer):
+    """utils/trainer.py:600-610 + Adapt.connect_enhance_to_separator (models/adapt.py:456-469): pretrained front / back and a
+    trained separator, all frozen; the enhance BLSTM layer is trained on the k-means separated front output with the PIT-L2
+    enhance cost against the sources' front responses (models/network.py:662-693 with the plugged X_non_mix).
+    model_folder restore is replaced by an optional state dict; init_idx as in STFT_Separator_enhance_Trainer."""
+
+    def __init__(self, separator, name="Front_Separator_Enhance", state=None, **kwargs):
+        self.separator_class, self.name, self.state = separator, name, state
+        self.init_idx = None
+        super().__init__(**kwargs)
+
+    def build(self):
+        args = {k: v for k, v in self.args.items() if k in DEFAULTS or k in ("window_size", "hop_size")}
+        args["pretraining"] = False
+        self.model = Adapt(**args)
+        self.sepNet = self.model.connect_front(self.separator_class)
+        self.sepNet.add_enhance_layer()
+        self.store = self.model.store
+
+    def post_build(self):
+        if self.state:
+            self.store.load_state_dict(self.state, strict=False)
+        self.model.freeze_all_except("enhance/")
+
+    def loss(self, x_mix, x_non_mix, ind):
+        sn = self.sepNet
+        B = x_mix.shape[0]
+        with torch.no_grad():
+            y, _ = self.model.front(x_mix, x_non_mix)
+            inp = sn.plugged_inputs(y, B)
+            X_in = inp["X_raw"].contiguous()
+            V = sn.prediction(inp["X"].contiguous())
+            sep, _ = sn.separate(V, X_in, self.init_idx)
+            Tp, N = y.shape[1], y.shape[2]
+            X_non_mix = y[B:].reshape(B, sn.S, Tp, N).permute(0, 2, 3, 1).contiguous()          # [B,T,N,S] (network.py:372)
+        _, cost_in = sn.enhance(sep, X_in)
+        return sn.enhance_cost(cost_in, X_non_mix)
 
 
 class Adapt_Pretrainer(Trainer):
@@ -522,8 +563,8 @@ class STFT_Separator_enhance_Trainer(Trainer):
         pre = m.preprocessing(x_mix, x_non_mix, want_mag_non_mix=True)
         with torch.no_grad():                       # hard k-means labels are not differentiable (network.py:554-582)
             V = m.prediction(pre["X"])
-            sep, _ = m.separate(V, pre["X"], self.init_idx)
-        _, cost_in = m.enhance(sep, pre["X"])
+            sep, _ = m.separate(V, pre["X_input"], self.init_idx)
+        _, cost_in = m.enhance(sep, pre["X_input"])
         return m.enhance_cost(cost_in, pre["X_non_mix"])
 
 
@@ -555,7 +596,7 @@ class STFT_Separator_FineTune_Trainer(Trainer):
         m = self.model
         spec, X = ops.stft(x_mix.contiguous(), m.window_size, m.hop_size)
         with torch.no_grad():
-            V = m.prediction(X)
+            V = m.prediction(m._prep(X, False))
             sep, _ = m.separate(V, X, self.init_idx)
         m.enhance(sep, X)
         out = m.postprocessing_masks(spec, m.enhance_masks)                   # [B,S,L']
@@ -595,7 +636,7 @@ class Front_Separator_Enhance_Finetuning_Trainer(Trainer):
         y, am = m.front(x_mix, x_non_mix)
         X = y[:B].contiguous()
         with torch.no_grad():                       # hard k-means labels are not differentiable
-            V = sn.prediction(X.detach())
+            V = sn.prediction(sn._prep(X.detach(), True))
             _, lab = sn.separate(V, X.detach(), self.init_idx)
         Xf = X.reshape(B, -1)
         sep = torch.stack([Xf * (lab == k).to(Xf.dtype) for k in range(sn.S)], 1).reshape(B * sn.S, X.shape[1], X.shape[2]) \
@@ -667,7 +708,7 @@ class STFT_Separator_Inference(_StreamingInference):
     def infer(self, x_mix, init_idx=None):
         m = self.model
         spec, X = ops.stft(x_mix.contiguous(), m.window_size, m.hop_size)
-        V = m.prediction(X)
+        V = m.prediction(m._prep(X, False))
         _, lab = m.separate(V, X, init_idx if init_idx is not None else self.init_idx)
         return m.postprocessing(spec, lab)
 
@@ -693,7 +734,7 @@ class Front_Separator_Inference(_StreamingInference):
         B, Lw = x_mix.shape
         y, am = self.model.front(x_mix, x_non_mix)
         X = y[:B].contiguous()
-        V = self.sepNet.prediction(X)
+        V = self.sepNet.prediction(self.sepNet._prep(X, True))
         sep, _ = self.sepNet.separate(V, X, init_idx if init_idx is not None else self.init_idx)
         return self.model.back(sep, am, B, Lw)
 

@@ -241,12 +241,15 @@ int amss_dpcl_loss_bwd_normalized_bf16(const float* V, const uint8_t* labels, co
 /* L41Model.cost, sampling=None (models/L41.py:47-63, 150-178):
  * mean_{b,tf,s} -log sigmoid(y * <spk[b,s,:], emb[b,tf,:]>), y=+1 if labels==s else -1.
  * spk[B,S,E] = (normalised) gathered speaker vectors.                                   */
-int amss_l41_loss_fwd(const float* emb, const uint8_t* labels, const float* spk, int B,
-                      int64_t TF, int E, int S, float* loss, void* workspace,
-                      size_t workspace_bytes, void* stream);
+/* weights[B,TF] (optional, NULL = 1): y is multiplied by it -- the label weighting of
+ * --function_mask / --silence_loss (models/network.py:381-396, amss_label_weights).      */
+int amss_l41_loss_fwd(const float* emb, const uint8_t* labels, const float* spk,
+                      const float* weights, int B, int64_t TF, int E, int S, float* loss,
+                      void* workspace, size_t workspace_bytes, void* stream);
 int amss_l41_loss_bwd(const float* emb, const uint8_t* labels, const float* spk,
-                      const float* dloss, int B, int64_t TF, int E, int S, float* demb,
-                      float* dspk, void* workspace, size_t workspace_bytes, void* stream);
+                      const float* weights, const float* dloss, int B, int64_t TF, int E, int S,
+                      float* demb, float* dspk, void* workspace, size_t workspace_bytes,
+                      void* stream);
 size_t amss_l41_workspace_bytes(int B, int64_t TF, int E, int S);
 /* labels_u8[B,T,F] = argmax_s |X_non_mix| from the front output (network.py:369-378):
  * front_y[B(S+1),Tp,N]: rows [0,B) mixtures, rows B+b*S+s the sources.                  */
@@ -283,6 +286,18 @@ int amss_apply_masks(const float* X_input, const int32_t* labels, const float* s
  * mixture x_mix[B,L] = ((x_0 + x_1) + x_2 ...) (data/dataset.py:462-468).  S <= 8.         */
 int amss_prepare_inputs(float* x_non_mix, int B, int S, int64_t L, int normalize, float* stats,
                         float* x_mix, void* stream);
+/* Separator input options (models/network.py:409-443, 504-521), applied per mixture row of
+ * X[B,TF] in this order: abs_input -> pre_func (0 none, 1 sqrt, 2 log10(x+1e-12)) ->
+ * normalize (0 none, 1 '01': (x-min)/(max-min), 2 'meanstd': (x-mean)/sqrt(var)) ->
+ * silence mask (silence_db > 0: x * [(max - x) < silence_db/20], max of the normalised row).
+ * out may alias X.  Forward only (the input of the separator is data in every recipe).  */
+int amss_separator_input_prep(const float* X, int B, int64_t TF, int abs_input, int pre_func,
+                              int normalize, float silence_db, float* out, void* stream);
+/* Label weights of the plugged separator (models/network.py:381-396) from the mixture rows X[B,TF]:
+ * function_mask 0 none / 1 linear |X|/max / 2 sqrt / 3 square, times (silence_threshold > 0)
+ * [log10(max/|X|) < silence_threshold]  ->  w[B,TF].                                      */
+int amss_label_weights(const float* X, int B, int64_t TF, int function_mask,
+                       float silence_threshold, float* w, void* stream);
 
 /* ------------------------------------------------------------------------------------ *
  * Optimizer  (utils/ops.py:639-704 AMSGrad; models/network.py:181-192)

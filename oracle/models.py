@@ -249,6 +249,49 @@ def separator_plugged_inputs(front_y, B, S, a, b):
     return {"X": X, "X_non_mix": X_nm, "y": y, "argmax": idx}
 
 
+def separator_input_prep(X, plugged, abs_input=False, pre_func="None", normalize="None", silence_db=0.0):
+    """Separator.init_separator (models/network.py:409-443) + normalization01 / normalization_mean_std (:504-521).
+    plugged: abs_input -> normalisation.  STFT: pre_func (sqrt | log10(x + 1e-12)) -> normalisation -> silent-dB mask
+    `mask = (max - X) < silence_db / 20` (max over (T,F) of the normalised X)."""
+    if plugged:
+        if abs_input:
+            X = X.abs()
+    else:
+        if pre_func == "sqrt":
+            X = torch.sqrt(X)
+        elif pre_func == "log":
+            X = T.log10(X + 1e-12)
+    if normalize == "01":
+        mn = X.amin((1, 2), keepdim=True)
+        mx = X.amax((1, 2), keepdim=True)
+        X = (X - mn) / (mx - mn)
+    elif normalize == "meanstd":
+        mean = X.mean((1, 2), keepdim=True)
+        var = X.var((1, 2), unbiased=False, keepdim=True)
+        X = (X - mean) / torch.sqrt(var)
+    if not plugged and silence_db > 0:
+        mx = X.amax((1, 2), keepdim=True)
+        X = ((mx - X) < silence_db / 20.0).to(X.dtype) * X
+    return X
+
+
+def plugged_label_weights(X, function_mask="None", silence_loss=False, threshold_silence_loss=2.0):
+    """Separator.__init__ plugged branch (models/network.py:381-396): the factor the one-hot labels are multiplied by:
+    function_mask linear |X|/max, sqrt, square; silence_loss: [log10(max/|X|) < threshold].  X = mixture rows [B,T,N]."""
+    a = X.abs()
+    mx = a.amax((1, 2), keepdim=True)
+    w = torch.ones_like(a)
+    if function_mask == "linear":
+        w = a / mx
+    elif function_mask == "sqrt":
+        w = torch.sqrt(a / mx)
+    elif function_mask == "square":
+        w = (a / mx) ** 2
+    if silence_loss:
+        w = w * (T.log10(mx / a) < threshold_silence_loss).to(a.dtype)
+    return w
+
+
 def blstm_stack(p, prefix, nb_layers, x):
     for i in range(nb_layers):
         f = f"{prefix}/forward_BLSTM_{i}/rnn/basic_lstm_cell"
@@ -287,7 +330,8 @@ def dpcl_cost(V4, y):
 
 
 def l41_cost(p, emb, y, I, normalize=True):
-    """L41Model.cost, sampling=None branch (models/L41.py:47-63, 150-178)."""
+    """L41Model.cost, sampling=None branch (models/L41.py:47-63, 150-178).  y may already carry the label weights of
+    --function_mask / --silence_loss (y * w[..., None], models/network.py:381-396)."""
     sv = p["speaker_centroids"]
     if normalize:
         sv = T.l2_normalize(sv, 1)
@@ -355,6 +399,36 @@ def enhance_cost(cost_in, X_non_mix):
     for perm in itertools.permutations(range(S)):
         costs.append(((tgt - est[:, list(perm)]) ** 2).sum(-1).sum(-1))
     return torch.stack(costs, 1).min(1).values.mean()
+
+
+def adapt_separation_cost(p, x_mix, x_non_mix, back, *, loss="sdr", regularization=1e-4):
+    """Adapt.cost, pretraining=False branch (models/adapt.py:339-372) + Network.sdr_improvement(with_perm=True)
+    (models/network.py:196-221), written with the SAME broadcasting the TF graph performs: the targets are reshaped to
+    [B,1,S,L] while `back` stays [B,S,L] (= [1,B,S,L]), so every product below has shape [B,B,S(,L)] -- targets of mixture
+    b against the estimates of every mixture b' -- and `reduce_min(sdr, 1)` runs over b'.  Only the l2 term sees the
+    permuted estimates.  KL / overlap / non-negativity terms need the front output and are left to the caller."""
+    B, S, L = x_non_mix.shape
+    perms = list(itertools.permutations(range(S)))
+    permuted = torch.stack([back[:, list(pm)] for pm in perms], 1)          # [B,P,S,L]
+    X_nmr = x_non_mix.reshape(B, 1, S, L)
+    l2 = ((X_nmr - permuted) ** 2).mean(-1).sum(-1).min(-1).values.mean(-1)
+    # sdr_improvement(X_nmr, back, True)
+    mix = x_mix.unsqueeze(1).repeat(1, S, 1)                                # [B,S,L]
+    tn = (X_nmr ** 2).sum(-1)                                               # [B,1,S]
+    an = (back ** 2).sum(-1)                                                # [B,S]   -> broadcasts as [1,B,S]
+    mn = (mix ** 2).sum(-1)
+    ts2 = ((X_nmr * back).sum(-1)) ** 2                                     # [B,B,S]
+    tm2 = ((X_nmr * mix).sum(-1)) ** 2
+    separated = 10.0 * T.log10(1.0 / ((tn * an) / ts2 - 1.0))
+    non_separated = 10.0 * T.log10(1.0 / ((tn * mn) / tm2 - 1.0))
+    sdr_tab = (tn * an) / (ts2 + 1e-12)
+    val = (separated - non_separated).mean(-1).mean(0).max(-1).values
+    sdr = sdr_tab.min(1).values.sum(-1).mean(-1)
+    cost = l2 if loss == "l2" else (sdr if loss == "sdr" else 1e-3 * l2 + sdr)
+    if regularization != 0.0:
+        f1, f2 = adapt_filters(p, "front"), adapt_filters(p, "back")
+        cost = cost + regularization * (regularization * (0.5 * (f2 ** 2).sum() + 0.5 * (f1 ** 2).sum()))
+    return cost, {"l2": l2, "sdr": sdr, "sdr_improvement": val}
 
 
 def cost_finetuning(x_non_mix, est):

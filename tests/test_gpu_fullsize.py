@@ -1,5 +1,6 @@
 """Full-size (BASELINE.json geometry: L = 64000 samples, W = 1024 taps, 256 filters, pool 256, T = 250, 3 x BLSTM-600,
-E = 40) checks through size-independent properties -- the oracle is too slow for these sizes, so each test states a
+E = 40) checks through size-independent properties (the comparisons with the ORACLE at this geometry are in
+test_gpu_fullsize_oracle.py): each test states a
 property of the reference operator that must hold at any size, plus agreement between the fp32 parity kernels and the
 tensor-core kernels on the same inputs."""
 import numpy as np

@@ -512,3 +512,121 @@ def test_dataset_normalize_and_device_built_mixture(amss):
     assert abs(float(c) - c_ref) < REL * abs(c_ref)
     for k in st.tr:
         assert rel(t.store[k], st.tr[k]) < REL, k
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round 2: separator input / label options, the PIT branch of Adapt.cost, the plugged enhance recipe
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("plugged,opts", [
+    (True, dict(abs_input=True, normalize="01")), (True, dict(abs_input=False, normalize="meanstd")),
+    (False, dict(pre_func="sqrt", normalize="meanstd", silence_db=30.0)), (False, dict(pre_func="log", normalize="01")),
+    (False, dict(silence_db=40.0)),
+])
+def test_separator_input_options_match_oracle(amss, plugged, opts):
+    """--abs_input / --pre_func / --normalize_separator / --silence_mask_db (models/network.py:409-443, 504-521)."""
+    ops = amss["ops"]
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(3, 37, 65, generator=g)
+    if not plugged:
+        X = X.abs() + 1e-3
+    want = M.separator_input_prep(X, plugged, **opts)
+    got = ops.separator_input_prep(_dev(X), **opts)
+    if opts.get("silence_db", 0) > 0:                     # the mask is a threshold: compare away from it
+        mx = want.amax((1, 2), keepdim=True) if False else None
+        agree = ((got.cpu() == 0) == (want == 0)).float().mean()
+        assert float(agree) > 0.999
+        keep = (got.cpu() != 0) & (want != 0)
+        assert rel(got.cpu()[keep], want[keep]) < 1e-5
+    else:
+        assert rel(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("fm,sl", [("linear", False), ("sqrt", True), ("square", False), ("None", True)])
+def test_l41_with_weighted_labels_matches_oracle(amss, fm, sl):
+    """--function_mask / --silence_loss (models/network.py:381-396) on the plugged L41 separator: the labels +-1 are scaled
+    per bin; two optimisation steps of the frozen-front recipe against the oracle."""
+    tr, mo = amss["trainer"], amss["models"]
+    ops = amss["ops"]
+    B, S, Lw = 2, 2, 2048
+    cfg = dict(nb_layers=1, layer_size=16, embedding_size=6, window_size=32, filters=16, max_pool=32, hop_size=32,
+               with_max_pool=True, function_mask=fm, silence_loss=sl, threshold_silence_loss=1.0)
+    t = tr.Front_Separator_Trainer(mo.L41Model, learning_rate=1e-3, **cfg)
+    p = _copy_params(t.store, {})
+
+    def fn(pp, xm, xn, I):
+        with torch.no_grad():
+            fr = M.adapt_front(pp, xm, xn, 32, 32)
+        inp = M.separator_plugged_inputs(fr["y"], B, S, 1.0, -1.0)
+        w = M.plugged_label_weights(inp["X"], fm, sl, 1.0)
+        V = M.separator_prediction(pp, inp["X"], 1, 6)
+        return M.l41_cost(pp, V, inp["y"] * w.unsqueeze(-1), I), {"w": w}
+
+    st = OS.Stepper(p, fn, lr=1e-3)
+    for step in range(2):
+        mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=700 + step)
+        c_ref, aux = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+    for k in st.tr:
+        assert rel(t.store[k], st.tr[k]) < REL, k
+    with pytest.raises(NotImplementedError):              # the DPCL cost refuses weighted labels (and says why)
+        tr.Front_Separator_Trainer(mo.DPCL, learning_rate=1e-3, **cfg).train_step(_dev(mix), _dev(nm), _dev(I))
+
+
+@pytest.mark.parametrize("loss", ["sdr", "l2", "sdr+l2"])
+def test_adapt_cost_pit_branch_matches_oracle(amss, loss):
+    """Adapt.cost with pretraining=False (models/adapt.py:339-372) incl. the reference's cross-mixture broadcast in the sdr
+    term (sdr_improvement(..., with_perm=True), models/network.py:196-221): cost, SDR-improvement metric and d cost / d back."""
+    mo = amss["models"]
+    B, S, Lw = 3, 2, 1500
+    a = mo.Adapt(window_size=32, filters=8, max_pool=16, hop_size=16, with_max_pool=True, pretraining=False, loss=loss)
+    a.finalize()
+    p = _copy_params(a.store, {})
+    g = torch.Generator().manual_seed(11)
+    xn = torch.randn(B, S, Lw, generator=g) * 0.1
+    est = (xn[:, [1, 0]] + 0.03 * torch.randn(B, S, Lw, generator=g))
+    e_ref = est.clone().requires_grad_(True)
+    c_ref, aux_ref = M.adapt_separation_cost(p, xn.sum(1), xn, e_ref, loss=loss)
+    (g_ref,) = torch.autograd.grad(c_ref, e_ref)
+    e = _dev(est).requires_grad_(True)
+    c, aux = a.cost_separation(_dev(xn.sum(1)), _dev(xn), e)
+    (gd,) = torch.autograd.grad(c, e)
+    assert abs(float(c) - float(c_ref)) < REL * abs(float(c_ref))
+    assert abs(float(aux["sdr_improvement"]) - float(aux_ref["sdr_improvement"])) < 1e-2
+    assert rel(gd, g_ref) < REL
+
+
+def test_front_separator_enhance_trainer_matches_oracle(amss):
+    """Front_Separator_Enhance_Trainer (utils/trainer.py:600-610, models/adapt.py:456-469): frozen front + separator, the
+    enhance layer trained with the plugged PIT-L2 enhance cost against the sources' front responses."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 2048
+    cfg = dict(nb_layers=1, layer_size=16, embedding_size=6, window_size=32, filters=16, max_pool=32, hop_size=32,
+               with_max_pool=True, nb_layers_enhance=1, layer_size_enhance=12, nonlinearity="softmax", nb_tries=2, nb_steps=3)
+    t = tr.Front_Separator_Enhance_Trainer(mo.DPCL, learning_rate=1e-3, **cfg)
+    p = _copy_params(t.store, {})
+    rng = np.random.RandomState(4)
+
+    def fn(pp, xm, xn, I):
+        with torch.no_grad():
+            fr = M.adapt_front(pp, xm, xn, 32, 32)
+            inp = M.separator_plugged_inputs(fr["y"], B, S, 1.0, 0.0)
+            V = M.separator_prediction(pp, inp["X"], 1, 6)
+            km = OracleKMeans(nb_clusters=S, nb_tries=2, nb_iterations=3)
+            sep, _ = M.separate(V, inp["X"], lambda e: km.fit(e, init_idx=fn.init)[1], S)
+        _, cost_in, _ = M.enhance(pp, sep, inp["X"], S, 1)
+        return M.enhance_cost(cost_in, inp["X_non_mix"]), {}
+
+    st = OS.Stepper(p, fn, train_prefixes=("enhance/",), lr=1e-3)
+    front_before = t.store["front/bases/bases"].detach().clone()
+    for step in range(2):
+        mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=800 + step)
+        fn.init = random_init_idx(B * 2, (Lw // 32) * 16, S, rng)
+        t.init_idx = fn.init
+        c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+    for k in st.tr:
+        a, b = t.store[k].detach().double().cpu(), st.tr[k].detach().double()
+        assert float((a - b).abs().max()) < REL * max(float(b.abs().max()), 1e-3), k
+    assert torch.equal(front_before, t.store["front/bases/bases"].detach())
