@@ -20,6 +20,7 @@ int gemm_dispatch(const float* A, int lda, const float* B, int ldb, const float*
                   size_t workspace_bytes, cudaStream_t st);
 bool blstm_rec_tc_supported(int B, int T, int H);
 void blstm_tc_set_profile(long long* dev_buf);
+void blstm_tc_max_clusters(int H, int* out4);
 int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, cudaStream_t st);
 int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
               int K, int accumulate, float* C, int ldc, int swapB, int swapT, int norm_E, float* inv, cudaStream_t st);
@@ -456,5 +457,12 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
 // written to dev_buf (>= 48 int64) by subsequent amss_blstm_fwd calls; NULL switches it off.
 extern "C" int amss_debug_blstm_profile(long long* dev_buf) {
     blstm_tc_set_profile(dev_buf);
+    return AMSS_OK;
+}
+// Diagnostics: co-resident clusters (cudaOccupancyMaxActiveClusters) of the tensor-core recurrence kernels for H hidden
+// units per direction: out[4] = {forward NB=16, forward NB=32, backward NB=16, backward NB=32} (host memory).
+extern "C" int amss_debug_blstm_clusters(int H, int* out4) {
+    AMSS_REQUIRE(out4 && blstm_rec_tc_supported(1, 1, H), "debug_blstm_clusters: bad arguments");
+    blstm_tc_max_clusters(H, out4);
     return AMSS_OK;
 }

@@ -80,10 +80,14 @@ struct RecTcFwd {
 // Dependent tcgen05.mma into ONE accumulator serialise at the MMA pipeline latency (~75 clk each at N = 16..64,
 // measured), so the K steps are dealt round-robin to FW_NACC independent accumulators, summed in the epilogue.
 constexpr int FW_NACC = 1;
-constexpr uint32_t FW_ACOL = 256;     // TMEM: D_a at columns [a*NB, (a+1)*NB), A at [FW_ACOL, FW_ACOL + 8*ksteps)
+// TMEM: D_a at columns [a*NB, (a+1)*NB), A at [FW_ACOL, FW_ACOL + 8*ksteps).  H = 300: 32 + 152 columns -> a 256-column
+// allocation, so TWO CTAs fit the 512 columns of an SM (the NB = 16 variant runs two clusters per SM set: one CTA's
+// exchange / MMA latency is covered by the other CTA's gate math).
+constexpr uint32_t FW_ACOL = 32;
+static_assert(FW_NACC == 1, "FW_ACOL assumes one accumulator of NB <= 32 columns");
 
 template <int NB>
-__global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_fwd_tc_kernel(RecTcFwd p) {
+__global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_fwd_tc_kernel(RecTcFwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[5];          // [0] MMA done, [1..2] h_full[buf], [3..4] zx_full[buf]
     __shared__ uint32_t tmem_base_s;
@@ -402,10 +406,12 @@ struct RecTcBwd {
     int B, T, H, nsub, MT;
 };
 
-constexpr uint32_t BW_ACOL = 256;     // TMEM: D tile (m, parity of the K step) at [(2m+par)*NB, +NB), A tile m at [BW_ACOL + 64m, +64)
+// TMEM: D tile m at [m*NB, +NB), A tile m at [acol + 64m, +64) with acol = MT*NB rounded up to 32 columns.  H = 300, NB = 16:
+// 64 + 192 = 256 columns, two CTAs per SM.
+__host__ __device__ inline uint32_t bw_acol(int MT, int NB) { return (uint32_t)((MT * NB + 31) & ~31); }
 
 template <int NB>
-__global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBwd p) {
+__global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc_kernel(RecTcBwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[6];          // [0] MMA done, [1..2] r_full[buf], [3..5] sv_full[slot]
     __shared__ uint32_t tmem_base_s;
@@ -425,6 +431,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) blstm_rec_bwd_tc_kernel(RecTcBw
     float* dzs = reinterpret_cast<float*>(p_s + 2 * r_bytes);            // [2][128][NB+1] fp32 dz staging for the writers
     float* svs = dzs + 2 * 128 * ZP;                                     // [3][7][NB][32] saved gates / c / c_prev / dy, 3 steps ahead (cp.async ring)
     const uint32_t bar_mma = smem_u32(&bars[0]), r_full = smem_u32(&bars[1]), sv_full = smem_u32(&bars[3]);
+    const uint32_t BW_ACOL = bw_acol(MT, NB);
     const uint32_t tcols = pow2_cols(BW_ACOL + 64 * MT);
 
     if (tid == 0) {
@@ -707,14 +714,17 @@ size_t bwd_smem(int NC, int NB) {
     return (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)3 * 7 * NB * 32 * 4;
 }
 
-int pick_nb(int B, int maxc, int nb_max) {
-    for (int nb : {16, 32, 64}) {
-        if (nb > nb_max) break;
-        const int nsub = (B + nb - 1) / nb;
-        if (2 * nsub <= maxc) return nb;
-    }
-    return nb_max;
+// Sub-batch size: NB = 16 runs two CTAs per SM (twice the co-resident clusters if the GPCs take them), NB = 32 one.
+// A step of an NB = 32 cluster costs ~1.6x a step of an NB = 16 cluster (measured, profiles/r01_blstm_step_profile.txt),
+// so compare waves x step cost; ties go to the smaller sub-batch.
+int pick_nb(int B, int maxc16, int maxc32) {
+    if (const char* e = getenv("AMSS_BLSTM_NB")) { const int v = atoi(e); if (v == 16 || v == 32) return v; }
+    const int c16 = 2 * ((B + 15) / 16), c32 = 2 * ((B + 31) / 32);
+    const float t16 = (float)((c16 + maxc16 - 1) / maxc16) * 1.0f, t32 = (float)((c32 + maxc32 - 1) / maxc32) * 1.6f;
+    return t16 <= t32 ? 16 : 32;
 }
+
+struct MaxC { int c16 = 0, c32 = 0; };
 
 }  // namespace
 
@@ -733,9 +743,12 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
     p.prof = g_prof;
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.y = y;
     p.B = B; p.T = T; p.H = H; p.forget_bias = forget_bias;
-    static int maxc_cache[17] = {0};
-    if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32));
-    const int nb = pick_nb(B, maxc_cache[NC], 32);       // larger batches run as several waves of clusters
+    static MaxC mc[17];
+    if (!mc[NC].c16) {
+        mc[NC].c16 = max_clusters(blstm_rec_fwd_tc_kernel<16>, NC, fwd_smem(NC, 16));
+        mc[NC].c32 = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32));
+    }
+    const int nb = pick_nb(B, mc[NC].c16, mc[NC].c32);   // larger batches run as several waves of clusters
     p.nsub = (B + nb - 1) / nb;
     if (nb == 16) return launch_fwd<16>(p, NC, st);
     return launch_fwd<32>(p, NC, st);
@@ -743,6 +756,15 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
 
 // Sub-batches (clusters per direction) the backward recurrence will run with: sizes the bias-partial buffer.
 int blstm_rec_bwd_tc_nsub(int B, int H);
+
+static int bwd_nb(int B, int NC) {
+    static MaxC mc[17];
+    if (!mc[NC].c16) {
+        mc[NC].c16 = max_clusters(blstm_rec_bwd_tc_kernel<16>, NC, bwd_smem(NC, 16));
+        mc[NC].c32 = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
+    }
+    return pick_nb(B, mc[NC].c16, mc[NC].c32);
+}
 
 int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const float* gates, const float* cst,
                      const float* dy, float* dZ, uint16_t* dZb, int ldzb, float* dbpart, int B, int T, int H, cudaStream_t st) {
@@ -752,9 +774,7 @@ int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const floa
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.dy = dy; p.dZ = dZ;
     p.dZb = dZb; p.ldzb = ldzb; p.dbpart = dbpart;
     p.B = B; p.T = T; p.H = H; p.MT = (NC * 32 + 127) / 128;
-    static int maxc_cache[17] = {0};
-    if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
-    const int nb = pick_nb(B, maxc_cache[NC], 32);
+    const int nb = bwd_nb(B, NC);
     p.nsub = (B + nb - 1) / nb;
     if (nb == 16) return launch_bwd<16>(p, NC, st);
     return launch_bwd<32>(p, NC, st);
@@ -762,10 +782,17 @@ int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const floa
 
 int blstm_rec_bwd_tc_nsub(int B, int H) {
     const int NC = (H + 31) / 32;
-    static int maxc_cache[17] = {0};
-    if (!maxc_cache[NC]) maxc_cache[NC] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
-    const int nb = pick_nb(B, maxc_cache[NC], 32);
+    const int nb = bwd_nb(B, NC);
     return (B + nb - 1) / nb;
+}
+
+// co-resident clusters of both variants (diagnostics: amss_debug_blstm_clusters)
+void blstm_tc_max_clusters(int H, int* out4) {
+    const int NC = (H + 31) / 32;
+    out4[0] = max_clusters(blstm_rec_fwd_tc_kernel<16>, NC, fwd_smem(NC, 16));
+    out4[1] = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32));
+    out4[2] = max_clusters(blstm_rec_bwd_tc_kernel<16>, NC, bwd_smem(NC, 16));
+    out4[3] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
 }
 
 }  // namespace amss

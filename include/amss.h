@@ -159,6 +159,9 @@ int amss_blstm_bwd(const float* x, const float* kernel_fw, const float* kernel_b
 /* Diagnostics only: clock64() stamps of the tensor-core recurrence (CTA 0, steps 100..103, 12
  * slots per step; forward at [0,48), backward at [64,112)) are written to dev_buf (>= 128 int64) by later amss_blstm_fwd calls; NULL = off. */
 int amss_debug_blstm_profile(long long* dev_buf);
+/* Diagnostics only: co-resident clusters of the tensor-core recurrence kernels for H hidden units
+ * per direction, out4 (HOST memory) = {fwd NB=16, fwd NB=32, bwd NB=16, bwd NB=32}.          */
+int amss_debug_blstm_clusters(int H, int* out4);
 
 /* ------------------------------------------------------------------------------------ *
  * Dense / embedding head  (utils/ops.py:486-503 Conv1D k=1, :318-324 Normalize)
