@@ -7,6 +7,11 @@
 // the per-(try, cluster) sums are accumulated by one owner thread per (try, feature) in a fixed
 // order (phase 2), so the result is deterministic (no floating-point atomics anywhere).
 // Per-CTA partials are reduced in a fixed order by a small finalize kernel.
+//
+// HBM traffic: the input is L2-normalised ON THE FLY while a tile is staged (tf.nn.l2_normalize, Kmeans_2.py:40-41): no
+// normalised copy is written or re-read.  The batch is processed in GROUPS of mixtures whose X (10.24 MB per mixture at
+// TF = 64000, E = 40) fits the 126 MB L2 together: all iterations + the inertia pass + the final assignment of a group run
+// before the next group starts, so X is fetched from HBM once per group and the remaining (iters + 2) passes hit L2.
 #include "common.cuh"
 #include <algorithm>
 
@@ -49,8 +54,8 @@ __host__ __device__ inline KmSmemLayout km_layout(int E, int K, int tries, int m
 template <int MODE, int SOFT>
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_pass_kernel(const float* __restrict__ X, const float* __restrict__ cent,
-                   const uint8_t* __restrict__ notsilent, int B, int64_t L, int E, int K, int tries,
-                   float beta, float* __restrict__ part) {
+                   const uint8_t* __restrict__ notsilent, int B, int b_off, int normalize, int64_t L, int E, int K,
+                   int tries, float beta, float* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char km_smem[];
     const KmSmemLayout lay = km_layout(E, K, tries, MODE, SOFT);
     float* xs = reinterpret_cast<float*>(km_smem + lay.xs);
@@ -79,13 +84,24 @@ kmeans_pass_kernel(const float* __restrict__ X, const float* __restrict__ cent,
             xs[p * EP + e] = src[i];
         }
         __syncthreads();
+        if (normalize) {      // x * rsqrt(max(sum x^2, 1e-12)) per point (Kmeans_2.py:40-41), in place in the staged tile
+            if (tid < np) {
+                float* xp = xs + tid * EP;
+                float ss = 0.f;
+                for (int e = 0; e < E; ++e) ss = fmaf(xp[e], xp[e], ss);
+                const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+                for (int e = 0; e < E; ++e) xp[e] *= inv;
+            }
+            __syncthreads();
+        }
         // ---- phase 1: one thread per point, all tries -------------------------------------
         if (tid < np) {
             const float* xp = xs + tid * EP;
             for (int t = 0; t < tries; ++t) {
                 // the reference tiles notsilent try-major while X is batch-major
-                // (Kmeans_2.py:80 vs :48-52): row r of [B*tries] uses mask row r % B.
-                const int r = b * tries + t;
+                // (Kmeans_2.py:80 vs :48-52): row r of [B*tries] uses mask row r % B (b counts from the start of the
+                // whole batch: the kernel sees a group of it, b_off mixtures in).
+                const int r = (b_off + b) * tries + t;
                 float ns = 1.f;
                 if (notsilent) ns = notsilent[(size_t)(r % B) * L + p0 + tid] ? 1.f : 0.f;
                 float d2u[KM_MAXK];
@@ -133,7 +149,7 @@ kmeans_pass_kernel(const float* __restrict__ X, const float* __restrict__ cent,
             const int f = item % NF;
             const int t = (item / NF) % tries;
             const int g = item / (NF * tries);
-            const int r = b * tries + t;
+            const int r = (b_off + b) * tries + t;
             const uint8_t* nsrow = notsilent ? notsilent + (size_t)(r % B) * L + p0 : nullptr;
             float acc[KM_MAXK];
 #pragma unroll
@@ -232,30 +248,23 @@ __global__ void kmeans_select_kernel(const float* __restrict__ part, const float
 }
 
 // centroids0[r][k] = X[b][init_idx[r][k]]   (Kmeans_2.py:66-71)
+// (normalised on the fly like every other read of X: one warp per initial row)
 __global__ void kmeans_gather_init_kernel(const float* __restrict__ X, const int* __restrict__ idx, int B,
-                                          int64_t L, int E, int K, int tries, float* __restrict__ cent) {
-    const int64_t n = (int64_t)B * tries * K * E;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int e = (int)(i % E);
-        const int64_t rk = i / E;
-        const int b = (int)(rk / ((int64_t)tries * K));
-        const int64_t row = idx[rk];
-        cent[i] = X[((size_t)b * L + row) * E + e];
-    }
-}
-
-// x * rsqrt(max(sum x^2, 1e-12)) per row of E   (Kmeans_2.py:40-41)
-__global__ void rows_l2norm_kernel(const float* __restrict__ X, int64_t rows, int E, float* __restrict__ Y) {
+                                          int64_t L, int E, int K, int tries, int normalize, float* __restrict__ cent) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp; r < rows; r += nwarps) {
-        const float* x = X + r * E;
-        float ss = 0.f;
-        for (int e = lane; e < E; e += 32) ss = fmaf(x[e], x[e], ss);
-        ss = warp_sum(ss);
-        const float inv = rsqrtf(fmaxf(ss, 1e-12f));
-        for (int e = lane; e < E; e += 32) Y[r * E + e] = x[e] * inv;
+    const int64_t rows = (int64_t)B * tries * K;
+    for (int64_t rk = warp; rk < rows; rk += nwarps) {
+        const int b = (int)(rk / ((int64_t)tries * K));
+        const float* x = X + ((size_t)b * L + idx[rk]) * E;
+        float inv = 1.f;
+        if (normalize) {                    // same sequential order as the tile path: bit-identical rows
+            float ss = 0.f;
+            for (int e = 0; e < E; ++e) ss = fmaf(x[e], x[e], ss);
+            inv = rsqrtf(fmaxf(ss, 1e-12f));
+        }
+        for (int e = lane; e < E; e += 32) cent[rk * E + e] = normalize ? x[e] * inv : x[e];
     }
 }
 
@@ -263,15 +272,15 @@ __global__ void rows_l2norm_kernel(const float* __restrict__ X, int64_t rows, in
 template <int SOFT>
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_assign_kernel(const float* __restrict__ X, const float* __restrict__ cent, const uint8_t* __restrict__ notsilent,
-                     const int* __restrict__ best, int B, int64_t L, int E, int K, int tries, float beta,
-                     int* __restrict__ labels, float* __restrict__ soft) {
+                     const int* __restrict__ best, int B, int b_off, int normalize, int64_t L, int E, int K, int tries,
+                     float beta, int* __restrict__ labels, float* __restrict__ soft) {
     extern __shared__ __align__(16) unsigned char km_smem[];
     float* xs = reinterpret_cast<float*>(km_smem);
     float* cs = xs + KM_TILE * (E + 1);
     const int b = blockIdx.y, tid = threadIdx.x, EP = E + 1;
     for (int i = tid; i < K * E; i += KM_THREADS) cs[i] = cent[(size_t)b * K * E + i];
     const uint8_t* nsrow = nullptr;
-    if (notsilent) nsrow = notsilent + (size_t)((b * tries + best[b]) % B) * L;
+    if (notsilent) nsrow = notsilent + (size_t)(((b_off + b) * tries + best[b]) % B) * L;
     const int64_t ntiles = (L + KM_TILE - 1) / KM_TILE;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t p0 = tile * KM_TILE;
@@ -284,7 +293,14 @@ kmeans_assign_kernel(const float* __restrict__ X, const float* __restrict__ cent
         }
         __syncthreads();
         if (tid < np) {
-            const float* xp = xs + tid * EP;
+            float* xw = xs + tid * EP;
+            if (normalize) {
+                float ss = 0.f;
+                for (int e = 0; e < E; ++e) ss = fmaf(xw[e], xw[e], ss);
+                const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+                for (int e = 0; e < E; ++e) xw[e] *= inv;
+            }
+            const float* xp = xw;
             const float ns = nsrow ? (nsrow[p0 + tid] ? 1.f : 0.f) : 1.f;
             float d2[KM_MAXK];
 #pragma unroll
@@ -357,32 +373,40 @@ int km_chunks(int B, int64_t L) {
     return (int)(ntiles < want ? ntiles : want);
 }
 
+// Mixtures per group: as many as keep the group's X inside ~3/4 of the 126 MB L2 (at least 1).
+int km_group(int B, int64_t L, int E) {
+    const double per = (double)L * E * 4.0;
+    int g = (int)(96.0e6 / per);
+    if (g < 1) g = 1;
+    return g < B ? g : B;
+}
+
 struct KmWs {
-    float *Xn, *cent, *part;
+    float *cent, *part;
     size_t total;
 };
 KmWs km_ws(void* base, int B, int64_t L, int E, int K, int tries) {
     KmWs w;
     size_t off = 0;
     char* p = (char*)base;
-    w.Xn = (float*)(p + off);   off += align_up((size_t)B * L * E * 4, 256);
+    const int G = km_group(B, L, E);
     w.cent = (float*)(p + off); off += align_up((size_t)B * tries * K * E * 4, 256);
-    w.part = (float*)(p + off); off += align_up((size_t)B * km_chunks(B, L) * tries * K * (E + 1) * 4, 256);
+    w.part = (float*)(p + off); off += align_up((size_t)G * km_chunks(G, L) * tries * K * (E + 1) * 4, 256);
     w.total = off;
     return w;
 }
 
 template <int MODE, int SOFT>
-int launch_pass(const float* X, const float* cent, const uint8_t* ns, int B, int64_t L, int E, int K, int tries,
-                float beta, float* part, cudaStream_t st) {
+int launch_pass(const float* X, const float* cent, const uint8_t* ns, int Bg, int B, int b_off, int normalize, int64_t L,
+                int E, int K, int tries, float beta, float* part, cudaStream_t st) {
     const KmSmemLayout lay = km_layout(E, K, tries, MODE, SOFT);
     AMSS_REQUIRE(lay.total <= 227 * 1024, "kmeans: shared memory %zu B exceeds 227 KB (E=%d K=%d tries=%d)",
                  lay.total, E, K, tries);
     AMSS_CUDA(cudaFuncSetAttribute(kmeans_pass_kernel<MODE, SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)lay.total));
-    dim3 grid(km_chunks(B, L), B);
-    AMSS_LAUNCH((kmeans_pass_kernel<MODE, SOFT>), grid, KM_THREADS, lay.total, st, X, cent, ns, B, L, E, K, tries,
-                beta, part);
+    dim3 grid(km_chunks(Bg, L), Bg);
+    AMSS_LAUNCH((kmeans_pass_kernel<MODE, SOFT>), grid, KM_THREADS, lay.total, st, X, cent, ns, B, b_off, normalize, L, E, K,
+                tries, beta, part);
     return AMSS_OK;
 }
 
@@ -411,37 +435,41 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
         return AMSS_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const float* Xw = X;
-    if (normalize_input) {
-        AMSS_LAUNCH(rows_l2norm_kernel, 4 * kNumSMs, 256, 0, st, X, (int64_t)B * L, E, w.Xn);
-        Xw = w.Xn;
-    }
-    AMSS_LAUNCH(kmeans_gather_init_kernel, 64, 256, 0, st, Xw, init_idx, B, L, E, K, tries, w.cent);
-    const int chunks = km_chunks(B, L);
-    int rc;
-    for (int it = 0; it < iters; ++it) {
-        rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st)
-                     : launch_pass<KM_UPDATE, 0>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st);
-        if (rc != AMSS_OK) return rc;
-        AMSS_LAUNCH(kmeans_finalize_kernel, 64, 256, 0, st, w.part, B, chunks, tries, K, E, w.cent);
-    }
-    rc = is_soft ? launch_pass<KM_INERTIA, 1>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st)
-                 : launch_pass<KM_INERTIA, 0>(Xw, w.cent, notsilent, B, L, E, K, tries, beta, w.part, st);
-    if (rc != AMSS_OK) return rc;
-    AMSS_LAUNCH(kmeans_select_kernel, B, 128, 0, st, w.part, w.cent, B, chunks, tries, K, E, inertia, best_try,
-                centroids);
-    // final labels: un-gated X if assign_at_end (Kmeans_2.py:106-107), else the best try's gated labels
-    const uint8_t* ns_final = assign_at_end ? nullptr : notsilent;
+    const int G = km_group(B, L, E);
     const size_t smem = ((size_t)KM_TILE * (E + 1) + (size_t)K * E) * 4;
-    dim3 grid((unsigned)std::min<int64_t>((L + KM_TILE - 1) / KM_TILE, (int64_t)std::max(1, 4 * kNumSMs / B)), B);
-    if (is_soft) {
-        AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(kmeans_assign_kernel<1>, grid, KM_THREADS, smem, st, Xw, centroids, ns_final, best_try, B, L, E, K,
-                    tries, beta, labels, soft);
-    } else {
-        AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        AMSS_LAUNCH(kmeans_assign_kernel<0>, grid, KM_THREADS, smem, st, Xw, centroids, ns_final, best_try, B, L, E, K,
-                    tries, beta, labels, soft);
+    if (is_soft) AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one group of mixtures at a time: every pass over the group's X after the first one is served by the L2
+    for (int b0 = 0; b0 < B; b0 += G) {
+        const int Bg = std::min(G, B - b0);
+        const float* Xg = X + (size_t)b0 * L * E;
+        float* centg = w.cent + (size_t)b0 * tries * K * E;
+        const int chunks = km_chunks(Bg, L);
+        AMSS_LAUNCH(kmeans_gather_init_kernel, 64, 256, 0, st, Xg, init_idx + (size_t)b0 * tries * K, Bg, L, E, K, tries,
+                    normalize_input, centg);
+        int rc;
+        for (int it = 0; it < iters; ++it) {
+            rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
+                         : launch_pass<KM_UPDATE, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
+            if (rc != AMSS_OK) return rc;
+            AMSS_LAUNCH(kmeans_finalize_kernel, 64, 256, 0, st, w.part, Bg, chunks, tries, K, E, centg);
+        }
+        rc = is_soft ? launch_pass<KM_INERTIA, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
+                     : launch_pass<KM_INERTIA, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
+        if (rc != AMSS_OK) return rc;
+        float* centroids_g = centroids + (size_t)b0 * K * E;
+        AMSS_LAUNCH(kmeans_select_kernel, Bg, 128, 0, st, w.part, centg, Bg, chunks, tries, K, E,
+                    inertia ? inertia + (size_t)b0 * tries : nullptr, best_try + b0, centroids_g);
+        // final labels: un-gated X if assign_at_end (Kmeans_2.py:106-107), else the best try's gated labels
+        const uint8_t* ns_final = assign_at_end ? nullptr : notsilent;
+        dim3 grid((unsigned)std::min<int64_t>((L + KM_TILE - 1) / KM_TILE, (int64_t)std::max(1, 4 * kNumSMs / Bg)), Bg);
+        if (is_soft) {
+            AMSS_LAUNCH(kmeans_assign_kernel<1>, grid, KM_THREADS, smem, st, Xg, centroids_g, ns_final, best_try + b0, B, b0,
+                        normalize_input, L, E, K, tries, beta, (int*)nullptr, soft + (size_t)b0 * L * K);
+        } else {
+            AMSS_LAUNCH(kmeans_assign_kernel<0>, grid, KM_THREADS, smem, st, Xg, centroids_g, ns_final, best_try + b0, B, b0,
+                        normalize_input, L, E, K, tries, beta, labels + (size_t)b0 * L, (float*)nullptr);
+        }
     }
     return AMSS_OK;
 }

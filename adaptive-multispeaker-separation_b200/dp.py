@@ -37,6 +37,48 @@ def allreduce_sum_(flat):
     return 1.0 / dist.get_world_size()
 
 
+class GradBuckets:
+    """The gradient all-reduce of the path, overlapped with the backward pass: the flat gradient buffer is cut into
+    contiguous buckets (one per layer, in the order the backward pass finishes them: head first, first BLSTM layer last),
+    and a bucket's all-reduce(sum) is launched asynchronously the moment the last of its parameters has received its
+    gradient (post-accumulate-grad hooks call ready()).  finish() launches whatever is left (parameters the loss did not
+    reach keep a zero gradient), waits for every bucket and returns the 1/G scale for the optimizer.  Still ONE logical
+    exchange of the gradient per step over the same bytes; on the GPUs the NCCL kernels are captured into the step's CUDA
+    graph together with forward + backward.  Works on any backend (tests/test_dp_gloo.py drives it over gloo)."""
+
+    def __init__(self, flat, buckets):
+        """flat: the 1-D gradient buffer; buckets: [(lo, hi, n_params)] disjoint slices of it."""
+        self.flat = flat
+        self.buckets = [(int(lo), int(hi), int(n)) for lo, hi, n in buckets]
+        self.reset()
+
+    def reset(self):
+        self.left = [n for _, _, n in self.buckets]
+        self.launched = [False] * len(self.buckets)
+        self.works = []
+
+    def _launch(self, i):
+        lo, hi, _ = self.buckets[i]
+        self.launched[i] = True
+        if active() and hi > lo:
+            self.works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def ready(self, i):
+        """One more parameter of bucket i has its gradient."""
+        self.left[i] -= 1
+        if self.left[i] == 0 and not self.launched[i]:
+            self._launch(i)
+
+    def finish(self):
+        for i in range(len(self.buckets)):
+            if not self.launched[i]:
+                self._launch(i)
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return 1.0 / dist.get_world_size() if active() else 1.0
+
+
 def clip_factor(norm_of_sum, clip, grad_scale=1.0):
     """Host statement of what amss_clip_factor computes on the device: tf.clip_by_global_norm (models/network.py:191-192)
     acts on the gradient of the batch-MEAN loss, while after the all-reduce the buffer holds the SUM over the G ranks,

@@ -100,6 +100,22 @@ class ParamStore:
             self._segments = segs
         return self._segments
 
+    def grad_buckets(self):
+        """[(lo, hi, [names])] : the trainable parameters grouped per layer (name up to the last '/'-component that
+        identifies the layer), contiguous in the flat buffer, for the bucketed gradient exchange (dp.GradBuckets)."""
+        out = []
+        for name, (o, n, _, tr) in sorted(self._slices.items(), key=lambda kv: kv[1][0]):
+            if not tr or not self.params[name].requires_grad:
+                continue
+            n4 = (n + 3) // 4 * 4
+            parts = name.split("/")
+            key = parts[0] + "/" + parts[1].replace("forward_", "").replace("backward_", "") if len(parts) > 2 else parts[0]
+            if out and out[-1][3] == key and out[-1][1] == o:
+                out[-1] = (out[-1][0], o + n4, out[-1][2] + [name], key)
+            else:
+                out.append((o, o + n4, [name], key))
+        return [(lo, hi, names) for lo, hi, names, _ in out]
+
     def trainable_span(self):
         """(lo, hi) covering every trainable segment: the range the single gradient all-reduce runs over."""
         segs = self.trainable_segments()

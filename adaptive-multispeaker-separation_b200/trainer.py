@@ -224,8 +224,9 @@ class Trainer:
     # -- optional CUDA-graph replay of forward + backward ---------------------------------------
     def enable_cuda_graph(self, eager_steps=2):
         """Capture zero-grad + loss + backward of one step into a CUDA graph (after `eager_steps` ordinary steps, which
-        also warm every lazily initialised kernel attribute) and replay it from then on; the gradient all-reduce and the
-        optimizer stay outside the graph (their arguments change per step).  Each train_step() call is still exactly
+        also warm every lazily initialised kernel attribute and the NCCL communicator) and replay it from then on; under
+        data parallelism the per-layer gradient all-reduces are part of the graph (launched from the backward pass as each
+        layer's gradients complete); the optimizer stays outside (its step count changes per step).  Each train_step() call is still exactly
         one optimisation step on the batch it is given (inputs are copied into the graph's static buffers).  The loss
         must not depend on host-side state that changes between steps (k-means initial rows, Python control flow on
         data): use it for the Front / STFT separator trainers."""
@@ -245,7 +246,7 @@ class Trainer:
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self.store.grad_flat.zero_()
             cost = self.loss(*self.prepare(cg["inputs"][0], cg["inputs"][1]), cg["inputs"][2])
-            cost.backward()
+            cg["scale"] = self._backward(cost)           # under data parallelism the NCCL kernels are captured too
         cg["graph"], cg["cost"] = graph, cost.detach()
         cg["kernels"] = _lib.launch_count() - n0          # library kernels recorded in the graph = run by every replay
         cg["replays"] = 0
@@ -264,10 +265,33 @@ class Trainer:
             x_mix, _ = ops.prepare_inputs(x_non_mix.contiguous())
         return x_mix, x_non_mix
 
-    def _exchange_and_update(self):
-        lo, hi = self.store.trainable_span()
-        scale = dp.allreduce_sum_(self.store.grad_flat[lo:hi])       # the single collective of the path
-        self.optimizer.step(scale)
+    # -- the gradient exchange: per-layer buckets launched from the backward pass (dp.GradBuckets) ---------------------
+    def _buckets(self):
+        """(Re)build the buckets and the post-accumulate-grad hooks when the trainable set changed."""
+        st = self.store
+        if getattr(self, "_gb_key", None) is not st.trainable_segments():
+            for h in getattr(self, "_gb_hooks", []):
+                h.remove()
+            groups = st.grad_buckets()
+            self._gb = dp.GradBuckets(st.grad_flat, [(lo, hi, len(names)) for lo, hi, names in groups])
+            self._gb_hooks = []
+            for i, (_, _, names) in enumerate(groups):
+                for nme in names:
+                    self._gb_hooks.append(st[nme].register_post_accumulate_grad_hook(lambda p_, i=i: self._gb.ready(i)))
+            self._gb_key = st.trainable_segments()
+        return self._gb
+
+    def _backward(self, cost):
+        """backward + the gradient exchange; returns the scale (1 / world size) the optimizer applies.  Single process:
+        plain backward, no hooks consulted."""
+        if not self.distributed or not self.args.get("overlap_allreduce", True):
+            cost.backward()
+            lo, hi = self.store.trainable_span()
+            return dp.allreduce_sum_(self.store.grad_flat[lo:hi])    # the single collective of the path
+        gb = self._buckets()
+        gb.reset()
+        cost.backward()
+        return gb.finish()
 
     # -- one optimisation step on device tensors ------------------------------------------------
     def train_step(self, x_mix, x_non_mix, ind):
@@ -282,14 +306,14 @@ class Trainer:
                 for dst, src in zip(cg["inputs"], (x_mix, x_non_mix, ind)):
                     if dst is not None:
                         dst.copy_(src, non_blocking=True)
-                cg["graph"].replay()
+                cg["graph"].replay()                     # forward + backward + the bucketed gradient all-reduce
                 cg["replays"] += 1
-                self._exchange_and_update()
+                self.optimizer.step(cg["scale"])
                 return cg["cost"].clone()
         self.store.grad_flat.zero_()
         cost = self.loss(*self.prepare(x_mix, x_non_mix), ind)
-        cost.backward()
-        self._exchange_and_update()
+        scale = self._backward(cost)
+        self.optimizer.step(scale)
         return cost.detach()
 
     @torch.no_grad()

@@ -51,6 +51,18 @@ def _worker(rank, world_size, port, out):
     flat, cost = _flat_grads(_params(), shard)
     scale = dp.allreduce_sum_(flat)
     worst = dp.max_over_ranks(float(rank))
+    # the same exchange through the per-layer buckets (dp.GradBuckets): two buckets complete "during the backward pass",
+    # the third never reports (a layer the loss did not reach) and is flushed by finish()
+    flat_b, _ = _flat_grads(_params(), shard)
+    n = flat_b.numel()
+    cuts = [(0, n // 3, 2), (n // 3, 2 * n // 3, 1), (2 * n // 3, n, 4)]
+    gb = dp.GradBuckets(flat_b, cuts)
+    gb.ready(1)
+    gb.ready(0); gb.ready(0)
+    gb.ready(2)                                                    # 1 of 4: stays pending
+    assert gb.launched == [True, True, False]
+    assert gb.finish() == scale and all(gb.launched)
+    assert torch.equal(flat_b, flat)
     clip = 0.5 * float(flat.norm()) * scale                        # a clip that bites: half the mean-gradient norm
     clipped = flat * scale * dp.clip_factor(float(flat.norm()), clip, scale)
     out[rank] = ((flat * scale).numpy(), cost, worst, clipped.numpy(), clip)
