@@ -450,6 +450,34 @@ def istft_masked(spec, masks, S, frame, hop):
     return _ISTFTMaskedFn.apply(spec, masks, S, frame, hop)
 
 
+class _AdaptTermsFn(torch.autograd.Function):
+    """The reduction / elementwise terms of the Adapt pre-training graph over the front output, one fused kernel each
+    way (amss_adapt_terms_fwd / _bwd): y -> (separator output, p_hat, [sparse_constraint, overlapping, nonneg])."""
+
+    @staticmethod
+    def forward(ctx, y, B, S, rho, separation, want_sep):
+        y = y.contiguous()
+        sep, p_hat, terms = ops.adapt_terms_fwd(y, B, S, rho, separation, want_sep)
+        ctx.save_for_backward(y, p_hat)
+        ctx.cfg = (B, S, rho, separation)
+        ctx.mark_non_differentiable(p_hat)
+        if sep is None:
+            sep = y.new_zeros(0)
+        return sep, p_hat, terms
+
+    @staticmethod
+    def backward(ctx, dsep, _dp, dterms):
+        y, p_hat = ctx.saved_tensors
+        B, S, rho, separation = ctx.cfg
+        dsep = dsep.contiguous() if dsep is not None and dsep.numel() else None
+        dterms = dterms.contiguous() if dterms is not None else torch.zeros(3, dtype=y.dtype, device=y.device)
+        return ops.adapt_terms_bwd(y, p_hat, dsep, dterms, B, S, rho, separation), None, None, None, None, None
+
+
+def adapt_terms(y, B, S, rho, separation, want_sep=True):
+    return _AdaptTermsFn.apply(y, B, S, rho, separation, want_sep)
+
+
 class _PairDotsFn(torch.autograd.Function):
     """G[b, b'] = <t[b], a[b']> over L (library GEMM t a^T); gradient to a only: da = dG^T t."""
 

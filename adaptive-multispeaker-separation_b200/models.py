@@ -217,20 +217,15 @@ class Adapt(Network):
     # adapt.py:307-338, 374-385 (pretraining branch)
     def cost(self, x_mix, x_non_mix):
         """Pre-training cost of the autoencoder: l2 / sdr (/ both) + beta*KL sparsity + lambda^2*reg +
-        overlap_coef*overlap + non_negativity^2*neg.  The heavy nodes (analysis, synthesis, waveform
-        statistics and their gradients) are library kernels; the remaining terms are reductions over the
-        [B(S+1),Tp,N] front output (0.26 MB per signal) composed from device tensor ops.
+        overlap_coef*overlap + non_negativity^2*neg.  Every node is a library kernel: analysis, the fused front-output
+        terms (p_hat / KL, overlap, separator, non-negativity: amss_adapt_terms_*), synthesis, waveform statistics, and
+        their gradients; what remains on the host side is scalar arithmetic on a handful of device scalars.
         Returns (cost, aux)."""
         B, S, Lw = x_non_mix.shape
         y, am = self.front(x_mix, x_non_mix)
         filt, filt2 = self.conv_filter("front"), self.conv_filter("back")
-        p_hat = y.abs().reshape(y.shape[0], -1).sum(0)                                   # adapt.py:129-131 (sum over batch)
-        rho = torch.as_tensor(self.p, dtype=y.dtype, device=y.device)
-        clip = lambda t: torch.clamp(t, 1e-10, 1.0)                                      # noqa: E731  utils/ops.py:46-54
-        kl = rho * torch.log(clip(rho) / clip(p_hat)) + (1 - rho) * torch.log(clip(1 - rho) / clip(1 - p_hat))
-        sparse = kl.sum()
-        overlapping = self.overlap(y, B)
-        sep = self.separator(y, B)
+        sep, p_hat, terms = L.adapt_terms(y, B, S, self.p, 0 if self.separation == "mask" else 1)
+        sparse, overlapping, nonneg = terms[0], terms[1], terms[2]
         back = self.back(sep, am, B, Lw)
         val, sdr_bs, st = self.sdr_improvement(x_mix, x_non_mix, back)
         l2 = st[:, 3].reshape(B, S).sum(-1).mean(-1)                                    # adapt.py:323-325
@@ -244,8 +239,7 @@ class Adapt(Network):
         if self.overlap_coef != 0.0:
             cost = cost + self.overlap_coef * overlapping
         if self.non_negativity:                                                          # applied twice (:316, :384)
-            neg = torch.where(y < 0, y, torch.zeros_like(y)) ** 2
-            cost = cost + self.non_negativity * (self.non_negativity * neg.reshape(neg.shape[0], -1).sum(1).mean())
+            cost = cost + self.non_negativity * (self.non_negativity * nonneg)
         return cost, {"y": y, "argmax": am, "back": back, "l2": l2, "sdr": sdr, "sdr_improvement": val,
                       "sparse_constraint": sparse, "overlapping": overlapping, "p_hat": p_hat}
 
@@ -277,17 +271,13 @@ class Adapt(Network):
         cost = l2 if self.loss == "l2" else (sdr if self.loss == "sdr" else 1e-3 * l2 + sdr)
         filt, filt2 = self.conv_filter("front"), self.conv_filter("back")
         if front_y is not None:
+            _, _, terms = L.adapt_terms(front_y, B, S, self.p, 1, want_sep=False)
             if self.beta != 0.0:
-                p_hat = front_y.abs().reshape(front_y.shape[0], -1).sum(0)
-                rho = torch.as_tensor(self.p, dtype=front_y.dtype, device=front_y.device)
-                clip = lambda t: torch.clamp(t, 1e-10, 1.0)                                # noqa: E731
-                kl = rho * torch.log(clip(rho) / clip(p_hat)) + (1 - rho) * torch.log(clip(1 - rho) / clip(1 - p_hat))
-                cost = cost + self.beta * kl.sum()
+                cost = cost + self.beta * terms[0]
             if self.overlap_coef != 0.0:
-                cost = cost + self.overlap_coef * self.overlap(front_y, B)
+                cost = cost + self.overlap_coef * terms[1]
             if self.non_negativity:
-                neg = torch.where(front_y < 0, front_y, torch.zeros_like(front_y)) ** 2
-                cost = cost + self.non_negativity * (self.non_negativity * neg.reshape(neg.shape[0], -1).sum(1).mean())
+                cost = cost + self.non_negativity * (self.non_negativity * terms[2])
         if self.l != 0.0:
             cost = cost + self.l * (self.l * (0.5 * (filt2 ** 2).sum() + 0.5 * (filt ** 2).sum()))
         return cost, {"l2": l2, "sdr": sdr, "sdr_improvement": val}

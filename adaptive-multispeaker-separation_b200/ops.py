@@ -452,6 +452,28 @@ def prepare_inputs(x_non_mix, normalize=False):
     return x_mix, stats
 
 
+def adapt_terms_fwd(y, B, S, rho, separation, want_sep=True):
+    """y[B(S+1),Tp,N] -> (sep[B*S,Tp,N] or None, p_hat[Tp*N], terms[3] = sparse_constraint, overlapping, nonneg)."""
+    _chk(y)
+    TN = y.shape[1] * y.shape[2]
+    sep = torch.empty(B * S, y.shape[1], y.shape[2], dtype=_f32, device=y.device) if want_sep else None
+    p_hat = torch.empty(TN, dtype=_f32, device=y.device)
+    terms = torch.empty(3, dtype=_f32, device=y.device)
+    ws = _ws(_lib.query("amss_adapt_terms_workspace_bytes", TN), y.device)
+    _lib.call("amss_adapt_terms_fwd", _p(y), B, S, TN, float(rho), int(separation), _p(sep), _p(p_hat), _p(terms), _p(ws),
+              ws.numel(), _stream())
+    return sep, p_hat, terms
+
+
+def adapt_terms_bwd(y, p_hat, dsep, dterms, B, S, rho, separation):
+    _chk(y, p_hat, dsep, dterms)
+    TN = y.shape[1] * y.shape[2]
+    dy = torch.empty_like(y)
+    _lib.call("amss_adapt_terms_bwd", _p(y), _p(p_hat), _p(dsep), _p(dterms), B, S, TN, float(rho), int(separation), _p(dy),
+              _stream())
+    return dy
+
+
 PRE_FUNC = {"None": 0, None: 0, "sqrt": 1, "log": 2}
 NORMALIZE = {"None": 0, None: 0, "01": 1, "meanstd": 2}
 FUNCTION_MASK = {"None": 0, None: 0, "linear": 1, "sqrt": 2, "square": 3}

@@ -339,6 +339,19 @@ int amss_rmsprop_step(float* p, const float* g, float* ms, float* mom, int64_t n
 int amss_wave_stats(const float* target, const float* approx, int R, int64_t L,
                     float* stats, void* stream);
 
+/* The remaining terms of the pre-training graph over the front output y[B(S+1),TN] (TN = Tp*N; mixture rows
+ * first), one fused pass (models/adapt.py:127-132 p_hat + KL sparsity, :141-160 overlap measure, :162-196 the
+ * pre-training separator -- separation 0 'mask', 1 'perfect' --, :315-316 non-negativity):
+ *   sep[B*S,TN] (may be NULL), p_hat[TN], terms[3] = {sparse_constraint, overlapping, mean_rows sum neg^2}.
+ * bwd: dy[B(S+1),TN] from dsep (may be NULL) and dterms[3].                                        */
+size_t amss_adapt_terms_workspace_bytes(int64_t TN);
+int amss_adapt_terms_fwd(const float* y, int B, int S, int64_t TN, float rho, int separation,
+                         float* sep, float* p_hat, float* terms, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int amss_adapt_terms_bwd(const float* y, const float* p_hat, const float* dsep, const float* dterms,
+                         int B, int S, int64_t TN, float rho, int separation, float* dy,
+                         void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -504,3 +504,30 @@ def test_prepare_inputs_mix_and_normalize(ops):
         assert rel(d, want) < 1e-5
         assert rel(stats[:, 0], mean.reshape(-1)) < 1e-4 and rel(stats[:, 1], var.reshape(-1)) < 1e-4
         assert rel(x_mix, want.sum(1)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ fused Adapt front-output terms
+@pytest.mark.parametrize("S,separation", [(2, "mask"), (2, "perfect"), (3, "perfect")])
+def test_adapt_terms_fwd_bwd_match_oracle(ops, S, separation):
+    """amss_adapt_terms_fwd / _bwd (models/adapt.py:127-132, 141-160, 162-196, 315-316): separator output, p_hat, the three
+    scalar terms and d(weighted sum)/dy against torch autograd of the oracle's restatement."""
+    g = torch.Generator().manual_seed(60 + S)
+    B, Tp, N = 3, 9, 16
+    y = (torch.randn(B * (S + 1), Tp, N, generator=g, dtype=torch.float64) * 0.02).requires_grad_(True)
+    rho = 0.01
+    p_hat = y.abs().reshape(y.shape[0], -1).sum(0)
+    sparse = T.kl_div(rho, p_hat).sum()
+    overlap = M.adapt_overlap(y, B, S)
+    sep = M.adapt_separator_pretraining(y, B, S, separation)
+    neg = (torch.where(y < 0, y, torch.zeros_like(y)) ** 2).reshape(y.shape[0], -1).sum(1).mean()
+    gsep = torch.randn(sep.shape, generator=g, dtype=torch.float64)
+    w = torch.tensor([0.7, -1.3, 2.1], dtype=torch.float64)
+    total = (sep * gsep).sum() + w[0] * sparse + w[1] * overlap + w[2] * neg
+    (dy_ref,) = torch.autograd.grad(total, y)
+    yd = dev(y.detach().float())
+    sep_d, ph_d, terms = ops.adapt_terms_fwd(yd, B, S, rho, 0 if separation == "mask" else 1)
+    assert rel(sep_d, sep) < 1e-5 and rel(ph_d, p_hat) < 1e-5
+    for got, want in zip(terms.cpu().tolist(), (sparse, overlap, neg)):
+        assert abs(got - float(want)) < 1e-4 * max(abs(float(want)), 1e-6), (got, float(want))
+    dy = ops.adapt_terms_bwd(yd, ph_d, dev(gsep.float()), dev(w.float()), B, S, rho, 0 if separation == "mask" else 1)
+    assert rel(dy, dy_ref) < 1e-4
