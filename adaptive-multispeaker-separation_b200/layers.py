@@ -478,6 +478,37 @@ def adapt_terms(y, B, S, rho, separation, want_sep=True):
     return _AdaptTermsFn.apply(y, B, S, rho, separation, want_sep)
 
 
+class _EnhanceCostFn(torch.autograd.Function):
+    """enhance_cost (models/network.py:662-693) of the enhance Conv1D output, fused with the softmax / tanh over the
+    sources and the multiplication with X_input (:640-656): one kernel builds the [B,S,S] distance table, the best of
+    the S! permutations is picked from it (S*S scalars per mixture), one kernel writes d cost / d logits."""
+
+    @staticmethod
+    def forward(ctx, logits, X_input, X_non_mix, nonlinearity):
+        import itertools
+        logits, X_input, X_non_mix = logits.contiguous(), X_input.contiguous(), X_non_mix.contiguous()
+        B, S, TF = logits.shape
+        table, _ = ops.enhance_cost_table(logits, X_input, X_non_mix, nonlinearity)
+        perms = list(itertools.permutations(range(S)))
+        pt = torch.tensor(perms, device=logits.device)                               # [P,S]
+        costs = table[:, torch.arange(S, device=logits.device).unsqueeze(0), pt].sum(-1)     # [B,P]
+        best = costs.argmin(1)
+        ctx.save_for_backward(logits, X_input, X_non_mix, pt[best].to(torch.int32).contiguous())
+        ctx.nonlinearity = nonlinearity
+        return costs.gather(1, best.unsqueeze(1)).mean()
+
+    @staticmethod
+    def backward(ctx, dcost):
+        logits, X_input, X_non_mix, perm = ctx.saved_tensors
+        B = logits.shape[0]
+        dcost_b = (dcost / B).reshape(1).expand(B).contiguous()
+        return ops.enhance_cost_bwd(logits, X_input, X_non_mix, perm, dcost_b, ctx.nonlinearity), None, None, None
+
+
+def enhance_cost_fused(logits, X_input, X_non_mix, nonlinearity="softmax"):
+    return _EnhanceCostFn.apply(logits, X_input, X_non_mix, nonlinearity)
+
+
 class _PairDotsFn(torch.autograd.Function):
     """G[b, b'] = <t[b], a[b']> over L (library GEMM t a^T); gradient to a only: da = dG^T t."""
 

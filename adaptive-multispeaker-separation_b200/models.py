@@ -422,9 +422,8 @@ class Separator(Network):
         self.enhance_layers.append(L.Conv1D([1, in_dim, self.F], store=st, scope="enhance", precision=prec))
         return self
 
-    # network.py:610-660
-    def enhance(self, separated, X_input):
-        """separated [B*S,T,F] (k-means masks applied), X_input [B,T,F] -> (enhanced [B,S,TF], cost_in [B,TF,S])."""
+    # network.py:610-639: [separated || X_input] -> enhance BLSTM stack -> Conv1D: the logits [B,S,TF]
+    def enhance_logits(self, separated, X_input):
         B, Tt, Fb = X_input.shape
         S = self.S
         sep4 = separated.reshape(B, S, Tt, Fb)
@@ -434,7 +433,19 @@ class Separator(Network):
             var = z.var((1, 2), unbiased=False, keepdim=True)
             z = (z - mean) / torch.sqrt(var)
         yv = L.f_props(self.enhance_layers, z.contiguous())                       # [B*S,T,F]
-        yv = yv.reshape(B, S, Tt * Fb).transpose(1, 2)                           # [B,TF,S]
+        return yv.reshape(B, S, Tt * Fb)
+
+    # network.py:640-693 fused: nonlinearity over the sources, * X_input, PIT-L2 against the sources' magnitudes
+    def enhance_cost_fused(self, logits, X_input, X_non_mix):
+        B, S, TF = logits.shape
+        return L.enhance_cost_fused(logits, X_input.reshape(B, TF), X_non_mix.reshape(B, TF, S), self.args["nonlinearity"])
+
+    # network.py:610-660
+    def enhance(self, separated, X_input):
+        """separated [B*S,T,F] (k-means masks applied), X_input [B,T,F] -> (enhanced [B,S,TF], cost_in [B,TF,S])."""
+        B, Tt, Fb = X_input.shape
+        S = self.S
+        yv = self.enhance_logits(separated, X_input).transpose(1, 2)             # [B,TF,S]
         nl = self.args["nonlinearity"]
         if nl == "softmax":
             yv = torch.softmax(yv, -1)

@@ -474,6 +474,30 @@ def adapt_terms_bwd(y, p_hat, dsep, dterms, B, S, rho, separation):
     return dy
 
 
+NONLINEARITY = {"softmax": 0, "tanh": 1, "None": 2, None: 2}
+
+
+def enhance_cost_table(logits, X_input, X_non_mix, nonlinearity="softmax", want_masks=False):
+    """logits[B,S,TF], X_input[B,TF], X_non_mix[B,TF,S] -> (table[B,S,S], masks[B,TF,S] or None)."""
+    _chk(logits, X_input, X_non_mix)
+    B, S, TF = logits.shape
+    table = torch.empty(B, S, S, dtype=_f32, device=logits.device)
+    masks = torch.empty(B, TF, S, dtype=_f32, device=logits.device) if want_masks else None
+    ws = _ws(_lib.query("amss_enhance_cost_workspace_bytes", B, TF, S), logits.device)
+    _lib.call("amss_enhance_cost_table", _p(logits), _p(X_input), _p(X_non_mix), B, S, TF, NONLINEARITY[nonlinearity],
+              _p(masks), _p(table), _p(ws), ws.numel(), _stream())
+    return table, masks
+
+
+def enhance_cost_bwd(logits, X_input, X_non_mix, perm, dcost_b, nonlinearity="softmax"):
+    _chk(logits, X_input, X_non_mix, perm, dcost_b)
+    B, S, TF = logits.shape
+    dlogits = torch.empty_like(logits)
+    _lib.call("amss_enhance_cost_bwd", _p(logits), _p(X_input), _p(X_non_mix), _p(perm), _p(dcost_b), B, S, TF,
+              NONLINEARITY[nonlinearity], _p(dlogits), _stream())
+    return dlogits
+
+
 PRE_FUNC = {"None": 0, None: 0, "sqrt": 1, "log": 2}
 NORMALIZE = {"None": 0, None: 0, "01": 1, "meanstd": 2}
 FUNCTION_MASK = {"None": 0, None: 0, "linear": 1, "sqrt": 2, "square": 3}

@@ -538,8 +538,7 @@ class Front_Separator_Enhance_Trainer(Trainer):
             sep, _ = sn.separate(V, X_in, self.init_idx)
             Tp, N = y.shape[1], y.shape[2]
             X_non_mix = y[B:].reshape(B, sn.S, Tp, N).permute(0, 2, 3, 1).contiguous()          # [B,T,N,S] (network.py:372)
-        _, cost_in = sn.enhance(sep, X_in)
-        return sn.enhance_cost(cost_in, X_non_mix)
+        return sn.enhance_cost_fused(sn.enhance_logits(sep, X_in), X_in, X_non_mix)
 
 
 class Adapt_Pretrainer(Trainer):
@@ -588,8 +587,7 @@ class STFT_Separator_enhance_Trainer(Trainer):
         with torch.no_grad():                       # hard k-means labels are not differentiable (network.py:554-582)
             V = m.prediction(pre["X"])
             sep, _ = m.separate(V, pre["X_input"], self.init_idx)
-        _, cost_in = m.enhance(sep, pre["X_input"])
-        return m.enhance_cost(cost_in, pre["X_non_mix"])
+        return m.enhance_cost_fused(m.enhance_logits(sep, pre["X_input"]), pre["X_input"], pre["X_non_mix"])
 
 
 class STFT_Separator_FineTune_Trainer(Trainer):

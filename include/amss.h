@@ -352,6 +352,19 @@ int amss_adapt_terms_bwd(const float* y, const float* p_hat, const float* dsep, 
                          int B, int S, int64_t TN, float rho, int separation, float* dy,
                          void* stream);
 
+/* Tail of the enhance layer (models/network.py:640-693), fused: logits[B,S,TF] (the enhance Conv1D output) ->
+ * nonlinearity over the sources (0 softmax, 1 tanh, 2 none) -> masks[B,TF,S] (optional output) * X_input[B,TF] ->
+ * table[B,S,S], table[b][s][k] = sum_j (X_non_mix[b,j,s] - mask[b,j,k] X_input[b,j])^2: the pairwise distances the PIT
+ * enhance cost minimises over permutations (the caller picks the permutation from S*S scalars per mixture).
+ * bwd: perm[B,S] = estimate paired with source s, dcost_b[B] -> dlogits[B,S,TF].               */
+size_t amss_enhance_cost_workspace_bytes(int B, int64_t TF, int S);
+int amss_enhance_cost_table(const float* logits, const float* X_input, const float* X_non_mix, int B,
+                            int S, int64_t TF, int nonlinearity, float* masks, float* table,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int amss_enhance_cost_bwd(const float* logits, const float* X_input, const float* X_non_mix,
+                          const int32_t* perm, const float* dcost_b, int B, int S, int64_t TF,
+                          int nonlinearity, float* dlogits, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

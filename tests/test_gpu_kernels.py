@@ -531,3 +531,24 @@ def test_adapt_terms_fwd_bwd_match_oracle(ops, S, separation):
         assert abs(got - float(want)) < 1e-4 * max(abs(float(want)), 1e-6), (got, float(want))
     dy = ops.adapt_terms_bwd(yd, ph_d, dev(gsep.float()), dev(w.float()), B, S, rho, 0 if separation == "mask" else 1)
     assert rel(dy, dy_ref) < 1e-4
+
+
+@pytest.mark.parametrize("S,nl", [(2, "softmax"), (3, "softmax"), (2, "tanh"), (2, "None")])
+def test_enhance_cost_fused_matches_oracle(S, nl):
+    """amss_enhance_cost_table / _bwd (models/network.py:640-693): cost and d cost / d logits vs torch autograd of the oracle."""
+    import amss_b200  # noqa: F401
+    from amss_b200 import layers
+    g = torch.Generator().manual_seed(90 + S)
+    B, TF = 3, 777
+    logits = torch.randn(B, S, TF, generator=g, dtype=torch.float64).requires_grad_(True)
+    X = torch.rand(B, TF, generator=g, dtype=torch.float64) + 0.1
+    tgt = torch.rand(B, TF, S, generator=g, dtype=torch.float64)
+    yv = logits.transpose(1, 2)
+    yv = torch.softmax(yv, -1) if nl == "softmax" else (torch.tanh(yv) if nl == "tanh" else yv)
+    cost = M.enhance_cost(yv * X.unsqueeze(-1), tgt)
+    (gref,) = torch.autograd.grad(cost, logits)
+    ld = dev(logits.detach().float()).requires_grad_(True)
+    c = layers.enhance_cost_fused(ld, dev(X.float()), dev(tgt.float()), nl)
+    (gd,) = torch.autograd.grad(c, ld)
+    assert abs(float(c) - float(cost)) < 1e-4 * abs(float(cost))
+    assert rel(gd, gref) < 1e-4
