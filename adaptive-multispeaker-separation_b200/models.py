@@ -77,7 +77,11 @@ class Network:
                       "nb_tries", "nb_steps", "threshold", "optimizer", "men", "women", "recurrent_dropout",
                       "recurrent_dropout_enhance")
 
-    def save(self, folder):
+    def save(self, folder, tf_checkpoint=False, step=0):
+        """<folder>/params (JSON) + <folder>/model.npz; tf_checkpoint=True also writes <folder>/model-<step>.index /
+        .data-00000-of-00001 in TensorFlow's tensor-bundle format (tf_bundle.py) with Conv1D filters in the
+        reference's [1, in, out] shape (utils/ops.py:486-494) plus the `checkpoint` state file tf.train.latest_checkpoint
+        reads (models/network.py:254-262)."""
         import json
         import os
         os.makedirs(folder, exist_ok=True)
@@ -85,7 +89,14 @@ class Network:
         with open(os.path.join(folder, "params"), "w") as f:
             json.dump(args, f)
         self.finalize()
-        np.savez(os.path.join(folder, "model.npz"), **{k: v.numpy() for k, v in self.store.state_dict().items()})
+        sd = {k: v.numpy() for k, v in self.store.state_dict().items()}
+        np.savez(os.path.join(folder, "model.npz"), **sd)
+        if tf_checkpoint:
+            from . import tf_bundle
+            tfv = {k: (v[None] if k.endswith("/W") and v.ndim == 2 else v) for k, v in sd.items()}
+            tf_bundle.save_checkpoint(os.path.join(folder, f"model-{step}"), tfv)
+            with open(os.path.join(folder, "checkpoint"), "w") as f:
+                f.write(f'model_checkpoint_path: "model-{step}"\nall_model_checkpoint_paths: "model-{step}"\n')
         return folder
 
     @classmethod
@@ -103,11 +114,31 @@ class Network:
         return cls(**args)
 
     def restore_model(self, path, strict=False):
-        """models/network.py:254-262: load every stored variable this model also has (by name)."""
+        """models/network.py:254-262: load every stored variable this model also has (by name).  `path` is a model folder
+        holding model.npz, or a folder / prefix of a TensorFlow checkpoint written by the reference's Saver
+        (`checkpoint` state file -> latest `model-<step>`; read without TensorFlow by tf_bundle.py; Conv1D filters
+        [1,in,out] are reshaped by load_state_dict)."""
         import os
+        import re
         self.finalize()
-        with np.load(os.path.join(path, "model.npz")) as z:
-            self.store.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=strict)
+        npz = os.path.join(path, "model.npz")
+        if os.path.isdir(path) and os.path.exists(npz):
+            with np.load(npz) as z:
+                self.store.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files}, strict=strict)
+            return self
+        from . import tf_bundle
+        prefix = path
+        if os.path.isdir(path):                                  # tf.train.latest_checkpoint(path)
+            state = os.path.join(path, "checkpoint")
+            if not os.path.exists(state):
+                raise FileNotFoundError(f"{path}: neither model.npz nor a TensorFlow `checkpoint` state file")
+            m = re.search(r'model_checkpoint_path:\s*"([^"]+)"', open(state).read())
+            prefix = m.group(1) if os.path.isabs(m.group(1)) else os.path.join(path, m.group(1))
+        names = set(self.store.names())
+        tensors = tf_bundle.load_checkpoint(prefix, names=names)
+        # TF appends ":0" to tensor names but stores variables under their op names; Adam/AMSGrad slot variables
+        # (".../AMSGrad", ".../AMSGrad_1") and global_epoch are simply not part of this model's names
+        self.store.load_state_dict({k: torch.from_numpy(v) for k, v in tensors.items()}, strict=strict)
         return self
 
     # the reference's freeze_all_with(prefix) (models/network.py:276-289)

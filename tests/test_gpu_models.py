@@ -630,3 +630,26 @@ def test_front_separator_enhance_trainer_matches_oracle(amss):
         a, b = t.store[k].detach().double().cpu(), st.tr[k].detach().double()
         assert float((a - b).abs().max()) < REL * max(float(b.abs().max()), 1e-3), k
     assert torch.equal(front_before, t.store["front/bases/bases"].detach())
+
+
+def test_tf_checkpoint_bundle_roundtrip(amss, tmp_path):
+    """Network.save(tf_checkpoint=True) writes a TensorFlow tensor bundle under the reference's variable
+    names (Conv1D filter as [1,in,out]); restore_model reads it back without TensorFlow (folder with `checkpoint` state
+    file, or an explicit prefix)."""
+    import os
+    mo = amss["models"]
+    cfg = dict(nb_layers=2, layer_size=20, embedding_size=4, window_size=64, hop_size=32)
+    a = mo.L41Model(plugged=False, **cfg).finalize()
+    folder = a.save(str(tmp_path / "run"), tf_checkpoint=True, step=1234)
+    assert os.path.exists(os.path.join(folder, "model-1234.index")) and os.path.exists(os.path.join(folder, "checkpoint"))
+    os.remove(os.path.join(folder, "model.npz"))                 # force the TF path
+    from amss_b200 import tf_bundle
+    _, entries = tf_bundle.read_index(os.path.join(folder, "model-1234"))
+    assert entries["prediction/W"]["shape"] == (1, 20, 4 * 33)
+    assert "prediction/forward_BLSTM_1/rnn/basic_lstm_cell/kernel" in entries and "speaker_centroids" in entries
+    for target in (folder, os.path.join(folder, "model-1234")):
+        b = mo.L41Model(plugged=False, seed=7, **cfg).finalize()
+        assert not torch.equal(b.store["prediction/W"], a.store["prediction/W"])
+        b.restore_model(target, strict=True)
+        for k in a.store.names():
+            assert torch.equal(a.store[k].detach(), b.store[k].detach()), k
