@@ -374,6 +374,7 @@ int launch_fwd(const RecTcFwd& p, int NC, cudaStream_t st) {
     const size_t smem = fwd_smem(NC, NB);
     if (smem > 226 * 1024) { set_error("blstm_rec_fwd_tc: H=%d NB=%d needs %zu B of shared memory", p.H, NB, smem); return AMSS_ERR_UNSUPPORTED; }
     AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_fwd_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_fwd_tc_kernel<NB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (NC > 8) AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_fwd_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC * 2 * p.nsub);
@@ -673,6 +674,7 @@ int launch_bwd(const RecTcBwd& p, int NC, cudaStream_t st) {
     const size_t smem = bwd_smem(NC, NB);
     if (smem > 226 * 1024) { set_error("blstm_rec_bwd_tc: H=%d NB=%d needs %zu B of shared memory", p.H, NB, smem); return AMSS_ERR_UNSUPPORTED; }
     AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (NC > 8) AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC * 2 * p.nsub);
@@ -702,6 +704,7 @@ int max_clusters(K kernel, int NC, size_t smem) {
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (NC > 8) cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 2) { cudaGetLastError(); n = std::max(2, kNumSMs / NC / 2); }
     return n;
@@ -714,14 +717,15 @@ size_t bwd_smem(int NC, int NB) {
     return (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)3 * 7 * NB * 32 * 4;
 }
 
-// Sub-batch size: NB = 16 runs two CTAs per SM (twice the co-resident clusters if the GPCs take them), NB = 32 one.
-// A step of an NB = 32 cluster costs ~1.6x a step of an NB = 16 cluster (measured, profiles/r01_blstm_step_profile.txt),
-// so compare waves x step cost; ties go to the smaller sub-batch.
+// Sub-batch size.  Measured on B200 (tools/blstm_bench.py, T = 250, I = 600, H = 300; fwd + bwd layer times in ms):
+//   B = 32: 1.36 (NB 16) vs 2.00 (NB 32);  64: 1.43 vs 2.06;  128: 1.83 vs 2.21;  256: 3.27 vs 4.25
+// -- the 16-mixture clusters win at every batch size, also where they need more than one wave of co-resident clusters
+// (a step of an NB = 16 cluster is ~1.6x shorter and two of its CTAs share an SM), so NB = 16 is the default whenever
+// the kernel fits; AMSS_BLSTM_NB=32 forces the one-CTA-per-SM variant (A/B runs).
 int pick_nb(int B, int maxc16, int maxc32) {
+    (void)B; (void)maxc16; (void)maxc32;
     if (const char* e = getenv("AMSS_BLSTM_NB")) { const int v = atoi(e); if (v == 16 || v == 32) return v; }
-    const int c16 = 2 * ((B + 15) / 16), c32 = 2 * ((B + 31) / 32);
-    const float t16 = (float)((c16 + maxc16 - 1) / maxc16) * 1.0f, t32 = (float)((c32 + maxc32 - 1) / maxc32) * 1.6f;
-    return t16 <= t32 ? 16 : 32;
+    return 16;
 }
 
 struct MaxC { int c16 = 0, c32 = 0; };

@@ -388,6 +388,43 @@ class _AnalysisFn(torch.autograd.Function):
         return None, ops.filterbank_analysis_bwd(x, dy.contiguous(), am, ctx.W), None, None, None, None
 
 
+def strided_positions(Bt, L, W, N, hop, device):
+    """The strided front end (tf.nn.conv2d, strides [1,1,hop,1], SAME; models/adapt.py:121-122) computes
+    y[r,tp,n] = sum_k x[tp*hop + k - pl_s] filt[k,n] with TF's SAME split pl_s = max((ceil(L/hop)-1)*hop + W - L, 0) // 2,
+    i.e. the stride-1 response at the FIXED position pos = tp*hop - pl_s + (W-1)//2.  Written as a per-sample flat index
+    pos*N + n -- the convention of max_pool_with_argmax -- these positions let the sparse kernels of the max-pool path
+    (filter gradient through the arg-max, unpool + transposed-conv synthesis and their gradients) serve the strided
+    mode unchanged: -> (int64 [Bt,Tp,N], offset c = pos - tp*hop)."""
+    Tp = -(-L // hop)
+    pl_s = max((Tp - 1) * hop + W - L, 0) // 2
+    c = (W - 1) // 2 - pl_s
+    pos = torch.arange(Tp, device=device, dtype=torch.int64) * hop + c
+    am = pos.view(1, Tp, 1) * N + torch.arange(N, device=device, dtype=torch.int64).view(1, 1, N)
+    return am.expand(Bt, Tp, N).contiguous(), c
+
+
+class _AnalysisStridedFn(torch.autograd.Function):
+    """Strided front end with the filter gradient (sparse kernel at the fixed positions, see strided_positions)."""
+
+    @staticmethod
+    def forward(ctx, x, filt, hop):
+        y, _ = ops.filterbank_analysis(x, filt, hop, hop, ops.AMSS_POOL_STRIDE, AMSS_PREC_FP32)
+        am, _ = strided_positions(x.shape[0], x.shape[1], filt.shape[0], filt.shape[1], hop, x.device)
+        ctx.save_for_backward(x, am)
+        ctx.W = filt.shape[0]
+        ctx.mark_non_differentiable(am)
+        return y, am
+
+    @staticmethod
+    def backward(ctx, dy, _dam):
+        x, am = ctx.saved_tensors
+        return None, ops.filterbank_analysis_bwd(x, dy.contiguous(), am, ctx.W), None
+
+
+def analysis_strided(x, filt, hop):
+    return _AnalysisStridedFn.apply(x, filt, hop)
+
+
 class _SynthesisFn(torch.autograd.Function):
     """unpool + conv2d_transpose fused as a sparse overlap-add (reference models/adapt.py:205-252)."""
 

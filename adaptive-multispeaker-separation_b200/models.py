@@ -193,9 +193,13 @@ class Adapt(Network):
         filt = self.conv_filter("front")
         if self.with_max_pool:
             y, am = L.analysis(x, filt, self.max_pool_value, self.hop_size, self.precision, batch=(B, S))
+        elif not self.with_average_pool:
+            # the reference's DEFAULT front end: strided convolution (adapt.py:121-122).  `am` holds the fixed positions
+            # tp*hop + c in the arg-max convention, so back() and both filter gradients run on the sparse kernels
+            y, am = L.analysis_strided(x, filt, self.hop_size)
         else:
             if filt.requires_grad:
-                raise AmssError("avg-pool / strided front ends are inference-only here (no filter gradient kernel)")
+                raise AmssError("the average-pool front end is inference-only here (no filter gradient kernel)")
             y, am = ops.filterbank_analysis(x, filt.detach(), self.max_pool_value, self.hop_size, self.pool_mode,
                                             AMSS_PREC_FP32)
         return y, am
@@ -214,11 +218,16 @@ class Adapt(Network):
 
     # adapt.py:205-252
     def back(self, sep_out, argmax, B, Lw):
-        if not self.with_max_pool:
-            raise AmssError("back(): only the max-pool (unpool + transposed conv) synthesis is on the hot path")
         filt2 = self.conv_filter("back")
-        out = L.synthesis(sep_out.contiguous(), argmax[:B].contiguous(), filt2, B, self.S, Lw, self.max_pool_value,
-                          self.hop_size)
+        if self.with_max_pool:
+            out = L.synthesis(sep_out.contiguous(), argmax[:B].contiguous(), filt2, B, self.S, Lw, self.max_pool_value,
+                              self.hop_size)
+        elif not self.with_average_pool:
+            # conv2d_transpose with strides [1,1,hop,1] (adapt.py:236-243) = overlap-add of atoms at the fixed positions
+            _, c = L.strided_positions(1, Lw, self.window, self.N, self.hop_size, sep_out.device)
+            out = L.synthesis(sep_out.contiguous(), argmax[:B].contiguous(), filt2, B, self.S, Lw, c + 1, self.hop_size)
+        else:
+            raise AmssError("back(): the average-pool synthesis (UpSampling2D + dense transposed conv) is not on the hot path")
         return out.reshape(B, self.S, Lw)
 
     # network.py:196-221 (with_perm=False): SDR improvement metric and the 'sdr' loss ratio per (b,s)
@@ -431,6 +440,11 @@ class Separator(Network):
         """V [B,T,F,E], X_input [B,T,F] -> (separated [B*S,T,F], labels int32 [B,TF] | soft [B,TF,S])."""
         B, Tt, Fb, E = V.shape
         emb = V.detach().reshape(B, Tt * Fb, E).contiguous()
+        if rng is None:               # one stream per separator (fresh draws every call, as the reference's py_func), per rank
+            if not hasattr(self, "_kmeans_rng"):
+                import os
+                self._kmeans_rng = np.random.RandomState(self.args["seed"] + int(os.environ.get("RANK", "0")))
+            rng = self._kmeans_rng
         km = KMeans(nb_clusters=self.S, nb_tries=self.nb_tries, nb_iterations=self.nb_steps, beta=self.beta,
                     latent_space_tensor=X_input.abs().reshape(B, Tt * Fb) if self.with_silence else None,
                     threshold=self.threshold, assign_at_end=self.args["end_assign"], rng=rng)
@@ -567,7 +581,19 @@ class KMeans:
         self.input_tensor = input_tensor
 
     def random_init(self, rows, Lp):
-        return np.stack([self.rng.choice(Lp, size=self.nb_clusters, replace=False) for _ in range(rows)]).astype(np.int32)
+        """`nb_clusters` distinct rows of X per (mixture, try), uniformly at random -- the distribution of the reference's
+        py_func (np.random.choice(range(l), size=K, replace=False) per row, Kmeans_2.py:61-65), drawn for all rows at once:
+        np.random.choice without replacement permutes the whole population per call (O(L) each; 0.5 s of host time per
+        64-mixture batch at TF = 64000), so rows are drawn with replacement and the few rows that repeat an index are
+        redrawn."""
+        K = self.nb_clusters
+        idx = self.rng.randint(0, Lp, size=(rows, K))
+        while True:
+            srt = np.sort(idx, axis=1)
+            bad = (srt[:, 1:] == srt[:, :-1]).any(axis=1)
+            if not bad.any():
+                return idx.astype(np.int32)
+            idx[bad] = self.rng.randint(0, Lp, size=(int(bad.sum()), K))
 
     def fit(self, X, init_idx=None):
         """X [B,L,E] (CUDA) -> (centroids [B,K,E], labels int32 [B,L] or soft [B,L,K])."""

@@ -556,7 +556,10 @@ class Adapt_Pretrainer(Trainer):
         self.store = self.model.store
 
     def loss(self, x_mix, x_non_mix, ind):
-        cost, self.aux = self.model.cost(x_mix, x_non_mix)
+        cost, aux = self.model.cost(x_mix, x_non_mix)
+        # detached: holding the autograd graph of a finished step would keep its AccumulateGrad nodes (and their stream) alive,
+        # which breaks the capture of the next step into a CUDA graph
+        self.aux = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in aux.items()}
         return cost
 
 
