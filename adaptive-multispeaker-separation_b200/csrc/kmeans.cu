@@ -16,6 +16,12 @@
 #include <algorithm>
 
 namespace amss {
+
+// tensor-core pass (kmeans_tc.cu): hard assignments, E = 40, K in {2,3,4}, tries*K <= 32, no silence gate
+bool kmeans_tc_supported(int E, int K, int tries, bool soft, bool gated);
+int kmeans_pass_tc(const float* X, const float* cent, int Bg, int64_t L, int K, int tries, int chunks, int normalize, int mode,
+                   float* part, cudaStream_t st);
+
 namespace {
 
 constexpr int KM_TILE = 256;     // points per tile
@@ -436,6 +442,9 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int G = km_group(B, L, E);
+    // the update / inertia passes run on the tensor cores when the shape allows (kmeans_tc.cu); AMSS_KMEANS_SIMT=1 forces
+    // the fp32 SIMT kernels of this file (the parity path for every other shape)
+    const bool use_tc = kmeans_tc_supported(E, K, tries, is_soft, notsilent != nullptr);
     const size_t smem = ((size_t)KM_TILE * (E + 1) + (size_t)K * E) * 4;
     if (is_soft) AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else AMSS_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -448,14 +457,17 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
         AMSS_LAUNCH(kmeans_gather_init_kernel, 64, 256, 0, st, Xg, init_idx + (size_t)b0 * tries * K, Bg, L, E, K, tries,
                     normalize_input, centg);
         int rc;
+        const bool tcp = use_tc && (((uintptr_t)Xg & 15) == 0);
         for (int it = 0; it < iters; ++it) {
-            rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
-                         : launch_pass<KM_UPDATE, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
+            if (tcp) rc = kmeans_pass_tc(Xg, centg, Bg, L, K, tries, chunks, normalize_input, KM_UPDATE, w.part, st);
+            else rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
+                              : launch_pass<KM_UPDATE, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
             if (rc != AMSS_OK) return rc;
             AMSS_LAUNCH(kmeans_finalize_kernel, 64, 256, 0, st, w.part, Bg, chunks, tries, K, E, centg);
         }
-        rc = is_soft ? launch_pass<KM_INERTIA, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
-                     : launch_pass<KM_INERTIA, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
+        if (tcp) rc = kmeans_pass_tc(Xg, centg, Bg, L, K, tries, chunks, normalize_input, KM_INERTIA, w.part, st);
+        else rc = is_soft ? launch_pass<KM_INERTIA, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
+                          : launch_pass<KM_INERTIA, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
         if (rc != AMSS_OK) return rc;
         float* centroids_g = centroids + (size_t)b0 * K * E;
         AMSS_LAUNCH(kmeans_select_kernel, Bg, 128, 0, st, w.part, centg, Bg, chunks, tries, K, E,
