@@ -249,6 +249,155 @@ sparse_filter_grad_kernel(const float* __restrict__ vals, const int64_t* __restr
         }
     }
 }
+// ---- filter-stationary versions of the two sparse reductions (W <= 1024) -------------------------------------------------
+// A CTA owns SG_F consecutive filters and a slice of the (row, frame) pairs.  For one (row, frame) the arg-max positions of
+// all filters lie inside one pooling window, so the sample windows [pos - pl, pos - pl + W) of the CTA's filters overlap
+// almost completely: the union (<= pool + W - 1 samples) is staged in shared memory ONCE and every filter reads its W taps
+// from there at its own offset -- consecutive threads read consecutive words.  The per-atom global traffic of the
+// one-warp-per-atom kernels above (2 x 4 KB from L2 per atom, 8.4-9.7 ms per step at 32 mixtures) becomes one 5 KB span
+// per SG_F atoms.  Thread t owns taps k = t, t + 256, t + 512, t + 768.
+constexpr int SG_F = 8;
+constexpr int SG_SPAN = 3072;            // staged samples (a span longer than this takes the direct global path)
+
+struct SgAtoms {
+    int pos[SG_F];
+    float v[SG_F];
+};
+
+// stage (positions, values) of the CTA's filters for atom (r, tp) and the union span of `sig`; returns pmin
+__device__ __forceinline__ int sg_stage(const float* __restrict__ vals, const int64_t* __restrict__ argmax,
+                                        const float* __restrict__ sig, int r, int tp, int argdiv, int L, int W, int N, int Tp,
+                                        int n0, int* sp, float* sv, float* xs, int& len) {
+    const int tid = threadIdx.x, pl = (W - 1) / 2;
+    if (tid < SG_F) {
+        const int n = n0 + tid;
+        const bool ok = n < N;
+        sp[tid] = ok ? (int)(argmax[((size_t)(r / argdiv) * Tp + tp) * N + n] / N) : 0;
+        if (sv) sv[tid] = ok ? vals[((size_t)r * Tp + tp) * N + n] : 0.f;
+    }
+    __syncthreads();
+    int pmin = sp[0], pmax = sp[0];
+#pragma unroll
+    for (int f = 1; f < SG_F; ++f) { pmin = min(pmin, sp[f]); pmax = max(pmax, sp[f]); }
+    len = pmax - pmin + W;
+    if (len <= SG_SPAN) {
+        const int base = pmin - pl;
+        for (int i = tid; i < len; i += blockDim.x) {
+            const int s = base + i;
+            xs[i] = (s >= 0 && s < L) ? __ldg(sig + (size_t)r * L + s) : 0.f;
+        }
+    }
+    __syncthreads();
+    return pmin;
+}
+
+// dfilt partials: part[chunk][n][k] = sum over the chunk's (r,tp) of vals[r,tp,n] * sig[r, pos + k - pl]
+__global__ void __launch_bounds__(256)
+sparse_filter_grad_fs_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax,
+                             const float* __restrict__ sig, int R, int argdiv, int L, int W, int N, int Tp,
+                             float* __restrict__ part) {
+    __shared__ int sp[SG_F];
+    __shared__ float sv[SG_F];
+    __shared__ float xs[SG_SPAN];
+    const int n0 = blockIdx.x * SG_F, chunk = blockIdx.y, chunks = gridDim.y, tid = threadIdx.x, pl = (W - 1) / 2;
+    const int64_t natoms = (int64_t)R * Tp;
+    const int64_t a0 = natoms * chunk / chunks, a1 = natoms * (chunk + 1) / chunks;
+    float acc[SG_F][4];
+#pragma unroll
+    for (int f = 0; f < SG_F; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[f][j] = 0.f;
+    int r = (int)(a0 / Tp), tp = (int)(a0 - (int64_t)r * Tp);
+    for (int64_t a = a0; a < a1; ++a) {
+        int len;
+        const int pmin = sg_stage(vals, argmax, sig, r, tp, argdiv, L, W, N, Tp, n0, sp, sv, xs, len);
+#pragma unroll
+        for (int f = 0; f < SG_F; ++f) {
+            const float v = sv[f];
+            if (v != 0.f) {                                     // warp-uniform
+                const int off = sp[f] - pmin;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = tid + 256 * j;
+                    if (k < W) {
+                        float x;
+                        if (len <= SG_SPAN) x = xs[off + k];
+                        else { const int s = sp[f] + k - pl; x = (s >= 0 && s < L) ? sig[(size_t)r * L + s] : 0.f; }
+                        acc[f][j] = fmaf(v, x, acc[f][j]);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                        // sp / sv / xs are rewritten by the next atom
+        if (++tp == Tp) { tp = 0; ++r; }
+    }
+#pragma unroll
+    for (int f = 0; f < SG_F; ++f)
+        if (n0 + f < N)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = tid + 256 * j;
+                if (k < W) part[((size_t)chunk * N + n0 + f) * W + k] = acc[f][j];
+            }
+}
+
+// dvals[r,tp,n] = sum_k dout[r, pos + k - pl] * filt2[k,n]: the CTA's filter taps live in registers for the whole kernel
+__global__ void __launch_bounds__(256)
+synthesis_bwd_vals_fs_kernel(const float* __restrict__ dout, const int64_t* __restrict__ argmax,
+                             const float* __restrict__ filt2, int R, int S, int L, int W, int N, int Tp,
+                             float* __restrict__ dvals) {
+    __shared__ int sp[SG_F];
+    __shared__ float xs[SG_SPAN];
+    __shared__ float red[8][SG_F];
+    const int n0 = blockIdx.x * SG_F, chunk = blockIdx.y, chunks = gridDim.y, tid = threadIdx.x, pl = (W - 1) / 2;
+    const int lane = tid & 31, warp = tid >> 5;
+    float w[SG_F][4];
+#pragma unroll
+    for (int f = 0; f < SG_F; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = tid + 256 * j;
+            w[f][j] = (k < W && n0 + f < N) ? __ldg(filt2 + (size_t)k * N + n0 + f) : 0.f;
+        }
+    const int64_t natoms = (int64_t)R * Tp;
+    const int64_t a0 = natoms * chunk / chunks, a1 = natoms * (chunk + 1) / chunks;
+    int r = (int)(a0 / Tp), tp = (int)(a0 - (int64_t)r * Tp);
+    for (int64_t a = a0; a < a1; ++a) {
+        int len;
+        const int pmin = sg_stage(nullptr, argmax, dout, r, tp, S, L, W, N, Tp, n0, sp, nullptr, xs, len);
+        float part[SG_F];
+#pragma unroll
+        for (int f = 0; f < SG_F; ++f) {
+            const int off = sp[f] - pmin;
+            float pacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = tid + 256 * j;
+                if (k < W) {
+                    float x;
+                    if (len <= SG_SPAN) x = xs[off + k];
+                    else { const int s = sp[f] + k - pl; x = (s >= 0 && s < L) ? dout[(size_t)r * L + s] : 0.f; }
+                    pacc = fmaf(w[f][j], x, pacc);
+                }
+            }
+            part[f] = warp_sum(pacc);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int f = 0; f < SG_F; ++f) red[warp][f] = part[f];
+        }
+        __syncthreads();
+        if (tid < SG_F && n0 + tid < N) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += red[q][tid];
+            dvals[((size_t)r * Tp + tp) * N + n0 + tid] = t;
+        }
+        __syncthreads();
+        if (++tp == Tp) { tp = 0; ++r; }
+    }
+}
+
 // dfilt[k][n] (+)= sum_chunks part[chunk][n][k]
 __global__ void filter_grad_final_kernel(const float* __restrict__ part, int chunks, int W, int N, int accumulate,
                                          float* __restrict__ dfilt) {
@@ -271,7 +420,7 @@ __global__ void filter_grad_final_kernel(const float* __restrict__ part, int chu
     }
 }
 
-constexpr int FG_CHUNKS = 8;
+constexpr int FG_CHUNKS = 32;     // slices of the (row, frame) list per filter group: 32 x 32 CTAs for 256 filters
 
 }  // namespace
 }  // namespace amss
@@ -350,8 +499,13 @@ extern "C" int amss_filterbank_analysis_bwd(const float* x, const float* dy, con
     AMSS_REQUIRE(x && dy && argmax && dfilt && workspace, "filterbank_analysis_bwd: null pointer");
     if (workspace_bytes < amss_filterbank_grad_workspace_bytes(W, N)) { set_error("filterbank_analysis_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
     float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
-    dim3 grid(N, FG_CHUNKS);
-    AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
+    if (W <= 1024) {
+        dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
+        AMSS_LAUNCH(sparse_filter_grad_fs_kernel, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
+    } else {
+        dim3 grid(N, FG_CHUNKS);
+        AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
+    }
     dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);
     AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, FG_CHUNKS, W, N, accumulate, dfilt);
     return AMSS_OK;
@@ -385,13 +539,21 @@ extern "C" int amss_filterbank_synthesis_bwd(const float* dout, const float* val
     if (workspace_bytes < amss_filterbank_grad_workspace_bytes(W, N)) { set_error("filterbank_synthesis_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
     float* fT = (float*)workspace;
     float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
-    if (dvals) {
+    if (dvals && W <= 1024) {
+        dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
+        AMSS_LAUNCH(synthesis_bwd_vals_fs_kernel, grid, 256, 0, stream, dout, argmax, filt2, B * S, S, L, W, N, Tp, dvals);
+    } else if (dvals) {
         dim3 gt((W + 31) / 32, (N + 31) / 32), bt(32, 8);
         AMSS_LAUNCH(transpose_filter_kernel, gt, bt, 0, stream, filt2, W, N, fT);
         dim3 grid(Tp, B * S);
         AMSS_LAUNCH(synthesis_bwd_vals_kernel, grid, 256, 0, stream, dout, argmax, fT, S, L, W, N, Tp, dvals);
     }
-    if (dfilt2) {
+    if (dfilt2 && W <= 1024) {
+        dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
+        AMSS_LAUNCH(sparse_filter_grad_fs_kernel, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
+        dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);
+        AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, FG_CHUNKS, W, N, 0, dfilt2);
+    } else if (dfilt2) {
         dim3 grid(N, FG_CHUNKS);
         AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
         dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);

@@ -13,7 +13,9 @@
 // fp32 rows in shared memory -> the row owner normalises (tf.nn.l2_normalize, Kmeans_2.py:40-41), splits and writes 18
 // 16-byte units (3 splits x 48 features) in the canonical core-matrix layout: read K-major by phase 1 (LBO = 128,
 // SBO = 2304) and MN-major by phase 2 (LBO = 2304, SBO = 128).
-// Warp roles: 0-3 loaders, 4 MMA issuer (+TMEM), 5-8 epilogue.  HBM/L2-bound: 4E bytes per point and pass.
+// Warp roles: 0-7 loaders (a point's row is split between two threads: features [0,24) and [24,48), because one warp per
+// scheduler left the normalise / split chain latency-bound: ncu 14 % active warps, 5000 clk per tile), 8 MMA issuer
+// (+TMEM), 9-12 epilogue.  HBM/L2-bound by design: 4E bytes per point and pass.
 // Restrictions (anything else takes the SIMT kernels of kmeans.cu): hard assignments, E == 40, tries*K <= 32, no silence
 // gate.
 #include "common.cuh"
@@ -26,7 +28,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int KT_THREADS = 288;
+constexpr int KT_THREADS = 416;
+constexpr int KT_LOADERS = 256;
 constexpr int KT_E = 40;
 constexpr int KT_PITCH = 44;                     // fp32 staging pitch: LDS.128 of a row per thread is conflict-free
 constexpr int KT_NCH = 18;                       // 16-byte units per point: 3 splits x 6 chunks of 8 features (48 >= E + 1)
@@ -67,6 +70,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     __shared__ uint32_t tmem_base_s;
     __shared__ float cc_s[KT_N1];
     __shared__ float xx_s[2][128];
+    __shared__ float ss_s[2][128];                 // per-half partial sums of squares of the raw row
+    __shared__ float xn_s[2][128];                 // ... and of the normalised row
     __shared__ float fin_s[4][32][2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
@@ -79,14 +84,14 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
                    oh_full = x3_full + 64, oh_empty = x3_full + 80, done = x3_full + 96;
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(x3_full + 8 * i, 128); mbar_init(x3_empty + 8 * i, 1);
+            mbar_init(x3_full + 8 * i, KT_LOADERS); mbar_init(x3_empty + 8 * i, 1);
             mbar_init(d1_full + 8 * i, 1);   mbar_init(d1_empty + 8 * i, 128);
             mbar_init(oh_full + 8 * i, 128); mbar_init(oh_empty + 8 * i, 1);
         }
         mbar_init(done, 1);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), 256);
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 256);
     // centroid operand (K-major B, N = 32 columns n = t*K + k; unit (n, c) at (c*4 + n/8)*128 + (n%8)*16) + |c|^2
     for (int u = tid; u < KT_N1 * KT_NCH; u += KT_THREADS) {
         const int n = u % KT_N1, c = u / KT_N1, sp = c / 6, kc = c % 6;
@@ -121,16 +126,19 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     const int64_t t0 = p.ntiles * chunk / p.chunks, t1 = p.ntiles * (chunk + 1) / p.chunks;
     const uint32_t ntile = (uint32_t)(t1 - t0);
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ================= loaders: tile -> fp32 rows -> normalise -> 3 bf16 splits in the operand layout =================
-        float4 tilev[10];
+        // thread = (row r, half h): h = 0 owns features [0,24) = chunks 0-2, h = 1 features [24,48) = chunks 3-5 (16 real
+        // features + the ones column at feature 40)
+        const int r = tid & 127, h = tid >> 7;
+        float4 tilev[5];
         auto fetch = [&](int64_t tile) {
             const int64_t p0 = tile * 128;
             const int np = (int)min((int64_t)128, p.L - p0);
             const float4* src = reinterpret_cast<const float4*>(p.X + ((size_t)b * p.L + p0) * KT_E);
 #pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const int u = tid + 128 * j;
+            for (int j = 0; j < 5; ++j) {
+                const int u = tid + KT_LOADERS * j;
                 tilev[j] = u < np * 10 ? __ldg(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -138,56 +146,56 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         for (uint32_t i = 0; i < ntile; ++i) {
             const uint32_t buf = i & 1, ph = (i >> 1) & 1;
             const int64_t p0 = (t0 + i) * 128;
-            const bool valid = p0 + tid < p.L;
-            kt_sync(1, 128);                                     // the rows of the previous tile have been consumed
+            const bool valid = p0 + r < p.L;
+            kt_sync(1, KT_LOADERS);                              // the rows of the previous tile have been consumed
 #pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const int u = tid + 128 * j, r = u / 10, c = u - r * 10;
-                *reinterpret_cast<float4*>(vs + r * KT_PITCH + c * 4) = tilev[j];
+            for (int j = 0; j < 5; ++j) {
+                const int u = tid + KT_LOADERS * j, rr = u / 10, c = u - rr * 10;
+                *reinterpret_cast<float4*>(vs + rr * KT_PITCH + c * 4) = tilev[j];
             }
             if (i + 1 < ntile) fetch(t0 + i + 1);
-            kt_sync(1, 128);
-            float x[KT_E];
-            const float* row = vs + tid * KT_PITCH;
+            kt_sync(1, KT_LOADERS);
+            float x[24];
+            const float* row = vs + r * KT_PITCH + 24 * h;
 #pragma unroll
-            for (int c = 0; c < 10; ++c) {
-                const float4 v = *reinterpret_cast<const float4*>(row + c * 4);
+            for (int c = 0; c < 6; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (24 * h + 4 * c < KT_E) v = *reinterpret_cast<const float4*>(row + c * 4);
                 x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
             }
-            if (p.normalize) {
-                float ss = 0.f;
+            float ss = 0.f;
 #pragma unroll
-                for (int e = 0; e < KT_E; ++e) ss = fmaf(x[e], x[e], ss);
-                const float inv = rsqrtf(fmaxf(ss, 1e-12f));
-#pragma unroll
-                for (int e = 0; e < KT_E; ++e) x[e] *= inv;
-            }
+            for (int e = 0; e < 24; ++e) ss = fmaf(x[e], x[e], ss);
+            ss_s[h][r] = ss;
+            kt_sync(1, KT_LOADERS);
+            float inv = 1.f;
+            if (p.normalize) inv = rsqrtf(fmaxf(ss_s[0][r] + ss_s[1][r], 1e-12f));
             float xx = 0.f;
 #pragma unroll
-            for (int e = 0; e < KT_E; ++e) xx = fmaf(x[e], x[e], xx);
+            for (int e = 0; e < 24; ++e) { x[e] *= inv; xx = fmaf(x[e], x[e], xx); }
             mbar_wait(x3_empty + 8 * buf, ph ^ 1);               // the MMAs of tile i-2 have finished with x3[buf]
             mbar_wait(d1_empty + 8 * buf, ph ^ 1);               // ... and its epilogue has read xx_s[buf]
-            xx_s[buf][tid] = xx;
-            uint8_t* dst = x3_s + buf * KT_X3 + (size_t)(tid >> 3) * KT_RG + (tid & 7) * 16;
+            if (h == 1) x[16] = valid ? 1.f : 0.f;               // the ones column (feature 40): exact in bf16
+            uint8_t* dst = x3_s + buf * KT_X3 + (size_t)(r >> 3) * KT_RG + (r & 7) * 16;
 #pragma unroll
-            for (int kc = 0; kc < 6; ++kc) {
-                float s[3][8];
+            for (int c = 0; c < 3; ++c) {
+                float sp3[3][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int e = kc * 8 + j;
-                    if (e < KT_E) split3(x[e < KT_E ? e : 0], s[0][j], s[1][j], s[2][j]);
-                    else { s[0][j] = (e == KT_E && valid) ? 1.f : 0.f; s[1][j] = 0.f; s[2][j] = 0.f; }    // the ones column
-                }
+                for (int j = 0; j < 8; ++j) split3(x[c * 8 + j], sp3[0][j], sp3[1][j], sp3[2][j]);
 #pragma unroll
                 for (int sp = 0; sp < 3; ++sp)
-                    *reinterpret_cast<uint4*>(dst + (sp * 6 + kc) * 128) =
-                        make_uint4(pack_bf16(s[sp][0], s[sp][1]), pack_bf16(s[sp][2], s[sp][3]), pack_bf16(s[sp][4], s[sp][5]),
-                                   pack_bf16(s[sp][6], s[sp][7]));
+                    *reinterpret_cast<uint4*>(dst + (sp * 6 + 3 * h + c) * 128) =
+                        make_uint4(pack_bf16(sp3[sp][0], sp3[sp][1]), pack_bf16(sp3[sp][2], sp3[sp][3]),
+                                   pack_bf16(sp3[sp][4], sp3[sp][5]), pack_bf16(sp3[sp][6], sp3[sp][7]));
             }
+            // |x|^2 of the normalised row: the two halves are added by the h = 1 thread after a second exchange
+            xn_s[h][r] = xx;
             fence_async_smem();
+            kt_sync(1, KT_LOADERS);
+            if (h == 1) xx_s[buf][r] = xn_s[0][r] + xn_s[1][r];
             mbar_arrive(x3_full + 8 * buf);
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================= MMA issuer =================
         const uint32_t idesc1 = idesc_bf16(128, KT_N1, 0, 0), idesc2 = idesc_bf16(128, KT_N2, 1, 1);
         const bool leader = elect_one();
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 256);
+    if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 constexpr size_t KT_SMEM = 2 * (size_t)KT_X3 + 2 * (size_t)KT_OH + KT_C3 + (size_t)128 * KT_PITCH * 4 + 2048;

@@ -450,6 +450,8 @@ def run_gpu(args):
     else:
         t = trainer.STFT_Separator_Inference(models.DPCL, precision=precision, **m)
     training = kind != "stft_infer"
+    if training and args.flat_allreduce:
+        t.args["overlap_allreduce"] = False
     use_graph = bool(args.cuda_graph and c["graph"] and precision == "bf16" and args.warmup >= 3 and training)
     if use_graph:
         t.enable_cuda_graph()
@@ -587,6 +589,10 @@ def run_gpu(args):
         "config": {"workload": c["workload"], "baseline_config": cid, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}" if training else f"replicas x{world} (no collective)",
                    "precision": precision, "cuda_graph": use_graph,
+                   "gradient_exchange": ("none (1 process)" if world == 1 or not training else
+                                         "one flat all-reduce after backward" if args.flat_allreduce else
+                                         "per-layer buckets all-reduced from the backward pass" +
+                                         (", captured in the step graph" if use_graph else "")),
                    "inputs": ("sources + speaker ids from the host; the mixture is built on the device (amss_prepare_inputs)"
                               if training and not args.ship_mix else "mixture (+ sources) from the host"),
                    "timed_region_s": ms / 1e3,
@@ -671,6 +677,9 @@ def main():
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="launch every kernel of the step from the host instead of replaying forward + backward from a CUDA "
                          "graph (Trainer.enable_cuda_graph)")
+    ap.add_argument("--flat-allreduce", action="store_true",
+                    help="A/B (multi-GPU): one all-reduce of the whole gradient buffer after backward, outside the step graph, "
+                         "instead of the per-layer buckets launched from the backward pass and captured into the graph")
     ap.add_argument("--stock-front", action="store_true",
                     help="A/B: run all B*(S+1) signals through the stock analysis kernel instead of deriving the mixture "
                          "rows from the source rows by linearity (sets AMSS_NO_LINEAR_MIX=1)")
