@@ -40,6 +40,8 @@ constexpr uint32_t KT_OH = 16 * KT_OHG;
 constexpr int KT_N1 = 32;                        // centroid columns (tries * K <= 32)
 constexpr int KT_N2 = 144;                       // 3 x 48 feature columns
 constexpr uint32_t KT_C3 = KT_NCH * (KT_N1 / 8) * 128;
+constexpr int KT_NBUF = 3;                      // operand / one-hot / distance-accumulator ring: the loaders (most of the
+                                                 // instructions) run two tiles ahead of the MMA -> epilogue -> MMA chain
 
 enum { KT_UPDATE = 0, KT_INERTIA = 1 };
 
@@ -53,37 +55,43 @@ struct KtParams {
 
 __device__ __forceinline__ void kt_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// x -> (hi, mid, lo) bf16 with hi + mid + lo == x exactly
+// x -> (hi, mid, lo), each representable in bf16, with hi + mid + lo == x exactly: hi and mid by truncation of the fp32
+// mantissa (one LOP each), the remainders by exact subtractions; lo has at most 8 significant bits left
 __device__ __forceinline__ void split3(float x, float& hi, float& mid, float& lo) {
-    hi = __bfloat162float(__float2bfloat16_rn(x));
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFF0000u);
     const float r1 = x - hi;
-    mid = __bfloat162float(__float2bfloat16_rn(r1));
-    lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
+    mid = __uint_as_float(__float_as_uint(r1) & 0xFFFF0000u);
+    lo = r1 - mid;
+}
+// two floats that are exactly representable in bf16 -> one packed word (byte permute, no conversion)
+__device__ __forceinline__ uint32_t pack_trunc(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
 }
 
 // KC = clusters per try (compile time: column m = t*KC + k is then a static register index in the epilogue)
 template <int MODE, int KC>
 __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // [0..1] x3_full, [2..3] x3_empty, [4..5] d1_full, [6..7] d1_empty, [8..9] oh_full, [10..11] oh_empty, [12] done
-    __shared__ __align__(8) uint64_t bars[13];
+    // x3_full[NBUF], x3_empty[NBUF], d1_full[NBUF], d1_empty[NBUF], oh_full[NBUF], oh_empty[NBUF], done
+    __shared__ __align__(8) uint64_t bars[6 * KT_NBUF + 1];
     __shared__ uint32_t tmem_base_s;
     __shared__ float cc_s[KT_N1];
-    __shared__ float xx_s[2][128];
+    __shared__ float xx_s[KT_NBUF][128];
     __shared__ float ss_s[2][128];                 // per-half partial sums of squares of the raw row
     __shared__ float xn_s[2][128];                 // ... and of the normalised row
     __shared__ float fin_s[4][32][2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
     const int TK = p.tries * KC;
-    uint8_t* x3_s = smem;                                        // [2][KT_X3]
-    uint8_t* oh_s = x3_s + 2 * KT_X3;                            // [2][KT_OH]  (the MMA also reads the 1.5 KB behind a tile:
-    uint8_t* c3_s = oh_s + 2 * KT_OH;                            //  rows >= 32 of the M = 128 product, never used)
+    uint8_t* x3_s = smem;                                        // [NBUF][KT_X3]
+    uint8_t* oh_s = x3_s + KT_NBUF * KT_X3;                      // [NBUF][KT_OH]  (the MMA also reads the 1.5 KB behind a tile:
+    uint8_t* c3_s = oh_s + KT_NBUF * KT_OH;                      //  rows >= 32 of the M = 128 product, never used)
     float* vs = reinterpret_cast<float*>(c3_s + KT_C3);          // [128][KT_PITCH] fp32 staging
-    const uint32_t x3_full = smem_u32(&bars[0]), x3_empty = x3_full + 16, d1_full = x3_full + 32, d1_empty = x3_full + 48,
-                   oh_full = x3_full + 64, oh_empty = x3_full + 80, done = x3_full + 96;
+    const uint32_t x3_full = smem_u32(&bars[0]), x3_empty = x3_full + 8 * KT_NBUF, d1_full = x3_full + 16 * KT_NBUF,
+                   d1_empty = x3_full + 24 * KT_NBUF, oh_full = x3_full + 32 * KT_NBUF, oh_empty = x3_full + 40 * KT_NBUF,
+                   done = x3_full + 48 * KT_NBUF;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < KT_NBUF; ++i) {
             mbar_init(x3_full + 8 * i, KT_LOADERS); mbar_init(x3_empty + 8 * i, 1);
             mbar_init(d1_full + 8 * i, 1);   mbar_init(d1_empty + 8 * i, 128);
             mbar_init(oh_full + 8 * i, 128); mbar_init(oh_empty + 8 * i, 1);
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
                 split3(x, s0, s1, s2);
                 v2[h] = sp == 0 ? s0 : (sp == 1 ? s1 : s2);
             }
-            w[j] = pack_bf16(v2[0], v2[1]);
+            w[j] = pack_trunc(v2[0], v2[1]);
         }
         *reinterpret_cast<uint4*>(c3_s + (size_t)(c * (KT_N1 / 8) + (n >> 3)) * 128 + (n & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
             for (int e = 0; e < KT_E; ++e) { const float x = p.cent[((size_t)b * TK + tid) * KT_E + e]; a = fmaf(x, x, a); }
         cc_s[tid] = a;
     }
-    for (uint32_t i = tid * 16; i < 2 * KT_OH; i += KT_THREADS * 16) *reinterpret_cast<uint4*>(oh_s + i) = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid * 16; i < KT_NBUF * KT_OH; i += KT_THREADS * 16) *reinterpret_cast<uint4*>(oh_s + i) = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         };
         if (ntile) fetch(t0);
         for (uint32_t i = 0; i < ntile; ++i) {
-            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
             const int64_t p0 = (t0 + i) * 128;
             const bool valid = p0 + r < p.L;
             kt_sync(1, KT_LOADERS);                              // the rows of the previous tile have been consumed
@@ -185,8 +193,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
 #pragma unroll
                 for (int sp = 0; sp < 3; ++sp)
                     *reinterpret_cast<uint4*>(dst + (sp * 6 + 3 * h + c) * 128) =
-                        make_uint4(pack_bf16(sp3[sp][0], sp3[sp][1]), pack_bf16(sp3[sp][2], sp3[sp][3]),
-                                   pack_bf16(sp3[sp][4], sp3[sp][5]), pack_bf16(sp3[sp][6], sp3[sp][7]));
+                        make_uint4(pack_trunc(sp3[sp][0], sp3[sp][1]), pack_trunc(sp3[sp][2], sp3[sp][3]),
+                                   pack_trunc(sp3[sp][4], sp3[sp][5]), pack_trunc(sp3[sp][6], sp3[sp][7]));
             }
             // |x|^2 of the normalised row: the two halves are added by the h = 1 thread after a second exchange
             xn_s[h][r] = xx;
@@ -201,19 +209,19 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         const bool leader = elect_one();
         const uint32_t cbase = smem_u32(c3_s);
         auto phase2 = [&](uint32_t j) {                           // sums of tile j: onehot^T [x splits | ones]
-            const uint32_t bj = j & 1, pj = (j >> 1) & 1;
+            const uint32_t bj = j % KT_NBUF, pj = (j / KT_NBUF) & 1;
             mbar_wait(oh_full + 8 * bj, pj);
             tc_fence_after();
             const uint32_t oa = smem_u32(oh_s + bj * KT_OH), xa = smem_u32(x3_s + bj * KT_X3);
             for (int kk = 0; kk < 8; ++kk) {
                 const uint64_t ad = smem_desc(oa + kk * 2 * KT_OHG, KT_OHG, 128);
                 const uint64_t bd = smem_desc(xa + kk * 2 * KT_RG, KT_RG, 128);
-                if (leader) mma_bf16(tmem + 64, ad, bd, idesc2, (j | (uint32_t)kk) != 0);
+                if (leader) mma_bf16(tmem + KT_NBUF * KT_N1, ad, bd, idesc2, (j | (uint32_t)kk) != 0);
             }
             if (leader) { mma_commit(x3_empty + 8 * bj); mma_commit(oh_empty + 8 * bj); }
         };
         for (uint32_t i = 0; i < ntile; ++i) {
-            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
             mbar_wait(x3_full + 8 * buf, ph);
             mbar_wait(d1_empty + 8 * buf, ph ^ 1);               // the epilogue of tile i-2 has drained D1[buf]
             tc_fence_after();
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         const int q = warp & 3, r = q * 32 + lane;
         float tot = 0.f, cnt = 0.f;                              // INERTIA: column m = lane of this warp's points
         for (uint32_t i = 0; i < ntile; ++i) {
-            const uint32_t buf = i & 1, ph = (i >> 1) & 1;
+            const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
             const int64_t p0 = (t0 + i) * 128;
             const bool valid = p0 + r < p.L;
             mbar_wait(x3_full + 8 * buf, ph);                     // acquire |x|^2 written by the loaders
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
 #pragma unroll
                 for (int c = 0; c < KT_N2 / 16; ++c) {
                     uint32_t v[16];
-                    if (ntile) { tmem_ld16(tmem + 64 + c * 16, v); tmem_ld_wait(); }
+                    if (ntile) { tmem_ld16(tmem + KT_NBUF * KT_N1 + c * 16, v); tmem_ld_wait(); }
                     else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = 0u;
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
-constexpr size_t KT_SMEM = 2 * (size_t)KT_X3 + 2 * (size_t)KT_OH + KT_C3 + (size_t)128 * KT_PITCH * 4 + 2048;
+constexpr size_t KT_SMEM = KT_NBUF * (size_t)KT_X3 + KT_NBUF * (size_t)KT_OH + KT_C3 + (size_t)128 * KT_PITCH * 4 + 2048;
 
 }  // namespace
 

@@ -2,11 +2,8 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 grep -E "passed|failed|FAILED|Error" gpurun_out/pytest_gpu.log | tail -15
-python tools/profile_kmeans.py 16 3 > gpurun_out/kmeans_time.txt 2>&1; AMSS_KMEANS_SIMT=1 python tools/profile_kmeans.py 16 3 >> gpurun_out/kmeans_time.txt 2>&1
-python tools/profile_kmeans.py 64 3 >> gpurun_out/kmeans_time.txt 2>&1; python tools/profile_kmeans.py 32 2 >> gpurun_out/kmeans_time.txt 2>&1; cat gpurun_out/kmeans_time.txt
-for c in 4 3 5; do
+python tools/profile_kmeans.py 16 3 > gpurun_out/kmeans_time.txt 2>&1; python tools/profile_kmeans.py 64 3 >> gpurun_out/kmeans_time.txt 2>&1; python tools/profile_kmeans.py 32 2 >> gpurun_out/kmeans_time.txt 2>&1; cat gpurun_out/kmeans_time.txt
+for c in 5 3; do
   timeout 600 python bench.py --config $c --steps 10 --warmup 3 > gpurun_out/bench_cfg$c.json 2> gpurun_out/bench_cfg$c.err
   echo "cfg $c rc=$?"; tail -3 gpurun_out/bench_cfg$c.err; cut -c1-300 gpurun_out/bench_cfg$c.json
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:kmeans_pass -s 4 -c 2 -o gpurun_out/prof_kmeans -f python tools/profile_kmeans.py 8 3 > gpurun_out/ncu_kmeans.log 2>&1
-echo "ncu kmeans rc=$?"; tail -2 gpurun_out/ncu_kmeans.log | cut -c1-200
