@@ -254,41 +254,55 @@ sparse_filter_grad_kernel(const float* __restrict__ vals, const int64_t* __restr
 // all filters lie inside one pooling window, so the sample windows [pos - pl, pos - pl + W) of the CTA's filters overlap
 // almost completely: the union (<= pool + W - 1 samples) is staged in shared memory ONCE and every filter reads its W taps
 // from there at its own offset -- consecutive threads read consecutive words.  The per-atom global traffic of the
-// one-warp-per-atom kernels above (2 x 4 KB from L2 per atom, 8.4-9.7 ms per step at 32 mixtures) becomes one 5 KB span
-// per SG_F atoms.  Thread t owns taps k = t, t + 256, t + 512, t + 768.
+// one-warp-per-atom kernels above (2 x 4 KB from L2 per atom) becomes one 5 KB span per SG_F atoms.  The (row, frame) list
+// is walked in blocks of SG_AB pairs: positions / values of a block are fetched up front, and the span of pair i+1 is in
+// flight (cp.async, zero-filled outside the signal) while pair i is accumulated: one __syncthreads per pair, no exposed
+// global latency.  Thread t owns taps k = t, t + 256, t + 512, t + 768.
 constexpr int SG_F = 8;
-constexpr int SG_SPAN = 3072;            // staged samples (a span longer than this takes the direct global path)
+constexpr int SG_SPAN = 2560;            // staged samples per pair (a longer span takes the direct global path)
+constexpr int SG_AB = 64;                // (row, frame) pairs per block
 
-struct SgAtoms {
-    int pos[SG_F];
-    float v[SG_F];
+struct SgBlock {
+    int pos[SG_AB][SG_F];
+    float val[SG_AB][SG_F];
+    int pmin[SG_AB], len[SG_AB];
 };
 
-// stage (positions, values) of the CTA's filters for atom (r, tp) and the union span of `sig`; returns pmin
-__device__ __forceinline__ int sg_stage(const float* __restrict__ vals, const int64_t* __restrict__ argmax,
-                                        const float* __restrict__ sig, int r, int tp, int argdiv, int L, int W, int N, int Tp,
-                                        int n0, int* sp, float* sv, float* xs, int& len) {
-    const int tid = threadIdx.x, pl = (W - 1) / 2;
-    if (tid < SG_F) {
-        const int n = n0 + tid;
+// positions (and values) of the CTA's filters for pairs [a, a + cnt): coalesced over the SG_F consecutive filters
+__device__ __forceinline__ void sg_load_block(SgBlock& blk, const float* __restrict__ vals, const int64_t* __restrict__ argmax,
+                                              int64_t a, int cnt, int argdiv, int W, int N, int Tp, int n0) {
+    for (int u = threadIdx.x; u < cnt * SG_F; u += blockDim.x) {
+        const int i = u / SG_F, f = u - i * SG_F, n = n0 + f;
+        const int64_t at = a + i;
+        const int r = (int)(at / Tp), tp = (int)(at - (int64_t)r * Tp);
         const bool ok = n < N;
-        sp[tid] = ok ? (int)(argmax[((size_t)(r / argdiv) * Tp + tp) * N + n] / N) : 0;
-        if (sv) sv[tid] = ok ? vals[((size_t)r * Tp + tp) * N + n] : 0.f;
+        blk.pos[i][f] = ok ? (int)(argmax[((size_t)(r / argdiv) * Tp + tp) * N + n] / N) : -1;
+        if (vals) blk.val[i][f] = ok ? vals[((size_t)r * Tp + tp) * N + n] : 0.f;
     }
     __syncthreads();
-    int pmin = sp[0], pmax = sp[0];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        int lo = 0x7fffffff, hi = -1;
 #pragma unroll
-    for (int f = 1; f < SG_F; ++f) { pmin = min(pmin, sp[f]); pmax = max(pmax, sp[f]); }
-    len = pmax - pmin + W;
+        for (int f = 0; f < SG_F; ++f) { const int q = blk.pos[i][f]; if (q >= 0) { lo = min(lo, q); hi = max(hi, q); } }
+        blk.pmin[i] = hi < 0 ? 0 : lo;
+        blk.len[i] = hi < 0 ? 0 : hi - lo + W;
+    }
+    __syncthreads();
+}
+
+// asynchronous copy of sig[r, pmin - pl .. + len) into xs (zero-filled outside [0, L)); one commit group per call
+__device__ __forceinline__ void sg_issue_span(float* xs, const float* __restrict__ sig, int r, int L, int pl, int pmin, int len) {
     if (len <= SG_SPAN) {
         const int base = pmin - pl;
-        for (int i = tid; i < len; i += blockDim.x) {
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(xs);
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
             const int s = base + i;
-            xs[i] = (s >= 0 && s < L) ? __ldg(sig + (size_t)r * L + s) : 0.f;
+            const bool ok = s >= 0 && s < L;
+            const float* src = sig + (size_t)r * L + (ok ? s : 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * i), "l"(src), "r"(ok ? 4u : 0u) : "memory");
         }
     }
-    __syncthreads();
-    return pmin;
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // dfilt partials: part[chunk][n][k] = sum over the chunk's (r,tp) of vals[r,tp,n] * sig[r, pos + k - pl]
@@ -296,9 +310,8 @@ __global__ void __launch_bounds__(256)
 sparse_filter_grad_fs_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax,
                              const float* __restrict__ sig, int R, int argdiv, int L, int W, int N, int Tp,
                              float* __restrict__ part) {
-    __shared__ int sp[SG_F];
-    __shared__ float sv[SG_F];
-    __shared__ float xs[SG_SPAN];
+    __shared__ SgBlock blk;
+    __shared__ float xs[2][SG_SPAN];
     const int n0 = blockIdx.x * SG_F, chunk = blockIdx.y, chunks = gridDim.y, tid = threadIdx.x, pl = (W - 1) / 2;
     const int64_t natoms = (int64_t)R * Tp;
     const int64_t a0 = natoms * chunk / chunks, a1 = natoms * (chunk + 1) / chunks;
@@ -307,29 +320,36 @@ sparse_filter_grad_fs_kernel(const float* __restrict__ vals, const int64_t* __re
     for (int f = 0; f < SG_F; ++f)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[f][j] = 0.f;
-    int r = (int)(a0 / Tp), tp = (int)(a0 - (int64_t)r * Tp);
-    for (int64_t a = a0; a < a1; ++a) {
-        int len;
-        const int pmin = sg_stage(vals, argmax, sig, r, tp, argdiv, L, W, N, Tp, n0, sp, sv, xs, len);
+    for (int64_t ab = a0; ab < a1; ab += SG_AB) {
+        const int cnt = (int)min((int64_t)SG_AB, a1 - ab);
+        __syncthreads();                                        // the previous block's entries are no longer read
+        sg_load_block(blk, vals, argmax, ab, cnt, argdiv, W, N, Tp, n0);
+        sg_issue_span(xs[0], sig, (int)(ab / Tp), L, pl, blk.pmin[0], blk.len[0]);
+        for (int i = 0; i < cnt; ++i) {
+            const int r = (int)((ab + i) / Tp);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                    // span i visible to all; span buffer (i+1)&1 free again
+            if (i + 1 < cnt) sg_issue_span(xs[(i + 1) & 1], sig, (int)((ab + i + 1) / Tp), L, pl, blk.pmin[i + 1], blk.len[i + 1]);
+            const float* xb = xs[i & 1];
+            const int pmin = blk.pmin[i], len = blk.len[i];
 #pragma unroll
-        for (int f = 0; f < SG_F; ++f) {
-            const float v = sv[f];
-            if (v != 0.f) {                                     // warp-uniform
-                const int off = sp[f] - pmin;
+            for (int f = 0; f < SG_F; ++f) {
+                const float v = blk.val[i][f];
+                if (v != 0.f) {                                 // warp-uniform
+                    const int off = blk.pos[i][f] - pmin;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = tid + 256 * j;
-                    if (k < W) {
-                        float x;
-                        if (len <= SG_SPAN) x = xs[off + k];
-                        else { const int s = sp[f] + k - pl; x = (s >= 0 && s < L) ? sig[(size_t)r * L + s] : 0.f; }
-                        acc[f][j] = fmaf(v, x, acc[f][j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = tid + 256 * j;
+                        if (k < W) {
+                            float x;
+                            if (len <= SG_SPAN) x = xb[off + k];
+                            else { const int s = blk.pos[i][f] + k - pl; x = (s >= 0 && s < L) ? sig[(size_t)r * L + s] : 0.f; }
+                            acc[f][j] = fmaf(v, x, acc[f][j]);
+                        }
                     }
                 }
             }
         }
-        __syncthreads();                                        // sp / sv / xs are rewritten by the next atom
-        if (++tp == Tp) { tp = 0; ++r; }
     }
 #pragma unroll
     for (int f = 0; f < SG_F; ++f)
@@ -346,9 +366,9 @@ __global__ void __launch_bounds__(256)
 synthesis_bwd_vals_fs_kernel(const float* __restrict__ dout, const int64_t* __restrict__ argmax,
                              const float* __restrict__ filt2, int R, int S, int L, int W, int N, int Tp,
                              float* __restrict__ dvals) {
-    __shared__ int sp[SG_F];
-    __shared__ float xs[SG_SPAN];
-    __shared__ float red[8][SG_F];
+    __shared__ SgBlock blk;
+    __shared__ float xs[2][SG_SPAN];
+    __shared__ float red[2][8][SG_F];
     const int n0 = blockIdx.x * SG_F, chunk = blockIdx.y, chunks = gridDim.y, tid = threadIdx.x, pl = (W - 1) / 2;
     const int lane = tid & 31, warp = tid >> 5;
     float w[SG_F][4];
@@ -361,40 +381,55 @@ synthesis_bwd_vals_fs_kernel(const float* __restrict__ dout, const int64_t* __re
         }
     const int64_t natoms = (int64_t)R * Tp;
     const int64_t a0 = natoms * chunk / chunks, a1 = natoms * (chunk + 1) / chunks;
-    int r = (int)(a0 / Tp), tp = (int)(a0 - (int64_t)r * Tp);
-    for (int64_t a = a0; a < a1; ++a) {
-        int len;
-        const int pmin = sg_stage(nullptr, argmax, dout, r, tp, S, L, W, N, Tp, n0, sp, nullptr, xs, len);
-        float part[SG_F];
-#pragma unroll
-        for (int f = 0; f < SG_F; ++f) {
-            const int off = sp[f] - pmin;
-            float pacc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = tid + 256 * j;
-                if (k < W) {
-                    float x;
-                    if (len <= SG_SPAN) x = xs[off + k];
-                    else { const int s = sp[f] + k - pl; x = (s >= 0 && s < L) ? dout[(size_t)r * L + s] : 0.f; }
-                    pacc = fmaf(w[f][j], x, pacc);
-                }
-            }
-            part[f] = warp_sum(pacc);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int f = 0; f < SG_F; ++f) red[warp][f] = part[f];
-        }
+    for (int64_t ab = a0; ab < a1; ab += SG_AB) {
+        const int cnt = (int)min((int64_t)SG_AB, a1 - ab);
         __syncthreads();
+        sg_load_block(blk, nullptr, argmax, ab, cnt, S, W, N, Tp, n0);
+        sg_issue_span(xs[0], dout, (int)(ab / Tp), L, pl, blk.pmin[0], blk.len[0]);
+        for (int i = 0; i < cnt; ++i) {
+            const int64_t at = ab + i;
+            const int r = (int)(at / Tp), tp = (int)(at - (int64_t)r * Tp);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                    // span i visible; red[(i-1)&1] complete
+            if (i > 0 && tid < SG_F && n0 + tid < N) {          // finish pair i-1: fixed-order sum of the 8 warp partials
+                const int64_t ap = at - 1;
+                const int rp = (int)(ap / Tp), tpp = (int)(ap - (int64_t)rp * Tp);
+                float t = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t += red[(i - 1) & 1][q][tid];
+                dvals[((size_t)rp * Tp + tpp) * N + n0 + tid] = t;
+            }
+            if (i + 1 < cnt) sg_issue_span(xs[(i + 1) & 1], dout, (int)((at + 1) / Tp), L, pl, blk.pmin[i + 1], blk.len[i + 1]);
+            const float* xb = xs[i & 1];
+            const int pmin = blk.pmin[i], len = blk.len[i];
+#pragma unroll
+            for (int f = 0; f < SG_F; ++f) {
+                const int off = blk.pos[i][f] - pmin;
+                float pacc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = tid + 256 * j;
+                    if (k < W && blk.pos[i][f] >= 0) {
+                        float x;
+                        if (len <= SG_SPAN) x = xb[off + k];
+                        else { const int s = blk.pos[i][f] + k - pl; x = (s >= 0 && s < L) ? dout[(size_t)r * L + s] : 0.f; }
+                        pacc = fmaf(w[f][j], x, pacc);
+                    }
+                }
+                pacc = warp_sum(pacc);
+                if (lane == 0) red[i & 1][warp][f] = pacc;
+            }
+            (void)tp;
+        }
+        __syncthreads();                                        // the last pair of the block
         if (tid < SG_F && n0 + tid < N) {
+            const int64_t ap = ab + cnt - 1;
+            const int rp = (int)(ap / Tp), tpp = (int)(ap - (int64_t)rp * Tp);
             float t = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) t += red[q][tid];
-            dvals[((size_t)r * Tp + tp) * N + n0 + tid] = t;
+            for (int q = 0; q < 8; ++q) t += red[(cnt - 1) & 1][q][tid];
+            dvals[((size_t)rp * Tp + tpp) * N + n0 + tid] = t;
         }
-        __syncthreads();
-        if (++tp == Tp) { tp = 0; ++r; }
     }
 }
 

@@ -9,6 +9,10 @@
 //   phase 2  sum[(t,k)][e] = sum_p onehot[p][(t,k)] x[p][e]  with the one-hot matrix (exact in bf16) as the MN-major A
 //            operand and the SAME operand tile of x splits as the MN-major B operand (K = points); a ones column in the
 //            tile's padding yields the counts.  The accumulator stays in TMEM for all tiles of the CTA.
+// Phase 1 reads its A operand (the x splits, K-major) from TENSOR MEMORY: the loader thread that owns a point's (half) row
+// also parks the packed splits in its TMEM lane (tcgen05.st); with both operands in shared memory every one of the 18
+// small-N MMAs of a tile paid ~100 clk of operand fetch (5000 clk per tile measured, unchanged by more loader warps or a
+// deeper ring), from TMEM they issue at ~36 clk.
 // The operand tile of 128 points is built once per tile: coalesced float4 fetch (software-pipelined in registers) ->
 // fp32 rows in shared memory -> the row owner normalises (tf.nn.l2_normalize, Kmeans_2.py:40-41), splits and writes 18
 // 16-byte units (3 splits x 48 features) in the canonical core-matrix layout: read K-major by phase 1 (LBO = 128,
@@ -40,6 +44,7 @@ constexpr uint32_t KT_OH = 16 * KT_OHG;
 constexpr int KT_N1 = 32;                        // centroid columns (tries * K <= 32)
 constexpr int KT_N2 = 144;                       // 3 x 48 feature columns
 constexpr uint32_t KT_C3 = KT_NCH * (KT_N1 / 8) * 128;
+constexpr uint32_t KT_ACOL = 256;                // TMEM: D1 ring [0,96), D2 [96,240), A ring [256, 256 + 72*NBUF)
 constexpr int KT_NBUF = 3;                      // operand / one-hot / distance-accumulator ring: the loaders (most of the
                                                  // instructions) run two tiles ahead of the MMA -> epilogue -> MMA chain
 
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         mbar_init(done, 1);
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 256);
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 512);
     // centroid operand (K-major B, N = 32 columns n = t*K + k; unit (n, c) at (c*4 + n/8)*128 + (n%8)*16) + |c|^2
     for (int u = tid; u < KT_N1 * KT_NCH; u += KT_THREADS) {
         const int n = u % KT_N1, c = u / KT_N1, sp = c / 6, kc = c % 6;
@@ -191,11 +196,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) split3(x[c * 8 + j], sp3[0][j], sp3[1][j], sp3[2][j]);
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp)
-                    *reinterpret_cast<uint4*>(dst + (sp * 6 + 3 * h + c) * 128) =
-                        make_uint4(pack_trunc(sp3[sp][0], sp3[sp][1]), pack_trunc(sp3[sp][2], sp3[sp][3]),
-                                   pack_trunc(sp3[sp][4], sp3[sp][5]), pack_trunc(sp3[sp][6], sp3[sp][7]));
+                for (int sp = 0; sp < 3; ++sp) {
+                    const uint32_t w0 = pack_trunc(sp3[sp][0], sp3[sp][1]), w1 = pack_trunc(sp3[sp][2], sp3[sp][3]),
+                                   w2 = pack_trunc(sp3[sp][4], sp3[sp][5]), w3 = pack_trunc(sp3[sp][6], sp3[sp][7]);
+                    *reinterpret_cast<uint4*>(dst + (sp * 6 + 3 * h + c) * 128) = make_uint4(w0, w1, w2, w3);   // phase-2 operand
+                    // phase-1 A operand: TMEM lane = point, 24 columns per split (two k per column), chunk = 4 columns
+                    tmem_st4(tmem + ((uint32_t)((warp & 3) * 32) << 16) + KT_ACOL + buf * 72 + sp * 24 + (3 * h + c) * 4, w0, w1, w2, w3);
+                }
             }
+            tmem_st_wait();
+            tc_fence_before();
             // |x|^2 of the normalised row: the two halves are added by the h = 1 thread after a second exchange
             xn_s[h][r] = xx;
             fence_async_smem();
@@ -225,7 +235,6 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
             mbar_wait(x3_full + 8 * buf, ph);
             mbar_wait(d1_empty + 8 * buf, ph ^ 1);               // the epilogue of tile i-2 has drained D1[buf]
             tc_fence_after();
-            const uint32_t xa = smem_u32(x3_s + buf * KT_X3);
             uint32_t acc = 0;
 #pragma unroll
             for (int term = 0; term < 6; ++term) {
@@ -233,9 +242,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
                 const int sj = term == 0 ? 0 : term == 1 ? 1 : term == 2 ? 0 : term == 3 ? 2 : term == 4 ? 1 : 0;
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) {
-                    const uint64_t ad = smem_desc(xa + (si * 6 + 2 * kk) * 128, 128, KT_RG);
                     const uint64_t bd = smem_desc(cbase + (sj * 6 + 2 * kk) * (KT_N1 / 8) * 128, (KT_N1 / 8) * 128, 128);
-                    if (leader) mma_bf16(tmem + buf * KT_N1, ad, bd, idesc1, acc);
+                    if (leader) mma_bf16_ts(tmem + buf * KT_N1, tmem + KT_ACOL + buf * 72 + si * 24 + kk * 8, bd, idesc1, acc);
                     acc = 1;
                 }
             }
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 256);
+    if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 constexpr size_t KT_SMEM = KT_NBUF * (size_t)KT_X3 + KT_NBUF * (size_t)KT_OH + KT_C3 + (size_t)128 * KT_PITCH * 4 + 2048;

@@ -166,6 +166,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* w) {
                  "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // bulk copy own shared memory -> a cluster peer's shared memory, completion on the PEER's mbarrier
 // (dst / bar are shared::cluster addresses obtained with mapa).
