@@ -20,6 +20,7 @@ int gemm_dispatch(const float* A, int lda, const float* B, int ldb, const float*
                   size_t workspace_bytes, cudaStream_t st);
 bool blstm_rec_tc_supported(int B, int T, int H);
 void blstm_tc_set_profile(long long* dev_buf);
+void blstm_tc_set_sched(long long* dev_buf);
 void blstm_tc_max_clusters(int H, int* out4);
 int convert_bf16(const float* src, int rows, int cols, int ld, uint16_t* dst, int ldd, cudaStream_t st);
 int gemm_bf16(const uint16_t* A, int lda, int a_mn, const uint16_t* B, int ldb, int b_mn, const float* bias, int M, int N,
@@ -457,6 +458,12 @@ extern "C" int amss_blstm_bwd(const float* x, const float* kernel_fw, const floa
 // written to dev_buf (>= 48 int64) by subsequent amss_blstm_fwd calls; NULL switches it off.
 extern "C" int amss_debug_blstm_profile(long long* dev_buf) {
     blstm_tc_set_profile(dev_buf);
+    return AMSS_OK;
+}
+// Diagnostics: schedule trace of the tcgen05 recurrence kernels: per CTA {SM id, globaltimer ns at start, at end, at the end of the prologue},
+// forward launches at [0, 4*4096), backward at [4*4096, 8*4096) of dev_buf (>= 8*4096 int64); NULL switches it off.
+extern "C" int amss_debug_blstm_sched(long long* dev_buf) {
+    blstm_tc_set_sched(dev_buf);
     return AMSS_OK;
 }
 // Diagnostics: co-resident clusters (cudaOccupancyMaxActiveClusters) of the tensor-core recurrence kernels for H hidden

@@ -35,7 +35,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int BT_THREADS = 288;   // warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA/control, 5-8 writers
+constexpr int BT_THREADS = 288;   // warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA / control (forward; TMEM owner), 5-8 writers
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -60,6 +60,12 @@ __host__ __device__ inline uint32_t pow2_cols(uint32_t c) { uint32_t r = 32; whi
 constexpr int PROF_S0 = 100, PROF_N = 4, PROF_K = 12;
 long long* g_prof = nullptr;
 long long* g_prof_bwd = nullptr;
+// Optional schedule trace (diagnostics): per CTA {SM id, globaltimer at start, at end, at the end of the prologue}; forward at [0, 4*4096),
+// backward at [4*4096, 8*4096).
+long long* g_sched = nullptr;
+constexpr int SCHED_MAX = 4096;
+__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint32_t sm_id() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #define PROFB(k) do { if (prof0 && n >= PROF_S0 && n < PROF_S0 + PROF_N) prof0[(n - PROF_S0) * PROF_K + (k)] = clock64(); } while (0)
 #define PROF(k) do { if (prof && s >= PROF_S0 && s < PROF_S0 + PROF_N) prof[(s - PROF_S0) * PROF_K + (k)] = clock64(); } while (0)
 
@@ -68,6 +74,8 @@ long long* g_prof_bwd = nullptr;
 // =================================================================================================
 struct RecTcFwd {
     long long* prof;
+    long long* sched;
+    int dbg;              // experiments (AMSS_BLSTM_DBG): 1 = no global stores, 2 = no input-projection loads, 4 = TMA input loads
     const float* Wh[2];   // [H][ldw]
     int ldw;
     float* gates;         // [2][T][B][4H] in: hoisted input projection (+bias); out: activated gates
@@ -77,61 +85,70 @@ struct RecTcFwd {
     float forget_bias;
 };
 
-// Dependent tcgen05.mma into ONE accumulator serialise at the MMA pipeline latency (~75 clk each at N = 16..64,
-// measured), so the K steps are dealt round-robin to FW_NACC independent accumulators, summed in the epilogue.
-constexpr int FW_NACC = 1;
-// TMEM: D_a at columns [a*NB, (a+1)*NB), A at [FW_ACOL, FW_ACOL + 8*ksteps).  H = 300: 32 + 152 columns -> a 256-column
-// allocation, so TWO CTAs fit the 512 columns of an SM (the NB = 16 variant runs two clusters per SM set: one CTA's
-// exchange / MMA latency is covered by the other CTA's gate math).
+// TMEM: D at columns [0, NB), A at [FW_ACOL, FW_ACOL + 8*ksteps).  H = 300: 32 + 152 columns -> a 256-column allocation, so
+// TWO CTAs fit the 512 columns of an SM (the NB = 16 variant runs two clusters per SM set: one CTA's exchange / MMA latency
+// is covered by the other CTA's gate math).
 constexpr uint32_t FW_ACOL = 32;
-static_assert(FW_NACC == 1, "FW_ACOL assumes one accumulator of NB <= 32 columns");
+constexpr int FW_ZP = 36;   // row pitch (floats) of the [gate][mixture][32 units] staging tiles: 16-byte rows for the writers'
+                            // vector accesses, and bank = 4*mixture + unit for the compute threads' scalar ones (conflict free)
 
+// Lane assignment of the accumulator (= row order of the parked W_h slice): lane 32q + 8g + j holds gate g of unit 8q + j.
+// tcgen05.ld.16x256b puts the TMEM lanes {l, l+8} x two loads (lanes 32q.. and 32q+16..) into ONE thread, so thread t of warp q
+// receives all four gates of unit 8q + t/4 for the mixtures 8*rep + 2*(t%4) + {0,1}: the whole cell update runs in registers
+// (no shared-memory transpose, no barrier between the activations and the cell update).
 template <int NB>
 __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_fwd_tc_kernel(RecTcFwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[5];          // [0] MMA done, [1..2] h_full[buf], [3..4] zx_full[buf]
+    __shared__ __align__(8) uint64_t bars[6];          // [0] MMA done, [1..2] h_full[buf], [3..5] zx_full[slot]
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), NC = cluster_nctarank();
+    if (p.sched && tid == 0 && blockIdx.x < SCHED_MAX) {
+        p.sched[4 * blockIdx.x] = sm_id(); p.sched[4 * blockIdx.x + 1] = globaltimer_ns();
+    }
     const int cid = blockIdx.x / NC, d = cid / p.nsub, sub = cid % p.nsub;
     const int H = p.H, T = p.T, B = p.B, H4 = 4 * H;
     const int b0 = sub * NB, nvalid = min(NB, B - b0);
     const int u0 = crank * 32;
     const int KST = (H + 15) / 16;                // K steps of 16
     const int KCHB = NC * 4;                      // k-chunks (of 8) present in the h buffers
-    constexpr int BG = NB / 8;                    // batch groups of 8
-    constexpr int GXP = NB + 1;                   // gx row pitch
+    constexpr int BG = NB / 8;                    // mixture groups of 8 (= repetitions of the TMEM load)
+    constexpr int ZP = FW_ZP;
     constexpr uint32_t SLICE = 4 * BG * 128;      // bytes of one CTA's h block (32 units x NB mixtures, bf16)
     const uint32_t h_bytes = (uint32_t)KCHB * BG * 128;
     uint8_t* h_s = smem;                                              // [2][h_bytes]   B operand
     uint8_t* hst = h_s + 2 * h_bytes;                                 // [2][SLICE]     own block, source of the bulk copies
-    float* gx = reinterpret_cast<float*>(hst + 2 * SLICE);            // [2][128][NB+1] activated gates
-    float* cy = gx + 2 * 128 * GXP;                                   // [2][2][NB][33] (c | h) staging for the writers
-    float* zxs = cy + 2 * 2 * NB * 33;                                // [2][128][NB+1] hoisted input projection, two steps ahead
+    float* og = reinterpret_cast<float*>(hst + 2 * SLICE);            // [6][NB][ZP]    activated gates i j f o, c, h -> writers
+    float* zxs = og + 6 * NB * ZP;                                    // [3][4][NB][ZP] hoisted input projection, 3 steps ahead
     const uint32_t bar_mma = smem_u32(&bars[0]), h_full = smem_u32(&bars[1]), zx_full = smem_u32(&bars[3]);
     const uint32_t tcols = pow2_cols(FW_ACOL + 8 * KST);
+    const bool tma_zx = (H & 3) == 0 && (p.dbg & 4);   // (experiment) TMA bulk copies for the input projection rows
 
     if (tid == 0) {
         mbar_init(bar_mma, 1); mbar_init(h_full, 1); mbar_init(h_full + 8, 1);
-        mbar_init(zx_full, 128); mbar_init(zx_full + 8, 128);
+        const uint32_t zc = tma_zx ? 1 : 128;
+        mbar_init(zx_full, zc); mbar_init(zx_full + 8, zc); mbar_init(zx_full + 16, zc);
         mbar_fence_init();
     }
     if (warp == 4) tmem_alloc(smem_u32(&tmem_base_s), tcols);
-    for (uint32_t i = tid * 16; i < 2 * h_bytes; i += BT_THREADS * 16) *reinterpret_cast<uint4*>(h_s + i) = make_uint4(0, 0, 0, 0);
+    {   // zero the h operand buffers (h_{-1} = 0, padded units) and the staging tiles (rows / units the copies never write)
+        const uint32_t total = (uint32_t)(reinterpret_cast<uint8_t*>(zxs + 3 * 4 * NB * ZP) - smem);
+        for (uint32_t i = tid * 16; i < total; i += BT_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    if (warp < 4) {   // park this CTA's W_h slice in TMEM:  A[g][k] = Wh[k][gate(g)*H + u0 + g%32]
+    if (warp < 4) {   // park this CTA's W_h slice in TMEM:  A[32q + 8g + j][k] = Wh[k][g*H + u0 + 8q + j]
         const float* Wh = p.Wh[d];
-        const int u = u0 + lane;
+        const int g = lane >> 3, u = u0 + 8 * warp + (lane & 7);
         for (int kk = 0; kk < KST; ++kk) {
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = kk * 16 + 2 * j;
-                const float e0 = (u < H && k < H) ? __ldg(Wh + (size_t)k * p.ldw + warp * H + u) : 0.f;
-                const float e1 = (u < H && k + 1 < H) ? __ldg(Wh + (size_t)(k + 1) * p.ldw + warp * H + u) : 0.f;
+                const float e0 = (u < H && k < H) ? __ldg(Wh + (size_t)k * p.ldw + g * H + u) : 0.f;
+                const float e1 = (u < H && k + 1 < H) ? __ldg(Wh + (size_t)(k + 1) * p.ldw + g * H + u) : 0.f;
                 w[j] = pack_bf16(e0, e1);
             }
             tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + FW_ACOL + kk * 8, w);
@@ -148,83 +165,92 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_fwd_tc
     cluster_sync_all();                               // every CTA's barriers / buffers are ready for remote traffic
     tc_fence_after();
     const uint32_t idesc = idesc_bf16(128, NB, 0, 0);
+    if (p.sched && tid == 0 && blockIdx.x < SCHED_MAX) p.sched[4 * blockIdx.x + 3] = globaltimer_ns();
 
     if (warp < 4) {
         // =========================== compute warps ===========================
-        const int q = warp;
-        constexpr int ITEMS = (8 * NB + 127) / 128;   // (k-chunk, half, mixture) items of 4 units per thread in the cell phase
-        float creg[ITEMS][4];
+        const int q = warp, j8 = lane >> 2, m4 = lane & 3;
+        const int ul = 8 * q + j8;                    // this thread's unit; its mixtures are 8*rep + 2*m4 + e
+        float creg[2 * BG];
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) creg[i][e] = 0.f;
-        const float fb = q == 2 ? p.forget_bias : 0.f;
+        for (int i = 0; i < 2 * BG; ++i) creg[i] = 0.f;
+        const float fb = p.forget_bias;
         long long* prof = (blockIdx.x == 0 && tid == 0) ? p.prof : nullptr;
         for (int s = 0; s < T; ++s) {
             PROF(0);
-            uint32_t acc[NB];
+            // input projection of this step (staged three steps ago): fetched before the wait for the MMAs
+            const int slot = s % 3;
+            mbar_wait(zx_full + 8 * slot, (s / 3) & 1);
+            float z[4][2 * BG];
+            {
+                const float* zb = zxs + slot * (4 * NB * ZP) + ul;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int i = 0; i < 2 * BG; ++i) z[g][i] = zb[(g * NB + 8 * (i >> 1) + 2 * m4 + (i & 1)) * ZP];
+            }
+            uint32_t v0[4 * BG], v1[4 * BG];          // v0: gates i (r 0,1) / j (r 2,3);  v1: gates f / o
             if (s > 0) {
                 mbar_wait(bar_mma, (s - 1) & 1);
                 PROF(1);
                 tc_fence_after();
-#pragma unroll
-                for (int a = 0; a < FW_NACC; ++a) {
-                    if (a >= KST) break;              // fewer K steps than accumulators (tiny H)
-                    uint32_t part[NB];
-                    if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + a * NB, part);
-                    else {
-#pragma unroll
-                        for (int c0 = 0; c0 < NB; c0 += 32) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + a * NB + c0, part + c0);
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int b = 0; b < NB; ++b)
-                        acc[b] = a == 0 ? part[b] : __float_as_uint(__uint_as_float(acc[b]) + __uint_as_float(part[b]));
+                if (NB == 16) {
+                    tmem_ld_16x256b_x2(tmem + ((uint32_t)(q * 32) << 16), v0);
+                    tmem_ld_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16) << 16), v1);
+                } else {
+                    tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32) << 16), v0);
+                    tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32 + 16) << 16), v1);
                 }
+                tmem_ld_wait();
                 tc_fence_before();
             } else {
 #pragma unroll
-                for (int b = 0; b < NB; ++b) acc[b] = 0u;
+                for (int i = 0; i < 4 * BG; ++i) v0[i] = v1[i] = 0u;
             }
             PROF(2);
-            mbar_wait(zx_full + 8 * (s & 1), (s >> 1) & 1);   // the writer warps staged this step's input projection 2 steps ago
-            float* gxs = gx + (s & 1) * (128 * GXP);
-            const float* zr = zxs + (s & 1) * (128 * GXP) + (q * 32 + lane) * GXP;
+            float hv[2 * BG];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float z = __uint_as_float(acc[b]) + zr[b] + fb;
-                gxs[(q * 32 + lane) * GXP + b] = q == 1 ? tanh_fast(z) : sigmoid_fast(z);
+            for (int i = 0; i < 2 * BG; ++i) {
+                const int r = 4 * (i >> 1) + (i & 1);
+                const float gi = sigmoid_fast(__uint_as_float(v0[r]) + z[0][i]);
+                const float gj = tanh_fast(__uint_as_float(v0[r + 2]) + z[1][i]);
+                const float gf = sigmoid_fast(__uint_as_float(v1[r]) + z[2][i] + fb);
+                const float go = sigmoid_fast(__uint_as_float(v1[r + 2]) + z[3][i]);
+                const float c = fmaf(creg[i], gf, gi * gj);
+                creg[i] = c;
+                hv[i] = (8 * (i >> 1) + 2 * m4 + (i & 1)) < nvalid ? tanh_fast(c) * go : 0.f;
+                z[0][i] = gi; z[1][i] = gj; z[2][i] = gf; z[3][i] = go;
             }
             PROF(3);
-            bar_sync_named(1, 256);               // gx[s&1] complete, zxs consumed (compute + writer warps)
-            PROF(4);
-            uint8_t* hsl = hst + (s & 1) * SLICE;
-            float* cys = cy + (s & 1) * (2 * NB * 33);
+            {   // h block in the operand layout; units are paired across lanes t, t^4 so every store is one 32-bit word
+                uint8_t* hsl = hst + (s & 1) * SLICE + (size_t)q * BG * 128 + (2 * m4 + (j8 & 1)) * 16 + (j8 >> 1) * 4;
 #pragma unroll
-            for (int it = 0; it < ITEMS; ++it) {
-                const int item = tid + it * 128;
-                if (item < 8 * NB) {
-                    const int kc = item / (2 * NB), rem = item % (2 * NB), half = rem / NB, b = rem % NB;
-                    float hv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int ul = kc * 8 + half * 4 + e;
-                        const float gi = gxs[(0 * 32 + ul) * GXP + b], gj = gxs[(1 * 32 + ul) * GXP + b];
-                        const float gf = gxs[(2 * 32 + ul) * GXP + b], go = gxs[(3 * 32 + ul) * GXP + b];
-                        const float c = fmaf(creg[it][e], gf, gi * gj);
-                        creg[it][e] = c;
-                        hv[e] = b < nvalid ? tanh_fast(c) * go : 0.f;
-                        cys[b * 33 + ul] = c;
-                        cys[NB * 33 + b * 33 + ul] = hv[e];
-                    }
-                    *reinterpret_cast<uint2*>(hsl + (size_t)(kc * BG + (b >> 3)) * 128 + (b & 7) * 16 + half * 8) =
-                        make_uint2(pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]));
+                for (int rep = 0; rep < BG; ++rep) {
+                    const float mine = (j8 & 1) ? hv[2 * rep + 1] : hv[2 * rep];
+                    const float give = (j8 & 1) ? hv[2 * rep] : hv[2 * rep + 1];
+                    const float got = __shfl_xor_sync(0xffffffffu, give, 4);
+                    *reinterpret_cast<uint32_t*>(hsl + rep * 128) = (j8 & 1) ? pack_bf16(got, mine) : pack_bf16(mine, got);
                 }
             }
             PROF(5);
             fence_async_smem();                   // staged block -> visible to the bulk-copy engine
             bar_arrive_named(2, 160);             // hand the block to the MMA/control warp (no wait here)
             PROF(6);
+            // ---- off the critical path: activated gates, c, h of this step -> staging for the writer warps ----
+            if (s > 0) bar_sync_named(3, 256);    // the writers have read the previous step's tiles
+            {
+                float* ob = og + ul;
+#pragma unroll
+                for (int i = 0; i < 2 * BG; ++i) {
+                    const int b = 8 * (i >> 1) + 2 * m4 + (i & 1);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) ob[(g * NB + b) * ZP] = z[g][i];
+                    ob[(4 * NB + b) * ZP] = creg[i];
+                    ob[(5 * NB + b) * ZP] = hv[i];
+                }
+            }
+            bar_arrive_named(1, 256);             // tiles complete, zx slot consumed
+            PROF(4);
         }
     } else if (warp == 4) {
         // =========================== MMA issuer (converged loop, elected lane) ===========================
@@ -249,120 +275,111 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_fwd_tc
             const uint32_t haddr = smem_u32(h_s + buf * h_bytes);
             for (int kk = 0; kk < KST; ++kk) {
                 const uint64_t bd = smem_desc(haddr + kk * 2 * BG * 128, BG * 128, 128);
-                if (leader) mma_bf16_ts(tmem + (kk % FW_NACC) * NB, tmem + FW_ACOL + kk * 8, bd, idesc, kk >= FW_NACC);
+                if (leader) mma_bf16_ts(tmem, tmem + FW_ACOL + kk * 8, bd, idesc, kk > 0);
             }
             if (leader) mma_commit(bar_mma);
             PROF(10);
             push_h(s);
         }
     } else {
-        // =========================== writer warps: saved gates, c, y -> global ===========================
+        // =========================== writer warps: input projection in, saved gates / c / y out ===========================
         const int wt = tid - 160;                     // 0..127
-        auto flush_cy = [&](int sprev) {
-            const int tp = d == 0 ? sprev : T - 1 - sprev;
-            const float* cys = cy + (sprev & 1) * (2 * NB * 33);
-            const int ul = wt & 31;
-            if (u0 + ul < H) {
-                float cv[NB / 4], hv[NB / 4];
-#pragma unroll
-                for (int i = 0; i < NB / 4; ++i) {      // loads first, then the stores: no LDS -> STG dependency chain
-                    const int b = (wt >> 5) + 4 * i;
-                    cv[i] = cys[b * 33 + ul];
-                    hv[i] = cys[NB * 33 + b * 33 + ul];
-                }
-#pragma unroll
-                for (int i = 0; i < NB / 4; ++i) {
-                    const int b = (wt >> 5) + 4 * i;
-                    if (b < nvalid) {
-                        __stcg(p.cst + (((size_t)d * T + tp) * B + b0 + b) * H + u0 + ul, cv[i]);
-                        __stcg(p.y + ((size_t)tp * B + b0 + b) * 2 * H + d * H + u0 + ul, hv[i]);
+        const int u4 = (wt & 7) * 4, rb = wt >> 3;    // unit quad, mixture row within a group of 16
+        const bool vec = (H & 3) == 0 && u0 + u4 + 4 <= H;
+        long long* prof = (blockIdx.x == 0 && wt == 0) ? p.prof : nullptr;
+        // hoisted input projection (+bias) of step sn -> zxs[sn % 3], three steps ahead.  H % 4 == 0: one TMA bulk copy per
+        // (gate, mixture) row of this CTA's units (<= 128 B), issued by one warp, completing on zx_full[slot] (the LSU never sees
+        // them: per-thread cp.async copies stalled the writers ~1500 clk per step on their own outstanding-request limit).
+        // Rows / units that do not exist are never written and stay zero from the prologue.  Other H: 4-byte cp.async copies.
+        const int nu = min(32, H - u0);
+        auto stage_zx = [&](int sn) {
+            const int t = d == 0 ? sn : T - 1 - sn;
+            const uint32_t bar = zx_full + 8 * (sn % 3);
+            if (tma_zx) {
+                if (wt < 32) {
+                    if (wt == 0) mbar_expect_tx(bar, (uint32_t)(4 * nvalid * nu * 4));
+                    __syncwarp();
+                    const uint32_t sb = smem_u32(zxs + (sn % 3) * (4 * NB * ZP));
+                    for (int r = wt; r < 4 * NB; r += 32) {
+                        const int g4 = r / NB, b = r % NB;
+                        if (b < nvalid)
+                            bulk_g2s(sb + (g4 * NB + b) * ZP * 4, p.gates + (((size_t)d * T + t) * B + b0 + b) * H4 + g4 * H + u0, nu * 4, bar);
                     }
                 }
+                return;
             }
-        };
-        long long* prof = (blockIdx.x == 0 && wt == 0) ? p.prof : nullptr;
-        // hoisted input projection (+bias) of step sn -> registers (issue) -> zxs[sn&1][gate*32+unit][mixture] (commit);
-        // 16-byte loads, a warp = 4 rows x 128 B.  Issued two steps ahead: the rows were just written by the projection
-        // GEMM and mostly come from HBM (~2 us under load).
-        constexpr int ZV = 4 * (NB / 16);
-        float4 zreg[ZV];
-        const int u4 = (wt & 7) * 4, rb = wt >> 3;
-        const bool vec = (H & 3) == 0 && u0 + u4 + 4 <= H;
-        auto issue_zx = [&](int sn) {
-            const int t = d == 0 ? sn : T - 1 - sn;
+            const uint32_t sb = smem_u32(zxs + (sn % 3) * (4 * NB * ZP));
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4)
 #pragma unroll
                 for (int rr = 0; rr < NB / 16; ++rr) {
                     const int b = rr * 16 + rb;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b < nvalid) {
-                        const float* gi = p.gates + (((size_t)d * T + t) * B + b0 + b) * H4 + g4 * H + u0 + u4;
-                        if (vec) v = __ldcg(reinterpret_cast<const float4*>(gi));
-                        else {
-                            if (u0 + u4 < H) v.x = __ldcg(gi);
-                            if (u0 + u4 + 1 < H) v.y = __ldcg(gi + 1);
-                            if (u0 + u4 + 2 < H) v.z = __ldcg(gi + 2);
-                            if (u0 + u4 + 3 < H) v.w = __ldcg(gi + 3);
+                    const bool ok = b < nvalid;
+                    const float* gi = ok ? p.gates + (((size_t)d * T + t) * B + b0 + b) * H4 + g4 * H + u0 + u4 : p.gates;
+                    const uint32_t dst = sb + ((g4 * NB + b) * ZP + u4) * 4;
+                    if (p.dbg & 2) continue;
+                    if (vec) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gi), "r"(ok ? 16u : 0u) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool okj = ok && u0 + u4 + j < H;
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * j), "l"(okj ? gi + j : p.gates), "r"(okj ? 4u : 0u) : "memory");
                         }
                     }
-                    zreg[g4 * (NB / 16) + rr] = v;
                 }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
         };
-        auto commit_zx = [&](int sn) {
-            float* zb = zxs + (sn & 1) * (128 * GXP);
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4)
-#pragma unroll
-                for (int rr = 0; rr < NB / 16; ++rr) {
-                    const float4 v = zreg[g4 * (NB / 16) + rr];
-                    float* zp = zb + (g4 * 32 + u4) * GXP + rr * 16 + rb;
-                    zp[0] = v.x; zp[GXP] = v.y; zp[2 * GXP] = v.z; zp[3 * GXP] = v.w;
-                }
-            mbar_arrive(zx_full + 8 * (sn & 1));
-        };
-        issue_zx(0); commit_zx(0);
-        if (T > 1) { issue_zx(1); commit_zx(1); }
+        for (int n = 0; n < 3 && n < T; ++n) stage_zx(n);
         for (int s = 0; s < T; ++s) {
             const int t = d == 0 ? s : T - 1 - s;
-            if (s + 2 < T) issue_zx(s + 2);               // in flight under this step's stores
-            bar_sync_named(1, 256);                       // gx[s&1] complete; zxs[s&1] consumed by the compute warps
-            PROF(7);
-            const float* gxs = gx + (s & 1) * (128 * GXP);
-            {   // saved gates: 16-byte stores, thread = (4 consecutive units, one mixture row); a warp covers 4 rows x 128 B
-                const int u4 = (wt & 7) * 4, rb = wt >> 3;            // unit quad, row within a group of 16 rows
-                const bool vec = (H & 3) == 0 && u0 + u4 + 4 <= H;
+            bar_sync_named(1, 256);                       // this step's tiles are complete; zx slot s%3 has been consumed
+            long long tw0 = 0, tw1 = 0, tw2 = 0;          // profile stamps stay in registers until the stores are out
+            if (prof) tw0 = clock64();
+            if (!(p.dbg & 8) && s + 3 < T) stage_zx(s + 3);   // first: refill the slot just freed, three steps ahead (A/B: 428 -> 399 us)
+            float4 gv[4 * (NB / 16)], cv[NB / 16], yv[NB / 16];
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4)
+            for (int rr = 0; rr < NB / 16; ++rr) {
+                const int b = rr * 16 + rb;
 #pragma unroll
-                    for (int rr = 0; rr < NB; rr += 16) {
-                        const int b = rr + rb;
-                        const float* gp = gxs + (g4 * 32 + u4) * GXP + b;
-                        const float4 v = make_float4(gp[0], gp[GXP], gp[2 * GXP], gp[3 * GXP]);
-                        if (b < nvalid) {
-                            float* go = p.gates + (((size_t)d * T + t) * B + b0 + b) * H4 + g4 * H + u0 + u4;
-                            if (vec) __stcg(reinterpret_cast<float4*>(go), v);
-                            else {
-                                if (u0 + u4 < H) __stcg(go, v.x);
-                                if (u0 + u4 + 1 < H) __stcg(go + 1, v.y);
-                                if (u0 + u4 + 2 < H) __stcg(go + 2, v.z);
-                                if (u0 + u4 + 3 < H) __stcg(go + 3, v.w);
-                            }
-                        }
-                    }
+                for (int g4 = 0; g4 < 4; ++g4) gv[g4 * (NB / 16) + rr] = *reinterpret_cast<const float4*>(og + (g4 * NB + b) * ZP + u4);
+                cv[rr] = *reinterpret_cast<const float4*>(og + (4 * NB + b) * ZP + u4);
+                yv[rr] = *reinterpret_cast<const float4*>(og + (5 * NB + b) * ZP + u4);
             }
-            PROF(8);
-            if (s > 0) flush_cy(s - 1);
-            if (s + 2 < T) commit_zx(s + 2);
-            PROF(11);
+            if (s + 1 < T) bar_arrive_named(3, 256);      // tiles are in registers: the compute warps may overwrite them
+            if (prof) tw1 = clock64();
+            if ((p.dbg & 8) && s + 3 < T) stage_zx(s + 3);
+            if (prof) tw2 = clock64();
+            auto put4 = [&](float* dst, const float4& v) {
+                if (vec) __stcg(reinterpret_cast<float4*>(dst), v);
+                else {
+                    if (u0 + u4 < H) __stcg(dst, v.x);
+                    if (u0 + u4 + 1 < H) __stcg(dst + 1, v.y);
+                    if (u0 + u4 + 2 < H) __stcg(dst + 2, v.z);
+                    if (u0 + u4 + 3 < H) __stcg(dst + 3, v.w);
+                }
+            };
+#pragma unroll
+            for (int rr = 0; rr < NB / 16; ++rr) {
+                const int b = rr * 16 + rb;
+                if (b < nvalid && !(p.dbg & 1)) {
+                    const size_t row = ((size_t)d * T + t) * B + b0 + b;
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) put4(p.gates + row * H4 + g4 * H + u0 + u4, gv[g4 * (NB / 16) + rr]);
+                    put4(p.cst + row * H + u0 + u4, cv[rr]);
+                    put4(p.y + ((size_t)t * B + b0 + b) * 2 * H + d * H + u0 + u4, yv[rr]);
+                }
+            }
+            if (prof && s >= PROF_S0 && s < PROF_S0 + PROF_N) {
+                long long* pr = prof + (s - PROF_S0) * PROF_K;
+                pr[8] = clock64(); pr[7] = tw0; pr[11] = tw2; prof[48 + (s - PROF_S0)] = tw1;
+            }
         }
-        bar_sync_named(3, 256);                       // the last cell phase has written cy
-        flush_cy(T - 1);
     }
-    if (warp < 4) bar_sync_named(3, 256);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                               // no CTA exits while peers may still push into it
+    if (p.sched && tid == 0 && blockIdx.x < SCHED_MAX) p.sched[4 * blockIdx.x + 2] = globaltimer_ns();
     if (warp == 4) tmem_dealloc(tmem, tcols);
 }
 
@@ -395,6 +412,7 @@ int launch_fwd(const RecTcFwd& p, int NC, cudaStream_t st) {
 // =================================================================================================
 struct RecTcBwd {
     long long* prof;
+    long long* sched;
     const float* Wh[2];   // [H][ldw]
     int ldw;
     const float* gates;   // [2][T][B][4H] activated gates (saved by the forward pass)
@@ -414,29 +432,36 @@ __host__ __device__ inline uint32_t bw_acol(int MT, int NB) { return (uint32_t)(
 template <int NB>
 __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc_kernel(RecTcBwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[6];          // [0] MMA done, [1..2] r_full[buf], [3..5] sv_full[slot]
+    __shared__ __align__(8) uint64_t bars[9];          // [0..3] MMA tile m done, [4..5] r_full[buf], [6..8] sv_full[slot]
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), NC = cluster_nctarank();
+    if (p.sched && tid == 0 && blockIdx.x < SCHED_MAX) {
+        p.sched[4 * blockIdx.x] = sm_id(); p.sched[4 * blockIdx.x + 1] = globaltimer_ns();
+    }
     const int cid = blockIdx.x / NC, d = cid / p.nsub, sub = cid % p.nsub;
     const int H = p.H, T = p.T, B = p.B, H4 = 4 * H, MT = p.MT;
     const int b0 = sub * NB, nvalid = min(NB, B - b0);
     const int u0 = crank * 32;
     constexpr int BG = NB / 8;
     constexpr int ZP = NB + 1;
-    constexpr uint32_t BLK = 32 * NB * 2;                                // one (src CTA -> dest CTA) block of bf16 partial sums
+    constexpr uint32_t BLK = 32 * NB * 2;                                // one (src CTA -> dest CTA) block of bf16 partial sums:
+                                                                         //   [NB/4 mixture quads][32 units][4 mixtures] (8-byte items)
+    constexpr uint32_t ZLBO = BG * 128 + 16;                             // k-chunk stride of the dz operand, padded by 16 B: the four
+                                                                         // 8-unit groups of a warp's 2-byte stores fall on different banks
     const uint32_t r_bytes = (uint32_t)NC * BLK;
-    uint8_t* z_s = smem;                                                 // dz operand [NB][128] bf16, K-major
-    uint8_t* r_s = z_s + NB * 128 * 2;                                   // [2][NC][32][NB] bf16   received partials
-    uint8_t* p_s = r_s + 2 * r_bytes;                                    // [2][NC][32][NB] bf16   partials to send (by dest)
+    uint8_t* z_s = smem;                                                 // dz operand [16 k-chunks][NB][8] bf16, K-major
+    uint8_t* r_s = z_s + 16 * ZLBO;                                      // [2][NC][BLK]   received partials (by source)
+    uint8_t* p_s = r_s + 2 * r_bytes;                                    // [2][NC][BLK]   partials to send (by dest)
     float* dzs = reinterpret_cast<float*>(p_s + 2 * r_bytes);            // [2][128][NB+1] fp32 dz staging for the writers
     float* svs = dzs + 2 * 128 * ZP;                                     // [3][7][NB][32] saved gates / c / c_prev / dy, 3 steps ahead (cp.async ring)
-    const uint32_t bar_mma = smem_u32(&bars[0]), r_full = smem_u32(&bars[1]), sv_full = smem_u32(&bars[3]);
+    const uint32_t bar_mma = smem_u32(&bars[0]), r_full = smem_u32(&bars[4]), sv_full = smem_u32(&bars[6]);
     const uint32_t BW_ACOL = bw_acol(MT, NB);
     const uint32_t tcols = pow2_cols(BW_ACOL + 64 * MT);
 
     if (tid == 0) {
-        mbar_init(bar_mma, 1); mbar_init(r_full, 1); mbar_init(r_full + 8, 1);
+        for (int m = 0; m < 4; ++m) mbar_init(bar_mma + 8 * m, 1);
+        mbar_init(r_full, 1); mbar_init(r_full + 8, 1);
         mbar_init(sv_full, 128); mbar_init(sv_full + 8, 128); mbar_init(sv_full + 16, 128);
         mbar_fence_init();
     }
@@ -447,18 +472,26 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
     const uint32_t tmem = tmem_base_s;
     if (warp < 4) {   // park A[u][g] = Wh[u][gate(g)*H + u0 + g%32] in TMEM (lane = unit of the M tile)
         const float* Wh = p.Wh[d];
+        const bool vec = (H & 3) == 0 && (p.ldw & 3) == 0;
         for (int m = 0; m < MT; ++m) {
             const int u = m * 128 + warp * 32 + lane;
             for (int kk = 0; kk < 8; ++kk) {
-                const int gate = kk >> 1, ul = (kk & 1) * 16;
+                const int gate = kk >> 1, c0 = u0 + (kk & 1) * 16;
+                const float* src = Wh + (size_t)u * p.ldw + gate * H + c0;
+                float e[16];
+                if (vec && u < H && c0 + 16 <= H) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + j);
+                        e[4 * j] = v.x; e[4 * j + 1] = v.y; e[4 * j + 2] = v.z; e[4 * j + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) e[j] = (u < H && c0 + j < H) ? __ldg(src + j) : 0.f;
+                }
                 uint32_t w[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c0 = u0 + ul + 2 * j;
-                    const float e0 = (u < H && c0 < H) ? __ldg(Wh + (size_t)u * p.ldw + gate * H + c0) : 0.f;
-                    const float e1 = (u < H && c0 + 1 < H) ? __ldg(Wh + (size_t)u * p.ldw + gate * H + c0 + 1) : 0.f;
-                    w[j] = pack_bf16(e0, e1);
-                }
+                for (int j = 0; j < 8; ++j) w[j] = pack_bf16(e[2 * j], e[2 * j + 1]);
                 tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + BW_ACOL + m * 64 + kk * 8, w);
             }
         }
@@ -473,6 +506,7 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
     cluster_sync_all();
     tc_fence_after();
     const uint32_t idesc = idesc_bf16(128, NB, 0, 0);
+    if (p.sched && tid == 0 && blockIdx.x < SCHED_MAX) p.sched[4 * blockIdx.x + 3] = globaltimer_ns();
 
     if (warp < 4) {
         // =========================== compute warps ===========================
@@ -482,53 +516,76 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
 #pragma unroll
         for (int i = 0; i < IT; ++i) dcc[i] = 0.f;
         long long* prof0 = (blockIdx.x == 0 && tid == 0) ? p.prof : nullptr;
+        const bool leader = elect_one();
         for (int s = T - 1; s >= 0; --s) {
             const int n = T - 1 - s;                  // step counter
             PROFB(0);
             float dh[IT];
-            if (n > 0) {
-                // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]  ->  staged per owner CTA
-                uint8_t* ps = p_s + (n & 1) * r_bytes;
-                mbar_wait(bar_mma, (n - 1) & 1);
-                PROFB(2);
+            if (n > 0 && q < MT) {
+                // MMAs of tile q, issued by THIS warp: chains issued by several warps in parallel run at the tensor pipe's rate
+                // (~36 clk per N = 16 MMA) instead of one thread's issue rate (~55 clk, tools/ld_probe.cu)
+                PROFB(9);
                 tc_fence_after();
+                const uint32_t zaddr = smem_u32(z_s);
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint64_t bd = smem_desc(zaddr + kk * 2 * ZLBO, ZLBO, 128);
+                    if (leader) mma_bf16_ts(tmem + q * NB, tmem + BW_ACOL + q * 64 + kk * 8, bd, idesc, kk > 0);
+                }
+                if (leader) mma_commit(bar_mma + 8 * q);
+                __syncwarp();
+                PROFB(10);
+            }
+            if (n > 0) {
+                // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]: tile m (units m*128 + q*32 + lane) is staged as the
+                // block of its owner CTA m*4 + q and pushed by THIS warp as soon as the tile's MMAs have completed -- the later
+                // tiles' MMAs run under the exchange of the earlier ones, and no other warp is involved in the push.
+                uint8_t* ps = p_s + (n & 1) * r_bytes;
                 for (int m = 0; m < MT; ++m) {
-                    const uint32_t dest = m * 4 + q;  // units m*128 + q*32 + lane  ->  CTA dest, local unit = lane
+                    const uint32_t dest = m * 4 + q;
+                    if (dest >= NC) break;            // warp-uniform: the tail tile has fewer owner CTAs
+                    mbar_wait(bar_mma + 8 * m, (n - 1) & 1);
+                    if (m == 0) PROFB(2);
+                    tc_fence_after();
                     uint32_t acc[NB];
                     if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
                     else tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
                     tmem_ld_wait();
-                    if (dest < NC) {
-                        uint8_t* pd = ps + (size_t)dest * BLK + lane * (NB * 2);
+                    tc_fence_before();
+                    uint8_t* pd = ps + (size_t)dest * BLK + lane * 8;
 #pragma unroll
-                        for (int b = 0; b < NB; b += 8)
-                            *reinterpret_cast<uint4*>(pd + b * 2) =
-                                make_uint4(pack_bf16(__uint_as_float(acc[b]), __uint_as_float(acc[b + 1])),
-                                           pack_bf16(__uint_as_float(acc[b + 2]), __uint_as_float(acc[b + 3])),
-                                           pack_bf16(__uint_as_float(acc[b + 4]), __uint_as_float(acc[b + 5])),
-                                           pack_bf16(__uint_as_float(acc[b + 6]), __uint_as_float(acc[b + 7])));
-                    }
+                    for (int g = 0; g < NB / 4; ++g)
+                        *reinterpret_cast<uint2*>(pd + g * 256) =
+                            make_uint2(pack_bf16(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1])),
+                                       pack_bf16(__uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3])));
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0)
+                        bulk_s2c(mapa(smem_u32(r_s + (n & 1) * r_bytes) + crank * BLK, dest), smem_u32(ps) + dest * BLK, BLK,
+                                 mapa(r_full + 8 * (n & 1), dest));
                 }
-                tc_fence_before();
-                fence_async_smem();
-                bar_arrive_named(2, 160);                 // the MMA/control warp pushes the staged partials
                 PROFB(3);
                 mbar_wait(r_full + 8 * (n & 1), ((n - 1) >> 1) & 1);       // every CTA's partials for my units have landed
                 PROFB(4);
                 if (tid == 0 && n + 2 < T) mbar_expect_tx(r_full + 8 * (n & 1), NC * BLK);   // re-arm for step n+2
-                const uint8_t* rb = r_s + (n & 1) * r_bytes + (size_t)lane * (NB * 2) + q * IT * 2;
+                // this thread's unit = lane, mixtures q*IT .. q*IT+IT-1: one 8-byte item per mixture quad, lanes consecutive
+                const uint8_t* rb = r_s + (n & 1) * r_bytes + (size_t)(q * (IT / 4) * 32 + lane) * 8;
 #pragma unroll
                 for (int i = 0; i < IT; ++i) dh[i] = 0.f;
-#pragma unroll 4
-                for (uint32_t c = 0; c < NC; ++c) {
-                    const uint8_t* rp = rb + (size_t)c * BLK;
-                    if (IT == 4) {
-                        const uint2 w = *reinterpret_cast<const uint2*>(rp);
-                        dh[0] += bf16_lo(w.x); dh[1] += bf16_hi(w.x); dh[2] += bf16_lo(w.y); dh[3] += bf16_hi(w.y);
-                    } else {
-                        const uint4 w = *reinterpret_cast<const uint4*>(rp);
-                        dh[0] += bf16_lo(w.x); dh[1] += bf16_hi(w.x); dh[2] += bf16_lo(w.y); dh[3] += bf16_hi(w.y);
-                        dh[4 % IT] += bf16_lo(w.z); dh[5 % IT] += bf16_hi(w.z); dh[6 % IT] += bf16_lo(w.w); dh[7 % IT] += bf16_hi(w.w);
+                // all loads first (a source index beyond the cluster re-reads block 0 and is masked out below): a branch per source
+                // would serialise load -> add -> load
+                uint2 w[16][IT / 4];
+#pragma unroll
+                for (uint32_t c = 0; c < 16; ++c)
+#pragma unroll
+                    for (int g = 0; g < IT / 4; ++g)
+                        w[c][g] = *reinterpret_cast<const uint2*>(rb + (size_t)(c < NC ? c : 0) * BLK + g * 256);
+#pragma unroll
+                for (uint32_t c = 0; c < 16; ++c) {
+                    const float on = c < NC ? 1.f : 0.f;
+#pragma unroll
+                    for (int g = 0; g < IT / 4; ++g) {
+                        dh[4 * g] = fmaf(on, bf16_lo(w[c][g].x), dh[4 * g]); dh[4 * g + 1] = fmaf(on, bf16_hi(w[c][g].x), dh[4 * g + 1]);
+                        dh[4 * g + 2] = fmaf(on, bf16_lo(w[c][g].y), dh[4 * g + 2]); dh[4 * g + 3] = fmaf(on, bf16_hi(w[c][g].y), dh[4 * g + 3]);
                     }
                 }
             } else {
@@ -536,6 +593,9 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
                 for (int i = 0; i < IT; ++i) dh[i] = 0.f;
             }
             PROFB(5);
+            // the dz operand is rewritten below: ALL of this step's MMAs (they read it) must have completed, also for the warps
+            // that own no block of the last tile
+            if (n > 0) mbar_wait(bar_mma + 8 * (MT - 1), (n - 1) & 1);
             mbar_wait(sv_full + 8 * (n % 3), (n / 3) & 1);    // staged three steps ago by the writer warps (cp.async)
             const float* svb = svs + (n % 3) * (7 * NB * 32) + (q * IT) * 32 + lane;
             // gate derivatives; dz -> fp32 staging (writers) and bf16 operand of the next step's MMA
@@ -558,42 +618,17 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
                 for (int g4 = 0; g4 < 4; ++g4) {
                     dzb[(g4 * 32 + lane) * ZP + b] = dz[g4];
                     const int k = g4 * 32 + lane;
-                    *reinterpret_cast<__nv_bfloat16*>(z_s + (size_t)((k >> 3) * BG + (b >> 3)) * 128 + (b & 7) * 16 + (k & 7) * 2) =
+                    *reinterpret_cast<__nv_bfloat16*>(z_s + (size_t)(k >> 3) * ZLBO + (b >> 3) * 128 + (b & 7) * 16 + (k & 7) * 2) =
                         __float2bfloat16_rn(dz[g4]);
                 }
             }
             PROFB(6);
             fence_async_smem();
-            bar_sync_named(1, 288);                   // dz staged: MMA warp may issue, writers may store
+            bar_sync_named(1, 256);                   // dz staged by every warp: the next step's MMAs may issue, writers may store
             PROFB(7);
         }
     } else if (warp == 4) {
-        // =========================== MMA issuer (converged loop, elected lane) ===========================
-        const bool leader = elect_one();
-        long long* prof0 = (blockIdx.x == 0 && lane == 0) ? p.prof : nullptr;
-        for (int n = 0; n < T; ++n) {
-            if (n > 0) {
-                PROFB(9);
-                tc_fence_after();
-                const uint32_t zaddr = smem_u32(z_s);
-                for (int kk = 0; kk < 8; ++kk)
-                    for (int m = 0; m < MT; ++m) {
-                        const uint64_t bd = smem_desc(zaddr + kk * 2 * BG * 128, BG * 128, 128);
-                        if (leader) mma_bf16_ts(tmem + m * NB, tmem + BW_ACOL + m * 64 + kk * 8, bd, idesc, kk > 0);
-                    }
-                if (leader) mma_commit(bar_mma);
-                PROFB(10);
-                bar_sync_named(2, 160);                   // partial sums of this step are staged in p_s[n&1]
-                if ((uint32_t)lane < NC) {                // one bulk copy per lane
-                    const uint32_t dst = smem_u32(r_s + (n & 1) * r_bytes) + crank * BLK;
-                    const uint32_t bar = r_full + 8 * (n & 1);
-                    bulk_s2c(mapa(dst, lane), smem_u32(p_s + (n & 1) * r_bytes) + lane * BLK, BLK, mapa(bar, lane));
-                }
-                PROFB(11);
-            }
-            __syncwarp();
-            bar_sync_named(1, 288);
-        }
+        // (warp 4 only owns the TMEM allocation: the compute warps issue their own tiles' MMAs)
     } else {
         // =========================== writer warps: dZ -> global ===========================
         const int wt = tid - 160, wq = wt >> 5, wu = u0 + (wt & 31);
@@ -639,7 +674,7 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
         for (int n = 0; n < 3 && n < T; ++n) stage_sv(n);
         for (int s = T - 1; s >= 0; --s) {
             const int t = d == 0 ? s : T - 1 - s, n = T - 1 - s;
-            bar_sync_named(1, 288);                               // dz(n) staged; svs[n%3] consumed by the compute warps
+            bar_sync_named(1, 256);                               // dz(n) staged; svs[n%3] consumed by the compute warps
             if (n + 3 < T) stage_sv(n + 3);                       // refill the slot just freed, three steps ahead
             const float* dzb = dzs + (n & 1) * (128 * ZP);
             if (wu < H) {
@@ -666,6 +701,7 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
+    if (p.sched && tid == 0 && blockIdx.x < SCHED_MAX) p.sched[4 * blockIdx.x + 2] = globaltimer_ns();
     if (warp == 4) tmem_dealloc(tmem, tcols);
 }
 
@@ -711,10 +747,10 @@ int max_clusters(K kernel, int NC, size_t smem) {
 }
 
 size_t fwd_smem(int NC, int NB) {
-    return 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)4 * 128 * (NB + 1) * 4 + (size_t)2 * 2 * NB * 33 * 4;
+    return 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)(6 + 12) * NB * FW_ZP * 4;
 }
 size_t bwd_smem(int NC, int NB) {
-    return (size_t)NB * 128 * 2 + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)3 * 7 * NB * 32 * 4;
+    return (size_t)16 * ((NB / 8) * 128 + 16) + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)3 * 7 * NB * 32 * 4;
 }
 
 // Sub-batch size.  Measured on B200 (tools/blstm_bench.py, T = 250, I = 600, H = 300; fwd + bwd layer times in ms):
@@ -732,6 +768,7 @@ struct MaxC { int c16 = 0, c32 = 0; };
 
 }  // namespace
 
+void blstm_tc_set_sched(long long* dev_buf) { g_sched = dev_buf; }
 void blstm_tc_set_profile(long long* dev_buf) { g_prof = dev_buf; g_prof_bwd = dev_buf ? dev_buf + 64 : nullptr; }
 
 bool blstm_rec_tc_supported(int B, int T, int H) {
@@ -745,6 +782,8 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
     const int NC = (H + 31) / 32;
     RecTcFwd p;
     p.prof = g_prof;
+    p.sched = g_sched;
+    { const char* e = getenv("AMSS_BLSTM_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.y = y;
     p.B = B; p.T = T; p.H = H; p.forget_bias = forget_bias;
     static MaxC mc[17];
@@ -775,6 +814,7 @@ int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const floa
     const int NC = (H + 31) / 32;
     RecTcBwd p;
     p.prof = g_prof_bwd;
+    p.sched = g_sched ? g_sched + 4 * SCHED_MAX : nullptr;
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.dy = dy; p.dZ = dZ;
     p.dZb = dZb; p.ldzb = ldzb; p.dbpart = dbpart;
     p.B = B; p.T = T; p.H = H; p.MT = (NC * 32 + 127) / 128;

@@ -35,10 +35,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware until the phase completes instead of
+                                                  // returning early and polling (polling warps starve their SM sub-partition)
         : "memory");
     return ok != 0;
 }
@@ -101,6 +102,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr)
                  : "memory");
+}
+// 16 lanes x 256 bits per repetition (the mma.m16n8 accumulator fragment; pinned on hardware by tools/ld_probe.cu): with
+// the address pointing at lane l0 (a multiple of 16 inside the warp's quadrant), thread t receives in register 4*rep + r
+// lane l0 + t/4 + 8*(r/2), column c0 + 8*rep + 2*(t%4) + r%2.  Four TMEM lanes 8 apart meet in one thread after two loads.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -159,6 +159,9 @@ int amss_blstm_bwd(const float* x, const float* kernel_fw, const float* kernel_b
 /* Diagnostics only: clock64() stamps of the tensor-core recurrence (CTA 0, steps 100..103, 12
  * slots per step; forward at [0,48), backward at [64,112)) are written to dev_buf (>= 128 int64) by later amss_blstm_fwd calls; NULL = off. */
 int amss_debug_blstm_profile(long long* dev_buf);
+/* Diagnostics only: schedule trace of the tensor-core recurrence kernels: per CTA {SM id, globaltimer ns at start, at end,
+ * at the end of the prologue}; forward launches at [0, 4*4096), backward at [4*4096, 8*4096) of dev_buf (>= 8*4096 int64); NULL = off.    */
+int amss_debug_blstm_sched(long long* dev_buf);
 /* Diagnostics only: co-resident clusters of the tensor-core recurrence kernels for H hidden units
  * per direction, out4 (HOST memory) = {fwd NB=16, fwd NB=32, bwd NB=16, bwd NB=32}.          */
 int amss_debug_blstm_clusters(int H, int* out4);

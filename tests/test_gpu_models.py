@@ -501,11 +501,16 @@ def test_dataset_normalize_and_device_built_mixture(amss):
     B, S, Lw = 2, 2, 2048
     t = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=24, embedding_size=8, learning_rate=1e-3,
                                   window_size=128, hop_size=64, dataset_normalize=True)
-    # unit-variance inputs are 20x the usual level: the first BLSTM layer runs deep in saturation, where (1 - tanh^2) and
-    # y (1 - y) cancel catastrophically in fp32 -- its gradient is round-off in BOTH implementations (measured: two fp32
-    # evaluations differ by 10 % of the gradient norm there, fp32 vs float64 by 3e-3 on the cost).  The comparison is
-    # therefore on the forward cost and on the gradient of the head (the well-conditioned part); the normalisation kernel
-    # itself is checked element-wise in test_gpu_kernels.py::test_prepare_inputs_mix_and_normalize
+    # unit-variance inputs are 20x the usual level: with the stock initialisation the first BLSTM layer runs deep in saturation
+    # and every embedding collapses onto one direction, where BOTH the recurrence's (1 - tanh^2) factors and the DPCL gradient
+    # (a radial term that the normalisation projects out) are pure round-off in fp32 -- two fp32 evaluations of the same graph
+    # then differ by 10-20 % of the gradient norm (measured).  The BLSTM kernels are therefore scaled down so that the step is
+    # well conditioned and every tensor can be compared; the normalisation kernel itself is checked element-wise in
+    # test_gpu_kernels.py::test_prepare_inputs_mix_and_normalize
+    with torch.no_grad():
+        for k, v in t.store.params.items():
+            if v.dim() == 2 and v.shape[1] == 4 * 24:
+                v.mul_(0.05)
     p = _copy_params(t.store, {})
     fn = functools.partial(OS.stft_separator_loss, nb_layers=1, embedding_size=8, window_size=128, hop_size=64)
     st = OS.Stepper(p, fn, lr=1e-3)
@@ -515,9 +520,12 @@ def test_dataset_normalize_and_device_built_mixture(amss):
     c_ref, _ = st.step(nmn.sum(1), nmn, torch.tensor(I))
     c = t.train_step(None, _dev(nm), _dev(I))
     assert abs(float(c) - c_ref) < REL * abs(c_ref)
-    for k in ("prediction/W", "prediction/b"):
+    gmax = max(float(g.double().norm()) for g in st.last_grads.values())
+    for k in st.tr:
         g_dev, g_ref = t.store[k].grad.detach().double().cpu(), st.last_grads[k].double()
-        assert float((g_dev - g_ref).norm() / g_ref.norm()) < 1e-2, k
+        err = float((g_dev - g_ref).norm())
+        print(f"dataset_normalize step: {k}: |g| {float(g_ref.norm()):.3e} err {err:.3e}")
+        assert err < 5e-3 * max(float(g_ref.norm()), 1e-2 * gmax), k
     assert bool(torch.isfinite(t.store.grad_flat).all())
 
 

@@ -15,7 +15,7 @@ NAMES = ["0 step start", "1 mma done", "2 tmem ld done", "3 activation done", "4
          "6 staged+arrive", "7 writer: barrier passed", "8 writer: gates stored", "9 mma warp: h landed", "10 mma issued",
          "11 writer: c,y stored"]
 
-for B in (16, 64, 128):
+for B in [int(a) for a in sys.argv[1:]] or [16, 64, 128]:
     T, I, H = 250, 600, 300
     x = torch.randn(T, B, I, device="cuda") * 0.1
     kf = torch.randn(I + H, 4 * H, device="cuda") * 0.05
@@ -34,7 +34,11 @@ for B in (16, 64, 128):
         row = p[s]
         base = int(row[0])
         print(f" step {100 + s}: total {int(p[s + 1][0]) - base} clk ; " +
-              " ".join(f"[{k}]+{int(row[k]) - base}" for k in range(1, 12)))
+              " ".join(f"[{k}]+{int(row[k]) - base}" for k in (1, 2, 3, 5, 6, 4)) + " | mma warp " +
+              " ".join(f"[{k}]+{int(row[k]) - base}" for k in (9, 10)))
+        w7 = int(row[7])   # writer stamps come from another SM sub-partition (own clock offset): differences only
+        print(f"      writer: zx issued +{int(row[11]) - w7}, tiles read +{int(buf.cpu()[48 + s]) - w7}, stores issued +{int(row[8]) - w7}"
+              f" ; barrier-to-barrier {int(p[s + 1][7]) - w7}")
 
     pb = buf.cpu().view(-1)[64:112].view(4, 12)
     for s in range(1, 3):
