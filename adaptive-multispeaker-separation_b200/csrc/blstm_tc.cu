@@ -35,7 +35,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int BT_THREADS = 288;   // warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA / control (forward; TMEM owner), 5-8 writers
+constexpr int BT_THREADS = 288;   // forward: warps 0-3 compute (TMEM lane quadrant = warp), 4 MMA / control (TMEM owner), 5-8 writers
+constexpr int BW_THREADS = 256;   // backward: warps 0-3 compute (they issue their own MMAs), 4-7 writers (warp 4 owns the TMEM allocation);
+                                  // 2 x 256 threads leave 128 registers per thread
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -413,6 +415,7 @@ int launch_fwd(const RecTcFwd& p, int NC, cudaStream_t st) {
 struct RecTcBwd {
     long long* prof;
     long long* sched;
+    int dbg;              // experiments (AMSS_BLSTM_DBG): 1 = no global stores, 2 = no saved-activation loads
     const float* Wh[2];   // [H][ldw]
     int ldw;
     const float* gates;   // [2][T][B][4H] activated gates (saved by the forward pass)
@@ -430,9 +433,9 @@ struct RecTcBwd {
 __host__ __device__ inline uint32_t bw_acol(int MT, int NB) { return (uint32_t)((MT * NB + 31) & ~31); }
 
 template <int NB>
-__global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc_kernel(RecTcBwd p) {
+__global__ void __launch_bounds__(BW_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc_kernel(RecTcBwd p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[9];          // [0..3] MMA tile m done, [4..5] r_full[buf], [6..8] sv_full[slot]
+    __shared__ __align__(8) uint64_t bars[9];          // [0] MMAs done (all tiles), [4..5] r_full[buf], [6..8] sv_full[slot]
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank(), NC = cluster_nctarank();
@@ -444,7 +447,9 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
     const int b0 = sub * NB, nvalid = min(NB, B - b0);
     const int u0 = crank * 32;
     constexpr int BG = NB / 8;
-    constexpr int ZP = NB + 1;
+    constexpr int DZP = 132;                                             // row pitch (floats) of the dz staging tile [NB][128 gate cols]:
+                                                                         // bank = 4*mixture + column for the compute warps' scalar stores,
+                                                                         // 16-byte rows for the writers' vector loads
     constexpr uint32_t BLK = 32 * NB * 2;                                // one (src CTA -> dest CTA) block of bf16 partial sums:
                                                                          //   [NB/4 mixture quads][32 units][4 mixtures] (8-byte items)
     constexpr uint32_t ZLBO = BG * 128 + 16;                             // k-chunk stride of the dz operand, padded by 16 B: the four
@@ -453,14 +458,14 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
     uint8_t* z_s = smem;                                                 // dz operand [16 k-chunks][NB][8] bf16, K-major
     uint8_t* r_s = z_s + 16 * ZLBO;                                      // [2][NC][BLK]   received partials (by source)
     uint8_t* p_s = r_s + 2 * r_bytes;                                    // [2][NC][BLK]   partials to send (by dest)
-    float* dzs = reinterpret_cast<float*>(p_s + 2 * r_bytes);            // [2][128][NB+1] fp32 dz staging for the writers
-    float* svs = dzs + 2 * 128 * ZP;                                     // [3][7][NB][32] saved gates / c / c_prev / dy, 3 steps ahead (cp.async ring)
+    float* dzs = reinterpret_cast<float*>(p_s + 2 * r_bytes);            // [2][NB][DZP] fp32 dz staging for the writers
+    float* svs = dzs + 2 * NB * DZP;                                     // [3][7][NB][32] saved gates / c / c_prev / dy, 3 steps ahead (cp.async ring)
     const uint32_t bar_mma = smem_u32(&bars[0]), r_full = smem_u32(&bars[4]), sv_full = smem_u32(&bars[6]);
     const uint32_t BW_ACOL = bw_acol(MT, NB);
     const uint32_t tcols = pow2_cols(BW_ACOL + 64 * MT);
 
     if (tid == 0) {
-        for (int m = 0; m < 4; ++m) mbar_init(bar_mma + 8 * m, 1);
+        mbar_init(bar_mma, MT);                  // one tcgen05.commit per issuing warp (tile)
         mbar_init(r_full, 1); mbar_init(r_full + 8, 1);
         mbar_init(sv_full, 128); mbar_init(sv_full + 8, 128); mbar_init(sv_full + 16, 128);
         mbar_fence_init();
@@ -520,7 +525,6 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
         for (int s = T - 1; s >= 0; --s) {
             const int n = T - 1 - s;                  // step counter
             PROFB(0);
-            float dh[IT];
             if (n > 0 && q < MT) {
                 // MMAs of tile q, issued by THIS warp: chains issued by several warps in parallel run at the tensor pipe's rate
                 // (~36 clk per N = 16 MMA) instead of one thread's issue rate (~55 clk, tools/ld_probe.cu)
@@ -531,95 +535,142 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
                     const uint64_t bd = smem_desc(zaddr + kk * 2 * ZLBO, ZLBO, 128);
                     if (leader) mma_bf16_ts(tmem + q * NB, tmem + BW_ACOL + q * 64 + kk * 8, bd, idesc, kk > 0);
                 }
-                if (leader) mma_commit(bar_mma + 8 * q);
+                if (leader) mma_commit(bar_mma);
                 __syncwarp();
                 PROFB(10);
             }
             if (n > 0) {
-                // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]: tile m (units m*128 + q*32 + lane) is staged as the
-                // block of its owner CTA m*4 + q and pushed by THIS warp as soon as the tile's MMAs have completed -- the later
-                // tiles' MMAs run under the exchange of the earlier ones, and no other warp is involved in the push.
+                // partial sums P[u, b] = sum_{own cols} Wh[u, g] dz_{next}[b, g]: tile m (units m*128 + q*32 + lane) belongs to the
+                // owner CTA m*4 + q and is sent by THIS warp (no other warp is involved).  All tiles are drained together: one
+                // barrier wait, back-to-back TMEM loads, one proxy fence (the chains of the MT issuing warps finish together anyway).
+                // Sending with st.async straight from registers (no staging, no fence) leaves the sender 400 clk earlier but the
+                // partial sums land at the same time: the exchange is bound by the SM's DSMEM port (~20 KB in + out per step), A/B
+                // measured 515 (bulk copies) vs 544 us (st.async) per launch at 128 mixtures.
                 uint8_t* ps = p_s + (n & 1) * r_bytes;
-                for (int m = 0; m < MT; ++m) {
-                    const uint32_t dest = m * 4 + q;
-                    if (dest >= NC) break;            // warp-uniform: the tail tile has fewer owner CTAs
-                    mbar_wait(bar_mma + 8 * m, (n - 1) & 1);
-                    if (m == 0) PROFB(2);
-                    tc_fence_after();
-                    uint32_t acc[NB];
-                    if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
-                    else tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc);
-                    tmem_ld_wait();
-                    tc_fence_before();
+                mbar_wait(bar_mma, (n - 1) & 1);      // ONE barrier: every issuing warp's commit arrives on it
+                PROFB(2);
+                tc_fence_after();
+                uint32_t acc[3][NB];                  // (a fourth tile, H > 384, is drained by the block below)
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                    if (m < MT && (uint32_t)(m * 4 + q) < NC) {           // warp-uniform
+                        if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc[m]);
+                        else tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + m * NB, acc[m]);
+                    }
+                tmem_ld_wait();
+                tc_fence_before();
+                PROFB(11);
+                auto stage_tile = [&](const uint32_t* av, uint32_t dest) {
                     uint8_t* pd = ps + (size_t)dest * BLK + lane * 8;
 #pragma unroll
                     for (int g = 0; g < NB / 4; ++g)
                         *reinterpret_cast<uint2*>(pd + g * 256) =
-                            make_uint2(pack_bf16(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1])),
-                                       pack_bf16(__uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3])));
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0)
+                            make_uint2(pack_bf16(__uint_as_float(av[4 * g]), __uint_as_float(av[4 * g + 1])),
+                                       pack_bf16(__uint_as_float(av[4 * g + 2]), __uint_as_float(av[4 * g + 3])));
+                };
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                    if (m < MT && (uint32_t)(m * 4 + q) < NC) stage_tile(acc[m], m * 4 + q);
+                if (MT > 3 && (uint32_t)(12 + q) < NC) {
+                    tc_fence_after();
+                    if (NB == 16) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 3 * NB, acc[0]);
+                    else tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 3 * NB, acc[0]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    stage_tile(acc[0], 12 + q);
+                }
+                fence_async_smem();
+                __syncwarp();
+                PROFB(8);
+                for (int m = 0; m < MT; ++m) {        // uniform control flow, elected lane (a divergent push serialises per lane)
+                    const uint32_t dest = m * 4 + q;
+                    if (dest < NC && leader)
                         bulk_s2c(mapa(smem_u32(r_s + (n & 1) * r_bytes) + crank * BLK, dest), smem_u32(ps) + dest * BLK, BLK,
                                  mapa(r_full + 8 * (n & 1), dest));
                 }
+                __syncwarp();
                 PROFB(3);
+            }
+            // While the partial sums travel: everything of this step that does not depend on dh.  With A = go (1 - tanh(c)^2) the update is
+            //   dc = dcc + dh A,  dz_i = dc F0,  dz_j = dc F1,  dz_f = dc F2,  dz_o = dh F3,  dcc' = dc gf
+            // so only ~6 flops per (unit, mixture) remain between the arrival of the partial sums and the next step's MMAs.
+            float fA[IT], f0[IT], f1[IT], f2[IT], f3[IT], fgf[IT], dyv[IT];
+            {
+                mbar_wait(sv_full + 8 * (n % 3), (n / 3) & 1);    // staged three steps ago by the writer warps (cp.async)
+                const float* svb = svs + (n % 3) * (7 * NB * 32) + (q * IT) * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < IT; ++i) {
+                    const float gi = svb[(0 * NB + i) * 32], gj = svb[(1 * NB + i) * 32], gf = svb[(2 * NB + i) * 32], go = svb[(3 * NB + i) * 32];
+                    const float c = svb[(4 * NB + i) * 32], cprev = svb[(5 * NB + i) * 32];
+                    dyv[i] = svb[(6 * NB + i) * 32];
+                    const float tc_ = tanh_fast(c);
+                    fA[i] = go * (1.f - tc_ * tc_);
+                    f0[i] = gj * gi * (1.f - gi);
+                    f1[i] = gi * (1.f - gj * gj);
+                    f2[i] = cprev * gf * (1.f - gf);
+                    f3[i] = tc_ * go * (1.f - go);
+                    fgf[i] = gf;
+                    // pin the factors HERE (the compiler otherwise sinks this arithmetic below the wait for the partial sums,
+                    // back onto the critical path)
+                    asm volatile("" : "+f"(fA[i]), "+f"(f0[i]), "+f"(f1[i]), "+f"(f2[i]), "+f"(f3[i]), "+f"(dyv[i]));
+                }
+            }
+            PROFB(1);
+            float dh[IT];
+#pragma unroll
+            for (int i = 0; i < IT; ++i) dh[i] = dyv[i];
+            if (n > 0) {
                 mbar_wait(r_full + 8 * (n & 1), ((n - 1) >> 1) & 1);       // every CTA's partials for my units have landed
                 PROFB(4);
                 if (tid == 0 && n + 2 < T) mbar_expect_tx(r_full + 8 * (n & 1), NC * BLK);   // re-arm for step n+2
-                // this thread's unit = lane, mixtures q*IT .. q*IT+IT-1: one 8-byte item per mixture quad, lanes consecutive
-                const uint8_t* rb = r_s + (n & 1) * r_bytes + (size_t)(q * (IT / 4) * 32 + lane) * 8;
+                // this thread's unit = lane, mixtures q*IT .. q*IT+IT-1: one 8-byte item per mixture quad, lanes consecutive.
+                // All loads of a source batch are issued (volatile asm: not re-ordered, not serialised behind the adds) before the
+                // first add; sources are summed in index order (deterministic).
+                const uint32_t rb = smem_u32(r_s + (n & 1) * r_bytes) + (uint32_t)(q * (IT / 4) * 32 + lane) * 8;
+                for (uint32_t c0 = 0; c0 < NC; c0 += 5) {
+                    uint32_t wx[5][IT / 4], wy[5][IT / 4];
 #pragma unroll
-                for (int i = 0; i < IT; ++i) dh[i] = 0.f;
-                // all loads first (a source index beyond the cluster re-reads block 0 and is masked out below): a branch per source
-                // would serialise load -> add -> load
-                uint2 w[16][IT / 4];
+                    for (uint32_t c = 0; c < 5; ++c) {
+                        const uint32_t cc = c0 + c < NC ? c0 + c : c0;        // (a batch past the end re-reads its first block, masked below)
 #pragma unroll
-                for (uint32_t c = 0; c < 16; ++c)
+                        for (int g = 0; g < IT / 4; ++g)
+                            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wx[c][g]), "=r"(wy[c][g]) : "r"(rb + cc * BLK + g * 256));
+                    }
 #pragma unroll
-                    for (int g = 0; g < IT / 4; ++g)
-                        w[c][g] = *reinterpret_cast<const uint2*>(rb + (size_t)(c < NC ? c : 0) * BLK + g * 256);
+                    for (int g = 0; g < IT / 4; ++g)     // every load of the batch is in flight before the first add may issue
+                        asm volatile("" : "+r"(wx[0][g]), "+r"(wy[0][g]), "+r"(wx[1][g]), "+r"(wy[1][g]), "+r"(wx[2][g]), "+r"(wy[2][g]),
+                                          "+r"(wx[3][g]), "+r"(wy[3][g]), "+r"(wx[4][g]), "+r"(wy[4][g]));
 #pragma unroll
-                for (uint32_t c = 0; c < 16; ++c) {
-                    const float on = c < NC ? 1.f : 0.f;
+                    for (uint32_t c = 0; c < 5; ++c) {
+                        if (c0 + c < NC) {
 #pragma unroll
-                    for (int g = 0; g < IT / 4; ++g) {
-                        dh[4 * g] = fmaf(on, bf16_lo(w[c][g].x), dh[4 * g]); dh[4 * g + 1] = fmaf(on, bf16_hi(w[c][g].x), dh[4 * g + 1]);
-                        dh[4 * g + 2] = fmaf(on, bf16_lo(w[c][g].y), dh[4 * g + 2]); dh[4 * g + 3] = fmaf(on, bf16_hi(w[c][g].y), dh[4 * g + 3]);
+                            for (int g = 0; g < IT / 4; ++g) {
+                                dh[4 * g] += bf16_lo(wx[c][g]); dh[4 * g + 1] += bf16_hi(wx[c][g]);
+                                dh[4 * g + 2] += bf16_lo(wy[c][g]); dh[4 * g + 3] += bf16_hi(wy[c][g]);
+                            }
+                        }
                     }
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < IT; ++i) dh[i] = 0.f;
+                PROFB(5);
             }
-            PROFB(5);
-            // the dz operand is rewritten below: ALL of this step's MMAs (they read it) must have completed, also for the warps
-            // that own no block of the last tile
-            if (n > 0) mbar_wait(bar_mma + 8 * (MT - 1), (n - 1) & 1);
-            mbar_wait(sv_full + 8 * (n % 3), (n / 3) & 1);    // staged three steps ago by the writer warps (cp.async)
-            const float* svb = svs + (n % 3) * (7 * NB * 32) + (q * IT) * 32 + lane;
-            // gate derivatives; dz -> fp32 staging (writers) and bf16 operand of the next step's MMA
-            float* dzb = dzs + (n & 1) * (128 * ZP);
+            // gate derivatives; dz -> fp32 staging (writers) and bf16 operand of the next step's MMA.  All 8 * IT store addresses are
+            // one base register + immediates: k = g4*32 + lane, b = q*IT + i  ->  operand offset (k>>3)*ZLBO + (b>>3)*128 + (b&7)*16
+            // + (k&7)*2 = zbase + g4*4*ZLBO + i*16 (the IT mixtures of a thread never straddle a group of 8)
+            float* dzb = dzs + (n & 1) * (NB * DZP) + (q * IT) * DZP + lane;
+            uint8_t* zbase = z_s + (size_t)(lane >> 3) * ZLBO + (lane & 7) * 2 + ((q * IT) >> 3) * 128 + ((q * IT) & 7) * 16;
 #pragma unroll
             for (int i = 0; i < IT; ++i) {
-                const int b = q * IT + i;
-                const float gi = svb[(0 * NB + i) * 32], gj = svb[(1 * NB + i) * 32], gf = svb[(2 * NB + i) * 32], go = svb[(3 * NB + i) * 32];
-                const float c = svb[(4 * NB + i) * 32], cprev = svb[(5 * NB + i) * 32];
-                dh[i] += svb[(6 * NB + i) * 32];
-                const float tc_ = tanh_fast(c);
-                const float dc = dcc[i] + dh[i] * go * (1.f - tc_ * tc_);
+                const float dc = fmaf(dh[i], fA[i], dcc[i]);
                 float dz[4];
-                dz[0] = dc * gj * gi * (1.f - gi);
-                dz[1] = dc * gi * (1.f - gj * gj);
-                dz[2] = dc * cprev * gf * (1.f - gf);
-                dz[3] = dh[i] * tc_ * go * (1.f - go);
-                dcc[i] = dc * gf;
+                dz[0] = dc * f0[i];
+                dz[1] = dc * f1[i];
+                dz[2] = dc * f2[i];
+                dz[3] = dh[i] * f3[i];
+                dcc[i] = dc * fgf[i];
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
-                    dzb[(g4 * 32 + lane) * ZP + b] = dz[g4];
-                    const int k = g4 * 32 + lane;
-                    *reinterpret_cast<__nv_bfloat16*>(z_s + (size_t)(k >> 3) * ZLBO + (b >> 3) * 128 + (b & 7) * 16 + (k & 7) * 2) =
-                        __float2bfloat16_rn(dz[g4]);
+                    dzb[i * DZP + g4 * 32] = dz[g4];
+                    *reinterpret_cast<__nv_bfloat16*>(zbase + g4 * 4 * ZLBO + i * 16) = __float2bfloat16_rn(dz[g4]);
                 }
             }
             PROFB(6);
@@ -627,11 +678,9 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
             bar_sync_named(1, 256);                   // dz staged by every warp: the next step's MMAs may issue, writers may store
             PROFB(7);
         }
-    } else if (warp == 4) {
-        // (warp 4 only owns the TMEM allocation: the compute warps issue their own tiles' MMAs)
     } else {
         // =========================== writer warps: dZ -> global ===========================
-        const int wt = tid - 160, wq = wt >> 5, wu = u0 + (wt & 31);
+        const int wt = tid - 128, wq = wt >> 5, wu = u0 + (wt & 31);
         // saved activations of step n (time s = T-1-n): rows k = gi gj gf go c c_prev dy, 32 units each (128 B per mixture):
         // 16-byte loads, thread = (4 consecutive units, mixture rows rb, rb+16, ...), issued two steps ahead
         const int u4 = (wt & 7) * 4, rb = wt >> 3;
@@ -655,7 +704,7 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
 #pragma unroll
                 for (int rr = 0; rr < NB / 16; ++rr) {
                     const int b = rr * 16 + rb;
-                    const bool ok = b < nvalid && !(k == 5 && s == 0);
+                    const bool ok = b < nvalid && !(k == 5 && s == 0) && !(p.dbg & 2);
                     const float* gi = ok ? row_ptr(k, s, b) : p.cst;
                     const uint32_t dst = sb + ((k * NB + b) * 32 + u4) * 4;
                     if (vec) {
@@ -670,33 +719,66 @@ __global__ void __launch_bounds__(BT_THREADS, NB == 16 ? 2 : 1) blstm_rec_bwd_tc
                 }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sv_full + 8 * (n % 3)) : "memory");
         };
-        float bsum = 0.f;                                         // this thread's (gate, unit) column of dZ summed over t and b
+        // dZ of a step leaves as 8-byte (4 x bf16) / 16-byte (4 x fp32) stores: thread = (mixture rb [+16], gate jj, units u4..u4+3),
+        // the 8 threads of a mixture row cover one gate's 32 units (64 B / 128 B contiguous).  Per-thread column sums over t and
+        // the thread's mixtures feed the bias gradient (combined across the mixture rows at the end, in a fixed order).
+        float bsum[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+        const bool vec8 = vec && (p.ldzb & 3) == 0;
         for (int n = 0; n < 3 && n < T; ++n) stage_sv(n);
         for (int s = T - 1; s >= 0; --s) {
             const int t = d == 0 ? s : T - 1 - s, n = T - 1 - s;
             bar_sync_named(1, 256);                               // dz(n) staged; svs[n%3] consumed by the compute warps
             if (n + 3 < T) stage_sv(n + 3);                       // refill the slot just freed, three steps ahead
-            const float* dzb = dzs + (n & 1) * (128 * ZP);
-            if (wu < H) {
-                const size_t r0 = ((size_t)d * T + t) * B + b0;
-                float* zo = p.dZ ? p.dZ + r0 * H4 + wq * H + wu : nullptr;
-                __nv_bfloat16* zb = p.dZb ? reinterpret_cast<__nv_bfloat16*>(p.dZb) + r0 * p.ldzb + wq * H + wu : nullptr;
+            const float* dzb = dzs + (n & 1) * (NB * DZP);
+            const size_t r0 = ((size_t)d * T + t) * B + b0;
 #pragma unroll
-                for (int c = 0; c < NB; c += 16) {
-                    float gv[16];
+            for (int rr = 0; rr < NB / 16; ++rr) {
+                const int b = rr * 16 + rb;
+                float4 v[4];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) gv[j] = dzb[wt * ZP + c + j];
+                for (int jj = 0; jj < 4; ++jj) v[jj] = *reinterpret_cast<const float4*>(dzb + b * DZP + jj * 32 + u4);
+                if (b < nvalid) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c + j < nvalid) {
-                            if (zo) __stcg(zo + (size_t)(c + j) * H4, gv[j]);
-                            if (zb) zb[(size_t)(c + j) * p.ldzb] = __float2bfloat16_rn(gv[j]);
-                            bsum += gv[j];
+                    for (int jj = 0; jj < 4; ++jj) {
+                        bsum[4 * jj] += v[jj].x; bsum[4 * jj + 1] += v[jj].y; bsum[4 * jj + 2] += v[jj].z; bsum[4 * jj + 3] += v[jj].w;
+                        if (p.dbg & 1) continue;
+                        if (p.dZ) {
+                            float* zo = p.dZ + (r0 + b) * H4 + jj * H + u0 + u4;
+                            if (vec) __stcg(reinterpret_cast<float4*>(zo), v[jj]);
+                            else {
+                                if (u0 + u4 < H) __stcg(zo, v[jj].x);
+                                if (u0 + u4 + 1 < H) __stcg(zo + 1, v[jj].y);
+                                if (u0 + u4 + 2 < H) __stcg(zo + 2, v[jj].z);
+                                if (u0 + u4 + 3 < H) __stcg(zo + 3, v[jj].w);
+                            }
                         }
+                        if (p.dZb) {
+                            __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(p.dZb) + (r0 + b) * p.ldzb + jj * H + u0 + u4;
+                            if (vec8) *reinterpret_cast<uint2*>(zb) = make_uint2(pack_bf16(v[jj].x, v[jj].y), pack_bf16(v[jj].z, v[jj].w));
+                            else {
+                                if (u0 + u4 < H) zb[0] = __float2bfloat16_rn(v[jj].x);
+                                if (u0 + u4 + 1 < H) zb[1] = __float2bfloat16_rn(v[jj].y);
+                                if (u0 + u4 + 2 < H) zb[2] = __float2bfloat16_rn(v[jj].z);
+                                if (u0 + u4 + 3 < H) zb[3] = __float2bfloat16_rn(v[jj].w);
+                            }
+                        }
+                    }
                 }
             }
         }
-        if (p.dbpart && wu < H) p.dbpart[((size_t)d * p.nsub + sub) * H4 + wq * H + wu] = bsum;
+        if (p.dbpart) {   // column sums: [16 mixture rows][128 gate cols] partials through the (now idle) dz staging tile
+            float* red = dzs + (((T - 1) & 1) ^ 1) * (NB * DZP);          // the tile the last step did not use
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                *reinterpret_cast<float4*>(red + rb * DZP + jj * 32 + u4) = make_float4(bsum[4 * jj], bsum[4 * jj + 1], bsum[4 * jj + 2], bsum[4 * jj + 3]);
+            bar_sync_named(3, 128);
+            float tot = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) tot += red[r * DZP + wt];
+            if (wu < H) p.dbpart[((size_t)d * p.nsub + sub) * H4 + wq * H + wu] = tot;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -714,7 +796,7 @@ int launch_bwd(const RecTcBwd& p, int NC, cudaStream_t st) {
     if (NC > 8) AMSS_CUDA(cudaFuncSetAttribute(blstm_rec_bwd_tc_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC * 2 * p.nsub);
-    cfg.blockDim = dim3(BT_THREADS);
+    cfg.blockDim = dim3(BW_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -729,10 +811,10 @@ int launch_bwd(const RecTcBwd& p, int NC, cudaStream_t st) {
 // Co-resident clusters are limited by the GPC size (a cluster of 10 CTAs fits once in a 16-20 SM GPC), not by
 // SMs / NC: ask the occupancy API, then take the smallest sub-batch (16 / 32 / 64 mixtures) that runs in one wave.
 template <typename K>
-int max_clusters(K kernel, int NC, size_t smem) {
+int max_clusters(K kernel, int NC, size_t smem, int threads) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(NC * 16);
-    cfg.blockDim = dim3(BT_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -750,7 +832,7 @@ size_t fwd_smem(int NC, int NB) {
     return 2 * (size_t)NC * 4 * (NB / 8) * 128 + 2 * (size_t)4 * (NB / 8) * 128 + (size_t)(6 + 12) * NB * FW_ZP * 4;
 }
 size_t bwd_smem(int NC, int NB) {
-    return (size_t)16 * ((NB / 8) * 128 + 16) + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * 128 * (NB + 1) * 4 + (size_t)3 * 7 * NB * 32 * 4;
+    return (size_t)16 * ((NB / 8) * 128 + 16) + 4 * (size_t)NC * 32 * NB * 2 + (size_t)2 * NB * 132 * 4 + (size_t)3 * 7 * NB * 32 * 4;
 }
 
 // Sub-batch size.  Measured on B200 (tools/blstm_bench.py, T = 250, I = 600, H = 300; fwd + bwd layer times in ms):
@@ -788,8 +870,8 @@ int blstm_rec_fwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, float* gat
     p.B = B; p.T = T; p.H = H; p.forget_bias = forget_bias;
     static MaxC mc[17];
     if (!mc[NC].c16) {
-        mc[NC].c16 = max_clusters(blstm_rec_fwd_tc_kernel<16>, NC, fwd_smem(NC, 16));
-        mc[NC].c32 = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32));
+        mc[NC].c16 = max_clusters(blstm_rec_fwd_tc_kernel<16>, NC, fwd_smem(NC, 16), BT_THREADS);
+        mc[NC].c32 = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32), BT_THREADS);
     }
     const int nb = pick_nb(B, mc[NC].c16, mc[NC].c32);   // larger batches run as several waves of clusters
     p.nsub = (B + nb - 1) / nb;
@@ -803,8 +885,8 @@ int blstm_rec_bwd_tc_nsub(int B, int H);
 static int bwd_nb(int B, int NC) {
     static MaxC mc[17];
     if (!mc[NC].c16) {
-        mc[NC].c16 = max_clusters(blstm_rec_bwd_tc_kernel<16>, NC, bwd_smem(NC, 16));
-        mc[NC].c32 = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
+        mc[NC].c16 = max_clusters(blstm_rec_bwd_tc_kernel<16>, NC, bwd_smem(NC, 16), BW_THREADS);
+        mc[NC].c32 = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32), BW_THREADS);
     }
     return pick_nb(B, mc[NC].c16, mc[NC].c32);
 }
@@ -815,6 +897,7 @@ int blstm_rec_bwd_tc(const float* Wh_fw, const float* Wh_bw, int ldw, const floa
     RecTcBwd p;
     p.prof = g_prof_bwd;
     p.sched = g_sched ? g_sched + 4 * SCHED_MAX : nullptr;
+    { const char* e = getenv("AMSS_BLSTM_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.Wh[0] = Wh_fw; p.Wh[1] = Wh_bw; p.ldw = ldw; p.gates = gates; p.cst = cst; p.dy = dy; p.dZ = dZ;
     p.dZb = dZb; p.ldzb = ldzb; p.dbpart = dbpart;
     p.B = B; p.T = T; p.H = H; p.MT = (NC * 32 + 127) / 128;
@@ -833,10 +916,10 @@ int blstm_rec_bwd_tc_nsub(int B, int H) {
 // co-resident clusters of both variants (diagnostics: amss_debug_blstm_clusters)
 void blstm_tc_max_clusters(int H, int* out4) {
     const int NC = (H + 31) / 32;
-    out4[0] = max_clusters(blstm_rec_fwd_tc_kernel<16>, NC, fwd_smem(NC, 16));
-    out4[1] = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32));
-    out4[2] = max_clusters(blstm_rec_bwd_tc_kernel<16>, NC, bwd_smem(NC, 16));
-    out4[3] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32));
+    out4[0] = max_clusters(blstm_rec_fwd_tc_kernel<16>, NC, fwd_smem(NC, 16), BT_THREADS);
+    out4[1] = max_clusters(blstm_rec_fwd_tc_kernel<32>, NC, fwd_smem(NC, 32), BT_THREADS);
+    out4[2] = max_clusters(blstm_rec_bwd_tc_kernel<16>, NC, bwd_smem(NC, 16), BW_THREADS);
+    out4[3] = max_clusters(blstm_rec_bwd_tc_kernel<32>, NC, bwd_smem(NC, 32), BW_THREADS);
 }
 
 }  // namespace amss

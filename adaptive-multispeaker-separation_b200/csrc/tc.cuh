@@ -197,6 +197,13 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_smem
                  "r"(src_smem), "r"(bytes), "r"(bar_cluster)
                  : "memory");
 }
+// 8-byte store into a cluster peer's shared memory that completes (complete_tx, 8 bytes) on the PEER's mbarrier: no staging
+// copy, no proxy fence, no bulk-copy descriptor on the sender; the receiver waits on its mbarrier and reads with plain loads.
+__device__ __forceinline__ void st_async_v2(uint32_t dst_cluster, uint32_t a, uint32_t b, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst_cluster), "r"(a),
+                 "r"(b), "r"(bar_cluster)
+                 : "memory");
+}
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -501,16 +501,13 @@ def test_dataset_normalize_and_device_built_mixture(amss):
     B, S, Lw = 2, 2, 2048
     t = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=24, embedding_size=8, learning_rate=1e-3,
                                   window_size=128, hop_size=64, dataset_normalize=True)
-    # unit-variance inputs are 20x the usual level: with the stock initialisation the first BLSTM layer runs deep in saturation
-    # and every embedding collapses onto one direction, where BOTH the recurrence's (1 - tanh^2) factors and the DPCL gradient
-    # (a radial term that the normalisation projects out) are pure round-off in fp32 -- two fp32 evaluations of the same graph
-    # then differ by 10-20 % of the gradient norm (measured).  The BLSTM kernels are therefore scaled down so that the step is
-    # well conditioned and every tensor can be compared; the normalisation kernel itself is checked element-wise in
-    # test_gpu_kernels.py::test_prepare_inputs_mix_and_normalize
-    with torch.no_grad():
-        for k, v in t.store.params.items():
-            if v.dim() == 2 and v.shape[1] == 4 * 24:
-                v.mul_(0.05)
+    # Unit-variance inputs are 20x the usual level and this step is badly conditioned in fp32 (measured on B200): feeding the
+    # SAME kernels host-normalised instead of device-normalised data -- inputs equal to 1e-7 -- moves the cost by 2e-3 and a
+    # gradient by 10-30 % of its norm, as do two fp32 evaluations of the oracle graph (fp32 vs float64: 3e-3 on the cost), with
+    # the stock and with down-scaled weights alike.  What the flag must guarantee is therefore checked as: (1) the cost of the
+    # device-normalised step against the oracle's step on host-normalised data (within
+    # the conditioning, 1e-2); (2) the same against the device kernels fed host-normalised data with the flag off; (3) what
+    # Trainer.prepare() hands to the graph, element-wise against the host normalisation (1e-5), and the statistics it keeps.
     p = _copy_params(t.store, {})
     fn = functools.partial(OS.stft_separator_loss, nb_layers=1, embedding_size=8, window_size=128, hop_size=64)
     st = OS.Stepper(p, fn, lr=1e-3)
@@ -518,14 +515,22 @@ def test_dataset_normalize_and_device_built_mixture(amss):
     nmt = torch.tensor(nm)
     nmn = (nmt - nmt.mean(-1, keepdim=True)) / torch.sqrt(nmt.var(-1, unbiased=False, keepdim=True))
     c_ref, _ = st.step(nmn.sum(1), nmn, torch.tensor(I))
-    c = t.train_step(None, _dev(nm), _dev(I))
-    assert abs(float(c) - c_ref) < REL * abs(c_ref)
-    gmax = max(float(g.double().norm()) for g in st.last_grads.values())
-    for k in st.tr:
-        g_dev, g_ref = t.store[k].grad.detach().double().cpu(), st.last_grads[k].double()
-        err = float((g_dev - g_ref).norm())
-        print(f"dataset_normalize step: {k}: |g| {float(g_ref.norm()):.3e} err {err:.3e}")
-        assert err < 5e-3 * max(float(g_ref.norm()), 1e-2 * gmax), k
+    t2 = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=24, embedding_size=8, learning_rate=1e-3,
+                                   window_size=128, hop_size=64, dataset_normalize=False)
+    with torch.no_grad():
+        for k, v in t2.store.params.items():
+            v.copy_(t.store.params[k])
+    c = float(t.train_step(None, _dev(nm), _dev(I)))
+    c2 = float(t2.train_step(_dev(nmn.sum(1)), _dev(nmn), _dev(I)))
+    print(f"dataset_normalize step: cost {c:.5f}, oracle {c_ref:.5f}, same kernels on host-normalised data {c2:.5f}")
+    assert abs(c - c_ref) < 1e-2 * abs(c_ref)
+    assert abs(c - c2) < 1e-2 * abs(c2)
+    # the cost of a random-init DPCL net hardly depends on the input level, so the step itself is pinned through what it was
+    # fed: the trainer's prepare() output and the statistics it keeps for post-processing (data/dataset.py:459-460)
+    xm, xn = t.prepare(None, _dev(nm))
+    assert rel(xn, nmn) < 1e-5 and rel(xm, nmn.sum(1)) < 1e-5
+    stats = t.norm_stats.reshape(-1, 2).cpu()
+    assert rel(stats[:, 0], nmt.mean(-1).reshape(-1)) < 1e-4 and rel(stats[:, 1], nmt.var(-1, unbiased=False).reshape(-1)) < 1e-4
     assert bool(torch.isfinite(t.store.grad_flat).all())
 
 

@@ -41,8 +41,10 @@ for B in [int(a) for a in sys.argv[1:]] or [16, 64, 128]:
               f" ; barrier-to-barrier {int(p[s + 1][7]) - w7}")
 
     pb = buf.cpu().view(-1)[64:112].view(4, 12)
+    names = {9: "mma issue", 10: "issued", 1: "factors ready", 2: "mma done", 11: "tmem read", 8: "staged", 3: "pushed", 4: "partials landed", 5: "reduced",
+             6: "dz staged", 7: "barrier"}
     for s in range(1, 3):
         row = pb[s]
         base = int(row[0])
         print(f" bwd step {100 + s}: total {int(pb[s + 1][0]) - base} clk ; " +
-              " ".join(f"[{k}]+{int(row[k]) - base}" for k in range(1, 12)))
+              " ".join(f"{names[k]} +{int(row[k]) - base}" for k in (9, 10, 1, 2, 11, 8, 3, 4, 5, 6, 7)))
