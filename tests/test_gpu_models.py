@@ -495,6 +495,36 @@ def test_trainer_train_runs_the_reference_loop(amss, tmp_path):
     assert hist["test_cost"] == hist["test_cost"]
 
 
+def test_trainer_train_reads_the_reference_tfrecords(amss, tmp_path):
+    """Trainer.train driven by TFDataset over '<split>_<sex>.tfrecords' files in the reference's format
+    (data/dataset.py:398-442 writer, :520-645 pipeline): the loop sees every batch the dataset yields, the speaker ids reach
+    the graph, and a second pass over the same files with the same seed reproduces the costs."""
+    import os
+    import numpy as np
+    from amss_b200 import dataset as D
+    tr, mo = amss["trainer"], amss["models"]
+    rng = np.random.RandomState(5)
+    chunk = 1024
+    for split in ("train", "valid", "test"):
+        for si, sex in enumerate(("M", "F")):
+            utts = [((rng.randn(int(rng.choice([1500, 2300, 3100]))) * 0.05).astype(np.float32), si * 4 + int(rng.randint(4)))
+                    for _ in range(8)]
+            D.write_speaker_file(os.path.join(str(tmp_path), f"{split}_{sex}.tfrecords"), utts)
+    ds = D.TFDataset(str(tmp_path), batch_size=2, chunk_size=chunk, nb_speakers=2, sex=("M", "F"))
+    n_train = sum(1 for _ in ds.train())
+    assert n_train >= 2
+
+    def run(sub):
+        t = tr.STFT_Separator_Trainer(mo.DPCL, nb_layers=1, layer_size=16, embedding_size=4, learning_rate=3e-3,
+                                      window_size=64, hop_size=32, epochs=1, validation_step=1000)
+        return t.train(ds, log_dir=os.path.join(str(tmp_path), sub), runID="tfrec", verbose=False)
+
+    h1, h2 = run("a"), run("b")
+    assert h1["steps"] == n_train and len(h1["train_costs"]) == n_train
+    assert all(np.isfinite(c) for c in h1["train_costs"]) and np.isfinite(h1["test_cost"])
+    assert np.allclose(h1["train_costs"], h2["train_costs"], rtol=1e-5)
+
+
 def test_dataset_normalize_and_device_built_mixture(amss):
     """--dataset_normalize (data/dataset.py:456-460) + x_mix=None: the step equals the oracle's step on host-normalised data."""
     tr, mo = amss["trainer"], amss["models"]
