@@ -104,8 +104,11 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
                  "h"((uint16_t)3)
                  : "memory");
 }
+// Relaxed: the arrival only tells the MMA warp that this warp's TMEM reads are done (ordered by the tcgen05 fence that
+// precedes it); a release arrival made every epilogue warp wait for its outstanding global stores (MEMBAR + ERRBAR were 17 %
+// of the head GEMM's stall samples).
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t result_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(result_smem), "r"(cols) : "memory");
@@ -277,19 +280,24 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
 #pragma unroll 1
                 for (int g = half; g < groups; g += 2) {
                     uint32_t v[GT_EMAX];
+                    const int nb = n0 + g * E;
+                    // the group's bias first: all loads in flight together and under the TMEM load (a load next to each use
+                    // serialised ten L1 / L2 round trips per group -- 35 % of the kernel's stall samples, ncu source page)
+                    float4 bb[GT_EMAX / 4];
+#pragma unroll
+                    for (int c = 0; c < GT_EMAX / 4; ++c)
+                        bb[c] = (add_bias && c < e4) ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                     load_group(tacc + g * E, E, v);
                     tmem_ld_wait();
-                    const int nb = n0 + g * E;
                     float ss = 0.f;
 #pragma unroll
                     for (int c = 0; c < GT_EMAX / 4; ++c)
                         if (c < e4) {
                             if (add_bias) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + c);
-                                v[4 * c] = __float_as_uint(__uint_as_float(v[4 * c]) + bb.x);
-                                v[4 * c + 1] = __float_as_uint(__uint_as_float(v[4 * c + 1]) + bb.y);
-                                v[4 * c + 2] = __float_as_uint(__uint_as_float(v[4 * c + 2]) + bb.z);
-                                v[4 * c + 3] = __float_as_uint(__uint_as_float(v[4 * c + 3]) + bb.w);
+                                v[4 * c] = __float_as_uint(__uint_as_float(v[4 * c]) + bb[c].x);
+                                v[4 * c + 1] = __float_as_uint(__uint_as_float(v[4 * c + 1]) + bb[c].y);
+                                v[4 * c + 2] = __float_as_uint(__uint_as_float(v[4 * c + 2]) + bb[c].z);
+                                v[4 * c + 3] = __float_as_uint(__uint_as_float(v[4 * c + 3]) + bb[c].w);
                             }
 #pragma unroll
                             for (int e = 0; e < 4; ++e) ss = fmaf(__uint_as_float(v[4 * c + e]), __uint_as_float(v[4 * c + e]), ss);
@@ -329,6 +337,11 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                 const bool more = ci + 2 < chunks;
                 if (more) tmem_ld32(tacc + (ci + 2) * 32, vn);
                 const int nb = n0 + ci * 32;
+                float4 bb[8];                                       // the chunk's bias, all loads in flight together
+#pragma unroll
+                for (int gq = 0; gq < 8; ++gq)
+                    bb[gq] = (add_bias && vec_ok && nb + 4 * gq + 4 <= p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + gq)
+                                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ctma && ci * 32 + 32 <= p.bn) {                 // (a chunk cut by the tile edge takes the direct path)
                     if (lane == 0) tma_store_wait_read();           // the previous store has finished reading the block
                     __syncwarp();
@@ -336,10 +349,7 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                     for (int gq = 0; gq < 8; ++gq) {
                         float4 o = make_float4(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1]),
                                                __uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3]));
-                        if (add_bias && nb + 4 * gq + 4 <= p.N) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + gq);
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                        }
+                        if (add_bias && nb + 4 * gq + 4 <= p.N) { o.x += bb[gq].x; o.y += bb[gq].y; o.z += bb[gq].z; o.w += bb[gq].w; }
                         // 128-byte rows, SWIZZLE_128B: 16-byte chunk gq of row r sits at chunk gq ^ (r & 7)
                         *reinterpret_cast<float4*>(stg + lane * 128 + ((gq ^ (lane & 7)) << 4)) = o;
                     }
@@ -354,10 +364,7 @@ __device__ __forceinline__ void gemm_tc_body(const GtParams& p) {
                         for (int gq = 0; gq < 8; ++gq) {
                             float4 o = make_float4(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1]),
                                                    __uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3]));
-                            if (add_bias) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + gq);
-                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                            }
+                            if (add_bias) { o.x += bb[gq].x; o.y += bb[gq].y; o.z += bb[gq].z; o.w += bb[gq].w; }
                             if (p.accumulate) { const float4 old = dst[gq]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
                             dst[gq] = o;
                         }
