@@ -255,32 +255,37 @@ sparse_filter_grad_kernel(const float* __restrict__ vals, const int64_t* __restr
 // almost completely: the union (<= pool + W - 1 samples) is staged in shared memory ONCE and every filter reads its W taps
 // from there at its own offset -- consecutive threads read consecutive words.  The per-atom global traffic of the
 // one-warp-per-atom kernels above (2 x 4 KB from L2 per atom) becomes one 5 KB span per SG_F atoms.  The (row, frame) list
-// is walked in blocks of SG_AB pairs: positions / values of a block are fetched up front, and the span of pair i+1 is in
-// flight (cp.async, zero-filled outside the signal) while pair i is accumulated: one __syncthreads per pair, no exposed
-// global latency.  Thread t owns taps k = t, t + 256, t + 512, t + 768.
+// is walked in blocks of SG_AB pairs: positions / values of a block are fetched up front, and the spans of the next SG_NS - 2
+// pairs are in flight (cp.async ring, zero-filled outside the signal) while pair i is accumulated: one __syncthreads per pair
+// (with a single span in flight every pair paid most of an L2 round trip: 3.2 -> 1.x ms for the analysis backward).  Thread t owns taps k = t, t + 256, t + 512, t + 768.
 constexpr int SG_F = 8;
 constexpr int SG_SPAN = 2560;            // staged samples per pair (a longer span takes the direct global path)
 constexpr int SG_AB = 64;                // (row, frame) pairs per block
+constexpr int SG_NS = 4;                 // span buffers: spans i+1 .. i+SG_NS-2 are in flight while pair i is accumulated
 
-struct SgBlock {
-    int pos[SG_AB][SG_F];
+struct __align__(16) SgBlock {
+    int pos[SG_AB][SG_F];        // 16-byte aligned rows (SG_F = 8): a pair's positions / values are read as two vectors each
     float val[SG_AB][SG_F];
-    int pmin[SG_AB], len[SG_AB];
+    int pmin[SG_AB], len[SG_AB], row[SG_AB], frame[SG_AB];   // (row, frame) split once per pair: no 64-bit division in the loops
 };
 
 // positions (and values) of the CTA's filters for pairs [a, a + cnt): coalesced over the SG_F consecutive filters
 __device__ __forceinline__ void sg_load_block(SgBlock& blk, const float* __restrict__ vals, const int64_t* __restrict__ argmax,
                                               int64_t a, int cnt, int argdiv, int W, int N, int Tp, int n0) {
+    const uint32_t a32 = (uint32_t)a, N32 = (uint32_t)N;         // R * Tp and the per-sample index L * N fit 32 bits (checked on the host)
     for (int u = threadIdx.x; u < cnt * SG_F; u += blockDim.x) {
         const int i = u / SG_F, f = u - i * SG_F, n = n0 + f;
-        const int64_t at = a + i;
-        const int r = (int)(at / Tp), tp = (int)(at - (int64_t)r * Tp);
+        const uint32_t at = a32 + (uint32_t)i;
+        const int r = (int)(at / (uint32_t)Tp), tp = (int)(at - (uint32_t)r * (uint32_t)Tp);
         const bool ok = n < N;
-        blk.pos[i][f] = ok ? (int)(argmax[((size_t)(r / argdiv) * Tp + tp) * N + n] / N) : -1;
+        blk.pos[i][f] = ok ? (int)((uint32_t)argmax[((size_t)(r / argdiv) * Tp + tp) * N + n] / N32) : -1;
         if (vals) blk.val[i][f] = ok ? vals[((size_t)r * Tp + tp) * N + n] : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t at = a32 + (uint32_t)i;
+        blk.row[i] = (int)(at / (uint32_t)Tp);
+        blk.frame[i] = (int)(at - (uint32_t)blk.row[i] * (uint32_t)Tp);
         int lo = 0x7fffffff, hi = -1;
 #pragma unroll
         for (int f = 0; f < SG_F; ++f) { const int q = blk.pos[i][f]; if (q >= 0) { lo = min(lo, q); hi = max(hi, q); } }
@@ -290,29 +295,47 @@ __device__ __forceinline__ void sg_load_block(SgBlock& blk, const float* __restr
     __syncthreads();
 }
 
-// asynchronous copy of sig[r, pmin - pl .. + len) into xs (zero-filled outside [0, L)); one commit group per call
-__device__ __forceinline__ void sg_issue_span(float* xs, const float* __restrict__ sig, int r, int L, int pl, int pmin, int len) {
-    if (len <= SG_SPAN) {
+// asynchronous copy of sig[r, pmin - pl .. + len) into xs (zero-filled outside [0, L)); one commit group per call.
+// vec16 (L % 4 == 0, 16-byte aligned rows): the span is fetched as 16-byte chunks starting at the 4-sample boundary below its
+// first sample -- a chunk is then either entirely inside or entirely outside the row -- and the consumer reads at
+// xs[sg_adj(pmin - pl) + ...]; otherwise sample by sample.
+__device__ __forceinline__ int sg_adj(int base, bool vec16) { return vec16 ? (base & 3) : 0; }
+__device__ __forceinline__ void sg_issue_span(float* xs, const float* __restrict__ sig, int r, int L, int pl, int pmin, int len,
+                                              bool vec16) {
+    if (len > 0 && len <= SG_SPAN) {
         const int base = pmin - pl;
         const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(xs);
-        for (int i = threadIdx.x; i < len; i += blockDim.x) {
-            const int s = base + i;
-            const bool ok = s >= 0 && s < L;
-            const float* src = sig + (size_t)r * L + (ok ? s : 0);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * i), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+        if (vec16) {
+            const int s0 = base - (base & 3), n4 = (len + (base & 3) + 3) >> 2;
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                const int s = s0 + 4 * i;
+                const bool ok = s >= 0 && s < L;
+                const float* src = sig + (size_t)r * L + (ok ? s : 0);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 16u * i), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+            }
+        } else {
+            for (int i = threadIdx.x; i < len; i += blockDim.x) {
+                const int s = base + i;
+                const bool ok = s >= 0 && s < L;
+                const float* src = sig + (size_t)r * L + (ok ? s : 0);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + 4u * i), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+            }
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
+template <int N_> __device__ __forceinline__ void sg_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 // dfilt partials: part[chunk][n][k] = sum over the chunk's (r,tp) of vals[r,tp,n] * sig[r, pos + k - pl]
+template <bool FULLW>   // W == 1024: thread t owns exactly the taps t, t + 256, t + 512, t + 768
 __global__ void __launch_bounds__(256)
 sparse_filter_grad_fs_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax,
                              const float* __restrict__ sig, int R, int argdiv, int L, int W, int N, int Tp,
                              float* __restrict__ part) {
     __shared__ SgBlock blk;
-    __shared__ float xs[2][SG_SPAN];
+    __shared__ __align__(16) float xs[SG_NS][SG_SPAN + 8];
     const int n0 = blockIdx.x * SG_F, chunk = blockIdx.y, chunks = gridDim.y, tid = threadIdx.x, pl = (W - 1) / 2;
+    const bool vec16 = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(sig) & 15) == 0;
     const int64_t natoms = (int64_t)R * Tp;
     const int64_t a0 = natoms * chunk / chunks, a1 = natoms * (chunk + 1) / chunks;
     float acc[SG_F][4];
@@ -322,29 +345,55 @@ sparse_filter_grad_fs_kernel(const float* __restrict__ vals, const int64_t* __re
         for (int j = 0; j < 4; ++j) acc[f][j] = 0.f;
     for (int64_t ab = a0; ab < a1; ab += SG_AB) {
         const int cnt = (int)min((int64_t)SG_AB, a1 - ab);
-        __syncthreads();                                        // the previous block's entries are no longer read
+        __syncthreads();                                        // the previous block's entries / spans are no longer read
         sg_load_block(blk, vals, argmax, ab, cnt, argdiv, W, N, Tp, n0);
-        sg_issue_span(xs[0], sig, (int)(ab / Tp), L, pl, blk.pmin[0], blk.len[0]);
+        for (int i = 0; i < SG_NS - 1; ++i) {                   // prologue: spans 0 .. SG_NS-2 (empty groups past the end)
+            if (i < cnt) sg_issue_span(xs[i], sig, blk.row[i], L, pl, blk.pmin[i], blk.len[i], vec16);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         for (int i = 0; i < cnt; ++i) {
-            const int r = (int)((ab + i) / Tp);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();                                    // span i visible to all; span buffer (i+1)&1 free again
-            if (i + 1 < cnt) sg_issue_span(xs[(i + 1) & 1], sig, (int)((ab + i + 1) / Tp), L, pl, blk.pmin[i + 1], blk.len[i + 1]);
-            const float* xb = xs[i & 1];
+            const int r = blk.row[i];
+            sg_wait_pending<SG_NS - 2>();                       // this thread's copies of span i have landed
+            __syncthreads();                                    // span i visible to all; buffer (i-1) % SG_NS free again
+            if (i + SG_NS - 1 < cnt)
+                sg_issue_span(xs[(i + SG_NS - 1) % SG_NS], sig, blk.row[i + SG_NS - 1], L, pl, blk.pmin[i + SG_NS - 1],
+                              blk.len[i + SG_NS - 1], vec16);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
             const int pmin = blk.pmin[i], len = blk.len[i];
+            const float* xb = xs[i % SG_NS] + sg_adj(pmin - pl, vec16) - pmin + tid;
+            int posv[SG_F];
+            float valv[SG_F];
 #pragma unroll
-            for (int f = 0; f < SG_F; ++f) {
-                const float v = blk.val[i][f];
-                if (v != 0.f) {                                 // warp-uniform
-                    const int off = blk.pos[i][f] - pmin;
+            for (int f4 = 0; f4 < SG_F; f4 += 4) {              // the pair's positions / values: vector loads (broadcast)
+                const int4 pq = *reinterpret_cast<const int4*>(&blk.pos[i][f4]);
+                const float4 vq = *reinterpret_cast<const float4*>(&blk.val[i][f4]);
+                posv[f4] = pq.x; posv[f4 + 1] = pq.y; posv[f4 + 2] = pq.z; posv[f4 + 3] = pq.w;
+                valv[f4] = vq.x; valv[f4 + 1] = vq.y; valv[f4 + 2] = vq.z; valv[f4 + 3] = vq.w;
+            }
+            if (FULLW && len <= SG_SPAN) {                      // W = 1024 taps, span staged: 4 loads + 4 FMAs per filter, no tests
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int k = tid + 256 * j;
-                        if (k < W) {
-                            float x;
-                            if (len <= SG_SPAN) x = xb[off + k];
-                            else { const int s = blk.pos[i][f] + k - pl; x = (s >= 0 && s < L) ? sig[(size_t)r * L + s] : 0.f; }
-                            acc[f][j] = fmaf(v, x, acc[f][j]);
+                for (int f = 0; f < SG_F; ++f) {
+                    const float* xf = xb + posv[f];
+                    const float v = valv[f];
+                    if (v != 0.f) {                             // warp-uniform (a filter beyond N carries value 0)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[f][j] = fmaf(v, xf[256 * j], acc[f][j]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < SG_F; ++f) {
+                    const float v = valv[f];
+                    if (v != 0.f) {                             // warp-uniform
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = tid + 256 * j;
+                            if (k < W) {
+                                float x;
+                                if (len <= SG_SPAN) x = xb[posv[f] + 256 * j];
+                                else { const int s = posv[f] + k - pl; x = (s >= 0 && s < L) ? sig[(size_t)r * L + s] : 0.f; }
+                                acc[f][j] = fmaf(v, x, acc[f][j]);
+                            }
                         }
                     }
                 }
@@ -362,15 +411,17 @@ sparse_filter_grad_fs_kernel(const float* __restrict__ vals, const int64_t* __re
 }
 
 // dvals[r,tp,n] = sum_k dout[r, pos + k - pl] * filt2[k,n]: the CTA's filter taps live in registers for the whole kernel
+template <bool FULLW>
 __global__ void __launch_bounds__(256)
 synthesis_bwd_vals_fs_kernel(const float* __restrict__ dout, const int64_t* __restrict__ argmax,
                              const float* __restrict__ filt2, int R, int S, int L, int W, int N, int Tp,
                              float* __restrict__ dvals) {
     __shared__ SgBlock blk;
-    __shared__ float xs[2][SG_SPAN];
+    __shared__ __align__(16) float xs[SG_NS][SG_SPAN + 8];
     __shared__ float red[2][8][SG_F];
     const int n0 = blockIdx.x * SG_F, chunk = blockIdx.y, chunks = gridDim.y, tid = threadIdx.x, pl = (W - 1) / 2;
     const int lane = tid & 31, warp = tid >> 5;
+    const bool vec16 = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
     float w[SG_F][4];
 #pragma unroll
     for (int f = 0; f < SG_F; ++f)
@@ -385,46 +436,74 @@ synthesis_bwd_vals_fs_kernel(const float* __restrict__ dout, const int64_t* __re
         const int cnt = (int)min((int64_t)SG_AB, a1 - ab);
         __syncthreads();
         sg_load_block(blk, nullptr, argmax, ab, cnt, S, W, N, Tp, n0);
-        sg_issue_span(xs[0], dout, (int)(ab / Tp), L, pl, blk.pmin[0], blk.len[0]);
+        for (int i = 0; i < SG_NS - 1; ++i) {
+            if (i < cnt) sg_issue_span(xs[i], dout, blk.row[i], L, pl, blk.pmin[i], blk.len[i], vec16);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         for (int i = 0; i < cnt; ++i) {
-            const int64_t at = ab + i;
-            const int r = (int)(at / Tp), tp = (int)(at - (int64_t)r * Tp);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();                                    // span i visible; red[(i-1)&1] complete
+            const int r = blk.row[i];
+            sg_wait_pending<SG_NS - 2>();
+            __syncthreads();                                    // span i visible; red[(i-1)&1] complete; buffer (i-1) % SG_NS free
             if (i > 0 && tid < SG_F && n0 + tid < N) {          // finish pair i-1: fixed-order sum of the 8 warp partials
-                const int64_t ap = at - 1;
-                const int rp = (int)(ap / Tp), tpp = (int)(ap - (int64_t)rp * Tp);
+                const int rp = blk.row[i - 1], tpp = blk.frame[i - 1];
                 float t = 0.f;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) t += red[(i - 1) & 1][q][tid];
                 dvals[((size_t)rp * Tp + tpp) * N + n0 + tid] = t;
             }
-            if (i + 1 < cnt) sg_issue_span(xs[(i + 1) & 1], dout, (int)((at + 1) / Tp), L, pl, blk.pmin[i + 1], blk.len[i + 1]);
-            const float* xb = xs[i & 1];
+            if (i + SG_NS - 1 < cnt)
+                sg_issue_span(xs[(i + SG_NS - 1) % SG_NS], dout, blk.row[i + SG_NS - 1], L, pl, blk.pmin[i + SG_NS - 1],
+                              blk.len[i + SG_NS - 1], vec16);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
             const int pmin = blk.pmin[i], len = blk.len[i];
+            const float* xb = xs[i % SG_NS] + sg_adj(pmin - pl, vec16) - pmin + tid;
+            int posv[SG_F];
+#pragma unroll
+            for (int f4 = 0; f4 < SG_F; f4 += 4) {
+                const int4 pq = *reinterpret_cast<const int4*>(&blk.pos[i][f4]);
+                posv[f4] = pq.x; posv[f4 + 1] = pq.y; posv[f4 + 2] = pq.z; posv[f4 + 3] = pq.w;
+            }
+            float pacc[SG_F];
 #pragma unroll
             for (int f = 0; f < SG_F; ++f) {
-                const int off = blk.pos[i][f] - pmin;
-                float pacc = 0.f;
+                pacc[f] = 0.f;
+                if (posv[f] >= 0) {                             // warp-uniform
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = tid + 256 * j;
-                    if (k < W && blk.pos[i][f] >= 0) {
-                        float x;
-                        if (len <= SG_SPAN) x = xb[off + k];
-                        else { const int s = blk.pos[i][f] + k - pl; x = (s >= 0 && s < L) ? dout[(size_t)r * L + s] : 0.f; }
-                        pacc = fmaf(w[f][j], x, pacc);
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = tid + 256 * j;
+                        if (FULLW || k < W) {
+                            float x;
+                            if (len <= SG_SPAN) x = xb[posv[f] + 256 * j];
+                            else { const int s = posv[f] + k - pl; x = (s >= 0 && s < L) ? dout[(size_t)r * L + s] : 0.f; }
+                            pacc[f] = fmaf(w[f][j], x, pacc[f]);
+                        }
                     }
                 }
-                pacc = warp_sum(pacc);
-                if (lane == 0) red[i & 1][warp][f] = pacc;
             }
-            (void)tp;
+            {   // warp reduction of the SG_F = 8 partial sums together: a halving butterfly (4 + 2 + 1 exchanges) leaves lane l with
+                // the 4-lane partial of filter l >> 2, two more exchanges finish it: 9 shuffles instead of 8 x 5
+                static_assert(SG_F == 8, "the butterfly below reduces exactly 8 values");
+                float q4[4], q2[2];
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float keep = b4 ? pacc[j + 4] : pacc[j], give = b4 ? pacc[j] : pacc[j + 4];
+                    q4[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float keep = b3 ? q4[j + 2] : q4[j], give = b3 ? q4[j] : q4[j + 2];
+                    q2[j] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+                }
+                float q1 = (b2 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? q2[0] : q2[1], 4);
+                q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+                q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+                if ((lane & 3) == 0) red[i & 1][warp][lane >> 2] = q1;
+            }
         }
         __syncthreads();                                        // the last pair of the block
         if (tid < SG_F && n0 + tid < N) {
-            const int64_t ap = ab + cnt - 1;
-            const int rp = (int)(ap / Tp), tpp = (int)(ap - (int64_t)rp * Tp);
+            const int rp = blk.row[cnt - 1], tpp = blk.frame[cnt - 1];
             float t = 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) t += red[(cnt - 1) & 1][q][tid];
@@ -455,6 +534,8 @@ __global__ void filter_grad_final_kernel(const float* __restrict__ part, int chu
     }
 }
 
+// the filter-stationary kernels index (row, frame) pairs and arg-max values with 32-bit arithmetic
+static bool sg_fits_32bit(int R, int Tp, int L, int N) { return (int64_t)R * Tp < (1ll << 31) && (int64_t)L * N < (1ll << 32); }
 constexpr int FG_CHUNKS = 32;     // slices of the (row, frame) list per filter group: 32 x 32 CTAs for 256 filters
 
 }  // namespace
@@ -534,9 +615,10 @@ extern "C" int amss_filterbank_analysis_bwd(const float* x, const float* dy, con
     AMSS_REQUIRE(x && dy && argmax && dfilt && workspace, "filterbank_analysis_bwd: null pointer");
     if (workspace_bytes < amss_filterbank_grad_workspace_bytes(W, N)) { set_error("filterbank_analysis_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
     float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
-    if (W <= 1024) {
+    if (W <= 1024 && sg_fits_32bit(Bt, Tp, L, N)) {
         dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
-        AMSS_LAUNCH(sparse_filter_grad_fs_kernel, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
+        if (W == 1024) AMSS_LAUNCH(sparse_filter_grad_fs_kernel<true>, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
+        else AMSS_LAUNCH(sparse_filter_grad_fs_kernel<false>, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
     } else {
         dim3 grid(N, FG_CHUNKS);
         AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
@@ -574,18 +656,21 @@ extern "C" int amss_filterbank_synthesis_bwd(const float* dout, const float* val
     if (workspace_bytes < amss_filterbank_grad_workspace_bytes(W, N)) { set_error("filterbank_synthesis_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
     float* fT = (float*)workspace;
     float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
-    if (dvals && W <= 1024) {
+    const bool fs = W <= 1024 && sg_fits_32bit(B * S, Tp, L, N);
+    if (dvals && fs) {
         dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
-        AMSS_LAUNCH(synthesis_bwd_vals_fs_kernel, grid, 256, 0, stream, dout, argmax, filt2, B * S, S, L, W, N, Tp, dvals);
+        if (W == 1024) AMSS_LAUNCH(synthesis_bwd_vals_fs_kernel<true>, grid, 256, 0, stream, dout, argmax, filt2, B * S, S, L, W, N, Tp, dvals);
+        else AMSS_LAUNCH(synthesis_bwd_vals_fs_kernel<false>, grid, 256, 0, stream, dout, argmax, filt2, B * S, S, L, W, N, Tp, dvals);
     } else if (dvals) {
         dim3 gt((W + 31) / 32, (N + 31) / 32), bt(32, 8);
         AMSS_LAUNCH(transpose_filter_kernel, gt, bt, 0, stream, filt2, W, N, fT);
         dim3 grid(Tp, B * S);
         AMSS_LAUNCH(synthesis_bwd_vals_kernel, grid, 256, 0, stream, dout, argmax, fT, S, L, W, N, Tp, dvals);
     }
-    if (dfilt2 && W <= 1024) {
+    if (dfilt2 && fs) {
         dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
-        AMSS_LAUNCH(sparse_filter_grad_fs_kernel, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
+        if (W == 1024) AMSS_LAUNCH(sparse_filter_grad_fs_kernel<true>, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
+        else AMSS_LAUNCH(sparse_filter_grad_fs_kernel<false>, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
         dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);
         AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, FG_CHUNKS, W, N, 0, dfilt2);
     } else if (dfilt2) {
