@@ -196,6 +196,127 @@ synthesis_fwd_kernel(const float* __restrict__ vals, const int64_t* __restrict__
     if (u < L) out[(size_t)r * L + u] = acc;
 }
 
+// ---- filter-stationary sparse overlap-add (W = 1024 taps, pool = hop = 256) ---------------------------------------------------
+// The gather above reads one filter tap from L1 / L2 per multiply-add.  Here a CTA keeps SF_F filters in shared memory
+// (64 KB) and walks the frames of ONE mixture in time order for all of its S rows at once (they share the arg-max
+// positions, adapt.py:212-218): an atom (frame tp, filter f) at pos = 256 tp + off touches the samples
+// [256 tp - 511, 256 tp + 767], i.e. five 256-sample blocks starting at block tp - 2.  Thread t owns sample t of each of
+// the five blocks; with kk = t - off - 1 its taps are kk + 256 m for the blocks m = 1..3 and the single tap kk & 1023 for
+// block 0 (kk >= 0) or block 4 (kk < 0): four shared-memory loads (consecutive threads, consecutive taps) feed 5 S
+// multiply-adds.  After frame tp block tp - 2 is complete for this filter group: it is stored and the five accumulators
+// slide by one block.  Partial outputs [N / SF_F][R][L] are summed in filter-group order by a second kernel, so the result does
+// not depend on the launch geometry.  A CTA owns SF_Q consecutive blocks (it starts two frames early and ends two frames late).
+constexpr int SF_F = 16;                 // filters per CTA (64 KB of taps)
+constexpr int SF_Q = 50;                 // 256-sample output blocks per CTA
+
+template <int S>
+__global__ void __launch_bounds__(256, 3)
+synthesis_fwd_fs_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax, const float* __restrict__ filt2,
+                        int L, int N, int Tp, float* __restrict__ part) {
+    constexpr int W = 1024;
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    float* ws = reinterpret_cast<float*>(fb_smem);                    // [SF_F][W]
+    __shared__ int s_pos[2][SF_F];
+    __shared__ float s_val[2][S][SF_F];
+    const int g = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * SF_Q, t = threadIdx.x, n0 = g * SF_F;
+    const int nblk = (L + 255) / 256, q1 = min(q0 + SF_Q, nblk);
+    for (int i = t; i < SF_F * W; i += 256) {                         // taps of the group: ws[f][k] = filt2[k][n0 + f]
+        const int k = i / SF_F, f = i - k * SF_F;
+        ws[f * W + k] = n0 + f < N ? __ldg(filt2 + (size_t)k * N + n0 + f) : 0.f;
+    }
+    const int tp0 = max(q0 - 2, 0), tp1 = min(q1 + 2, Tp);             // frames that touch the blocks [q0, q1)
+    auto stage = [&](int tp, int buf) {                               // positions / values of frame tp for the group's filters
+        if (t < SF_F) {
+            const int n = n0 + t;
+            // an arg-max of the pooling window lies in [256 tp, 256 tp + 256); the clamp keeps the tap indices inside the staged
+            // filters when the caller hands over garbage (e.g. the arg-max of an all-NaN window after a diverged step)
+            const int off = n < N ? (int)((uint32_t)argmax[((size_t)b * Tp + tp) * N + n] / (uint32_t)N) - 256 * tp : 0;
+            s_pos[buf][t] = min(max(off, 0), 255);
+        } else if (t < SF_F * (S + 1)) {
+            const int s = t / SF_F - 1, f = t - (s + 1) * SF_F, n = n0 + f;
+            s_val[buf][s][f] = n < N ? vals[(((size_t)b * S + s) * Tp + tp) * N + n] : 0.f;
+        }
+    };
+    float acc[S][5];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[s][m] = 0.f;
+    if (tp0 < tp1) stage(tp0, 0);
+    __syncthreads();
+    for (int tp = tp0; tp < tp1; ++tp) {
+        const int buf = (tp - tp0) & 1;
+        if (tp + 1 < tp1) stage(tp + 1, buf ^ 1);                     // next frame's atoms while this one is accumulated
+#pragma unroll 4
+        for (int f = 0; f < SF_F; ++f) {
+            const int kk = t - s_pos[buf][f] - 1;                     // off in [0, 256): kk in [-256, 255]
+            const float* wf = ws + f * W;
+            const float x04 = wf[kk & 1023], x1 = wf[kk + 256], x2 = wf[kk + 512], x3 = wf[kk + 768];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const float v = s_val[buf][s][f];
+                const float v0 = kk >= 0 ? v : 0.f;
+                acc[s][0] = fmaf(v0, x04, acc[s][0]);
+                acc[s][1] = fmaf(v, x1, acc[s][1]);
+                acc[s][2] = fmaf(v, x2, acc[s][2]);
+                acc[s][3] = fmaf(v, x3, acc[s][3]);
+                acc[s][4] = fmaf(v - v0, x04, acc[s][4]);
+            }
+        }
+        const int q = tp - 2;                                         // block completed by this frame
+        if (q >= q0 && q < q1) {
+            const int u = 256 * q + t;
+            if (u < L) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) part[((size_t)g * gridDim.y * S + (size_t)b * S + s) * L + u] = acc[s][0];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[s][m] = acc[s][m + 1];
+            acc[s][4] = 0.f;
+        }
+        __syncthreads();                                              // staged frame visible; this frame's buffer free
+    }
+    // frames beyond Tp do not exist: the blocks still held by the accumulators are complete (slot m = block tp1 - 2 + m after
+    // the last shift); blocks no frame reaches are zero
+    for (int q = max(tp1 - 2, q0); q < q1; ++q) {
+        const int m = q - (tp1 - 2);
+        const int u = 256 * q + t;
+        if (u < L) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                float v = 0.f;
+#pragma unroll
+                for (int mm = 0; mm < 5; ++mm) v = mm == m ? acc[s][mm] : v;
+                part[((size_t)g * gridDim.y * S + (size_t)b * S + s) * L + u] = v;
+            }
+        }
+    }
+}
+
+// out[i] = sum_g part[g][i] in group order (i over R * L), 16-byte vectors when n % 4 == 0
+__global__ void synthesis_sum_groups_kernel(const float* __restrict__ part, int groups, int64_t n, float* __restrict__ out) {
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        for (int64_t i = i0; i < n / 4; i += stride) {
+            float4 a = __ldcs(reinterpret_cast<const float4*>(part) + i);
+            for (int g = 1; g < groups; ++g) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(part + (size_t)g * n) + i);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            reinterpret_cast<float4*>(out)[i] = a;
+        }
+    } else {
+        for (int64_t i = i0; i < n; i += stride) {
+            float a = part[i];
+            for (int g = 1; g < groups; ++g) a += part[(size_t)g * n + i];
+            out[i] = a;
+        }
+    }
+}
+
 // dvals[r,tp,n] = sum_k dout[r, pos + k - pl] * filt2[k,n] : one warp per atom, lanes over taps.
 __global__ void __launch_bounds__(256)
 synthesis_bwd_vals_kernel(const float* __restrict__ dout, const int64_t* __restrict__ argmax,
@@ -628,9 +749,20 @@ extern "C" int amss_filterbank_analysis_bwd(const float* x, const float* dy, con
     return AMSS_OK;
 }
 
+// the filter-stationary forward: the reference geometry only (other shapes take the gather kernel)
+static bool synthesis_fs_ok(int S, int W, int N, int pool, int hop, int L) {
+    return W == 1024 && pool == 256 && hop == 256 && S >= 1 && S <= 4 && N % 4 == 0 && (int64_t)L * N < (1ll << 32);
+}
+static size_t synthesis_fs_bytes(int B, int S, int L, int N) {
+    return (size_t)((N + SF_F - 1) / SF_F) * (size_t)B * S * L * 4;
+}
+
 extern "C" size_t amss_filterbank_synthesis_workspace_bytes(int B, int S, int L, int W, int N, int Tp) {
-    (void)B; (void)S; (void)L; (void)Tp;
-    return amss_filterbank_grad_workspace_bytes(W, N);
+    (void)Tp;
+    // (pool / hop are not known here: the partial-output buffer of the filter-stationary forward is reserved whenever the
+    // rest of the geometry allows it)
+    const size_t fs = synthesis_fs_ok(S, W, N, 256, 256, L) ? align_up((size_t)W * N * 4, 256) + synthesis_fs_bytes(B, S, L, N) : 0;
+    return std::max(amss_filterbank_grad_workspace_bytes(W, N), fs);
 }
 
 extern "C" int amss_filterbank_synthesis_fwd(const float* vals, const int64_t* argmax, const float* filt2, int B,
@@ -640,6 +772,24 @@ extern "C" int amss_filterbank_synthesis_fwd(const float* vals, const int64_t* a
     AMSS_REQUIRE(B > 0 && S > 0 && pool > 0 && hop > 0, "filterbank_synthesis_fwd: bad sizes");
     if (workspace_bytes < (size_t)W * N * 4) { set_error("filterbank_synthesis_fwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
     float* fT = (float*)workspace;
+    const size_t fs_off = align_up((size_t)W * N * 4, 256);
+    const bool no_fs = getenv("AMSS_SYNTHESIS_GATHER") != nullptr;             // A/B and parity tests: force the gather kernel
+    if (!no_fs && synthesis_fs_ok(S, W, N, pool, hop, L) && workspace_bytes >= fs_off + synthesis_fs_bytes(B, S, L, N)) {
+        float* part = (float*)((char*)workspace + fs_off);
+        const int groups = (N + SF_F - 1) / SF_F, nblk = (L + 255) / 256;
+        dim3 grid(groups, B, (nblk + SF_Q - 1) / SF_Q);
+        const size_t smem = (size_t)SF_F * 1024 * 4;
+#define AMSS_SYN_FS(SS)                                                                                                         \
+    do {                                                                                                                        \
+        AMSS_CUDA(cudaFuncSetAttribute(synthesis_fwd_fs_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        AMSS_LAUNCH(synthesis_fwd_fs_kernel<SS>, grid, 256, smem, stream, vals, argmax, filt2, L, N, Tp, part);                 \
+    } while (0)
+        if (S == 1) AMSS_SYN_FS(1); else if (S == 2) AMSS_SYN_FS(2); else if (S == 3) AMSS_SYN_FS(3); else AMSS_SYN_FS(4);
+#undef AMSS_SYN_FS
+        const int64_t n = (int64_t)B * S * L;
+        AMSS_LAUNCH(synthesis_sum_groups_kernel, 8 * kNumSMs, 256, 0, stream, part, groups, n, out);
+        return AMSS_OK;
+    }
     dim3 gt((W + 31) / 32, (N + 31) / 32), bt(32, 8);
     AMSS_LAUNCH(transpose_filter_kernel, gt, bt, 0, stream, filt2, W, N, fT);
     dim3 grid((L + 255) / 256, B * S);

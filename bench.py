@@ -243,17 +243,20 @@ def _rl_analysis(a):          # (x, filt, Bt, L, W, N, pool, hop, mode, prec, ..
 
 def _rl_analysis_bwd(a):      # (x, dy, am, Bt, L, W, N, Tp, ...)
     Bt, L, W, N, Tp = a[3:8]
-    return "hbm", Bt * (Tp * N * 12.0 + L * 4.0) + W * N * 4.0, "filter gradient through the max-pool arg-max: dy + int64 arg-max + waveform in, dfilt out"
+    return ("hbm", Bt * (Tp * N * 12.0 + L * 4.0) + W * N * 4.0,
+            "filter gradient through the max-pool arg-max: dy + int64 arg-max + waveform in, dfilt out", {"fma": 1.0 * Bt * Tp * N * W, "fma_per_lds": 1})
 
 
 def _rl_synth_fwd(a):         # (vals, am, filt2, B, S, L, W, N, Tp, pool, hop, out, ...)
     B, S, L, W, N, Tp = a[3:9]
-    return "hbm", B * S * Tp * N * 4.0 + B * Tp * N * 8.0 + W * N * 4.0 + B * S * L * 4.0, "sparse overlap-add synthesis: unpool + conv2d_transpose fused (adapt.py:205-252)"
+    return ("hbm", B * S * Tp * N * 4.0 + B * Tp * N * 8.0 + W * N * 4.0 + B * S * L * 4.0,
+            "sparse overlap-add synthesis: unpool + conv2d_transpose fused (adapt.py:205-252)", {"fma": 1.0 * B * S * Tp * N * W, "fma_per_lds": S})
 
 
 def _rl_synth_bwd(a):         # (dout, vals, am, filt2, B, S, L, W, N, Tp, ...)
     B, S, L, W, N, Tp = a[4:10]
-    return "hbm", B * S * L * 4.0 + 2.0 * B * S * Tp * N * 4.0 + B * Tp * N * 8.0 + 2.0 * W * N * 4.0, "synthesis backward: dvals + dfilt2"
+    return ("hbm", B * S * L * 4.0 + 2.0 * B * S * Tp * N * 4.0 + B * Tp * N * 8.0 + 2.0 * W * N * 4.0, "synthesis backward: dvals + dfilt2",
+            {"fma": 2.0 * B * S * Tp * N * W, "fma_per_lds": 1})
 
 
 def _rl_blstm_fwd(a):         # (x, kf, bf, kb, bb, B, T, I, H, ...)
@@ -322,10 +325,14 @@ def kernel_table(timed, nsteps, step_ms, pk, sustained):
         row = {"entry": name, "calls_per_step": len(calls) / nsteps, "ms_per_step": ms, "share_of_step": ms / step_ms}
         fn = ROOFLINES.get(name)
         if fn is not None:
-            work, bound, what = 0.0, None, None
+            work, bound, what, fma, per_lds = 0.0, None, None, 0.0, 1
             for a, _ in calls:
-                bound, w, what = fn(a)
+                spec = fn(a)
+                bound, w, what = spec[:3]
                 work += w
+                if len(spec) > 3:
+                    fma += spec[3]["fma"]
+                    per_lds = spec[3]["fma_per_lds"]
             work /= nsteps
             if bound == "tensor":
                 ach = work / (ms / 1e3) / 1e12
@@ -333,6 +340,14 @@ def kernel_table(timed, nsteps, step_ms, pk, sustained):
             else:
                 ach = work / (ms / 1e3) / 1e9
                 row.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], work_per_step=work)
+            if fma > 0:
+                # sparse CUDA-core kernels: every multiply-add of an atom reads one filter tap / signal sample from shared
+                # memory (shared across the S rows of a mixture in the forward): the limiter is the 128 B/clk/SM shared-memory
+                # pipe, not HBM -- the algorithmic bytes above are a few MB per step
+                roof = 148 * 32 * 1.965e9 * per_lds / 1e12
+                tf = fma / nsteps / (ms / 1e3) / 1e12
+                row.update(limiter="shared-memory loads (1 per %d multiply-adds)" % per_lds, achieved_tfma=tf, smem_roof_tfma=roof,
+                           frac_of_smem_roof=tf / roof)
             row["what"] = what
         rows.append(row)
     rows.sort(key=lambda r: -r["ms_per_step"])
@@ -622,6 +637,12 @@ def run_gpu(args):
                       note="achieved follows SURVEY 8(d) (2*L*W*N per signal, S+1 signals per mixture); the kernel executes "
                            "S of the S+1 convolutions, so frac_executed is the hardware utilisation; compute-bound "
                            "(ncu: 86.5 % tensor pipe, profiles/), DRAM traffic not a limiter")
+        if "achieved_tfma" in dom:
+            rl.update(limiter=dom["limiter"], achieved_tfma=dom["achieved_tfma"], smem_roof_tfma=dom["smem_roof_tfma"],
+                      frac_of_smem_roof=dom["frac_of_smem_roof"],
+                      note="a sparse CUDA-core kernel: its algorithmic HBM bytes (SURVEY 8(d)) are a few MB per step, so `frac` says "
+                           "nothing about it; the multiply-adds are fed from shared memory and bound by that pipe "
+                           "(achieved_tfma / smem_roof_tfma)")
         if dom["entry"] == "amss_kmeans_fit":
             a = table_raw["amss_kmeans_fit"][0][0]
             moved = float(a[3]) * (a[8] + 2) * a[4] * a[5] * 4.0 * len(table_raw["amss_kmeans_fit"]) / nprof

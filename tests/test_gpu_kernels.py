@@ -302,6 +302,34 @@ def test_filterbank_synthesis_fwd_bwd_and_analysis_bwd(ops, L, W, N, pool, hop, 
     assert rel(dfilt, gf) < 1e-4
 
 
+@pytest.mark.parametrize("L,N,B,S", [(5000, 40, 2, 2), (2048, 16, 3, 1), (13000, 256, 1, 3), (700, 24, 2, 4)])
+def test_synthesis_filter_stationary_kernel_matches_oracle_and_gather(ops, L, N, B, S):
+    """The filter-stationary overlap-add (W = 1024 taps, pool = hop = 256: the reference geometry) against the oracle's
+    unpool + conv2d_transpose (utils/ops.py:94-120, adapt.py:241-243) and against the gather kernel
+    (AMSS_SYNTHESIS_GATHER=1): ragged last block (L % 256 != 0), a filter count that does not fill the last group of 16,
+    one to four rows per mixture, signals shorter than the filter."""
+    import os
+    W, pool = 1024, 256
+    g = torch.Generator().manual_seed(47 + L)
+    x = torch.randn(B * (S + 1), L, generator=g, dtype=torch.float64) * 0.1
+    filt = torch.randn(W, N, generator=g, dtype=torch.float64) / math.sqrt(W)
+    filt2 = torch.randn(W, N, generator=g, dtype=torch.float64) / math.sqrt(W)
+    y, am = T.max_pool_with_argmax_1d(T.conv2d_same_1d(x, filt, 1), pool, pool)
+    Tp = y.shape[1]
+    vals = y[B:].clone()
+    am_mix = am[:B].unsqueeze(1).repeat(1, S, 1, 1).reshape(B * S, Tp, N)
+    out = T.conv2d_transpose_same_1d(T.unpool(vals, am_mix, L, N), filt2, L, 1)
+    f = lambda t: dev(t.float())
+    fast = ops.filterbank_synthesis(f(vals), dev(am[:B]), f(filt2), B, S, L, pool, pool)
+    os.environ["AMSS_SYNTHESIS_GATHER"] = "1"
+    try:
+        slow = ops.filterbank_synthesis(f(vals), dev(am[:B]), f(filt2), B, S, L, pool, pool)
+    finally:
+        del os.environ["AMSS_SYNTHESIS_GATHER"]
+    assert rel(fast, out) < 1e-4 and rel(slow, out) < 1e-4
+    assert rel(fast, slow) < 1e-5
+
+
 def test_synthesis_is_adjoint_of_analysis_full_size(ops):
     """<A x, y> = <x, A^T y> at the BASELINE size (L=64000, W=1024, N=256, pool=hop=256), using the
     sparse structure: scatter y at the arg-max positions == synthesis with the same filter."""
