@@ -11,7 +11,12 @@
  *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer
  *     unless the name ends in _host.  The caller owns every buffer (including the
  *     scratch ones, whose sizes come from the *_workspace_bytes queries); the library
- *     never allocates device memory and keeps no global mutable state.
+ *     never allocates device memory.  Process-wide state is limited to: the lazily
+ *     applied cudaFuncSetAttribute settings of its kernels, the cached occupancy /
+ *     cluster queries, the launch counter read by amss_launch_count(), and the
+ *     diagnostic pointers set by the amss_debug_* calls (NULL unless a tool sets
+ *     them).  Calls may be issued from several host threads on different streams; the
+ *     amss_debug_* switches are not synchronised with running launches.
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
  *   - All tensors are row-major contiguous with the layouts written in the comments.
  *   - Return value: AMSS_OK (0) or a negative AMSS_ERR_* code; amss_last_error()
