@@ -119,6 +119,28 @@ def test_istft_masked_matches_oracle(ops):
     assert rel(out2, ref2) < 1e-4
 
 
+@pytest.mark.parametrize("Lw,frame,hop,S", [(8192, 512, 256, 2), (5000, 256, 64, 3), (64000, 512, 256, 1), (700, 512, 128, 2)])
+def test_istft_run_kernel_matches_per_block_kernel(ops, Lw, frame, hop, S):
+    """The inverse STFT that evaluates every frame once (runs of 16 output blocks per CTA, ring of N / hop block accumulators)
+    against the one-CTA-per-block kernel (AMSS_ISTFT_PER_BLOCK=1): hop = frame / 2, / 4, / 8, block counts that are not a
+    multiple of the run length, a signal with fewer frames than one run; hard labels and soft masks."""
+    import os
+    g = torch.Generator().manual_seed(11 + Lw)
+    x = dev(torch.randn(2, Lw, generator=g) * 0.1)
+    spec, _ = ops.stft(x, frame, hop)
+    B, Tt, Fb = spec.shape[0], spec.shape[1], spec.shape[2]
+    soft = dev(torch.softmax(torch.randn(B, Tt * Fb, S, generator=g), -1))
+    lab = dev(torch.randint(0, S, (B, Tt * Fb), generator=g).to(torch.int32))
+    fast = [ops.istft_masked(spec, S, frame, hop, masks=soft), ops.istft_masked(spec, S, frame, hop, labels=lab)]
+    os.environ["AMSS_ISTFT_PER_BLOCK"] = "1"
+    try:
+        slow = [ops.istft_masked(spec, S, frame, hop, masks=soft), ops.istft_masked(spec, S, frame, hop, labels=lab)]
+    finally:
+        del os.environ["AMSS_ISTFT_PER_BLOCK"]
+    for a, b in zip(fast, slow):
+        assert a.shape == b.shape and rel(a, b) < 1e-5
+
+
 def test_stft_istft_round_trip_full_size(ops):
     """Size-independent property at the BASELINE size (L=64000): all-ones masks give back the
     mixture on [hop, L-hop) (the TF inverse window does not reconstruct the edges)."""
