@@ -148,11 +148,13 @@ __global__ void istft_masked_kernel(const float2* __restrict__ spec, const int* 
     }
 }
 
-// The same inverse with every frame's inverse FFT evaluated ONCE: a CTA owns IR_Q consecutive output blocks of one signal and
-// walks the frames that touch them in time order; frame t adds its r = N / hop windowed pieces to a ring of r block
-// accumulators in shared memory, after frame t block t is complete, stored and its slot cleared.  Twiddles and the
-// normalised synthesis window (inverse_stft_window_fn / N) are tabulated once per CTA instead of once per frame.  The
-// kernel above evaluated each frame r times (once per block it overlaps): 0.80 -> 0.3x ms for 192 signals of 4 s.
+// The same inverse with every frame's inverse FFT evaluated ONCE, two frames per transform: a CTA owns IR_Q consecutive
+// output blocks of one signal and walks the frames that touch them in time order.  The (Hermitian-filled) spectra of frames
+// t and t+1 are combined as Z = X_t + i X_{t+1}: one complex inverse FFT returns frame t in the real and frame t+1 in the
+// imaginary part.  Every frame adds its r = N / hop windowed pieces to a ring of r + 1 block accumulators in shared memory
+// (two frames touch r + 1 blocks); after frame t block t is complete, stored and its slot cleared.  Twiddles and the
+// normalised synthesis window (inverse_stft_window_fn / N) are tabulated once per CTA.  The per-block kernel above evaluates
+// each frame r times and rebuilds the tables per block: 0.80 -> 0.3x ms for 192 signals of 4 s.
 constexpr int IR_Q = 16;
 __global__ void istft_masked_run_kernel(const float2* __restrict__ spec, const int* __restrict__ labels,
                                         const float* __restrict__ masks, int S, int T, int N, int logN, int hop, int nblocks,
@@ -161,9 +163,9 @@ __global__ void istft_masked_run_kernel(const float2* __restrict__ spec, const i
     float2* buf = reinterpret_cast<float2*>(st_smem);
     float2* tw = buf + N;
     float* winv = reinterpret_cast<float*>(tw + N / 2);   // [N]  w[i] / (N * sum_o w^2[(i mod hop) + o hop])
-    float* ring = winv + N;                               // [r][hop]
+    float* ring = winv + N;                               // [r + 1][hop]
     const int m0 = blockIdx.x * IR_Q, m1 = min(m0 + IR_Q, nblocks), bs = blockIdx.y, b = bs / S, s = bs % S;
-    const int F = N / 2 + 1, r = N / hop;
+    const int F = N / 2 + 1, r = N / hop, R1 = r + 1;
     const int64_t Lout = (int64_t)(T - 1) * hop + N;
     fill_twiddles(tw, N, +1.f);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -172,41 +174,48 @@ __global__ void istft_masked_run_kernel(const float2* __restrict__ spec, const i
         for (int o2 = 0; o2 < r; ++o2) { const float w = hann_periodic(j + o2 * hop, N); den = fmaf(w, w, den); }
         winv[i] = hann_periodic(i, N) / den * (1.0f / (float)N);
     }
-    for (int i = threadIdx.x; i < r * hop; i += blockDim.x) ring[i] = 0.f;
+    for (int i = threadIdx.x; i < R1 * hop; i += blockDim.x) ring[i] = 0.f;
     auto emit = [&](int m) {                              // block m is complete: store it and clear its slot
-        float* slot = ring + (m % r) * hop;
+        float* slot = ring + (m % R1) * hop;
         for (int j = threadIdx.x; j < hop; j += blockDim.x) {
             const int64_t u = (int64_t)m * hop + j;
             if (m >= m0 && u < Lout) out[(size_t)bs * Lout + u] = slot[j];
             slot[j] = 0.f;
         }
     };
+    auto masked = [&](size_t o, int k) {
+        const float w = labels ? (labels[o + k] == s ? 1.f : 0.f) : masks[(o + k) * S + s];
+        float2 v = spec[o + k];
+        v.x *= w; v.y *= w;
+        if (k == 0 || k == N / 2) v.y = 0.f;              // irfft ignores the imaginary part of DC and Nyquist
+        return v;
+    };
     const int t_lo = max(m0 - r + 1, 0), t_hi = min(m1 - 1, T - 1);       // frames that touch the blocks [m0, m1)
-    for (int t = t_lo; t <= t_hi; ++t) {
+    for (int t = t_lo; t <= t_hi; t += 2) {
+        const bool two = t + 1 <= t_hi;
         const size_t o = ((size_t)b * T + t) * F;
         __syncthreads();                                  // tables / cleared slots visible; buf free again
         for (int k = threadIdx.x; k < F; k += blockDim.x) {
-            const float w = labels ? (labels[o + k] == s ? 1.f : 0.f) : masks[(o + k) * S + s];
-            float2 v = spec[o + k];
-            v.x *= w; v.y *= w;
-            if (k == 0 || k == N / 2) {   // irfft ignores the imaginary part of DC and Nyquist
-                buf[__brev((unsigned)k) >> (32 - logN)] = make_float2(v.x, 0.f);
-            } else {
-                buf[__brev((unsigned)k) >> (32 - logN)] = v;
-                buf[__brev((unsigned)(N - k)) >> (32 - logN)] = make_float2(v.x, -v.y);
-            }
+            const float2 v1 = masked(o, k);
+            const float2 v2 = two ? masked(o + F, k) : make_float2(0.f, 0.f);
+            // Z[k] = X1[k] + i X2[k];  Z[N-k] = conj(X1[k]) + i conj(X2[k])
+            buf[__brev((unsigned)k) >> (32 - logN)] = make_float2(v1.x - v2.y, v1.y + v2.x);
+            if (k != 0 && k != N / 2) buf[__brev((unsigned)(N - k)) >> (32 - logN)] = make_float2(v1.x + v2.y, v2.x - v1.y);
         }
         fft_shared(buf, tw, N, logN);
-        // piece o2 of the frame belongs to block t + o2; a thread only ever touches its own j of every slot
+        // piece o2 of frame t belongs to block t + o2, of frame t+1 to block t + 1 + o2: r + 1 different slots
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
             const int o2 = i / hop, j = i - o2 * hop;
-            ring[((t + o2) % r) * hop + j] += buf[i].x * winv[i];
+            const float2 z = buf[i];
+            ring[((t + o2) % R1) * hop + j] += z.x * winv[i];
+            if (two) ring[((t + 1 + o2) % R1) * hop + j] += z.y * winv[i];
         }
         __syncthreads();
         emit(t);                                          // frames t-r+1 .. t have all been added (or do not exist)
+        if (two) { __syncthreads(); emit(t + 1); }
     }
     __syncthreads();
-    for (int m = max(t_hi + 1, m0); m < m1; ++m) emit(m);  // the tail blocks after the last frame
+    for (int m = max(t_hi + 1, m0); m < m1; ++m) { emit(m); __syncthreads(); }   // the tail blocks after the last frame
 }
 
 // Backward of istft_masked w.r.t. the soft masks (fine-tuning through Separator.postprocessing, network.py:584-607,
@@ -288,7 +297,7 @@ extern "C" int amss_istft_masked_fwd(const float* spec, const int32_t* labels, c
     AMSS_REQUIRE(hop > 0 && frame % hop == 0, "istft_masked_fwd: frame must be a multiple of hop");
     const int nblocks = T - 1 + frame / hop;
     if (getenv("AMSS_ISTFT_PER_BLOCK") == nullptr) {       // (A/B and parity tests: the one-CTA-per-block kernel)
-        const size_t smem = (size_t)frame * 8 + (size_t)frame / 2 * 8 + (size_t)frame * 4 + (size_t)frame * 4;
+        const size_t smem = (size_t)frame * 8 + (size_t)frame / 2 * 8 + (size_t)frame * 4 + (size_t)(frame + hop) * 4;
         dim3 grid((nblocks + IR_Q - 1) / IR_Q, B * S);
         AMSS_LAUNCH(istft_masked_run_kernel, grid, frame / 2, smem, stream, reinterpret_cast<const float2*>(spec), labels,
                     masks, S, T, frame, logN, hop, nblocks, out);
