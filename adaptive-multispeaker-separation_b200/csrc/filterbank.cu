@@ -9,6 +9,7 @@
 // This file holds the fp32 SIMT path (AMSS_PREC_FP32, the parity path).  The tcgen05 Toeplitz
 // implicit-GEMM analysis kernel lives in filterbank_tc.cu.
 #include "common.cuh"
+#include "tc.cuh"
 #include <algorithm>
 
 namespace amss {
@@ -198,7 +199,7 @@ synthesis_fwd_kernel(const float* __restrict__ vals, const int64_t* __restrict__
 
 // ---- filter-stationary sparse overlap-add (W = 1024 taps, pool = hop = 256) ---------------------------------------------------
 // The gather above reads one filter tap from L1 / L2 per multiply-add.  Here a CTA keeps SF_F filters in shared memory
-// (64 KB) and walks the frames of ONE mixture in time order for all of its S rows at once (they share the arg-max
+// (64 KB, staged by TMA bulk copies) and walks the frames of ONE mixture in time order for all of its S rows at once (they share the arg-max
 // positions, adapt.py:212-218): an atom (frame tp, filter f) at pos = 256 tp + off touches the samples
 // [256 tp - 511, 256 tp + 767], i.e. five 256-sample blocks starting at block tp - 2.  Thread t owns sample t of each of
 // the five blocks; with kk = t - off - 1 its taps are kk + 256 m for the blocks m = 1..3 and the single tap kk & 1023 for
@@ -211,7 +212,7 @@ constexpr int SF_Q = 50;                 // 256-sample output blocks per CTA
 
 template <int S>
 __global__ void __launch_bounds__(256, 3)
-synthesis_fwd_fs_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax, const float* __restrict__ filt2,
+synthesis_fwd_fs_kernel(const float* __restrict__ vals, const int64_t* __restrict__ argmax, const float* __restrict__ filtT,
                         int L, int N, int Tp, float* __restrict__ part) {
     constexpr int W = 1024;
     extern __shared__ __align__(16) unsigned char fb_smem[];
@@ -220,9 +221,17 @@ synthesis_fwd_fs_kernel(const float* __restrict__ vals, const int64_t* __restric
     __shared__ float s_val[2][S][SF_F];
     const int g = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * SF_Q, t = threadIdx.x, n0 = g * SF_F;
     const int nblk = (L + 255) / 256, q1 = min(q0 + SF_Q, nblk);
-    for (int i = t; i < SF_F * W; i += 256) {                         // taps of the group: ws[f][k] = filt2[k][n0 + f]
-        const int k = i / SF_F, f = i - k * SF_F;
-        ws[f * W + k] = n0 + f < N ? __ldg(filt2 + (size_t)k * N + n0 + f) : 0.f;
+    // taps of the group: ws[f][k] = filtT[n0 + f][k], one 4 KB TMA bulk copy per filter from the transposed bank (completion
+    // on an mbarrier); filters beyond N are zero-filled by the threads
+    __shared__ __align__(8) uint64_t tap_bar;
+    const uint32_t bar = tc::smem_u32(&tap_bar);
+    const int nf = min(SF_F, N - n0);
+    if (t == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+    for (int i = t; i < (SF_F - nf) * W; i += 256) ws[nf * W + i] = 0.f;
+    __syncthreads();
+    if (t == 0) {
+        tc::mbar_expect_tx(bar, (uint32_t)nf * W * 4);
+        for (int f = 0; f < nf; ++f) tc::bulk_g2s(tc::smem_u32(ws + f * W), filtT + (size_t)(n0 + f) * W, W * 4, bar);
     }
     const int tp0 = max(q0 - 2, 0), tp1 = min(q1 + 2, Tp);             // frames that touch the blocks [q0, q1)
     auto stage = [&](int tp, int buf) {                               // positions / values of frame tp for the group's filters
@@ -243,6 +252,7 @@ synthesis_fwd_fs_kernel(const float* __restrict__ vals, const int64_t* __restric
 #pragma unroll
         for (int m = 0; m < 5; ++m) acc[s][m] = 0.f;
     if (tp0 < tp1) stage(tp0, 0);
+    tc::mbar_wait(bar, 0);                                            // the taps have landed
     __syncthreads();
     for (int tp = tp0; tp < tp1; ++tp) {
         const int buf = (tp - tp0) & 1;
@@ -776,13 +786,17 @@ extern "C" int amss_filterbank_synthesis_fwd(const float* vals, const int64_t* a
     const bool no_fs = getenv("AMSS_SYNTHESIS_GATHER") != nullptr;             // A/B and parity tests: force the gather kernel
     if (!no_fs && synthesis_fs_ok(S, W, N, pool, hop, L) && workspace_bytes >= fs_off + synthesis_fs_bytes(B, S, L, N)) {
         float* part = (float*)((char*)workspace + fs_off);
+        {   // the transposed bank fT[n][k] = filt2[k][n]: a filter's 1024 taps become one contiguous 4 KB bulk-copy source
+            dim3 gt((W + 31) / 32, (N + 31) / 32), bt(32, 8);
+            AMSS_LAUNCH(transpose_filter_kernel, gt, bt, 0, stream, filt2, W, N, fT);
+        }
         const int groups = (N + SF_F - 1) / SF_F, nblk = (L + 255) / 256;
         dim3 grid(groups, B, (nblk + SF_Q - 1) / SF_Q);
         const size_t smem = (size_t)SF_F * 1024 * 4;
 #define AMSS_SYN_FS(SS)                                                                                                         \
     do {                                                                                                                        \
         AMSS_CUDA(cudaFuncSetAttribute(synthesis_fwd_fs_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        AMSS_LAUNCH(synthesis_fwd_fs_kernel<SS>, grid, 256, smem, stream, vals, argmax, filt2, L, N, Tp, part);                 \
+        AMSS_LAUNCH(synthesis_fwd_fs_kernel<SS>, grid, 256, smem, stream, vals, argmax, fT, L, N, Tp, part);                    \
     } while (0)
         if (S == 1) AMSS_SYN_FS(1); else if (S == 2) AMSS_SYN_FS(2); else if (S == 3) AMSS_SYN_FS(3); else AMSS_SYN_FS(4);
 #undef AMSS_SYN_FS
