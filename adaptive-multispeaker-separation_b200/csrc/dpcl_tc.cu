@@ -200,28 +200,46 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dpcl_bwd_tc_kernel(DtParams p) 
                     dot = fmaf(x.z, dv[4 * c + 2], dot); dot = fmaf(x.w, dv[4 * c + 3], dot);
                 }
             if (inv < 0.f) { inv = -inv; dot = 0.f; }      // clamped branch of l2_normalize: linear map
+            if (p.dzb && (E & 7) == 0) {
+                // bf16 dz straight from the registers of the thread that owns the point: E / 8 16-byte stores per row (the rows of
+                // a warp are contiguous in memory, so the warp's stores fill whole lines between them); no staging pass, no
+                // block barrier, no second trip through shared memory
+                if (r < np) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.dzb + ((size_t)b * p.TF + p0 + r) * E);
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
-                if (c < e4) {
-                    const float4 x = row4[c];
-                    row4[c] = make_float4(inv * (dv[4 * c] - x.x * dot), inv * (dv[4 * c + 1] - x.y * dot),
-                                          inv * (dv[4 * c + 2] - x.z * dot), inv * (dv[4 * c + 3] - x.w * dot));
-                }
-            named_sync(2, 128);                            // all dz rows of the tile are in vs[buf]
-            if (p.dzb) {
-                const int e8 = E / 8;
-                uint4* dst = reinterpret_cast<uint4*>(p.dzb + ((size_t)b * p.TF + p0) * E);
-                for (int u = et; u < np * e8; u += 128) {
-                    const int rr = u / e8, c = u - rr * e8;
-                    const float4 f0 = *reinterpret_cast<const float4*>(vb + rr * pitch + c * 8);
-                    const float4 f1 = *reinterpret_cast<const float4*>(vb + rr * pitch + c * 8 + 4);
-                    __stcs(dst + u, make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w)));
+                    for (int c = 0; c < 8; ++c)
+                        if (2 * c < e4) {
+                            const float4 x0 = row4[2 * c], x1 = row4[2 * c + 1];
+                            __stcs(dst + c, make_uint4(pack_bf16(inv * (dv[8 * c] - x0.x * dot), inv * (dv[8 * c + 1] - x0.y * dot)),
+                                                       pack_bf16(inv * (dv[8 * c + 2] - x0.z * dot), inv * (dv[8 * c + 3] - x0.w * dot)),
+                                                       pack_bf16(inv * (dv[8 * c + 4] - x1.x * dot), inv * (dv[8 * c + 5] - x1.y * dot)),
+                                                       pack_bf16(inv * (dv[8 * c + 6] - x1.z * dot), inv * (dv[8 * c + 7] - x1.w * dot))));
+                        }
                 }
             } else {
-                float4* dst = reinterpret_cast<float4*>(p.dz + ((size_t)b * p.TF + p0) * E);
-                for (int u = et; u < np * e4; u += 128) {
-                    const int rr = u / e4, c = u - rr * e4;
-                    __stcs(dst + u, *reinterpret_cast<const float4*>(vb + rr * pitch + c * 4));
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if (c < e4) {
+                        const float4 x = row4[c];
+                        row4[c] = make_float4(inv * (dv[4 * c] - x.x * dot), inv * (dv[4 * c + 1] - x.y * dot),
+                                              inv * (dv[4 * c + 2] - x.z * dot), inv * (dv[4 * c + 3] - x.w * dot));
+                    }
+                named_sync(2, 128);                        // all dz rows of the tile are in vs[buf]
+                if (p.dzb) {
+                    const int e8 = E / 8;
+                    uint4* dst = reinterpret_cast<uint4*>(p.dzb + ((size_t)b * p.TF + p0) * E);
+                    for (int u = et; u < np * e8; u += 128) {
+                        const int rr = u / e8, c = u - rr * e8;
+                        const float4 f0 = *reinterpret_cast<const float4*>(vb + rr * pitch + c * 8);
+                        const float4 f1 = *reinterpret_cast<const float4*>(vb + rr * pitch + c * 8 + 4);
+                        __stcs(dst + u, make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w)));
+                    }
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(p.dz + ((size_t)b * p.TF + p0) * E);
+                    for (int u = et; u < np * e4; u += 128) {
+                        const int rr = u / e4, c = u - rr * e4;
+                        __stcs(dst + u, *reinterpret_cast<const float4*>(vb + rr * pitch + c * 4));
+                    }
                 }
             }
             mbar_arrive(t_empty + 8 * buf);                // vs[buf] and TMEM[buf] may be reused
