@@ -152,3 +152,41 @@ extern "C" int amss_prepare_inputs(float* x_non_mix, int B, int S, int64_t L, in
     AMSS_LAUNCH(mix_sources_kernel, dim3(chunks, B), MIX_THREADS, 0, stream, x_non_mix, S, L, x_mix);
     return AMSS_OK;
 }
+
+// ---- box sums: the average-pool front / back end written on the sparse kernels ---------------------------------------------
+// tf.layers.average_pooling2d over the stride-1 convolution (models/adapt.py:118-120) is the strided response of the
+// BOX-FILTERED signal, and UpSampling2D + conv2d_transpose (:224-243) is the sparse overlap-add with BOX-FILTERED filters, so
+// both directions (and all their gradients) run on the kernels of the max-pool path once the operand has been summed over a
+// sliding window of P samples:  out[s][u] = scale * sum_{j<P} in[s][u + dir*j]   (in = 0 outside [0, len_in)).
+// series s start at in + s*ss / out + s*oss, consecutive elements are es / oes apart (rows of a signal batch: ss = L, es = 1;
+// columns of a filter bank [W][N]: ss = 1, es = N).
+namespace amss {
+namespace {
+__global__ void box_sum_kernel(const float* __restrict__ in, int nser, int64_t len_in, int64_t ss, int64_t es, int P, int dir,
+                               float scale, int64_t len_out, int64_t oss, int64_t oes, float* __restrict__ out) {
+    const int64_t total = (int64_t)nser * len_out;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // consecutive threads take consecutive addresses of the output (and of the input)
+        const int64_t s = oes == 1 ? i / len_out : i % nser, u = oes == 1 ? i % len_out : i / nser;
+        const float* src = in + s * ss;
+        float acc = 0.f;
+        for (int j = 0; j < P; ++j) {                       // fixed order: deterministic
+            const int64_t v = u + (int64_t)dir * j;
+            if (v >= 0 && v < len_in) acc += src[v * es];
+        }
+        out[s * oss + u * oes] = acc * scale;
+    }
+}
+}  // namespace
+}  // namespace amss
+
+extern "C" int amss_box_sum(const float* in, int nser, int64_t len_in, int64_t series_stride, int64_t elem_stride, int P, int dir,
+                            float scale, int64_t len_out, int64_t out_series_stride, int64_t out_elem_stride, float* out,
+                            void* stream) {
+    AMSS_REQUIRE(in && out && nser > 0 && len_in > 0 && len_out > 0 && P > 0 && (dir == 1 || dir == -1), "box_sum: bad arguments");
+    const int64_t total = (int64_t)nser * len_out;
+    AMSS_LAUNCH(amss::box_sum_kernel, (int)std::min<int64_t>((total + 255) / 256, 32 * amss::kNumSMs), 256, 0, stream, in, nser, len_in,
+                series_stride, elem_stride, P, dir, scale, len_out, out_series_stride, out_elem_stride, out);
+    return AMSS_OK;
+}
+

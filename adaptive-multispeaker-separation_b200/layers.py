@@ -425,6 +425,62 @@ def analysis_strided(x, filt, hop):
     return _AnalysisStridedFn.apply(x, filt, hop)
 
 
+class _AnalysisAvgFn(torch.autograd.Function):
+    """Average-pool front end (conv2d SAME stride 1 + average_pooling2d(pool, stride pool), models/adapt.py:118-120) with the
+    filter gradient: y[r,tp,n] = sum_k xs[r, tp*P + k - pl] filt[k,n] with the box-filtered signal
+    xs[u] = (1/P) sum_{j<P} x[u + j] (u from -(P-1) on), i.e. the sparse filter-gradient kernel at the fixed positions tp*P on xs."""
+
+    @staticmethod
+    def forward(ctx, x, filt, pool):
+        y, _ = ops.filterbank_analysis(x, filt, pool, pool, ops.AMSS_POOL_AVG, AMSS_PREC_FP32)
+        ctx.save_for_backward(x)
+        ctx.W, ctx.N, ctx.pool, ctx.Tp = filt.shape[0], filt.shape[1], pool, y.shape[1]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        P, N, Tp = ctx.pool, ctx.N, ctx.Tp
+        # xs is needed for u in [-(P-1), L) (the window of a frame's first taps reaches before the signal): it is stored shifted
+        # by P - 1, xs_ext[i] = (1/P) sum_{j<P} x[i - j], and the positions move with it
+        xs = ops.box_sum(x.contiguous(), P, dir=-1, scale=1.0 / P, len_out=x.shape[1] + P - 1)
+        pos = torch.arange(Tp, device=x.device, dtype=torch.int64) * P + (P - 1)
+        am = (pos.view(1, Tp, 1) * N + torch.arange(N, device=x.device, dtype=torch.int64).view(1, 1, N))
+        am = am.expand(x.shape[0], Tp, N).contiguous()
+        return None, ops.filterbank_analysis_bwd(xs, dy.contiguous(), am, ctx.W), None
+
+
+def analysis_avg(x, filt, pool):
+    return _AnalysisAvgFn.apply(x, filt, pool)
+
+
+class _BoxFilterFn(torch.autograd.Function):
+    """wbox[k', n] = sum_{j<P} filt[k' - j, n], k' < W + P - 1 (columns of a [W, N] bank); adjoint: sum_{j<P} dwbox[k + j, n]."""
+
+    @staticmethod
+    def forward(ctx, filt, P):
+        ctx.P, ctx.W = P, filt.shape[0]
+        return ops.box_sum(filt.contiguous(), P, dir=-1, len_out=filt.shape[0] + P - 1, axis=0)
+
+    @staticmethod
+    def backward(ctx, dwbox):
+        return ops.box_sum(dwbox.contiguous(), ctx.P, dir=1, len_out=ctx.W, axis=0), None
+
+
+def synthesis_avg(vals, filt2, B, S, L, pool):
+    """Average-pool back end (UpSampling2D((1, pool)) + conv2d_transpose SAME stride 1, models/adapt.py:224-243): every pooled
+    value is an atom at the fixed position tp*pool of the BOX-FILTERED bank wbox (W + pool - 1 taps); the positions are
+    shifted by the difference of the two banks' left paddings so that the sparse overlap-add indexes wbox as the reference's
+    transposed convolution indexes filt2.  Gradients flow to vals and (through the box filter's adjoint) to filt2."""
+    W, N = filt2.shape
+    Tp = vals.shape[1]
+    wbox = _BoxFilterFn.apply(filt2, pool)
+    c = (W + pool - 2) // 2 - (W - 1) // 2
+    pos = torch.arange(Tp, device=vals.device, dtype=torch.int64) * pool + c
+    am = (pos.view(1, Tp, 1) * N + torch.arange(N, device=vals.device, dtype=torch.int64).view(1, 1, N)).expand(B, Tp, N).contiguous()
+    return _SynthesisFn.apply(vals, am, wbox, B, S, L, c + 1, pool)
+
+
 class _SynthesisFn(torch.autograd.Function):
     """unpool + conv2d_transpose fused as a sparse overlap-add (reference models/adapt.py:205-252)."""
 

@@ -198,10 +198,9 @@ class Adapt(Network):
             # tp*hop + c in the arg-max convention, so back() and both filter gradients run on the sparse kernels
             y, am = L.analysis_strided(x, filt, self.hop_size)
         else:
-            if filt.requires_grad:
-                raise AmssError("the average-pool front end is inference-only here (no filter gradient kernel)")
-            y, am = ops.filterbank_analysis(x, filt.detach(), self.max_pool_value, self.hop_size, self.pool_mode,
-                                            AMSS_PREC_FP32)
+            # conv2d stride 1 + average_pooling2d(pool, stride pool) (adapt.py:118-120); trainable through the box-filtered
+            # signal (layers._AnalysisAvgFn); no arg-max: back() places the atoms at the fixed positions tp*pool
+            y, am = L.analysis_avg(x, filt, self.max_pool_value), None
         return y, am
 
     # adapt.py:162-196 (pretraining separator)
@@ -227,7 +226,8 @@ class Adapt(Network):
             _, c = L.strided_positions(1, Lw, self.window, self.N, self.hop_size, sep_out.device)
             out = L.synthesis(sep_out.contiguous(), argmax[:B].contiguous(), filt2, B, self.S, Lw, c + 1, self.hop_size)
         else:
-            raise AmssError("back(): the average-pool synthesis (UpSampling2D + dense transposed conv) is not on the hot path")
+            # UpSampling2D((1, pool)) + conv2d_transpose stride 1 (adapt.py:224-243) = sparse overlap-add of the box-filtered bank
+            out = L.synthesis_avg(sep_out.contiguous(), filt2, B, self.S, Lw, self.max_pool_value)
         return out.reshape(B, self.S, Lw)
 
     # network.py:196-221 (with_perm=False): SDR improvement metric and the 'sdr' loss ratio per (b,s)

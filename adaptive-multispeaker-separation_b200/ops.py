@@ -107,6 +107,24 @@ def filterbank_analysis_bwd(x, dy, argmax, W):
     return dfilt
 
 
+def box_sum(x, P, dir=1, scale=1.0, len_out=None, axis=-1):
+    """Sliding box sum along `axis` of a contiguous 2-D tensor: out[.., u, ..] = scale * sum_{j<P} x[.., u + dir*j, ..]
+    (zero outside).  axis=-1: rows are the series; axis=0: columns are the series ([W, N] filter banks)."""
+    _chk(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    if axis in (-1, 1):
+        nser, len_in = x.shape
+        lo = len_in if len_out is None else int(len_out)
+        out = torch.empty(nser, lo, dtype=_f32, device=x.device)
+        _lib.call("amss_box_sum", _p(x), nser, len_in, len_in, 1, int(P), int(dir), float(scale), lo, lo, 1, _p(out), _stream())
+    else:
+        len_in, nser = x.shape
+        lo = len_in if len_out is None else int(len_out)
+        out = torch.empty(lo, nser, dtype=_f32, device=x.device)
+        _lib.call("amss_box_sum", _p(x), nser, len_in, 1, nser, int(P), int(dir), float(scale), lo, 1, nser, _p(out), _stream())
+    return out
+
+
 def filterbank_synthesis(vals, argmax_mix, filt2, B, S, L, pool, hop):
     """vals[B*S,Tp,N], argmax_mix[B,Tp,N] (mixture rows), filt2[W,N] -> out[B*S,L]."""
     _chk(vals, argmax_mix, filt2)

@@ -99,6 +99,15 @@ int amss_filterbank_analysis_bwd(const float* x, const float* dy, const int64_t*
                                  void* stream);
 size_t amss_filterbank_grad_workspace_bytes(int W, int N);
 
+/* Sliding box sum: out[s][u] = scale * sum_{j<P} in[s][u + dir*j] (in = 0 outside [0,len_in)), dir = +1 / -1; series s starts
+ * at in + s*series_stride (out + s*out_series_stride), consecutive elements are elem_stride apart.  The average-pool front
+ * end (tf.layers.average_pooling2d over the stride-1 convolution, models/adapt.py:118-120) is the strided response of the
+ * box-filtered signal, and UpSampling2D + conv2d_transpose (:224-243) the sparse overlap-add with box-filtered filters: with
+ * this operand transform both run, with all their gradients, on the kernels of the max-pool path.                           */
+int amss_box_sum(const float* in, int nser, int64_t len_in, int64_t series_stride, int64_t elem_stride, int P,
+                 int dir, float scale, int64_t len_out, int64_t out_series_stride, int64_t out_elem_stride,
+                 float* out, void* stream);
+
 /* unpool (utils/ops.py:94-120) + tf.nn.conv2d_transpose(SAME)  (adapt.py:205-252), fused
  * as a sparse overlap-add: out[r,u] = sum_{tp,n} vals[r,tp,n]*filt2[u-pos+pad_left,n],
  * pos = argmax[r / S][tp][n] / N  (the mixture's argmax, tiled S times: adapt.py:212-218).

@@ -352,6 +352,25 @@ def test_synthesis_filter_stationary_kernel_matches_oracle_and_gather(ops, L, N,
     assert rel(fast, slow) < 1e-5
 
 
+def test_box_sum_rows_columns_and_adjoint(ops):
+    """amss_box_sum: sliding sums along rows (signals) and columns (filter banks), both directions, zero outside; the
+    column adjoint used for the filter gradient of the average-pool back end."""
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(3, 700, generator=g, dtype=torch.float64)
+    P = 32
+    xp = torch.nn.functional.pad(x, (0, P - 1))
+    ref = xp.unfold(1, P, 1).sum(-1) / P                                   # (1/P) sum_j x[u + j]
+    assert rel(ops.box_sum(dev(x.float()), P, dir=1, scale=1.0 / P), ref) < 1e-5
+    w = torch.randn(64, 24, generator=g, dtype=torch.float64)
+    wp = torch.nn.functional.pad(w.t(), (P - 1, P - 1))                    # [N, W + 2(P-1)]
+    wbox = wp.unfold(1, P, 1).sum(-1).t()                                  # wbox[k'] = sum_j w[k' - j], k' < W + P - 1
+    got = ops.box_sum(dev(w.float()), P, dir=-1, len_out=64 + P - 1, axis=0)
+    assert got.shape == (64 + P - 1, 24) and rel(got, wbox) < 1e-5
+    d = torch.randn(64 + P - 1, 24, generator=g, dtype=torch.float64)
+    adj = ops.box_sum(dev(d.float()), P, dir=1, len_out=64, axis=0)
+    assert abs(float((wbox * d).sum()) - float((w * adj.double().cpu()).sum())) < 1e-3 * float((wbox * d).abs().sum())
+
+
 def test_synthesis_is_adjoint_of_analysis_full_size(ops):
     """<A x, y> = <x, A^T y> at the BASELINE size (L=64000, W=1024, N=256, pool=hop=256), using the
     sparse structure: scatter y at the arg-max positions == synthesis with the same filter."""
