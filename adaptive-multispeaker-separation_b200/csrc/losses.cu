@@ -26,8 +26,23 @@ __global__ void dpcl_count_kernel(const uint8_t* __restrict__ labels, int64_t TF
     __shared__ float red[32];
     const int b = blockIdx.x;
     int c[LS_MAXS] = {0, 0, 0, 0};
-    for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) {
-        const int l = labels[(size_t)b * TF + i];
+    const uint8_t* lb = labels + (size_t)b * TF;
+    int64_t i0 = 0;
+    if ((reinterpret_cast<uintptr_t>(lb) & 15) == 0) {    // 16 labels per load, byte-wise compare + popcount
+        const uint4* l4 = reinterpret_cast<const uint4*>(lb);
+        const int64_t n4 = TF / 16;
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+            const uint4 v = __ldg(l4 + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int s = 0; s < LS_MAXS; ++s) c[s] += __popc(__vcmpeq4(w[k], 0x01010101u * s)) >> 3;
+        }
+        i0 = n4 * 16;
+    }
+    for (int64_t i = i0 + threadIdx.x; i < TF; i += blockDim.x) {
+        const int l = lb[i];
 #pragma unroll
         for (int s = 0; s < LS_MAXS; ++s) c[s] += (l == s);
     }
@@ -37,14 +52,41 @@ __global__ void dpcl_count_kernel(const uint8_t* __restrict__ labels, int64_t TF
     }
 }
 
+// Weighted labels (--function_mask, models/network.py:381-389): Y[i,:] = u_i e_{l_i}, so (Y Y^T 1)_i = u_i U_{l_i} with
+// U_s = sum_{i in s} u_i, and
+//   V^T D V = sum_i (u_i U_{l_i})^{-1/2} v_i v_i^T,   V^T D Y[:, s] = U_s^{-1/2} sum_{i in s} sqrt(u_i) v_i,
+//   Y^T D Y = diag(U_s^{-1/2} sum_{i in s} u_i^{3/2}).
+// counts[b][s] = U_s, counts[B*LS_MAXS + b*LS_MAXS + s] = sum u^{3/2}; strided per-thread sums + block_sum: fixed order.
+__global__ void dpcl_wcount_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ weights, int64_t TF,
+                                   int S, int B, float* __restrict__ counts) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    float c[LS_MAXS] = {0.f, 0.f, 0.f, 0.f}, c15[LS_MAXS] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = threadIdx.x; i < TF; i += blockDim.x) {
+        const int l = labels[(size_t)b * TF + i];
+        const float u = weights[(size_t)b * TF + i], u15 = u * sqrtf(u);
+#pragma unroll
+        for (int s = 0; s < LS_MAXS; ++s) { c[s] += (l == s) ? u : 0.f; c15[s] += (l == s) ? u15 : 0.f; }
+    }
+    for (int s = 0; s < LS_MAXS; ++s) {
+        const float v = block_sum(c[s], red);
+        const float v15 = block_sum(c15[s], red);
+        if (threadIdx.x == 0) {
+            counts[b * LS_MAXS + s] = s < S ? v : 0.f;
+            counts[(B + b) * LS_MAXS + s] = s < S ? v15 : 0.f;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(LS_THREADS)
 dpcl_gram_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels, const float* __restrict__ counts,
-                 int64_t TF, int E, int S, float* __restrict__ part) {
+                 const float* __restrict__ weights, int64_t TF, int E, int S, float* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
     const int EP = (E + 3) & ~3;
     float* xs = reinterpret_cast<float*>(ls_smem);              // [LS_PT][EP]   (reused for the final reduction)
-    float* wsm = xs + LS_PT * EP;                               // [LS_PT] weights
-    uint8_t* ls = reinterpret_cast<uint8_t*>(wsm + LS_PT);      // [LS_PT] labels
+    float* wsm = xs + LS_PT * EP;                               // [LS_PT] weights of the Gram term
+    float* usm = wsm + LS_PT;                                   // [LS_PT] sqrt(u) of the column sums (1 without label weights)
+    uint8_t* ls = reinterpret_cast<uint8_t*>(usm + LS_PT);      // [LS_PT] labels
     const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x, tid = threadIdx.x;
     const int nb = EP / 4, nt = nb * (nb + 1) / 2;
     int G = LS_THREADS / nt; if (G > 8) G = 8; if (G < 1) G = 1;
@@ -78,7 +120,15 @@ dpcl_gram_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels
         for (int i = tid; i < np; i += LS_THREADS) {
             const int l = labels[(size_t)b * TF + p0 + i];
             ls[i] = (uint8_t)l;
-            wsm[i] = l == 0 ? wS[0] : (l == 1 ? wS[1] : (l == 2 ? wS[2] : wS[3]));
+            const float wl = l == 0 ? wS[0] : (l == 1 ? wS[1] : (l == 2 ? wS[2] : wS[3]));
+            if (weights) {
+                const float u = weights[(size_t)b * TF + p0 + i];
+                wsm[i] = wl * rsqrtf(u);                        // u == 0: inf, as 1/sqrt(0) in the reference
+                usm[i] = sqrtf(u);
+            } else {
+                wsm[i] = wl;
+                usm[i] = 1.f;
+            }
         }
         __syncthreads();
         if (active) {
@@ -97,7 +147,7 @@ dpcl_gram_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels
         if (mg < 4) {
             for (int p = mg; p < np; p += 4) {
                 const int l = ls[p];
-                const float v = xs[p * EP + me];
+                const float v = xs[p * EP + me] * usm[p];
 #pragma unroll
                 for (int s = 0; s < LS_MAXS; ++s) macc[s] += (l == s) ? v : 0.f;
             }
@@ -141,8 +191,9 @@ dpcl_gram_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels
 
 // One CTA per batch row: reduce the partials, form the three Frobenius norms, keep what the
 // backward needs:  stats[b] = { An[E*E] = 2*A/||A||, Bn[S*E] = 2*Bm[:,s]/||Bm||, dinv[S], loss_b }.
-__global__ void dpcl_finalize_kernel(const float* __restrict__ part, const float* __restrict__ counts, int chunks, int E,
-                                     int S, float* __restrict__ stats) {
+// c15 != NULL (weighted labels): ||Y^T D Y||_F^2 = sum_s (c15_s)^2 / U_s.
+__global__ void dpcl_finalize_kernel(const float* __restrict__ part, const float* __restrict__ counts,
+                                     const float* __restrict__ c15, int chunks, int E, int S, float* __restrict__ stats) {
     __shared__ float red[32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int stride = E * E + S * E;
@@ -164,7 +215,11 @@ __global__ void dpcl_finalize_kernel(const float* __restrict__ part, const float
     sa = block_sum(sa, red);
     sb = block_sum(sb, red);
     float sc = 0.f;
-    for (int s = 0; s < S; ++s) sc += counts[b * LS_MAXS + s];     // ||diag(sqrt(N_s))||_F^2 = sum N_s
+    for (int s = 0; s < S; ++s) {                                  // ||diag(sqrt(N_s))||_F^2 = sum N_s
+        const float n = counts[b * LS_MAXS + s];
+        if (c15) { const float c = c15[b * LS_MAXS + s]; sc += n > 0.f ? c * c / n : 0.f; }
+        else sc += n;
+    }
     const float na = sqrtf(sa), nbm = sqrtf(sb), nc = sqrtf(sc);
     __syncthreads();
     for (int i = tid; i < E * E; i += blockDim.x) out[i] = 2.f * out[i] / na;
@@ -196,8 +251,8 @@ constexpr int LS_BP = 256, LS_BPT = 260, LS_BWD_THREADS = 320;
 template <int OB, int EC>
 __global__ void __launch_bounds__(LS_BWD_THREADS)
 dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels, const float* __restrict__ dloss,
-                const float* __restrict__ stats, const float* __restrict__ inv_norm, int B, int64_t TF, int Ert, int S,
-                float* __restrict__ out) {
+                const float* __restrict__ stats, const float* __restrict__ inv_norm, const float* __restrict__ weights,
+                int B, int64_t TF, int Ert, int S, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
     const int E = EC > 0 ? EC : Ert;
     const int EO = E | 1;                                       // odd row pitch of the result staging
@@ -262,9 +317,17 @@ dpcl_bwd_kernel(const float* __restrict__ V, const uint8_t* __restrict__ labels,
                 if (p < np) {
                     const int l = labels[(size_t)b * TF + p0 + p];
                     const float d = gscale * dinv[l];
+                    if (weights) {                              // weighted labels: D_i = dinv / sqrt(u), D_i u_i = dinv * sqrt(u)
+                        const float u = weights[(size_t)b * TF + p0 + p], ru = rsqrtf(u), su = sqrtf(u);
 #pragma unroll
-                    for (int j = 0; j < OB; ++j)
-                        if (EC > 0 || (j < OBr && o0 + j < E)) os[p * EO + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
+                        for (int j = 0; j < OB; ++j)
+                            if (EC > 0 || (j < OBr && o0 + j < E))
+                                os[p * EO + o0 + j] = d * (acc[i][j] * ru - Bn[l * E + o0 + j] * su);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < OB; ++j)
+                            if (EC > 0 || (j < OBr && o0 + j < E)) os[p * EO + o0 + j] = d * (acc[i][j] - Bn[l * E + o0 + j]);
+                    }
                 }
             }
         }
@@ -576,7 +639,7 @@ using namespace amss;
 extern "C" size_t amss_dpcl_workspace_bytes(int B, int64_t TF, int E, int S) {
     const size_t stride = (size_t)E * E + (size_t)S * E;
     const size_t sstride = (size_t)E * E + (size_t)S * E + S + 1;
-    return align_up((size_t)B * sstride * 4, 256) + align_up((size_t)B * LS_MAXS * 4, 256) +
+    return align_up((size_t)B * sstride * 4, 256) + align_up((size_t)2 * B * LS_MAXS * 4, 256) +
            align_up((size_t)B * ls_chunks(B, TF, LS_PT) * stride * 4, 256);
 }
 
@@ -587,8 +650,8 @@ int dpcl_gram_tc(const float* V, const uint8_t* labels, const float* counts, int
                  float* part, cudaStream_t st);
 }  // namespace amss
 
-static int dpcl_fwd_impl(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S, int precision, float* loss,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+static int dpcl_fwd_impl(const float* V, const uint8_t* labels, const float* weights, int B, int64_t TF, int E, int S,
+                         int precision, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
     AMSS_REQUIRE(V && labels && loss && workspace, "dpcl_loss_fwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_fwd: S=%d outside [1,%d]", S, LS_MAXS);
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_fwd: E=%d outside [1,64]", E);
@@ -596,52 +659,62 @@ static int dpcl_fwd_impl(const float* V, const uint8_t* labels, int B, int64_t T
     const int sstride = E * E + S * E + S + 1;
     float* stats = (float*)workspace;
     float* counts = (float*)((char*)workspace + align_up((size_t)B * sstride * 4, 256));
-    float* part = (float*)((char*)counts + align_up((size_t)B * LS_MAXS * 4, 256));
-    AMSS_LAUNCH(dpcl_count_kernel, B, 256, 0, stream, labels, TF, S, counts);
+    float* part = (float*)((char*)counts + align_up((size_t)2 * B * LS_MAXS * 4, 256));
+    if (weights) AMSS_LAUNCH(dpcl_wcount_kernel, B, 256, 0, stream, labels, weights, TF, S, B, counts);
+    else AMSS_LAUNCH(dpcl_count_kernel, B, 256, 0, stream, labels, TF, S, counts);
     int chunks = ls_chunks(B, TF, LS_PT);
-    const bool tc = precision == AMSS_PREC_BF16 && dpcl_gram_tc_supported(E, S) && (reinterpret_cast<uintptr_t>(V) & 15) == 0;
+    const bool tc = !weights && precision == AMSS_PREC_BF16 && dpcl_gram_tc_supported(E, S) &&
+                    (reinterpret_cast<uintptr_t>(V) & 15) == 0;
     if (tc) {
         chunks = std::min(chunks, dpcl_gram_tc_chunks(B));
         int rc = dpcl_gram_tc(V, labels, counts, B, TF, E, S, chunks, part, (cudaStream_t)stream);
         if (rc != AMSS_OK) return rc;
     } else {
         const int EP = (E + 3) & ~3, nb = EP / 4, nt = nb * (nb + 1) / 2;
-        size_t smem1 = (size_t)LS_PT * EP * 4 + LS_PT * 4 + LS_PT;
+        size_t smem1 = (size_t)LS_PT * EP * 4 + 2 * LS_PT * 4 + LS_PT;
         smem1 = std::max(smem1, ((size_t)8 * nt * 16 + (size_t)4 * LS_MAXS * EP) * 4);
         AMSS_CUDA(cudaFuncSetAttribute(dpcl_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         dim3 grid(chunks, B);
-        AMSS_LAUNCH(dpcl_gram_kernel, grid, LS_THREADS, smem1, stream, V, labels, counts, TF, E, S, part);
+        AMSS_LAUNCH(dpcl_gram_kernel, grid, LS_THREADS, smem1, stream, V, labels, counts, weights, TF, E, S, part);
     }
-    AMSS_LAUNCH(dpcl_finalize_kernel, B, 256, 0, stream, part, counts, chunks, E, S, stats);
+    AMSS_LAUNCH(dpcl_finalize_kernel, B, 256, 0, stream, part, counts,
+                weights ? (const float*)(counts + (size_t)B * LS_MAXS) : (const float*)nullptr, chunks, E, S, stats);
     AMSS_LAUNCH(mean_of_stat_kernel, 1, 32, 0, stream, stats, B, sstride, sstride - 1, loss);
     return AMSS_OK;
 }
 
 extern "C" int amss_dpcl_loss_fwd(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S, float* loss,
                                   void* workspace, size_t workspace_bytes, void* stream) {
-    return dpcl_fwd_impl(V, labels, B, TF, E, S, AMSS_PREC_FP32, loss, workspace, workspace_bytes, stream);
+    return dpcl_fwd_impl(V, labels, nullptr, B, TF, E, S, AMSS_PREC_FP32, loss, workspace, workspace_bytes, stream);
 }
 
 extern "C" int amss_dpcl_loss_fwd_prec(const float* V, const uint8_t* labels, int B, int64_t TF, int E, int S,
                                        int precision, float* loss, void* workspace, size_t workspace_bytes,
                                        void* stream) {
-    return dpcl_fwd_impl(V, labels, B, TF, E, S, precision, loss, workspace, workspace_bytes, stream);
+    return dpcl_fwd_impl(V, labels, nullptr, B, TF, E, S, precision, loss, workspace, workspace_bytes, stream);
+}
+
+extern "C" int amss_dpcl_loss_weighted_fwd(const float* V, const uint8_t* labels, const float* weights, int B, int64_t TF,
+                                           int E, int S, float* loss, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+    AMSS_REQUIRE(weights, "dpcl_loss_weighted_fwd: null weights");
+    return dpcl_fwd_impl(V, labels, weights, B, TF, E, S, AMSS_PREC_FP32, loss, workspace, workspace_bytes, stream);
 }
 
 namespace {
-int dpcl_bwd_launch(const float* V, const uint8_t* labels, const float* dloss, const float* inv_norm, int B, int64_t TF,
-                    int E, int S, float* out, const void* workspace, void* stream) {
+int dpcl_bwd_launch(const float* V, const uint8_t* labels, const float* dloss, const float* inv_norm, const float* weights,
+                    int B, int64_t TF, int E, int S, float* out, const void* workspace, void* stream) {
     const size_t smem = ((size_t)E * LS_BPT + (size_t)LS_BP * (E | 1) + (size_t)E * E + (size_t)S * E + S) * 4;
     const int64_t work = (int64_t)B * ((TF + LS_BP - 1) / LS_BP);
     const int grid = (int)std::min<int64_t>(work, 2 * kNumSMs);      // 2 resident CTAs per SM (89 KB of shared memory each)
     if (E == 40) {
         AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<8, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AMSS_LAUNCH((dpcl_bwd_kernel<8, 40>), grid, LS_BWD_THREADS, smem, stream, V, labels, dloss, (const float*)workspace,
-                    inv_norm, B, TF, E, S, out);
+                    inv_norm, weights, B, TF, E, S, out);
     } else {
         AMSS_CUDA(cudaFuncSetAttribute(dpcl_bwd_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         AMSS_LAUNCH((dpcl_bwd_kernel<16, 0>), grid, LS_BWD_THREADS, smem, stream, V, labels, dloss, (const float*)workspace,
-                    inv_norm, B, TF, E, S, out);
+                    inv_norm, weights, B, TF, E, S, out);
     }
     return AMSS_OK;
 }
@@ -652,7 +725,16 @@ extern "C" int amss_dpcl_loss_bwd(const float* V, const uint8_t* labels, const f
     AMSS_REQUIRE(V && labels && dloss && dV && workspace, "dpcl_loss_bwd: null pointer");
     AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_bwd: S out of range");
     AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_bwd: E=%d outside [1,64]", E);
-    return dpcl_bwd_launch(V, labels, dloss, nullptr, B, TF, E, S, dV, workspace, stream);
+    return dpcl_bwd_launch(V, labels, dloss, nullptr, nullptr, B, TF, E, S, dV, workspace, stream);
+}
+
+extern "C" int amss_dpcl_loss_weighted_bwd(const float* V, const uint8_t* labels, const float* weights, const float* dloss,
+                                           const float* inv_norm, int B, int64_t TF, int E, int S, float* dV,
+                                           const void* workspace, void* stream) {
+    AMSS_REQUIRE(V && labels && weights && dloss && dV && workspace, "dpcl_loss_weighted_bwd: null pointer");
+    AMSS_REQUIRE(S >= 1 && S <= LS_MAXS, "dpcl_loss_weighted_bwd: S out of range");
+    AMSS_REQUIRE(E >= 1 && E <= 64, "dpcl_loss_weighted_bwd: E=%d outside [1,64]", E);
+    return dpcl_bwd_launch(V, labels, dloss, inv_norm, weights, B, TF, E, S, dV, workspace, stream);
 }
 
 namespace amss {
@@ -670,7 +752,7 @@ extern "C" int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labe
     if (precision == AMSS_PREC_BF16 && dpcl_bwd_tc_supported(E, S) &&
         ((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0)
         return dpcl_bwd_tc(V, labels, dloss, (const float*)workspace, inv_norm, B, TF, E, S, dz, nullptr, (cudaStream_t)stream);
-    return dpcl_bwd_launch(V, labels, dloss, inv_norm, B, TF, E, S, dz, workspace, stream);
+    return dpcl_bwd_launch(V, labels, dloss, inv_norm, nullptr, B, TF, E, S, dz, workspace, stream);
 }
 
 extern "C" int amss_dpcl_loss_bwd_normalized_bf16(const float* V, const uint8_t* labels, const float* dloss,

@@ -313,6 +313,25 @@ class _NormDPCLLossFn(torch.autograd.Function):
         return dz.view(ctx.zshape), None, None, None, None, None
 
 
+class _WeightedDPCLLossFn(torch.autograd.Function):
+    """DPCL cost with Y = weights * one_hot(labels) (--function_mask, models/network.py:381-389): fp32 kernels; one node
+    on z when V = l2_normalize(z) (inv given), on V otherwise.  The weights are data (computed from the detached front
+    output)."""
+
+    @staticmethod
+    def forward(ctx, z, V, inv, labels, weights, S):
+        loss, ws = ops.dpcl_loss_weighted_fwd(V, labels, weights, S)
+        ctx.save_for_backward(V, inv, labels, weights, ws)
+        ctx.S, ctx.zshape = S, z.shape
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        V, inv, labels, weights, ws = ctx.saved_tensors
+        dz = ops.dpcl_loss_weighted_bwd(V, labels, weights, ctx.S, dloss.reshape(1).contiguous(), ws, inv)
+        return dz.view(ctx.zshape), None, None, None, None, None
+
+
 class _HeadNormDPCLLossFn(torch.autograd.Function):
     """DPCL cost of l2_normalize(x W + b) as ONE autograd node on (x, W, b) for the tensor-core path: the backward
     writes dz once, in bf16, straight from the fused DPCL + normalisation kernel and feeds it to the two head GEMMs
@@ -680,10 +699,20 @@ def l2_normalize(z, E):
     return v
 
 
-def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32, head=None):
+def dpcl_loss(V, labels, S, prenorm=None, precision=AMSS_PREC_FP32, head=None, weights=None):
     """prenorm = (z, inv_norm) as stashed by l2_normalize() on its output: the loss becomes one autograd node
     on z with a fused backward (DPCL gradient + normalisation Jacobian).  On the tensor-core path, when z is the
-    output of a dense layer, the node moves one step further up (onto the layer's x, W, b): _HeadNormDPCLLossFn."""
+    output of a dense layer, the node moves one step further up (onto the layer's x, W, b): _HeadNormDPCLLossFn.
+    weights [B,TF] (--function_mask): the weighted label matrix, fp32 kernels whatever the precision."""
+    if weights is not None:
+        weights = weights.reshape(labels.shape).contiguous()
+        # (a V that came out of dense_normalized() keeps its generic backward: dV -> dz -> dx, dW, db)
+        if prenorm is not None and head is None:
+            z, inv = prenorm
+            if z.numel() == V.numel():
+                return _WeightedDPCLLossFn.apply(z, V.detach().contiguous(), inv, labels, weights, S)
+        Vc = V.contiguous()
+        return _WeightedDPCLLossFn.apply(Vc, Vc, None, labels, weights, S)
     if head is not None and precision != AMSS_PREC_FP32 and S <= 4:
         # V came out of dense_normalized(): (x, W, b, bf16 copies, swap, inv_norm)
         x, W, b, xb, Wb, swap, inv = head

@@ -531,13 +531,15 @@ class DPCL(Separator):
 
     def cost(self, V, labels, I=None, weights=None):
         B, Tt, Fb, E = V.shape
-        if weights is not None:
-            # Y = one_hot * w is no longer one-hot: D = 1/sqrt(Y Y^T 1) needs per-point weights in every DPCL kernel, and
-            # with --silence_loss the reference itself divides by zero there (D = 1/sqrt(0)); supported for L41 only
-            raise NotImplementedError("--function_mask / --silence_loss with the DPCL cost (weighted label matrix)")
+        if weights is not None and self.loss_with_silence:
+            # the silence mask zeroes rows of Y, and the reference's D = 1/sqrt(Y Y^T 1) (dpcl.py:58-62) is then 1/sqrt(0):
+            # its DPCL cost is inf / NaN from the first step.  Refused loudly instead of reproducing the NaN
+            raise ValueError("--silence_loss with the DPCL cost divides by zero in the reference (models/dpcl.py:58-62); "
+                             "use it with L41, or --function_mask alone")
+        # weights: Y = one_hot * f(|X| / max) (--function_mask, network.py:381-389), fp32 kernels
         return L.dpcl_loss(V.reshape(B, Tt * Fb, E), labels.reshape(B, Tt * Fb), self.S,
                            prenorm=getattr(V, "_amss_prenorm", None), precision=self.precision,
-                           head=getattr(V, "_amss_head", None))
+                           head=getattr(V, "_amss_head", None), weights=weights)
 
 
 class L41Model(Separator):

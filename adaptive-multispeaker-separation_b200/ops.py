@@ -345,6 +345,27 @@ def dpcl_loss_fwd(V, labels, S, precision=AMSS_PREC_FP32):
     return loss, ws
 
 
+def dpcl_loss_weighted_fwd(V, labels, weights, S):
+    """DPCL cost with Y = weights * one_hot(labels) (--function_mask): -> (loss[1], workspace for the backward)."""
+    _chk(V, labels, weights)
+    B, TF, E = V.shape
+    loss = torch.empty(1, dtype=_f32, device=V.device)
+    ws = _ws(_lib.query("amss_dpcl_workspace_bytes", B, TF, E, S), V.device)
+    _lib.call("amss_dpcl_loss_weighted_fwd", _p(V), _p(labels), _p(weights), B, TF, E, S, _p(loss), _p(ws), ws.numel(),
+              _stream())
+    return loss, ws
+
+
+def dpcl_loss_weighted_bwd(V, labels, weights, S, dloss, ws, inv_norm=None):
+    """dV, or dz through the l2_normalize Jacobian when inv_norm is given."""
+    _chk(V, labels, weights, dloss)
+    B, TF, E = V.shape
+    out = torch.empty_like(V)
+    _lib.call("amss_dpcl_loss_weighted_bwd", _p(V), _p(labels), _p(weights), _p(dloss),
+              _p(inv_norm), B, TF, E, S, _p(out), _p(ws), _stream())
+    return out
+
+
 def dpcl_loss_bwd(V, labels, S, dloss, ws):
     _chk(V, labels, dloss)
     B, TF, E = V.shape

@@ -258,6 +258,17 @@ int amss_dpcl_loss_bwd_normalized(const float* V, const uint8_t* labels, const f
 int amss_dpcl_loss_bwd_normalized_bf16(const float* V, const uint8_t* labels, const float* dloss,
                                        const float* inv_norm, int B, int64_t TF, int E, int S,
                                        uint16_t* dz_bf16, const void* workspace, void* stream);
+/* DPCL.cost with the weighted label matrix of --function_mask (models/network.py:381-389 feeding
+ * models/dpcl.py:41-86): Y[i,:] = weights[i] * one_hot(labels[i]), so D_i = 1/sqrt(w_i * sum_{j in
+ * class(i)} w_j).  fp32 kernels; weights[B,TF] are data (no gradient), a zero weight gives the
+ * reference's 1/sqrt(0).  The backward writes dV, or -- with inv_norm != NULL -- dz through the
+ * l2_normalize Jacobian as amss_dpcl_loss_bwd_normalized does.  Workspace: amss_dpcl_workspace_bytes. */
+int amss_dpcl_loss_weighted_fwd(const float* V, const uint8_t* labels, const float* weights, int B,
+                                int64_t TF, int E, int S, float* loss, void* workspace,
+                                size_t workspace_bytes, void* stream);
+int amss_dpcl_loss_weighted_bwd(const float* V, const uint8_t* labels, const float* weights,
+                                const float* dloss, const float* inv_norm, int B, int64_t TF, int E,
+                                int S, float* dV, const void* workspace, void* stream);
 /* L41Model.cost, sampling=None (models/L41.py:47-63, 150-178):
  * mean_{b,tf,s} -log sigmoid(y * <spk[b,s,:], emb[b,tf,:]>), y=+1 if labels==s else -1.
  * spk[B,S,E] = (normalised) gathered speaker vectors.                                   */

@@ -225,6 +225,35 @@ def test_dpcl_loss_fwd_bwd(ops, S):
     assert rel(dV, gV.reshape(B, Tt * Fb, E)) < REL
 
 
+@pytest.mark.parametrize("S,E", [(2, 40), (3, 12)])
+def test_dpcl_loss_weighted_fwd_bwd(ops, S, E):
+    """DPCL.cost on the weighted label matrix of --function_mask (models/network.py:381-389 -> models/dpcl.py:41-86):
+    Y = w * one_hot; cost, dV, and dz through the l2_normalize Jacobian against the oracle's general-Y formula."""
+    g = torch.Generator().manual_seed(34)
+    B, Tt, Fb = 3, 9, 33
+    z = torch.randn(B, Tt, Fb, E, generator=g, dtype=torch.float64).requires_grad_(True)
+    V = T.l2_normalize(z, 3)
+    lab = torch.randint(0, S, (B, Tt, Fb), generator=g)
+    w = torch.rand(B, Tt, Fb, generator=g, dtype=torch.float64) * 0.9 + 0.1
+    y = torch.nn.functional.one_hot(lab, S).double() * w.unsqueeze(-1)
+    cost = M.dpcl_cost(V, y)
+    gV, gz = torch.autograd.grad(cost, [V, z])
+    vg, inv = ops.l2norm_fwd(dev(z.detach().float().reshape(-1, E)), E)
+    Vg = vg.view(B, Tt * Fb, E)
+    labg = dev(lab.to(torch.uint8).reshape(B, Tt * Fb))
+    wg = dev(w.float().reshape(B, Tt * Fb))
+    loss, ws = ops.dpcl_loss_weighted_fwd(Vg, labg, wg, S)
+    assert abs(float(loss) - float(cost)) < REL * abs(float(cost))
+    one = torch.ones(1, device="cuda")
+    assert rel(ops.dpcl_loss_weighted_bwd(Vg, labg, wg, S, one, ws), gV.reshape(B, Tt * Fb, E)) < REL
+    assert rel(ops.dpcl_loss_weighted_bwd(Vg, labg, wg, S, one, ws, inv), gz.reshape(B, Tt * Fb, E)) < REL
+    # unit weights reproduce the one-hot kernels
+    l1, ws1 = ops.dpcl_loss_weighted_fwd(Vg, labg, torch.ones_like(wg), S)
+    l0, ws0 = ops.dpcl_loss_fwd(Vg, labg, S)
+    assert abs(float(l1) - float(l0)) < 1e-6 * abs(float(l0))
+    assert rel(ops.dpcl_loss_weighted_bwd(Vg, labg, torch.ones_like(wg), S, one, ws1), ops.dpcl_loss_bwd(Vg, labg, S, one, ws0)) < 1e-6
+
+
 def test_l41_loss_fwd_bwd(ops):
     g = torch.Generator().manual_seed(33)
     B, Tt, Fb, E, S = 2, 7, 21, 40, 2

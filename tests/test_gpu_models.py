@@ -649,8 +649,47 @@ def test_l41_with_weighted_labels_matches_oracle(amss, fm, sl):
         assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
     for k in st.tr:
         assert rel(t.store[k], st.tr[k]) < REL, k
-    with pytest.raises(NotImplementedError):              # the DPCL cost refuses weighted labels (and says why)
-        tr.Front_Separator_Trainer(mo.DPCL, learning_rate=1e-3, **cfg).train_step(_dev(mix), _dev(nm), _dev(I))
+    if sl:                                                # DPCL + silence mask: 1/sqrt(0) in the reference; refused, and says why
+        with pytest.raises(ValueError):
+            tr.Front_Separator_Trainer(mo.DPCL, learning_rate=1e-3, **cfg).train_step(_dev(mix), _dev(nm), _dev(I))
+
+
+@pytest.mark.parametrize("fm", ["linear", "sqrt", "square"])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_dpcl_with_function_mask_matches_oracle(amss, fm, bf16):
+    """--function_mask (models/network.py:381-389) on the plugged DPCL separator: Y = one_hot * f(|X| / max) in DPCL.cost
+    (models/dpcl.py:41-86); two optimisation steps of the frozen-front recipe against the oracle.  On the tensor-core path
+    the weighted cost still runs on the fp32 kernels (the trunk is bf16: looser bound)."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 2048
+    cfg = dict(nb_layers=1, layer_size=16, embedding_size=8, window_size=32, filters=16, max_pool=32, hop_size=32,
+               with_max_pool=True, function_mask=fm)
+    t = tr.Front_Separator_Trainer(mo.DPCL, learning_rate=1e-3, precision="bf16" if bf16 else "fp32", **cfg)
+    p = _copy_params(t.store, {})
+
+    def fn(pp, xm, xn, I):
+        with torch.no_grad():
+            fr = M.adapt_front(pp, xm, xn, 32, 32)
+        inp = M.separator_plugged_inputs(fr["y"], B, S, 1.0, 0.0)
+        w = M.plugged_label_weights(inp["X"], fm, False, 2.0)
+        V = M.separator_prediction(pp, inp["X"], 1, 8)
+        return M.dpcl_cost(V, inp["y"] * w.unsqueeze(-1)), {"w": w}
+
+    st = OS.Stepper(p, fn, lr=1e-3)
+    tol = 3e-2 if bf16 else REL
+    for step in range(2):
+        # noise sources: the synthetic mixtures have silent stretches, |X| = 0 there, and a zero weight is 1/sqrt(0) in the
+        # reference's D (both the oracle and the kernels return NaN for it)
+        g = torch.Generator().manual_seed(710 + step)
+        nm = (torch.randn(B, S, Lw, generator=g) * 0.1).numpy()
+        mix, I = nm.sum(1), np.zeros((B, S), np.int32)
+        c_ref, aux = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        assert float(aux["w"].min()) > 0 and np.isfinite(c_ref)
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < tol * abs(c_ref), (step, float(c), c_ref)
+    if not bf16:
+        for k in st.tr:
+            assert rel(t.store[k], st.tr[k]) < REL, k
 
 
 @pytest.mark.parametrize("loss", ["sdr", "l2", "sdr+l2"])
