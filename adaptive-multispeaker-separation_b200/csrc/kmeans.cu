@@ -379,12 +379,25 @@ int km_chunks(int B, int64_t L) {
     return (int)(ntiles < want ? ntiles : want);
 }
 
-// Mixtures per group: as many as keep the group's X inside ~3/4 of the 126 MB L2 (at least 1).
+// The tensor-core pass runs ONE CTA per SM (512 TMEM columns, 165 KB of shared memory) and every CTA gets the same number
+// of tiles, so its grid must not spill into a second, nearly empty wave: chunks = floor(SMs / Bg) (Bg * chunks <= SMs; with
+// 2 * SMs / Bg a group of 9 mixtures launched 297 CTAs = two waves + ONE straggler CTA, a third of the pass time).
+int km_chunks_tc(int Bg, int64_t L) {
+    const int64_t ntiles = (L + 127) / 128;
+    int64_t want = kNumSMs / Bg;
+    if (want < 1) want = 1;
+    return (int)(ntiles < want ? ntiles : want);
+}
+
+// Mixtures per group: as many as keep the group's X inside ~3/4 of the 126 MB L2 (at least 1), then evened out over the
+// groups (64 mixtures = 8 groups of 8 rather than 7 of 9 and a group of one).
 int km_group(int B, int64_t L, int E) {
     const double per = (double)L * E * 4.0;
     int g = (int)(96.0e6 / per);
     if (g < 1) g = 1;
-    return g < B ? g : B;
+    if (g >= B) return B;
+    const int ngroups = (B + g - 1) / g;
+    return (B + ngroups - 1) / ngroups;
 }
 
 struct KmWs {
@@ -397,7 +410,8 @@ KmWs km_ws(void* base, int B, int64_t L, int E, int K, int tries) {
     char* p = (char*)base;
     const int G = km_group(B, L, E);
     w.cent = (float*)(p + off); off += align_up((size_t)B * tries * K * E * 4, 256);
-    w.part = (float*)(p + off); off += align_up((size_t)G * km_chunks(G, L) * tries * K * (E + 1) * 4, 256);
+    // Bg * km_chunks(Bg) <= 2 * SMs + Bg - 1 for every group size Bg <= G (a smaller last group gets more chunks per mixture)
+    w.part = (float*)(p + off); off += align_up((size_t)(2 * kNumSMs + G) * tries * K * (E + 1) * 4, 256);
     w.total = off;
     return w;
 }
@@ -453,11 +467,11 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
         const int Bg = std::min(G, B - b0);
         const float* Xg = X + (size_t)b0 * L * E;
         float* centg = w.cent + (size_t)b0 * tries * K * E;
-        const int chunks = km_chunks(Bg, L);
+        const bool tcp = use_tc && (((uintptr_t)Xg & 15) == 0);
+        const int chunks = tcp ? km_chunks_tc(Bg, L) : km_chunks(Bg, L);
         AMSS_LAUNCH(kmeans_gather_init_kernel, 64, 256, 0, st, Xg, init_idx + (size_t)b0 * tries * K, Bg, L, E, K, tries,
                     normalize_input, centg);
         int rc;
-        const bool tcp = use_tc && (((uintptr_t)Xg & 15) == 0);
         for (int it = 0; it < iters; ++it) {
             if (tcp) rc = kmeans_pass_tc(Xg, centg, Bg, L, K, tries, chunks, normalize_input, KM_UPDATE, w.part, st);
             else rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
