@@ -19,8 +19,9 @@ namespace amss {
 
 // tensor-core pass (kmeans_tc.cu): hard assignments, E = 40, K in {2,3,4}, tries*K <= 32, no silence gate
 bool kmeans_tc_supported(int E, int K, int tries, bool soft, bool gated);
-int kmeans_pass_tc(const float* X, const float* cent, int Bg, int64_t L, int K, int tries, int chunks, int normalize, int mode,
-                   float* part, cudaStream_t st);
+void kmeans_tc_set_profile(long long* dev_buf);
+int kmeans_pass_tc(const float* X, const float* cent, const float* prev_part, float* cent_out, int Bg, int64_t L, int K, int tries,
+                   int chunks, int normalize, int mode, float* part, cudaStream_t st);
 
 namespace {
 
@@ -226,19 +227,36 @@ __global__ void kmeans_select_kernel(const float* __restrict__ part, const float
                                      int* __restrict__ best_out, float* __restrict__ cent_out) {
     const int b = blockIdx.x;
     __shared__ int sbest;
+    __shared__ float ratio[128];
+    // one thread per (try, cluster): the chunks in sequence, as before; thread 0 adds the clusters of a try in order
+    for (int tk = threadIdx.x; tk < tries * K && tk < 128; tk += blockDim.x) {
+        float s = 0.f, c = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const float* p = part + (((size_t)b * chunks + ch) * tries * K + tk) * 2;
+            s += p[0];
+            c += p[1];
+        }
+        ratio[tk] = s / c;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         int best = 0;
         float bv = 0.f;
         for (int t = 0; t < tries; ++t) {
             float in = 0.f;
             for (int k = 0; k < K; ++k) {
-                float s = 0.f, c = 0.f;
-                for (int ch = 0; ch < chunks; ++ch) {
-                    const float* p = part + (((size_t)b * chunks + ch) * tries * K + t * K + k) * 2;
-                    s += p[0];
-                    c += p[1];
+                float q;
+                if (t * K + k < 128) q = ratio[t * K + k];
+                else {
+                    float s = 0.f, c = 0.f;
+                    for (int ch = 0; ch < chunks; ++ch) {
+                        const float* p = part + (((size_t)b * chunks + ch) * tries * K + t * K + k) * 2;
+                        s += p[0];
+                        c += p[1];
+                    }
+                    q = s / c;
                 }
-                in += s / c;
+                in += q;
             }
             if (inertia_out) inertia_out[b * tries + t] = in;
             if (t == 0) { bv = isnan(in) ? INFINITY : in; best = 0; }
@@ -401,7 +419,7 @@ int km_group(int B, int64_t L, int E) {
 }
 
 struct KmWs {
-    float *cent, *part;
+    float *cent, *part, *part2;
     size_t total;
 };
 KmWs km_ws(void* base, int B, int64_t L, int E, int K, int tries) {
@@ -412,6 +430,8 @@ KmWs km_ws(void* base, int B, int64_t L, int E, int K, int tries) {
     w.cent = (float*)(p + off); off += align_up((size_t)B * tries * K * E * 4, 256);
     // Bg * km_chunks(Bg) <= 2 * SMs + Bg - 1 for every group size Bg <= G (a smaller last group gets more chunks per mixture)
     w.part = (float*)(p + off); off += align_up((size_t)(2 * kNumSMs + G) * tries * K * (E + 1) * 4, 256);
+    // second buffer: the tensor-core pass reduces the previous pass's partial sums in its prologue while it writes its own
+    w.part2 = (float*)(p + off); off += align_up((size_t)(2 * kNumSMs + G) * tries * K * (E + 1) * 4, 256);
     w.total = off;
     return w;
 }
@@ -434,6 +454,13 @@ int launch_pass(const float* X, const float* cent, const uint8_t* ns, int Bg, in
 }  // namespace amss
 
 using namespace amss;
+
+// Diagnostics: clock64() stamps of the tensor-core update pass (CTA 0, tiles 8..11, 8 slots per tile for the loader, the MMA
+// issuer and the first epilogue thread) are written to dev_buf (>= 96 int64) by subsequent amss_kmeans_fit calls; NULL = off.
+extern "C" int amss_debug_kmeans_profile(long long* dev_buf) {
+    kmeans_tc_set_profile(dev_buf);
+    return AMSS_OK;
+}
 
 extern "C" size_t amss_kmeans_workspace_bytes(int B, int64_t L, int E, int K, int tries) {
     return km_ws(nullptr, B, L, E, K, tries).total;
@@ -467,24 +494,40 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
         const int Bg = std::min(G, B - b0);
         const float* Xg = X + (size_t)b0 * L * E;
         float* centg = w.cent + (size_t)b0 * tries * K * E;
-        const bool tcp = use_tc && (((uintptr_t)Xg & 15) == 0);
+        // (the inertia pass of the tensor-core kernel counts a CTA's tiles in 16-bit counters)
+        const bool tcp = use_tc && (((uintptr_t)Xg & 15) == 0) && (L + 127) / 128 / km_chunks_tc(Bg, L) < 65000;
         const int chunks = tcp ? km_chunks_tc(Bg, L) : km_chunks(Bg, L);
         AMSS_LAUNCH(kmeans_gather_init_kernel, 64, 256, 0, st, Xg, init_idx + (size_t)b0 * tries * K, Bg, L, E, K, tries,
                     normalize_input, centg);
         int rc;
-        for (int it = 0; it < iters; ++it) {
-            if (tcp) rc = kmeans_pass_tc(Xg, centg, Bg, L, K, tries, chunks, normalize_input, KM_UPDATE, w.part, st);
-            else rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
-                              : launch_pass<KM_UPDATE, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
+        const float* inertia_part = w.part;
+        if (tcp) {
+            // update passes chained through their partial sums (no finalize launch in between); the inertia pass reduces the
+            // last ones and leaves the final centroids of every try in centg for the selection
+            float* cur = w.part;
+            const float* prev = nullptr;
+            for (int it = 0; it < iters; ++it) {
+                rc = kmeans_pass_tc(Xg, centg, prev, nullptr, Bg, L, K, tries, chunks, normalize_input, KM_UPDATE, cur, st);
+                if (rc != AMSS_OK) return rc;
+                prev = cur;
+                cur = cur == w.part ? w.part2 : w.part;
+            }
+            rc = kmeans_pass_tc(Xg, centg, prev, centg, Bg, L, K, tries, chunks, normalize_input, KM_INERTIA, cur, st);
             if (rc != AMSS_OK) return rc;
-            AMSS_LAUNCH(kmeans_finalize_kernel, 64, 256, 0, st, w.part, Bg, chunks, tries, K, E, centg);
+            inertia_part = cur;
+        } else {
+            for (int it = 0; it < iters; ++it) {
+                rc = is_soft ? launch_pass<KM_UPDATE, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
+                             : launch_pass<KM_UPDATE, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
+                if (rc != AMSS_OK) return rc;
+                AMSS_LAUNCH(kmeans_finalize_kernel, 64, 256, 0, st, w.part, Bg, chunks, tries, K, E, centg);
+            }
+            rc = is_soft ? launch_pass<KM_INERTIA, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
+                         : launch_pass<KM_INERTIA, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
+            if (rc != AMSS_OK) return rc;
         }
-        if (tcp) rc = kmeans_pass_tc(Xg, centg, Bg, L, K, tries, chunks, normalize_input, KM_INERTIA, w.part, st);
-        else rc = is_soft ? launch_pass<KM_INERTIA, 1>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st)
-                          : launch_pass<KM_INERTIA, 0>(Xg, centg, notsilent, Bg, B, b0, normalize_input, L, E, K, tries, beta, w.part, st);
-        if (rc != AMSS_OK) return rc;
         float* centroids_g = centroids + (size_t)b0 * K * E;
-        AMSS_LAUNCH(kmeans_select_kernel, Bg, 128, 0, st, w.part, centg, Bg, chunks, tries, K, E,
+        AMSS_LAUNCH(kmeans_select_kernel, Bg, 128, 0, st, inertia_part, centg, Bg, chunks, tries, K, E,
                     inertia ? inertia + (size_t)b0 * tries : nullptr, best_try + b0, centroids_g);
         // final labels: un-gated X if assign_at_end (Kmeans_2.py:106-107), else the best try's gated labels
         const uint8_t* ns_final = assign_at_end ? nullptr : notsilent;

@@ -32,27 +32,38 @@ namespace {
 
 using namespace tc;
 
-constexpr int KT_THREADS = 416;
+constexpr int KT_THREADS = 448;
+constexpr int KT_NRAW = 4;                       // raw fp32 tiles in flight (one TMA bulk copy each, dense 160-byte rows)
 constexpr int KT_LOADERS = 256;
 constexpr int KT_E = 40;
-constexpr int KT_PITCH = 44;                     // fp32 staging pitch: LDS.128 of a row per thread is conflict-free
 constexpr int KT_NCH = 18;                       // 16-byte units per point: 3 splits x 6 chunks of 8 features (48 >= E + 1)
-constexpr uint32_t KT_RG = KT_NCH * 128;         // bytes per group of 8 points
-constexpr uint32_t KT_X3 = 16 * KT_RG;           // operand tile of 128 points
+constexpr uint32_t KT_RG = 16 * 128;             // phase-2 operand tile: bytes per group of 8 points = 16 feature chunks: hi 0-4,
+                                                 // mid 0-4, lo 0-4 (5 chunks of 8 features per split) + the ones chunk -> M = 128 rows
+constexpr uint32_t KT_X3 = 16 * KT_RG;           // ... of 128 points
 constexpr uint32_t KT_OHG = 4 * 128;             // one-hot tile: 4 units (32 columns) per point, 8 points per group
 constexpr uint32_t KT_OH = 16 * KT_OHG;
 constexpr int KT_N1 = 32;                        // centroid columns (tries * K <= 32)
-constexpr int KT_N2 = 144;                       // 3 x 48 feature columns
+constexpr int KT_ONES = 120;                     // row of the phase-2 product that holds the counts (chunk 15, feature 40)
 constexpr uint32_t KT_C3 = KT_NCH * (KT_N1 / 8) * 128;
-constexpr uint32_t KT_ACOL = 256;                // TMEM: D1 ring [0,96), D2 [96,240), A ring [256, 256 + 72*NBUF)
+constexpr uint32_t KT_ACOL = 256;                // TMEM: D1 ring [0,96), D2 [96,128), A ring [256, 256 + 72*NBUF)
 constexpr int KT_NBUF = 3;                      // operand / one-hot / distance-accumulator ring: the loaders (most of the
                                                  // instructions) run two tiles ahead of the MMA -> epilogue -> MMA chain
 
 enum { KT_UPDATE = 0, KT_INERTIA = 1 };
 
+// Optional tile profile (diagnostics, amss_debug_kmeans_profile): clock64() stamps of CTA 0, tiles [KT_PROF_T0, +4), 8 slots
+// per tile and role (0 loader thread 0, 1 MMA issuer, 2 first epilogue thread): dev_buf[(role*4 + tile)*8 + slot].
+long long* g_kt_prof = nullptr;
+constexpr uint32_t KT_PROF_T0 = 8;
+#define KPROF(role, k) do { if (prof && i >= KT_PROF_T0 && i < KT_PROF_T0 + 4) prof[((role) * 4 + (i - KT_PROF_T0)) * 8 + (k)] = clock64(); } while (0)
+
 struct KtParams {
+    long long* prof;
     const float* X;        // [Bg][L][E]
-    const float* cent;     // [Bg][tries][K][E]
+    const float* cent;     // [Bg][tries][K][E]  (read when prev_part is null)
+    const float* prev_part;  // UPDATE partial sums of the previous pass [Bg][chunks][tries*K][E+1]: the centroids are reduced from
+                           // them in the prologue (the arithmetic of kmeans_finalize_kernel, no launch in between) ...
+    float* cent_out;       // ... and written here by the first CTA of every mixture (may be null)
     float* part;           // UPDATE: [Bg][chunks][tries*K][E+1]; INERTIA: [Bg][chunks][tries*K][2]
     int64_t L, ntiles;
     int K, tries, chunks, normalize;
@@ -77,13 +88,11 @@ __device__ __forceinline__ uint32_t pack_trunc(float lo, float hi) {
 template <int MODE, int KC>
 __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // x3_full[NBUF], x3_empty[NBUF], d1_full[NBUF], d1_empty[NBUF], oh_full[NBUF], oh_empty[NBUF], done
-    __shared__ __align__(8) uint64_t bars[6 * KT_NBUF + 1];
+    // x3_full[NBUF], x3_empty[NBUF], d1_full[NBUF], d1_empty[NBUF], oh_full[NBUF], oh_empty[NBUF], done, raw_full[NRAW], raw_empty[NRAW]
+    __shared__ __align__(8) uint64_t bars[6 * KT_NBUF + 1 + 2 * KT_NRAW];
     __shared__ uint32_t tmem_base_s;
     __shared__ float cc_s[KT_N1];
     __shared__ float xx_s[KT_NBUF][128];
-    __shared__ float ss_s[2][128];                 // per-half partial sums of squares of the raw row
-    __shared__ float xn_s[2][128];                 // ... and of the normalised row
     __shared__ float fin_s[4][32][2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
@@ -91,20 +100,42 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     uint8_t* x3_s = smem;                                        // [NBUF][KT_X3]
     uint8_t* oh_s = x3_s + KT_NBUF * KT_X3;                      // [NBUF][KT_OH]  (the MMA also reads the 1.5 KB behind a tile:
     uint8_t* c3_s = oh_s + KT_NBUF * KT_OH;                      //  rows >= 32 of the M = 128 product, never used)
-    float* vs = reinterpret_cast<float*>(c3_s + KT_C3);          // [128][KT_PITCH] fp32 staging
+    float* vs = reinterpret_cast<float*>(c3_s + KT_C3);          // [NRAW][128][KT_E] raw fp32 tiles
     const uint32_t x3_full = smem_u32(&bars[0]), x3_empty = x3_full + 8 * KT_NBUF, d1_full = x3_full + 16 * KT_NBUF,
                    d1_empty = x3_full + 24 * KT_NBUF, oh_full = x3_full + 32 * KT_NBUF, oh_empty = x3_full + 40 * KT_NBUF,
-                   done = x3_full + 48 * KT_NBUF;
+                   done = x3_full + 48 * KT_NBUF, raw_full = done + 8, raw_empty = raw_full + 8 * KT_NRAW;
     if (tid == 0) {
         for (int i = 0; i < KT_NBUF; ++i) {
-            mbar_init(x3_full + 8 * i, KT_LOADERS); mbar_init(x3_empty + 8 * i, 1);
+            mbar_init(x3_full + 8 * i, 128); mbar_init(x3_empty + 8 * i, 1);
             mbar_init(d1_full + 8 * i, 1);   mbar_init(d1_empty + 8 * i, 128);
             mbar_init(oh_full + 8 * i, 128); mbar_init(oh_empty + 8 * i, 1);
         }
         mbar_init(done, 1);
+        for (int i = 0; i < KT_NRAW; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 128); }
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    // centroids of this mixture: cent[m][e] = sum_chunks part_sum / sum_chunks part_cnt (Kmeans_2.py:158-165; chunks in
+    // sequence, an empty cluster gives 0/0 = NaN as in the reference), or the given ones
+    __shared__ float cent_s[KT_N1 * KT_E];
+    for (int idx = tid; idx < TK * KT_E; idx += KT_THREADS) {
+        float v;
+        if (p.prev_part) {
+            const int m = idx / KT_E, e = idx - m * KT_E;
+            float sacc = 0.f, cacc = 0.f;
+            for (int ch = 0; ch < p.chunks; ++ch) {
+                const float* q = p.prev_part + (((size_t)b * p.chunks + ch) * TK + m) * (KT_E + 1);
+                sacc += q[e];
+                cacc += q[KT_E];
+            }
+            v = sacc / cacc;
+            if (chunk == 0 && p.cent_out) p.cent_out[(size_t)b * TK * KT_E + idx] = v;
+        } else {
+            v = p.cent[(size_t)b * TK * KT_E + idx];
+        }
+        cent_s[idx] = v;
+    }
+    __syncthreads();
     // centroid operand (K-major B, N = 32 columns n = t*K + k; unit (n, c) at (c*4 + n/8)*128 + (n%8)*16) + |c|^2
     for (int u = tid; u < KT_N1 * KT_NCH; u += KT_THREADS) {
         const int n = u % KT_N1, c = u / KT_N1, sp = c / 6, kc = c % 6;
@@ -115,7 +146,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int e = kc * 8 + 2 * j + h;
-                const float x = (n < TK && e < KT_E) ? p.cent[((size_t)b * TK + n) * KT_E + e] : 0.f;
+                const float x = (n < TK && e < KT_E) ? cent_s[n * KT_E + e] : 0.f;
                 float s0, s1, s2;
                 split3(x, s0, s1, s2);
                 v2[h] = sp == 0 ? s0 : (sp == 1 ? s1 : s2);
@@ -127,7 +158,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     if (tid < KT_N1) {
         float a = 0.f;
         if (tid < TK)
-            for (int e = 0; e < KT_E; ++e) { const float x = p.cent[((size_t)b * TK + tid) * KT_E + e]; a = fmaf(x, x, a); }
+            for (int e = 0; e < KT_E; ++e) { const float x = cent_s[tid * KT_E + e]; a = fmaf(x, x, a); }
         cc_s[tid] = a;
     }
     for (uint32_t i = tid * 16; i < KT_NBUF * KT_OH; i += KT_THREADS * 16) *reinterpret_cast<uint4*>(oh_s + i) = make_uint4(0, 0, 0, 0);
@@ -141,100 +172,120 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
 
     if (warp < 8) {
         // ================= loaders: tile -> fp32 rows -> normalise -> 3 bf16 splits in the operand layout =================
-        // thread = (row r, half h): h = 0 owns features [0,24) = chunks 0-2, h = 1 features [24,48) = chunks 3-5 (16 real
-        // features + the ones column at feature 40)
-        const int r = tid & 127, h = tid >> 7;
-        float4 tilev[5];
-        auto fetch = [&](int64_t tile) {
-            const int64_t p0 = tile * 128;
-            const int np = (int)min((int64_t)128, p.L - p0);
-            const float4* src = reinterpret_cast<const float4*>(p.X + ((size_t)b * p.L + p0) * KT_E);
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int u = tid + KT_LOADERS * j;
-                tilev[j] = u < np * 10 ? __ldg(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        if (ntile) fetch(t0);
-        for (uint32_t i = 0; i < ntile; ++i) {
+        // thread = (row r, group g): ONE thread owns a whole row (the norm needs no exchange and no barrier), the two groups of
+        // four warps take alternate tiles.  (Two threads per row, each computing the row norm redundantly, cost 1100 issue
+        // slots per tile and scheduler against the epilogue's 450: the SM's instruction issue bounds this kernel.)
+        const int r = tid & 127, g = tid >> 7;
+        long long* prof = (blockIdx.x == 0 && r == 0) ? p.prof : nullptr;
+        const int rot = (r >> 2) & 1;
+        for (uint32_t i = g; i < ntile; i += 2) {
             const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
+            const uint32_t slot = i % KT_NRAW, rph = (i / KT_NRAW) & 1;
             const int64_t p0 = (t0 + i) * 128;
             const bool valid = p0 + r < p.L;
-            kt_sync(1, KT_LOADERS);                              // the rows of the previous tile have been consumed
+            KPROF(0, 0);
+            mbar_wait(raw_full + 8 * slot, rph);                 // the producer's bulk copy of this tile has landed
+            KPROF(0, 1);
+            // The tile lies dense (160-byte rows): rows r and r + 4 start in the same bank, so the upper half of every
+            // quarter-warp reads its 16-byte chunks rotated by one (conflict-free LDS.128) and un-rotates in registers
+            float x[48];
+            const float* row = vs + ((size_t)slot * 128 + r) * KT_E;
+            {
+                float4 rv[KT_E / 4];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int u = tid + KT_LOADERS * j, rr = u / 10, c = u - rr * 10;
-                *reinterpret_cast<float4*>(vs + rr * KT_PITCH + c * 4) = tilev[j];
+                for (int c = 0; c < KT_E / 4; ++c) {
+                    int cc = c + rot; if (cc == KT_E / 4) cc = 0;
+                    rv[c] = valid ? *reinterpret_cast<const float4*>(row + cc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);   // rows past the end are not copied
+                }
+#pragma unroll
+                for (int c = 0; c < KT_E / 4; ++c) {
+                    const float4 a = rv[c], bq = rv[(c + KT_E / 4 - 1) % (KT_E / 4)];      // chunk c sits in rv[c] (rot 0) or rv[c - 1] (rot 1)
+                    x[4 * c] = rot ? bq.x : a.x; x[4 * c + 1] = rot ? bq.y : a.y; x[4 * c + 2] = rot ? bq.z : a.z; x[4 * c + 3] = rot ? bq.w : a.w;
+                }
             }
-            if (i + 1 < ntile) fetch(t0 + i + 1);
-            kt_sync(1, KT_LOADERS);
-            float x[24];
-            const float* row = vs + r * KT_PITCH + 24 * h;
+            // sums of squares as two sequential chains over features [0,24) and [24,40), added at the end
+            float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 24; ++e) ss0 = fmaf(x[e], x[e], ss0);
+#pragma unroll
+            for (int e = 24; e < KT_E; ++e) ss1 = fmaf(x[e], x[e], ss1);
+            const float ss = ss0 + ss1;
+            mbar_arrive(raw_empty + 8 * slot);
+            KPROF(0, 2);
+            float inv = 1.f;
+            if (p.normalize) inv = rsqrtf(fmaxf(ss, 1e-12f));
+            float xx0 = 0.f, xx1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 24; ++e) { x[e] *= inv; xx0 = fmaf(x[e], x[e], xx0); }
+#pragma unroll
+            for (int e = 24; e < KT_E; ++e) { x[e] *= inv; xx1 = fmaf(x[e], x[e], xx1); }
+            const float xx = xx0 + xx1;
+            x[KT_E] = valid ? 1.f : 0.f;                         // the ones column (feature 40): exact in bf16
+#pragma unroll
+            for (int e = KT_E + 1; e < 48; ++e) x[e] = 0.f;
+            KPROF(0, 3);
+            mbar_wait(x3_empty + 8 * buf, ph ^ 1);               // the MMAs of tile i-3 have finished with x3[buf]
+            mbar_wait(d1_empty + 8 * buf, ph ^ 1);               // ... and its epilogue has read xx_s[buf]
+            KPROF(0, 4);
+            uint8_t* dst = x3_s + buf * KT_X3 + (size_t)(r >> 3) * KT_RG + (r & 7) * 16;
+            const uint32_t acol = tmem + ((uint32_t)((warp & 3) * 32) << 16) + KT_ACOL + buf * 72;
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (24 * h + 4 * c < KT_E) v = *reinterpret_cast<const float4*>(row + c * 4);
-                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-            }
-            float ss = 0.f;
-#pragma unroll
-            for (int e = 0; e < 24; ++e) ss = fmaf(x[e], x[e], ss);
-            ss_s[h][r] = ss;
-            kt_sync(1, KT_LOADERS);
-            float inv = 1.f;
-            if (p.normalize) inv = rsqrtf(fmaxf(ss_s[0][r] + ss_s[1][r], 1e-12f));
-            float xx = 0.f;
-#pragma unroll
-            for (int e = 0; e < 24; ++e) { x[e] *= inv; xx = fmaf(x[e], x[e], xx); }
-            mbar_wait(x3_empty + 8 * buf, ph ^ 1);               // the MMAs of tile i-2 have finished with x3[buf]
-            mbar_wait(d1_empty + 8 * buf, ph ^ 1);               // ... and its epilogue has read xx_s[buf]
-            if (h == 1) x[16] = valid ? 1.f : 0.f;               // the ones column (feature 40): exact in bf16
-            uint8_t* dst = x3_s + buf * KT_X3 + (size_t)(r >> 3) * KT_RG + (r & 7) * 16;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
                 float sp3[3][8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) split3(x[c * 8 + j], sp3[0][j], sp3[1][j], sp3[2][j]);
 #pragma unroll
                 for (int sp = 0; sp < 3; ++sp) {
+                    // the padding chunk (features 40-47) carries the ones column in the hi split and zeros in the others:
+                    // those zeros are written on the first use of a buffer only (nothing else touches them)
+                    if (c == 5 && sp > 0 && i >= KT_NBUF) continue;
                     const uint32_t w0 = pack_trunc(sp3[sp][0], sp3[sp][1]), w1 = pack_trunc(sp3[sp][2], sp3[sp][3]),
                                    w2 = pack_trunc(sp3[sp][4], sp3[sp][5]), w3 = pack_trunc(sp3[sp][6], sp3[sp][7]);
-                    *reinterpret_cast<uint4*>(dst + (sp * 6 + 3 * h + c) * 128) = make_uint4(w0, w1, w2, w3);   // phase-2 operand
+                    // phase-2 operand: feature chunk c of split sp -> chunk sp*5 + c, the ones chunk -> chunk 15
+                    if (c < 5) *reinterpret_cast<uint4*>(dst + (sp * 5 + c) * 128) = make_uint4(w0, w1, w2, w3);
+                    else if (sp == 0) *reinterpret_cast<uint4*>(dst + 15 * 128) = make_uint4(w0, w1, w2, w3);
                     // phase-1 A operand: TMEM lane = point, 24 columns per split (two k per column), chunk = 4 columns
-                    tmem_st4(tmem + ((uint32_t)((warp & 3) * 32) << 16) + KT_ACOL + buf * 72 + sp * 24 + (3 * h + c) * 4, w0, w1, w2, w3);
+                    tmem_st4(acol + sp * 24 + c * 4, w0, w1, w2, w3);
                 }
             }
+            KPROF(0, 5);
             tmem_st_wait();
             tc_fence_before();
-            // |x|^2 of the normalised row: the two halves are added by the h = 1 thread after a second exchange
-            xn_s[h][r] = xx;
+            KPROF(0, 6);
+            xx_s[buf][r] = xx;                                   // |x|^2 of the normalised row
             fence_async_smem();
-            kt_sync(1, KT_LOADERS);
-            if (h == 1) xx_s[buf][r] = xn_s[0][r] + xn_s[1][r];
             mbar_arrive(x3_full + 8 * buf);
+            KPROF(0, 7);
         }
     } else if (warp == 8) {
         // ================= MMA issuer =================
-        const uint32_t idesc1 = idesc_bf16(128, KT_N1, 0, 0), idesc2 = idesc_bf16(128, KT_N2, 1, 1);
+        const uint32_t idesc1 = idesc_bf16(128, KT_N1, 0, 0), idesc2 = idesc_bf16(128, KT_N1, 1, 1);
         const bool leader = elect_one();
         const uint32_t cbase = smem_u32(c3_s);
-        auto phase2 = [&](uint32_t j) {                           // sums of tile j: onehot^T [x splits | ones]
+        long long* prof = (blockIdx.x == 0 && leader) ? p.prof : nullptr;
+        auto phase2 = [&](uint32_t j) {                           // sums of tile j: [x splits | ones]^T onehot  (M = 128 feature rows,
+                                                                  // N = 32 columns, K = points: 8 small MMAs instead of 8 of N = 144)
             const uint32_t bj = j % KT_NBUF, pj = (j / KT_NBUF) & 1;
             mbar_wait(oh_full + 8 * bj, pj);
             tc_fence_after();
+            { const uint32_t i = j + 1; KPROF(1, 4); }
             const uint32_t oa = smem_u32(oh_s + bj * KT_OH), xa = smem_u32(x3_s + bj * KT_X3);
             for (int kk = 0; kk < 8; ++kk) {
-                const uint64_t ad = smem_desc(oa + kk * 2 * KT_OHG, KT_OHG, 128);
-                const uint64_t bd = smem_desc(xa + kk * 2 * KT_RG, KT_RG, 128);
+                const uint64_t ad = smem_desc(xa + kk * 2 * KT_RG, KT_RG, 128);
+                const uint64_t bd = smem_desc(oa + kk * 2 * KT_OHG, KT_OHG, 128);
                 if (leader) mma_bf16(tmem + KT_NBUF * KT_N1, ad, bd, idesc2, (j | (uint32_t)kk) != 0);
             }
             if (leader) { mma_commit(x3_empty + 8 * bj); mma_commit(oh_empty + 8 * bj); }
+            { const uint32_t i = j + 1; KPROF(1, 5); }
         };
         for (uint32_t i = 0; i < ntile; ++i) {
             const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
+            KPROF(1, 0);
             mbar_wait(x3_full + 8 * buf, ph);
+            KPROF(1, 1);
             mbar_wait(d1_empty + 8 * buf, ph ^ 1);               // the epilogue of tile i-2 has drained D1[buf]
             tc_fence_after();
+            KPROF(1, 2);
             uint32_t acc = 0;
 #pragma unroll
             for (int term = 0; term < 6; ++term) {
@@ -251,46 +302,86 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
                 mma_commit(d1_full + 8 * buf);
                 if (MODE == KT_INERTIA) mma_commit(x3_empty + 8 * buf);
             }
+            KPROF(1, 3);
             if (MODE == KT_UPDATE && i > 0) phase2(i - 1);
         }
         if (MODE == KT_UPDATE && ntile) { phase2(ntile - 1); if (leader) mma_commit(done); }
+    } else if (warp == 13) {
+        // ================= producer: one TMA bulk copy per tile (128 row copies into a padded pitch were tried: ~50 clk per
+        // copy on the TMA engine, 6300 clk per tile) =================
+        for (uint32_t i = 0; i < ntile; ++i) {
+            const uint32_t slot = i % KT_NRAW, rph = (i / KT_NRAW) & 1;
+            const int64_t p0 = (t0 + i) * 128;
+            const int np = (int)min((int64_t)128, p.L - p0);
+            mbar_wait(raw_empty + 8 * slot, rph ^ 1);            // every loader has read its row of tile i - NRAW
+            if (lane == 0) {                                     // the tile is one contiguous block of np * 160 bytes
+                const float* src = p.X + ((size_t)b * p.L + p0) * KT_E;
+                mbar_expect_tx(raw_full + 8 * slot, (uint32_t)np * KT_E * 4);
+                bulk_g2s(smem_u32(vs + (size_t)slot * 128 * KT_E), src, (uint32_t)np * KT_E * 4, raw_full + 8 * slot);
+            }
+            __syncwarp();
+        }
     } else {
         // ================= epilogue: thread = point =================
         const int q = warp & 3, r = q * 32 + lane;
-        float tot = 0.f, cnt = 0.f;                              // INERTIA: column m = lane of this warp's points
+        // INERTIA: per-thread sums of the selected squared distances and counts per column (this thread's points, in tile
+        // order), reduced over the lanes / warps once at the end
+        constexpr int TMAXI = MODE == KT_INERTIA ? KT_N1 / KC : 1;
+        float tot[TMAXI][KC];
+        uint32_t cpk[(KT_N1 + 1) / 2];                           // counts, two 16-bit counters per word (ntile < 65536, checked by the host)
+#pragma unroll
+        for (int t = 0; t < TMAXI; ++t)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) tot[t][k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < (KT_N1 + 1) / 2; ++j) cpk[j] = 0u;
+        // |c|^2 of every column stays in registers for all tiles (columns >= tries*K hold zero centroids: computed, masked off):
+        // the epilogue is branch-free -- per-try uniform branches and shared-memory reads of |c|^2 made a serial
+        // S2UR -> LDS -> FADD chain per try (1800-2300 clk of the 2900 clk a tile took, tools/kmeans_tile_profile.py)
+        constexpr int NCC = MODE == KT_UPDATE ? KT_N1 : 1;       // (the inertia pass keeps its sums in registers instead)
+        float ccr[NCC];
+#pragma unroll
+        for (int m = 0; m < NCC; ++m) ccr[m] = cc_s[m];
+        const uint32_t colmask = TK >= 32 ? 0xFFFFFFFFu : ((1u << TK) - 1u);
+        long long* prof = (blockIdx.x == 0 && r == 0) ? p.prof : nullptr;
         for (uint32_t i = 0; i < ntile; ++i) {
             const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
             const int64_t p0 = (t0 + i) * 128;
             const bool valid = p0 + r < p.L;
+            KPROF(2, 0);
             mbar_wait(x3_full + 8 * buf, ph);                     // acquire |x|^2 written by the loaders
+            KPROF(2, 1);
             mbar_wait(d1_full + 8 * buf, ph);
             tc_fence_after();
+            KPROF(2, 2);
             uint32_t v[KT_N1];
             const float xx = xx_s[buf][r];
             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * KT_N1, v);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(d1_empty + 8 * buf);
+            KPROF(2, 3);
             uint32_t mask = 0;                                   // bit m = 1: this point belongs to column m = t*KC + k
             constexpr int TMAX = KT_N1 / KC;
             float dmin[TMAX];
 #pragma unroll
             for (int t = 0; t < TMAX; ++t) {
-                dmin[t] = 0.f;
-                if (t < p.tries) {                               // warp-uniform
-                    float bd = 0.f;
-                    int bk = 0;
+                float bd = 0.f;
+                uint32_t bit = 0;
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) {
-                        const float d2 = fmaxf(xx - 2.f * __uint_as_float(v[t * KC + k]) + cc_s[t * KC + k], 0.f);
-                        if (k == 0 || d2 < bd) { bd = d2; bk = k; }   // first minimum wins ties (tf.argmin)
-                    }
-                    dmin[t] = bd;
-                    if (valid) mask |= 1u << (t * KC + bk);
+                for (int k = 0; k < KC; ++k) {
+                    const float cc = MODE == KT_UPDATE ? ccr[(t * KC + k) % NCC] : cc_s[t * KC + k];
+                    const float d2 = fmaxf(xx - 2.f * __uint_as_float(v[t * KC + k]) + cc, 0.f);
+                    if (k == 0 || d2 < bd) { bd = d2; bit = 1u << (t * KC + k); }   // first minimum wins ties (tf.argmin)
                 }
+                dmin[t] = bd;
+                mask |= bit;
             }
+            mask = valid ? (mask & colmask) : 0u;
+            KPROF(2, 4);
             if (MODE == KT_UPDATE) {
                 mbar_wait(oh_empty + 8 * buf, ph ^ 1);           // phase 2 of tile i-2 has finished with oh[buf]
+                KPROF(2, 5);
                 uint8_t* dst = oh_s + buf * KT_OH + (size_t)(r >> 3) * KT_OHG + (r & 7) * 16;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -304,54 +395,56 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
                 }
                 fence_async_smem();
                 mbar_arrive(oh_full + 8 * buf);
+                KPROF(2, 6);
             } else {
-                // inertia: per column m the sum of the selected squared distances and the count (fixed shuffle order)
+                // inertia: per column m the sum of the selected squared distances and the count
 #pragma unroll
-                for (int t = 0; t < TMAX; ++t) {
-                    if (t < p.tries) {
+                for (int t = 0; t < TMAX; ++t)
 #pragma unroll
-                        for (int k = 0; k < KC; ++k) {
-                            const bool mine = (mask >> (t * KC + k)) & 1u;
-                            const float s = warp_sum(mine ? dmin[t] : 0.f);
-                            const float c = (float)__popc(__ballot_sync(0xffffffffu, mine));
-                            if (lane == t * KC + k) { tot += s; cnt += c; }
-                        }
+                    for (int k = 0; k < KC; ++k) {
+                        const bool mine = (mask >> (t * KC + k)) & 1u;
+                        tot[t % TMAXI][k] += mine ? dmin[t] : 0.f;
                     }
-                }
+#pragma unroll
+                for (int j = 0; j < (KT_N1 + 1) / 2; ++j)        // bits 2j, 2j+1 of the mask -> the two halves of counter word j
+                    cpk[j] += ((mask >> (2 * j)) & 1u) | (((mask >> (2 * j + 1)) & 1u) << 16);
             }
         }
         if (MODE == KT_UPDATE) {
-            // final: rows m = lane of TMEM quadrant 0 (warp 8) hold sum_p onehot[p][m] * [x splits | ones]
-            if (q == 0) {
-                float* dst = p.part + (((size_t)b * p.chunks + chunk) * TK + lane) * (KT_E + 1);
-                float sum[KT_E];
+            // final: TMEM lane f = feature row (hi 0-39, mid 40-79, lo 80-119, ones 120), column m = (try, cluster): through
+            // shared memory (the fp32 staging block is free by now), then sum[m][e] = (hi + mid) + lo, coalesced store
+            float* fin = vs;                                     // [128][33]
+            if (ntile) { mbar_wait(done, 0); tc_fence_after(); }
+            {
+                uint32_t v[KT_N1];
+                if (ntile) { tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + KT_NBUF * KT_N1, v); tmem_ld_wait(); }
+                else {
 #pragma unroll
-                for (int e = 0; e < KT_E; ++e) sum[e] = 0.f;
-                float count = 0.f;
-                if (ntile) { mbar_wait(done, 0); tc_fence_after(); }
-#pragma unroll
-                for (int c = 0; c < KT_N2 / 16; ++c) {
-                    uint32_t v[16];
-                    if (ntile) { tmem_ld16(tmem + KT_NBUF * KT_N1 + c * 16, v); tmem_ld_wait(); }
-                    else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = 0u;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = c * 16 + j, e = n % 48;
-                        if (e < KT_E) sum[e] += __uint_as_float(v[j]);
-                        else if (n == KT_E) count = __uint_as_float(v[j]);
-                    }
+                    for (int j = 0; j < KT_N1; ++j) v[j] = 0u;
                 }
-                if (lane < TK) {
 #pragma unroll
-                    for (int e = 0; e < KT_E; ++e) dst[e] = sum[e];
-                    dst[KT_E] = count;
-                }
+                for (int j = 0; j < KT_N1; ++j) fin[r * 33 + j] = __uint_as_float(v[j]);
+            }
+            kt_sync(2, 128);
+            float* dst = p.part + ((size_t)b * p.chunks + chunk) * TK * (KT_E + 1);
+            for (int idx = r; idx < TK * (KT_E + 1); idx += 128) {
+                const int m = idx / (KT_E + 1), e = idx - m * (KT_E + 1);
+                dst[idx] = e < KT_E ? (fin[e * 33 + m] + fin[(KT_E + e) * 33 + m]) + fin[(2 * KT_E + e) * 33 + m]
+                                    : fin[KT_ONES * 33 + m];
             }
         } else {
-            fin_s[q][lane][0] = tot; fin_s[q][lane][1] = cnt;
+            // lanes in the fixed butterfly order of warp_sum, then the four warps in a fixed order
+            float mytot = 0.f, mycnt = 0.f;
+#pragma unroll
+            for (int t = 0; t < TMAXI; ++t)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int m = t * KC + k;
+                    const float s = warp_sum(tot[t][k]);
+                    const float c = warp_sum((float)((cpk[m / 2] >> (16 * (m & 1))) & 0xFFFFu));   // exact: integers < 2^24
+                    if (lane == m) { mytot = s; mycnt = c; }
+                }
+            fin_s[q][lane][0] = mytot; fin_s[q][lane][1] = mycnt;
             kt_sync(2, 128);
             if (q == 0 && lane < TK) {
                 float* dst = p.part + (((size_t)b * p.chunks + chunk) * TK + lane) * 2;
@@ -365,18 +458,22 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-constexpr size_t KT_SMEM = KT_NBUF * (size_t)KT_X3 + KT_NBUF * (size_t)KT_OH + KT_C3 + (size_t)128 * KT_PITCH * 4 + 2048;
+constexpr size_t KT_SMEM = KT_NBUF * (size_t)KT_X3 + KT_NBUF * (size_t)KT_OH + KT_C3 + (size_t)KT_NRAW * 128 * KT_E * 4 + 2048;
 
 }  // namespace
+
+void kmeans_tc_set_profile(long long* dev_buf) { g_kt_prof = dev_buf; }
 
 bool kmeans_tc_supported(int E, int K, int tries, bool soft, bool gated) {
     if (const char* e = getenv("AMSS_KMEANS_SIMT")) { if (atoi(e)) return false; }
     return !soft && !gated && E == KT_E && K >= 2 && K <= 4 && tries >= 1 && tries * K <= KT_N1;
 }
 
-int kmeans_pass_tc(const float* X, const float* cent, int Bg, int64_t L, int K, int tries, int chunks, int normalize, int mode,
-                   float* part, cudaStream_t st) {
+int kmeans_pass_tc(const float* X, const float* cent, const float* prev_part, float* cent_out, int Bg, int64_t L, int K, int tries,
+                   int chunks, int normalize, int mode, float* part, cudaStream_t st) {
     KtParams p;
+    p.prev_part = prev_part; p.cent_out = cent_out;
+    p.prof = mode == KT_UPDATE ? g_kt_prof : nullptr;
     p.X = X; p.cent = cent; p.part = part; p.L = L; p.ntiles = (L + 127) / 128; p.K = K; p.tries = tries; p.chunks = chunks;
     p.normalize = normalize;
 #define KT_LAUNCH(MODE_, KC_)                                                                                                   \

@@ -173,6 +173,9 @@ int amss_blstm_bwd(const float* x, const float* kernel_fw, const float* kernel_b
 /* Diagnostics only: clock64() stamps of the tensor-core recurrence (CTA 0, steps 100..103, 12
  * slots per step; forward at [0,48), backward at [64,112)) are written to dev_buf (>= 128 int64) by later amss_blstm_fwd calls; NULL = off. */
 int amss_debug_blstm_profile(long long* dev_buf);
+/* Diagnostics only: clock64() stamps of the tensor-core k-means update pass (CTA 0, tiles 8..11; role 0 loader, 1 MMA
+ * issuer, 2 epilogue; dev_buf[(role*4 + tile)*8 + slot], >= 96 int64) written by later amss_kmeans_fit calls; NULL = off. */
+int amss_debug_kmeans_profile(long long* dev_buf);
 /* Diagnostics only: schedule trace of the tensor-core recurrence kernels: per CTA {SM id, globaltimer ns at start, at end,
  * at the end of the prologue}; forward launches at [0, 4*4096), backward at [4*4096, 8*4096) of dev_buf (>= 8*4096 int64); NULL = off.    */
 int amss_debug_blstm_sched(long long* dev_buf);
