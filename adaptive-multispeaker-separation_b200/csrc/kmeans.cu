@@ -9,11 +9,13 @@
 // Per-CTA partials are reduced in a fixed order by a small finalize kernel.
 //
 // HBM traffic: the input is L2-normalised ON THE FLY while a tile is staged (tf.nn.l2_normalize, Kmeans_2.py:40-41): no
-// normalised copy is written or re-read.  The batch is processed in GROUPS of mixtures whose X (10.24 MB per mixture at
-// TF = 64000, E = 40) fits the 126 MB L2 together: all iterations + the inertia pass + the final assignment of a group run
-// before the next group starts, so X is fetched from HBM once per group and the remaining (iters + 2) passes hit L2.
+// normalised copy is written or re-read.  The batch is processed in GROUPS of mixtures: all iterations + the inertia pass +
+// the final assignment of a group run before the next group starts.  A group that fits the 126 MB L2 (9 mixtures of 10.24 MB
+// at TF = 64000, E = 40) fetches X from HBM once; since the tensor-core pass became issue-bound rather than byte-bound the
+// default group is larger (km_group: fewer, longer passes amortise the fixed cost of a pass) and X streams from HBM.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace amss {
 
@@ -353,6 +355,66 @@ kmeans_assign_kernel(const float* __restrict__ X, const float* __restrict__ cent
     }
 }
 
+// Hard final assignment, E = 40, no silence gate (the inference path of config 5): the arithmetic of kmeans_assign_kernel<0>
+// per point (sequential sums, sqrt, first minimum), with the tile staged by coalesced 16-byte loads into a 44-float pitch
+// (conflict-free LDS.128 of a row) and the row held in registers.
+constexpr int KA_E = 40, KA_PITCH = 44, KA_TILE = 256;
+__global__ void __launch_bounds__(KA_TILE)
+kmeans_assign_hard40_kernel(const float* __restrict__ X, const float* __restrict__ cent, int normalize, int64_t L, int K,
+                            int* __restrict__ labels) {
+    __shared__ __align__(16) float xs[KA_TILE * KA_PITCH];
+    __shared__ __align__(16) float cs[KM_MAXK * KA_E];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < K * KA_E; i += KA_TILE) cs[i] = cent[(size_t)b * K * KA_E + i];
+    const int64_t ntiles = (L + KA_TILE - 1) / KA_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p0 = tile * KA_TILE;
+        const int np = (int)((L - p0) < KA_TILE ? (L - p0) : KA_TILE);
+        const float4* src = reinterpret_cast<const float4*>(X + ((size_t)b * L + p0) * KA_E);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KA_E / 4; ++j) {
+            const int u = tid + KA_TILE * j, rr = u / (KA_E / 4), c = u - rr * (KA_E / 4);
+            if (u < np * (KA_E / 4)) *reinterpret_cast<float4*>(xs + rr * KA_PITCH + c * 4) = __ldg(src + u);
+        }
+        __syncthreads();
+        if (tid < np) {
+            float x[KA_E];
+#pragma unroll
+            for (int c = 0; c < KA_E / 4; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(xs + tid * KA_PITCH + c * 4);
+                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+            if (normalize) {
+                float ss = 0.f;
+#pragma unroll
+                for (int e = 0; e < KA_E; ++e) ss = fmaf(x[e], x[e], ss);
+                const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+#pragma unroll
+                for (int e = 0; e < KA_E; ++e) x[e] *= inv;
+            }
+            int bi = 0;
+            float bd = 0.f;
+#pragma unroll
+            for (int k = 0; k < KM_MAXK; ++k)
+                if (k < K) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int c = 0; c < KA_E / 4; ++c) {
+                        const float4 cv = *reinterpret_cast<const float4*>(cs + k * KA_E + c * 4);
+                        float d = x[4 * c] - cv.x; a = fmaf(d, d, a);
+                        d = x[4 * c + 1] - cv.y; a = fmaf(d, d, a);
+                        d = x[4 * c + 2] - cv.z; a = fmaf(d, d, a);
+                        d = x[4 * c + 3] - cv.w; a = fmaf(d, d, a);
+                    }
+                    const float dk = sqrtf(a);
+                    if (k == 0 || dk < bd) { bd = dk; bi = k; }
+                }
+            labels[(size_t)b * L + p0 + tid] = bi;
+        }
+    }
+}
+
 // max over L of latent per batch row, then notsilent = log10(max/latent) < threshold (Kmeans_2.py:76-79)
 __global__ void row_max_kernel(const float* __restrict__ x, int64_t L, float* __restrict__ out) {
     __shared__ float red[32];
@@ -411,7 +473,13 @@ int km_chunks_tc(int Bg, int64_t L) {
 // groups (64 mixtures = 8 groups of 8 rather than 7 of 9 and a group of one).
 int km_group(int B, int64_t L, int E) {
     const double per = (double)L * E * 4.0;
-    int g = (int)(96.0e6 / per);
+    // The passes are bound by instruction / tensor issue (~1700 clk per 128-point tile, 20 KB), not by bytes: 64 mixtures in
+    // one group stream 655 MB per pass from HBM at ~2.8 TB/s and finish sooner (2.85 ms) than eight L2-resident groups of
+    // 8 (3.61 ms), because every pass of every group pays ~14 us of launch / prologue / drain.  AMSS_KMEANS_GROUP_MB=96
+    // restores the L2-resident schedule (12x fewer DRAM bytes).
+    double budget = 700.0e6;
+    if (const char* e = getenv("AMSS_KMEANS_GROUP_MB")) { const double v = atof(e); if (v > 0.0) budget = v * 1.0e6; }
+    int g = (int)(budget / per);
     if (g < 1) g = 1;
     if (g >= B) return B;
     const int ngroups = (B + g - 1) / g;
@@ -532,7 +600,11 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
         // final labels: un-gated X if assign_at_end (Kmeans_2.py:106-107), else the best try's gated labels
         const uint8_t* ns_final = assign_at_end ? nullptr : notsilent;
         dim3 grid((unsigned)std::min<int64_t>((L + KM_TILE - 1) / KM_TILE, (int64_t)std::max(1, 4 * kNumSMs / Bg)), Bg);
-        if (is_soft) {
+        if (!is_soft && ns_final == nullptr && E == KA_E && (((uintptr_t)Xg & 15) == 0)) {
+            dim3 gridf((unsigned)std::min<int64_t>((L + KA_TILE - 1) / KA_TILE, (int64_t)std::max(1, 4 * kNumSMs / Bg)), Bg);
+            AMSS_LAUNCH(kmeans_assign_hard40_kernel, gridf, KA_TILE, 0, st, Xg, centroids_g, normalize_input, L, K,
+                        labels + (size_t)b0 * L);
+        } else if (is_soft) {
             AMSS_LAUNCH(kmeans_assign_kernel<1>, grid, KM_THREADS, smem, st, Xg, centroids_g, ns_final, best_try + b0, B, b0,
                         normalize_input, L, E, K, tries, beta, (int*)nullptr, soft + (size_t)b0 * L * K);
         } else {

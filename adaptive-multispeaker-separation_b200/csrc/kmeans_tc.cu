@@ -6,20 +6,23 @@
 //            lo.hi; the dropped terms are below 2^-24 |x||c|), M = 128 points, N = 32 centroid columns, K = 48 per split;
 //            d^2 = |x|^2 - 2 dot + |c|^2, arg-min over the clusters of each try in the epilogue thread that owns the
 //            point (TMEM lane = point: all tries x clusters of a point sit in one thread's registers, no shuffles);
-//   phase 2  sum[(t,k)][e] = sum_p onehot[p][(t,k)] x[p][e]  with the one-hot matrix (exact in bf16) as the MN-major A
-//            operand and the SAME operand tile of x splits as the MN-major B operand (K = points); a ones column in the
-//            tile's padding yields the counts.  The accumulator stays in TMEM for all tiles of the CTA.
-// Phase 1 reads its A operand (the x splits, K-major) from TENSOR MEMORY: the loader thread that owns a point's (half) row
-// also parks the packed splits in its TMEM lane (tcgen05.st); with both operands in shared memory every one of the 18
-// small-N MMAs of a tile paid ~100 clk of operand fetch (5000 clk per tile measured, unchanged by more loader warps or a
-// deeper ring), from TMEM they issue at ~36 clk.
-// The operand tile of 128 points is built once per tile: coalesced float4 fetch (software-pipelined in registers) ->
-// fp32 rows in shared memory -> the row owner normalises (tf.nn.l2_normalize, Kmeans_2.py:40-41), splits and writes 18
-// 16-byte units (3 splits x 48 features) in the canonical core-matrix layout: read K-major by phase 1 (LBO = 128,
-// SBO = 2304) and MN-major by phase 2 (LBO = 2304, SBO = 128).
-// Warp roles: 0-7 loaders (a point's row is split between two threads: features [0,24) and [24,48), because one warp per
-// scheduler left the normalise / split chain latency-bound: ncu 14 % active warps, 5000 clk per tile), 8 MMA issuer
-// (+TMEM), 9-12 epilogue.  HBM/L2-bound by design: 4E bytes per point and pass.
+//   phase 2  D2[feature row][(t,k)] = sum_p xsplit[p][feature] onehot[p][(t,k)]: the x splits are the MN-major A operand
+//            (M = 128 rows: hi 0-39, mid 40-79, lo 80-119, the ones column 120 -> counts), the one-hot tile (exact in bf16)
+//            the MN-major B operand (N = 32), K = points; the accumulator (32 TMEM columns) stays resident for all tiles
+//            of the CTA and is reduced to sum[(t,k)][e] = (hi + mid) + lo once at the end.
+// Phase 1 reads its A operand (the x splits, K-major) from TENSOR MEMORY: the loader thread that owns a point's row also parks
+// the packed splits in its TMEM lane (tcgen05.st); with both operands in shared memory every one of the 18 small-N MMAs of a
+// tile paid ~100 clk of operand fetch, from TMEM they issue at ~36 clk.  (Phase 2's 8 MMAs still pay it: their A operand
+// would have to sit feature-per-lane in TMEM, and a thread can only write its own lane.)
+// Raw tiles (128 points x 160 B, contiguous in X) arrive by ONE TMA bulk copy each into a 4-deep ring (a producer warp; 128
+// row copies into a padded pitch cost ~50 clk each on the TMA engine).  ONE loader thread owns a row: conflict-free LDS.128
+// of the dense rows (the upper half of a quarter-warp reads its chunks rotated by one), normalise (tf.nn.l2_normalize,
+// Kmeans_2.py:40-41), split, 16 stores of 16 bytes in the canonical core-matrix layout (phase-2 operand) + 18 tcgen05.st
+// (phase-1 operand); the two loader groups (4 warps each) take alternate tiles; no CTA-wide barrier anywhere in the loop.
+// The epilogue thread owns a point: |c|^2 in registers, branch-free arg-min over the clusters of every try, one-hot row.
+// Measured per tile (tools/kmeans_tile_profile.py, profiles/r02l_kmeans_tile_profile.txt): 2900 clk -> 1740 clk; what is left
+// is the tensor pipe's fixed cost per small MMA (18 x ~36 + 8 x ~100 clk) and the SM's instruction issue.
+// Warp roles: 0-7 loaders, 8 MMA issuer (+TMEM), 9-12 epilogue, 13 TMA producer.
 // Restrictions (anything else takes the SIMT kernels of kmeans.cu): hard assignments, E == 40, tries*K <= 32, no silence
 // gate.
 #include "common.cuh"
@@ -123,11 +126,17 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         if (p.prev_part) {
             const int m = idx / KT_E, e = idx - m * KT_E;
             float sacc = 0.f, cacc = 0.f;
-            for (int ch = 0; ch < p.chunks; ++ch) {
-                const float* q = p.prev_part + (((size_t)b * p.chunks + ch) * TK + m) * (KT_E + 1);
-                sacc += q[e];
-                cacc += q[KT_E];
+            const float* q0 = p.prev_part + ((size_t)b * p.chunks * TK + m) * (KT_E + 1);
+            const size_t qs = (size_t)TK * (KT_E + 1);
+            int ch = 0;
+            for (; ch + 6 <= p.chunks; ch += 6) {                // six chunks' loads in flight, added in chunk order
+                float sv[6], cv[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { sv[j] = q0[(ch + j) * qs + e]; cv[j] = q0[(ch + j) * qs + KT_E]; }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { sacc += sv[j]; cacc += cv[j]; }
             }
+            for (; ch < p.chunks; ++ch) { sacc += q0[ch * qs + e]; cacc += q0[ch * qs + KT_E]; }
             v = sacc / cacc;
             if (chunk == 0 && p.cent_out) p.cent_out[(size_t)b * TK * KT_E + idx] = v;
         } else {

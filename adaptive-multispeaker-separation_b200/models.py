@@ -602,7 +602,24 @@ class KMeans:
         B, Lp, E = X.shape
         if init_idx is None:
             init_idx = self.random_init(B * self.nb_tries, Lp)
-        idx = torch.as_tensor(np.asarray(init_idx), dtype=torch.int32).to(X.device).contiguous()
+        if torch.is_tensor(init_idx) and init_idx.is_cuda:
+            idx = init_idx.to(torch.int32).contiguous()
+        else:
+            # pinned staging + asynchronous copy: a pageable .to(device) blocks the host until the GPU has drained everything
+            # queued before it (the whole trunk of this step), which serialises a streaming loop
+            host = torch.as_tensor(np.asarray(init_idx), dtype=torch.int32).contiguous()
+            ring = getattr(self, "_idx_ring", None)
+            if ring is None or ring[0][0].shape != host.shape:
+                ring = self._idx_ring = [[torch.empty(host.shape, dtype=torch.int32).pin_memory(), None] for _ in range(4)]
+                self._idx_k = 0
+            buf = ring[self._idx_k]
+            self._idx_k = (self._idx_k + 1) % len(ring)
+            if buf[1] is not None:
+                buf[1].synchronize()                     # the copy that last used this staging buffer has run
+            buf[0].copy_(host)
+            idx = buf[0].to(X.device, non_blocking=True)
+            buf[1] = torch.cuda.Event()
+            buf[1].record(torch.cuda.current_stream())
         ns = None
         if self.latent is not None:
             ns = ops.kmeans_silence_mask(self.latent.reshape(B, Lp).contiguous(), self.threshold)

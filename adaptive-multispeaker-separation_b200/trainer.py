@@ -693,11 +693,14 @@ class _StreamingInference:
         d2h = torch.cuda.Stream()
         host, done, pending, k, n = [None, None], [None, None], None, 0, 0
         while slot is not None and (steps is None or n < steps):
-            out = self._infer_batch(pf.get(slot))
-            pf.release(slot)
+            # the next batch's H2D copy goes out BEFORE this batch's kernels are queued (it targets the other device slot,
+            # last read two steps ago), so it overlaps the whole step
             n += 1
             nxt = next(it, None) if (steps is None or n < steps) else None
-            slot = pf.submit(as_pinned(nxt)) if nxt is not None else None
+            nslot = pf.submit(as_pinned(nxt)) if nxt is not None else None
+            out = self._infer_batch(pf.get(slot))
+            pf.release(slot)
+            slot = nslot
             if host[k] is None or host[k].shape != out.shape:
                 host[k] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
             ready = torch.cuda.Event()
