@@ -691,7 +691,10 @@ class _StreamingInference:
         pf = DevicePrefetcher(nxt)
         slot = pf.submit(nxt)
         d2h = torch.cuda.Stream()
-        host, done, pending, k, n = [None, None], [None, None], None, 0, 0
+        # the two pinned result buffers live on the instance: pinning 49 MB costs ~30 ms, once, not once per call
+        if not hasattr(self, "_host_out"):
+            self._host_out = [None, None]
+        host, done, pending, k, n = self._host_out, [None, None], None, 0, 0
         while slot is not None and (steps is None or n < steps):
             # the next batch's H2D copy goes out BEFORE this batch's kernels are queued (it targets the other device slot,
             # last read two steps ago), so it overlaps the whole step
