@@ -483,6 +483,37 @@ def test_kmeans_hard_bit_exact(ops, K, tries, with_silence, assign_at_end):
             assert _same_partition(labels[b].cpu(), l_ref[b], K)
 
 
+@pytest.mark.parametrize("B,L,K,tries", [(1, 100, 2, 1), (1, 128, 3, 10), (2, 129, 4, 8), (3, 257, 3, 10), (5, 1000, 2, 16),
+                                         (20, 700, 3, 4), (150, 300, 3, 2), (2, 20000, 3, 10)])
+def test_kmeans_tensor_core_pass_matches_simt_kernels(ops, B, L, K, tries, monkeypatch):
+    """The tcgen05 k-means pass (kmeans_tc.cu: TMA tile ring, two loader groups on alternate tiles, chained passes, one
+    wave of CTAs) against the fp32 SIMT kernels (AMSS_KMEANS_SIMT=1) over geometries that exercise its edges: a single
+    partial tile, exact / off-by-one tile counts, fewer tiles than ring slots, more mixtures than SMs (chunks = 1),
+    tries * K = 32, many tiles per CTA.  Same initial rows: same best try, same labels off near-ties, centroids to 1e-5."""
+    E, iters = 40, 5
+    X, _ = _blobs(B, L, E, K, seed=300 + B + L)
+    idx = random_init_idx(B * tries, L, K, np.random.RandomState(301))
+    Xd, idxd = dev(X), dev(idx)
+    monkeypatch.setenv("AMSS_KMEANS_SIMT", "1")
+    c0, l0, i0, b0 = ops.kmeans_fit(Xd, idxd, K, tries, iters, None, None, True, True)
+    monkeypatch.setenv("AMSS_KMEANS_SIMT", "0")
+    c1, l1, i1, b1 = ops.kmeans_fit(Xd, idxd, K, tries, iters, None, None, True, True)
+    torch.cuda.synchronize()
+    ok = ~torch.isnan(i0)
+    assert torch.equal(torch.isnan(i1), ~ok)
+    assert rel(i1[ok], i0[ok]) < 1e-5
+    Xn = torch.tensor(X) / torch.tensor(X).norm(dim=-1, keepdim=True)
+    for b in range(B):
+        if int(b0[b]) != int(b1[b]):                           # two tries tie to rounding: same partition required
+            assert abs(float(i0[b, b1[b]] - i0[b, b0[b]])) < 1e-5 * abs(float(i0[b, b0[b]]))
+            assert _same_partition(l1[b].cpu(), l0[b].cpu(), K)
+            continue
+        assert rel(c1[b], c0[b]) < 1e-5
+        d = ((Xn[b].unsqueeze(1) - c0[b].cpu().unsqueeze(0)) ** 2).sum(-1).sort(-1).values
+        safe = (d[:, 1] - d[:, 0]) > 1e-5
+        assert torch.equal(l1[b].cpu()[safe], l0[b].cpu()[safe])
+
+
 def test_kmeans_soft_matches_oracle(ops):
     B, L, E, K, tries, iters = 2, 2000, 40, 2, 3, 5
     X, _ = _blobs(B, L, E, K, seed=70, spread=0.2)
