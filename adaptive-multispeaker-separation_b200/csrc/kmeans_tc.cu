@@ -380,7 +380,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
                     const float cc = MODE == KT_UPDATE ? ccr[(t * KC + k) % NCC] : cc_s[t * KC + k];
-                    const float d2 = fmaxf(xx - 2.f * __uint_as_float(v[t * KC + k]) + cc, 0.f);
+                    // clamp rounding negatives, but keep NaN (an empty cluster's 0/0 centroid): fmaxf(NaN, 0) = 0 would make
+                    // the NaN cluster everybody's nearest; `NaN < bd` is false, as in the SIMT kernels and tf.argmin
+                    const float dr = xx - 2.f * __uint_as_float(v[t * KC + k]) + cc;
+                    const float d2 = dr < 0.f ? 0.f : dr;
                     if (k == 0 || d2 < bd) { bd = d2; bit = 1u << (t * KC + k); }   // first minimum wins ties (tf.argmin)
                 }
                 dmin[t] = bd;

@@ -488,8 +488,9 @@ def test_kmeans_hard_bit_exact(ops, K, tries, with_silence, assign_at_end):
 def test_kmeans_tensor_core_pass_matches_simt_kernels(ops, B, L, K, tries, monkeypatch):
     """The tcgen05 k-means pass (kmeans_tc.cu: TMA tile ring, two loader groups on alternate tiles, chained passes, one
     wave of CTAs) against the fp32 SIMT kernels (AMSS_KMEANS_SIMT=1) over geometries that exercise its edges: a single
-    partial tile, exact / off-by-one tile counts, fewer tiles than ring slots, more mixtures than SMs (chunks = 1),
-    tries * K = 32, many tiles per CTA.  Same initial rows: same best try, same labels off near-ties, centroids to 1e-5."""
+    partial tile, exact / off-by-one tile counts, fewer tiles than ring slots, more mixtures than SMs (chunks = 1; with two
+    tries some mixtures end with an EMPTY cluster, whose NaN centroid must never be anybody's nearest), tries * K = 32, many
+    tiles per CTA.  Same initial rows: same best try, same labels off near-ties, centroids to 1e-5."""
     E, iters = 40, 5
     X, _ = _blobs(B, L, E, K, seed=300 + B + L)
     idx = random_init_idx(B * tries, L, K, np.random.RandomState(301))
@@ -501,16 +502,20 @@ def test_kmeans_tensor_core_pass_matches_simt_kernels(ops, B, L, K, tries, monke
     torch.cuda.synchronize()
     ok = ~torch.isnan(i0)
     assert torch.equal(torch.isnan(i1), ~ok)
-    assert rel(i1[ok], i0[ok]) < 1e-5
+    # (the tensor-core pass evaluates |x|^2 - 2 x.c + |c|^2, the SIMT kernels sum (x - c)^2: the inertia of tight blobs is
+    # a sum of cancellations in the former)
+    assert rel(i1[ok], i0[ok]) < 2e-4
     Xn = torch.tensor(X) / torch.tensor(X).norm(dim=-1, keepdim=True)
     for b in range(B):
         if int(b0[b]) != int(b1[b]):                           # two tries tie to rounding: same partition required
-            assert abs(float(i0[b, b1[b]] - i0[b, b0[b]])) < 1e-5 * abs(float(i0[b, b0[b]]))
+            assert abs(float(i0[b, b1[b]] - i0[b, b0[b]])) < 2e-4 * abs(float(i0[b, b0[b]]))
             assert _same_partition(l1[b].cpu(), l0[b].cpu(), K)
             continue
-        assert rel(c1[b], c0[b]) < 1e-5
+        nan0 = torch.isnan(c0[b])                              # an empty cluster's centroid is 0/0 in both paths (Kmeans_2.py:158-165)
+        assert torch.equal(torch.isnan(c1[b]), nan0)
+        assert rel(c1[b][~nan0], c0[b][~nan0]) < 1e-5
         d = ((Xn[b].unsqueeze(1) - c0[b].cpu().unsqueeze(0)) ** 2).sum(-1).sort(-1).values
-        safe = (d[:, 1] - d[:, 0]) > 1e-5
+        safe = (d[:, 1] - d[:, 0]) > 1e-4
         assert torch.equal(l1[b].cpu()[safe], l0[b].cpu()[safe])
 
 
