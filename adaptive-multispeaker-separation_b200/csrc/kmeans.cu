@@ -14,6 +14,7 @@
 // at TF = 64000, E = 40) fetches X from HBM once; since the tensor-core pass became issue-bound rather than byte-bound the
 // default group is larger (km_group: fewer, longer passes amortise the fixed cost of a pass) and X streams from HBM.
 #include "common.cuh"
+#include "kmeans_pieces.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -22,6 +23,7 @@ namespace amss {
 // tensor-core pass (kmeans_tc.cu): hard assignments, E = 40, K in {2,3,4}, tries*K <= 32, no silence gate
 bool kmeans_tc_supported(int E, int K, int tries, bool soft, bool gated);
 void kmeans_tc_set_profile(long long* dev_buf);
+void kmeans_tc_geometry(int Bg, int64_t L, int* G_out, int* pmax_out);
 int kmeans_pass_tc(const float* X, const float* cent, const float* prev_part, float* cent_out, int Bg, int64_t L, int K, int tries,
                    int chunks, int normalize, int mode, float* part, cudaStream_t st);
 
@@ -226,8 +228,15 @@ __global__ void kmeans_finalize_kernel(const float* __restrict__ part, int B, in
 // cluster -- is never selected, as with tf.argmin's `<` reducer) ; centroids_out[b] = cent[b*tries+best]   (Kmeans_2.py:99-104)
 __global__ void kmeans_select_kernel(const float* __restrict__ part, const float* __restrict__ cent, int B,
                                      int chunks, int tries, int K, int E, float* __restrict__ inertia_out,
-                                     int* __restrict__ best_out, float* __restrict__ cent_out) {
+                                     int* __restrict__ best_out, float* __restrict__ cent_out, int64_t nt, int64_t Tt, int G) {
     const int b = blockIdx.x;
+    if (G > 0) {                // partials of the tensor-core pass: mixture b has kt_pieces() of the `chunks` slots filled
+        int c0, n;
+        kt_pieces(b, nt, Tt, G, c0, n);
+        const int pitch = chunks;
+        chunks = n;
+        part += (size_t)b * (pitch - n) * tries * K * 2;        // rows of mixture b start at b * pitch
+    }
     __shared__ int sbest;
     __shared__ float ratio[128];
     // one thread per (try, cluster): the chunks in sequence, as before; thread 0 adds the clusters of a try in order
@@ -459,14 +468,14 @@ int km_chunks(int B, int64_t L) {
     return (int)(ntiles < want ? ntiles : want);
 }
 
-// The tensor-core pass runs ONE CTA per SM (512 TMEM columns, 165 KB of shared memory) and every CTA gets the same number
-// of tiles, so its grid must not spill into a second, nearly empty wave: chunks = floor(SMs / Bg) (Bg * chunks <= SMs; with
-// 2 * SMs / Bg a group of 9 mixtures launched 297 CTAs = two waves + ONE straggler CTA, a third of the pass time).
+// The tensor-core pass runs ONE CTA per SM (512 TMEM columns, ~210 KB of shared memory) in ONE wave: the Bg * ntiles tiles of
+// the group are cut into min(SMs, tiles) equal contiguous ranges, whatever Bg is (kmeans_pieces.cuh; with whole chunks per
+// mixture 64 mixtures filled 128 of the 148 SMs, and a group of 9 launched 297 CTAs = two waves + ONE straggler CTA).
+// km_chunks_tc = the most pieces a mixture is cut into = the row pitch of the partial sums.
 int km_chunks_tc(int Bg, int64_t L) {
-    const int64_t ntiles = (L + 127) / 128;
-    int64_t want = kNumSMs / Bg;
-    if (want < 1) want = 1;
-    return (int)(ntiles < want ? ntiles : want);
+    int G, pmax;
+    kmeans_tc_geometry(Bg, L, &G, &pmax);
+    return pmax;
 }
 
 // Mixtures per group: as many as keep the group's X inside ~3/4 of the 126 MB L2 (at least 1), then evened out over the
@@ -497,9 +506,10 @@ KmWs km_ws(void* base, int B, int64_t L, int E, int K, int tries) {
     const int G = km_group(B, L, E);
     w.cent = (float*)(p + off); off += align_up((size_t)B * tries * K * E * 4, 256);
     // Bg * km_chunks(Bg) <= 2 * SMs + Bg - 1 for every group size Bg <= G (a smaller last group gets more chunks per mixture)
-    w.part = (float*)(p + off); off += align_up((size_t)(2 * kNumSMs + G) * tries * K * (E + 1) * 4, 256);
+    // (and Bg * pieces <= SMs + 2 * Bg for the flat decomposition of the tensor-core pass)
+    w.part = (float*)(p + off); off += align_up((size_t)(2 * kNumSMs + 2 * G) * tries * K * (E + 1) * 4, 256);
     // second buffer: the tensor-core pass reduces the previous pass's partial sums in its prologue while it writes its own
-    w.part2 = (float*)(p + off); off += align_up((size_t)(2 * kNumSMs + G) * tries * K * (E + 1) * 4, 256);
+    w.part2 = (float*)(p + off); off += align_up((size_t)(2 * kNumSMs + 2 * G) * tries * K * (E + 1) * 4, 256);
     w.total = off;
     return w;
 }
@@ -563,7 +573,7 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
         const float* Xg = X + (size_t)b0 * L * E;
         float* centg = w.cent + (size_t)b0 * tries * K * E;
         // (the inertia pass of the tensor-core kernel counts a CTA's tiles in 16-bit counters)
-        const bool tcp = use_tc && (((uintptr_t)Xg & 15) == 0) && (L + 127) / 128 / km_chunks_tc(Bg, L) < 65000;
+        const bool tcp = use_tc && (((uintptr_t)Xg & 15) == 0) && (L + 127) / 128 * Bg / kNumSMs < 65000;
         const int chunks = tcp ? km_chunks_tc(Bg, L) : km_chunks(Bg, L);
         AMSS_LAUNCH(kmeans_gather_init_kernel, 64, 256, 0, st, Xg, init_idx + (size_t)b0 * tries * K, Bg, L, E, K, tries,
                     normalize_input, centg);
@@ -595,8 +605,11 @@ extern "C" int amss_kmeans_fit(const float* X, const int32_t* init_idx, const ui
             if (rc != AMSS_OK) return rc;
         }
         float* centroids_g = centroids + (size_t)b0 * K * E;
+        int tcG = 0, tcP = 0;
+        if (tcp) kmeans_tc_geometry(Bg, L, &tcG, &tcP);
         AMSS_LAUNCH(kmeans_select_kernel, Bg, 128, 0, st, inertia_part, centg, Bg, chunks, tries, K, E,
-                    inertia ? inertia + (size_t)b0 * tries : nullptr, best_try + b0, centroids_g);
+                    inertia ? inertia + (size_t)b0 * tries : nullptr, best_try + b0, centroids_g, (L + 127) / 128,
+                    (int64_t)Bg * ((L + 127) / 128), tcG);
         // final labels: un-gated X if assign_at_end (Kmeans_2.py:106-107), else the best try's gated labels
         const uint8_t* ns_final = assign_at_end ? nullptr : notsilent;
         dim3 grid((unsigned)std::min<int64_t>((L + KM_TILE - 1) / KM_TILE, (int64_t)std::max(1, 4 * kNumSMs / Bg)), Bg);

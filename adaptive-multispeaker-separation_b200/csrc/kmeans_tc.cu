@@ -27,6 +27,7 @@
 // gate.
 #include "common.cuh"
 #include "tc.cuh"
+#include "kmeans_pieces.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -68,8 +69,9 @@ struct KtParams {
                            // them in the prologue (the arithmetic of kmeans_finalize_kernel, no launch in between) ...
     float* cent_out;       // ... and written here by the first CTA of every mixture (may be null)
     float* part;           // UPDATE: [Bg][chunks][tries*K][E+1]; INERTIA: [Bg][chunks][tries*K][2]
-    int64_t L, ntiles;
-    int K, tries, chunks, normalize;
+    int64_t L, ntiles, Tt;   // points and 128-point tiles per mixture, tiles of the group
+    int K, tries, chunks, normalize;   // chunks = row pitch of `part` in pieces per mixture (>= the most pieces any mixture has)
+    int G;                 // CTAs = equal contiguous ranges of the group's flat tile list (kmeans_pieces.cuh)
 };
 
 __device__ __forceinline__ void kt_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -98,7 +100,6 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
     __shared__ float xx_s[KT_NBUF][128];
     __shared__ float fin_s[4][32][2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
     const int TK = p.tries * KC;
     uint8_t* x3_s = smem;                                        // [NBUF][KT_X3]
     uint8_t* oh_s = x3_s + KT_NBUF * KT_X3;                      // [NBUF][KT_OH]  (the MMA also reads the 1.5 KB behind a tile:
@@ -118,9 +119,27 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 512);
-    // centroids of this mixture: cent[m][e] = sum_chunks part_sum / sum_chunks part_cnt (Kmeans_2.py:158-165; chunks in
-    // sequence, an empty cluster gives 0/0 = NaN as in the reference), or the given ones
+    for (uint32_t i = tid * 16; i < KT_NBUF * KT_OH; i += KT_THREADS * 16) *reinterpret_cast<uint4*>(oh_s + i) = make_uint4(0, 0, 0, 0);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
     __shared__ float cent_s[KT_N1 * KT_E];
+    // this CTA's range of the group's flat tile list, walked mixture by mixture ("segments"; the rings and their mbarrier
+    // phases run on through the segments: ibase = tiles of the earlier segments)
+    const int64_t f0 = kt_start(blockIdx.x, p.Tt, p.G), f1 = kt_start(blockIdx.x + 1, p.Tt, p.G);
+    uint32_t ibase = 0, seg = 0;
+    for (int64_t fs = f0; fs < f1; ++seg) {
+    const int b = (int)(fs / p.ntiles);
+    const int64_t t0 = fs - (int64_t)b * p.ntiles;
+    const int64_t fe = min(f1, (int64_t)(b + 1) * p.ntiles);
+    const uint32_t ntile = (uint32_t)(fe - fs);
+    fs = fe;
+    int c_first, npieces;
+    kt_pieces(b, p.ntiles, p.Tt, p.G, c_first, npieces);
+    const int chunk = (int)blockIdx.x - c_first;                 // which piece of mixture b this segment is
+    // centroids of this mixture: cent[m][e] = sum_pieces part_sum / sum_pieces part_cnt (Kmeans_2.py:158-165; pieces in
+    // sequence, an empty cluster gives 0/0 = NaN as in the reference), or the given ones
     for (int idx = tid; idx < TK * KT_E; idx += KT_THREADS) {
         float v;
         if (p.prev_part) {
@@ -129,14 +148,14 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
             const float* q0 = p.prev_part + ((size_t)b * p.chunks * TK + m) * (KT_E + 1);
             const size_t qs = (size_t)TK * (KT_E + 1);
             int ch = 0;
-            for (; ch + 6 <= p.chunks; ch += 6) {                // six chunks' loads in flight, added in chunk order
+            for (; ch + 6 <= npieces; ch += 6) {                 // six pieces' loads in flight, added in piece order
                 float sv[6], cv[6];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) { sv[j] = q0[(ch + j) * qs + e]; cv[j] = q0[(ch + j) * qs + KT_E]; }
 #pragma unroll
                 for (int j = 0; j < 6; ++j) { sacc += sv[j]; cacc += cv[j]; }
             }
-            for (; ch < p.chunks; ++ch) { sacc += q0[ch * qs + e]; cacc += q0[ch * qs + KT_E]; }
+            for (; ch < npieces; ++ch) { sacc += q0[ch * qs + e]; cacc += q0[ch * qs + KT_E]; }
             v = sacc / cacc;
             if (chunk == 0 && p.cent_out) p.cent_out[(size_t)b * TK * KT_E + idx] = v;
         } else {
@@ -170,14 +189,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
             for (int e = 0; e < KT_E; ++e) { const float x = cent_s[tid * KT_E + e]; a = fmaf(x, x, a); }
         cc_s[tid] = a;
     }
-    for (uint32_t i = tid * 16; i < KT_NBUF * KT_OH; i += KT_THREADS * 16) *reinterpret_cast<uint4*>(oh_s + i) = make_uint4(0, 0, 0, 0);
     fence_async_smem();
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_base_s;
-    const int64_t t0 = p.ntiles * chunk / p.chunks, t1 = p.ntiles * (chunk + 1) / p.chunks;
-    const uint32_t ntile = (uint32_t)(t1 - t0);
 
     if (warp < 8) {
         // ================= loaders: tile -> fp32 rows -> normalise -> 3 bf16 splits in the operand layout =================
@@ -187,9 +200,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         const int r = tid & 127, g = tid >> 7;
         long long* prof = (blockIdx.x == 0 && r == 0) ? p.prof : nullptr;
         const int rot = (r >> 2) & 1;
-        for (uint32_t i = g; i < ntile; i += 2) {
-            const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
-            const uint32_t slot = i % KT_NRAW, rph = (i / KT_NRAW) & 1;
+        for (uint32_t i = (g + ibase) & 1; i < ntile; i += 2) {  // group g takes the tiles whose running index is g mod 2
+            const uint32_t ig = ibase + i;
+            const uint32_t buf = ig % KT_NBUF, ph = (ig / KT_NBUF) & 1;
+            const uint32_t slot = ig % KT_NRAW, rph = (ig / KT_NRAW) & 1;
             const int64_t p0 = (t0 + i) * 128;
             const bool valid = p0 + r < p.L;
             KPROF(0, 0);
@@ -247,7 +261,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
                 for (int sp = 0; sp < 3; ++sp) {
                     // the padding chunk (features 40-47) carries the ones column in the hi split and zeros in the others:
                     // those zeros are written on the first use of a buffer only (nothing else touches them)
-                    if (c == 5 && sp > 0 && i >= KT_NBUF) continue;
+                    if (c == 5 && sp > 0 && ig >= KT_NBUF) continue;
                     const uint32_t w0 = pack_trunc(sp3[sp][0], sp3[sp][1]), w1 = pack_trunc(sp3[sp][2], sp3[sp][3]),
                                    w2 = pack_trunc(sp3[sp][4], sp3[sp][5]), w3 = pack_trunc(sp3[sp][6], sp3[sp][7]);
                     // phase-2 operand: feature chunk c of split sp -> chunk sp*5 + c, the ones chunk -> chunk 15
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         long long* prof = (blockIdx.x == 0 && leader) ? p.prof : nullptr;
         auto phase2 = [&](uint32_t j) {                           // sums of tile j: [x splits | ones]^T onehot  (M = 128 feature rows,
                                                                   // N = 32 columns, K = points: 8 small MMAs instead of 8 of N = 144)
-            const uint32_t bj = j % KT_NBUF, pj = (j / KT_NBUF) & 1;
+            const uint32_t bj = (ibase + j) % KT_NBUF, pj = ((ibase + j) / KT_NBUF) & 1;
             mbar_wait(oh_full + 8 * bj, pj);
             tc_fence_after();
             { const uint32_t i = j + 1; KPROF(1, 4); }
@@ -288,7 +302,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
             { const uint32_t i = j + 1; KPROF(1, 5); }
         };
         for (uint32_t i = 0; i < ntile; ++i) {
-            const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
+            const uint32_t buf = (ibase + i) % KT_NBUF, ph = ((ibase + i) / KT_NBUF) & 1;
             KPROF(1, 0);
             mbar_wait(x3_full + 8 * buf, ph);
             KPROF(1, 1);
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         // ================= producer: one TMA bulk copy per tile (128 row copies into a padded pitch were tried: ~50 clk per
         // copy on the TMA engine, 6300 clk per tile) =================
         for (uint32_t i = 0; i < ntile; ++i) {
-            const uint32_t slot = i % KT_NRAW, rph = (i / KT_NRAW) & 1;
+            const uint32_t slot = (ibase + i) % KT_NRAW, rph = ((ibase + i) / KT_NRAW) & 1;
             const int64_t p0 = (t0 + i) * 128;
             const int np = (int)min((int64_t)128, p.L - p0);
             mbar_wait(raw_empty + 8 * slot, rph ^ 1);            // every loader has read its row of tile i - NRAW
@@ -354,7 +368,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
         const uint32_t colmask = TK >= 32 ? 0xFFFFFFFFu : ((1u << TK) - 1u);
         long long* prof = (blockIdx.x == 0 && r == 0) ? p.prof : nullptr;
         for (uint32_t i = 0; i < ntile; ++i) {
-            const uint32_t buf = i % KT_NBUF, ph = (i / KT_NBUF) & 1;
+            const uint32_t buf = (ibase + i) % KT_NBUF, ph = ((ibase + i) / KT_NBUF) & 1;
             const int64_t p0 = (t0 + i) * 128;
             const bool valid = p0 + r < p.L;
             KPROF(2, 0);
@@ -426,7 +440,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
             // final: TMEM lane f = feature row (hi 0-39, mid 40-79, lo 80-119, ones 120), column m = (try, cluster): through
             // shared memory (the fp32 staging block is free by now), then sum[m][e] = (hi + mid) + lo, coalesced store
             float* fin = vs;                                     // [128][33]
-            if (ntile) { mbar_wait(done, 0); tc_fence_after(); }
+            if (ntile) { mbar_wait(done, seg & 1); tc_fence_after(); }
             {
                 uint32_t v[KT_N1];
                 if (ntile) { tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + KT_NBUF * KT_N1, v); tmem_ld_wait(); }
@@ -465,6 +479,12 @@ __global__ void __launch_bounds__(KT_THREADS, 1) kmeans_pass_tc_kernel(KtParams 
             }
         }
     }
+    // end of the segment: every role has finished with the centroid operand, |c|^2 and the staging block
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    ibase += ntile;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem, 512);
@@ -481,9 +501,26 @@ bool kmeans_tc_supported(int E, int K, int tries, bool soft, bool gated) {
     return !soft && !gated && E == KT_E && K >= 2 && K <= 4 && tries >= 1 && tries * K <= KT_N1;
 }
 
+// CTAs of a pass over a group of Bg mixtures and the most pieces any mixture is cut into (the row pitch of `part`)
+void kmeans_tc_geometry(int Bg, int64_t L, int* G_out, int* pmax_out) {
+    const int64_t nt = (L + 127) / 128, Tt = nt * Bg;
+    const int G = (int)std::min<int64_t>(kNumSMs, Tt);
+    int pmax = 1;
+    for (int b = 0; b < Bg; ++b) {
+        int c0, n;
+        kt_pieces(b, nt, Tt, G, c0, n);
+        pmax = std::max(pmax, n);
+    }
+    *G_out = G; *pmax_out = pmax;
+}
+
 int kmeans_pass_tc(const float* X, const float* cent, const float* prev_part, float* cent_out, int Bg, int64_t L, int K, int tries,
                    int chunks, int normalize, int mode, float* part, cudaStream_t st) {
     KtParams p;
+    int G, pmax;
+    kmeans_tc_geometry(Bg, L, &G, &pmax);
+    if (chunks < pmax) { set_error("kmeans_pass_tc: part pitch %d < %d pieces", chunks, pmax); return AMSS_ERR_INVALID_ARG; }
+    p.G = G; p.Tt = (int64_t)Bg * ((L + 127) / 128);
     p.prev_part = prev_part; p.cent_out = cent_out;
     p.prof = mode == KT_UPDATE ? g_kt_prof : nullptr;
     p.X = X; p.cent = cent; p.part = part; p.L = L; p.ntiles = (L + 127) / 128; p.K = K; p.tries = tries; p.chunks = chunks;
@@ -491,7 +528,7 @@ int kmeans_pass_tc(const float* X, const float* cent, const float* prev_part, fl
 #define KT_LAUNCH(MODE_, KC_)                                                                                                   \
     do {                                                                                                                        \
         AMSS_CUDA(cudaFuncSetAttribute((kmeans_pass_tc_kernel<MODE_, KC_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KT_SMEM)); \
-        AMSS_LAUNCH((kmeans_pass_tc_kernel<MODE_, KC_>), Bg * chunks, KT_THREADS, KT_SMEM, st, p);                              \
+        AMSS_LAUNCH((kmeans_pass_tc_kernel<MODE_, KC_>), G, KT_THREADS, KT_SMEM, st, p);                                        \
     } while (0)
     if (mode == KT_UPDATE) {
         if (K == 2) KT_LAUNCH(KT_UPDATE, 2); else if (K == 3) KT_LAUNCH(KT_UPDATE, 3); else KT_LAUNCH(KT_UPDATE, 4);
