@@ -667,7 +667,17 @@ __global__ void filter_grad_final_kernel(const float* __restrict__ part, int chu
 
 // the filter-stationary kernels index (row, frame) pairs and arg-max values with 32-bit arithmetic
 static bool sg_fits_32bit(int R, int Tp, int L, int N) { return (int64_t)R * Tp < (1ll << 31) && (int64_t)L * N < (1ll << 32); }
-constexpr int FG_CHUNKS = 32;     // slices of the (row, frame) list per filter group: 32 x 32 CTAs for 256 filters
+constexpr int FG_CHUNKS = 32;     // slices of the (row, frame) list per filter (gather kernels)
+// Slices per filter GROUP of the filter-stationary kernels: four CTAs of 256 threads are resident per SM (64 registers, 46 KB of
+// shared memory), so the grid is cut to fill whole waves of 4 x SMs CTAs: 256 filters = 32 groups x 37 slices = 1184 = two full
+// waves (32 x 32 = 1024 ran as one full wave + one at 73 %).
+constexpr int FG_CHUNKS_MAX = 96;
+inline int fg_chunks_fs(int N) {
+    const int groups = (N + 7) / 8, resident = 4 * kNumSMs;
+    int c = 2 * resident / groups;
+    if (c > FG_CHUNKS_MAX) c = resident / groups;
+    return std::max(1, std::min(c, FG_CHUNKS_MAX));
+}
 
 }  // namespace
 }  // namespace amss
@@ -737,7 +747,7 @@ extern "C" int amss_filterbank_analysis_mix_fwd(const float* x, const float* fil
 }
 
 extern "C" size_t amss_filterbank_grad_workspace_bytes(int W, int N) {
-    return align_up((size_t)W * N * 4, 256) + (size_t)FG_CHUNKS * N * W * 4;
+    return align_up((size_t)W * N * 4, 256) + (size_t)std::max(FG_CHUNKS, fg_chunks_fs(N)) * N * W * 4;
 }
 
 extern "C" int amss_filterbank_analysis_bwd(const float* x, const float* dy, const int64_t* argmax, int Bt, int L,
@@ -746,8 +756,10 @@ extern "C" int amss_filterbank_analysis_bwd(const float* x, const float* dy, con
     AMSS_REQUIRE(x && dy && argmax && dfilt && workspace, "filterbank_analysis_bwd: null pointer");
     if (workspace_bytes < amss_filterbank_grad_workspace_bytes(W, N)) { set_error("filterbank_analysis_bwd: workspace too small"); return AMSS_ERR_WORKSPACE; }
     float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
+    int chunks = FG_CHUNKS;
     if (W <= 1024 && sg_fits_32bit(Bt, Tp, L, N)) {
-        dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
+        chunks = fg_chunks_fs(N);
+        dim3 grid((N + SG_F - 1) / SG_F, chunks);
         if (W == 1024) AMSS_LAUNCH(sparse_filter_grad_fs_kernel<true>, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
         else AMSS_LAUNCH(sparse_filter_grad_fs_kernel<false>, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
     } else {
@@ -755,7 +767,7 @@ extern "C" int amss_filterbank_analysis_bwd(const float* x, const float* dy, con
         AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, dy, argmax, x, Bt, 1, L, W, N, Tp, part);
     }
     dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);
-    AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, FG_CHUNKS, W, N, accumulate, dfilt);
+    AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, chunks, W, N, accumulate, dfilt);
     return AMSS_OK;
 }
 
@@ -822,7 +834,7 @@ extern "C" int amss_filterbank_synthesis_bwd(const float* dout, const float* val
     float* part = (float*)((char*)workspace + align_up((size_t)W * N * 4, 256));
     const bool fs = W <= 1024 && sg_fits_32bit(B * S, Tp, L, N);
     if (dvals && fs) {
-        dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
+        dim3 grid((N + SG_F - 1) / SG_F, fg_chunks_fs(N));
         if (W == 1024) AMSS_LAUNCH(synthesis_bwd_vals_fs_kernel<true>, grid, 256, 0, stream, dout, argmax, filt2, B * S, S, L, W, N, Tp, dvals);
         else AMSS_LAUNCH(synthesis_bwd_vals_fs_kernel<false>, grid, 256, 0, stream, dout, argmax, filt2, B * S, S, L, W, N, Tp, dvals);
     } else if (dvals) {
@@ -832,11 +844,12 @@ extern "C" int amss_filterbank_synthesis_bwd(const float* dout, const float* val
         AMSS_LAUNCH(synthesis_bwd_vals_kernel, grid, 256, 0, stream, dout, argmax, fT, S, L, W, N, Tp, dvals);
     }
     if (dfilt2 && fs) {
-        dim3 grid((N + SG_F - 1) / SG_F, FG_CHUNKS);
+        const int chunks = fg_chunks_fs(N);
+        dim3 grid((N + SG_F - 1) / SG_F, chunks);
         if (W == 1024) AMSS_LAUNCH(sparse_filter_grad_fs_kernel<true>, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
         else AMSS_LAUNCH(sparse_filter_grad_fs_kernel<false>, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
         dim3 g2((N + 31) / 32, (W + 31) / 32), b2(32, 8);
-        AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, FG_CHUNKS, W, N, 0, dfilt2);
+        AMSS_LAUNCH(filter_grad_final_kernel, g2, b2, 0, stream, part, chunks, W, N, 0, dfilt2);
     } else if (dfilt2) {
         dim3 grid(N, FG_CHUNKS);
         AMSS_LAUNCH(sparse_filter_grad_kernel, grid, 256, 0, stream, vals, argmax, dout, B * S, S, L, W, N, Tp, part);
