@@ -88,6 +88,31 @@ def test_stft_other_frames(ops, frame, hop):
     assert rel(torch.view_as_real(spec), torch.view_as_real(ref)) < 1e-4
 
 
+@pytest.mark.parametrize("R,Lw,frame,hop", [(40, 30000, 512, 256), (14, 5000, 64, 16), (9, 120000, 1024, 256), (36, 31232, 512, 256)])
+def test_stft_run_kernels_match_oracle(ops, R, Lw, frame, hop):
+    """Batches of >= 4000 frames take the multi-frame kernels (two real frames per complex FFT, window / twiddles once per
+    CTA): odd and even frame counts, runs that end inside a pair, other frame sizes; spectra, magnitudes and labels."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(R, Lw, generator=g) * 0.1
+    Tn = 1 + (Lw - frame) // hop
+    assert Tn * R >= 4000
+    ref = T.stft(x, frame, hop)
+    spec, mag = ops.stft(dev(x), frame, hop)
+    assert spec.shape == ref.shape
+    assert rel(torch.view_as_real(spec), torch.view_as_real(ref)) < 1e-4
+    assert rel(mag, ref.abs()) < 1e-4
+    S = 3
+    B = R // S
+    nm = x[:B * S].reshape(B, S, Lw)
+    if Tn * B >= 4000:
+        refm = ref[:B * S].abs().reshape(B, S, Tn, -1).permute(0, 2, 3, 1)       # [B,T,F,S]
+        labels, magn = ops.stft_labels(dev(nm), frame, hop, want_mag=True)
+        assert rel(magn, refm) < 1e-4
+        srt = refm.sort(-1).values
+        margin = (srt[..., -1] - srt[..., -2]) > 1e-4 * srt[..., -1].clamp_min(1e-6)
+        assert torch.equal(labels.cpu().long()[margin], refm.argmax(-1)[margin])
+
+
 def test_stft_labels_bit_exact_off_ties(ops):
     mix, nm, _ = M.synthetic_mixtures(2, 3, 8192, seed=5)
     pre = M.separator_preprocessing(torch.tensor(mix), torch.tensor(nm), 512, 256, 1.0, 0.0)
