@@ -128,10 +128,69 @@ adapt_terms_bwd_kernel(const float* __restrict__ y, const float* __restrict__ p_
     }
 }
 
+// ---- the scalar tail of Adapt.cost (pre-training branch) ---------------------------------------------------------------
+// models/adapt.py:323-337, 374-385 + models/network.py:196-221 (with_perm = False), from the per-(b,s) waveform statistics
+//   st[r] = (<t,t>, <a,a>, <t,a>, <t-a,t-a>)  (target vs synthesis)      sm[r] = (<t,t>, <m,m>, <t,m>, .)  (target vs mixture)
+//   l2  = mean_B sum_S <t-a,t-a>                       sdr = mean_{B,S} <t,t><a,a> / (<t,a>^2 + 1e-12)
+//   cost = l2 | sdr | l2 + sdr  + beta sparse + lambda^2 (|f|^2 + |f2|^2) / 2 + overlap_coef overlapping + nn^2 nonneg
+//   sdr_improvement = mean_{B,S} 10 log10(1 / (<t,t><a,a>/<t,a>^2 - 1)) - 10 log10(1 / (<t,t><m,m>/<t,m>^2 - 1))
+// and the derivatives of cost w.r.t. every input (the graph is a scalar function of ~B*S*4 + 4 numbers: ~90 elementwise
+// launches of 2-4 us each when written with tensor ops).  One CTA, fixed-order sums.
+__global__ void adapt_cost_kernel(const float* __restrict__ st, const float* __restrict__ sm, const float* __restrict__ terms,
+                                  const float* __restrict__ regsq, int B, int S, int loss_kind, float beta, float lam, float ov,
+                                  float nn, float* __restrict__ out, float* __restrict__ dst, float* __restrict__ dterms,
+                                  float* __restrict__ dreg) {
+    __shared__ float red[32];
+    const int R = B * S;
+    const float wl2 = (loss_kind == 0 || loss_kind == 2) ? 1.f / (float)B : 0.f;
+    const float wsdr = (loss_kind == 1 || loss_kind == 2) ? 1.f / (float)R : 0.f;
+    float l2s = 0.f, sdrs = 0.f, vals = 0.f;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const float tn = st[r * 4 + 0], an = st[r * 4 + 1], ta = st[r * 4 + 2], ee = st[r * 4 + 3];
+        const float den = ta * ta + 1e-12f;
+        l2s += ee;
+        sdrs += tn * an / den;
+        if (sm) {
+            const float mm = sm[r * 4 + 1], tm = sm[r * 4 + 2], tn2 = sm[r * 4 + 0];
+            const float sep = 10.f * logf(1.f / ((tn * an) / (ta * ta) - 1.f)) / logf(10.f);
+            const float nsep = 10.f * logf(1.f / ((tn2 * mm) / (tm * tm) - 1.f)) / logf(10.f);
+            vals += sep - nsep;
+        }
+        dst[r * 4 + 0] = wsdr * an / den;
+        dst[r * 4 + 1] = wsdr * tn / den;
+        dst[r * 4 + 2] = -2.f * wsdr * tn * an * ta / (den * den);
+        dst[r * 4 + 3] = wl2;
+    }
+    l2s = block_sum(l2s, red);
+    sdrs = block_sum(sdrs, red);
+    vals = block_sum(vals, red);
+    if (threadIdx.x == 0) {
+        const float l2 = l2s / (float)B, sdr = sdrs / (float)R;
+        float cost = loss_kind == 0 ? l2 : (loss_kind == 1 ? sdr : l2 + sdr);
+        if (beta != 0.f) cost += beta * terms[0];
+        if (lam != 0.f) cost += lam * (lam * (0.5f * regsq[0]));        // lambda applied twice (adapt.py:312, :380)
+        if (ov != 0.f) cost += ov * terms[1];
+        if (nn != 0.f) cost += nn * (nn * terms[2]);                    // applied twice (:316, :384)
+        out[0] = cost; out[1] = l2; out[2] = sdr; out[3] = vals / (float)R;
+        dterms[0] = beta; dterms[1] = ov; dterms[2] = nn * nn;
+        dreg[0] = lam * lam;
+    }
+}
+
 }  // namespace
 }  // namespace amss
 
 using namespace amss;
+
+extern "C" int amss_adapt_cost_fwd(const float* stats, const float* mix_stats, const float* terms, const float* regsq, int B,
+                                   int S, int loss_kind, float beta, float lambda, float overlap_coef, float nonneg_coef,
+                                   float* out4, float* dstats, float* dterms, float* dreg, void* stream) {
+    AMSS_REQUIRE(stats && terms && regsq && out4 && dstats && dterms && dreg && B > 0 && S > 0, "adapt_cost_fwd: bad arguments");
+    AMSS_REQUIRE(loss_kind >= 0 && loss_kind <= 2, "adapt_cost_fwd: loss_kind must be 0 (l2), 1 (sdr) or 2 (l2 + sdr)");
+    AMSS_LAUNCH(adapt_cost_kernel, 1, 256, 0, stream, stats, mix_stats, terms, regsq, B, S, loss_kind, beta, lambda, overlap_coef,
+                nonneg_coef, out4, dstats, dterms, dreg);
+    return AMSS_OK;
+}
 
 extern "C" size_t amss_adapt_terms_workspace_bytes(int64_t TN) { return (size_t)((TN + AC_THREADS - 1) / AC_THREADS) * 3 * 4 + 256; }
 

@@ -611,13 +611,14 @@ __global__ void plugged_labels_kernel(const float* __restrict__ y, int B, int S,
 }
 
 // stats[r] = { <t,t>, <a,a>, <t,a>, <t-a,t-a> } over L   (fixed-order two-level reduction)
-__global__ void wave_stats_kernel(const float* __restrict__ tg, const float* __restrict__ ap, int64_t L,
+__global__ void wave_stats_kernel(const float* __restrict__ tg, const float* __restrict__ ap, int64_t L, int ap_div,
                                   float* __restrict__ stats) {
     __shared__ float red[32];
     const int r = blockIdx.x;
+    const size_t ar = (size_t)(r / ap_div);
     float tt = 0.f, aa = 0.f, ta = 0.f, ee = 0.f;
     for (int64_t i = threadIdx.x; i < L; i += blockDim.x) {
-        const float t = tg[(size_t)r * L + i], a = ap[(size_t)r * L + i], d = t - a;
+        const float t = tg[(size_t)r * L + i], a = ap[ar * L + i], d = t - a;
         tt = fmaf(t, t, tt); aa = fmaf(a, a, aa); ta = fmaf(t, a, ta); ee = fmaf(d, d, ee);
     }
     tt = block_sum(tt, red); aa = block_sum(aa, red); ta = block_sum(ta, red); ee = block_sum(ee, red);
@@ -860,6 +861,13 @@ extern "C" int amss_plugged_labels(const float* front_y, int B, int S, int64_t T
 extern "C" int amss_wave_stats(const float* target, const float* approx, int R, int64_t L, float* stats,
                                void* stream) {
     AMSS_REQUIRE(target && approx && stats && R > 0, "wave_stats: bad arguments");
-    AMSS_LAUNCH(wave_stats_kernel, R, 512, 0, stream, target, approx, L, stats);
+    AMSS_LAUNCH(wave_stats_kernel, R, 512, 0, stream, target, approx, L, 1, stats);
+    return AMSS_OK;
+}
+
+extern "C" int amss_wave_stats_rows(const float* target, const float* approx, int R, int64_t L, int approx_div, float* stats,
+                                    void* stream) {
+    AMSS_REQUIRE(target && approx && stats && R > 0 && approx_div > 0, "wave_stats_rows: bad arguments");
+    AMSS_LAUNCH(wave_stats_kernel, R, 512, 0, stream, target, approx, L, approx_div, stats);
     return AMSS_OK;
 }

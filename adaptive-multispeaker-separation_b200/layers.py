@@ -541,6 +541,39 @@ def wave_stats(target, approx):
     return _WaveLossFn.apply(target, approx)
 
 
+class _AdaptCostFn(torch.autograd.Function):
+    """The scalar tail of Adapt.cost (pre-training branch) as ONE node: waveform statistics, the three front-output terms
+    and the two filter banks -> cost, with (l2, sdr, sdr_improvement) as by-products; forward and every derivative come from
+    amss_adapt_cost_fwd (the tensor-op version was ~90 launches of 2-4 us on a handful of numbers)."""
+
+    @staticmethod
+    def forward(ctx, st, terms, filt, filt2, sm, B, S, loss_kind, beta, lam, ov, nn):
+        regsq = ops.sumsq([filt, filt2]) if lam != 0.0 else torch.zeros(1, dtype=st.dtype, device=st.device)
+        out4, dst, dterms, dreg = ops.adapt_cost_fwd(st.contiguous(), sm, terms.contiguous(), regsq, B, S, loss_kind, beta, lam, ov, nn)
+        ctx.save_for_backward(dst, dterms, dreg, filt, filt2)
+        ctx.lam = lam
+        aux = out4[1:].clone()
+        ctx.mark_non_differentiable(aux)
+        return out4[0].clone(), aux
+
+    @staticmethod
+    def backward(ctx, dcost, _daux):
+        dst, dterms, dreg, filt, filt2 = ctx.saved_tensors
+        g = dcost.reshape(())
+        dfilt = dfilt2 = None
+        if ctx.lam != 0.0:
+            c = dreg[0] * g
+            dfilt = filt * c if ctx.needs_input_grad[2] else None
+            dfilt2 = filt2 * c if ctx.needs_input_grad[3] else None
+        return dst * g, dterms * g, dfilt, dfilt2, None, None, None, None, None, None, None, None
+
+
+def adapt_cost(st, terms, filt, filt2, sm, B, S, loss, beta, lam, ov, nn):
+    """-> (cost, aux[3] = l2, sdr, sdr_improvement)."""
+    kind = 0 if loss == "l2" else (1 if loss == "sdr" else 2)
+    return _AdaptCostFn.apply(st, terms, filt, filt2, sm, B, S, kind, float(beta), float(lam), float(ov), float(nn))
+
+
 class _ISTFTMaskedFn(torch.autograd.Function):
     """Separator.postprocessing with soft masks (network.py:584-607) as a differentiable node: (masks * X) ->
     inverse_stft.  The gradient reaches the masks (the enhance layer's softmax output); the mixture STFT is data."""

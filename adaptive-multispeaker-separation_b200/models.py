@@ -267,19 +267,16 @@ class Adapt(Network):
         sep, p_hat, terms = L.adapt_terms(y, B, S, self.p, 0 if self.separation == "mask" else 1)
         sparse, overlapping, nonneg = terms[0], terms[1], terms[2]
         back = self.back(sep, am, B, Lw)
-        val, sdr_bs, st = self.sdr_improvement(x_mix, x_non_mix, back)
-        l2 = st[:, 3].reshape(B, S).sum(-1).mean(-1)                                    # adapt.py:323-325
-        sdr = sdr_bs.mean(-1).mean(-1)                                                   # adapt.py:327-330
-        cost = l2 if self.loss == "l2" else (sdr if self.loss == "sdr" else l2 + sdr)    # adapt.py:332-337
-        if self.beta != 0.0:
-            cost = cost + self.beta * sparse
-        if self.l != 0.0:                                                                # lambda applied twice (:312, :380)
-            reg = self.l * (0.5 * (filt2 ** 2).sum() + 0.5 * (filt ** 2).sum())
-            cost = cost + self.l * reg
-        if self.overlap_coef != 0.0:
-            cost = cost + self.overlap_coef * overlapping
-        if self.non_negativity:                                                          # applied twice (:316, :384)
-            cost = cost + self.non_negativity * (self.non_negativity * nonneg)
+        # l2 (adapt.py:323-325), sdr (:327-330), the choice of loss (:332-337), beta * KL, lambda^2 * reg (lambda applied
+        # twice, :312, :380), overlap_coef * overlap, nn^2 * neg (applied twice, :316, :384) and the SDR-improvement metric
+        # (network.py:196-221) from the waveform statistics: one kernel (amss_adapt_cost_fwd)
+        tgt = x_non_mix.reshape(B * S, Lw)
+        st = L.wave_stats(tgt, back.reshape(B * S, Lw))
+        with torch.no_grad():
+            sm = ops.wave_stats_rows(tgt.contiguous(), x_mix.contiguous(), S)
+        cost, aux3 = L.adapt_cost(st, terms, filt, filt2, sm, B, S, self.loss, self.beta, self.l, self.overlap_coef,
+                                  float(self.non_negativity or 0.0))
+        l2, sdr, val = aux3[0], aux3[1], aux3[2]
         return cost, {"y": y, "argmax": am, "back": back, "l2": l2, "sdr": sdr, "sdr_improvement": val,
                       "sparse_constraint": sparse, "overlapping": overlapping, "p_hat": p_hat}
 

@@ -436,6 +436,39 @@ def wave_stats(target, approx):
     return out
 
 
+def wave_stats_rows(target, approx, approx_div):
+    """wave_stats with approx row r // approx_div (target [R,L], approx [R // approx_div, L])."""
+    _chk(target, approx)
+    R, L = target.shape
+    out = torch.empty(R, 4, dtype=_f32, device=target.device)
+    _lib.call("amss_wave_stats_rows", _p(target), _p(approx), R, L, int(approx_div), _p(out), _stream())
+    return out
+
+
+def sumsq(tensors):
+    """-> device scalar sum of squares of the given tensors (fixed-order reduction, amss_sumsq)."""
+    tensors = [t for t in tensors]
+    _chk(*tensors)
+    out = torch.zeros(1, dtype=_f32, device=tensors[0].device)
+    ws = _ws(_lib.query("amss_sumsq_workspace_bytes"), tensors[0].device)
+    for t in tensors:
+        _lib.call("amss_sumsq", _p(t), t.numel(), _p(out), _p(ws), _stream())
+    return out
+
+
+def adapt_cost_fwd(stats, mix_stats, terms, regsq, B, S, loss_kind, beta, lam, overlap_coef, nonneg_coef):
+    """-> (out4 = cost, l2, sdr, sdr_improvement; dstats [B*S,4]; dterms [3]; dreg [1])."""
+    _chk(stats, mix_stats, terms, regsq)
+    dev = stats.device
+    out4 = torch.empty(4, dtype=_f32, device=dev)
+    dstats = torch.empty(B * S, 4, dtype=_f32, device=dev)
+    dterms = torch.empty(3, dtype=_f32, device=dev)
+    dreg = torch.empty(1, dtype=_f32, device=dev)
+    _lib.call("amss_adapt_cost_fwd", _p(stats), _p(mix_stats), _p(terms), _p(regsq), B, S, int(loss_kind), float(beta), float(lam),
+              float(overlap_coef), float(nonneg_coef), _p(out4), _p(dstats), _p(dterms), _p(dreg), _stream())
+    return out4, dstats, dterms, dreg
+
+
 # ------------------------------------------------------------------------------------------
 # k-means
 # ------------------------------------------------------------------------------------------

@@ -375,6 +375,18 @@ int amss_wave_stats(const float* target, const float* approx, int R, int64_t L,
  * pre-training separator -- separation 0 'mask', 1 'perfect' --, :315-316 non-negativity):
  *   sep[B*S,TN] (may be NULL), p_hat[TN], terms[3] = {sparse_constraint, overlapping, mean_rows sum neg^2}.
  * bwd: dy[B(S+1),TN] from dsep (may be NULL) and dterms[3].                                        */
+/* The scalar tail of Adapt.cost, pre-training branch (models/adapt.py:323-337, 374-385; models/network.py:196-221):
+ * stats[B*S,4] as written by amss_wave_stats(target, synthesis), mix_stats[B*S,4] = amss_wave_stats_rows(target, mixture)
+ * (may be NULL: no SDR-improvement metric), terms[3] of amss_adapt_terms_fwd, regsq[1] = |filt|^2 + |filt2|^2 ->
+ * out4 = (cost, l2, sdr, sdr_improvement) and the derivatives of cost: dstats[B*S,4], dterms[3], dreg[1] (d cost / d regsq * 2:
+ * the factor the filters are multiplied by).  loss_kind 0 l2, 1 sdr, 2 l2 + sdr; zero coefficients drop their term.      */
+int amss_adapt_cost_fwd(const float* stats, const float* mix_stats, const float* terms, const float* regsq,
+                        int B, int S, int loss_kind, float beta, float lambda, float overlap_coef,
+                        float nonneg_coef, float* out4, float* dstats, float* dterms, float* dreg,
+                        void* stream);
+/* amss_wave_stats with approx row r / approx_div (the mixture of target row r when approx_div = S).  */
+int amss_wave_stats_rows(const float* target, const float* approx, int R, int64_t L, int approx_div,
+                         float* stats, void* stream);
 size_t amss_adapt_terms_workspace_bytes(int64_t TN);
 int amss_adapt_terms_fwd(const float* y, int B, int S, int64_t TN, float rho, int separation,
                          float* sep, float* p_hat, float* terms, void* workspace,
