@@ -258,6 +258,19 @@ __global__ void mix_is_sum_kernel(const float* __restrict__ x, int B, int64_t L,
     if (bad) *mismatch = 1;
 }
 
+// the same in 16-byte units (L % 4 == 0, aligned rows)
+__global__ void mix_is_sum_vec_kernel(const float4* __restrict__ x, int B, int64_t L4, int* __restrict__ mismatch) {
+    const int64_t n = (int64_t)B * L4;
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / L4, o = i - b * L4;
+        const float4 m = __ldg(x + i), a = __ldg(x + (B + 2 * b) * L4 + o), c = __ldg(x + (B + 2 * b + 1) * L4 + o);
+        bad |= !(m.x == __fadd_rn(a.x, c.x)) | !(m.y == __fadd_rn(a.y, c.y)) | !(m.z == __fadd_rn(a.z, c.z)) |
+               !(m.w == __fadd_rn(a.w, c.w));
+    }
+    if (bad) *mismatch = 1;
+}
+
 __global__ void __launch_bounds__(FT_THREADS, 1) analysis_pair_tc_kernel(FtParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // carve-up: [A stages][G(buf 0: src 0, src 1)][G(buf 1: src 0, src 1)][xs src 0][xs src 1]
@@ -528,7 +541,10 @@ int filterbank_analysis_mix_tc(const float* x, const float* filt, int B, int S, 
     if (off || !filterbank_analysis_mix_tc_supported(S, L, W, N, pool, hop)) return launch_stock(p, Bt, L, pool, hop, st);
     int* flag = reinterpret_cast<int*>(const_cast<uint8_t*>(p.packed) - 256);
     AMSS_CUDA(cudaMemsetAsync(flag, 0, 4, st));
-    AMSS_LAUNCH(mix_is_sum_kernel, 4 * kNumSMs, 256, 0, st, x, B, (int64_t)L, flag);
+    if ((L & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        AMSS_LAUNCH(mix_is_sum_vec_kernel, 8 * kNumSMs, 256, 0, st, reinterpret_cast<const float4*>(x), B, (int64_t)(L / 4), flag);
+    else
+        AMSS_LAUNCH(mix_is_sum_kernel, 4 * kNumSMs, 256, 0, st, x, B, (int64_t)L, flag);
     FtParams q = p;                                   // linear-mixture kernel: runs iff no mismatch was found
     q.gate = flag; q.gate_zero = 1; q.B = B; q.Bt = Bt;
     q.QB = q.KS * 8 + FP_NT / 8 - 1;

@@ -5,6 +5,7 @@
 //   AMSS_PREC_BF16 : tcgen05 bf16 tiles with TMEM accumulators (gemm_tc.cu) when the shape is
 //                    supported, else an error (never a silent fallback).
 #include "common.cuh"
+#include <algorithm>
 #include <cuda_bf16.h>
 
 namespace amss {
@@ -104,6 +105,16 @@ __global__ void transpose_01_kernel(const float* __restrict__ in, int D0, int D1
     }
 }
 
+// the same in 16-byte units (C % 4 == 0, aligned buffers, fewer than 2^31 units: 32-bit index arithmetic)
+__global__ void transpose_01_vec_kernel(const float4* __restrict__ in, int D0, int D1, int C4, float4* __restrict__ out) {
+    const uint32_t n = (uint32_t)D0 * (uint32_t)D1 * (uint32_t)C4;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = i % (uint32_t)C4, r = i / (uint32_t)C4;
+        const uint32_t d1 = r % (uint32_t)D1, d0 = r / (uint32_t)D1;
+        out[((size_t)d1 * D0 + d0) * C4 + c] = __ldg(in + i);
+    }
+}
+
 // in[D0][D1][C] fp32 -> out[D1][D0][ldd] bf16 (ldd = C padded to 8, zero filled): the [T,B,C] -> [B,T,C] hand-over into
 // the embedding head fused with its operand conversion (one pass instead of transpose + convert)
 __global__ void transpose_01_bf16_kernel(const float* __restrict__ in, int D0, int D1, int C, int ldd, uint4* __restrict__ out) {
@@ -164,6 +175,13 @@ int gemm_dispatch(const float* A, int lda, const float* B, int ldb, const float*
 }
 
 int transpose_01(const float* in, int D0, int D1, int C, float* out, cudaStream_t st) {
+    const int64_t n4 = (int64_t)D0 * D1 * (C / 4);
+    if ((C & 3) == 0 && n4 < (1ll << 31) && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const int grid = (int)std::min<int64_t>((n4 + 255) / 256, 16 * kNumSMs);
+        AMSS_LAUNCH(transpose_01_vec_kernel, grid, 256, 0, st, reinterpret_cast<const float4*>(in), D0, D1, C / 4,
+                    reinterpret_cast<float4*>(out));
+        return AMSS_OK;
+    }
     AMSS_LAUNCH(transpose_01_kernel, 4 * kNumSMs, 256, 0, st, in, D0, D1, C, out);
     return AMSS_OK;
 }

@@ -610,6 +610,24 @@ __global__ void plugged_labels_kernel(const float* __restrict__ y, int B, int S,
     }
 }
 
+// the same, four bins per thread (TN % 4 == 0, aligned buffers)
+__global__ void plugged_labels_vec_kernel(const float4* __restrict__ y, int B, int S, int64_t TN4, uint32_t* __restrict__ labels) {
+    const int64_t n = (int64_t)B * TN4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / TN4, j = i - b * TN4;
+        float best[4] = {-1.f, -1.f, -1.f, -1.f};
+        uint32_t bi[4] = {0, 0, 0, 0};
+        for (int s = 0; s < S; ++s) {
+            const float4 v = __ldg(y + ((size_t)B + b * S + s) * TN4 + j);
+            const float a[4] = {fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w)};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (a[q] > best[q]) { best[q] = a[q]; bi[q] = (uint32_t)s; }
+        }
+        labels[i] = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    }
+}
+
 // stats[r] = { <t,t>, <a,a>, <t,a>, <t-a,t-a> } over L   (fixed-order two-level reduction)
 __global__ void wave_stats_kernel(const float* __restrict__ tg, const float* __restrict__ ap, int64_t L, int ap_div,
                                   float* __restrict__ stats) {
@@ -854,6 +872,12 @@ extern "C" int amss_l41_loss_bwd(const float* emb, const uint8_t* labels, const 
 
 extern "C" int amss_plugged_labels(const float* front_y, int B, int S, int64_t TN, uint8_t* labels, void* stream) {
     AMSS_REQUIRE(front_y && labels && S >= 1 && S < 256, "plugged_labels: bad arguments");
+    if ((TN & 3) == 0 && ((reinterpret_cast<uintptr_t>(front_y) | reinterpret_cast<uintptr_t>(labels)) & 15) == 0) {
+        const int64_t n4 = (int64_t)B * (TN / 4);
+        AMSS_LAUNCH(plugged_labels_vec_kernel, (int)std::min<int64_t>((n4 + 255) / 256, 16 * kNumSMs), 256, 0, stream,
+                    reinterpret_cast<const float4*>(front_y), B, S, TN / 4, reinterpret_cast<uint32_t*>(labels));
+        return AMSS_OK;
+    }
     AMSS_LAUNCH(plugged_labels_kernel, 4 * kNumSMs, 256, 0, stream, front_y, B, S, TN, labels);
     return AMSS_OK;
 }
