@@ -38,6 +38,7 @@ ANALYSIS_CASES = [
     (2, 8192, 1024, 256, 256),    # the bench geometry, short signal
     (2, 5000, 200, 130, 128),     # ragged: W not a multiple of 64, N spills into a 2nd m-tile, L % pool != 0
     (1, 4096, 96, 128, 512),      # frames spanning two time tiles
+    (2, 4096, 1024, 512, 512),    # the reference's DEFAULT bank (utils/trainer.py:136-147): four filter tiles, pool 512
 ]
 
 
@@ -67,7 +68,8 @@ def test_analysis_tc_matches_oracle_on_bf16_operands(ops, Bt, L, W, N, pool):
     assert agree > 0.98, agree
 
 
-@pytest.mark.parametrize("B,L,W,N,pool", [(2, 4096, 64, 16, 128), (3, 8192, 1024, 256, 256), (1, 5000, 200, 130, 256)])
+@pytest.mark.parametrize("B,L,W,N,pool", [(2, 4096, 64, 16, 128), (3, 8192, 1024, 256, 256), (1, 5000, 200, 130, 256),
+                                          (2, 4096, 1024, 512, 512)])
 def test_analysis_mix_linear_mixture_path(ops, B, L, W, N, pool):
     """amss_filterbank_analysis_mix_fwd, S = 2: when x_mix == x_0 + x_1 bit for bit the mixture rows come from the sum of
     the two source responses.  Source rows must equal the stock kernel's bit for bit (same products, same order);
