@@ -164,6 +164,34 @@ def test_adapt_pretraining_steps_match_oracle(amss, loss, separation, beta):
         assert rel(t.store[k], st.tr[k]) < REL, k
 
 
+def test_adapt_pretraining_overlapping_pool_windows_match_oracle(amss):
+    """The reference's DEFAULT pooling geometry is pool = 2 x hop (--max_pool 512 --hop_size 256, utils/trainer.py:136-147):
+    overlapping max-pool windows (max_pool_with_argmax with ksize != strides, models/adapt.py:116-117), so one sample can be
+    the arg-max of two frames and `unpool` adds both atoms at the same place (utils/ops.py:111-118).  Reduced geometry, 3 steps."""
+    tr = amss["trainer"]
+    B, S, Lw = 2, 2, 2048
+    kw = dict(window_size=64, filters=16, max_pool=64, hop_size=32, with_max_pool=True, loss="sdr+l2", separation="perfect",
+              beta=0.01, regularization=1e-4, overlap_coef=1e-3, sparsity=0.01)
+    t = tr.Adapt_Pretrainer(learning_rate=1e-3, **kw)
+    p = _copy_params(t.store, {})
+
+    def fn(pp, xm, xn, I):
+        return M.adapt_pretraining_cost(pp, xm, xn, max_pool=64, hop=32, loss="sdr+l2", separation="perfect", beta=0.01,
+                                        regularization=1e-4, sparsity=0.01, overlap_coef=1e-3, non_negativity=0.0)
+
+    st = OS.Stepper(p, fn, train_prefixes=("front/", "back/"), lr=1e-3)
+    g = torch.Generator().manual_seed(301)
+    for step in range(3):
+        nm = (torch.randn(B, S, Lw, generator=g) * 0.05).numpy()
+        mix, I = nm.sum(1), np.zeros((B, S), np.int32)
+        c_ref, aux = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+        c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+        assert abs(float(c) - c_ref) < REL * abs(c_ref), (step, float(c), c_ref)
+        assert rel(t.aux["back"], aux["back"]) < REL
+    for k in st.tr:
+        assert rel(t.store[k], st.tr[k]) < REL, k
+
+
 @pytest.mark.parametrize("loss,separation", [("sdr+l2", "perfect"), ("l2", "mask")])
 def test_adapt_pretraining_average_pool_front_matches_oracle(amss, loss, separation):
     """--with_average_pool (models/adapt.py:118-120, 224-243): conv stride 1 + average pooling in the front end, UpSampling2D +
