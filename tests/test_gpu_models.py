@@ -408,6 +408,30 @@ def test_three_speaker_kmeans_inference(amss):
     assert rel(out.sum(1), full[:, 0]) < 1e-3
 
 
+def test_reference_default_flags_front_dpcl_step(amss):
+    """The reference's own DEFAULT flags for the front + DPCL recipe (utils/trainer.py:17-166: --chunk_size 20480,
+    --window_size 1024, --filters 512, --max_pool 512, --hop_size 256 (overlapping pooling windows), --nb_layers 3,
+    --layer_size 600, --embedding_size 40) with --with_max_pool: one training step of the fp32 path against the oracle, and
+    the bf16 path (tensor-core BLSTM / head / DPCL; the analysis falls back to the fp32 kernel because pool != hop) close to it."""
+    tr, mo = amss["trainer"], amss["models"]
+    B, S, Lw = 2, 2, 20480
+    cfg = dict(nb_layers=3, layer_size=600, embedding_size=40, window_size=1024, filters=512, max_pool=512, hop_size=256,
+               with_max_pool=True)
+    t = tr.Front_Separator_Trainer(mo.DPCL, learning_rate=1e-3, **cfg)
+    p = _copy_params(t.store, {})
+    p0 = {k: v.clone() for k, v in p.items()}
+    fn = functools.partial(OS.front_separator_loss, nb_layers=3, embedding_size=40, max_pool=512, hop=256)
+    st = OS.Stepper(p, fn, lr=1e-3)
+    mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=720)
+    c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+    c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+    assert abs(float(c) - c_ref) < REL * abs(c_ref), (float(c), c_ref)
+    tb = tr.Front_Separator_Trainer(mo.DPCL, learning_rate=1e-3, precision="bf16", **cfg)
+    tb.store.load_state_dict(p0, strict=False)
+    cb = tb.train_step(_dev(mix), _dev(nm), _dev(I))
+    assert abs(float(cb) - c_ref) < 2e-2 * abs(c_ref), (float(cb), c_ref)
+
+
 def test_model_folder_roundtrip(amss, tmp_path):
     """`params` JSON + variables under the reference's names (models/network.py:124-129, 223-226, 291-306): save, rebuild
     with `load` (only the reference's updatable keys are overridden), restore, and get the same embeddings."""
