@@ -432,6 +432,38 @@ def test_reference_default_flags_front_dpcl_step(amss):
     assert abs(float(cb) - c_ref) < 2e-2 * abs(c_ref), (float(cb), c_ref)
 
 
+@pytest.mark.parametrize("loss", ["dpcl", "l41"])
+def test_reference_default_flags_stft_step_and_inference(amss, loss):
+    """The reference's DEFAULT flags for the STFT recipes (utils/trainer.py:17-109: --chunk_size 20480, STFT 512 / 256,
+    --nb_layers 3, --layer_size 600, --embedding_size 40, --nb_tries 10, --nb_steps 10): one training step of both precisions
+    against the oracle, then inference (k-means masks, inverse STFT) with the trained weights: the separated signals add up to
+    the all-ones-mask reconstruction of the mixture."""
+    tr, mo, ops = amss["trainer"], amss["models"], amss["ops"]
+    B, S, Lw = 2, 2, 20480
+    cls = mo.DPCL if loss == "dpcl" else mo.L41Model
+    cfg = dict(nb_layers=3, layer_size=600, embedding_size=40, window_size=512, hop_size=256, nb_tries=10, nb_steps=10)
+    t = tr.STFT_Separator_Trainer(cls, learning_rate=1e-3, **cfg)
+    p = _copy_params(t.store, {})
+    p0 = {k: v.clone() for k, v in p.items()}
+    fn = functools.partial(OS.stft_separator_loss, nb_layers=3, embedding_size=40, window_size=512, hop_size=256, loss=loss)
+    st = OS.Stepper(p, fn, lr=1e-3)
+    mix, nm, I = M.synthetic_mixtures(B, S, Lw, seed=730)
+    c_ref, _ = st.step(torch.tensor(mix), torch.tensor(nm), torch.tensor(I))
+    c = t.train_step(_dev(mix), _dev(nm), _dev(I))
+    assert abs(float(c) - c_ref) < REL * abs(c_ref), (float(c), c_ref)
+    tb = tr.STFT_Separator_Trainer(cls, learning_rate=1e-3, precision="bf16", **cfg)
+    tb.store.load_state_dict(p0, strict=False)
+    cb = tb.train_step(_dev(mix), _dev(nm), _dev(I))
+    assert abs(float(cb) - c_ref) < 2e-2 * abs(c_ref), (float(cb), c_ref)
+    inf = tr.STFT_Separator_Inference(cls, state=t.store.state_dict(), precision="bf16", **cfg)
+    out = inf.infer(_dev(mix))
+    assert out.shape == (B, S, Lw) and bool(torch.isfinite(out).all())
+    spec, _ = ops.stft(_dev(mix), 512, 256)
+    ones = torch.zeros(B, spec.shape[1] * spec.shape[2], dtype=torch.int32, device="cuda")
+    full = ops.istft_masked(spec, 1, 512, 256, labels=ones)
+    assert rel(out.sum(1), full[:, 0]) < 1e-3
+
+
 def test_model_folder_roundtrip(amss, tmp_path):
     """`params` JSON + variables under the reference's names (models/network.py:124-129, 223-226, 291-306): save, rebuild
     with `load` (only the reference's updatable keys are overridden), restore, and get the same embeddings."""
