@@ -15,6 +15,35 @@ def world():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
+def bind_to_gpu_numa_node(pci_bus_id):
+    """Pin this process (and with it the pages of the pinned host buffers it allocates next) to the CPUs of the NUMA node the
+    GPU hangs off (`/sys/bus/pci/devices/<id>/numa_node`): with one process per GPU the H2D / D2H traffic of eight ranks
+    otherwise crosses the socket interconnect at random.  Returns the node, or None when it cannot be determined
+    (AMSS_NO_NUMA_BIND=1 switches it off).  Host-side plumbing only."""
+    if os.environ.get("AMSS_NO_NUMA_BIND") == "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        dev = pci_bus_id.lower()
+        if len(dev.split(":")[0]) == 8:                 # nvml style 00000000:1B:00.0 -> sysfs 0000:1b:00.0
+            dev = dev[4:]
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError):
+        return None
+
+
 def active():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 

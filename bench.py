@@ -444,7 +444,14 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import amss_b200  # noqa: F401
-    from amss_b200 import models, trainer, synth, _lib
+    from amss_b200 import models, trainer, synth, _lib, dp
+    numa_node = None
+    if world > 1:           # one process per GPU: keep its host buffers and its launcher thread next to the GPU
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            numa_node = dp.bind_to_gpu_numa_node(f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:   # noqa: BLE001 -- host-side plumbing, never fatal
+            numa_node = None
 
     cid = args.config
     c = CONFIGS[cid]
@@ -605,6 +612,7 @@ def run_gpu(args):
         "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": c["workload"], "baseline_config": cid, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}" if training else f"replicas x{world} (no collective)",
+                   "host_numa_node": numa_node,
                    "precision": precision, "cuda_graph": use_graph,
                    "gradient_exchange": ("none (1 process)" if world == 1 or not training else
                                          "one flat all-reduce after backward" if args.flat_allreduce else
