@@ -682,6 +682,9 @@ class _StreamingInference:
         raise NotImplementedError
 
     def inference(self, data, steps=None):
+        """Generator over the separated batches of `data` (pinned host tensors [B,S,L]).  Pipelined: the H2D copy of batch
+        n+1 and the D2H copy of batch n-1 overlap the kernels of batch n.  The yielded tensor is one of TWO pinned buffers
+        kept on the instance: it is overwritten two batches later (and by the next call) -- copy it to keep it."""
         it = iter(data)
         as_pinned = lambda b: b if _is_pinned(b) else DevicePrefetcher.pin(b)  # noqa: E731
         nxt = next(it, None)
