@@ -13,19 +13,39 @@ namespace {
 
 // In-place radix-2 DIT FFT of N complex points held bit-reversed in `buf`; N/2 threads.
 // tw[k] = exp(-+ 2*pi*i*k/N), k < N/2 (sign chosen by the caller when filling tw).
+// Two consecutive stages are fused per barrier (the four elements {i, i+h, i+2h, i+3h} are closed under stages s and
+// s+1): every element crosses shared memory once per TWO stages -- the kernels are bound by shared-memory traffic, 9 stages
+// of 5 x 8 bytes per thread -- with exactly the operations of the stage-by-stage form (bit-identical results).
+__device__ __forceinline__ float2 cmul_(float2 b, float2 w) { return make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x); }
 __device__ __forceinline__ void fft_shared(float2* buf, const float2* tw, int N, int logN) {
     const int tid = threadIdx.x;
-    for (int s = 1; s <= logN; ++s) {
-        const int half = 1 << (s - 1);
+    int s = 1;
+    if (logN & 1) {                                             // odd number of stages: stage 1 on its own
         __syncthreads();
         if (tid < N / 2) {
-            const int grp = tid >> (s - 1), j = tid & (half - 1);
-            const int i0 = (grp << s) + j, i1 = i0 + half;
-            const float2 w = tw[j << (logN - s)];
-            const float2 a = buf[i0], b = buf[i1];
-            const float2 bw = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+            const int i0 = tid << 1;
+            const float2 a = buf[i0], bw = cmul_(buf[i0 + 1], tw[0]);
             buf[i0] = make_float2(a.x + bw.x, a.y + bw.y);
-            buf[i1] = make_float2(a.x - bw.x, a.y - bw.y);
+            buf[i0 + 1] = make_float2(a.x - bw.x, a.y - bw.y);
+        }
+        s = 2;
+    }
+    for (; s < logN; s += 2) {
+        const int h = 1 << (s - 1);
+        __syncthreads();
+        if (tid < N / 4) {
+            const int grp = tid >> (s - 1), j = tid & (h - 1);
+            const int ia = (grp << (s + 1)) + j, ib = ia + h, ic = ia + 2 * h, id = ia + 3 * h;
+            const float2 w1 = tw[j << (logN - s)], w2 = tw[j << (logN - s - 1)], w3 = tw[(j + h) << (logN - s - 1)];
+            const float2 a = buf[ia], c = buf[ic];
+            const float2 bw = cmul_(buf[ib], w1), dw = cmul_(buf[id], w1);
+            const float2 a1 = make_float2(a.x + bw.x, a.y + bw.y), b1 = make_float2(a.x - bw.x, a.y - bw.y);
+            const float2 c1 = make_float2(c.x + dw.x, c.y + dw.y), d1 = make_float2(c.x - dw.x, c.y - dw.y);
+            const float2 cw = cmul_(c1, w2), ew = cmul_(d1, w3);
+            buf[ia] = make_float2(a1.x + cw.x, a1.y + cw.y);
+            buf[ic] = make_float2(a1.x - cw.x, a1.y - cw.y);
+            buf[ib] = make_float2(b1.x + ew.x, b1.y + ew.y);
+            buf[id] = make_float2(b1.x - ew.x, b1.y - ew.y);
         }
     }
     __syncthreads();
