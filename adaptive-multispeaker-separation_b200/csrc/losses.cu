@@ -643,6 +643,18 @@ __global__ void wave_stats_kernel(const float* __restrict__ tg, const float* __r
     if (threadIdx.x == 0) { stats[r * 4 + 0] = tt; stats[r * 4 + 1] = aa; stats[r * 4 + 2] = ta; stats[r * 4 + 3] = ee; }
 }
 
+// d approx[r][i] = ca[r] * approx[r][i] + ct[r] * target[r][i],  ca = 2 d<a,a> + 2 d<t-a,t-a>,  ct = d<t,a> - 2 d<t-a,t-a>
+// (the gradient of the four statistics w.r.t. the approximation; the targets are data)
+__global__ void wave_stats_bwd_kernel(const float* __restrict__ tg, const float* __restrict__ ap, const float* __restrict__ dstats,
+                                      int R, int64_t L, float* __restrict__ dap) {
+    const int64_t n = (int64_t)R * L;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / L);
+        const float d1 = dstats[r * 4 + 1], d2 = dstats[r * 4 + 2], d3 = dstats[r * 4 + 3];
+        dap[i] = (2.f * d1 + 2.f * d3) * ap[i] + (d2 - 2.f * d3) * tg[i];
+    }
+}
+
 int ls_chunks(int B, int64_t TF, int tile) {
     int64_t nt = (TF + tile - 1) / tile;
     int64_t want = (2 * kNumSMs + B - 1) / B;
@@ -886,6 +898,13 @@ extern "C" int amss_wave_stats(const float* target, const float* approx, int R, 
                                void* stream) {
     AMSS_REQUIRE(target && approx && stats && R > 0, "wave_stats: bad arguments");
     AMSS_LAUNCH(wave_stats_kernel, R, 512, 0, stream, target, approx, L, 1, stats);
+    return AMSS_OK;
+}
+
+extern "C" int amss_wave_stats_bwd(const float* target, const float* approx, const float* dstats, int R, int64_t L,
+                                   float* dapprox, void* stream) {
+    AMSS_REQUIRE(target && approx && dstats && dapprox && R > 0 && L > 0, "wave_stats_bwd: bad arguments");
+    AMSS_LAUNCH(wave_stats_bwd_kernel, 8 * kNumSMs, 256, 0, stream, target, approx, dstats, R, L, dapprox);
     return AMSS_OK;
 }
 

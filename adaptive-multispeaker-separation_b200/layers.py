@@ -526,15 +526,14 @@ class _WaveLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, target, approx):
+        target, approx = target.contiguous(), approx.contiguous()
         ctx.save_for_backward(target, approx)
-        return ops.wave_stats(target.contiguous(), approx.contiguous())
+        return ops.wave_stats(target, approx)
 
     @staticmethod
     def backward(ctx, dstats):
         target, approx = ctx.saved_tensors
-        ca = (2.0 * dstats[:, 1] + 2.0 * dstats[:, 3]).unsqueeze(1)
-        ct = (dstats[:, 2] - 2.0 * dstats[:, 3]).unsqueeze(1)
-        return None, ca * approx + ct * target
+        return None, ops.wave_stats_bwd(target, approx, dstats.contiguous())
 
 
 def wave_stats(target, approx):

@@ -436,6 +436,15 @@ def wave_stats(target, approx):
     return out
 
 
+def wave_stats_bwd(target, approx, dstats):
+    """-> d approx [R,L] of wave_stats(target, approx) for the upstream gradient dstats [R,4]."""
+    _chk(target, approx, dstats)
+    R, L = target.shape
+    out = torch.empty_like(approx)
+    _lib.call("amss_wave_stats_bwd", _p(target), _p(approx), _p(dstats), R, L, _p(out), _stream())
+    return out
+
+
 def wave_stats_rows(target, approx, approx_div):
     """wave_stats with approx row r // approx_div (target [R,L], approx [R // approx_div, L])."""
     _chk(target, approx)

@@ -384,6 +384,9 @@ int amss_adapt_cost_fwd(const float* stats, const float* mix_stats, const float*
                         int B, int S, int loss_kind, float beta, float lambda, float overlap_coef,
                         float nonneg_coef, float* out4, float* dstats, float* dterms, float* dreg,
                         void* stream);
+/* Gradient of amss_wave_stats w.r.t. the approximation: dapprox[R,L] from dstats[R,4] (the targets are data).     */
+int amss_wave_stats_bwd(const float* target, const float* approx, const float* dstats, int R,
+                        int64_t L, float* dapprox, void* stream);
 /* amss_wave_stats with approx row r / approx_div (the mixture of target row r when approx_div = S).  */
 int amss_wave_stats_rows(const float* target, const float* approx, int R, int64_t L, int approx_div,
                          float* stats, void* stream);
