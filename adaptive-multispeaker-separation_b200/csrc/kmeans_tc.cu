@@ -38,7 +38,6 @@ using namespace tc;
 
 constexpr int KT_THREADS = 448;
 constexpr int KT_NRAW = 4;                       // raw fp32 tiles in flight (one TMA bulk copy each, dense 160-byte rows)
-constexpr int KT_LOADERS = 256;
 constexpr int KT_E = 40;
 constexpr int KT_NCH = 18;                       // 16-byte units per point: 3 splits x 6 chunks of 8 features (48 >= E + 1)
 constexpr uint32_t KT_RG = 16 * 128;             // phase-2 operand tile: bytes per group of 8 points = 16 feature chunks: hi 0-4,
