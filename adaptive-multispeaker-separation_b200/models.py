@@ -562,6 +562,9 @@ class L41Model(Separator):
 # =================================================================================================
 # KMeans                                                                       models/Kmeans_2.py
 # =================================================================================================
+_IDX_RINGS = {}      # pinned staging rings of the k-means initial rows, keyed by shape (KMeans.fit)
+
+
 class KMeans:
     """KMeans(nb_clusters, centroids_init, nb_tries, nb_iterations, input_tensor, normalize_input,
     latent_space_tensor, beta, threshold, assign_at_end) -- same argument names as the reference
@@ -605,12 +608,14 @@ class KMeans:
             # pinned staging + asynchronous copy: a pageable .to(device) blocks the host until the GPU has drained everything
             # queued before it (the whole trunk of this step), which serialises a streaming loop
             host = torch.as_tensor(np.asarray(init_idx), dtype=torch.int32).contiguous()
-            ring = getattr(self, "_idx_ring", None)
-            if ring is None or ring[0][0].shape != host.shape:
-                ring = self._idx_ring = [[torch.empty(host.shape, dtype=torch.int32).pin_memory(), None] for _ in range(4)]
-                self._idx_k = 0
-            buf = ring[self._idx_k]
-            self._idx_k = (self._idx_k + 1) % len(ring)
+            # (the ring is shared by every KMeans of the process: Separator.separate builds a new object per call, and pinning
+            # costs ~0.1 ms per buffer)
+            ring = _IDX_RINGS.get(tuple(host.shape))
+            if ring is None:
+                ring = _IDX_RINGS[tuple(host.shape)] = {"bufs": [[torch.empty(host.shape, dtype=torch.int32).pin_memory(), None]
+                                                                 for _ in range(4)], "k": 0}
+            buf = ring["bufs"][ring["k"]]
+            ring["k"] = (ring["k"] + 1) % len(ring["bufs"])
             if buf[1] is not None:
                 buf[1].synchronize()                     # the copy that last used this staging buffer has run
             buf[0].copy_(host)
