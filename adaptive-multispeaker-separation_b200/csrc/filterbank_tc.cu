@@ -240,9 +240,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) analysis_tc_kernel(FtParams p) 
 // data pipeline builds every mixture as the fp32 sum of its sources (data/dataset.py:462-468).  The convolution is
 // linear, so when x_mix == x_0 + x_1 holds bit for bit (checked on the device for every batch, mix_is_sum_kernel) the
 // mixture's pre-pool response is the sum of the two source responses: only the SOURCE rows are multiplied and the
-// epilogue pools a, b and a + b.  One tile = 128 time positions of BOTH sources (two N = 128 MMAs per K step into the
-// two halves of one 256-column accumulator), so the pipeline, the filter ring and the TMEM double buffering are the
-// ones of analysis_tc_kernel; a third of the tensor work of the batch disappears.  If the check fails the kernel exits
+// epilogue pools a, b and a + b.  One tile = 128 time positions of BOTH sources: ONE N = 256 MMA per K step over the two
+// sources' Hankel blocks interleaved in shared memory (accumulator column 16 jb + 8 s + r = source s, time 8 jb + r), so the
+// pipeline, the filter ring and the TMEM double buffering are the ones of analysis_tc_kernel; a third of the tensor work of
+// the batch disappears.  (Two N = 128 MMAs per K step, one per source, read the filter operand twice: 16 KB per 128 clk = the
+// whole shared-memory pipe; 4.95 -> 4.52 ms for 128 mixtures with the single MMA.)  If the check fails the kernel exits
 // at once and analysis_tc_kernel (gated the other way) runs the stock three-signal path.
 // =================================================================================================
 constexpr int FP_NT = 128;            // time positions per tile and per source
@@ -322,8 +324,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) analysis_pair_tc_kernel(FtParam
                     }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer: converged loop, elected lane (two N = 128 MMAs per K step) ----------------
-        const uint32_t idesc = idesc_bf16(128, FP_NT, 0, 0);
+        // ---------------- MMA issuer: converged loop, elected lane ----------------
+        // ONE N = 256 MMA per K step covers both sources: their Hankel blocks are INTERLEAVED in G (source s, block m at
+        // 256 m + 128 s), so the operand's N index n/8 = 2 j + s walks 128-byte units (SBO = 128) and a k-block is 256 bytes
+        // further (LBO = 256).  Two N = 128 MMAs read the 4 KB filter operand twice per K step: 16 KB per 128 clk is the whole
+        // shared-memory pipe (ncu: tensor-core wavefronts 79.5 % + LSU 13 %, profiles/r02q_ncu_full_analysis_pair_B128.csv);
+        // this form reads 12 KB.
+        const uint32_t idesc = idesc_bf16(128, FT_NT, 0, 0);
         const bool leader = elect_one();
         uint32_t ga = 0, it = 0;
         for (int64_t u = rank; u < units; u += nranks)
@@ -342,12 +349,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) analysis_pair_tc_kernel(FtParam
 #pragma unroll
                     for (int kk = 0; kk < FT_KS / 16; ++kk) {
                         const uint64_t ad = smem_desc(aaddr + kk * 4096, 2048, 128);
-                        const uint64_t b0 = smem_desc(gaddr + (j * 8 + kk * 2) * 128, 128, 128);
-                        const uint64_t b1 = smem_desc(gaddr + g1 + (j * 8 + kk * 2) * 128, 128, 128);
-                        if (leader) {
-                            mma_bf16(dcol, ad, b0, idesc, (j | kk) != 0);
-                            mma_bf16(dcol + FP_NT, ad, b1, idesc, (j | kk) != 0);
-                        }
+                        const uint64_t bd = smem_desc(gaddr + (j * 8 + kk * 2) * 256, 256, 128);
+                        if (leader) mma_bf16(dcol, ad, bd, idesc, (j | kk) != 0);
                     }
                     if (leader) mma_commit(a_empty + 8 * slot);
                 }
@@ -369,24 +372,29 @@ __global__ void __launch_bounds__(FT_THREADS, 1) analysis_pair_tc_kernel(FtParam
                 const int t0 = (tp * tpu + tt) * FP_NT;
                 mbar_wait(t_full + 8 * buf, ph);
                 tc_fence_after();
+                // accumulator columns: 16 jb + 8 s + r = source s at time t0 + 8 jb + r (time ascending within the scan)
 #pragma unroll 1
-                for (int c0 = 0; c0 < FP_NT; c0 += 32) {
+                for (int c0 = 0; c0 < FT_NT; c0 += 64) {
                     uint32_t v0[32], v1[32];
                     tmem_ld32(lane_base + buf * FT_NT + c0, v0);
-                    tmem_ld32(lane_base + buf * FT_NT + FP_NT + c0, v1);
+                    tmem_ld32(lane_base + buf * FT_NT + c0 + 32, v1);
                     tmem_ld_wait();
-                    if (c0 + 32 == FP_NT) {   // accumulator drained: hand the buffer back
+                    if (c0 + 64 == FT_NT) {   // accumulator drained: hand the buffer back
                         tc_fence_before();
                         mbar_arrive(t_empty + 8 * buf);
                     }
-                    const int tb = t0 + c0;
+                    const int tb = t0 + c0 / 2;
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const float a = __uint_as_float(v0[jj]), c = __uint_as_float(v1[jj]), m = a + c;
-                        if (a > best[1]) { best[1] = a; bestt[1] = tb + jj; }
-                        if (c > best[2]) { best[2] = c; bestt[2] = tb + jj; }
-                        if (m > best[0]) { best[0] = m; bestt[0] = tb + jj; }
-                    }
+                    for (int hb = 0; hb < 4; ++hb)
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const uint32_t* v = hb < 2 ? v0 : v1;
+                            const float a = __uint_as_float(v[16 * (hb & 1) + r]), c = __uint_as_float(v[16 * (hb & 1) + 8 + r]), m = a + c;
+                            const int t = tb + 8 * hb + r;
+                            if (a > best[1]) { best[1] = a; bestt[1] = t; }
+                            if (c > best[2]) { best[2] = c; bestt[2] = t; }
+                            if (m > best[0]) { best[0] = m; bestt[0] = t; }
+                        }
                 }
             }
             if (f < p.N) {
@@ -422,13 +430,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) analysis_pair_tc_kernel(FtParam
                 const unsigned short* xsu = reinterpret_cast<const unsigned short*>(xs);
 #pragma unroll
                 for (int src = 0; src < 2; ++src) {
-                    uint8_t* g = g_buf + buf * g_bytes + src * g1;
+                    uint8_t* g = g_buf + buf * g_bytes + src * 128;          // interleaved: block m of source s at 256 m + 128 s
                     for (int i = bt; i < nunits; i += 128) {
                         uint32_t w[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             w[e] = (uint32_t)xsu[src * ns + i + 2 * e] | ((uint32_t)xsu[src * ns + i + 2 * e + 1] << 16);
-                        *reinterpret_cast<uint4*>(g + (size_t)i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(g + (size_t)(i >> 3) * 256 + (i & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
                 fence_async_smem();
