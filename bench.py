@@ -646,8 +646,8 @@ def run_gpu(args):
                       executed_over_algorithmic_flops=ex,
                       note="achieved follows SURVEY 8(d) (2*L*W*N per signal, S+1 signals per mixture); the kernel executes "
                            "S of the S+1 convolutions, so frac_executed is the hardware utilisation; compute-bound "
-                           "(ncu at 128 mixtures: tensor pipe active 79.5 % of the cycles, SM throughput 88.7 %, DRAM 66 MB read + 237 MB "
-                           "written of the 66 + 295 MB algorithmic: profiles/r02q_ncu_full_analysis_pair_B128.csv), DRAM traffic not a limiter")
+                           "(ncu at 128 mixtures: tensor pipe active 95.9 % of the cycles, DRAM 66 MB read + 237 MB written of the "
+                           "66 + 295 MB algorithmic: profiles/r02r_ncu_full_analysis_pair_B128.csv), DRAM traffic not a limiter")
         if "achieved_tfma" in dom:
             rl.update(limiter=dom["limiter"], achieved_tfma=dom["achieved_tfma"], smem_roof_tfma=dom["smem_roof_tfma"],
                       frac_of_smem_roof=dom["frac_of_smem_roof"],
